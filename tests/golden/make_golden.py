@@ -1,0 +1,239 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (tatva v0.11.1).
+
+Run in the build container only (it needs /root/reference, which the GPU box lacks):
+
+    python tests/golden/make_golden.py
+
+JAX cannot be installed here, so the reference modules are executed eagerly on the NumPy
+stand-in under tests/golden/_jaxshim (vmap / lax.map -> loops, jnp -> numpy).  Every array
+written below is the output of reference code: tatva.element.*, tatva.Operator.{grad, eval,
+integrate, integrate_per_element, get_integration_weights}, tatva.sparse.pattern_from_mesh,
+tatva/sparse/_coloring.py:distance2_colors, tatva.mesh.extract_local_mesh, and (with an
+in-process thread-based stand-in for mpi4py, see _fakempi.py) tatva.mpi._create_dof_layout /
+ExchangePlan routing tables.
+
+Derivative fixtures: the reference has no residual/HVP code (they are jax.grad / jax.jvp of a
+user energy).  We differentiate the reference's *own* energy E(u) = op.integrate(psi(op.grad(u)))
+with the complex-step method (exact to rounding for analytic E):
+    r_i = Im E(u + i h e_i) / h,                   h = 1e-30
+    (Hv)_i = Im[ r-free mixed form ] -> see hvp_complex_fd below (complex step x central FD).
+The energy densities are written as in tests/test_sparse.py:20-38 and
+tests/test_sparse_tracer.py:103-115.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("TATVA_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "_jaxshim"))
+sys.path.insert(0, REF)
+
+import numpy as np  # noqa: E402
+
+import jax.numpy as jnp  # noqa: E402  (the shim)
+from jax_autovmap import autovmap  # noqa: E402
+from tatva import Mesh, Operator, element, sparse  # noqa: E402
+from tatva.mesh import extract_local_mesh  # noqa: E402
+from tatva_coloring import distance2_colors  # noqa: E402
+
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import tatva_oracle as orc  # noqa: E402  (mesh generators only: inputs, not outputs)
+
+KINDS = {"tri3": element.Tri3, "tet4": element.Tetrahedron4, "hex8": element.Hexahedron8}
+
+
+# -- user energies exactly as the reference tests write them -----------------------------
+@autovmap(grad_u=2, mu=0, lmbda=0)
+def strain_energy(grad_u, mu, lmbda):  # tests/test_sparse.py:20-38
+    eps = 0.5 * (grad_u + grad_u.T)
+    sig = 2 * mu * eps + lmbda * jnp.trace(eps) * jnp.eye(grad_u.shape[0])
+    return 0.5 * jnp.einsum("ij,ij->", sig, eps)
+
+
+@autovmap(grad_u=2, mu=0, lmbda=0)
+def neo_hookean_density(grad_u, mu, lmbda):  # tests/test_sparse_tracer.py:103-115
+    F = jnp.eye(3) + grad_u
+    J = jnp.linalg.det(F)
+    C = F.T @ F
+    I1 = jnp.trace(C)
+    return (mu / 2) * (I1 - 3 - 2 * jnp.log(J)) + (lmbda / 2) * (jnp.log(J)) ** 2
+
+
+def jitter(coords, h, seed=0):
+    rng = np.random.default_rng(seed)
+    return coords + 0.1 * h * rng.uniform(-1, 1, coords.shape)
+
+
+def smooth_u(coords):
+    x = coords
+    if x.shape[1] == 2:
+        return 0.05 * np.stack([np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1]), np.sin(2 * np.pi * x[:, 1]) * np.cos(2 * np.pi * x[:, 0])], -1)
+    return 0.05 * np.stack(
+        [
+            np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1]),
+            np.sin(2 * np.pi * x[:, 1]) * np.cos(2 * np.pi * x[:, 2]),
+            np.sin(2 * np.pi * x[:, 2]) * np.cos(2 * np.pi * x[:, 0]),
+        ],
+        -1,
+    )
+
+
+def make_case(kind):
+    if kind == "tri3":
+        c, el = orc.mesh_unit_square_tri(4, 3)
+        c = jitter(c, 0.25)
+        mat = ("linear_elastic",) + orc.lame_from_youngs_poisson_2d(1.0, 0.3)
+        psi = strain_energy
+    elif kind == "tet4":
+        c, el = orc.mesh_box_tet((1.0, 1.0, 1.0), (2, 2, 2))
+        c = jitter(c, 0.5)
+        mat = ("neo_hookean", 500.0, 1000.0)
+        psi = neo_hookean_density
+    else:
+        c, el = orc.mesh_box_hex(3)
+        c = jitter(c, 1.0 / 3)
+        mat = ("neo_hookean", 500.0, 1000.0)
+        psi = neo_hookean_density
+    return c, el, mat, psi
+
+
+def element_fixtures(out):
+    """tatva.element.* on one distorted element per kind."""
+    rng = np.random.default_rng(7)
+    for kind, cls in KINDS.items():
+        el = cls()
+        X = np.asarray(el._reference_nodes(), dtype=float)
+        X = X + 0.15 * rng.uniform(-1, 1, X.shape)
+        dim = X.shape[1]
+        uv = rng.normal(size=(X.shape[0], dim))
+        us = rng.normal(size=(X.shape[0],))
+        qp = np.asarray(el.quad_points, dtype=float)
+        out[f"el_{kind}_X"] = X
+        out[f"el_{kind}_uv"] = uv
+        out[f"el_{kind}_us"] = us
+        out[f"el_{kind}_qp"] = qp
+        out[f"el_{kind}_qw"] = np.asarray(el.quad_weights, dtype=float)
+        out[f"el_{kind}_N"] = np.stack([el.shape_function(x) for x in qp])
+        out[f"el_{kind}_dNdr"] = np.stack([el.shape_function_derivative(x) for x in qp])
+        out[f"el_{kind}_J"] = np.stack([el.get_jacobian(x, X)[0] for x in qp])
+        out[f"el_{kind}_detJ"] = np.stack([el.get_jacobian(x, X)[1] for x in qp])
+        out[f"el_{kind}_grad_v"] = np.stack([el.gradient(x, uv, X) for x in qp])
+        out[f"el_{kind}_grad_s"] = np.stack([el.gradient(x, us, X) for x in qp])
+        out[f"el_{kind}_interp_v"] = np.stack([el.interpolate(x, uv, X) for x in qp])
+
+
+def operator_fixtures(out):
+    rng = np.random.default_rng(11)
+    for kind, cls in KINDS.items():
+        c, el, mat, psi = make_case(kind)
+        op = Operator(Mesh(coords=c, elements=el), cls())
+        dim = c.shape[1]
+        u = smooth_u(c) + 0.01 * rng.normal(size=c.shape)
+        s = rng.normal(size=(c.shape[0],))
+        v = rng.normal(size=c.shape)
+        p = f"op_{kind}_"
+        out[p + "coords"], out[p + "conn"] = c, el
+        out[p + "u"], out[p + "s"], out[p + "v"] = u, s, v
+        out[p + "mat"] = np.array(mat[1:])
+        out[p + "grad_u"] = op.grad(u)
+        out[p + "grad_s"] = op.grad(s)
+        out[p + "eval_u"] = op.eval(u)
+        out[p + "eval_s"] = op.eval(s)
+        out[p + "weights"] = op.get_integration_weights()
+        out[p + "int_nodal_s"] = op.integrate(s)
+        out[p + "int_nodal_u_per_el"] = op.integrate_per_element(u)
+        q = rng.normal(size=(el.shape[0], len(op.element.quad_points), 2))
+        out[p + "quadvals"] = q
+        out[p + "int_quad_per_el"] = op.integrate_per_element(q)
+        # op.integrate(<python scalar>) relies on XLA clamping the out-of-bounds gather
+        # jnp.array([arg])[elements] (operator.py:335); NumPy raises instead, so that branch
+        # is not recorded here (the oracle restates it as arg * sum(W)).
+
+        def E(uu):
+            return op.integrate(psi(op.grad(uu), mat[1], mat[2]))
+
+        out[p + "energy"] = E(u)
+        # residual by complex step on the reference's own energy
+        h = 1e-30
+        r = np.zeros(u.shape)
+        for n in range(u.shape[0]):
+            for i in range(dim):
+                uc = u.astype(complex)
+                uc[n, i] += 1j * h
+                r[n, i] = np.imag(E(uc)) / h
+        out[p + "residual_cs"] = r
+        # w . H v  for a few probe directions w:  complex step (w) x 4th-order central FD (v)
+        ws = rng.normal(size=(3,) + u.shape)
+        hv = np.zeros(3)
+        d = 1e-4
+
+        def dE(uu, w):
+            return np.imag(E(uu.astype(complex) + 1j * h * w)) / h
+
+        for k in range(3):
+            hv[k] = (-dE(u + 2 * d * v, ws[k]) + 8 * dE(u + d * v, ws[k]) - 8 * dE(u - d * v, ws[k]) + dE(u - 2 * d * v, ws[k])) / (12 * d)
+        out[p + "hvp_probe_w"] = ws
+        out[p + "hvp_probe_wHv"] = hv
+
+
+def sparse_fixtures(out):
+    cases = {
+        "tri3_8x8_d2": (orc.mesh_unit_square_tri(8, 8), 2),  # tests/test_sparse.py:40-45
+        "tet4_3_d3": (orc.mesh_box_tet((1, 1, 1), (3, 3, 3)), 3),
+        "tet4_2_d4": (orc.mesh_box_tet((1, 1, 1), (2, 2, 2)), 4),
+        "hex8_3_d3": (orc.mesh_box_hex(3), 3),
+    }
+    for name, ((c, el), dpn) in cases.items():
+        pat = sparse.pattern_from_mesh(Mesh(coords=c, elements=el), dpn)
+        colors = np.asarray(distance2_colors(pat.indptr, pat.indices, pat.shape[0]))
+        out[f"sp_{name}_conn"] = el
+        out[f"sp_{name}_nnodes"] = np.array(c.shape[0])
+        out[f"sp_{name}_indptr"] = pat.indptr
+        out[f"sp_{name}_indices"] = pat.indices
+        out[f"sp_{name}_colors"] = colors
+        assert pat.indptr.dtype == np.int32 and pat.indices.dtype == np.int32
+
+
+def partition_fixtures(out):
+    c, el = orc.mesh_box_hex((4, 2, 2))
+    cx = c[el].mean(axis=1)[:, 0]
+    part = (cx > cx.mean()).astype(np.int32)
+    out["part_hex_coords"], out["part_hex_conn"], out["part_hex_partition"] = c, el, part
+    for r in range(2):
+        m, info = extract_local_mesh(Mesh(coords=c, elements=el), part, r)
+        out[f"part_hex_r{r}_coords"] = np.asarray(m.coords)
+        out[f"part_hex_r{r}_conn"] = np.asarray(m.elements)
+        out[f"part_hex_r{r}_l2g"] = np.asarray(info.nodes_local_to_global)
+        out[f"part_hex_r{r}_nowned"] = np.array(info.n_owned_nodes)
+    c, el = orc.mesh_unit_square_tri(4, 4)
+    cen = c[el].mean(axis=1)
+    part = ((cen[:, 0] > 0.5).astype(np.int32) + 2 * (cen[:, 1] > 0.5).astype(np.int32)).astype(np.int32)
+    out["part_tri_coords"], out["part_tri_conn"], out["part_tri_partition"] = c, el, part
+    for r in range(4):
+        m, info = extract_local_mesh(Mesh(coords=c, elements=el), part, r)
+        out[f"part_tri_r{r}_conn"] = np.asarray(m.elements)
+        out[f"part_tri_r{r}_l2g"] = np.asarray(info.nodes_local_to_global)
+        out[f"part_tri_r{r}_nowned"] = np.array(info.n_owned_nodes)
+
+
+def main():
+    out: dict[str, np.ndarray] = {}
+    element_fixtures(out)
+    operator_fixtures(out)
+    sparse_fixtures(out)
+    partition_fixtures(out)
+    try:
+        from _fakempi_golden import mpi_fixtures  # type: ignore
+
+        mpi_fixtures(out)
+    except ImportError:
+        pass
+    path = os.path.join(HERE, "reference_golden.npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""Pin the CPU oracle (oracle/tatva_oracle.py) to the reference.
+
+Fixtures in tests/golden/reference_golden.npz are outputs of the unmodified reference code
+(tests/golden/make_golden.py); the known-answer values are those of the reference's own tests.
+"""
+import numpy as np
+import pytest
+
+from oracle import tatva_oracle as orc
+
+KINDS = ["tri3", "tet4", "hex8"]
+MATS = {"tri3": orc.LinearElastic, "tet4": orc.NeoHookean, "hex8": orc.NeoHookean}
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_element_math_matches_reference(golden, kind):
+    g = lambda k: golden[f"el_{kind}_{k}"]  # noqa: E731
+    qp, qw = orc.quad_rule(kind)
+    np.testing.assert_array_equal(qp, g("qp"))
+    np.testing.assert_array_equal(qw, g("qw"))
+    X, uv, us = g("X"), g("uv"), g("us")
+    for q, xi in enumerate(qp):
+        np.testing.assert_allclose(orc.shape_function(kind, xi), g("N")[q], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(orc.shape_function_derivative(kind, xi), g("dNdr")[q], rtol=0, atol=1e-15)
+        J, detJ = orc.get_jacobian(kind, xi, X)
+        np.testing.assert_allclose(J, g("J")[q], rtol=1e-15, atol=1e-15)
+        np.testing.assert_allclose(detJ, g("detJ")[q], rtol=1e-14)
+        np.testing.assert_allclose(orc.element_gradient(kind, xi, uv, X), g("grad_v")[q], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(orc.element_gradient(kind, xi, us, X), g("grad_s")[q], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(orc.element_interpolate(kind, xi, uv, X), g("interp_v")[q], rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_linear_fields_have_exact_gradients(kind):
+    """reference tests/test_element.py:45-149 (scalar, vector, tensor; atol 1e-12)."""
+    rng = np.random.default_rng(0)
+    X = orc.reference_nodes(kind)
+    dim = X.shape[1]
+    a = np.array([2.0, 3.0, 4.0][:dim])
+    A = rng.normal(size=(dim, dim))
+    B = rng.normal(size=(2, 2, dim))
+    for xi in orc.quad_rule(kind)[0]:
+        np.testing.assert_allclose(orc.element_gradient(kind, xi, X @ a, X), a, atol=1e-12)
+        np.testing.assert_allclose(orc.element_gradient(kind, xi, np.einsum("ij,kj->ki", A, X), X), A, atol=1e-12)
+        np.testing.assert_allclose(orc.element_gradient(kind, xi, np.einsum("ijk,nk->nij", B, X), X), B, atol=1e-12)
+
+
+def test_operator_known_answers():
+    """reference tests/test_operator.py:14-30, :113-143."""
+    nodes = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    el = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    np.testing.assert_allclose(orc.op_eval("tri3", nodes, el, np.array([0.0, 1.0, 2.0, 3.0])), [[1.0], [5.0 / 3.0]])
+    np.testing.assert_allclose(orc.op_grad("tri3", nodes, el, nodes @ np.array([2.0, 3.0])), [[[2.0, 3.0]], [[2.0, 3.0]]])
+    np.testing.assert_allclose(orc.op_integrate_per_element("tri3", nodes, el, np.ones(4)), [0.5, 0.5])
+    np.testing.assert_allclose(orc.op_integrate("tri3", nodes, el, np.ones(4)), 1.0)
+    np.testing.assert_allclose(orc.op_integrate_per_element("tri3", nodes, el, np.full((2, 1), 4.0)), [2.0, 2.0])
+    np.testing.assert_allclose(orc.op_integrate("tri3", nodes, el, 3.0), 3.0)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_operator_matches_reference(golden, kind):
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    c, el, u, s = g("coords"), g("conn"), g("u"), g("s")
+    kw = dict(rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(orc.op_grad(kind, c, el, u), g("grad_u"), **kw)
+    np.testing.assert_allclose(orc.op_grad(kind, c, el, s), g("grad_s"), **kw)
+    np.testing.assert_allclose(orc.op_eval(kind, c, el, u), g("eval_u"), **kw)
+    np.testing.assert_allclose(orc.op_eval(kind, c, el, s), g("eval_s"), **kw)
+    np.testing.assert_allclose(orc.op_integration_weights(kind, c, el), g("weights"), **kw)
+    np.testing.assert_allclose(orc.op_integrate(kind, c, el, s), g("int_nodal_s"), **kw)
+    np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, u), g("int_nodal_u_per_el"), **kw)
+    np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, g("quadvals")), g("int_quad_per_el"), **kw)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    c, el, u, v = g("coords"), g("conn"), g("u"), g("v")
+    mat = MATS[kind](*g("mat"))
+    np.testing.assert_allclose(orc.energy(kind, mat, c, el, u), g("energy"), rtol=1e-13)
+    r = orc.residual(kind, mat, c, el, u)
+    np.testing.assert_allclose(r, g("residual_cs"), rtol=1e-11, atol=1e-12 * np.abs(r).max())
+    Hv = orc.hvp(kind, mat, c, el, u, v)
+    wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), Hv)
+    # complex step x 4th-order central difference: ~1e-9 relative
+    np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
+
+
+@pytest.mark.parametrize("name,dpn", [("tri3_8x8_d2", 2), ("tet4_3_d3", 3), ("tet4_2_d4", 4), ("hex8_3_d3", 3)])
+def test_pattern_and_colouring_bit_exact(golden, name, dpn):
+    conn, n_nodes = golden[f"sp_{name}_conn"], int(golden[f"sp_{name}_nnodes"])
+    indptr, indices = orc.pattern_from_mesh(conn, n_nodes, dpn)
+    assert indptr.dtype == np.int32 and indices.dtype == np.int32
+    np.testing.assert_array_equal(indptr, golden[f"sp_{name}_indptr"])
+    np.testing.assert_array_equal(indices, golden[f"sp_{name}_indices"])
+    colors = orc.distance2_colors(indptr, indices, n_nodes * dpn)
+    np.testing.assert_array_equal(colors, golden[f"sp_{name}_colors"])
+
+
+def test_tri3_pattern_nnz_formula():
+    """nnz = 4 (7 n^2 + 6 n + 1) for Tri3 n x n with 2 DOFs per node."""
+    for n in (4, 8):
+        c, el = orc.mesh_unit_square_tri(n, n)
+        indptr, _ = orc.pattern_from_mesh(el, len(c), 2)
+        assert indptr[-1] == 4 * (7 * n * n + 6 * n + 1)
+
+
+def test_coloured_jacobian_equals_dense_hessian():
+    """reference tests/test_sparse.py:48-80: Tri3 8x8, mu=1, lambda=0, at u=0."""
+    c, el = orc.mesh_unit_square_tri(8, 8)
+    mat = orc.LinearElastic(1.0, 0.0)
+    n = 2 * len(c)
+    u0 = np.zeros((len(c), 2))
+    indptr, indices = orc.pattern_from_mesh(el, len(c), 2)
+    colors = orc.distance2_colors(indptr, indices, n)
+    jvp = lambda seed: orc.hvp("tri3", mat, c, el, u0, seed.reshape(-1, 2)).ravel()  # noqa: E731
+    data = orc.colored_jacobian_data(jvp, n, indptr, indices, colors)
+    K = np.stack([jvp(e) for e in np.eye(n)], axis=1)
+    import scipy.sparse as sps
+
+    Ks = sps.csr_matrix((data, indices, indptr), shape=(n, n)).toarray()
+    np.testing.assert_allclose(Ks, K, rtol=1e-12, atol=1e-14)
+    direct = orc.assemble_csr_data("tri3", mat, c, el, u0, indptr, indices)
+    np.testing.assert_allclose(direct, data, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(orc.residual("tri3", mat, c, el, u0), 0.0)
+
+
+@pytest.mark.parametrize("case,nparts", [("hex", 2), ("tri", 4)])
+def test_extract_local_mesh_matches_reference(golden, case, nparts):
+    c, el, part = golden[f"part_{case}_coords"], golden[f"part_{case}_conn"], golden[f"part_{case}_partition"]
+    for r in range(nparts):
+        cl, el_l, l2g, n_owned = orc.extract_local_mesh(c, el, part, r)
+        np.testing.assert_array_equal(el_l, golden[f"part_{case}_r{r}_conn"])
+        np.testing.assert_array_equal(l2g, golden[f"part_{case}_r{r}_l2g"])
+        assert n_owned == int(golden[f"part_{case}_r{r}_nowned"])
+        np.testing.assert_array_equal(cl, c[l2g])
+
+
+def test_dof_range_block_distribution():
+    """reference tests/test_allreduce_plan.py:31-40: 6 DOFs on 2 ranks -> [0,3), [3,6); mpi.py:714-726."""
+    assert orc.dof_range(6, 2, 0) == (0, 3) and orc.dof_range(6, 2, 1) == (3, 6)
+    assert orc.dof_range(5, 2, 0) == (0, 3) and orc.dof_range(5, 2, 1) == (3, 5)
+    assert [orc.dof_range(7, 3, r) for r in range(3)] == [(0, 3), (3, 5), (5, 7)]
+
+
+def test_exchange_plan_known_answers():
+    """reference tests/test_exchange_plan.py:97-166: 2 ranks, 2 nodes, 1 DOF per node."""
+    nat = [np.array([0, 1], dtype=np.int32), np.array([1, 0], dtype=np.int32)]
+    own = [np.array([True, False]), np.array([True, False])]
+    layouts = orc.create_dof_layouts(nat, own, 2)
+    np.testing.assert_array_equal(layouts[0]["local_to_global"], [0, 1])
+    np.testing.assert_array_equal(layouts[1]["local_to_global"], [1, 0])
+    plans = orc.exchange_routing(layouts)
+    x = [np.array([10.0]), np.array([20.0])]
+    ul = orc.scatter_fwd_set(plans, layouts, x)
+    np.testing.assert_allclose(ul[0], [10.0, 20.0])
+    np.testing.assert_allclose(ul[1], [20.0, 10.0])
+    owned = orc.scatter_rev_add(plans, layouts, [2 * a for a in ul])
+    np.testing.assert_allclose(owned[0], [40.0])
+    np.testing.assert_allclose(owned[1], [80.0])
+
+
+def test_exchange_plan_layout_two_dofs_per_node():
+    """Nodal part of reference tests/test_exchange_plan.py:27-94 (u: 2 nodes x 2 DOFs):
+    rank-contiguous owned blocks, ghosts resolved through the natural directory."""
+    nat = [orc.dof_map_from_node_map([0, 1], 2), orc.dof_map_from_node_map([1, 0], 2)]
+    own = [np.array([True, True, False, False])] * 2
+    layouts = orc.create_dof_layouts(nat, own, 4)
+    np.testing.assert_array_equal(layouts[0]["local_to_global"], [0, 1, 2, 3])
+    np.testing.assert_array_equal(layouts[1]["local_to_global"], [2, 3, 0, 1])
+    assert layouts[1]["offset"] == 2 and layouts[0]["n_global"] == 4
