@@ -1,0 +1,163 @@
+/*
+ * tatva_b200 — C ABI of the B200-native element-level hot path of tatva.
+ *
+ * This header is the drop-in boundary: every entry point is `extern "C"`, takes plain
+ * pointers and sizes, enqueues work on the caller's CUDA stream and returns an int
+ * (0 = ok, >0 = cudaError_t, <0 = TATVA_E_*).  Hot calls do not allocate, do not
+ * synchronise and do not throw.  Device buffers are caller-owned, FP64 row-major,
+ * connectivity int32 (reference: tatva/mesh.py:205), CSR indptr/indices int32.
+ * Output buffers need not be zero-initialised (XLA does not zero FFI results): calls that
+ * scatter-add zero their output on-stream first.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the tatva
+ * v0.11.1 tree).  INTEGRATION.md shows the XLA-FFI / ctypes stubs that bind these symbols.
+ */
+#ifndef TATVA_B200_H
+#define TATVA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TATVA_B200_ABI_VERSION 1
+
+typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
+typedef void* tatva_stream_t;           /* a cudaStream_t */
+
+/* element kinds — tatva/element/base.py:245-265 (Tri3), :448-472 (Tetrahedron4), :475-568 (Hexahedron8) */
+enum { TATVA_TRI3 = 0, TATVA_TET4 = 1, TATVA_HEX8 = 2 };
+
+/* energy densities the configs name (user code in the reference, pinned by its tests):
+ *   LINEAR_ELASTIC          psi = 1/2 sigma:eps           params {mu, lambda}          tests/test_sparse.py:20-38
+ *   NEO_HOOKEAN             psi = mu/2 (I1-3-2lnJ) + lambda/2 (lnJ)^2   params {mu, lambda}   tests/test_sparse_tracer.py:103-115
+ *   NEO_HOOKEAN_PHASE_FIELD ((1-phi)^2+k) psi_NH + Gc (phi^2/(2l) + l/2 |grad phi|^2),   params {mu, lambda, Gc, l, k}
+ *                           nodal state interleaved [ux,uy,uz,phi] (tatva/compound/__init__.py:334-389)   */
+enum { TATVA_LINEAR_ELASTIC = 0, TATVA_NEO_HOOKEAN = 1, TATVA_NEO_HOOKEAN_PHASE_FIELD = 2 };
+
+/* error codes (negative); positive return values are cudaError_t */
+enum {
+  TATVA_OK = 0,
+  TATVA_E_INVALID = -1,     /* bad argument (null pointer, unknown kind, size <= 0) */
+  TATVA_E_UNSUPPORTED = -2, /* element/material combination has no kernel */
+  TATVA_E_NOMEM = -3,
+  TATVA_E_NODEVICE = -4
+};
+
+/* plan flags */
+enum {
+  TATVA_PLAN_CACHE_WEIGHTS = 1 /* Operator(cache_weights=True), tatva/operator.py:119-130 */
+};
+
+/* kernel variant selector for tatva_hvp on (HEX8, NEO_HOOKEAN): 0 = tuned default */
+enum { TATVA_VARIANT_DEFAULT = 0, TATVA_VARIANT_GENERIC = 1, TATVA_VARIANT_MODAL = 2 };
+
+const char* tatva_error_string(int code);
+int tatva_abi_version(void);
+int tatva_device_count(int* count);
+
+/* ---- plan lifetime ---------------------------------------------------------------------
+ * Replaces Operator.__post_init__ (tatva/operator.py:112-130).  `d_coords` (n_nodes, dim)
+ * f64 and `d_conn` (n_elems, npe) int32 are device pointers that must outlive the plan
+ * (the plan keeps views, not copies).  Allocates the plan's scratch (energy partials,
+ * cached weights when TATVA_PLAN_CACHE_WEIGHTS).                                           */
+int tatva_plan_create(tatva_plan_t** plan, int element, int64_t n_nodes, int64_t n_elems,
+                      const double* d_coords, const int32_t* d_conn, int flags,
+                      tatva_stream_t stream);
+int tatva_plan_destroy(tatva_plan_t* plan);
+int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, int* nq,
+                    int64_t* n_nodes, int64_t* n_elems);
+int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
+
+/* ---- quadrature-loop building blocks (generic path; any user energy on top) ------------ */
+
+/* Operator.grad -> Element.gradient  (tatva/operator.py:379-397, tatva/element/base.py:99-115)
+ * u (n_nodes, n_val) -> out (n_elems, nq, n_val, dim), out[e,q,i,j] = d u_i / d x_j.       */
+int tatva_op_grad(const tatva_plan_t* plan, const double* d_u, int n_val, double* d_out,
+                  tatva_stream_t stream);
+/* adjoint of the above = what jax.grad makes of the gather at operator.py:221:
+ * g (n_elems, nq, n_val, dim) -> y (n_nodes, n_val), y[n,i] = sum_{e,q,j} g[e,q,i,j] dNdX[e,q,j,n] */
+int tatva_op_grad_adjoint(const tatva_plan_t* plan, const double* d_g, int n_val, double* d_y,
+                          tatva_stream_t stream);
+/* Operator.eval -> Element.interpolate (tatva/operator.py:358-377, element/base.py:95-97)
+ * u (n_nodes, n_val) -> out (n_elems, nq, n_val)                                           */
+int tatva_op_eval(const tatva_plan_t* plan, const double* d_u, int n_val, double* d_out,
+                  tatva_stream_t stream);
+int tatva_op_eval_adjoint(const tatva_plan_t* plan, const double* d_g, int n_val, double* d_y,
+                          tatva_stream_t stream);
+/* Operator.get_integration_weights (tatva/operator.py:172-192): out (n_elems, nq) = det(J) w_q (no abs) */
+int tatva_op_integration_weights(const tatva_plan_t* plan, double* d_out, tatva_stream_t stream);
+/* Operator._integrate_quad_array (tatva/operator.py:342-356):
+ * vals (n_elems, nq, n_val) -> out (n_elems, n_val) = einsum("eq...,eq->e...", vals, W)    */
+int tatva_op_integrate_quad(const tatva_plan_t* plan, const double* d_vals, int n_val,
+                            double* d_out, tatva_stream_t stream);
+/* the gather `v[self.mesh.elements]` of Operator.map / map_over_elements
+ * (tatva/operator.py:254-257, :296-299): u (n_nodes, n_val) -> out (n_elems, npe, n_val)    */
+int tatva_op_gather(const tatva_plan_t* plan, const double* d_u, int n_val, double* d_out,
+                    tatva_stream_t stream);
+/* its transpose (scatter-add): g (n_elems, npe, n_val) -> y (n_nodes, n_val)                */
+int tatva_op_gather_adjoint(const tatva_plan_t* plan, const double* d_g, int n_val, double* d_y,
+                            tatva_stream_t stream);
+/* sum over axis 0 of (n_rows, n_val) -> (n_val): the `jnp.sum(res, axis=0)` of Operator.integrate
+ * (tatva/operator.py:319); deterministic two-pass tree, uses plan scratch                   */
+int tatva_op_sum_rows(tatva_plan_t* plan, const double* d_in, int64_t n_rows, int n_val,
+                      double* d_out, tatva_stream_t stream);
+
+/* ---- fused energy / residual / HVP ------------------------------------------------------
+ * E(u) = op.integrate(psi(op.grad(u)))           (README.md:93; tests/test_sparse.py:50-55)
+ * r    = jax.grad(E)(u)                          (tests/test_sparse.py:79)
+ * Hv   = jax.jvp(jax.grad(E), (u,), (v,))[1]     (tatva/sparse/base.py:264)
+ * u, v, y: (n_nodes, dofs_per_node) with dofs_per_node = dim (4 for the phase-field law).
+ * `params` is a HOST pointer to n_params doubles (copied into the launch).                 */
+int tatva_energy(tatva_plan_t* plan, int material, const double* params, int n_params,
+                 const double* d_u, double* d_energy, tatva_stream_t stream);
+int tatva_residual(tatva_plan_t* plan, int material, const double* params, int n_params,
+                   const double* d_u, double* d_r, tatva_stream_t stream);
+int tatva_hvp(tatva_plan_t* plan, int material, const double* params, int n_params,
+              const double* d_u, const double* d_v, double* d_y, tatva_stream_t stream);
+
+/* ---- coloured sparse Jacobian -> direct assembly into a fixed CSR pattern ---------------
+ * Replaces sparse.jacfwd / colored_jacobian_batch / compute_rows_cols
+ * (tatva/sparse/base.py:139-176, :230-270, :108-136): instead of n_colors HVPs and an
+ * (N, n_colors) temporary, one kernel adds every element stiffness into `d_data` (nnz).
+ * `d_elem_pos` (n_elems, npe, npe) int32: for element e and node pair (a,b), the offset of
+ * column dpn*conn[e,b] inside CSR row dpn*conn[e,a] (same offset in the dpn rows of node a);
+ * built once on the host by tatva_host_csr_element_positions.                              */
+int tatva_csr_assemble(tatva_plan_t* plan, int material, const double* params, int n_params,
+                       const double* d_u, const int32_t* d_indptr, const int32_t* d_elem_pos,
+                       int64_t nnz, double* d_data, tatva_stream_t stream);
+
+/* ---- halo exchange building blocks (tatva/mpi.py:372-409, :479-516) ---------------------
+ * pack:        dst[k]        = src[idx[k]]      (send_buf = x_owned[nbr_send], mpi.py:400)
+ * unpack_set:  dst[idx[k]]   = src[k]           (u_local.at[nbr_recv].set,     mpi.py:406-407)
+ * unpack_add:  dst[idx[k]]  += src[k]           (owned.at[nbr_recv].add,       mpi.py:512-513;
+ *                                                indices may repeat -> atomic)              */
+int tatva_halo_pack(const double* d_src, const int64_t* d_idx, int64_t n, double* d_dst,
+                    tatva_stream_t stream);
+int tatva_halo_unpack_set(const double* d_src, const int64_t* d_idx, int64_t n, double* d_dst,
+                          tatva_stream_t stream);
+int tatva_halo_unpack_add(const double* d_src, const int64_t* d_idx, int64_t n, double* d_dst,
+                          tatva_stream_t stream);
+
+/* ---- host-side setup (C++, no GPU needed) -----------------------------------------------
+ * pattern_from_mesh / _create_sparse_structure (tatva/sparse/_extraction.py:37-102):
+ * two-call protocol: pass indices == NULL to get nnz (indptr is filled), then call again.   */
+int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes,
+                                 int dofs_per_node, int32_t* indptr, int32_t* indices,
+                                 int64_t* nnz);
+/* distance2_colors (tatva-coloring; in-tree spec tatva/sparse/_coloring.py:27-48,:136-153,:270-283):
+ * greedy first-fit in natural order on the pattern of A@A.                                  */
+int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, int64_t n,
+                                int32_t* colors, int32_t* n_colors);
+int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe,
+                                     int dofs_per_node, const int32_t* indptr,
+                                     const int32_t* indices, int32_t* elem_pos);
+
+/* ---- measurement helper: sustained FP64 FMA rate of the device (DFMA microbenchmark) ---- */
+int tatva_fp64_peak_tflops(double* tflops, tatva_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TATVA_B200_H */

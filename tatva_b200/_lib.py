@@ -1,0 +1,88 @@
+"""ctypes binding of libtatva_b200.so (the C ABI declared in include/tatva_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtatva_b200.so")
+
+# enums mirrored from include/tatva_b200.h
+TRI3, TET4, HEX8 = 0, 1, 2
+LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
+PLAN_CACHE_WEIGHTS = 1
+VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol declared in the header
+SIGNATURES = {
+    "tatva_error_string": (C.c_char_p, [C.c_int]),
+    "tatva_abi_version": (C.c_int, []),
+    "tatva_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "tatva_plan_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]),
+    "tatva_plan_destroy": (C.c_int, [vp]),
+    "tatva_plan_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_i64p, c_i64p]),
+    "tatva_plan_set_variant": (C.c_int, [vp, C.c_int]),
+    "tatva_op_grad": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_grad_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_eval": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_eval_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_integration_weights": (C.c_int, [vp, vp, vp]),
+    "tatva_op_integrate_quad": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_gather": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_gather_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_sum_rows": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp]),
+    "tatva_energy": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
+    "tatva_residual": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
+    "tatva_hvp": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp]),
+    "tatva_csr_assemble": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, vp]),
+    "tatva_halo_pack": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "tatva_halo_unpack_set": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "tatva_halo_unpack_add": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "tatva_host_pattern_from_mesh": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, C.c_int, c_i32p, c_i32p, c_i64p]),
+    "tatva_host_distance2_colors": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p]),
+    "tatva_host_csr_element_positions": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p]),
+    "tatva_fp64_peak_tflops": (C.c_int, [c_f64p, vp]),
+}
+
+
+class TatvaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TatvaError(
+                f"{LIB_PATH} not found: build it with `python -m tatva_b200.build` (there is no CPU fallback)"
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().tatva_error_string(code).decode()
+        raise TatvaError(f"{what or 'tatva_b200 call'} failed: {msg} (code {code})")
+
+
+def params_array(values) -> tuple[C.Array, int]:
+    arr = (C.c_double * len(values))(*[float(v) for v in values])
+    return arr, len(values)

@@ -1,0 +1,385 @@
+// Shared device-side definitions: elements, small dense algebra, constitutive laws.
+// All arithmetic is FP64; nothing here touches tensor cores (the per-element contractions
+// are 2x2 / 3x3 / 3x8).  Reference citations are relative to the tatva v0.11.1 tree.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tatva_b200.h"
+
+#define TATVA_HD __host__ __device__ __forceinline__
+#define TATVA_D __device__ __forceinline__
+
+namespace tatva {
+
+constexpr int kBlock = 128;  // threads per CTA for element-per-thread kernels
+
+// ---------------------------------------------------------------------------------------------
+// Elements.  dNdr(q) is dN/dxi at quadrature point q, laid out [dim][npe] exactly like
+// Element.shape_function_derivative (tatva/element/base.py:86-88).
+// ---------------------------------------------------------------------------------------------
+
+struct Tri3 {  // tatva/element/base.py:245-265
+  static constexpr int dim = 2, npe = 3, nq = 1, kind = TATVA_TRI3;
+  TATVA_D static double weight(int) { return 0.5; }
+  TATVA_D static void N(int, double (&n)[npe]) {
+    n[0] = 1.0 - 1.0 / 3 - 1.0 / 3;
+    n[1] = 1.0 / 3;
+    n[2] = 1.0 / 3;
+  }
+  TATVA_D static void dNdr(int, double (&d)[dim][npe]) {
+    d[0][0] = -1.0; d[0][1] = 1.0; d[0][2] = 0.0;
+    d[1][0] = -1.0; d[1][1] = 0.0; d[1][2] = 1.0;
+  }
+};
+
+struct Tet4 {  // tatva/element/base.py:448-472
+  static constexpr int dim = 3, npe = 4, nq = 1, kind = TATVA_TET4;
+  TATVA_D static double weight(int) { return 1.0 / 6; }
+  TATVA_D static void N(int, double (&n)[npe]) {
+    n[0] = 1.0 - 0.25 - 0.25 - 0.25;
+    n[1] = 0.25;
+    n[2] = 0.25;
+    n[3] = 0.25;
+  }
+  TATVA_D static void dNdr(int, double (&d)[dim][npe]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      d[j][0] = -1.0;
+#pragma unroll
+      for (int n = 1; n < 4; ++n) d[j][n] = (n == j + 1) ? 1.0 : 0.0;
+    }
+  }
+};
+
+struct Hex8 {  // tatva/element/base.py:475-568
+  static constexpr int dim = 3, npe = 8, nq = 8, kind = TATVA_HEX8;
+  // sign of reference node n along axis d (bottom face CCW, then top; :478-491); the 2x2x2
+  // Gauss points are a * the same table (:493-513), all weights 1.
+  TATVA_HD static constexpr double sgn(int n, int d) {
+    return d == 0 ? (((n & 3) == 1 || (n & 3) == 2) ? 1.0 : -1.0)
+         : d == 1 ? (((n & 3) >= 2) ? 1.0 : -1.0)
+                  : ((n >= 4) ? 1.0 : -1.0);
+  }
+  TATVA_D static double weight(int) { return 1.0; }
+  TATVA_D static void N(int q, double (&n)[npe]) {
+    const double a = 0.57735026918962576451;  // 1/sqrt(3)
+    const double x = a * sgn(q, 0), y = a * sgn(q, 1), z = a * sgn(q, 2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      n[k] = 0.125 * (1.0 + sgn(k, 0) * x) * (1.0 + sgn(k, 1) * y) * (1.0 + sgn(k, 2) * z);
+  }
+  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+    const double a = 0.57735026918962576451;
+    const double x = a * sgn(q, 0), y = a * sgn(q, 1), z = a * sgn(q, 2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double fx = 1.0 + sgn(k, 0) * x, fy = 1.0 + sgn(k, 1) * y, fz = 1.0 + sgn(k, 2) * z;
+      d[0][k] = 0.125 * sgn(k, 0) * fy * fz;
+      d[1][k] = 0.125 * sgn(k, 1) * fx * fz;
+      d[2][k] = 0.125 * sgn(k, 2) * fx * fy;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// d x d determinant / inverse (closed form; reference uses jnp.linalg.det / inv on J,
+// tatva/element/base.py:92, :113)
+// ---------------------------------------------------------------------------------------------
+
+TATVA_D double det_inv(const double (&A)[2][2], double (&Ai)[2][2]) {
+  const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+  const double r = 1.0 / det;
+  Ai[0][0] = A[1][1] * r;
+  Ai[0][1] = -A[0][1] * r;
+  Ai[1][0] = -A[1][0] * r;
+  Ai[1][1] = A[0][0] * r;
+  return det;
+}
+
+TATVA_D double det_inv(const double (&A)[3][3], double (&Ai)[3][3]) {
+  const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+  const double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+  const double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+  const double det = A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02;
+  const double r = 1.0 / det;
+  Ai[0][0] = c00 * r;
+  Ai[1][0] = c01 * r;
+  Ai[2][0] = c02 * r;
+  Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * r;
+  Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * r;
+  Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * r;
+  Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * r;
+  Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * r;
+  Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * r;
+  return det;
+}
+
+// Per-quadrature-point geometry: dNdX = inv(J) @ dNdr with J = dNdr @ X_e
+// (tatva/element/base.py:111-113); returns det J (:92).
+template <class El>
+TATVA_D double geometry(int q, const double (&X)[El::npe][El::dim], double (&dNdX)[El::dim][El::npe]) {
+  double dNdr[El::dim][El::npe];
+  El::dNdr(q, dNdr);
+  double J[El::dim][El::dim], Ji[El::dim][El::dim];
+#pragma unroll
+  for (int d = 0; d < El::dim; ++d)
+#pragma unroll
+    for (int c = 0; c < El::dim; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) s += dNdr[d][n] * X[n][c];
+      J[d][c] = s;
+    }
+  const double det = det_inv(J, Ji);
+#pragma unroll
+  for (int c = 0; c < El::dim; ++c)
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n) {
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < El::dim; ++d) s += Ji[c][d] * dNdr[d][n];
+      dNdX[c][n] = s;
+    }
+  return det;
+}
+
+template <class El>
+TATVA_D double det_jacobian(int q, const double (&X)[El::npe][El::dim]) {
+  double dNdr[El::dim][El::npe];
+  El::dNdr(q, dNdr);
+  double J[El::dim][El::dim];
+#pragma unroll
+  for (int d = 0; d < El::dim; ++d)
+#pragma unroll
+    for (int c = 0; c < El::dim; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) s += dNdr[d][n] * X[n][c];
+      J[d][c] = s;
+    }
+  if constexpr (El::dim == 2) {
+    return J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  } else {
+    return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Constitutive laws.  A law sees, per quadrature point, the gradients G[c][j] = d s_c / d x_j of
+// every nodal component c (c < dpn) and — for components >= val_lo — the interpolated value.
+// first()  fills the conjugate fluxes  A[c][j] = d psi / d G[c][j],  b[c] = d psi / d val[c];
+// second() fills their directional derivative along (dG, dval).
+// ---------------------------------------------------------------------------------------------
+
+template <int DPN, int DIM>
+struct QState {
+  double G[DPN][DIM];
+  double val[DPN];
+};
+
+template <int DIM>
+struct LinearElastic {  // tests/test_sparse.py:20-38
+  static constexpr int dim = DIM, dpn = DIM, val_lo = DIM, n_params = 2;
+  static constexpr bool needs_u_for_hvp = false;  // quadratic energy: H does not depend on u
+  double mu, lmbda;
+  struct Cache {};
+  using S = QState<dpn, dim>;
+  TATVA_D void prepare(const S&, Cache&) const {}
+  TATVA_D double psi(const S& s, const Cache&) const {
+    double tr = 0.0, ee = 0.0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      tr += s.G[i][i];
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) {
+        const double e = 0.5 * (s.G[i][j] + s.G[j][i]);
+        ee += e * e;
+      }
+    }
+    return mu * ee + 0.5 * lmbda * tr * tr;
+  }
+  TATVA_D void first(const S& s, const Cache&, S& f) const {
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) tr += s.G[i][i];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) f.G[i][j] = mu * (s.G[i][j] + s.G[j][i]) + (i == j ? lmbda * tr : 0.0);
+  }
+  TATVA_D void second(const S&, const Cache& c, const S& ds, S& f) const { first(ds, c, f); }
+};
+
+struct NeoHookean {  // tests/test_sparse_tracer.py:103-115 (mu=500, lambda=1000 at :126)
+  static constexpr int dim = 3, dpn = 3, val_lo = 3, n_params = 2;
+  static constexpr bool needs_u_for_hvp = true;
+  double mu, lmbda;
+  struct Cache {
+    double Fi[3][3];  // F^-1
+    double lnJ;
+    double I1;
+  };
+  using S = QState<3, 3>;
+  TATVA_D void prepare(const S& s, Cache& c) const {
+    double F[3][3];
+    double I1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        F[i][j] = s.G[i][j] + (i == j ? 1.0 : 0.0);
+        I1 += F[i][j] * F[i][j];
+      }
+    const double J = det_inv(F, c.Fi);
+    c.lnJ = log(J);
+    c.I1 = I1;
+  }
+  TATVA_D double psi(const S&, const Cache& c) const {
+    return 0.5 * mu * (c.I1 - 3.0 - 2.0 * c.lnJ) + 0.5 * lmbda * c.lnJ * c.lnJ;
+  }
+  // P = mu (F - F^-T) + lambda lnJ F^-T
+  TATVA_D void first(const S& s, const Cache& c, S& f) const {
+    const double k = lmbda * c.lnJ - mu;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) f.G[i][j] = mu * (s.G[i][j] + (i == j ? 1.0 : 0.0)) + k * c.Fi[j][i];
+  }
+  // dP = mu dG + (mu - lambda lnJ) F^-T dG^T F^-T + lambda tr(F^-1 dG) F^-T
+  TATVA_D void second(const S&, const Cache& c, const S& ds, S& f) const {
+    double B[3][3];  // F^-1 dG
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t += c.Fi[i][k] * ds.G[k][j];
+        B[i][j] = t;
+        if (i == j) tr += t;
+      }
+    const double k1 = mu - lmbda * c.lnJ, k2 = lmbda * tr;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double t = 0.0;  // (B F^-1)[j][i]
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t += B[j][k] * c.Fi[k][i];
+        f.G[i][j] = mu * ds.G[i][j] + k1 * t + k2 * c.Fi[j][i];
+      }
+  }
+};
+
+// Config-5 two-field law (builder-defined AT2; no counterpart in the reference):
+// psi = ((1-phi)^2 + k) psi_NH(grad u) + Gc (phi^2/(2 l) + l/2 |grad phi|^2); nodal state [ux,uy,uz,phi].
+struct NeoHookeanPhaseField {
+  static constexpr int dim = 3, dpn = 4, val_lo = 3, n_params = 5;
+  static constexpr bool needs_u_for_hvp = true;
+  double mu, lmbda, Gc, ell, k;
+  struct Cache {
+    NeoHookean::Cache nh;
+    double psi_nh;
+    double P[3][3];
+  };
+  using S = QState<4, 3>;
+  TATVA_D NeoHookean nh() const { return NeoHookean{mu, lmbda}; }
+  TATVA_D static void sub(const S& s, NeoHookean::S& t) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t.G[i][j] = s.G[i][j];
+  }
+  TATVA_D void prepare(const S& s, Cache& c) const {
+    NeoHookean::S t, P;
+    sub(s, t);
+    const NeoHookean m = nh();
+    m.prepare(t, c.nh);
+    c.psi_nh = m.psi(t, c.nh);
+    m.first(t, c.nh, P);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) c.P[i][j] = P.G[i][j];
+  }
+  TATVA_D double psi(const S& s, const Cache& c) const {
+    const double phi = s.val[3];
+    const double g = (1.0 - phi) * (1.0 - phi) + k;
+    const double gg = s.G[3][0] * s.G[3][0] + s.G[3][1] * s.G[3][1] + s.G[3][2] * s.G[3][2];
+    return g * c.psi_nh + Gc * (phi * phi / (2.0 * ell) + 0.5 * ell * gg);
+  }
+  TATVA_D void first(const S& s, const Cache& c, S& f) const {
+    const double phi = s.val[3];
+    const double g = (1.0 - phi) * (1.0 - phi) + k, dg = -2.0 * (1.0 - phi);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) f.G[i][j] = g * c.P[i][j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f.G[3][j] = Gc * ell * s.G[3][j];
+    f.val[3] = dg * c.psi_nh + Gc * phi / ell;
+  }
+  TATVA_D void second(const S& s, const Cache& c, const S& ds, S& f) const {
+    const double phi = s.val[3], dphi = ds.val[3];
+    const double g = (1.0 - phi) * (1.0 - phi) + k, dg = -2.0 * (1.0 - phi);
+    NeoHookean::S t, dt, dP;
+    sub(s, t);
+    sub(ds, dt);
+    nh().second(t, c.nh, dt, dP);
+    double PdG = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        f.G[i][j] = g * dP.G[i][j] + dg * dphi * c.P[i][j];
+        PdG += c.P[i][j] * ds.G[i][j];
+      }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f.G[3][j] = Gc * ell * ds.G[3][j];
+    f.val[3] = dg * PdG + 2.0 * dphi * c.psi_nh + Gc * dphi / ell;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// The plan (opaque to C callers)
+// ---------------------------------------------------------------------------------------------
+
+}  // namespace tatva
+
+struct tatva_plan {
+  int element;
+  int dim, npe, nq;
+  int64_t n_nodes, n_elems;
+  const double* coords;  // caller-owned device view (n_nodes, dim)
+  const int32_t* conn;   // caller-owned device view (n_elems, npe)
+  int flags;
+  int variant;
+  double* scratch;  // plan-owned: energy partials / row-sum partials
+  int64_t scratch_len;
+  double* weights;  // plan-owned (n_elems, nq) when TATVA_PLAN_CACHE_WEIGHTS
+};
+
+namespace tatva {
+
+inline int grid_for(int64_t n, int block = kBlock) { return (int)((n + block - 1) / block); }
+
+#define TATVA_CUDA_TRY(expr)                \
+  do {                                      \
+    cudaError_t _e = (expr);                \
+    if (_e != cudaSuccess) return (int)_e;  \
+  } while (0)
+
+#define TATVA_LAUNCH_CHECK()                \
+  do {                                      \
+    cudaError_t _e = cudaPeekAtLastError(); \
+    if (_e != cudaSuccess) return (int)_e;  \
+  } while (0)
+
+// entry points implemented in the per-topic translation units
+int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                      cudaStream_t st);
+
+}  // namespace tatva

@@ -1,0 +1,784 @@
+// Generic element-per-thread kernels: the quadrature-loop building blocks behind
+// Operator.grad / eval / integrate / map, and the fused energy / residual / HVP / CSR-assembly
+// kernels for every (element, law) pair.  One thread owns one element: it gathers the element's
+// nodal rows by connectivity (the `v[self.mesh.elements]` of tatva/operator.py:221), runs the
+// quadrature loop in FP64 registers and scatter-adds with RED.F64 atomics (the transpose of that
+// gather, which is what jax.grad produces in the reference).
+#include <new>
+
+#include "common.cuh"
+
+namespace tatva {
+
+// ---- gather helpers ---------------------------------------------------------------------------
+
+template <class El>
+TATVA_D void load_conn(const int32_t* __restrict__ conn, int64_t e, int (&nd)[El::npe]) {
+  if constexpr (El::npe == 4) {
+    const int4 t = __ldg(reinterpret_cast<const int4*>(conn) + e);
+    nd[0] = t.x; nd[1] = t.y; nd[2] = t.z; nd[3] = t.w;
+  } else if constexpr (El::npe == 8) {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  } else {
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n) nd[n] = __ldg(conn + e * El::npe + n);
+  }
+}
+
+template <int NPE, int W>
+TATVA_D void gather_rows(const double* __restrict__ src, const int (&nd)[NPE], double (&dst)[NPE][W]) {
+#pragma unroll
+  for (int n = 0; n < NPE; ++n)
+#pragma unroll
+    for (int c = 0; c < W; ++c) dst[n][c] = __ldg(src + (int64_t)nd[n] * W + c);
+}
+
+// ---- Operator building blocks (runtime number of value components) -----------------------------
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_weights(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                    int64_t E, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim];
+  gather_rows(coords, nd, X);
+#pragma unroll
+  for (int q = 0; q < El::nq; ++q) out[e * El::nq + q] = det_jacobian<El>(q, X) * El::weight(q);
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_grad(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                 int64_t E, const double* __restrict__ u, int nv,
+                                                 double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim];
+  gather_rows(coords, nd, X);
+#pragma unroll 1
+  for (int q = 0; q < El::nq; ++q) {
+    double dNdX[El::dim][El::npe];
+    geometry<El>(q, X, dNdX);
+    for (int c = 0; c < nv; ++c) {
+      double ue[El::npe];
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
+#pragma unroll
+      for (int j = 0; j < El::dim; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n) s += dNdX[j][n] * ue[n];
+        out[((e * El::nq + q) * nv + c) * El::dim + j] = s;
+      }
+    }
+  }
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_grad_adjoint(const double* __restrict__ coords,
+                                                         const int32_t* __restrict__ conn, int64_t E,
+                                                         const double* __restrict__ g, int nv, double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim];
+  gather_rows(coords, nd, X);
+#pragma unroll 1
+  for (int q = 0; q < El::nq; ++q) {
+    double dNdX[El::dim][El::npe];
+    geometry<El>(q, X, dNdX);
+    for (int c = 0; c < nv; ++c) {
+      double gj[El::dim];
+#pragma unroll
+      for (int j = 0; j < El::dim; ++j) gj[j] = __ldg(g + ((e * El::nq + q) * nv + c) * El::dim + j);
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < El::dim; ++j) s += gj[j] * dNdX[j][n];
+        atomicAdd(y + (int64_t)nd[n] * nv + c, s);
+      }
+    }
+  }
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_eval(const int32_t* __restrict__ conn, int64_t E,
+                                                 const double* __restrict__ u, int nv, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  for (int c = 0; c < nv; ++c) {
+    double ue[El::npe];
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
+#pragma unroll
+    for (int q = 0; q < El::nq; ++q) {
+      double N[El::npe];
+      El::N(q, N);
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) s += N[n] * ue[n];
+      out[(e * El::nq + q) * nv + c] = s;
+    }
+  }
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_eval_adjoint(const int32_t* __restrict__ conn, int64_t E,
+                                                         const double* __restrict__ g, int nv, double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  for (int c = 0; c < nv; ++c) {
+    double acc[El::npe];
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n) acc[n] = 0.0;
+#pragma unroll
+    for (int q = 0; q < El::nq; ++q) {
+      double N[El::npe];
+      El::N(q, N);
+      const double gq = __ldg(g + (e * El::nq + q) * nv + c);
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) acc[n] += N[n] * gq;
+    }
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n) atomicAdd(y + (int64_t)nd[n] * nv + c, acc[n]);
+  }
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_integrate_quad(const double* __restrict__ coords,
+                                                           const int32_t* __restrict__ conn, int64_t E,
+                                                           const double* __restrict__ cachedW,
+                                                           const double* __restrict__ vals, int nv,
+                                                           double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double W[El::nq];
+  if (cachedW) {
+#pragma unroll
+    for (int q = 0; q < El::nq; ++q) W[q] = __ldg(cachedW + e * El::nq + q);
+  } else {
+    int nd[El::npe];
+    load_conn<El>(conn, e, nd);
+    double X[El::npe][El::dim];
+    gather_rows(coords, nd, X);
+#pragma unroll
+    for (int q = 0; q < El::nq; ++q) W[q] = det_jacobian<El>(q, X) * El::weight(q);
+  }
+  for (int c = 0; c < nv; ++c) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < El::nq; ++q) s += __ldg(vals + (e * El::nq + q) * nv + c) * W[q];
+    out[e * nv + c] = s;
+  }
+}
+
+// gather / scatter over (element, node, component) with one thread per entry: coalesced on the
+// element side, indexed on the nodal side.
+__global__ void __launch_bounds__(256) k_gather(const int32_t* __restrict__ conn, int64_t total, int nv,
+                                                const double* __restrict__ u, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t en = i / nv;
+  const int c = (int)(i - en * nv);
+  out[i] = __ldg(u + (int64_t)__ldg(conn + en) * nv + c);
+}
+
+__global__ void __launch_bounds__(256) k_gather_adjoint(const int32_t* __restrict__ conn, int64_t total, int nv,
+                                                        const double* __restrict__ g, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t en = i / nv;
+  const int c = (int)(i - en * nv);
+  atomicAdd(y + (int64_t)__ldg(conn + en) * nv + c, __ldg(g + i));
+}
+
+// ---- deterministic reductions -----------------------------------------------------------------
+
+TATVA_D double block_sum(double v) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  __syncthreads();
+  return v;  // valid on thread 0
+}
+
+// partial[b*nv + c] = sum over rows of chunk b; rows strided by blockDim
+__global__ void __launch_bounds__(256) k_sum_rows_partial(const double* __restrict__ in, int64_t rows, int nv,
+                                                          int64_t rows_per_block, double* __restrict__ partial) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  for (int c = 0; c < nv; ++c) {
+    double s = 0.0;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) s += __ldg(in + r * nv + c);
+    s = block_sum(s);
+    if (threadIdx.x == 0) partial[(int64_t)blockIdx.x * nv + c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sum_rows_final(const double* __restrict__ partial, int nblocks, int nv,
+                                                        double* __restrict__ out) {
+  for (int c = blockIdx.x; c < nv; c += gridDim.x) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partial[(int64_t)b * nv + c];
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[c] = s;
+  }
+}
+
+// ---- fused energy / residual / HVP ------------------------------------------------------------
+
+enum { MODE_ENERGY = 0, MODE_RESIDUAL = 1, MODE_HVP = 2 };
+
+template <class El, class Mat>
+TATVA_D void qp_state(const double (&dNdX)[El::dim][El::npe], const double (&N)[El::npe],
+                      const double (&U)[El::npe][Mat::dpn], typename Mat::S& s) {
+#pragma unroll
+  for (int c = 0; c < Mat::dpn; ++c) {
+#pragma unroll
+    for (int j = 0; j < El::dim; ++j) {
+      double t = 0.0;
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) t += dNdX[j][n] * U[n][c];
+      s.G[c][j] = t;
+    }
+    if (c >= Mat::val_lo) {
+      double t = 0.0;
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) t += N[n] * U[n][c];
+      s.val[c] = t;
+    }
+  }
+}
+
+template <class El, class Mat, int MODE>
+__global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                  int64_t E, Mat mat, const double* __restrict__ u,
+                                                  const double* __restrict__ v, double* __restrict__ y,
+                                                  double* __restrict__ partials) {
+  static_assert(El::dim == Mat::dim, "element / law dimension mismatch");
+  constexpr int dpn = Mat::dpn;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double energy = 0.0;
+  if (e < E) {
+    int nd[El::npe];
+    load_conn<El>(conn, e, nd);
+    double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn], Y[El::npe][dpn];
+    gather_rows(coords, nd, X);
+    gather_rows(u, nd, U);
+    if constexpr (MODE == MODE_HVP) gather_rows(v, nd, V);
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n)
+#pragma unroll
+      for (int c = 0; c < dpn; ++c) Y[n][c] = 0.0;
+
+#pragma unroll 1
+    for (int q = 0; q < El::nq; ++q) {
+      double dNdX[El::dim][El::npe], N[El::npe];
+      const double W = geometry<El>(q, X, dNdX) * El::weight(q);
+      El::N(q, N);
+      typename Mat::S s, ds, f;
+      typename Mat::Cache cache;
+      qp_state<El, Mat>(dNdX, N, U, s);
+      mat.prepare(s, cache);
+      if constexpr (MODE == MODE_ENERGY) {
+        energy += W * mat.psi(s, cache);
+      } else {
+        if constexpr (MODE == MODE_RESIDUAL) {
+          mat.first(s, cache, f);
+        } else {
+          qp_state<El, Mat>(dNdX, N, V, ds);
+          mat.second(s, cache, ds, f);
+        }
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n)
+#pragma unroll
+          for (int c = 0; c < dpn; ++c) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < El::dim; ++j) t += f.G[c][j] * dNdX[j][n];
+            if (c >= Mat::val_lo) t += f.val[c] * N[n];
+            Y[n][c] += W * t;
+          }
+      }
+    }
+    if constexpr (MODE != MODE_ENERGY) {
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n)
+#pragma unroll
+        for (int c = 0; c < dpn; ++c) atomicAdd(y + (int64_t)nd[n] * dpn + c, Y[n][c]);
+    }
+  }
+  if constexpr (MODE == MODE_ENERGY) {
+    energy = block_sum(energy);
+    if (threadIdx.x == 0) partials[blockIdx.x] = energy;
+  }
+}
+
+// ---- CSR assembly -----------------------------------------------------------------------------
+// Column (b,k) of the element stiffness is the element-local HVP with the unit direction
+// "component k of node b"; rows (a,i) go to data[indptr[dpn*node_a + i] + pos[e,a,b] + k].
+
+template <class El, class Mat>
+__global__ void __launch_bounds__(kBlock) k_csr(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                int64_t E, Mat mat, const double* __restrict__ u,
+                                                const int32_t* __restrict__ indptr, const int32_t* __restrict__ pos,
+                                                double* __restrict__ data) {
+  constexpr int dpn = Mat::dpn;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim], U[El::npe][dpn];
+  gather_rows(coords, nd, X);
+  gather_rows(u, nd, U);
+  int64_t row0[El::npe];  // indptr of the first DOF row of each node
+#pragma unroll
+  for (int a = 0; a < El::npe; ++a) row0[a] = (int64_t)nd[a] * dpn;
+
+#pragma unroll 1
+  for (int b = 0; b < El::npe; ++b) {
+#pragma unroll 1
+    for (int k = 0; k < dpn; ++k) {
+      double col[El::npe][dpn];
+#pragma unroll
+      for (int a = 0; a < El::npe; ++a)
+#pragma unroll
+        for (int i = 0; i < dpn; ++i) col[a][i] = 0.0;
+#pragma unroll 1
+      for (int q = 0; q < El::nq; ++q) {
+        double dNdX[El::dim][El::npe], N[El::npe];
+        const double W = geometry<El>(q, X, dNdX) * El::weight(q);
+        El::N(q, N);
+        typename Mat::S s, ds, f;
+        typename Mat::Cache cache;
+        qp_state<El, Mat>(dNdX, N, U, s);
+        mat.prepare(s, cache);
+#pragma unroll
+        for (int c = 0; c < dpn; ++c) {
+#pragma unroll
+          for (int j = 0; j < El::dim; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int n = 0; n < El::npe; ++n) t += (n == b && c == k) ? dNdX[j][n] : 0.0;
+            ds.G[c][j] = t;
+          }
+          double t = 0.0;
+#pragma unroll
+          for (int n = 0; n < El::npe; ++n) t += (n == b && c == k) ? N[n] : 0.0;
+          ds.val[c] = t;
+        }
+        mat.second(s, cache, ds, f);
+#pragma unroll
+        for (int a = 0; a < El::npe; ++a)
+#pragma unroll
+          for (int i = 0; i < dpn; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < El::dim; ++j) t += f.G[i][j] * dNdX[j][a];
+            if (i >= Mat::val_lo) t += f.val[i] * N[a];
+            col[a][i] += W * t;
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < El::npe; ++a) {
+        const int p = __ldg(pos + (e * El::npe + a) * El::npe + b) + k;
+#pragma unroll
+        for (int i = 0; i < dpn; ++i) atomicAdd(data + (int64_t)__ldg(indptr + row0[a] + i) + p, col[a][i]);
+      }
+    }
+  }
+}
+
+// ---- halo pack / unpack -----------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_pack(const double* __restrict__ src, const int64_t* __restrict__ idx,
+                                              int64_t n, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __ldg(src + __ldg(idx + i));
+}
+__global__ void __launch_bounds__(256) k_unpack_set(const double* __restrict__ src, const int64_t* __restrict__ idx,
+                                                    int64_t n, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[__ldg(idx + i)] = __ldg(src + i);
+}
+__global__ void __launch_bounds__(256) k_unpack_add(const double* __restrict__ src, const int64_t* __restrict__ idx,
+                                                    int64_t n, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(dst + __ldg(idx + i), __ldg(src + i));
+}
+
+// ---- FP64 FMA peak microbenchmark ---------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace tatva
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace tatva;
+
+#define DISPATCH_ELEMENT(p, CALL)                 \
+  switch ((p)->element) {                         \
+    case TATVA_TRI3: { using El = Tri3; CALL; } break; \
+    case TATVA_TET4: { using El = Tet4; CALL; } break; \
+    case TATVA_HEX8: { using El = Hex8; CALL; } break; \
+    default: return TATVA_E_INVALID;              \
+  }
+
+extern "C" {
+
+const char* tatva_error_string(int code) {
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case TATVA_OK: return "ok";
+    case TATVA_E_INVALID: return "invalid argument";
+    case TATVA_E_UNSUPPORTED: return "unsupported element/material combination";
+    case TATVA_E_NOMEM: return "out of memory";
+    case TATVA_E_NODEVICE: return "no CUDA device";
+    default: return "unknown error";
+  }
+}
+
+int tatva_abi_version(void) { return TATVA_B200_ABI_VERSION; }
+
+int tatva_device_count(int* count) {
+  if (!count) return TATVA_E_INVALID;
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return (int)e;
+  }
+  return TATVA_OK;
+}
+
+int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t n_elems, const double* d_coords,
+                      const int32_t* d_conn, int flags, tatva_stream_t stream) {
+  if (!out || !d_coords || !d_conn || n_nodes <= 0 || n_elems <= 0) return TATVA_E_INVALID;
+  tatva_plan* p = new (std::nothrow) tatva_plan();
+  if (!p) return TATVA_E_NOMEM;
+  p->element = element;
+  switch (element) {
+    case TATVA_TRI3: p->dim = Tri3::dim; p->npe = Tri3::npe; p->nq = Tri3::nq; break;
+    case TATVA_TET4: p->dim = Tet4::dim; p->npe = Tet4::npe; p->nq = Tet4::nq; break;
+    case TATVA_HEX8: p->dim = Hex8::dim; p->npe = Hex8::npe; p->nq = Hex8::nq; break;
+    default: delete p; return TATVA_E_INVALID;
+  }
+  p->n_nodes = n_nodes;
+  p->n_elems = n_elems;
+  p->coords = d_coords;
+  p->conn = d_conn;
+  p->flags = flags;
+  p->variant = TATVA_VARIANT_DEFAULT;
+  p->weights = nullptr;
+  p->scratch_len = (int64_t)grid_for(n_elems) > 1024 * 64 ? (int64_t)grid_for(n_elems) : 1024 * 64;
+  cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  if (flags & TATVA_PLAN_CACHE_WEIGHTS) {
+    e = cudaMalloc(&p->weights, sizeof(double) * n_elems * p->nq);
+    if (e != cudaSuccess) { cudaFree(p->scratch); delete p; return (int)e; }
+    double* w = p->weights;
+    p->weights = nullptr;  // compute (not read) the weights on the first pass
+    int rc = tatva_op_integration_weights(p, w, stream);
+    p->weights = w;
+    if (rc != 0) { tatva_plan_destroy(p); return rc; }
+  }
+  *out = p;
+  return TATVA_OK;
+}
+
+int tatva_plan_destroy(tatva_plan_t* p) {
+  if (!p) return TATVA_OK;
+  if (p->scratch) cudaFree(p->scratch);
+  if (p->weights) cudaFree(p->weights);
+  delete p;
+  return TATVA_OK;
+}
+
+int tatva_plan_info(const tatva_plan_t* p, int* element, int* dim, int* npe, int* nq, int64_t* n_nodes,
+                    int64_t* n_elems) {
+  if (!p) return TATVA_E_INVALID;
+  if (element) *element = p->element;
+  if (dim) *dim = p->dim;
+  if (npe) *npe = p->npe;
+  if (nq) *nq = p->nq;
+  if (n_nodes) *n_nodes = p->n_nodes;
+  if (n_elems) *n_elems = p->n_elems;
+  return TATVA_OK;
+}
+
+int tatva_plan_set_variant(tatva_plan_t* p, int variant) {
+  if (!p || variant < 0 || variant > TATVA_VARIANT_MODAL) return TATVA_E_INVALID;
+  p->variant = variant;
+  return TATVA_OK;
+}
+
+int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_stream_t stream) {
+  if (!p || !d_out) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->weights) {
+    TATVA_CUDA_TRY(cudaMemcpyAsync(d_out, p->weights, sizeof(double) * p->n_elems * p->nq, cudaMemcpyDeviceToDevice, st));
+    return TATVA_OK;
+  }
+  DISPATCH_ELEMENT(p, (k_weights<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_out)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_grad(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
+  if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_ELEMENT(p, (k_grad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, double* d_y, tatva_stream_t stream) {
+  if (!p || !d_g || !d_y || nv <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
+  DISPATCH_ELEMENT(p, (k_grad_adjoint<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_g, nv, d_y)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_eval(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
+  if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_ELEMENT(p, (k_eval<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->conn, p->n_elems, d_u, nv, d_out)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_eval_adjoint(const tatva_plan_t* p, const double* d_g, int nv, double* d_y, tatva_stream_t stream) {
+  if (!p || !d_g || !d_y || nv <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
+  DISPATCH_ELEMENT(p, (k_eval_adjoint<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->conn, p->n_elems, d_g, nv, d_y)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_integrate_quad(const tatva_plan_t* p, const double* d_vals, int nv, double* d_out, tatva_stream_t stream) {
+  if (!p || !d_vals || !d_out || nv <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_ELEMENT(p, (k_integrate_quad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, p->weights, d_vals, nv, d_out)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_gather(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
+  if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
+  const int64_t total = p->n_elems * p->npe * nv;
+  k_gather<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p->conn, total, nv, d_u, d_out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_gather_adjoint(const tatva_plan_t* p, const double* d_g, int nv, double* d_y, tatva_stream_t stream) {
+  if (!p || !d_g || !d_y || nv <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
+  const int64_t total = p->n_elems * p->npe * nv;
+  k_gather_adjoint<<<grid_for(total, 256), 256, 0, st>>>(p->conn, total, nv, d_g, d_y);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_op_sum_rows(tatva_plan_t* p, const double* d_in, int64_t rows, int nv, double* d_out, tatva_stream_t stream) {
+  if (!p || !d_in || !d_out || rows <= 0 || nv <= 0 || nv > 64) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int nblocks = (int)((rows + 4095) / 4096);
+  if (nblocks > 1024) nblocks = 1024;
+  const int64_t rpb = (rows + nblocks - 1) / nblocks;
+  k_sum_rows_partial<<<nblocks, 256, 0, st>>>(d_in, rows, nv, rpb, p->scratch);
+  k_sum_rows_final<<<nv, 256, 0, st>>>(p->scratch, nblocks, nv, d_out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// ---- fused dispatch ------------------------------------------------------------------------------
+}  // extern "C"
+
+template <class El, class Mat, int MODE>
+static int launch_fused(tatva_plan* p, const Mat& mat, const double* u, const double* v, double* out, cudaStream_t st) {
+  const int grid = grid_for(p->n_elems);
+  if (MODE == MODE_ENERGY) {
+    k_fused<El, Mat, MODE><<<grid, kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, nullptr, p->scratch);
+    k_sum_rows_final<<<1, 256, 0, st>>>(p->scratch, grid, 1, out);
+  } else {
+    TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
+    k_fused<El, Mat, MODE><<<grid, kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, nullptr);
+  }
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+template <int MODE>
+static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_params, const double* u, const double* v,
+                          double* out, cudaStream_t st) {
+  if (!p || !prm || !u || !out) return TATVA_E_INVALID;
+  if (MODE == MODE_HVP && !v) return TATVA_E_INVALID;
+  const int el = p->element;
+  if (material == TATVA_LINEAR_ELASTIC) {
+    if (n_params != 2) return TATVA_E_INVALID;
+    if (el == TATVA_TRI3) return launch_fused<Tri3, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_TET4) return launch_fused<Tet4, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_HEX8) return launch_fused<Hex8, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
+  } else if (material == TATVA_NEO_HOOKEAN) {
+    if (n_params != 2) return TATVA_E_INVALID;
+    if (el == TATVA_TET4) return launch_fused<Tet4, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_HEX8) {
+      if (MODE == MODE_HVP && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_hvp_modal(p, prm[0], prm[1], u, v, out, st);
+      return launch_fused<Hex8, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
+    }
+  } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD) {
+    if (n_params != 5) return TATVA_E_INVALID;
+    const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+    if (el == TATVA_TET4) return launch_fused<Tet4, NeoHookeanPhaseField, MODE>(p, m, u, v, out, st);
+    if (el == TATVA_HEX8) return launch_fused<Hex8, NeoHookeanPhaseField, MODE>(p, m, u, v, out, st);
+  } else {
+    return TATVA_E_INVALID;
+  }
+  return TATVA_E_UNSUPPORTED;
+}
+
+extern "C" {
+
+int tatva_energy(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u, double* d_energy,
+                 tatva_stream_t stream) {
+  return dispatch_fused<MODE_ENERGY>(p, material, params, n_params, d_u, nullptr, d_energy, (cudaStream_t)stream);
+}
+int tatva_residual(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u, double* d_r,
+                   tatva_stream_t stream) {
+  return dispatch_fused<MODE_RESIDUAL>(p, material, params, n_params, d_u, nullptr, d_r, (cudaStream_t)stream);
+}
+int tatva_hvp(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u, const double* d_v,
+              double* d_y, tatva_stream_t stream) {
+  return dispatch_fused<MODE_HVP>(p, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+template <class El, class Mat>
+static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int32_t* indptr, const int32_t* pos,
+                      int64_t nnz, double* data, cudaStream_t st) {
+  TATVA_CUDA_TRY(cudaMemsetAsync(data, 0, sizeof(double) * nnz, st));
+  k_csr<El, Mat><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+extern "C" {
+
+int tatva_csr_assemble(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
+                       const int32_t* d_indptr, const int32_t* d_pos, int64_t nnz, double* d_data,
+                       tatva_stream_t stream) {
+  if (!p || !prm || !d_u || !d_indptr || !d_pos || !d_data || nnz <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int el = p->element;
+  if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
+    if (el == TATVA_TRI3) return launch_csr<Tri3, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_TET4) return launch_csr<Tet4, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_HEX8) return launch_csr<Hex8, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+  } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
+    if (el == TATVA_TET4) return launch_csr<Tet4, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_HEX8) return launch_csr<Hex8, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+  } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5) {
+    const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+    if (el == TATVA_TET4) return launch_csr<Tet4, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_HEX8) return launch_csr<Hex8, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_pos, nnz, d_data, st);
+  } else {
+    return TATVA_E_INVALID;
+  }
+  return TATVA_E_UNSUPPORTED;
+}
+
+int tatva_halo_pack(const double* s, const int64_t* idx, int64_t n, double* d, tatva_stream_t stream) {
+  if (n == 0) return TATVA_OK;
+  if (!s || !idx || !d || n < 0) return TATVA_E_INVALID;
+  k_pack<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, idx, n, d);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_halo_unpack_set(const double* s, const int64_t* idx, int64_t n, double* d, tatva_stream_t stream) {
+  if (n == 0) return TATVA_OK;
+  if (!s || !idx || !d || n < 0) return TATVA_E_INVALID;
+  k_unpack_set<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, idx, n, d);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_halo_unpack_add(const double* s, const int64_t* idx, int64_t n, double* d, tatva_stream_t stream) {
+  if (n == 0) return TATVA_OK;
+  if (!s || !idx || !d || n < 0) return TATVA_E_INVALID;
+  k_unpack_add<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, idx, n, d);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_fp64_peak_tflops(double* tflops, tatva_stream_t stream) {
+  if (!tflops) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  TATVA_CUDA_TRY(cudaGetDevice(&dev));
+  TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double* buf = nullptr;
+  TATVA_CUDA_TRY(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  k_dfma<<<blocks, threads, 0, st>>>(buf, 64);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, st);
+    k_dfma<<<blocks, threads, 0, st>>>(buf, iters);
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(buf);
+  TATVA_LAUNCH_CHECK();
+  const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return TATVA_OK;
+}
+
+}  // extern "C"

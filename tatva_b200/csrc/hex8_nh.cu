@@ -1,0 +1,209 @@
+// Hex8 x compressible neo-Hookean matrix-free HVP — the headline kernel (config 3/4).
+//
+//   y = d/d eps  r(u + eps v),   r = dE/du,   E = sum_e sum_q W psi(grad u)           (README.md:93,
+//   psi = mu/2 (I1 - 3 - 2 ln J) + lambda/2 (ln J)^2,  F = I + grad u                   tests/test_sparse_tracer.py:103-115)
+//
+// The kernel is bound by the FP64 pipe (AI ~ 60 flop/B), so the design minimises
+// FP64 instructions per element rather than bytes:
+//
+//  * Modal form of the trilinear element.  Each nodal field is taken to its 7 non-constant
+//    trilinear coefficients by an 8-point Walsh-Hadamard transform (24 adds); the reference-space
+//    gradient at a 2x2x2 Gauss point (+-a,+-a,+-a) (tatva/element/base.py:493-513) is then 3 adds per
+//    direction instead of an 8-term dot product with dN/dxi (:531-568), and the scatter is the
+//    transposed accumulation into 7 modal residuals followed by one inverse transform.
+//  * Everything is kept in reference space.  With J = dX/dxi, Fr = d(X+u)/dxi, A = Fr^-1,
+//    K = J^-1, M = K^T K and Gv = dv/dxi:
+//        W dP(grad v) K = W [ mu Gv M + (mu - lambda lnJ) (A Gv A)^T + lambda tr(A Gv) A^T ],
+//        lnJ = log(det Fr / det J),  W = det J  (all quadrature weights are 1),
+//    which needs two 3x3 inverses, four 3x3 products, one log per point and never forms dN/dX.
+//  * One thread per element; gather by connectivity through the read-only path; scatter with
+//    RED.ADD.F64.  Elements of a lexicographic / locality-sorted mesh put consecutive lanes on
+//    consecutive nodes, so the 24-byte nodal rows of a warp share L1 lines.
+#include "common.cuh"
+
+namespace tatva {
+
+namespace {
+
+constexpr double kA = 0.57735026918962576451;  // 1/sqrt(3)
+
+// 8-point Walsh-Hadamard transform of the nodal values of one scalar field, in the element's node
+// order (bottom CCW, top CCW).  Output: c[0..6] = {x, y, z, xy, yz, zx, xyz} coefficients scaled so
+// that   d/dxi f = c_x + ty c_xy + tz c_zx + ty tz c_xyz   at the Gauss point a*(tx,ty,tz).
+TATVA_D void to_modal(const double (&f)[8], double (&c)[7]) {
+  // natural (bit) order: b = [sx>0] + 2 [sy>0] + 4 [sz>0]  <-  nodes 0,1,3,2,4,5,7,6
+  const double s01 = f[0] + f[1], d01 = f[1] - f[0];
+  const double s23 = f[3] + f[2], d23 = f[2] - f[3];
+  const double s45 = f[4] + f[5], d45 = f[5] - f[4];
+  const double s67 = f[7] + f[6], d67 = f[6] - f[7];
+  // y stage
+  const double ss0 = s01 + s23, ds0 = s23 - s01;  // (x-sum) y-sum / y-diff, lower face
+  const double sd0 = d01 + d23, dd0 = d23 - d01;  // (x-diff)
+  const double ss1 = s45 + s67, ds1 = s67 - s45;
+  const double sd1 = d45 + d67, dd1 = d67 - d45;
+  // z stage (the all-sum coefficient is not needed for gradients)
+  c[0] = 0.125 * (sd0 + sd1);                // x
+  c[1] = 0.125 * (ds0 + ds1);                // y
+  c[2] = 0.125 * (ss1 - ss0);                // z
+  c[3] = (0.125 * kA) * (dd0 + dd1);         // xy
+  c[4] = (0.125 * kA) * (ds1 - ds0);         // yz
+  c[5] = (0.125 * kA) * (sd1 - sd0);         // zx
+  c[6] = (0.125 * kA * kA) * (dd1 - dd0);    // xyz
+}
+
+// transpose of to_modal: modal residuals r[0..6] -> nodal contributions
+TATVA_D void from_modal(const double (&r)[7], double (&f)[8]) {
+  const double x = 0.125 * r[0], y = 0.125 * r[1], z = 0.125 * r[2];
+  const double xy = (0.125 * kA) * r[3], yz = (0.125 * kA) * r[4], zx = (0.125 * kA) * r[5];
+  const double xyz = (0.125 * kA * kA) * r[6];
+  // value at node with signs (sx,sy,sz):  sx x + sy y + sz z + sx sy xy + sy sz yz + sz sx zx + sx sy sz xyz
+  // sz = -1 / +1 halves
+  const double xm = x - zx, xp = x + zx;      // sx coefficient for sz = -1 / +1
+  const double ym = y - yz, yp = y + yz;      // sy coefficient
+  const double xym = xy - xyz, xyp = xy + xyz;  // sx sy coefficient
+  // lower face (sz = -1): -z + sx xm + sy ym + sx sy xym
+  f[0] = -z - xm - ym + xym;
+  f[1] = -z + xm - ym - xym;
+  f[2] = -z + xm + ym + xym;
+  f[3] = -z - xm + ym - xym;
+  f[4] = z - xp - yp + xyp;
+  f[5] = z + xp - yp - xyp;
+  f[6] = z + xp + yp + xyp;
+  f[7] = z - xp + yp - xyp;
+}
+
+// reference gradient of a modal field at Gauss point with signs (TX,TY,TZ)
+template <int TX, int TY, int TZ>
+TATVA_D void ref_grad(const double (&c)[7], double (&g)[3]) {
+  g[0] = (c[0] + TZ * c[5]) + TY * (c[3] + TZ * c[6]);
+  g[1] = (c[1] + TZ * c[4]) + TX * (c[3] + TZ * c[6]);
+  g[2] = (c[2] + TY * c[4]) + TX * (c[5] + TY * c[6]);
+}
+
+// transposed accumulation: r += ref_grad^T q
+template <int TX, int TY, int TZ>
+TATVA_D void ref_grad_T(const double (&q)[3], double (&r)[7]) {
+  r[0] += q[0];
+  r[1] += q[1];
+  r[2] += q[2];
+  r[3] += TY * q[0] + TX * q[1];
+  r[4] += TZ * q[1] + TY * q[2];
+  r[5] += TZ * q[0] + TX * q[2];
+  r[6] += (TY * TZ) * q[0] + (TX * TZ) * q[1] + (TX * TY) * q[2];
+}
+
+struct Modal {
+  double X[3][7];  // coordinates
+  double x[3][7];  // coordinates + displacement
+  double v[3][7];  // direction
+};
+
+template <int TX, int TY, int TZ>
+TATVA_D void qp_hvp(const Modal& m, double mu, double lmbda, double (&R)[3][7]) {
+  double J[3][3], K[3][3];  // J[d][c] = dX_c / dxi_d
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double g[3];
+    ref_grad<TX, TY, TZ>(m.X[c], g);
+    J[0][c] = g[0]; J[1][c] = g[1]; J[2][c] = g[2];
+  }
+  const double detJ = det_inv(J, K);
+  double M[3][3];  // K^T K (symmetric)
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      M[a][b] = K[0][a] * K[0][b] + K[1][a] * K[1][b] + K[2][a] * K[2][b];
+      M[b][a] = M[a][b];
+    }
+  double Fr[3][3], A[3][3];  // Fr[i][d] = d x_i / d xi_d
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ref_grad<TX, TY, TZ>(m.x[i], Fr[i]);
+  const double detFr = det_inv(Fr, A);
+  const double lnJ = log(detFr / detJ);
+  double Gv[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ref_grad<TX, TY, TZ>(m.v[i], Gv[i]);
+  double B[3][3];  // A Gv
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int e = 0; e < 3; ++e) B[d][e] = A[d][0] * Gv[0][e] + A[d][1] * Gv[1][e] + A[d][2] * Gv[2][e];
+  const double w1 = detJ * mu, w2 = detJ * (mu - lmbda * lnJ), w3 = detJ * lmbda * (B[0][0] + B[1][1] + B[2][2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double q[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double t1 = Gv[i][0] * M[0][d] + Gv[i][1] * M[1][d] + Gv[i][2] * M[2][d];
+      const double t2 = B[d][0] * A[0][i] + B[d][1] * A[1][i] + B[d][2] * A[2][i];
+      q[d] = w1 * t1 + w2 * t2 + w3 * A[d][i];
+    }
+    ref_grad_T<TX, TY, TZ>(q, R[i]);
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_hvp(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                  double lmbda, const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  Modal m;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8], fv[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal(fX, m.X[c]);
+    to_modal(fu, m.x[c]);
+    to_modal(fv, m.v[c]);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) m.x[c][k] += m.X[c][k];
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+
+  qp_hvp<-1, -1, -1>(m, mu, lmbda, R);
+  qp_hvp<+1, -1, -1>(m, mu, lmbda, R);
+  qp_hvp<+1, +1, -1>(m, mu, lmbda, R);
+  qp_hvp<-1, +1, -1>(m, mu, lmbda, R);
+  qp_hvp<-1, -1, +1>(m, mu, lmbda, R);
+  qp_hvp<+1, -1, +1>(m, mu, lmbda, R);
+  qp_hvp<+1, +1, +1>(m, mu, lmbda, R);
+  qp_hvp<-1, +1, +1>(m, mu, lmbda, R);
+
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
+}
+
+}  // namespace
+
+int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                      cudaStream_t st) {
+  TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  k_hex8_nh_hvp<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+}  // namespace tatva

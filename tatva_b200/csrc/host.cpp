@@ -1,0 +1,135 @@
+// Host-side setup for the coloured sparse-Jacobian path: sparsity pattern, distance-2 colouring and
+// the element -> CSR position map.  Integer work that runs once per mesh; results are bit-exact with
+// the reference's NumPy/SciPy code (tatva/sparse/_extraction.py:37-102, tatva/sparse/_coloring.py).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/tatva_b200.h"
+
+namespace {
+
+// node -> sorted unique neighbour nodes (nodes sharing an element, self included)
+void node_adjacency(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes, std::vector<int64_t>& ptr,
+                    std::vector<int32_t>& adj) {
+  std::vector<int64_t> n2e_ptr(n_nodes + 1, 0);
+  for (int64_t i = 0; i < n_elems * npe; ++i) n2e_ptr[conn[i] + 1]++;
+  for (int64_t n = 0; n < n_nodes; ++n) n2e_ptr[n + 1] += n2e_ptr[n];
+  std::vector<int64_t> n2e(n2e_ptr[n_nodes]);
+  {
+    std::vector<int64_t> fill(n2e_ptr.begin(), n2e_ptr.end() - 1);
+    for (int64_t e = 0; e < n_elems; ++e)
+      for (int a = 0; a < npe; ++a) n2e[fill[conn[e * npe + a]]++] = e;
+  }
+  ptr.assign(n_nodes + 1, 0);
+  std::vector<std::vector<int32_t>> rows(n_nodes);
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t n = 0; n < n_nodes; ++n) {
+    std::vector<int32_t>& r = rows[n];
+    r.reserve((n2e_ptr[n + 1] - n2e_ptr[n]) * npe);
+    for (int64_t k = n2e_ptr[n]; k < n2e_ptr[n + 1]; ++k) {
+      const int32_t* el = conn + n2e[k] * npe;
+      r.insert(r.end(), el, el + npe);
+    }
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+  }
+  for (int64_t n = 0; n < n_nodes; ++n) ptr[n + 1] = ptr[n] + (int64_t)rows[n].size();
+  adj.resize(ptr[n_nodes]);
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_nodes; ++n) std::copy(rows[n].begin(), rows[n].end(), adj.begin() + ptr[n]);
+}
+
+}  // namespace
+
+extern "C" {
+
+// tatva/sparse/_extraction.py:37-102.  DOF id = node * dpn + comp (:57-60); all (row, col) pairs of every
+// element, unique + sorted by row * ncols + col (:74-79) == per row, the sorted DOFs of the sorted
+// neighbour nodes.  Rows of nodes that appear in no element are empty.
+int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes, int dpn,
+                                 int32_t* indptr, int32_t* indices, int64_t* nnz_out) {
+  if (!conn || !indptr || !nnz_out || n_elems < 0 || npe <= 0 || n_nodes <= 0 || dpn <= 0) return TATVA_E_INVALID;
+  for (int64_t i = 0; i < n_elems * npe; ++i)
+    if (conn[i] < 0 || conn[i] >= n_nodes) return TATVA_E_INVALID;
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> adj;
+  node_adjacency(conn, n_elems, npe, n_nodes, ptr, adj);
+  const int64_t nnz = ptr[n_nodes] * dpn * dpn;
+  *nnz_out = nnz;
+  if (nnz > INT32_MAX) return TATVA_E_INVALID;  // scipy would switch to int64 indices here
+  indptr[0] = 0;
+  for (int64_t n = 0; n < n_nodes; ++n) {
+    const int64_t w = (ptr[n + 1] - ptr[n]) * dpn;
+    for (int i = 0; i < dpn; ++i) indptr[n * dpn + i + 1] = (int32_t)(indptr[n * dpn + i] + w);
+  }
+  if (!indices) return TATVA_OK;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_nodes; ++n) {
+    for (int i = 0; i < dpn; ++i) {
+      int32_t* out = indices + indptr[n * dpn + i];
+      for (int64_t k = ptr[n]; k < ptr[n + 1]; ++k)
+        for (int c = 0; c < dpn; ++c) *out++ = adj[k] * dpn + c;
+    }
+  }
+  return TATVA_OK;
+}
+
+// tatva/sparse/_coloring.py:270-283 -> :27-48 (pattern of A@A) -> :136-153 (first-fit, natural order).
+// The squared graph is never materialised: the distance-2 neighbours of i are the columns of the rows
+// named by row i.  `stamp[c] == i` marks colour c as used by a neighbour of i.
+int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t* colors,
+                                int32_t* n_colors) {
+  if (!indptr || !indices || !colors || n <= 0) return TATVA_E_INVALID;
+  std::fill(colors, colors + n, -1);
+  std::vector<int64_t> stamp;
+  stamp.reserve(256);
+  int32_t maxc = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    for (int32_t a = indptr[i]; a < indptr[i + 1]; ++a) {
+      const int32_t k = indices[a];
+      for (int32_t b = indptr[k]; b < indptr[k + 1]; ++b) {
+        const int32_t c = colors[indices[b]];
+        if (c >= 0) {
+          if ((size_t)c >= stamp.size()) stamp.resize(c + 1, -1);
+          stamp[c] = i;
+        }
+      }
+    }
+    int32_t c = 0;
+    while ((size_t)c < stamp.size() && stamp[c] == i) ++c;
+    colors[i] = c;
+    if (c > maxc) maxc = c;
+  }
+  if (n_colors) *n_colors = maxc + 1;
+  return TATVA_OK;
+}
+
+// elem_pos[e, a, b] = offset of column dpn*conn[e,b] inside CSR row dpn*conn[e,a]
+int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe, int dpn, const int32_t* indptr,
+                                     const int32_t* indices, int32_t* elem_pos) {
+  if (!conn || !indptr || !indices || !elem_pos || n_elems <= 0 || npe <= 0 || dpn <= 0) return TATVA_E_INVALID;
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for (int64_t e = 0; e < n_elems; ++e) {
+    for (int a = 0; a < npe; ++a) {
+      const int64_t row = (int64_t)conn[e * npe + a] * dpn;
+      const int32_t* lo = indices + indptr[row];
+      const int32_t* hi = indices + indptr[row + 1];
+      for (int b = 0; b < npe; ++b) {
+        const int32_t col = conn[e * npe + b] * dpn;
+        const int32_t* it = std::lower_bound(lo, hi, col);
+        if (it == hi || *it != col) {
+          bad |= 1;
+          elem_pos[(e * npe + a) * npe + b] = -1;
+        } else {
+          elem_pos[(e * npe + a) * npe + b] = (int32_t)(it - lo);
+        }
+      }
+    }
+  }
+  return bad ? TATVA_E_INVALID : TATVA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""Mesh container, structured generators and partition extraction — mirror of tatva/mesh.py.
+
+`Mesh(coords, elements)` keeps the reference's two fields (mesh.py:53-66).  Arrays may be NumPy
+or torch; `Operator` moves them to the device once.  Generators: `unit_square` / `rectangle`
+(mesh.py:147-231) plus the 3-D boxes the configs need (`box_tet` follows the reference's test
+helper tests/test_sparse_tracer.py:29-70; `box_hex` uses node id i + j(nx+1) + k(nx+1)(ny+1) and the
+Hexahedron8 node order of element/base.py:478-491).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+from enum import Enum
+from typing import Any, NamedTuple
+
+import numpy as np
+
+
+class ElementType(Enum):
+    TRIANGLE = "triangle"
+    QUAD = "quad"
+    TETRAHEDRON = "tetrahedron"
+    HEXAHEDRON = "hexahedron"
+
+
+class PartitionInfo(NamedTuple):
+    """mesh.py:38-47."""
+
+    nodes_local_to_global: np.ndarray
+    n_owned_nodes: int
+
+
+def _np(a):
+    if hasattr(a, "detach"):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+@dataclass(frozen=True)
+class Mesh:
+    coords: Any
+    """(n_nodes, n_dim) float64"""
+    elements: Any
+    """(n_elements, nodes_per_element) int32"""
+
+    def _replace(self, **changes):
+        return replace(self, **changes)
+
+    def set_coords(self, new_coords):
+        return replace(self, coords=new_coords)
+
+    # -- generators ---------------------------------------------------------------------------
+    @classmethod
+    def unit_square(cls, n_x, n_y, *, type=ElementType.TRIANGLE, dim=2):
+        return cls.rectangle((0.0, 1.0), (0.0, 1.0), n_x, n_y, type=type, dim=dim)
+
+    @classmethod
+    def rectangle(cls, x, y, n_x, n_y, *, type=ElementType.TRIANGLE, dim=2):
+        """mesh.py:156-231: node id = i (n_y+1) + j; triangles [n0,n1,n3],[n0,n3,n2]; quads CCW."""
+        xv, yv = np.meshgrid(np.linspace(x[0], x[1], n_x + 1), np.linspace(y[0], y[1], n_y + 1), indexing="ij")
+        coords = np.stack([xv.ravel(), yv.ravel()], axis=-1)
+        i, j = np.meshgrid(np.arange(n_x), np.arange(n_y), indexing="ij")
+        n0 = (i * (n_y + 1) + j).ravel()
+        n1, n2, n3 = n0 + (n_y + 1), n0 + 1, n0 + (n_y + 1) + 1
+        kind = ElementType(type)
+        if kind is ElementType.TRIANGLE:
+            el = np.stack([np.stack([n0, n1, n3], -1), np.stack([n0, n3, n2], -1)], axis=1).reshape(-1, 3)
+        elif kind is ElementType.QUAD:
+            el = np.stack([n0, n1, n3, n2], -1)
+        else:
+            raise NotImplementedError(f"Element type {type} not implemented.")
+        if dim == 3:
+            coords = np.hstack([coords, np.zeros((coords.shape[0], 1))])
+        return cls(coords=coords, elements=el.astype(np.int32))
+
+    @classmethod
+    def box_tet(cls, lengths, nb_elems):
+        """6 tetrahedra per cell, as tests/test_sparse_tracer.py:29-70."""
+        (lx, ly, lz), (nx, ny, nz) = lengths, nb_elems
+        xr = np.linspace(-lx / 2, lx / 2, nx + 1)
+        yr = np.linspace(-ly / 2, ly / 2, ny + 1)
+        zr = np.linspace(0, lz, nz + 1)
+        Z, Y, X = np.meshgrid(zr, yr, xr, indexing="ij")
+        nodes = np.stack([X, Y, Z], axis=-1).reshape(-1, 3)
+        sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+        k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        n0 = (i * sx + j * sy + k * sz).ravel()
+        n1, n2 = n0 + sx, n0 + sy
+        n3, n4 = n2 + sx, n0 + sz
+        n5, n6 = n4 + sx, n4 + sy
+        n7 = n6 + sx
+        corner_sets = [(n0, n1, n3, n7), (n0, n1, n7, n5), (n0, n5, n7, n4), (n0, n3, n2, n7), (n0, n2, n6, n7), (n0, n6, n4, n7)]
+        tets = np.stack([np.stack(t, -1) for t in corner_sets], axis=1).reshape(-1, 4)
+        return cls(coords=nodes, elements=tets.astype(np.int32))
+
+    @classmethod
+    def box_hex(cls, nb_elems, lengths=None):
+        """Structured Hex8 box on [0,lx]x[0,ly]x[0,lz]; elements and nodes lexicographic, x fastest."""
+        nx, ny, nz = (nb_elems,) * 3 if np.isscalar(nb_elems) else nb_elems
+        if lengths is None:
+            m = max(nx, ny, nz)
+            lengths = (nx / m, ny / m, nz / m)
+        xr, yr, zr = (np.linspace(0.0, L, n + 1) for L, n in zip(lengths, (nx, ny, nz)))
+        Z, Y, X = np.meshgrid(zr, yr, xr, indexing="ij")
+        nodes = np.stack([X, Y, Z], axis=-1).reshape(-1, 3)
+        sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+        k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        n0 = (i * sx + j * sy + k * sz).ravel()
+        el = np.stack([n0, n0 + sx, n0 + sx + sy, n0 + sy, n0 + sz, n0 + sz + sx, n0 + sz + sx + sy, n0 + sz + sy], -1)
+        return cls(coords=nodes, elements=el.astype(np.int32))
+
+
+def extract_local_mesh(mesh_global: Mesh, element_partition, part: int) -> tuple[Mesh, PartitionInfo]:
+    """Local mesh of partition `part`, owned nodes first then ghosts (mesh.py:234-291).
+
+    A node is owned by the smallest partition id among the elements touching it (:263-265);
+    owned and ghost blocks are each ascending in global id (:258, :267-273)."""
+    elements = _np(mesh_global.elements)
+    coords = _np(mesh_global.coords)
+    element_partition = np.asarray(element_partition)
+    local_el = elements[element_partition == part]
+    present = np.unique(local_el.ravel())
+    owner = np.full(len(coords), element_partition.max() + 1, dtype=np.int32)
+    for col in range(elements.shape[1]):
+        np.minimum.at(owner, elements[:, col], element_partition)
+    mine = owner[present] == part
+    l2g = np.concatenate([present[mine], present[~mine]])
+    g2l = np.full(len(coords), -1, dtype=np.int32)
+    g2l[l2g] = np.arange(len(l2g), dtype=np.int32)
+    return (
+        Mesh(coords=coords[l2g], elements=g2l[local_el]),
+        PartitionInfo(nodes_local_to_global=l2g, n_owned_nodes=int(mine.sum())),
+    )
+
+
+def block_partition(nb_elems, nparts):
+    """Cartesian block partition of a structured box (x fastest element order): 2 -> 2x1x1,
+    4 -> 2x2x1, 8 -> 2x2x2.  Returns an int32 partition id per element."""
+    nx, ny, nz = nb_elems
+    grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(nparts)
+    if grid is None:
+        raise ValueError("nparts must be 1, 2, 4 or 8")
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    px = (i * grid[0]) // nx
+    py = (j * grid[1]) // ny
+    pz = (k * grid[2]) // nz
+    return (px + grid[0] * (py + grid[1] * pz)).ravel().astype(np.int32)

@@ -1,0 +1,358 @@
+"""Operator — the quadrature loop, mirror of tatva/operator.py on hand-written CUDA kernels.
+
+Same constructor and methods as the reference (`Operator(mesh, element, batch_size, cache_weights)`;
+`map`, `map_over_elements`, `eval`, `grad`, `integrate`, `integrate_per_element`,
+`get_integration_weights`).  Arrays are torch CUDA float64 tensors (anything torch.as_tensor accepts
+is moved to the operator's device).  Every method launches kernels of libtatva_b200.so through the
+C ABI on torch's current stream; there is no CPU path.
+
+Differentiation: the reference leaves residuals and Hessian-vector products to jax.grad / jax.jvp.
+Here `grad`, `eval`, `integrate`, the gather of `map` and the fused `energy` are torch.autograd
+Functions whose backward / forward-mode rules are the adjoint / tangent kernels, so
+`torch.autograd.grad` (and double backward for H v) work on user energies, and the fused
+`energy(material)` -> `residual(material)` -> `hvp(material)` chain is what autograd follows for the
+laws in tatva_b200.materials.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .element import Element
+from .mesh import Mesh
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Operator:
+    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None):
+        self.mesh = mesh
+        self.element = element
+        self.cache_weights = bool(cache_weights)
+        self._check_init(mesh)
+        if element.kind is None or not getattr(element, "_default_rule", True):
+            raise NotImplementedError(
+                f"{type(element).__name__} with this quadrature rule has no CUDA kernel (Tri3, Tetrahedron4, "
+                "Hexahedron8 with their default rules are supported)"
+            )
+        if not torch.cuda.is_available():
+            raise _lib.TatvaError("tatva_b200.Operator needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.coords = torch.as_tensor(_to_np_or_tensor(mesh.coords), dtype=torch.float64, device=self.device).contiguous()
+        self.elements = torch.as_tensor(_to_np_or_tensor(mesh.elements), device=self.device).to(torch.int32).contiguous()
+        self.n_nodes, self.dim = self.coords.shape
+        self.n_elements, self.npe = self.elements.shape
+        self.nq = len(element.quad_weights)
+        self.batch_size = self.n_elements if batch_size is None else int(batch_size)  # operator.py:116-117
+        self.quad_points = torch.as_tensor(element.quad_points, dtype=torch.float64, device=self.device)
+        self._L = _lib.lib()
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self._L.tatva_plan_create(
+                    C.byref(handle), element.kind, self.n_nodes, self.n_elements, self.coords.data_ptr(),
+                    self.elements.data_ptr(), _lib.PLAN_CACHE_WEIGHTS if cache_weights else 0, _stream(),
+                ),
+                "tatva_plan_create",
+            )
+        self._plan = handle
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None and getattr(self, "_L", None) is not None:
+            try:
+                self._L.tatva_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
+
+    # operator.py:132-170
+    @staticmethod
+    def _check_init(mesh):
+        coords, elements = mesh.coords, mesh.elements
+        if coords.ndim != 2:
+            raise ValueError("Mesh coordinates must be a 2D array shaped (n_nodes, n_dim).")
+        if coords.shape[0] == 0:
+            raise ValueError("Mesh must contain at least one node.")
+        if elements.ndim != 2:
+            raise ValueError("Mesh elements must be a 2D array shaped (n_elements, n_nodes_per_element).")
+        if elements.shape[0] == 0:
+            raise ValueError("Mesh must contain at least one element.")
+        el = _to_np_or_tensor(elements)
+        is_int = (not el.dtype.is_floating_point and el.dtype != torch.bool) if isinstance(el, torch.Tensor) else np.issubdtype(el.dtype, np.integer)
+        if not is_int:
+            raise TypeError("Mesh element connectivity must contain integer indices.")
+        if int(el.min()) < 0:
+            raise ValueError("Mesh element connectivity contains negative node indices.")
+        if int(el.max()) >= coords.shape[0]:
+            raise ValueError("Mesh element connectivity references nodes outside the mesh coordinates array.")
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _as_dev(self, x) -> torch.Tensor:
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        if t.dtype != torch.float64 or t.device != self.device:
+            t = t.to(device=self.device, dtype=torch.float64)
+        return t
+
+    def set_variant(self, variant: int) -> None:
+        """Select the Hex8 neo-Hookean HVP kernel variant (benchmarking aid)."""
+        _lib.check(self._L.tatva_plan_set_variant(self._plan, int(variant)), "tatva_plan_set_variant")
+
+    def _call(self, name, *args):
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(self._L, name)(self._plan, *args, _stream()), name)
+
+    # raw (non-differentiable) kernel wrappers; nodal arrays are (N, nv) contiguous
+    def _k_grad(self, u2):
+        out = torch.empty((self.n_elements, self.nq, u2.shape[1], self.dim), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_grad", u2.data_ptr(), u2.shape[1], out.data_ptr())
+        return out
+
+    def _k_grad_adj(self, g4):
+        y = torch.empty((self.n_nodes, g4.shape[2]), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_grad_adjoint", g4.data_ptr(), g4.shape[2], y.data_ptr())
+        return y
+
+    def _k_eval(self, u2):
+        out = torch.empty((self.n_elements, self.nq, u2.shape[1]), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_eval", u2.data_ptr(), u2.shape[1], out.data_ptr())
+        return out
+
+    def _k_eval_adj(self, g3):
+        y = torch.empty((self.n_nodes, g3.shape[2]), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_eval_adjoint", g3.data_ptr(), g3.shape[2], y.data_ptr())
+        return y
+
+    def _k_gather(self, u2):
+        out = torch.empty((self.n_elements, self.npe, u2.shape[1]), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_gather", u2.data_ptr(), u2.shape[1], out.data_ptr())
+        return out
+
+    def _k_gather_adj(self, g3):
+        y = torch.empty((self.n_nodes, g3.shape[2]), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_gather_adjoint", g3.data_ptr(), g3.shape[2], y.data_ptr())
+        return y
+
+    def _k_integrate_quad(self, v3):
+        out = torch.empty((self.n_elements, v3.shape[2]), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_integrate_quad", v3.data_ptr(), v3.shape[2], out.data_ptr())
+        return out
+
+    def _k_sum_rows(self, a2):
+        out = torch.empty((a2.shape[1],), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_sum_rows", a2.data_ptr(), a2.shape[0], a2.shape[1], out.data_ptr())
+        return out
+
+    # -- reference API ------------------------------------------------------------------------
+    def get_integration_weights(self) -> torch.Tensor:
+        """det(J) * w per (element, quad point) — operator.py:172-192 (no abs)."""
+        out = torch.empty((self.n_elements, self.nq), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_integration_weights", out.data_ptr())
+        return out
+
+    def grad(self, nodal_values) -> torch.Tensor:
+        """(N, *v) -> (E, Q, *v, dim) — operator.py:379-397."""
+        u = self._as_dev(nodal_values)
+        vshape = tuple(u.shape[1:])
+        out = _LinearOp.apply(u.reshape(self.n_nodes, -1), self, "grad")
+        return out.reshape((self.n_elements, self.nq) + vshape + (self.dim,))
+
+    def eval(self, nodal_values) -> torch.Tensor:
+        """(N, *v) -> (E, Q, *v) — operator.py:358-377."""
+        u = self._as_dev(nodal_values)
+        vshape = tuple(u.shape[1:])
+        out = _LinearOp.apply(u.reshape(self.n_nodes, -1), self, "eval")
+        return out.reshape((self.n_elements, self.nq) + vshape)
+
+    def integrate_per_element(self, arg) -> torch.Tensor:
+        """operator.py:321-356, with the reference's dispatch on arg.shape[0]."""
+        if isinstance(arg, (int, float)) and not isinstance(arg, bool):
+            # operator.py:335 gathers jnp.array([arg]) with clamped indices: the constant field
+            vals = torch.full((self.n_nodes,), float(arg), dtype=torch.float64, device=self.device)
+            return self.integrate_per_element(self.eval(vals))
+        a = self._as_dev(arg)
+        if a.shape[0] == self.n_elements:
+            vshape = tuple(a.shape[2:])
+            out = _LinearOp.apply(a.reshape(self.n_elements, self.nq, -1), self, "integrate")
+            return out.reshape((self.n_elements,) + vshape)
+        return self.integrate_per_element(self.eval(a))
+
+    def integrate(self, arg) -> torch.Tensor:
+        """operator.py:307-319: sum over elements of integrate_per_element."""
+        res = self.integrate_per_element(arg)
+        vshape = tuple(res.shape[1:])
+        out = _LinearOp.apply(res.reshape(self.n_elements, -1), self, "sum")
+        return out.reshape(vshape)
+
+    def _gather(self, v) -> torch.Tensor:
+        t = self._as_dev(v)
+        vshape = tuple(t.shape[1:])
+        out = _LinearOp.apply(t.reshape(self.n_nodes, -1), self, "gather")
+        return out.reshape((self.n_elements, self.npe) + vshape)
+
+    def map(self, func: Callable, *, element_quantity: Sequence[int] = ()) -> Callable:
+        """operator.py:225-266: func(xi, *element_values, **kw) at every quadrature point of every
+        element.  Nodal arguments are gathered by the CUDA gather kernel; `func` itself is user torch
+        code, vectorised with torch.vmap in chunks of `batch_size` elements."""
+
+        def _mapped(*values, **kwargs):
+            xs = tuple(self._as_dev(v) if i in element_quantity else self._gather(v) for i, v in enumerate(values))
+
+            def at_each_element(*el_values):
+                return torch.vmap(lambda xi: func(xi, *el_values, **kwargs))(self.quad_points)
+
+            return torch.vmap(at_each_element, chunk_size=self.batch_size)(*xs)
+
+        return _mapped
+
+    def map_over_elements(self, func: Callable, *, element_quantity: Sequence[int] = ()) -> Callable:
+        """operator.py:268-305."""
+
+        def _mapped(*values, **kwargs):
+            xs = tuple(self._as_dev(v) if i in element_quantity else self._gather(v) for i, v in enumerate(values))
+            return torch.vmap(lambda *el: func(*el, **kwargs), chunk_size=self.batch_size)(*xs)
+
+        return _mapped
+
+    # -- fused energy / residual / HVP -----------------------------------------------------------
+    def _fused_shape(self, material, u):
+        dpn = material.dofs_per_node(self.dim)
+        t = self._as_dev(u)
+        if t.numel() != self.n_nodes * dpn:
+            raise ValueError(f"expected {self.n_nodes}x{dpn} nodal values, got shape {tuple(t.shape)}")
+        return t, dpn
+
+    def energy(self, material) -> Callable:
+        """u -> E(u) = op.integrate(psi(op.grad(u))) in one kernel; differentiable (grad -> residual kernel,
+        second derivative -> HVP kernel)."""
+        return lambda u: _Energy.apply(self._fused_shape(material, u)[0], self, material)
+
+    def residual(self, material) -> Callable:
+        """u -> dE/du (same shape as u) = jax.grad(E)(u) of the reference."""
+        return lambda u: _Residual.apply(self._fused_shape(material, u)[0], self, material)
+
+    def hvp(self, material) -> Callable:
+        """(u, v) -> H(u) v = jax.jvp(jax.grad(E), (u,), (v,))[1] of the reference (sparse/base.py:264)."""
+
+        def _hvp(u, v):
+            return self._raw_hvp(material, self._as_dev(u), self._as_dev(v))
+
+        return _hvp
+
+    def _raw_energy(self, material, u):
+        prm, n = _lib.params_array(material.params())
+        out = torch.empty((), dtype=torch.float64, device=self.device)
+        uc = u.contiguous()
+        self._call("tatva_energy", material.material_id, prm, n, uc.data_ptr(), out.data_ptr())
+        return out
+
+    def _raw_residual(self, material, u):
+        prm, n = _lib.params_array(material.params())
+        uc = u.contiguous()
+        out = torch.empty_like(uc)
+        self._call("tatva_residual", material.material_id, prm, n, uc.data_ptr(), out.data_ptr())
+        return out
+
+    def _raw_hvp(self, material, u, v, out=None):
+        prm, n = _lib.params_array(material.params())
+        uc, vc = u.contiguous(), v.contiguous()
+        if out is None:
+            out = torch.empty_like(uc)
+        self._call("tatva_hvp", material.material_id, prm, n, uc.data_ptr(), vc.data_ptr(), out.data_ptr())
+        return out
+
+
+def _to_np_or_tensor(a):
+    return a if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
+# forward kernel / adjoint kernel of each linear building block
+_LINEAR = {
+    "grad": ("_k_grad", "_k_grad_adj"),
+    "eval": ("_k_eval", "_k_eval_adj"),
+    "gather": ("_k_gather", "_k_gather_adj"),
+}
+
+
+class _LinearOp(torch.autograd.Function):
+    """y = A x for A in {grad, eval, gather, integrate, sum}; backward is the adjoint kernel, which is
+    itself differentiable (its backward is A again), so reverse-over-reverse gives H v."""
+
+    @staticmethod
+    def forward(x, op, which):
+        x = x.contiguous()
+        if which in _LINEAR:
+            return getattr(op, _LINEAR[which][0])(x)
+        if which.endswith("_adj"):
+            return getattr(op, _LINEAR[which[:-4]][1])(x)
+        if which == "integrate":
+            return op._k_integrate_quad(x)
+        if which == "integrate_adj":  # (E, nv) -> (E, Q, nv): g[e,c] * W[e,q]
+            return x[:, None, :] * op.get_integration_weights()[:, :, None]
+        if which == "sum":
+            return op._k_sum_rows(x)
+        if which == "sum_adj":  # (nv,) -> (E, nv)
+            return x[None, :].expand(op.n_elements, -1).contiguous()
+        raise ValueError(which)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        _, ctx.op, ctx.which = inputs
+
+    @staticmethod
+    def backward(ctx, g):
+        which = ctx.which
+        adj = which[:-4] if which.endswith("_adj") else which + "_adj"
+        return _LinearOp.apply(g.contiguous(), ctx.op, adj), None, None
+
+    @staticmethod
+    def jvp(ctx, t, *_):
+        return _LinearOp.apply(t.contiguous(), ctx.op, ctx.which)
+
+
+class _Energy(torch.autograd.Function):
+    @staticmethod
+    def forward(u, op, material):
+        return op._raw_energy(material, u)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        u, ctx.op, ctx.material = inputs
+        ctx.save_for_backward(u)
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        return g * _Residual.apply(u, ctx.op, ctx.material), None, None
+
+    @staticmethod
+    def jvp(ctx, t, *_):
+        (u,) = ctx.saved_tensors
+        return (_Residual.apply(u, ctx.op, ctx.material) * t).sum()
+
+
+class _Residual(torch.autograd.Function):
+    @staticmethod
+    def forward(u, op, material):
+        return op._raw_residual(material, u)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        u, ctx.op, ctx.material = inputs
+        ctx.save_for_backward(u)
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors  # the Hessian is symmetric: J^T g = H g
+        return ctx.op._raw_hvp(ctx.material, u, g.reshape(u.shape)).reshape(u.shape), None, None
+
+    @staticmethod
+    def jvp(ctx, t, *_):
+        (u,) = ctx.saved_tensors
+        return ctx.op._raw_hvp(ctx.material, u, t.reshape(u.shape)).reshape(u.shape)

@@ -1,0 +1,209 @@
+"""GPU parity tests: CUDA kernels (through the C ABI) against the CPU oracle and the reference fixtures.
+
+Tolerance: <= 1e-12 relative (l2 and max-norm) for FP64 results, as BASELINE.json's north star states.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tatva_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.linalg.norm(b.ravel())
+    l2 = np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0)
+    mx = np.abs(a - b).max() / (np.abs(b).max() if np.abs(b).max() > 0 else 1.0)
+    return max(l2, mx)
+
+
+def _assert_close(a, b, tol=RTOL):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    assert a.shape == np.asarray(b).shape, (a.shape, np.asarray(b).shape)
+    err = _rel(a, b)
+    assert err <= tol, f"relative error {err:.3e} > {tol:.1e}"
+
+
+def _tb():
+    import tatva_b200
+    from tatva_b200 import element, materials
+
+    return tatva_b200, element, materials
+
+
+ELEMS = {"tri3": "Tri3", "tet4": "Tetrahedron4", "hex8": "Hexahedron8"}
+
+
+def _make_op(kind, coords, conn, **kw):
+    tb, element, _ = _tb()
+    return tb.Operator(tb.Mesh(coords=coords, elements=conn), getattr(element, ELEMS[kind])(), **kw)
+
+
+def _smooth_u(x):
+    if x.shape[1] == 2:
+        return 0.05 * np.stack([np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1]), np.sin(2 * np.pi * x[:, 1]) * np.cos(2 * np.pi * x[:, 0])], -1)
+    return 0.05 * np.stack(
+        [
+            np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1]),
+            np.sin(2 * np.pi * x[:, 1]) * np.cos(2 * np.pi * x[:, 2]),
+            np.sin(2 * np.pi * x[:, 2]) * np.cos(2 * np.pi * x[:, 0]),
+        ],
+        -1,
+    )
+
+
+def _case(kind, n, seed=0):
+    """Synthetic inputs of SURVEY.md §8(d): jittered structured mesh, smooth u, Gaussian v."""
+    rng = np.random.default_rng(seed)
+    if kind == "tri3":
+        c, el = orc.mesh_unit_square_tri(n, n)
+        mat = ("LinearElastic", orc.LinearElastic(*orc.lame_from_youngs_poisson_2d(1.0, 0.3)))
+    elif kind == "tet4":
+        c, el = orc.mesh_box_tet((1.0, 1.0, 1.0), (n, n, n))
+        c = c + np.array([0.5, 0.5, 0.0])
+        mat = ("NeoHookean", orc.NeoHookean(500.0, 1000.0))
+    else:
+        c, el = orc.mesh_box_hex(n)
+        mat = ("NeoHookean", orc.NeoHookean(500.0, 1000.0))
+    c = c + 0.1 * (1.0 / n) * rng.uniform(-1, 1, c.shape)
+    u = _smooth_u(c)
+    v = np.random.default_rng(1).normal(size=c.shape)
+    return c, el, u, v, mat
+
+
+def _material(name, omat):
+    _, _, materials = _tb()
+    return getattr(materials, name)(omat.mu, omat.lmbda)
+
+
+# ---- building blocks against the reference's own outputs --------------------------------------
+
+
+@pytest.mark.parametrize("kind", ["tri3", "tet4", "hex8"])
+@pytest.mark.parametrize("cache_weights", [False, True])
+def test_operator_blocks_match_reference_fixtures(golden, kind, cache_weights):
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    op = _make_op(kind, g("coords"), g("conn"), cache_weights=cache_weights)
+    _assert_close(op.grad(g("u")), g("grad_u"))
+    _assert_close(op.grad(g("s")), g("grad_s"))
+    _assert_close(op.eval(g("u")), g("eval_u"))
+    _assert_close(op.eval(g("s")), g("eval_s"))
+    _assert_close(op.get_integration_weights(), g("weights"))
+    _assert_close(op.integrate(g("s")), g("int_nodal_s"))
+    _assert_close(op.integrate_per_element(g("u")), g("int_nodal_u_per_el"))
+    _assert_close(op.integrate_per_element(g("quadvals")), g("int_quad_per_el"))
+
+
+def test_operator_known_answers():
+    """reference tests/test_operator.py:14-30, :113-143."""
+    nodes = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    el = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    op = _make_op("tri3", nodes, el)
+    _assert_close(op.eval(np.array([0.0, 1.0, 2.0, 3.0])), np.array([[1.0], [5.0 / 3.0]]), 1e-15)
+    _assert_close(op.grad(nodes @ np.array([2.0, 3.0])), np.array([[[2.0, 3.0]], [[2.0, 3.0]]]), 1e-15)
+    _assert_close(op.integrate_per_element(np.ones(4)), np.array([0.5, 0.5]), 1e-15)
+    _assert_close(op.integrate(np.ones(4)), np.array(1.0), 1e-15)
+    _assert_close(op.integrate_per_element(np.full((2, 1), 4.0)), np.array([2.0, 2.0]), 1e-15)
+    _assert_close(op.integrate(3.0), np.array(3.0), 1e-15)
+
+
+def test_map_matches_manual_loop():
+    """reference tests/test_operator.py:52-110."""
+    nodes = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    el = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    op = _make_op("tri3", nodes, el)
+    vals = np.arange(4, dtype=np.float64)
+    res = op.map(lambda xi, ev: ev.sum() + xi.sum())(vals)
+    exp = np.array([[vals[e].sum() + 2.0 / 3] for e in el])
+    _assert_close(res, exp, 1e-15)
+    bias = np.array([10.0, 20.0])
+    res = op.map(lambda xi, ev, b: ev.sum() + b + xi[0], element_quantity=(1,))(vals, bias)
+    exp = np.array([[vals[e].sum() + bias[i] + 1.0 / 3] for i, e in enumerate(el)])
+    _assert_close(res, exp, 1e-15)
+    res = op.map_over_elements(lambda ev: ev.sum())(vals)
+    _assert_close(res, np.array([vals[e].sum() for e in el]), 1e-15)
+
+
+# ---- fused energy / residual / HVP against the oracle ------------------------------------------
+
+
+@pytest.mark.parametrize("kind,n", [("tri3", 8), ("tri3", 64), ("tet4", 6), ("tet4", 12), ("hex8", 8), ("hex8", 16)])
+def test_fused_energy_residual_hvp(kind, n):
+    c, el, u, v, (mname, omat) = _case(kind, n)
+    op = _make_op(kind, c, el)
+    mat = _material(mname, omat)
+    _assert_close(op.energy(mat)(u), orc.energy(kind, omat, c, el, u))
+    _assert_close(op.residual(mat)(u), orc.residual(kind, omat, c, el, u))
+    _assert_close(op.hvp(mat)(u, v), orc.hvp(kind, omat, c, el, u, v))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_hex8_hvp_variants_agree_with_oracle(variant):
+    c, el, u, v, (mname, omat) = _case("hex8", 12)
+    op = _make_op("hex8", c, el)
+    op.set_variant(variant)
+    _assert_close(op.hvp(_material(mname, omat))(u, v), orc.hvp("hex8", omat, c, el, u, v))
+
+
+def test_hex8_linear_elastic_3d():
+    c, el, u, v, _ = _case("hex8", 6)
+    omat = orc.LinearElastic(0.7, 1.3)
+    _, _, materials = _tb()
+    mat = materials.LinearElastic(0.7, 1.3)
+    op = _make_op("hex8", c, el)
+    _assert_close(op.energy(mat)(u), orc.energy("hex8", omat, c, el, u))
+    _assert_close(op.residual(mat)(u), orc.residual("hex8", omat, c, el, u))
+    _assert_close(op.hvp(mat)(u, v), orc.hvp("hex8", omat, c, el, u, v))
+
+
+def test_hvp_is_linear_and_symmetric_at_scale():
+    """Size-independent properties on a mesh too large for the NumPy oracle (Hex8 48^3):
+    H(a v + b w) = a H v + b H w and <w, H v> = <v, H w>."""
+    c, el, u, v, (mname, omat) = _case("hex8", 48)
+    op = _make_op("hex8", c, el)
+    H = op.hvp(_material(mname, omat))
+    ut = torch.as_tensor(u, device="cuda")
+    vt = torch.as_tensor(v, device="cuda")
+    wt = torch.as_tensor(np.random.default_rng(5).normal(size=v.shape), device="cuda")
+    Hv, Hw = H(ut, vt), H(ut, wt)
+    comb = H(ut, 0.3 * vt - 1.7 * wt)
+    assert _rel(comb.cpu().numpy(), (0.3 * Hv - 1.7 * Hw).cpu().numpy()) < 1e-12
+    a, b = float((wt * Hv).sum()), float((vt * Hw).sum())
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+
+
+# ---- autograd route: user energy on the building blocks == fused kernels ------------------------
+
+
+def test_user_energy_autograd_matches_fused_kernels():
+    c, el, u, v, (mname, omat) = _case("hex8", 6)
+    op = _make_op("hex8", c, el)
+    mat = _material(mname, omat)
+    ut = torch.as_tensor(u, device="cuda").requires_grad_(True)
+    vt = torch.as_tensor(v, device="cuda")
+
+    def total_energy(uu):  # reference tests/test_sparse_tracer.py:139-144 written in torch
+        G = op.grad(uu)
+        F = torch.eye(3, dtype=G.dtype, device=G.device) + G
+        lnJ = torch.log(torch.linalg.det(F))
+        I1 = (F * F).sum(dim=(-1, -2))
+        psi = 0.5 * omat.mu * (I1 - 3 - 2 * lnJ) + 0.5 * omat.lmbda * lnJ**2
+        return op.integrate(psi)
+
+    E = total_energy(ut)
+    _assert_close(E, orc.energy("hex8", omat, c, el, u))
+    (r,) = torch.autograd.grad(E, ut, create_graph=True)
+    _assert_close(r, orc.residual("hex8", omat, c, el, u))
+    (Hv,) = torch.autograd.grad(r, ut, vt)
+    _assert_close(Hv, orc.hvp("hex8", omat, c, el, u, v), 1e-11)
+    # fused chain through autograd
+    ut2 = torch.as_tensor(u, device="cuda").requires_grad_(True)
+    E2 = op.energy(mat)(ut2)
+    (r2,) = torch.autograd.grad(E2, ut2, create_graph=True)
+    (Hv2,) = torch.autograd.grad(r2, ut2, vt)
+    _assert_close(r2, orc.residual("hex8", omat, c, el, u))
+    _assert_close(Hv2, orc.hvp("hex8", omat, c, el, u, v))
