@@ -1,0 +1,58 @@
+"""ctypes binding of oracle/_build/libtatva_oracle.so (TEST INFRASTRUCTURE ONLY, see tatva_oracle.c)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_build", "libtatva_oracle.so")
+_KIND = {"tri3": 0, "tet4": 1, "hex8": 2}
+_MAT = {"linear_elastic": 0, "neo_hookean": 1}
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_PATH):
+            subprocess.run(["make", "-s", "-C", _HERE], check=True)
+        _lib = C.CDLL(_PATH)
+        _lib.oracle_fused.restype = C.c_int
+        _lib.oracle_fused.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 5
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def num_threads() -> int:
+    return _load().oracle_num_threads()
+
+
+def _run(kind, material, mode, params, coords, conn, u, v=None):
+    L = _load()
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    vv = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+    out = np.zeros(1) if mode == 0 else np.empty_like(u)
+    rc = L.oracle_fused(
+        _KIND[kind], _MAT[material], mode, float(params[0]), float(params[1]), coords.shape[0], conn.shape[0],
+        coords.ctypes.data, conn.ctypes.data, u.ctypes.data, vv.ctypes.data if vv is not None else None, out.ctypes.data,
+    )
+    if rc != 0:
+        raise ValueError("oracle_fused: unsupported element/material")
+    return float(out[0]) if mode == 0 else out
+
+
+def energy(kind, params, coords, conn, u, material="neo_hookean"):
+    return _run(kind, material, 0, params, coords, conn, u)
+
+
+def residual(kind, params, coords, conn, u, material="neo_hookean"):
+    return _run(kind, material, 1, params, coords, conn, u)
+
+
+def hvp(kind, params, coords, conn, u, v, material="neo_hookean"):
+    return _run(kind, material, 2, params, coords, conn, u, v)

@@ -196,12 +196,200 @@ __global__ void __launch_bounds__(kBlock, MINB)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Rolled variant: the 8 Gauss points run in a loop with the signs as data.  a + t*b is one DFMA,
+// so the FP64 instruction count matches the unrolled form, but nothing is hoisted across points
+// (fewer live registers, 8x less code).  STAGE selects which modal fields live in shared memory
+// (coefficient-major, one column per thread => conflict-free LDS.64):
+//   0: none     1: X and v      2: X, v and x
+// Reciprocals of the two determinants are folded into the three scalar weights so the inverses
+// stay unscaled adjugates.
+// ---------------------------------------------------------------------------------------------
+
+// `volatile`: the staged coefficients must be re-read from shared memory at every Gauss point;
+// otherwise the compiler hoists the (loop-invariant) loads and spills them to local memory.
+template <class Ptr>
+TATVA_D void ref_grad_s(Ptr c, int stride, double tx, double ty, double tz, double (&g)[3]) {
+  const double c0 = c[0], c1 = c[stride], c2 = c[2 * stride], c3 = c[3 * stride], c4 = c[4 * stride],
+               c5 = c[5 * stride], c6 = c[6 * stride];
+  const double s36 = fma(tz, c6, c3);
+  g[0] = fma(ty, s36, fma(tz, c5, c0));
+  g[1] = fma(tx, s36, fma(tz, c4, c1));
+  g[2] = fma(tx, fma(ty, c6, c5), fma(ty, c4, c2));
+}
+
+TATVA_D void adjugate(const double (&A)[3][3], double (&C)[3][3], double& det) {
+  C[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+  C[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+  C[2][0] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+  det = A[0][0] * C[0][0] + A[0][1] * C[1][0] + A[0][2] * C[2][0];
+  C[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2];
+  C[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0];
+  C[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1];
+  C[0][2] = A[0][1] * A[1][2] - A[0][2] * A[1][1];
+  C[1][2] = A[0][2] * A[1][0] - A[0][0] * A[1][2];
+  C[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+}
+
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_hvp_rolled(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                         double lmbda, const double* __restrict__ u, const double* __restrict__ v,
+                         double* __restrict__ y) {
+  constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 2 : 3);  // staged fields
+  extern __shared__ double sm[];                               // [NS][3][7][kBlock]
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  double rX[STAGE >= 1 ? 1 : 3][7], rv[STAGE >= 1 ? 1 : 3][7], rx[STAGE >= 2 ? 1 : 3][7];
+  volatile double* sX = sm + threadIdx.x;
+  volatile double* sv = sm + 21 * kBlock + threadIdx.x;
+  volatile double* sx = sm + 42 * kBlock + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8], fv[8], mX[7], mx[7], mv[7];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal(fX, mX);
+    to_modal(fu, mx);
+    to_modal(fv, mv);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      mx[k] += mX[k];
+      if constexpr (STAGE >= 1) {
+        sX[(c * 7 + k) * kBlock] = mX[k];
+        sv[(c * 7 + k) * kBlock] = mv[k];
+      } else {
+        rX[c][k] = mX[k];
+        rv[c][k] = mv[k];
+      }
+      if constexpr (STAGE >= 2) sx[(c * 7 + k) * kBlock] = mx[k];
+      else rx[c][k] = mx[k];
+    }
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+
+#pragma unroll 1
+  for (int q = 0; q < 8; ++q) {
+    const double tx = ((q + 1) & 2) ? 1.0 : -1.0;  // q&3 in {1,2}
+    const double ty = (q & 2) ? 1.0 : -1.0;
+    const double tz = (q & 4) ? 1.0 : -1.0;
+    double J[3][3], Kc[3][3], detJ;  // J[d][c] = dX_c/dxi_d ; Kc = adj(J) = detJ * K
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double g[3];
+      if constexpr (STAGE >= 1) ref_grad_s(sX + c * 7 * kBlock, kBlock, tx, ty, tz, g);
+      else ref_grad_s((const double*)rX[c], 1, tx, ty, tz, g);
+      J[0][c] = g[0]; J[1][c] = g[1]; J[2][c] = g[2];
+    }
+    adjugate(J, Kc, detJ);
+    double M[3][3];  // detJ^2 * K^T K
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = a; b < 3; ++b) {
+        M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+        M[b][a] = M[a][b];
+      }
+    double Fr[3][3], Ac[3][3], detF;  // Ac = adj(Fr) = detF * A
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if constexpr (STAGE >= 2) ref_grad_s(sx + i * 7 * kBlock, kBlock, tx, ty, tz, Fr[i]);
+      else ref_grad_s((const double*)rx[i], 1, tx, ty, tz, Fr[i]);
+    }
+    adjugate(Fr, Ac, detF);
+    const double rJ = 1.0 / detJ, rF = 1.0 / detF;
+    const double lnJ = log(detF * rJ);
+    double Gv[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if constexpr (STAGE >= 1) ref_grad_s(sv + i * 7 * kBlock, kBlock, tx, ty, tz, Gv[i]);
+      else ref_grad_s((const double*)rv[i], 1, tx, ty, tz, Gv[i]);
+    }
+    double B[3][3];  // Ac Gv = detF * A Gv
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int f = 0; f < 3; ++f) B[d][f] = Ac[d][0] * Gv[0][f] + Ac[d][1] * Gv[1][f] + Ac[d][2] * Gv[2][f];
+    // W = detJ:  mu W Gv M/detJ^2 ; (mu - lambda lnJ) W (B Ac)^T/detF^2 ; lambda W tr(B) Ac^T/detF^2
+    const double wF = detJ * rF * rF;
+    const double w1 = mu * rJ, w2 = (mu - lmbda * lnJ) * wF, w3 = lmbda * wF * (B[0][0] + B[1][1] + B[2][2]);
+    const double tyz = ty * tz, txz = tx * tz, txy = tx * ty;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double qv[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double t1 = Gv[i][0] * M[0][d] + Gv[i][1] * M[1][d] + Gv[i][2] * M[2][d];
+        const double t2 = B[d][0] * Ac[0][i] + B[d][1] * Ac[1][i] + B[d][2] * Ac[2][i];
+        qv[d] = w1 * t1 + w2 * t2 + w3 * Ac[d][i];
+      }
+      R[i][0] += qv[0];
+      R[i][1] += qv[1];
+      R[i][2] += qv[2];
+      R[i][3] = fma(ty, qv[0], fma(tx, qv[1], R[i][3]));
+      R[i][4] = fma(tz, qv[1], fma(ty, qv[2], R[i][4]));
+      R[i][5] = fma(tz, qv[0], fma(tx, qv[2], R[i][5]));
+      R[i][6] = fma(tyz, qv[0], fma(txz, qv[1], fma(txy, qv[2], R[i][6])));
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
+}
+
+template <int STAGE, int MINB>
+int launch_rolled(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                  cudaStream_t st) {
+  constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 2 : 3);
+  constexpr size_t smem = (size_t)NS * 21 * kBlock * sizeof(double);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_rolled<STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = true;
+  }
+  k_hex8_nh_hvp_rolled<STAGE, MINB><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu,
+                                                                               lmbda, u, v, y);
+  return TATVA_OK;
+}
+
 }  // namespace
 
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st) {
   TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
-  k_hex8_nh_hvp<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  int rc = TATVA_OK;
+  switch (p->variant) {
+    case 2: k_hex8_nh_hvp<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 3: rc = launch_rolled<0, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 4: rc = launch_rolled<1, 3>(p, mu, lmbda, u, v, y, st); break;
+    case 5: rc = launch_rolled<2, 4>(p, mu, lmbda, u, v, y, st); break;
+    case 6: rc = launch_rolled<1, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 7: rc = launch_rolled<2, 3>(p, mu, lmbda, u, v, y, st); break;
+    default: rc = launch_rolled<1, 3>(p, mu, lmbda, u, v, y, st); break;
+  }
+  if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

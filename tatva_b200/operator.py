@@ -289,7 +289,7 @@ class _LinearOp(torch.autograd.Function):
         x = x.contiguous()
         if which in _LINEAR:
             return getattr(op, _LINEAR[which][0])(x)
-        if which.endswith("_adj"):
+        if which.endswith("_adj") and which[:-4] in _LINEAR:
             return getattr(op, _LINEAR[which[:-4]][1])(x)
         if which == "integrate":
             return op._k_integrate_quad(x)
