@@ -232,7 +232,7 @@ TATVA_D void adjugate(const double (&A)[3][3], double (&C)[3][3], double& det) {
   C[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
 }
 
-template <int STAGE, int MINB>
+template <int STAGE, int MINB, int DEBUG = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_rolled(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                          double lmbda, const double* __restrict__ u, const double* __restrict__ v,
@@ -257,9 +257,15 @@ __global__ void __launch_bounds__(kBlock, MINB)
     double fX[8], fu[8], fv[8], mX[7], mx[7], mv[7];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
-      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
-      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+      if constexpr (DEBUG == 2) {  // timing experiment: no gather
+        fX[n] = Hex8::sgn(n, c) * 0.01 + 1e-9 * nd[n];
+        fu[n] = 1e-4 * (n + c) + 1e-10 * nd[n];
+        fv[n] = 1e-3 * (n - c) + 1e-9 * nd[n];
+      } else {
+        fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+        fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+        fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+      }
     }
     to_modal(fX, mX);
     to_modal(fu, mx);
@@ -349,6 +355,18 @@ __global__ void __launch_bounds__(kBlock, MINB)
     }
   }
 
+  if constexpr (DEBUG == 1) {  // timing experiment: no scatter
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double f[8];
+      from_modal(R[i], f);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) s += f[n] * (n + 1 + i);
+    }
+    y[e] = s;
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     double f[8];
@@ -358,18 +376,18 @@ __global__ void __launch_bounds__(kBlock, MINB)
   }
 }
 
-template <int STAGE, int MINB>
+template <int STAGE, int MINB, int DEBUG = 0>
 int launch_rolled(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                   cudaStream_t st) {
   constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 2 : 3);
   constexpr size_t smem = (size_t)NS * 21 * kBlock * sizeof(double);
   static bool configured = false;
   if (!configured && smem > 48 * 1024) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_rolled<STAGE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     configured = true;
   }
-  k_hex8_nh_hvp_rolled<STAGE, MINB><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu,
+  k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu,
                                                                                lmbda, u, v, y);
   return TATVA_OK;
 }
@@ -387,7 +405,11 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 5: rc = launch_rolled<2, 4>(p, mu, lmbda, u, v, y, st); break;
     case 6: rc = launch_rolled<1, 2>(p, mu, lmbda, u, v, y, st); break;
     case 7: rc = launch_rolled<2, 3>(p, mu, lmbda, u, v, y, st); break;
-    default: rc = launch_rolled<1, 3>(p, mu, lmbda, u, v, y, st); break;
+    case 8: rc = launch_rolled<0, 2, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 9: rc = launch_rolled<0, 2, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 10: rc = launch_rolled<2, 4, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 11: rc = launch_rolled<2, 4, 2>(p, mu, lmbda, u, v, y, st); break;
+    default: rc = launch_rolled<0, 2>(p, mu, lmbda, u, v, y, st); break;
   }
   if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();

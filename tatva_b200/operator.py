@@ -233,9 +233,10 @@ class Operator:
         second derivative -> HVP kernel)."""
         return lambda u: _Energy.apply(self._fused_shape(material, u)[0], self, material)
 
-    def residual(self, material) -> Callable:
-        """u -> dE/du (same shape as u) = jax.grad(E)(u) of the reference."""
-        return lambda u: _Residual.apply(self._fused_shape(material, u)[0], self, material)
+    def residual(self, material) -> "FusedResidual":
+        """u -> dE/du (same shape as u) = jax.grad(E)(u) of the reference.  The returned callable is
+        recognised by tatva_b200.sparse.jacfwd, which then assembles dR/du with one kernel."""
+        return FusedResidual(self, material)
 
     def hvp(self, material) -> Callable:
         """(u, v) -> H(u) v = jax.jvp(jax.grad(E), (u,), (v,))[1] of the reference (sparse/base.py:264)."""
@@ -266,6 +267,16 @@ class Operator:
             out = torch.empty_like(uc)
         self._call("tatva_hvp", material.material_id, prm, n, uc.data_ptr(), vc.data_ptr(), out.data_ptr())
         return out
+
+
+class FusedResidual:
+    """Callable u -> r(u) backed by the fused residual kernel (differentiable: its JVP / VJP is the HVP kernel)."""
+
+    def __init__(self, op: Operator, material):
+        self.op, self.material = op, material
+
+    def __call__(self, u):
+        return _Residual.apply(self.op._fused_shape(self.material, u)[0], self.op, self.material)
 
 
 def _to_np_or_tensor(a):

@@ -1,0 +1,275 @@
+"""Sparse Jacobians — mirror of tatva.sparse (tatva/sparse/base.py, _extraction.py, _coloring.py).
+
+* `pattern_from_mesh` / `pattern_from_compound`: bit-exact CSR pattern (int32, sorted columns, int8
+  ones), built by the C++ host routine `tatva_host_pattern_from_mesh`.
+* `distance2_colors`: greedy first-fit distance-2 colouring in natural DOF order (the in-tree
+  spec tatva/sparse/_coloring.py of the external `tatva-coloring` package), C++ host routine.
+* `ColoredMatrix`: same fields as the reference (data, indptr, indices, shape, colors).
+* `jacfwd` / `linearized_jacfwd`: when `fn` is a fused residual (`op.residual(material)`), the
+  Jacobian is assembled by ONE kernel that adds every element stiffness straight into the fixed
+  CSR pattern (`tatva_csr_assemble`) — no n_colors HVP sweeps, no (N, n_colors) temporary.  For any
+  other `fn` the reference algorithm is kept: one forward-mode JVP per colour with a 0/1 seed and
+  the decompression data[k] = J_c[row(k), colors[indices[k]]] (sparse/base.py:108-176, :230-270).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, replace
+from typing import Callable
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from .mesh import Mesh, _np
+
+
+def _i32p(a):
+    return a.ctypes.data_as(_lib.c_i32p)
+
+
+def pattern_arrays(elements, n_nodes: int, n_dofs_per_node: int) -> tuple[np.ndarray, np.ndarray]:
+    """(indptr, indices) int32 of the element-coupling pattern; DOF id = node * dpn + comp."""
+    conn = np.ascontiguousarray(_np(elements), dtype=np.int32)
+    n_elems, npe = conn.shape
+    n = n_nodes * n_dofs_per_node
+    indptr = np.empty(n + 1, dtype=np.int32)
+    nnz = C.c_int64()
+    L = _lib.lib()
+    _lib.check(L.tatva_host_pattern_from_mesh(_i32p(conn), n_elems, npe, n_nodes, n_dofs_per_node, _i32p(indptr), None, C.byref(nnz)), "pattern_from_mesh")
+    indices = np.empty(nnz.value, dtype=np.int32)
+    _lib.check(L.tatva_host_pattern_from_mesh(_i32p(conn), n_elems, npe, n_nodes, n_dofs_per_node, _i32p(indptr), _i32p(indices), C.byref(nnz)), "pattern_from_mesh")
+    return indptr, indices
+
+
+def pattern_from_mesh(mesh: Mesh, n_dofs_per_node: int) -> sp.csr_matrix:
+    """tatva/sparse/_extraction.py:91-102."""
+    n_nodes = mesh.coords.shape[0]
+    indptr, indices = pattern_arrays(mesh.elements, n_nodes, n_dofs_per_node)
+    n = n_nodes * n_dofs_per_node
+    return sp.csr_matrix((np.ones(indices.shape[0], dtype=np.int8), indices, indptr), shape=(n, n))
+
+
+def pattern_from_compound(compound_cls, block_wise: bool = False):
+    """tatva/sparse/_extraction.py:118-245: nodal fields coupled within elements, every other field
+    diagonal.  The all-full-Nodal stacked layout (node-interleaved, compound/__init__.py:334-389) takes the
+    fast C++ path; anything else goes through the general pair-list construction."""
+    from .compound import CompoundError, Nodal
+
+    if compound_cls._mesh is None:
+        raise CompoundError("Mesh must be set on Compound class to create sparsity pattern.")
+    mesh = compound_cls._mesh
+    n_nodes = mesh.coords.shape[0]
+    elements = _np(mesh.elements).astype(np.int64)
+    coupled, diagonal = [], []
+    for name, f in compound_cls.fields:
+        ft = f.field_type.get()
+        idx = np.asarray(f.indices(slice(None)))
+        if isinstance(ft, Nodal):
+            n_items = len(ft.node_ids) if ft.node_ids is not None else n_nodes
+            if n_items == 0:
+                continue
+            per = idx.size // n_items
+            node_dofs = np.full((n_nodes, per), -1, dtype=np.int64)
+            if ft.node_ids is None:
+                node_dofs[:] = idx.reshape(n_nodes, per)
+            else:
+                ids = np.asarray(ft.node_ids, dtype=np.int64)
+                ok = (ids >= 0) & (ids < n_nodes)
+                node_dofs[ids[ok]] = idx.reshape(-1, per)[ok]
+            coupled.append(node_dofs[elements].reshape(elements.shape[0], -1))
+        else:
+            import warnings
+
+            warnings.warn(
+                f"Custom space detected for field '{name}'. Only diagonal entries added to the sparsity pattern. "
+                "Please provide your own sparsity pattern if cross-coupling is required.",
+                UserWarning,
+            )
+            diagonal.append(idx.ravel())
+    n = compound_cls.size
+    rows, cols = [], []
+    if coupled:
+        ed = np.concatenate(coupled, axis=1)
+        w = ed.shape[1]
+        r, c = np.repeat(ed, w, axis=1).ravel(), np.tile(ed, (1, w)).ravel()
+        ok = (r >= 0) & (c >= 0)
+        rows.append(r[ok])
+        cols.append(c[ok])
+    if diagonal:
+        d = np.concatenate(diagonal)
+        rows.append(d)
+        cols.append(d)
+    if not rows:
+        full = sp.csr_matrix((n, n), dtype=np.int8)
+    else:
+        lin = np.unique(np.concatenate(rows).astype(np.int64) * n + np.concatenate(cols).astype(np.int64))
+        full = sp.csr_matrix((np.ones(lin.shape[0], dtype=np.int8), (lin // n, lin % n)), shape=(n, n))
+    if not block_wise:
+        return full
+    slices, seen = [], set()
+    for _, f in compound_cls.fields:
+        s = getattr(f, "_root_slice", getattr(f, "_slice", None))
+        if s is not None and (s.start, s.stop) not in seen:
+            slices.append(s)
+            seen.add((s.start, s.stop))
+    slices.sort(key=lambda s: s.start)
+    return [[full[a, b] for b in slices] for a in slices]
+
+
+def distance2_colors(row_ptr, col_idx, n_dofs: int) -> np.ndarray:
+    """Greedy distance-2 colouring (natural order, first fit) — tatva/sparse/_coloring.py:270-283."""
+    indptr = np.ascontiguousarray(_np(row_ptr), dtype=np.int32)
+    indices = np.ascontiguousarray(_np(col_idx), dtype=np.int32)
+    colors = np.empty(n_dofs, dtype=np.int32)
+    nc = C.c_int32()
+    _lib.check(_lib.lib().tatva_host_distance2_colors(_i32p(indptr), _i32p(indices), n_dofs, _i32p(colors), C.byref(nc)), "distance2_colors")
+    return colors
+
+
+def distance2_color_and_seeds(row_ptr, col_idx, n_dofs: int):
+    """tatva/sparse/_coloring.py:337-351: colours and the int32 0/1 seed matrix (n_colors, n_dofs)."""
+    colors = distance2_colors(row_ptr, col_idx, n_dofs)
+    seeds = (colors[None, :] == np.unique(colors)[:, None]).astype(np.int32)
+    return colors, seeds
+
+
+@dataclass(frozen=True)
+class ColoredMatrix:
+    """tatva/sparse/base.py:37-105."""
+
+    data: object
+    indptr: object
+    indices: object
+    shape: tuple
+    colors: object
+
+    @classmethod
+    def from_csr(cls, csr_matrix: sp.csr_matrix, colors=None):
+        indptr, indices = csr_matrix.indptr, csr_matrix.indices
+        if colors is None:
+            colors = distance2_colors(indptr, indices, csr_matrix.shape[0])
+        return cls(data=np.asarray(csr_matrix.data), indptr=np.asarray(indptr), indices=np.asarray(indices), shape=tuple(csr_matrix.shape), colors=np.asarray(colors))
+
+    def to_csr(self) -> sp.csr_matrix:
+        return sp.csr_matrix((_np(self.data), _np(self.indices), _np(self.indptr)), shape=self.shape)
+
+    def to_dense(self) -> np.ndarray:
+        return self.to_csr().toarray()
+
+    def _replace(self, **kw):
+        return replace(self, **kw)
+
+
+def compute_rows_cols(colored_matrix: ColoredMatrix):
+    """tatva/sparse/base.py:108-136: row index and column colour of every stored entry."""
+    indptr, indices, colors = _np(colored_matrix.indptr), _np(colored_matrix.indices), _np(colored_matrix.colors)
+    rows = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
+    return rows, colors[indices]
+
+
+class _Assembler:
+    """Direct CSR assembly plan for (operator, material, pattern): device copies of indptr and of the
+    element -> CSR position table."""
+
+    def __init__(self, op, material, colored_matrix: ColoredMatrix):
+        dpn = material.dofs_per_node(op.dim)
+        indptr = np.ascontiguousarray(_np(colored_matrix.indptr), dtype=np.int32)
+        indices = np.ascontiguousarray(_np(colored_matrix.indices), dtype=np.int32)
+        if indptr.shape[0] - 1 != op.n_nodes * dpn:
+            raise ValueError("sparsity pattern size does not match n_nodes * dofs_per_node")
+        conn = np.ascontiguousarray(op.elements.cpu().numpy(), dtype=np.int32)
+        pos = np.empty((conn.shape[0], conn.shape[1], conn.shape[1]), dtype=np.int32)
+        _lib.check(
+            _lib.lib().tatva_host_csr_element_positions(_i32p(conn), conn.shape[0], conn.shape[1], dpn, _i32p(indptr), _i32p(indices), _i32p(pos)),
+            "csr_element_positions (pattern must contain every element coupling, node-blocked)",
+        )
+        self.op, self.material, self.nnz = op, material, int(indices.shape[0])
+        self.d_indptr = torch.as_tensor(indptr, device=op.device)
+        self.d_pos = torch.as_tensor(pos, device=op.device)
+
+    def __call__(self, u, out=None) -> torch.Tensor:
+        op = self.op
+        uc = op._as_dev(u).contiguous()
+        if out is None:
+            out = torch.empty(self.nnz, dtype=torch.float64, device=op.device)
+        prm, n = _lib.params_array(self.material.params())
+        op._call("tatva_csr_assemble", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_pos.data_ptr(), self.nnz, out.data_ptr())
+        return out
+
+
+def assembler(op, material, colored_matrix: ColoredMatrix) -> Callable:
+    """u -> CSR data (nnz,) of d^2E/du^2 on the pattern of `colored_matrix` (one kernel)."""
+    return _Assembler(op, material, colored_matrix)
+
+
+def _coloured_columns(fn_jvp, u, colored_matrix, color_batch_size):
+    """Reference algorithm (sparse/base.py:230-270) without the dense (N, n_colors) temporary: each
+    colour's JVP column is decompressed straight into `data`."""
+    colors = _np(colored_matrix.colors)
+    n_colors = int(colors.max()) + 1
+    rows, col_colors = compute_rows_cols(colored_matrix)
+    dev = u.device
+    d_colors = torch.as_tensor(colors, device=dev)
+    order = np.argsort(col_colors, kind="stable")
+    bounds = np.searchsorted(col_colors[order], np.arange(n_colors + 1))
+    d_order = torch.as_tensor(order, device=dev)
+    d_rows = torch.as_tensor(rows[order], device=dev)
+    data = torch.zeros(rows.shape[0], dtype=u.dtype, device=dev)
+    for c in range(n_colors):
+        seed = (d_colors == c).to(u.dtype).reshape(u.shape)
+        col = fn_jvp(seed).reshape(-1)
+        lo, hi = int(bounds[c]), int(bounds[c + 1])
+        data[d_order[lo:hi]] = col[d_rows[lo:hi]]
+    return data
+
+
+def jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batch_size: int | None = None) -> Callable:
+    """tatva/sparse/base.py:139-176.  `fn(u, *args)` returns the residual; the result is a new
+    ColoredMatrix whose `data` holds d fn / d u on the pattern."""
+    from .operator import FusedResidual
+
+    if isinstance(fn, FusedResidual):
+        asm = _Assembler(fn.op, fn.material, colored_matrix)
+        return lambda u: replace(colored_matrix, data=asm(u))
+
+    def _wrapped(u, *args, **kwargs):
+        ut = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u), device="cuda")
+
+        def jvp(seed):
+            return torch.func.jvp(lambda x: fn(x, *args, **kwargs), (ut,), (seed,))[1]
+
+        return replace(colored_matrix, data=_coloured_columns(jvp, ut, colored_matrix, color_batch_size))
+
+    return _wrapped
+
+
+def linearized_jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batch_size: int | None = None) -> Callable:
+    """tatva/sparse/base.py:179-227: (primal, Jacobian) sharing the forward pass."""
+    from .operator import FusedResidual
+
+    if isinstance(fn, FusedResidual):
+        asm = _Assembler(fn.op, fn.material, colored_matrix)
+        return lambda u: (fn(u), replace(colored_matrix, data=asm(u)))
+
+    def _wrapped(u, *args, **kwargs):
+        ut = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u), device="cuda")
+        f = lambda x: fn(x, *args, **kwargs)  # noqa: E731
+        primal, lin = torch.func.linearize(f, ut)
+        return primal, replace(colored_matrix, data=_coloured_columns(lin, ut, colored_matrix, color_batch_size))
+
+    return _wrapped
+
+
+__all__ = [
+    "ColoredMatrix",
+    "jacfwd",
+    "linearized_jacfwd",
+    "pattern_from_mesh",
+    "pattern_from_compound",
+    "distance2_colors",
+    "distance2_color_and_seeds",
+    "assembler",
+    "compute_rows_cols",
+]

@@ -1,0 +1,218 @@
+"""Exchange / allreduce plans on 2 `gloo` ranks (CPU): known answers of the reference's
+tests/test_exchange_plan.py and tests/test_allreduce_plan.py, plus a partitioned-mesh residual whose
+assembled owned rows must equal the single-process oracle."""
+import os
+import socket
+import traceback
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from scipy.sparse import csr_matrix
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn_name, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        globals()[fn_name](rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, None))
+    except Exception:  # noqa: BLE001
+        q.put((rank, traceback.format_exc()))
+
+
+def _run(fn_name, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    errs = [f"rank {r}:\n{e}" for r, e in results if e]
+    assert not errs, "\n".join(errs)
+
+
+def _mock_state(rank, fields):
+    from tatva_b200.compound import Compound
+    from tatva_b200.mesh import Mesh, PartitionInfo
+
+    l2g = np.array([0, 1] if rank == 0 else [1, 0], dtype=np.int32)
+    info = PartitionInfo(nodes_local_to_global=l2g, n_owned_nodes=1)
+    mesh = Mesh(coords=np.zeros((2, 1)), elements=np.zeros((0, 2), dtype=np.int32))
+    ns = dict(fields)
+    return type("MyState", (Compound,), ns, mesh=mesh, partition_info=info, comm=dist.group.WORLD)
+
+
+# ---- bodies (run inside the spawned ranks) -----------------------------------------------------------
+
+
+def _body_layout(rank, world):
+    """reference tests/test_exchange_plan.py:27-94."""
+    from tatva_b200.compound import FieldType, field
+    from tatva_b200.mpi import ExchangePlan
+
+    S = _mock_state(rank, {"u": field(shape=(2, 2), field_type=FieldType.NODAL), "s": field(shape=(1,), field_type=FieldType.SHARED), "v": field(shape=(1,), field_type=FieldType.LOCAL)})
+    plan = ExchangePlan(S.get_layout(), comm=dist.group.WORLD)
+    assert plan.global_size == 7
+    if rank == 0:
+        assert (plan.local_size, plan.rstart, plan.rend) == (4, 0, 4)
+        np.testing.assert_array_equal(plan.layout.local_to_global, [0, 1, 4, 5, 2, 3])
+        np.testing.assert_array_equal(plan.layout.owned_mask, [True, True, False, False, True, True])
+    else:
+        assert (plan.local_size, plan.rstart, plan.rend) == (3, 4, 7)
+        np.testing.assert_array_equal(plan.layout.local_to_global, [4, 5, 0, 1, 2, 6])
+        np.testing.assert_array_equal(plan.layout.owned_mask, [True, True, False, False, False, True])
+
+
+def _body_communication(rank, world):
+    """reference tests/test_exchange_plan.py:97-166."""
+    from tatva_b200.compound import FieldType, field
+    from tatva_b200.mpi import ExchangePlan
+
+    S = _mock_state(rank, {"u": field(shape=(2, 1), field_type=FieldType.NODAL)})
+    plan = ExchangePlan(S.get_layout(), comm=dist.group.WORLD)
+    fwd = plan.make_scatter_fwd_set()
+    u_local = fwd(torch.tensor([10.0 if rank == 0 else 20.0], dtype=torch.float64))
+    np.testing.assert_allclose(u_local, [10.0, 20.0] if rank == 0 else [20.0, 10.0])
+    rev = plan.make_scatter_rev_add(lambda u: u * 2.0)
+    np.testing.assert_allclose(rev(u_local), [40.0] if rank == 0 else [80.0])
+
+
+def _body_incomplete_nodal(rank, world):
+    """reference tests/test_exchange_plan.py:169-245."""
+    from tatva_b200.compound import Compound, FieldSize, FieldType, Nodal, field
+    from tatva_b200.mesh import Mesh, PartitionInfo
+    from tatva_b200.mpi import ExchangePlan
+
+    if rank == 0:
+        info, subset = PartitionInfo(np.array([0, 1], dtype=np.int32), 1), np.array([0], dtype=np.int32)
+    else:
+        info, subset = PartitionInfo(np.array([1, 2], dtype=np.int32), 2), np.array([1], dtype=np.int32)
+    mesh = Mesh(coords=np.zeros((2, 1)), elements=np.zeros((0, 2), dtype=np.int32))
+
+    class MyState(Compound, mesh=mesh, partition_info=info, comm=dist.group.WORLD):
+        u = field(shape=(FieldSize.AUTO, 1), field_type=FieldType.NODAL)
+        l = field(shape=(FieldSize.AUTO, 1), field_type=Nodal(node_ids=subset))  # noqa: E741
+
+    plan = ExchangePlan(MyState.get_layout(), comm=dist.group.WORLD)
+    assert plan.global_size == 5
+    if rank == 0:
+        assert plan.local_size == 2
+        np.testing.assert_array_equal(plan.layout.local_to_global, [0, 2, 1])
+        np.testing.assert_array_equal(plan.layout.owned_mask, [True, False, True])
+    else:
+        assert plan.local_size == 3
+        np.testing.assert_array_equal(plan.layout.local_to_global, [2, 3, 4])
+        np.testing.assert_array_equal(plan.layout.owned_mask, [True, True, True])
+
+
+def _body_hessian(rank, world):
+    """reference tests/test_exchange_plan.py:248-355: assembled owned CSR data [410, 320] / [230, 140]."""
+    from dataclasses import replace
+
+    from tatva_b200.compound import FieldType, field
+    from tatva_b200.mpi import ExchangePlan
+    from tatva_b200.sparse import ColoredMatrix
+
+    S = _mock_state(rank, {"u": field(shape=(2, 1), field_type=FieldType.NODAL)})
+    indptr, indices = np.array([0, 2, 4], dtype=np.int32), np.array([0, 1, 0, 1], dtype=np.int32)
+    pattern = csr_matrix(([0.0] * 4, indices, indptr), shape=(2, 2))
+    cm = ColoredMatrix.from_csr(csr_matrix(([1.0] * 4, indices, indptr), shape=(2, 2)))
+    cm = replace(cm, data=torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64) * (10.0 if rank == 0 else 100.0))
+    plan = ExchangePlan(S.get_layout(), local_sparsity_pattern=pattern, comm=dist.group.WORLD)
+    out = plan.make_scatter_rev_add(lambda u: cm, is_hessian=True)(torch.zeros(2))
+    assert isinstance(out, ColoredMatrix) and plan.owned_nnz == 2
+    np.testing.assert_array_equal(plan.owned_csr[0], [0, 2])
+    np.testing.assert_array_equal(plan.owned_csr[1], [0, 1])
+    np.testing.assert_allclose(out.data, [410.0, 320.0] if rank == 0 else [230.0, 140.0])
+
+
+def _body_allreduce(rank, world):
+    """reference tests/test_allreduce_plan.py:24-129."""
+    from tatva_b200.mpi import AllreducePlan
+    from tatva_b200.sparse import ColoredMatrix
+
+    plan = AllreducePlan(global_size=6, comm=dist.group.WORLD)
+    full = plan.make_allgather()(torch.ones(plan.local_size, dtype=torch.float64) * (1.0 if rank == 0 else 40.0))
+    np.testing.assert_allclose(full, [1.0, 1.0, 1.0, 40.0, 40.0, 40.0])
+    u = torch.tensor([0.0, 1.0, 2.0, 3.0, 0.0, 0.0] if rank == 0 else [0.0, 0.0, 0.25, 0.25, 4.0, 5.0], dtype=torch.float64)
+    res = plan.make_allreduce_owned(lambda x: x)(u)
+    np.testing.assert_allclose(res, [0.0, 1.0, 2.25] if rank == 0 else [3.25, 4.0, 5.0])
+
+    indptr, indices = np.array([0, 1, 2, 3, 4, 5]), np.array([0, 1, 2, 3, 4])
+    pattern = csr_matrix((np.ones_like(indices), indices, indptr), shape=(5, 5))
+    vals = [1.0, 1.0, 1.0, 1.0, 0.0] if rank == 0 else [0.0, 0.0, 0.0, 1.0, 1.0]
+    cm = ColoredMatrix.from_csr(csr_matrix((vals, indices, indptr), shape=(5, 5)))
+    plan = AllreducePlan(global_size=5, global_sparsity_pattern=pattern, comm=dist.group.WORLD)
+    out = plan.make_allreduce_owned(lambda x: cm, is_hessian=True)(torch.zeros(6))
+    if rank == 0:
+        np.testing.assert_allclose(out.data, [1.0, 1.0, 1.0])
+        np.testing.assert_array_equal(out.indices, [0, 1, 2])
+        np.testing.assert_array_equal(out.indptr, [0, 1, 2, 3])
+    else:
+        np.testing.assert_allclose(out.data, [2.0, 1.0])
+        np.testing.assert_array_equal(out.indices, [3, 4])
+        np.testing.assert_array_equal(out.indptr, [0, 1, 2])
+
+
+def _body_partitioned_residual(rank, world):
+    """Hex8 box split in two: owned rows of scatter_rev_add(local oracle residual)(scatter_fwd(x)) equal
+    the single-process oracle residual in the plan's global numbering."""
+    from oracle import tatva_oracle as orc
+    from tatva_b200.compound import Compound, FieldSize, field
+    from tatva_b200.mesh import Mesh, extract_local_mesh
+    from tatva_b200.mpi import ExchangePlan
+
+    c, el = orc.mesh_box_hex((4, 3, 2))
+    c = c + 0.02 * np.random.default_rng(0).uniform(-1, 1, c.shape)
+    u = 0.02 * np.random.default_rng(1).normal(size=c.shape)
+    mat = orc.NeoHookean(500.0, 1000.0)
+    part = (c[el].mean(axis=1)[:, 0] > c[:, 0].mean()).astype(np.int32)
+    lm, info = extract_local_mesh(Mesh(coords=c, elements=el), part, rank)
+
+    class S(Compound, mesh=lm, partition_info=info, comm=dist.group.WORLD):
+        u = field(shape=(FieldSize.AUTO, 3))
+
+    plan = ExchangePlan(S.get_layout(), comm=dist.group.WORLD)
+    l2g_nodes = info.nodes_local_to_global
+    x_owned = torch.as_tensor(u[l2g_nodes[: info.n_owned_nodes]].ravel())
+    u_local = plan.make_scatter_fwd_set()(x_owned)
+    np.testing.assert_array_equal(u_local.numpy().reshape(-1, 3), u[l2g_nodes])
+    local_res = lambda ul: torch.as_tensor(orc.residual("hex8", mat, lm.coords, lm.elements, ul.numpy().reshape(-1, 3)).ravel())  # noqa: E731
+    r_owned = plan.make_scatter_rev_add(local_res)(u_local)
+    r_ref = orc.residual("hex8", mat, c, el, u)[l2g_nodes[: info.n_owned_nodes]].ravel()
+    np.testing.assert_allclose(r_owned.numpy(), r_ref, rtol=1e-12, atol=1e-12 * np.abs(r_ref).max())
+    assert plan.global_size == c.size
+
+
+# ---- pytest entry points -----------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize(
+    "body",
+    ["_body_layout", "_body_communication", "_body_incomplete_nodal", "_body_hessian", "_body_allreduce", "_body_partitioned_residual"],
+)
+def test_two_rank_gloo(body):
+    _run(body, world=2)
+
+
+def test_dof_range_and_single_process_plan():
+    from tatva_b200.mpi import AllreducePlan, _dof_range
+
+    assert [_dof_range(7, 3, r) for r in range(3)] == [(0, 3), (3, 5), (5, 7)]
+    plan = AllreducePlan(global_size=4)
+    assert (plan.rstart, plan.rend, plan.local_size) == (0, 4, 4)
+    np.testing.assert_allclose(plan.make_allreduce_owned(lambda x: x * 3)(torch.arange(4.0)), [0, 3, 6, 9])

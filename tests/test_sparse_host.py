@@ -1,0 +1,90 @@
+"""Host-side (C++) pattern, colouring and CSR position map: bit-exact against reference fixtures."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import tatva_oracle as orc
+from tatva_b200 import _lib, sparse
+from tatva_b200.mesh import Mesh
+
+
+def test_library_exports_every_declared_symbol():
+    import re, os
+
+    L = _lib.lib()
+    hdr = open(os.path.join(os.path.dirname(_lib.__file__), "..", "include", "tatva_b200.h")).read()
+    declared = set(re.findall(r"\b(tatva_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.tatva_abi_version() == 1
+
+
+@pytest.mark.parametrize("name,dpn", [("tri3_8x8_d2", 2), ("tet4_3_d3", 3), ("tet4_2_d4", 4), ("hex8_3_d3", 3)])
+def test_pattern_and_colours_bit_exact_with_reference(golden, name, dpn):
+    conn, n_nodes = golden[f"sp_{name}_conn"], int(golden[f"sp_{name}_nnodes"])
+    mesh = Mesh(coords=np.zeros((n_nodes, 3)), elements=conn)
+    pat = sparse.pattern_from_mesh(mesh, dpn)
+    assert pat.indptr.dtype == np.int32 and pat.indices.dtype == np.int32 and pat.data.dtype == np.int8
+    np.testing.assert_array_equal(pat.indptr, golden[f"sp_{name}_indptr"])
+    np.testing.assert_array_equal(pat.indices, golden[f"sp_{name}_indices"])
+    colors = sparse.distance2_colors(pat.indptr, pat.indices, pat.shape[0])
+    assert colors.dtype == np.int32
+    np.testing.assert_array_equal(colors, golden[f"sp_{name}_colors"])
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    np.testing.assert_array_equal(cm.colors, golden[f"sp_{name}_colors"])
+
+
+def test_colouring_is_valid_distance2_on_general_pattern():
+    """Ragged pattern with an isolated row: columns sharing a row must get different colours."""
+    rng = np.random.default_rng(0)
+    A = sps.random(60, 60, density=0.06, random_state=1, format="csr")
+    A = ((A + A.T + sps.eye(60)) != 0).astype(np.int8).tolil()
+    A[7, :] = 0
+    A[:, 7] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    colors = sparse.distance2_colors(A.indptr, A.indices, 60)
+    np.testing.assert_array_equal(colors, orc.distance2_colors(A.indptr.astype(np.int32), A.indices.astype(np.int32), 60))
+    for i in range(60):
+        cols = A.indices[A.indptr[i] : A.indptr[i + 1]]
+        assert len(set(colors[cols])) == len(cols)
+
+
+def test_pattern_with_unreferenced_nodes_and_repeated_elements():
+    conn = np.array([[0, 1, 2], [0, 1, 2], [2, 3, 5]], dtype=np.int32)  # node 4 unused, element repeated
+    ip, ix = sparse.pattern_arrays(conn, 6, 2)
+    rp, rx = orc.pattern_from_mesh(conn, 6, 2)
+    np.testing.assert_array_equal(ip, rp)
+    np.testing.assert_array_equal(ix, rx)
+    assert ip[9] == ip[8] == ip[10]  # rows of node 4 are empty
+
+
+def test_csr_element_positions():
+    c, el = orc.mesh_box_tet((1, 1, 1), (2, 2, 2))
+    dpn = 3
+    ip, ix = sparse.pattern_arrays(el, len(c), dpn)
+    pos = np.empty((el.shape[0], 4, 4), dtype=np.int32)
+    rc = _lib.lib().tatva_host_csr_element_positions(
+        el.ctypes.data_as(_lib.c_i32p), el.shape[0], 4, dpn, ip.ctypes.data_as(_lib.c_i32p), ix.ctypes.data_as(_lib.c_i32p), pos.ctypes.data_as(_lib.c_i32p)
+    )
+    assert rc == 0
+    for e in (0, 5, el.shape[0] - 1):
+        for a in range(4):
+            for b in range(4):
+                row = el[e, a] * dpn
+                assert ix[ip[row] + pos[e, a, b]] == el[e, b] * dpn
+                assert ix[ip[row + 2] + pos[e, a, b] + 2] == el[e, b] * dpn + 2
+
+
+def test_invalid_arguments_return_error_codes():
+    L = _lib.lib()
+    nnz = C.c_int64()
+    bad = np.array([[0, 1, 9]], dtype=np.int32)
+    ip = np.zeros(7, dtype=np.int32)
+    assert L.tatva_host_pattern_from_mesh(bad.ctypes.data_as(_lib.c_i32p), 1, 3, 3, 2, ip.ctypes.data_as(_lib.c_i32p), None, C.byref(nnz)) == -1
+    assert L.tatva_error_string(-1) == b"invalid argument"
+    assert L.tatva_plan_destroy(None) == 0
