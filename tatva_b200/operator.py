@@ -336,6 +336,7 @@ class _Energy(torch.autograd.Function):
     def setup_context(ctx, inputs, output):
         u, ctx.op, ctx.material = inputs
         ctx.save_for_backward(u)
+        ctx.save_for_forward(u)
 
     @staticmethod
     def backward(ctx, g):
@@ -357,6 +358,7 @@ class _Residual(torch.autograd.Function):
     def setup_context(ctx, inputs, output):
         u, ctx.op, ctx.material = inputs
         ctx.save_for_backward(u)
+        ctx.save_for_forward(u)
 
     @staticmethod
     def backward(ctx, g):

@@ -225,6 +225,20 @@ def _coloured_columns(fn_jvp, u, colored_matrix, color_batch_size):
     return data
 
 
+def _forward_mode(f, u):
+    """seed -> J(u) seed with torch's forward-mode AD (dual tensors) — the jax.jvp of sparse/base.py:264.
+    The kernels' autograd Functions implement `jvp`, so this dispatches to the tangent (HVP) kernels."""
+    import torch.autograd.forward_ad as fwAD
+
+    def jvp(seed):
+        with fwAD.dual_level():
+            out = f(fwAD.make_dual(u, seed))
+            tangent = fwAD.unpack_dual(out).tangent
+            return torch.zeros_like(out) if tangent is None else tangent.clone()
+
+    return jvp
+
+
 def jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batch_size: int | None = None) -> Callable:
     """tatva/sparse/base.py:139-176.  `fn(u, *args)` returns the residual; the result is a new
     ColoredMatrix whose `data` holds d fn / d u on the pattern."""
@@ -237,9 +251,7 @@ def jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batch_size: int
     def _wrapped(u, *args, **kwargs):
         ut = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u), device="cuda")
 
-        def jvp(seed):
-            return torch.func.jvp(lambda x: fn(x, *args, **kwargs), (ut,), (seed,))[1]
-
+        jvp = _forward_mode(lambda x: fn(x, *args, **kwargs), ut)
         return replace(colored_matrix, data=_coloured_columns(jvp, ut, colored_matrix, color_batch_size))
 
     return _wrapped
@@ -256,8 +268,11 @@ def linearized_jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batc
     def _wrapped(u, *args, **kwargs):
         ut = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u), device="cuda")
         f = lambda x: fn(x, *args, **kwargs)  # noqa: E731
-        primal, lin = torch.func.linearize(f, ut)
-        return primal, replace(colored_matrix, data=_coloured_columns(lin, ut, colored_matrix, color_batch_size))
+        # torch.func.linearize traces with fake tensors, which cannot pass through the C-ABI kernels;
+        # the primal is evaluated once and each colour is a forward-mode JVP.
+        primal = f(ut)
+        jvp = _forward_mode(f, ut)
+        return primal, replace(colored_matrix, data=_coloured_columns(jvp, ut, colored_matrix, color_batch_size))
 
     return _wrapped
 
