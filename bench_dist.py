@@ -1,4 +1,9 @@
-"""Problem set-up for bench.py: the per-GPU Hex8 block, its device buffers and the timed step."""
+"""Problem set-up for bench.py: the per-GPU Hex8 block, its device buffers and the timed step.
+
+N = 1: the whole 128^3 mesh on one GPU.  N = 2/4/8: weak scaling, one n^3 block per GPU of a
+(2n x n x n) / (2n x 2n x n) / (2n)^3 box (config 4 at N = 8, n = 128), partitioned with the reference's
+ownership rules and exchanged through tatva_b200.distributed.PartitionedOperator (NCCL over NVLink).
+"""
 from __future__ import annotations
 
 import ctypes as C
@@ -8,45 +13,81 @@ import torch
 
 import tatva_b200
 from tatva_b200 import _lib, element
+from tatva_b200.distributed import PartitionedOperator, structured_hex_block
+
+GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def smooth_u(c):
+    two_pi = 2 * np.pi
+    return 0.05 * np.stack(
+        [np.sin(two_pi * c[:, 0]) * np.cos(two_pi * c[:, 1]), np.sin(two_pi * c[:, 1]) * np.cos(two_pi * c[:, 2]), np.sin(two_pi * c[:, 2]) * np.cos(two_pi * c[:, 0])], -1
+    )
 
 
 class DistributedHex8Problem:
-    def __init__(self, n, rank, world, device, material, variant=0):
+    def __init__(self, n, rank, world, device, material, variant=0, overlap=True):
         from bench import synthetic_inputs
 
         self.rank, self.world, self.device, self.material = rank, world, device, material
-        if world > 1:
-            raise NotImplementedError("multi-GPU decomposition is wired in bench_dist.py in a later commit")
-        c, el, u, v = synthetic_inputs(n, rank)
-        self.op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8(), device=device)
+        if world == 1:
+            c, el, u, v = synthetic_inputs(n, rank)
+            self.op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8(), device=device)
+            self.pop = None
+            self.n_dofs_global = 3 * c.shape[0]
+            self.partition_desc = "1 GPU, whole mesh"
+            n_owned = u.size
+            self.launches_per_step = 1
+        else:
+            grid = GRID[world]
+            mesh, info = structured_hex_block(n, grid, rank)
+            c, el = mesh.coords, mesh.elements
+            self.pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=overlap)
+            self.op = self.pop.op
+            u = smooth_u(c)  # ghost values consistent by construction (function of the shared coordinates)
+            v = np.random.default_rng(1 + rank).normal(size=c.shape)
+            self.n_dofs_global = self.pop.n_global
+            self.partition_desc = f"{world} GPUs, {grid[0]}x{grid[1]}x{grid[2]} blocks of {n}^3, NCCL halo exchange ({'overlapped' if overlap else 'serial'})"
+            n_owned = self.pop.n_owned
+            self.launches_per_step = 6  # pack, unpack-set, boundary + interior element kernels, pack, unpack-add
         if variant:
             self.op.set_variant(variant)
         self.local_nodes, self.local_elems = c.shape[0], el.shape[0]
-        self.n_dofs_global = 3 * c.shape[0]
-        self.partition_desc = "1 GPU, whole mesh"
-        self.u = torch.as_tensor(u, device=device)
-        self.v = torch.as_tensor(v, device=device)
+        self.u = torch.as_tensor(u, device=device).reshape(-1)
+        self.v = torch.as_tensor(v, device=device).reshape(-1)
         self.y = torch.empty_like(self.u)
-        # host-side pinned buffers for the end-to-end leg
-        self.h_u = torch.as_tensor(u).pin_memory()
-        self.h_v = torch.as_tensor(v).pin_memory()
-        self.h_y = torch.empty_like(self.h_u).pin_memory()
-        self.h2d_bytes = self.h_u.numel() * 8 * 2
-        self.d2h_bytes = self.h_y.numel() * 8
-        self.launches_per_step = 1
+        self.n_owned = n_owned
+        # host-side pinned buffers for the end-to-end leg (owned entries only)
+        self.h_u = torch.as_tensor(u).reshape(-1)[:n_owned].clone().pin_memory()
+        self.h_v = torch.as_tensor(v).reshape(-1)[:n_owned].clone().pin_memory()
+        self.h_y = torch.empty(n_owned, dtype=torch.float64).pin_memory()
+        self.h2d_bytes = n_owned * 8 * 2
+        self.d2h_bytes = n_owned * 8
+        if self.pop is not None:
+            self.pop.fill_ghosts(self.u)
+            self.pop.fill_ghosts(self.v)
 
     def step(self):
-        self.op._raw_hvp(self.material, self.u, self.v, out=self.y)
+        if self.pop is None:
+            self.op._raw_hvp(self.material, self.u, self.v, out=self.y)
+        else:
+            self.pop.hvp(self.u, self.v, self.y)
 
     def step_e2e(self):
-        """Public-API call with host buffers: H2D of u and v, HVP, D2H of y."""
-        u = self.h_u.to(self.device, non_blocking=True)
-        v = self.h_v.to(self.device, non_blocking=True)
-        y = self.op.hvp(self.material)(u, v)
-        self.h_y.copy_(y, non_blocking=True)
+        """Public-API call with host buffers: H2D of the owned u and v, (halo exchange +) HVP, D2H of owned y."""
+        n = self.n_owned
+        self.u[:n].copy_(self.h_u, non_blocking=True)
+        self.v[:n].copy_(self.h_v, non_blocking=True)
+        if self.pop is None:
+            y = self.op.hvp(self.material)(self.u.view(-1, 3), self.v.view(-1, 3)).reshape(-1)
+        else:
+            self.pop.fill_ghosts(self.u)
+            y = self.pop.hvp(self.u, self.v, self.y)
+        self.h_y.copy_(y[:n], non_blocking=True)
 
     def time_kernel_only(self, reps):
-        """Average duration of one HVP call (memset + element kernel) on the launching stream."""
+        """Average duration of the element kernel over the rank's whole local mesh (memset included),
+        CUDA events on the launching stream, no exchange."""
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

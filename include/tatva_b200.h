@@ -117,6 +117,17 @@ int tatva_residual(tatva_plan_t* plan, int material, const double* params, int n
 int tatva_hvp(tatva_plan_t* plan, int material, const double* params, int n_params,
               const double* d_u, const double* d_v, double* d_y, tatva_stream_t stream);
 
+/* Element sub-range variants: only elements [elem_begin, elem_begin + elem_count) contribute, and the
+ * output is zeroed first only if zero_out != 0.  They let the caller run the elements that touch ghost
+ * nodes and the interior elements on different streams, so the halo exchange of tatva/mpi.py:372-409,
+ * :479-516 overlaps the interior quadrature loop.                                                    */
+int tatva_hvp_elems(tatva_plan_t* plan, int material, const double* params, int n_params,
+                    const double* d_u, const double* d_v, double* d_y, int64_t elem_begin,
+                    int64_t elem_count, int zero_out, tatva_stream_t stream);
+int tatva_residual_elems(tatva_plan_t* plan, int material, const double* params, int n_params,
+                         const double* d_u, double* d_r, int64_t elem_begin, int64_t elem_count,
+                         int zero_out, tatva_stream_t stream);
+
 /* ---- coloured sparse Jacobian -> direct assembly into a fixed CSR pattern ---------------
  * Replaces sparse.jacfwd / colored_jacobian_batch / compute_rows_cols
  * (tatva/sparse/base.py:139-176, :230-270, :108-136): instead of n_colors HVPs and an

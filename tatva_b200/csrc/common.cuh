@@ -357,6 +357,7 @@ struct tatva_plan {
   const int32_t* conn;   // caller-owned device view (n_elems, npe)
   int flags;
   int variant;
+  int zero_output;  // scatter-add entry points zero their output first (1) or accumulate (0)
   double* scratch;  // plan-owned: energy partials / row-sum partials
   int64_t scratch_len;
   double* weights;  // plan-owned (n_elems, nq) when TATVA_PLAN_CACHE_WEIGHTS

@@ -503,6 +503,7 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->conn = d_conn;
   p->flags = flags;
   p->variant = TATVA_VARIANT_DEFAULT;
+  p->zero_output = 1;
   p->weights = nullptr;
   p->scratch_len = (int64_t)grid_for(n_elems) > 1024 * 64 ? (int64_t)grid_for(n_elems) : 1024 * 64;
   cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
@@ -640,7 +641,7 @@ static int launch_fused(tatva_plan* p, const Mat& mat, const double* u, const do
     k_fused<El, Mat, MODE><<<grid, kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, nullptr, p->scratch);
     k_sum_rows_final<<<1, 256, 0, st>>>(p->scratch, grid, 1, out);
   } else {
-    TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
+    if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
     k_fused<El, Mat, MODE><<<grid, kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, nullptr);
   }
   TATVA_LAUNCH_CHECK();
@@ -691,6 +692,44 @@ int tatva_hvp(tatva_plan_t* p, int material, const double* params, int n_params,
   return dispatch_fused<MODE_HVP>(p, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
+extern "C" {
+// Element sub-range variants (overlap of halo exchange with interior elements): elements
+// [elem_begin, elem_begin + elem_count) only; y is zeroed first iff zero_y != 0.
+int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,
+                    const double* d_v, double* d_y, int64_t elem_begin, int64_t elem_count, int zero_y,
+                    tatva_stream_t stream) {
+  if (!p || elem_begin < 0 || elem_count < 0 || elem_begin + elem_count > p->n_elems) return TATVA_E_INVALID;
+  if (elem_count == 0) {
+    if (zero_y) {
+      int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+      TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * dpn, (cudaStream_t)stream));
+    }
+    return TATVA_OK;
+  }
+  tatva_plan sub = *p;
+  sub.conn = p->conn + elem_begin * p->npe;
+  sub.n_elems = elem_count;
+  sub.zero_output = zero_y ? 1 : 0;
+  return dispatch_fused<MODE_HVP>(&sub, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
+}
+int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,
+                         double* d_r, int64_t elem_begin, int64_t elem_count, int zero_r, tatva_stream_t stream) {
+  if (!p || elem_begin < 0 || elem_count < 0 || elem_begin + elem_count > p->n_elems) return TATVA_E_INVALID;
+  if (elem_count == 0) {
+    if (zero_r) {
+      int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+      TATVA_CUDA_TRY(cudaMemsetAsync(d_r, 0, sizeof(double) * p->n_nodes * dpn, (cudaStream_t)stream));
+    }
+    return TATVA_OK;
+  }
+  tatva_plan sub = *p;
+  sub.conn = p->conn + elem_begin * p->npe;
+  sub.n_elems = elem_count;
+  sub.zero_output = zero_r ? 1 : 0;
+  return dispatch_fused<MODE_RESIDUAL>(&sub, material, params, n_params, d_u, nullptr, d_r, (cudaStream_t)stream);
+}
 }  // extern "C"
 
 template <class El, class Mat>

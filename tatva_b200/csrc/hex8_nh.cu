@@ -396,7 +396,7 @@ int launch_rolled(const tatva_plan* p, double mu, double lmbda, const double* u,
 
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st) {
-  TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   int rc = TATVA_OK;
   switch (p->variant) {
     case 2: k_hex8_nh_hvp<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;

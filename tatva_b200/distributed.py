@@ -1,0 +1,176 @@
+"""Element-partitioned operator: one mesh partition per GPU, halo exchange overlapped with the
+interior quadrature loop.
+
+This is the B200 form of the reference's distributed call stack (tatva/mpi.py:372-409, :479-516):
+
+    x_owned --scatter_fwd--> u_local --local_fn (HVP over the rank's mesh)--> y_local --scatter_rev_add--> y_owned
+
+with the reference's ownership and numbering rules (`extract_local_mesh`, mesh.py:234-291; owned nodes
+first, so the owned block of a local vector IS the owned vector — no copy).  Per application:
+
+    compute stream:  zero y_local ........ interior elements (touch no ghost node) ...................|
+    comm stream:     pack owned v -> all_to_all (NVLink) -> ghost v | boundary elements | pack ghost y |
+                     -> all_to_all -> atomic add into owned y ........................................|
+
+Both element kernels and the unpack-add accumulate into y_local with FP64 atomics, so they may run
+concurrently; the two streams join at the end.  Only the halo (a few hundred kB per face at 128^3 per
+GPU) crosses NVLink; there is no other data-path collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .compound import Compound, FieldSize, field
+from .mesh import Mesh, PartitionInfo
+from .mpi import ExchangePlan, _as_comm
+from .operator import Operator
+
+
+def structured_hex_block(n, grid, rank, lengths=None, jitter=0.1, seed=0):
+    """Local mesh of block `rank` of a (gx*n) x (gy*n) x (gz*n) Hex8 box split into gx x gy x gz blocks
+    of n^3 elements (partition id = px + gx (py + gy pz)), WITHOUT materialising the global mesh.
+
+    Returns (Mesh, PartitionInfo) identical to `extract_local_mesh(global_mesh, block_partition, rank)`:
+    nodes owned by the smallest touching partition id, owned nodes first, each group ascending in global
+    node id (mesh.py:258-273); elements in global (x-fastest) order.  Coordinates carry the same
+    deterministic jitter a global generator would apply (hash of the global node id)."""
+    gx, gy, gz = grid
+    px, py, pz = rank % gx, (rank // gx) % gy, rank // (gx * gy)
+    NX, NY, NZ = gx * n, gy * n, gz * n
+    i0, j0, k0 = px * n, py * n, pz * n
+    ii, jj, kk = np.arange(i0, i0 + n + 1), np.arange(j0, j0 + n + 1), np.arange(k0, k0 + n + 1)
+    K, J, I = np.meshgrid(kk, jj, ii, indexing="ij")
+    gid = (I + (NX + 1) * (J + (NY + 1) * K)).ravel()  # ascending along the local lexicographic order
+    ghost = ((I == i0) & (px > 0)) | ((J == j0) & (py > 0)) | ((K == k0) & (pz > 0))
+    ghost = ghost.ravel()
+    order = np.concatenate([np.where(~ghost)[0], np.where(ghost)[0]])  # owned first, each ascending in gid
+    new_id = np.empty(order.size, dtype=np.int32)
+    new_id[order] = np.arange(order.size, dtype=np.int32)
+    m = max(NX, NY, NZ)
+    lengths = lengths or (NX / m, NY / m, NZ / m)
+    g = gid[order]
+    gi, gj, gk = g % (NX + 1), (g // (NX + 1)) % (NY + 1), g // ((NX + 1) * (NY + 1))
+    coords = np.stack([gi * (lengths[0] / NX), gj * (lengths[1] / NY), gk * (lengths[2] / NZ)], axis=-1).astype(np.float64)
+    if jitter:
+        coords = coords + jitter * (lengths[0] / NX) * _hash_uniform(g, seed)
+    sx, sy, sz = 1, n + 1, (n + 1) * (n + 1)
+    k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    n0 = (i * sx + j * sy + k * sz).ravel()
+    el = np.stack([n0, n0 + sx, n0 + sx + sy, n0 + sy, n0 + sz, n0 + sz + sx, n0 + sz + sx + sy, n0 + sz + sy], -1)
+    return Mesh(coords=coords, elements=new_id[el]), PartitionInfo(nodes_local_to_global=g.astype(np.int64), n_owned_nodes=int((~ghost).sum()))
+
+
+def _hash_uniform(gid, seed):
+    """Deterministic U(-1,1)^3 per global node id (same value on every rank that holds the node)."""
+    x = gid.astype(np.uint64)[:, None] * np.uint64(3) + np.arange(3, dtype=np.uint64)[None, :] + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xFF51AFD7ED558CCD)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xC4CEB9FE1A85EC53)
+    x ^= x >> np.uint64(33)
+    return (x >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+
+
+class PartitionedOperator:
+    """Operator over one partition + its ExchangePlan + the overlapped distributed HVP / residual."""
+
+    def __init__(self, local_mesh: Mesh, partition_info: PartitionInfo, element, material, comm=None, device=None, overlap=True):
+        self.comm = _as_comm(comm)
+        self.material = material
+        self.info = partition_info
+        conn = np.asarray(local_mesh.elements)
+        n_owned_nodes = int(partition_info.n_owned_nodes)
+        # boundary elements (touch a ghost node) first, interior after; stable => locality kept
+        touches_ghost = (conn >= n_owned_nodes).any(axis=1)
+        order = np.concatenate([np.where(touches_ghost)[0], np.where(~touches_ghost)[0]])
+        self.n_boundary = int(touches_ghost.sum())
+        self.mesh = Mesh(coords=local_mesh.coords, elements=conn[order])
+        self.op = Operator(self.mesh, element, device=device)
+        self.device = self.op.device
+        self.dpn = material.dofs_per_node(self.op.dim)
+        self.n_local = self.op.n_nodes * self.dpn
+        self.n_owned = n_owned_nodes * self.dpn
+
+        mesh_for_layout, dpn = self.mesh, self.dpn
+
+        class _State(Compound, mesh=mesh_for_layout, partition_info=partition_info, comm=self.comm):
+            s = field(shape=(FieldSize.AUTO, dpn))
+
+        self.plan = ExchangePlan(_State.get_layout(), comm=self.comm)
+        assert self.plan.local_size == self.n_owned
+        self.n_global = self.plan.global_size
+        self.overlap = bool(overlap) and self.comm.size > 1
+        self._comm_stream = torch.cuda.Stream(device=self.device) if self.overlap else None
+        self._prm = _lib.params_array(material.params())
+        self._L = _lib.lib()
+
+    # -- building blocks ------------------------------------------------------------------------------
+    def fill_ghosts(self, x_local: torch.Tensor) -> None:
+        """In place: ghost entries of a local vector <- owners' values (scatter_fwd_set, mpi.py:372-409)."""
+        if self.comm.size > 1:
+            self._exchange(self.plan._fwd, x_local, x_local, add=False)
+
+    def _elems(self, name, u, v, y, begin, count, zero):
+        prm, n = self._prm
+        args = (u.data_ptr(), v.data_ptr(), y.data_ptr()) if v is not None else (u.data_ptr(), y.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(self._L, name)(self.op._plan, self.material.material_id, prm, n, *args, begin, count, zero, torch.cuda.current_stream().cuda_stream), name)
+
+    def _apply(self, name, u_local, v_local, y_local):
+        E, nb = self.op.n_elements, self.n_boundary
+        if self.comm.size == 1:
+            self._elems(name, u_local, v_local, y_local, 0, E, 1)
+            return y_local
+        x = v_local if v_local is not None else u_local  # the vector whose ghosts must be refreshed
+        if not self.overlap:
+            self._exchange(self.plan._fwd, x, x, add=False)
+            self._elems(name, u_local, v_local, y_local, 0, E, 1)
+            self._exchange(self.plan._rev, y_local, y_local, add=True)
+            return y_local
+        main, side = torch.cuda.current_stream(self.device), self._comm_stream
+        y_local.zero_()
+        zeroed = torch.cuda.Event()
+        zeroed.record(main)
+        side.wait_stream(main)  # inputs are ready
+        self._elems(name, u_local, v_local, y_local, nb, E - nb, 0)  # interior, compute stream
+        with torch.cuda.stream(side):
+            self._exchange(self.plan._fwd, x, x, add=False)
+            side.wait_event(zeroed)
+            self._elems(name, u_local, v_local, y_local, 0, nb, 0)  # boundary elements
+            self._exchange(self.plan._rev, y_local, y_local, add=True)
+        main.wait_stream(side)
+        return y_local
+
+    def _exchange(self, router, src, dst, add):
+        """Neighbour part of a _Router.run.  On owned-first local vectors the self part is the identity
+        (and would double the owned rows when adding in place), so it is skipped."""
+        from .mpi import _pack, _unpack
+
+        send_idx, recv_idx, _, _ = router.tables(src.device)
+        send_buf = _pack(src, send_idx)
+        recv_buf = torch.empty(int(sum(router.recv_splits)), dtype=src.dtype, device=src.device)
+        dist.all_to_all_single(recv_buf, send_buf, router.recv_splits, router.send_splits, group=self.comm.group)
+        _unpack(dst, recv_idx, recv_buf, add)
+
+    # -- public -----------------------------------------------------------------------------------------
+    def new_local_vector(self) -> torch.Tensor:
+        return torch.zeros(self.n_local, dtype=torch.float64, device=self.device)
+
+    def owned(self, x_local: torch.Tensor) -> torch.Tensor:
+        return x_local[: self.n_owned]
+
+    def hvp(self, u_local: torch.Tensor, v_local: torch.Tensor, y_local: torch.Tensor | None = None) -> torch.Tensor:
+        """y_owned = (H(u) v)_owned.  `u_local` must already hold its ghost values (it changes once per
+        Newton step: call fill_ghosts then); the ghosts of `v_local` are refreshed here.  Returns the local
+        vector whose first n_owned entries are the assembled owned rows."""
+        if y_local is None:
+            y_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+        return self._apply("tatva_hvp_elems", u_local, v_local, y_local)
+
+    def residual(self, u_local: torch.Tensor, r_local: torch.Tensor | None = None) -> torch.Tensor:
+        if r_local is None:
+            r_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+        return self._apply("tatva_residual_elems", u_local, None, r_local)
