@@ -54,52 +54,90 @@ FLOP_PER_ELEMENT = 7944  # SURVEY.md §8(d) nominal count for the Hex8 NH HVP
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): an NVML polling
+    thread (2 ms period; the timed region can be as short as ~10 ms), nvidia-smi as a fallback."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {
+        "hw_slowdown": 0x8,
+        "sw_power_cap": 0x4,
+        "sw_thermal_slowdown": 0x20,
+        "hw_thermal_slowdown": 0x40,
+    }
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
+        self.sm, self.power, self.reasons = [], [], set()
+        self.max_mhz = None
+        self._stop = None
+        self._thread = None
+        self._nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            try:
+                return int(ids[self.gpu])
+            except (ValueError, IndexError):
+                return self.gpu
+        return self.gpu
 
     def start(self):
+        import threading
+
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
-            )
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, h)
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+            return
+        self._stop = threading.Event()
+
+        def poll():
+            nv, hh = self._nvml
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(hh, nv.NVML_CLOCK_SM)))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(hh) / 1000.0)
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hh)
+                    for name, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+                self._stop.wait(0.002)
+
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.sm:
+            return self._smi_once()
         return {
-            "sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm),
-            "reasons": sorted(reasons),
+            "sm_mhz": statistics.median(self.sm),
+            "sm_max_mhz": self.max_mhz,
+            "samples": len(self.sm),
+            "power_w_max": max(self.power) if self.power else None,
+            "reasons": sorted(self.reasons),
+            "source": "nvml, 2 ms polling during the timed region",
         }
+
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self._physical_index())], capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "samples": 1, "reasons": [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")], "source": "nvidia-smi (single sample after the timed region)"}
+        except Exception:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable"]}
 
 
 def cpu_port_baseline(n_sample, threads=None):
@@ -170,8 +208,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--n", type=int, default=128, help="cells per side of the per-GPU Hex8 block")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-n", type=int, default=48, help="cells per side of the CPU sample")

@@ -103,7 +103,8 @@ class PartitionedOperator:
         assert self.plan.local_size == self.n_owned
         self.n_global = self.plan.global_size
         self.overlap = bool(overlap) and self.comm.size > 1
-        self._comm_stream = torch.cuda.Stream(device=self.device) if self.overlap else None
+        # high priority: the small exchange / boundary kernels must not queue behind the interior grid
+        self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap else None
         self._prm = _lib.params_array(material.params())
         self._L = _lib.lib()
 
