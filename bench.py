@@ -295,6 +295,13 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (1-GPU, 128^3)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_hvp_traffic.json")))
+            if args.n == 128:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         alg_bytes = algorithmic_bytes(prob.local_nodes, prob.local_elems)
@@ -327,7 +334,7 @@ def main():
                 "peak": hbm_peak,
                 "unit": "GB/s",
                 "frac": achieved / hbm_peak,
-                "traffic": None,
+                "traffic": traffic,
                 "peak_source": peak_src,
                 "kernel": "k_hex8_nh_hvp",
                 "kernel_ms": k_ms,
