@@ -74,16 +74,43 @@ class DistributedHex8Problem:
             self.pop.hvp(self.u, self.v, self.y)
 
     def step_e2e(self):
-        """Public-API call with host buffers: H2D of the owned u and v, (halo exchange +) HVP, D2H of owned y."""
+        """Public-API call with HOST buffers, every step: H2D of the owned u and v (pinned), (halo exchange +)
+        HVP, D2H of the owned y.  Three streams and two device buffer sets pipeline consecutive steps: the
+        upload of step i+1 and the download of step i-1 overlap the kernel of step i (PCIe is full duplex)."""
+        if not hasattr(self, "_pipe"):
+            mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
+            self._pipe = dict(s_in=mk(), s_out=mk(), i=0, sets=[
+                dict(u=self.u.clone(), v=self.v.clone(), y=torch.empty_like(self.u), in_done=torch.cuda.Event(), comp_done=torch.cuda.Event(), out_done=torch.cuda.Event())
+                for _ in range(2)
+            ])
+        P = self._pipe
+        B = P["sets"][P["i"] % 2]
+        P["i"] += 1
         n = self.n_owned
-        self.u[:n].copy_(self.h_u, non_blocking=True)
-        self.v[:n].copy_(self.h_v, non_blocking=True)
+        main = torch.cuda.current_stream(self.device)
+        P["s_in"].wait_event(B["comp_done"])  # buffer set free again (no-op the first time round)
+        with torch.cuda.stream(P["s_in"]):
+            B["u"][:n].copy_(self.h_u, non_blocking=True)
+            B["v"][:n].copy_(self.h_v, non_blocking=True)
+            B["in_done"].record()
+        main.wait_event(B["in_done"])
+        main.wait_event(B["out_done"])  # previous download of this set's y finished
         if self.pop is None:
-            y = self.op.hvp(self.material)(self.u.view(-1, 3), self.v.view(-1, 3)).reshape(-1)
+            y = self.op.hvp(self.material)(B["u"].view(-1, 3), B["v"].view(-1, 3)).reshape(-1)
+            B["y_ref"] = y  # keep alive until downloaded
         else:
-            self.pop.fill_ghosts(self.u)
-            y = self.pop.hvp(self.u, self.v, self.y)
-        self.h_y.copy_(y[:n], non_blocking=True)
+            self.pop.fill_ghosts(B["u"])
+            y = self.pop.hvp(B["u"], B["v"], B["y"])
+        B["comp_done"].record(main)
+        P["s_out"].wait_event(B["comp_done"])
+        with torch.cuda.stream(P["s_out"]):
+            self.h_y.copy_(y[:n], non_blocking=True)
+            B["out_done"].record()
+
+    def e2e_finish(self):
+        """Join the download stream into the current stream (so a following event covers the last D2H)."""
+        if hasattr(self, "_pipe"):
+            torch.cuda.current_stream(self.device).wait_stream(self._pipe["s_out"])
 
     def time_kernel_only(self, reps):
         """Average duration of the element kernel over the rank's whole local mesh (memset included),

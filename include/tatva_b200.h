@@ -139,6 +139,16 @@ int tatva_csr_assemble(tatva_plan_t* plan, int material, const double* params, i
                        const double* d_u, const int32_t* d_indptr, const int32_t* d_elem_pos,
                        int64_t nnz, double* d_data, tatva_stream_t stream);
 
+/* Same matrix, assembled BY ROWS without atomics (deterministic): one warp owns the CSR rows of one node,
+ * computes the columns (a,i) of the stiffness of every incident element (= the rows, by symmetry of the
+ * energy Hessian) and stores each dpn x dpn block once.  Needs the node -> elements table of
+ * tatva_host_node_to_elements.  Single-quadrature-point elements (Tri3, Tet4); returns
+ * TATVA_E_UNSUPPORTED otherwise (use tatva_csr_assemble).  `d_data` needs no zeroing.              */
+int tatva_csr_assemble_rows(tatva_plan_t* plan, int material, const double* params, int n_params,
+                            const double* d_u, const int32_t* d_indptr, const int32_t* d_indices,
+                            const int32_t* d_n2e_ptr, const int32_t* d_n2e, double* d_data,
+                            tatva_stream_t stream);
+
 /* ---- halo exchange building blocks (tatva/mpi.py:372-409, :479-516) ---------------------
  * pack:        dst[k]        = src[idx[k]]      (send_buf = x_owned[nbr_send], mpi.py:400)
  * unpack_set:  dst[idx[k]]   = src[k]           (u_local.at[nbr_recv].set,     mpi.py:406-407)
@@ -161,6 +171,10 @@ int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, 
  * greedy first-fit in natural order on the pattern of A@A.                                  */
 int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, int64_t n,
                                 int32_t* colors, int32_t* n_colors);
+/* node -> incident elements in CSR form (ptr: n_nodes+1, list: sum of incidences); pass list == NULL
+ * first to size it (ptr[n_nodes]).                                                                   */
+int tatva_host_node_to_elements(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes,
+                                int32_t* ptr, int32_t* list);
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe,
                                      int dofs_per_node, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos);

@@ -45,11 +45,13 @@ SIGNATURES = {
     "tatva_hvp_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_residual_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_csr_assemble": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, vp]),
+    "tatva_csr_assemble_rows": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "tatva_halo_pack": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_halo_unpack_set": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_halo_unpack_add": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_host_pattern_from_mesh": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, C.c_int, c_i32p, c_i32p, c_i64p]),
     "tatva_host_distance2_colors": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p]),
+    "tatva_host_node_to_elements": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, c_i32p, c_i32p]),
     "tatva_host_csr_element_positions": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p]),
     "tatva_fp64_peak_tflops": (C.c_int, [c_f64p, vp]),
 }

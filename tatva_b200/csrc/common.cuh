@@ -383,4 +383,6 @@ inline int grid_for(int64_t n, int block = kBlock) { return (int)((n + block - 1
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st);
 
+int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
+
 }  // namespace tatva

@@ -410,6 +410,118 @@ __global__ void __launch_bounds__(kBlock) k_csr(const double* __restrict__ coord
   }
 }
 
+// ---- CSR assembly by rows (no atomics, deterministic) ---------------------------------------------
+// One warp owns the dpn CSR rows of one node a.  Phase 1: lane l takes the l-th element incident on a
+// and computes the three columns (a,i) of its stiffness — by symmetry of the energy Hessian these are
+// the rows (a,i) — into a shared-memory slab.  Phase 2: lane m takes the m-th block entry (a, b_m) of the
+// row, sums the slabs of the elements that contain b_m in a fixed order and stores the dpn x dpn block
+// with plain, row-contiguous stores.  Every stored entry of a mesh pattern is written exactly once.
+// Single-quadrature-point elements only (Tri3, Tet4); others keep the atomic kernel.
+
+template <class El, class Mat>
+__global__ void __launch_bounds__(128) k_csr_rows(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                  int64_t n_nodes, Mat mat, const double* __restrict__ u,
+                                                  const int32_t* __restrict__ indptr,
+                                                  const int32_t* __restrict__ indices,
+                                                  const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
+                                                  double* __restrict__ data) {
+  static_assert(El::nq == 1, "row-wise assembly is implemented for single-point elements");
+  constexpr int dpn = Mat::dpn, npe = El::npe, SLAB = dpn * npe * dpn;
+  extern __shared__ double sm_rows[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* slab = sm_rows + (size_t)wib * 32 * (SLAB + npe / 2 + 1);  // per warp: 32 slabs then 32 x npe node ids
+  int* sconn = reinterpret_cast<int*>(slab + 32 * SLAB);
+  const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (a >= n_nodes) return;
+  const int ebeg = __ldg(n2e_ptr + a), eend = __ldg(n2e_ptr + a + 1);
+  const int64_t row = a * dpn;
+  const int r0 = __ldg(indptr + row);
+  const int nb = (__ldg(indptr + row + 1) - r0) / dpn;
+
+  for (int mb = 0; mb < nb; mb += 32) {  // block entries of the row, 32 at a time (one pass for usual meshes)
+    const int m = mb + lane;
+    const int bnode = (m < nb) ? __ldg(indices + r0 + m * dpn) / dpn : -1;
+    double acc[dpn][dpn];
+#pragma unroll
+    for (int i = 0; i < dpn; ++i)
+#pragma unroll
+      for (int k = 0; k < dpn; ++k) acc[i][k] = 0.0;
+
+    for (int eb = ebeg; eb < eend; eb += 32) {
+      const int cnt = min(32, eend - eb);
+      __syncwarp();
+      if (lane < cnt) {
+        const int64_t e = __ldg(n2e + eb + lane);
+        int nd[npe];
+        load_conn<El>(conn, e, nd);
+        double X[npe][El::dim], U[npe][dpn];
+        gather_rows(coords, nd, X);
+        gather_rows(u, nd, U);
+        double dNdX[El::dim][npe], N[npe];
+        const double W = geometry<El>(0, X, dNdX) * El::weight(0);
+        El::N(0, N);
+        typename Mat::S s, ds, f;
+        typename Mat::Cache cache;
+        qp_state<El, Mat>(dNdX, N, U, s);
+        mat.prepare(s, cache);
+        double ga[El::dim], Na = 0.0;  // shape gradient / value of the row node inside this element
+#pragma unroll
+        for (int j = 0; j < El::dim; ++j) ga[j] = 0.0;
+#pragma unroll
+        for (int n = 0; n < npe; ++n) {
+          const bool hit = (nd[n] == (int)a);
+#pragma unroll
+          for (int j = 0; j < El::dim; ++j) ga[j] = hit ? dNdX[j][n] : ga[j];
+          Na = hit ? N[n] : Na;
+          sconn[lane * npe + n] = nd[n];
+        }
+#pragma unroll
+        for (int i = 0; i < dpn; ++i) {
+#pragma unroll
+          for (int c = 0; c < dpn; ++c) {
+#pragma unroll
+            for (int j = 0; j < El::dim; ++j) ds.G[c][j] = (c == i) ? ga[j] : 0.0;
+            ds.val[c] = (c == i) ? Na : 0.0;
+          }
+          mat.second(s, cache, ds, f);
+#pragma unroll
+          for (int b = 0; b < npe; ++b)
+#pragma unroll
+            for (int k = 0; k < dpn; ++k) {
+              double t = 0.0;
+#pragma unroll
+              for (int j = 0; j < El::dim; ++j) t += f.G[k][j] * dNdX[j][b];
+              if (k >= Mat::val_lo) t += f.val[k] * N[b];
+              slab[lane * SLAB + (i * npe + b) * dpn + k] = W * t;  // K_e[(b,k),(a,i)] = K_e[(a,i),(b,k)]
+            }
+        }
+      }
+      __syncwarp();
+      if (m < nb) {
+        for (int l = 0; l < cnt; ++l) {
+#pragma unroll
+          for (int b = 0; b < npe; ++b) {
+            if (sconn[l * npe + b] == bnode) {
+#pragma unroll
+              for (int i = 0; i < dpn; ++i)
+#pragma unroll
+                for (int k = 0; k < dpn; ++k) acc[i][k] += slab[l * SLAB + (i * npe + b) * dpn + k];
+            }
+          }
+        }
+      }
+    }
+    if (m < nb) {
+#pragma unroll
+      for (int i = 0; i < dpn; ++i) {
+        double* dst = data + (int64_t)__ldg(indptr + row + i) + (int64_t)m * dpn;
+#pragma unroll
+        for (int k = 0; k < dpn; ++k) dst[k] = acc[i][k];
+      }
+    }
+  }
+}
+
 // ---- halo pack / unpack -----------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_pack(const double* __restrict__ src, const int64_t* __restrict__ idx,
@@ -664,6 +776,7 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
     if (el == TATVA_TET4) return launch_fused<Tet4, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
     if (el == TATVA_HEX8) {
       if (MODE == MODE_HVP && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_hvp_modal(p, prm[0], prm[1], u, v, out, st);
+      if (MODE == MODE_RESIDUAL && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_residual_modal(p, prm[0], prm[1], u, out, st);
       return launch_fused<Hex8, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
     }
   } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD) {
@@ -764,6 +877,46 @@ int tatva_csr_assemble(tatva_plan_t* p, int material, const double* prm, int n_p
     return TATVA_E_INVALID;
   }
   return TATVA_E_UNSUPPORTED;
+}
+
+}  // extern "C"
+
+template <class El, class Mat>
+static int launch_csr_rows(tatva_plan* p, const Mat& mat, const double* u, const int32_t* indptr, const int32_t* indices,
+                           const int32_t* n2e_ptr, const int32_t* n2e, double* data, cudaStream_t st) {
+  constexpr int warps = 4, SLAB = Mat::dpn * El::npe * Mat::dpn;
+  constexpr size_t smem = (size_t)warps * 32 * (SLAB + El::npe / 2 + 1) * sizeof(double);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_rows<El, Mat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = (int)((p->n_nodes + warps - 1) / warps);
+  k_csr_rows<El, Mat><<<grid, warps * 32, smem, st>>>(p->coords, p->conn, p->n_nodes, mat, u, indptr, indices, n2e_ptr, n2e, data);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+extern "C" {
+
+int tatva_csr_assemble_rows(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
+                            const int32_t* d_indptr, const int32_t* d_indices, const int32_t* d_n2e_ptr,
+                            const int32_t* d_n2e, double* d_data, tatva_stream_t stream) {
+  if (!p || !prm || !d_u || !d_indptr || !d_indices || !d_n2e_ptr || !d_n2e || !d_data) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int el = p->element;
+  if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
+    if (el == TATVA_TRI3) return launch_csr_rows<Tri3, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_indices, d_n2e_ptr, d_n2e, d_data, st);
+    if (el == TATVA_TET4) return launch_csr_rows<Tet4, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_indices, d_n2e_ptr, d_n2e, d_data, st);
+  } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
+    if (el == TATVA_TET4) return launch_csr_rows<Tet4, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_indices, d_n2e_ptr, d_n2e, d_data, st);
+  } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5) {
+    const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+    if (el == TATVA_TET4) return launch_csr_rows<Tet4, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_indices, d_n2e_ptr, d_n2e, d_data, st);
+  } else {
+    return TATVA_E_INVALID;
+  }
+  return TATVA_E_UNSUPPORTED;  // multi-point elements: use tatva_csr_assemble
 }
 
 int tatva_halo_pack(const double* s, const int64_t* idx, int64_t n, double* d, tatva_stream_t stream) {

@@ -27,6 +27,13 @@ namespace {
 
 constexpr double kA = 0.57735026918962576451;  // 1/sqrt(3)
 
+// Gauss-point signs (tx, ty, tz, ty*tz, tx*tz, tx*ty) in the element's node order.  Read with a
+// warp-uniform index so they reach the DFMAs as constant-bank / uniform-register operands: a DFMA with
+// three distinct *vector*-register sources issues at 2/3 rate on B200 (tools/micro/dfma_operands.cu).
+__constant__ double kSigns[8][6] = {
+    {-1, -1, -1, +1, +1, +1}, {+1, -1, -1, +1, -1, -1}, {+1, +1, -1, -1, -1, +1}, {-1, +1, -1, -1, +1, -1},
+    {-1, -1, +1, -1, -1, +1}, {+1, -1, +1, -1, +1, -1}, {+1, +1, +1, +1, +1, +1}, {-1, +1, +1, +1, -1, -1}};
+
 // 8-point Walsh-Hadamard transform of the nodal values of one scalar field, in the element's node
 // order (bottom CCW, top CCW).  Output: c[0..6] = {x, y, z, xy, yz, zx, xyz} coefficients scaled so
 // that   d/dxi f = c_x + ty c_xy + tz c_zx + ty tz c_xyz   at the Gauss point a*(tx,ty,tz).
@@ -207,8 +214,6 @@ __global__ void __launch_bounds__(kBlock, MINB)
 // stay unscaled adjugates.
 // ---------------------------------------------------------------------------------------------
 
-// `volatile`: the staged coefficients must be re-read from shared memory at every Gauss point;
-// otherwise the compiler hoists the (loop-invariant) loads and spills them to local memory.
 template <class Ptr>
 TATVA_D void ref_grad_s(Ptr c, int stride, double tx, double ty, double tz, double (&g)[3]) {
   const double c0 = c[0], c1 = c[stride], c2 = c[2 * stride], c3 = c[3 * stride], c4 = c[4 * stride],
@@ -232,7 +237,7 @@ TATVA_D void adjugate(const double (&A)[3][3], double (&C)[3][3], double& det) {
   C[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
 }
 
-template <int STAGE, int MINB, int DEBUG = 0>
+template <int STAGE, int MINB, int DEBUG = 0, int UNROLL = 1, int FOLD = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_rolled(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                          double lmbda, const double* __restrict__ u, const double* __restrict__ v,
@@ -249,9 +254,9 @@ __global__ void __launch_bounds__(kBlock, MINB)
     nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
   }
   double rX[STAGE >= 1 ? 1 : 3][7], rv[STAGE >= 1 ? 1 : 3][7], rx[STAGE >= 2 ? 1 : 3][7];
-  volatile double* sX = sm + threadIdx.x;
-  volatile double* sv = sm + 21 * kBlock + threadIdx.x;
-  volatile double* sx = sm + 42 * kBlock + threadIdx.x;
+  double* sX0 = sm + threadIdx.x;
+  double* sv0 = sm + 21 * kBlock + threadIdx.x;
+  double* sx0 = sm + 42 * kBlock + threadIdx.x;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     double fX[8], fu[8], fv[8], mX[7], mx[7], mv[7];
@@ -274,13 +279,13 @@ __global__ void __launch_bounds__(kBlock, MINB)
     for (int k = 0; k < 7; ++k) {
       mx[k] += mX[k];
       if constexpr (STAGE >= 1) {
-        sX[(c * 7 + k) * kBlock] = mX[k];
-        sv[(c * 7 + k) * kBlock] = mv[k];
+        sX0[(c * 7 + k) * kBlock] = mX[k];
+        sv0[(c * 7 + k) * kBlock] = mv[k];
       } else {
         rX[c][k] = mX[k];
         rv[c][k] = mv[k];
       }
-      if constexpr (STAGE >= 2) sx[(c * 7 + k) * kBlock] = mx[k];
+      if constexpr (STAGE >= 2) sx0[(c * 7 + k) * kBlock] = mx[k];
       else rx[c][k] = mx[k];
     }
   }
@@ -290,11 +295,17 @@ __global__ void __launch_bounds__(kBlock, MINB)
 #pragma unroll
     for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
 
-#pragma unroll 1
+#pragma unroll UNROLL
   for (int q = 0; q < 8; ++q) {
-    const double tx = ((q + 1) & 2) ? 1.0 : -1.0;  // q&3 in {1,2}
-    const double ty = (q & 2) ? 1.0 : -1.0;
-    const double tz = (q & 4) ? 1.0 : -1.0;
+    const double tx = kSigns[q][0], ty = kSigns[q][1], tz = kSigns[q][2];
+    // Opaque per-iteration offset (always 0): the staged coefficients are re-read from shared memory at
+    // every Gauss point instead of being hoisted out of the loop (and spilled), while loads within one
+    // point stay freely schedulable (unlike `volatile`).
+    int opaque = 0;
+    asm volatile("" : "+r"(opaque));
+    const double* sX = sX0 + opaque;
+    const double* sv = sv0 + opaque;
+    const double* sx = sx0 + opaque;
     double J[3][3], Kc[3][3], detJ;  // J[d][c] = dX_c/dxi_d ; Kc = adj(J) = detJ * K
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -335,15 +346,33 @@ __global__ void __launch_bounds__(kBlock, MINB)
     // W = detJ:  mu W Gv M/detJ^2 ; (mu - lambda lnJ) W (B Ac)^T/detF^2 ; lambda W tr(B) Ac^T/detF^2
     const double wF = detJ * rF * rF;
     const double w1 = mu * rJ, w2 = (mu - lmbda * lnJ) * wF, w3 = lmbda * wF * (B[0][0] + B[1][1] + B[2][2]);
-    const double tyz = ty * tz, txz = tx * tz, txy = tx * ty;
+    const double tyz = kSigns[q][3], txz = kSigns[q][4], txy = kSigns[q][5];
+    if constexpr (FOLD) {  // fold the three weights into M and B: one 6-term chain per flux entry
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+          M[a][b] *= w1;
+          M[b][a] = M[a][b];
+        }
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int f = 0; f < 3; ++f) B[d][f] = (d == f) ? fma(w2, B[d][f], w3) : w2 * B[d][f];
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double qv[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const double t1 = Gv[i][0] * M[0][d] + Gv[i][1] * M[1][d] + Gv[i][2] * M[2][d];
-        const double t2 = B[d][0] * Ac[0][i] + B[d][1] * Ac[1][i] + B[d][2] * Ac[2][i];
-        qv[d] = w1 * t1 + w2 * t2 + w3 * Ac[d][i];
+        if constexpr (FOLD) {
+          qv[d] = fma(B[d][0], Ac[0][i], fma(B[d][1], Ac[1][i], fma(B[d][2], Ac[2][i],
+                  fma(Gv[i][0], M[0][d], fma(Gv[i][1], M[1][d], Gv[i][2] * M[2][d])))));
+        } else {
+          const double t1 = Gv[i][0] * M[0][d] + Gv[i][1] * M[1][d] + Gv[i][2] * M[2][d];
+          const double t2 = B[d][0] * Ac[0][i] + B[d][1] * Ac[1][i] + B[d][2] * Ac[2][i];
+          qv[d] = w1 * t1 + w2 * t2 + w3 * Ac[d][i];
+        }
       }
       R[i][0] += qv[0];
       R[i][1] += qv[1];
@@ -376,20 +405,110 @@ __global__ void __launch_bounds__(kBlock, MINB)
   }
 }
 
-template <int STAGE, int MINB, int DEBUG = 0>
+template <int STAGE, int MINB, int DEBUG = 0, int UNROLL = 1, int FOLD = 0>
 int launch_rolled(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                   cudaStream_t st) {
   constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 2 : 3);
   constexpr size_t smem = (size_t)NS * 21 * kBlock * sizeof(double);
   static bool configured = false;
   if (!configured && smem > 48 * 1024) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG, UNROLL, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     configured = true;
   }
-  k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu,
+  k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG, UNROLL, FOLD><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu,
                                                                                lmbda, u, v, y);
   return TATVA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Residual in the same modal / reference-space form:
+//   W P K = W [ mu Fr M + (lambda lnJ - mu) A^T ],   P = mu (F - F^-T) + lambda lnJ F^-T,  F = Fr K^T.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 2)
+    k_hex8_nh_residual_modal(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                             double lmbda, const double* __restrict__ u, double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  double rX[3][7], rx[3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal(fX, rX[c]);
+    to_modal(fu, rx[c]);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) rx[c][k] += rX[c][k];
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+
+#pragma unroll 1
+  for (int q = 0; q < 8; ++q) {
+    const double tx = kSigns[q][0], ty = kSigns[q][1], tz = kSigns[q][2];
+    double J[3][3], Kc[3][3], detJ;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double g[3];
+      ref_grad_s((const double*)rX[c], 1, tx, ty, tz, g);
+      J[0][c] = g[0]; J[1][c] = g[1]; J[2][c] = g[2];
+    }
+    adjugate(J, Kc, detJ);
+    double M[3][3];  // detJ^2 K^T K
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = a; b < 3; ++b) {
+        M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+        M[b][a] = M[a][b];
+      }
+    double Fr[3][3], Ac[3][3], detF;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ref_grad_s((const double*)rx[i], 1, tx, ty, tz, Fr[i]);
+    adjugate(Fr, Ac, detF);
+    const double rJ = 1.0 / detJ, rF = 1.0 / detF;
+    const double lnJ = log(detF * rJ);
+    const double w1 = mu * rJ, w2 = (lmbda * lnJ - mu) * detJ * rF;
+    const double tyz = kSigns[q][3], txz = kSigns[q][4], txy = kSigns[q][5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double qv[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double t1 = Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d];
+        qv[d] = w1 * t1 + w2 * Ac[d][i];
+      }
+      R[i][0] += qv[0];
+      R[i][1] += qv[1];
+      R[i][2] += qv[2];
+      R[i][3] = fma(ty, qv[0], fma(tx, qv[1], R[i][3]));
+      R[i][4] = fma(tz, qv[1], fma(ty, qv[2], R[i][4]));
+      R[i][5] = fma(tz, qv[0], fma(tx, qv[2], R[i][5]));
+      R[i][6] = fma(tyz, qv[0], fma(txz, qv[1], fma(txy, qv[2], R[i][6])));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
 }
 
 }  // namespace
@@ -409,9 +528,20 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 9: rc = launch_rolled<0, 2, 2>(p, mu, lmbda, u, v, y, st); break;
     case 10: rc = launch_rolled<2, 4, 1>(p, mu, lmbda, u, v, y, st); break;
     case 11: rc = launch_rolled<2, 4, 2>(p, mu, lmbda, u, v, y, st); break;
-    default: rc = launch_rolled<0, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 12: rc = launch_rolled<1, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 13: rc = launch_rolled<0, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 14: rc = launch_rolled<2, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 15: rc = launch_rolled<0, 2, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
+    default: rc = launch_rolled<0, 2, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
   }
   if (rc != TATVA_OK) return rc;
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
+  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  k_hex8_nh_residual_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

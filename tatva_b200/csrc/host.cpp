@@ -106,6 +106,41 @@ int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, i
   return TATVA_OK;
 }
 
+// node -> incident elements (CSR), elements ascending; two-call protocol (list == NULL: fill ptr only)
+int tatva_host_node_to_elements(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes, int32_t* ptr,
+                                int32_t* list) {
+  if (!conn || !ptr || n_elems <= 0 || npe <= 0 || n_nodes <= 0) return TATVA_E_INVALID;
+  if (n_elems * npe > INT32_MAX) return TATVA_E_INVALID;
+  std::fill(ptr, ptr + n_nodes + 1, 0);
+  for (int64_t i = 0; i < n_elems * npe; ++i) {
+    if (conn[i] < 0 || conn[i] >= n_nodes) return TATVA_E_INVALID;
+    ptr[conn[i] + 1]++;
+  }
+  for (int64_t n = 0; n < n_nodes; ++n) ptr[n + 1] += ptr[n];
+  if (!list) return TATVA_OK;
+  std::vector<int32_t> fill(ptr, ptr + n_nodes);
+  for (int64_t e = 0; e < n_elems; ++e)
+    for (int a = 0; a < npe; ++a) {
+      const int32_t n = conn[e * npe + a];
+      // an element listing the same node twice contributes once
+      if (fill[n] > ptr[n] && list[fill[n] - 1] == (int32_t)e) continue;
+      list[fill[n]++] = (int32_t)e;
+    }
+  // compact (only needed if some element repeated a node)
+  bool compact = false;
+  for (int64_t n = 0; n < n_nodes && !compact; ++n) compact = fill[n] != ptr[n + 1];
+  if (compact) {
+    int32_t w = 0;
+    std::vector<int32_t> np(n_nodes + 1, 0);
+    for (int64_t n = 0; n < n_nodes; ++n) {
+      for (int32_t k = ptr[n]; k < fill[n]; ++k) list[w++] = list[k];
+      np[n + 1] = w;
+    }
+    std::copy(np.begin(), np.end(), ptr);
+  }
+  return TATVA_OK;
+}
+
 // elem_pos[e, a, b] = offset of column dpn*conn[e,b] inside CSR row dpn*conn[e,a]
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe, int dpn, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos) {

@@ -173,7 +173,7 @@ class _Assembler:
     """Direct CSR assembly plan for (operator, material, pattern): device copies of indptr and of the
     element -> CSR position table."""
 
-    def __init__(self, op, material, colored_matrix: ColoredMatrix):
+    def __init__(self, op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None):
         dpn = material.dofs_per_node(op.dim)
         indptr = np.ascontiguousarray(_np(colored_matrix.indptr), dtype=np.int32)
         indices = np.ascontiguousarray(_np(colored_matrix.indices), dtype=np.int32)
@@ -187,7 +187,19 @@ class _Assembler:
         )
         self.op, self.material, self.nnz = op, material, int(indices.shape[0])
         self.d_indptr = torch.as_tensor(indptr, device=op.device)
-        self.d_pos = torch.as_tensor(pos, device=op.device)
+        # Row-wise (atomic-free, deterministic) kernel for single-point elements; per-entry atomics otherwise.
+        self.by_rows = (op.nq == 1) if by_rows is None else bool(by_rows)
+        if self.by_rows:
+            L = _lib.lib()
+            ptr = np.empty(op.n_nodes + 1, dtype=np.int32)
+            _lib.check(L.tatva_host_node_to_elements(_i32p(conn), conn.shape[0], conn.shape[1], op.n_nodes, _i32p(ptr), None), "node_to_elements")
+            lst = np.empty(int(ptr[-1]), dtype=np.int32)
+            _lib.check(L.tatva_host_node_to_elements(_i32p(conn), conn.shape[0], conn.shape[1], op.n_nodes, _i32p(ptr), _i32p(lst)), "node_to_elements")
+            self.d_indices = torch.as_tensor(indices, device=op.device)
+            self.d_n2e_ptr = torch.as_tensor(ptr, device=op.device)
+            self.d_n2e = torch.as_tensor(lst[: int(ptr[-1])], device=op.device)
+        else:
+            self.d_pos = torch.as_tensor(pos, device=op.device)
 
     def __call__(self, u, out=None) -> torch.Tensor:
         op = self.op
@@ -195,13 +207,19 @@ class _Assembler:
         if out is None:
             out = torch.empty(self.nnz, dtype=torch.float64, device=op.device)
         prm, n = _lib.params_array(self.material.params())
-        op._call("tatva_csr_assemble", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_pos.data_ptr(), self.nnz, out.data_ptr())
+        if self.by_rows:
+            op._call("tatva_csr_assemble_rows", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_indices.data_ptr(),
+                     self.d_n2e_ptr.data_ptr(), self.d_n2e.data_ptr(), out.data_ptr())
+        else:
+            op._call("tatva_csr_assemble", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_pos.data_ptr(), self.nnz, out.data_ptr())
         return out
 
 
-def assembler(op, material, colored_matrix: ColoredMatrix) -> Callable:
-    """u -> CSR data (nnz,) of d^2E/du^2 on the pattern of `colored_matrix` (one kernel)."""
-    return _Assembler(op, material, colored_matrix)
+def assembler(op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None) -> Callable:
+    """u -> CSR data (nnz,) of d^2E/du^2 on the pattern of `colored_matrix` (one kernel).
+    by_rows=None picks the atomic-free row-wise kernel for single-point elements (Tri3, Tet4) and the
+    per-entry-atomic kernel otherwise; True / False force one of them."""
+    return _Assembler(op, material, colored_matrix, by_rows)
 
 
 def _coloured_columns(fn_jvp, u, colored_matrix, color_batch_size):

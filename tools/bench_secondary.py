@@ -1,0 +1,119 @@
+"""Secondary kernels of SURVEY.md §8: timings at the configs' sizes (1 GPU).  One JSON line per kernel."""
+import sys, os, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import tatva_b200
+from tatva_b200 import element, materials, sparse
+from tatva_b200.mesh import Mesh
+
+HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+only = sys.argv[1].split(",") if len(sys.argv) > 1 else None
+
+
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def smooth_u(c):
+    t = 2 * np.pi
+    if c.shape[1] == 2:
+        return 0.05 * np.stack([np.sin(t * c[:, 0]) * np.cos(t * c[:, 1]), np.sin(t * c[:, 1]) * np.cos(t * c[:, 0])], -1)
+    return 0.05 * np.stack([np.sin(t * c[:, 0]) * np.cos(t * c[:, 1]), np.sin(t * c[:, 1]) * np.cos(t * c[:, 2]), np.sin(t * c[:, 2]) * np.cos(t * c[:, 0])], -1)
+
+
+def report(name, ms, alg_bytes, units, unit_name, **extra):
+    print(json.dumps(dict(kernel=name, ms=round(ms, 4), rate=units / ms * 1e3, unit=unit_name + "/s", alg_GBs=round(alg_bytes / ms / 1e6, 1), hbm_frac=round(alg_bytes / ms / 1e6 / HBM, 4), **extra)), flush=True)
+
+
+def want(tag):
+    return only is None or tag in only
+
+
+# ---- config 2: Tet4 box n=55 (998 250 elements), neo-Hookean ----
+if want("tet4"):
+    m = Mesh.box_tet((1.0, 1.0, 1.0), (55, 55, 55))
+    c = m.coords + np.array([0.5, 0.5, 0.0]) + 0.1 / 55 * np.random.default_rng(0).uniform(-1, 1, m.coords.shape)
+    m = Mesh(coords=c, elements=m.elements)
+    op = tatva_b200.Operator(m, element.Tetrahedron4())
+    mat = materials.NeoHookean(500.0, 1000.0)
+    N, E = c.shape[0], m.elements.shape[0]
+    u = torch.as_tensor(smooth_u(c), device="cuda")
+    v = torch.as_tensor(np.random.default_rng(1).normal(size=c.shape), device="cuda")
+    y = torch.empty_like(u)
+    report("tet4_nh_hvp_c2", timeit(lambda: op._raw_hvp(mat, u, v, out=y)), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", elems=E)
+    report("tet4_nh_residual_c2", timeit(lambda: op._raw_residual(mat, u)), 8 * (6 * N + 3 * N) + 16 * E, 3 * N, "DOF")
+    report("tet4_nh_energy_c2", timeit(lambda: op._raw_energy(mat, u)), 8 * (3 * N + 3 * N) + 16 * E, 3 * N, "DOF")
+    t0 = time.perf_counter()
+    pat = sparse.pattern_from_mesh(m, 3)
+    t1 = time.perf_counter()
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    t2 = time.perf_counter()
+    asm = sparse.assembler(op, mat, cm)
+    t3 = time.perf_counter()
+    data = torch.empty(asm.nnz, dtype=torch.float64, device="cuda")
+    nnz = asm.nnz
+    report("tet4_nh_csr_assemble_c2", timeit(lambda: asm(u, out=data), reps=10), 8 * nnz + 64 * E + 8 * 6 * N + 16 * E, nnz, "nnz", nnz=nnz, n_colors=int(cm.colors.max()) + 1,
+           host_pattern_s=round(t1 - t0, 3), host_colouring_s=round(t2 - t1, 3), host_positions_s=round(t3 - t2, 3))
+    asm2 = sparse.assembler(op, mat, cm, by_rows=False)
+    data2 = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    report("tet4_nh_csr_assemble_atomic_c2", timeit(lambda: asm2(u, out=data2), reps=10), 8 * nnz + 64 * E + 8 * 6 * N + 16 * E, nnz, "nnz", rel_diff=float((data - data2).norm() / data2.norm()))
+    del data2, asm2
+    # the reference algorithm costs n_colors HVPs: report what that would be with our HVP kernel
+    del data, asm
+
+# ---- config 5: Tet4 n=55 compound (u, phi) ----
+if want("pf"):
+    m = Mesh.box_tet((1.0, 1.0, 1.0), (55, 55, 55))
+    c = m.coords + np.array([0.5, 0.5, 0.0]) + 0.1 / 55 * np.random.default_rng(0).uniform(-1, 1, m.coords.shape)
+    m = Mesh(coords=c, elements=m.elements)
+    op = tatva_b200.Operator(m, element.Tetrahedron4())
+    mat = materials.NeoHookeanPhaseField(500.0, 1000.0, 2.7, 0.05, 1e-6)
+    N, E = c.shape[0], m.elements.shape[0]
+    s = torch.as_tensor(np.concatenate([smooth_u(c), 0.5 + 0.3 * np.sin(6 * c[:, :1])], axis=1), device="cuda")
+    t = torch.as_tensor(np.random.default_rng(1).normal(size=(N, 4)), device="cuda")
+    y = torch.empty_like(s)
+    report("tet4_pf_hvp_c5", timeit(lambda: op._raw_hvp(mat, s, t, out=y)), 8 * (12 * N + 3 * N) + 16 * E, 4 * N, "DOF")
+    report("tet4_pf_residual_c5", timeit(lambda: op._raw_residual(mat, s)), 8 * (8 * N + 3 * N) + 16 * E, 4 * N, "DOF")
+
+# ---- config 1: Tri3 256^2, linear elasticity ----
+if want("tri3"):
+    m = Mesh.unit_square(256, 256)
+    op = tatva_b200.Operator(m, element.Tri3())
+    mat = materials.LinearElastic.from_youngs_poisson_2d(1.0, 0.3)
+    N, E = m.coords.shape[0], m.elements.shape[0]
+    u = torch.as_tensor(smooth_u(m.coords), device="cuda")
+    v = torch.as_tensor(np.random.default_rng(1).normal(size=m.coords.shape), device="cuda")
+    y = torch.empty_like(u)
+    report("tri3_le_hvp_c1", timeit(lambda: op._raw_hvp(mat, u, v, out=y), reps=100), 8 * (2 * 2 * N + 2 * N) + 12 * E, 2 * N, "DOF")
+    report("tri3_le_residual_c1", timeit(lambda: op._raw_residual(mat, u), reps=100), 8 * (2 * 2 * N + 2 * N) + 12 * E, 2 * N, "DOF")
+
+# ---- config 3 extras: Hex8 128^3 residual / energy, building blocks at 64^3 ----
+if want("hex8"):
+    from bench import synthetic_inputs
+    c, el, u_, v_ = synthetic_inputs(128)
+    op = tatva_b200.Operator(Mesh(coords=c, elements=el), element.Hexahedron8())
+    mat = materials.NeoHookean(500.0, 1000.0)
+    N, E = c.shape[0], el.shape[0]
+    u = torch.as_tensor(u_, device="cuda")
+    report("hex8_nh_residual_c3", timeit(lambda: op._raw_residual(mat, u)), 8 * (9 * N) + 32 * E, 3 * N, "DOF")
+    report("hex8_nh_energy_c3", timeit(lambda: op._raw_energy(mat, u)), 8 * (6 * N) + 32 * E, 3 * N, "DOF")
+    del op
+    c, el, u_, v_ = synthetic_inputs(64)
+    op = tatva_b200.Operator(Mesh(coords=c, elements=el), element.Hexahedron8())
+    N, E = c.shape[0], el.shape[0]
+    u = torch.as_tensor(u_, device="cuda")
+    g = op._k_grad(u)
+    report("hex8_op_grad_64", timeit(lambda: op._k_grad(u)), 8 * (6 * N + 72 * E) + 32 * E, E * 8, "qp")
+    report("hex8_op_grad_adjoint_64", timeit(lambda: op._k_grad_adj(g)), 8 * (6 * N + 72 * E) + 32 * E, E * 8, "qp")
+    report("hex8_op_eval_64", timeit(lambda: op._k_eval(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "qp")
+    report("hex8_op_weights_64", timeit(lambda: op.get_integration_weights()), 8 * (3 * N + 8 * E) + 32 * E, E * 8, "qp")
+    report("hex8_op_gather_64", timeit(lambda: op._k_gather(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "node-ref")

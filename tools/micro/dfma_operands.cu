@@ -24,6 +24,9 @@ __global__ void __launch_bounds__(256) k(double* out, int iters, double m, doubl
         if (MODE == 4) a[i] = a[i] * b[i];                   // DMUL 2 distinct
         if (MODE == 5) a[i] = fma(b[i], d[(i + r) & 7], a[i]);  // 3 distinct, rotating
         if (MODE == 6) a[i] = fma(b[r], d[i], a[i]);         // b shared across the 8 consecutive FMAs
+        if (MODE == 7) { double t = a[i] + b[i]; a[i] = b[i]; b[i] = t; }          // DADD, destination differs from both sources
+        if (MODE == 8) { double t = fma(a[i], b[i], d[i]); d[i] = a[i]; a[i] = b[i]; b[i] = t; }  // DFMA, 3 distinct + distinct dest
+        if (MODE == 9) { double t = a[i] * b[i]; a[i] = b[i]; b[i] = t; }          // DMUL distinct dest
       }
     }
   }
@@ -61,7 +64,7 @@ void run(const char* name, int warps_per_sm) {
 }
 
 int main() {
-  for (int w : {8, 16, 32, 64}) {
+  for (int w : {8, 32}) {
     run<0>("DFMA a=fma(a,m,c)      [1 new reg operand]", w);
     run<1>("DFMA a=fma(b,d,a)      [3 distinct]", w);
     run<2>("DFMA a=fma(b,m,a)      [2 distinct + shared]", w);
@@ -69,6 +72,9 @@ int main() {
     run<4>("DMUL a=a*b             [2 distinct]", w);
     run<5>("DFMA a=fma(b,d[rot],a) [3 distinct]", w);
     run<6>("DFMA a=fma(b[r],d,a)   [b shared over 8]", w);
+    run<7>("DADD t=a+b             [distinct dest]", w);
+    run<8>("DFMA t=fma(a,b,d)      [3 distinct, distinct dest]", w);
+    run<9>("DMUL t=a*b             [distinct dest]", w);
   }
   return 0;
 }
