@@ -654,7 +654,7 @@ int tatva_plan_info(const tatva_plan_t* p, int* element, int* dim, int* npe, int
 }
 
 int tatva_plan_set_variant(tatva_plan_t* p, int variant) {
-  if (!p || variant < 0 || variant > 15) return TATVA_E_INVALID;
+  if (!p || variant < 0 || variant > 63) return TATVA_E_INVALID;
   p->variant = variant;
   return TATVA_OK;
 }

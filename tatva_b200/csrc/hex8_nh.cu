@@ -423,6 +423,215 @@ int launch_rolled(const tatva_plan* p, double mu, double lmbda, const double* u,
 
 
 // ---------------------------------------------------------------------------------------------
+// v2 of the rolled HVP kernel: every scale factor is folded away.
+//  * to_modal_raw / from_modal_raw are pure +-1 butterflies (no multiplies); the 1/8 of the shape
+//    functions and the Gauss abscissa a live in the sign table (s = a t) and in one factor 1/512 applied to
+//    the three scalar weights (gradients are carried as 8x their value; the tangent is homogeneous).
+//  * 3x3 products are written k-outer so that consecutive DFMAs share their first operand (operand reuse).
+// ---------------------------------------------------------------------------------------------
+__constant__ double kScaledSigns[8][6] = {
+#define TATVA_S(tx, ty, tz) {tx * kA, ty * kA, tz * kA, (ty * tz) * kA * kA, (tx * tz) * kA * kA, (tx * ty) * kA * kA}
+    TATVA_S(-1, -1, -1), TATVA_S(+1, -1, -1), TATVA_S(+1, +1, -1), TATVA_S(-1, +1, -1),
+    TATVA_S(-1, -1, +1), TATVA_S(+1, -1, +1), TATVA_S(+1, +1, +1), TATVA_S(-1, +1, +1)
+#undef TATVA_S
+};
+
+TATVA_D void to_modal_raw(const double (&f)[8], double (&h)[7]) {
+  const double s01 = f[0] + f[1], d01 = f[1] - f[0];
+  const double s23 = f[3] + f[2], d23 = f[2] - f[3];
+  const double s45 = f[4] + f[5], d45 = f[5] - f[4];
+  const double s67 = f[7] + f[6], d67 = f[6] - f[7];
+  const double ss0 = s01 + s23, ds0 = s23 - s01, sd0 = d01 + d23, dd0 = d23 - d01;
+  const double ss1 = s45 + s67, ds1 = s67 - s45, sd1 = d45 + d67, dd1 = d67 - d45;
+  h[0] = sd0 + sd1;  // x
+  h[1] = ds0 + ds1;  // y
+  h[2] = ss1 - ss0;  // z
+  h[3] = dd0 + dd1;  // xy
+  h[4] = ds1 - ds0;  // yz
+  h[5] = sd1 - sd0;  // zx
+  h[6] = dd1 - dd0;  // xyz
+}
+
+TATVA_D void from_modal_raw(const double (&r)[7], double (&f)[8]) {
+  const double xm = r[0] - r[5], xp = r[0] + r[5];
+  const double ym = r[1] - r[4], yp = r[1] + r[4];
+  const double xym = r[3] - r[6], xyp = r[3] + r[6];
+  const double a0 = xym - r[2], a1 = -xym - r[2];  // sx sy = +1 / -1 on the lower face
+  const double b0 = xm + ym, b1 = xm - ym;
+  f[0] = a0 - b0;
+  f[1] = a1 + b1;
+  f[2] = a0 + b0;
+  f[3] = a1 - b1;
+  const double c0 = xyp + r[2], c1 = r[2] - xyp;
+  const double e0 = xp + yp, e1 = xp - yp;
+  f[4] = c0 - e0;
+  f[5] = c1 + e1;
+  f[6] = c0 + e0;
+  f[7] = c1 - e1;
+}
+
+TATVA_D void ref_grad8(const double (&h)[7], double sx, double sy, double sz, double (&g)[3]) {
+  const double s36 = fma(sz, h[6], h[3]);
+  g[0] = fma(sy, s36, fma(sz, h[5], h[0]));
+  g[1] = fma(sx, s36, fma(sz, h[4], h[1]));
+  g[2] = fma(sx, fma(sy, h[6], h[5]), fma(sy, h[4], h[2]));
+}
+
+// C = A * B (3x3), written k-outer: consecutive DFMAs share A[i][k]
+TATVA_D void mat3(const double (&A)[3][3], const double (&Bm)[3][3], double (&C)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * Bm[0][j];
+#pragma unroll
+  for (int k = 1; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) C[i][j] = fma(A[i][k], Bm[k][j], C[i][j]);
+}
+
+template <int MINB, int STAGE = 0>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_hvp_v2(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                     double lmbda, const double* __restrict__ u, const double* __restrict__ v,
+                     double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  // STAGE 1: the modal coordinates and direction live in shared memory (coefficient-major, one column
+  // per thread: conflict-free), which frees 84 registers => 3 CTAs (12 warps) per SM instead of 2.
+  extern __shared__ double sm[];
+  double* sX0 = sm + threadIdx.x;
+  double* sv0 = sm + 21 * kBlock + threadIdx.x;
+  double hX[STAGE ? 1 : 3][7], hx[3][7], hv[STAGE ? 1 : 3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8], fv[8], tX[7], tv[7];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal_raw(fX, tX);
+    to_modal_raw(fu, hx[c]);
+    to_modal_raw(fv, tv);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      hx[c][k] += tX[k];
+      if constexpr (STAGE) {
+        sX0[(c * 7 + k) * kBlock] = tX[k];
+        sv0[(c * 7 + k) * kBlock] = tv[k];
+      } else {
+        hX[c][k] = tX[k];
+        hv[c][k] = tv[k];
+      }
+    }
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+
+#pragma unroll 1
+  for (int q = 0; q < 8; ++q) {
+    const double sx = kScaledSigns[q][0], sy = kScaledSigns[q][1], sz = kScaledSigns[q][2];
+    int opaque = 0;  // always 0; keeps the staged loads inside the loop (see k_hex8_nh_hvp_rolled)
+    asm volatile("" : "+r"(opaque));
+    const double* sX = sX0 + opaque;
+    const double* sv = sv0 + opaque;
+    double J[3][3], Kc[3][3], detJ;  // 8 dX_c/dxi_d ; adj
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double g[3];
+      if constexpr (STAGE) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sX[(c * 7 + k) * kBlock];
+        ref_grad8(t, sx, sy, sz, g);
+      } else {
+        ref_grad8(hX[c], sx, sy, sz, g);
+      }
+      J[0][c] = g[0]; J[1][c] = g[1]; J[2][c] = g[2];
+    }
+    adjugate(J, Kc, detJ);
+    double M[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = a; b < 3; ++b) {
+        M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+        M[b][a] = M[a][b];
+      }
+    double Fr[3][3], Ac[3][3], detF;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ref_grad8(hx[i], sx, sy, sz, Fr[i]);
+    adjugate(Fr, Ac, detF);
+    const double r = 1.0 / (detJ * detF);
+    const double rJ = r * detF, rF = r * detJ;
+    const double lnJ = log(detF * rJ);
+    double Gv[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if constexpr (STAGE) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sv[(i * 7 + k) * kBlock];
+        ref_grad8(t, sx, sy, sz, Gv[i]);
+      } else {
+        ref_grad8(hv[i], sx, sy, sz, Gv[i]);
+      }
+    }
+    double B[3][3];
+    mat3(Ac, Gv, B);
+    const double wF = detJ * rF * rF;
+    const double w1 = mu_s * rJ, w2 = (mu_s - lm_s * lnJ) * wF, w3 = lm_s * wF * (B[0][0] + B[1][1] + B[2][2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = a; b < 3; ++b) {
+        M[a][b] *= w1;
+        M[b][a] = M[a][b];
+      }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int f = 0; f < 3; ++f) B[d][f] = (d == f) ? fma(w2, B[d][f], w3) : w2 * B[d][f];
+    double T1[3][3], T2[3][3];  // T1 = Gv M' ; T2 = B' Ac ; flux Q[i][d] = T1[i][d] + T2[d][i]
+    mat3(Gv, M, T1);
+    mat3(B, Ac, T2);
+    const double syz = kScaledSigns[q][3], sxz = kScaledSigns[q][4], sxy = kScaledSigns[q][5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double q0 = T1[i][0] + T2[0][i], q1 = T1[i][1] + T2[1][i], q2 = T1[i][2] + T2[2][i];
+      R[i][0] += q0;
+      R[i][1] += q1;
+      R[i][2] += q2;
+      R[i][3] = fma(sy, q0, fma(sx, q1, R[i][3]));
+      R[i][4] = fma(sz, q1, fma(sy, q2, R[i][4]));
+      R[i][5] = fma(sz, q0, fma(sx, q2, R[i][5]));
+      R[i][6] = fma(syz, q0, fma(sxz, q1, fma(sxy, q2, R[i][6])));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal_raw(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Residual in the same modal / reference-space form:
 //   W P K = W [ mu Fr M + (lambda lnJ - mu) A^T ],   P = mu (F - F^-T) + lambda lnJ F^-T,  F = Fr K^T.
 // ---------------------------------------------------------------------------------------------
@@ -532,7 +741,13 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 13: rc = launch_rolled<0, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
     case 14: rc = launch_rolled<2, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
     case 15: rc = launch_rolled<0, 2, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
-    default: rc = launch_rolled<0, 2, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 17: rc = launch_rolled<1, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 18: rc = launch_rolled<2, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 19: rc = launch_rolled<2, 4, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 20: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 21: k_hex8_nh_hvp_v2<2, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    default: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
   }
   if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();

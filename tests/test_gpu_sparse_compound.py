@@ -71,11 +71,11 @@ def test_direct_assembly_matches_coloured_oracle(kind, n):
     pat = sparse.pattern_from_mesh(mesh, dpn)
     cm = sparse.ColoredMatrix.from_csr(pat)
     data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
-    if kind != "hex8":  # both kernels: row-wise (default for single-point elements) and per-entry atomics
-        data_atomic = sparse.assembler(op, mat, cm, by_rows=False)(u).cpu().numpy()
-        assert _rel(data_atomic, data) < 1e-13
-        again = sparse.assembler(op, mat, cm, by_rows=True)(u).cpu().numpy()
-        assert np.array_equal(again, data), "row-wise assembly must be bitwise reproducible"
+    if kind != "hex8":  # both kernels: per-entry atomics (default) and the deterministic row-wise one
+        rows1 = sparse.assembler(op, mat, cm, by_rows=True)(u).cpu().numpy()
+        assert _rel(rows1, data) < 1e-13
+        rows2 = sparse.assembler(op, mat, cm, by_rows=True)(u).cpu().numpy()
+        assert np.array_equal(rows1, rows2), "row-wise assembly must be bitwise reproducible"
     # oracle 1: the reference algorithm, n_colors HVPs + decompression
     ndof = dpn * len(c)
     jvp = lambda seed: orc.hvp(kind, omat, c, el, u, seed.reshape(-1, dpn)).ravel()  # noqa: E731
