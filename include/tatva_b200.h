@@ -161,6 +161,17 @@ int tatva_halo_unpack_set(const double* d_src, const int64_t* d_idx, int64_t n, 
 int tatva_halo_unpack_add(const double* d_src, const int64_t* d_idx, int64_t n, double* d_dst,
                           tatva_stream_t stream);
 
+/* ---- lifter (tatva/lifter/base.py:201-251): reduced <-> full vectors with all constraints composed ----
+ * The constraints (Fixed, Periodic, applied in order; lifter/constraints.py:214-221, :312-318) are composed
+ * once on the host into one source table, so lift is ONE gather and reduce_adjoint ONE segmented sum:
+ *   lift:            out[i] = src[i] >= 0 ? u_red[src[i]] : (src[i] == -1 ? base[i] (0 if base is NULL)
+ *                                                                          : consts[-(src[i] + 2)])
+ *   reduce_adjoint:  r_red[j] = sum_{k in [ptr[j], ptr[j+1])} r_full[list[k]]   (fixed order: deterministic) */
+int tatva_lift(const double* d_u_red, const int64_t* d_src, const double* d_consts,
+               const double* d_base, int64_t n_full, double* d_out, tatva_stream_t stream);
+int tatva_reduce_adjoint(const double* d_r_full, const int64_t* d_ptr, const int64_t* d_list,
+                         int64_t n_red, double* d_out, tatva_stream_t stream);
+
 /* ---- host-side setup (C++, no GPU needed) -----------------------------------------------
  * pattern_from_mesh / _create_sparse_structure (tatva/sparse/_extraction.py:37-102):
  * two-call protocol: pass indices == NULL to get nnz (indptr is filled), then call again.   */

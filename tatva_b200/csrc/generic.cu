@@ -540,6 +540,28 @@ __global__ void __launch_bounds__(256) k_unpack_add(const double* __restrict__ s
   if (i < n) atomicAdd(dst + __ldg(idx + i), __ldg(src + i));
 }
 
+// ---- lifter: reduced <-> full maps --------------------------------------------------------------
+// lift:   out[i] = src[i] >= 0 ? u_red[src[i]] : (src[i] == -1 ? base[i] : consts[-(src[i] + 2)])
+// adjoint: r_red[j] = sum of r_full over the full DOFs that read reduced DOF j (fixed order)
+__global__ void __launch_bounds__(256) k_lift(const double* __restrict__ u_red, const int64_t* __restrict__ src,
+                                              const double* __restrict__ consts, const double* __restrict__ base,
+                                              int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t s = __ldg(src + i);
+  out[i] = s >= 0 ? __ldg(u_red + s) : (s == -1 ? (base ? __ldg(base + i) : 0.0) : __ldg(consts - (s + 2)));
+}
+__global__ void __launch_bounds__(256) k_reduce_adjoint(const double* __restrict__ r_full,
+                                                        const int64_t* __restrict__ ptr,
+                                                        const int64_t* __restrict__ list, int64_t n_red,
+                                                        double* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_red) return;
+  double s = 0.0;
+  for (int64_t k = __ldg(ptr + j); k < __ldg(ptr + j + 1); ++k) s += __ldg(r_full + __ldg(list + k));
+  out[j] = s;
+}
+
 // ---- FP64 FMA peak microbenchmark ---------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
@@ -937,6 +959,23 @@ int tatva_halo_unpack_add(const double* s, const int64_t* idx, int64_t n, double
   if (n == 0) return TATVA_OK;
   if (!s || !idx || !d || n < 0) return TATVA_E_INVALID;
   k_unpack_add<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, idx, n, d);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_lift(const double* d_u_red, const int64_t* d_src, const double* d_consts, const double* d_base,
+               int64_t n_full, double* d_out, tatva_stream_t stream) {
+  if (n_full == 0) return TATVA_OK;
+  if (!d_src || !d_out || n_full < 0) return TATVA_E_INVALID;
+  k_lift<<<grid_for(n_full, 256), 256, 0, (cudaStream_t)stream>>>(d_u_red, d_src, d_consts, d_base, n_full, d_out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_reduce_adjoint(const double* d_r_full, const int64_t* d_ptr, const int64_t* d_list, int64_t n_red,
+                         double* d_out, tatva_stream_t stream) {
+  if (n_red == 0) return TATVA_OK;
+  if (!d_r_full || !d_ptr || !d_list || !d_out || n_red < 0) return TATVA_E_INVALID;
+  k_reduce_adjoint<<<grid_for(n_red, 256), 256, 0, (cudaStream_t)stream>>>(d_r_full, d_ptr, d_list, n_red, d_out);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

@@ -1,0 +1,135 @@
+"""Lifter — known answers of the reference's tests/test_lifter.py and tests/test_lifter_residual.py (NumPy
+path), plus the CUDA kernels against the NumPy path (gpu)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from tatva_b200.lifter import Fixed, Lifter, LifterError, Periodic, RuntimeValue, lifted
+
+
+def test_lifter_without_constraints_roundtrips():
+    lifter = Lifter(4)
+    u = np.arange(4, dtype=np.float64)
+    full = lifter.lift_from_zeros(u)
+    np.testing.assert_array_equal(full, u)
+    np.testing.assert_array_equal(lifter.reduce(full), u)
+    assert lifter.constrained_dofs.size == 0
+
+
+def _example():
+    return Lifter(6, Fixed(np.array([0, 5], dtype=np.int32)), Periodic(dofs=np.array([2], dtype=np.int32), master_dofs=np.array([1], dtype=np.int32)))
+
+
+def test_lifter_applies_dirichlet_and_periodic_constraints():
+    """reference tests/test_lifter.py:27-43."""
+    lifter = _example()
+    u = np.array([10.0, 20.0, 30.0])
+    full = lifter.lift_from_zeros(u)
+    np.testing.assert_array_equal(full, [0.0, 10.0, 10.0, 20.0, 30.0, 0.0])
+    np.testing.assert_array_equal(lifter.reduce(full), u)
+    assert lifter.size_reduced == 3
+    np.testing.assert_array_equal(lifter.free_dofs, [1, 3, 4])
+    np.testing.assert_array_equal(lifter.constrained_dofs, [0, 2, 5])
+
+
+def test_constraints_and_lifter_are_hashable():
+    lifter = _example()
+    assert all(isinstance(hash(x), int) for x in (lifter, *lifter.constraints))
+
+
+def test_runtime_values():
+    """reference tests/test_lifter.py:80-91."""
+    lifter = Lifter(4, Fixed(np.array([0, 3], dtype=np.int32), RuntimeValue("top")))
+    with pytest.raises(LifterError):
+        lifter.lift_from_zeros(np.array([1.0, 2.0]))
+    lhs = lifter.with_values({"top": np.array([1.0, 2.0])})
+    rhs = lifter.at["top"].set(np.array([1.0, 2.0]))
+    diff = lifter.with_values({"top": np.array([1.0, 3.0])})
+    assert lhs == rhs and lhs != diff
+    np.testing.assert_array_equal(lhs.lift_from_zeros(np.array([5.0, 6.0])), [1.0, 5.0, 6.0, 2.0])
+    with pytest.raises(LifterError):
+        lifter.with_values({"bottom": 1.0})
+
+
+def test_lifted_decorator():
+    """reference tests/test_lifter.py:94-117."""
+    lifter = Lifter(4, Fixed(np.array([0, 3]), 0.0))
+    assert lifted(lambda u: u.sum(), argnums=0)(lifter, np.array([10.0, 20.0])) == 30.0
+    np.testing.assert_array_equal(lifted(lambda u: u * 2, argnums=0, output="primal")(lifter, np.array([10.0, 20.0])), [20.0, 40.0])
+    with pytest.raises(LifterError):
+        lifted(lambda u: u)(lifter, np.zeros(3))
+
+
+def test_reduce_adjoint_known_answers():
+    """reference tests/test_lifter_residual.py."""
+    r = np.array([10.0, 20.0, 30.0, 40.0])
+    per = Lifter(4, Periodic(dofs=np.array([2]), master_dofs=np.array([1])))
+    np.testing.assert_array_equal(per.reduce_adjoint(r), [10.0, 50.0, 40.0])
+    np.testing.assert_array_equal(Lifter(4, Fixed(np.array([0, 3]), 0.0)).reduce_adjoint(r), [20.0, 30.0])
+    both = Lifter(4, Periodic(dofs=np.array([2]), master_dofs=np.array([1])), Fixed(np.array([3]), 0.0))
+    np.testing.assert_array_equal(both.reduce_adjoint(r), [10.0, 50.0])
+    out = lifted(lambda u: u * 2.0, argnums=0, output="dual")(per, np.array([1.0, 2.0, 3.0]))
+    np.testing.assert_array_equal(out, [2.0, 8.0, 6.0])
+
+
+def test_reduce_adjoint_is_the_adjoint_of_lift_and_chains_compose():
+    rng = np.random.default_rng(0)
+    n = 40
+    lifter = Lifter(n, Fixed(np.array([0, 1, 39]), 2.5), Periodic(dofs=np.array([10, 11]), master_dofs=np.array([5, 6])), Periodic(dofs=np.array([20]), master_dofs=np.array([10])))
+    u, r = rng.normal(size=lifter.size_reduced), rng.normal(size=n)
+    lin = lifter.lift_from_zeros(u) - lifter.lift_from_zeros(np.zeros_like(u))
+    assert abs(lin @ r - u @ lifter.reduce_adjoint(r)) < 1e-12
+    full = lifter.lift_from_zeros(u)
+    assert full[20] == full[10] == full[5] and full[0] == 2.5
+
+
+def test_sparsity_adaptation():
+    S = sps.csr_matrix(np.array([[1, 1, 0, 0], [1, 1, 1, 0], [0, 1, 1, 1], [0, 0, 1, 1]], dtype=np.int8))
+    lifter = Lifter(4, Periodic(dofs=np.array([3]), master_dofs=np.array([0])))
+    R = lifter.adapt_sparsity(S)
+    assert R.shape == (3, 3)
+    assert R[0, 2] != 0 and R[2, 0] != 0  # master 0 inherits the coupling of its slave 3 with dof 2
+
+
+@pytest.mark.gpu
+def test_cuda_kernels_match_numpy_path():
+    import torch
+
+    rng = np.random.default_rng(1)
+    n = 10000
+    slaves = np.arange(100, 200)
+    lifter = Lifter(n, Fixed(np.arange(0, 50), rng.normal(size=50)), Periodic(dofs=slaves, master_dofs=slaves + 1000), Fixed(np.array([n - 1]), RuntimeValue("load", 3.0)))
+    u, r, base = rng.normal(size=lifter.size_reduced), rng.normal(size=n), rng.normal(size=n)
+    ut, rt, bt = (torch.as_tensor(a, device="cuda") for a in (u, r, base))
+    np.testing.assert_array_equal(lifter.lift_from_zeros(ut).cpu().numpy(), lifter.lift_from_zeros(u))
+    np.testing.assert_array_equal(lifter.lift(ut, bt).cpu().numpy(), lifter.lift(u, base))
+    np.testing.assert_array_equal(lifter.reduce(rt).cpu().numpy(), lifter.reduce(r))
+    np.testing.assert_allclose(lifter.reduce_adjoint(rt).cpu().numpy(), lifter.reduce_adjoint(r), rtol=1e-15, atol=1e-15)
+    l2 = lifter.at["load"].set(7.0)
+    assert float(l2.lift_from_zeros(ut)[-1]) == 7.0 and float(lifter.lift_from_zeros(ut)[-1]) == 3.0
+
+
+@pytest.mark.gpu
+def test_reduced_hvp_through_lifter_matches_oracle():
+    """Dirichlet-constrained Hex8 neo-Hookean operator: reduce_adjoint(H(lift(u)) lift_lin(v)) vs the oracle."""
+    import torch
+
+    import tatva_b200
+    from oracle import tatva_oracle as orc
+    from tatva_b200 import element, materials
+
+    rng = np.random.default_rng(2)
+    c, el = orc.mesh_box_hex(6)
+    c = c + 0.01 * rng.uniform(-1, 1, c.shape)
+    fixed_nodes = np.where(c[:, 0] < 0.02)[0]
+    load_nodes = np.where(c[:, 0] > 0.98)[0]
+    lifter = Lifter(c.size, Fixed((fixed_nodes[:, None] * 3 + np.arange(3)).ravel()), Fixed(load_nodes * 3 + 2, 0.05))
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8())
+    mat, omat = materials.NeoHookean(500.0, 1000.0), orc.NeoHookean(500.0, 1000.0)
+    u_red, v_red = 0.01 * rng.normal(size=lifter.size_reduced), rng.normal(size=lifter.size_reduced)
+    zero_bc = Lifter(c.size, Fixed(lifter.constrained_dofs))  # tangent directions vanish on constrained DOFs
+    u_full = lifter.lift_from_zeros(torch.as_tensor(u_red, device="cuda"))
+    v_full = zero_bc.lift_from_zeros(torch.as_tensor(v_red, device="cuda"))
+    Hv = lifter.reduce_adjoint(op.hvp(mat)(u_full.view(-1, 3), v_full.view(-1, 3)).reshape(-1))
+    ref = lifter.reduce_adjoint(orc.hvp("hex8", omat, c, el, lifter.lift_from_zeros(u_red).reshape(-1, 3), zero_bc.lift_from_zeros(v_red).reshape(-1, 3)).ravel())
+    assert np.linalg.norm(Hv.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-12
