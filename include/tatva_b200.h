@@ -172,6 +172,17 @@ int tatva_lift(const double* d_u_red, const int64_t* d_src, const double* d_cons
 int tatva_reduce_adjoint(const double* d_r_full, const int64_t* d_ptr, const int64_t* d_list,
                          int64_t n_red, double* d_out, tatva_stream_t stream);
 
+/* ---- device-resident CG around the matrix-free HVP (the reference has no solver:
+ * its docstrings hand H v to an external one, tatva/mpi.py:594-595) ----------------------------------------
+ * Scalars stay on the device: d_scalars[0] = r.r, [1] = p.Ap, [2] = next r.r (>= 4 doubles); d_partials holds
+ * 1184 per-CTA partial sums.  Dots are two-pass with a fixed summation order (deterministic).
+ *   tatva_cg_dot(a, b, ..., slot):  d_scalars[slot] = a.b
+ *   tatva_cg_after_matvec:  alpha = s0/(p.Ap); x += alpha p; r -= alpha Ap; beta = (r.r)/s0; p = r + beta p; s0 = r.r */
+int tatva_cg_dot(const double* d_a, const double* d_b, int64_t n, double* d_partials,
+                 double* d_scalars, int slot, tatva_stream_t stream);
+int tatva_cg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap, int64_t n,
+                          double* d_partials, double* d_scalars, tatva_stream_t stream);
+
 /* ---- host-side setup (C++, no GPU needed) -----------------------------------------------
  * pattern_from_mesh / _create_sparse_structure (tatva/sparse/_extraction.py:37-102):
  * two-call protocol: pass indices == NULL to get nnz (indptr is filled), then call again.   */

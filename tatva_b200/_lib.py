@@ -51,6 +51,8 @@ SIGNATURES = {
     "tatva_halo_unpack_add": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_lift": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_reduce_adjoint": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
+    "tatva_cg_dot": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp]),
+    "tatva_cg_after_matvec": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "tatva_host_pattern_from_mesh": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, C.c_int, c_i32p, c_i32p, c_i64p]),
     "tatva_host_distance2_colors": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p]),
     "tatva_host_node_to_elements": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, c_i32p, c_i32p]),

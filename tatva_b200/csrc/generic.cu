@@ -562,6 +562,51 @@ __global__ void __launch_bounds__(256) k_reduce_adjoint(const double* __restrict
   out[j] = s;
 }
 
+// ---- device-resident conjugate gradient: fused vector kernels, scalars never leave the device --------
+// s[0] = r.r (current), s[1] = p.Ap, s[2] = r.r (next); partial sums in `part` (one slot per CTA, two lanes).
+constexpr int kCgBlocks = 1184;  // 148 SMs x 8 CTAs
+
+__global__ void __launch_bounds__(256) k_cg_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                                                double* __restrict__ part) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += __ldg(a + i) * __ldg(b + i);
+  s = block_sum(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+// out[slot] = sum(part[0..nblocks))  (single CTA, fixed order)
+__global__ void __launch_bounds__(256) k_cg_finish(const double* __restrict__ part, int nblocks, double* __restrict__ s,
+                                                   int slot) {
+  double t = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) t += part[b];
+  t = block_sum(t);
+  if (threadIdx.x == 0) s[slot] = t;
+}
+// alpha = s[0] / s[1];  x += alpha p;  r -= alpha Ap;  partial of r.r
+__global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, double* __restrict__ r,
+                                                   const double* __restrict__ p, const double* __restrict__ Ap,
+                                                   int64_t n, const double* __restrict__ s, double* __restrict__ part) {
+  const double alpha = s[0] / s[1];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, __ldg(p + i), x[i]);
+    const double ri = fma(-alpha, __ldg(Ap + i), r[i]);
+    r[i] = ri;
+    acc = fma(ri, ri, acc);
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+// beta = s[2] / s[0];  p = r + beta p;  then s[0] <- s[2] (done by CTA 0 after its own work; readers use the
+// value loaded at entry)
+__global__ void __launch_bounds__(256) k_cg_direction(double* __restrict__ p, const double* __restrict__ r, int64_t n,
+                                                      double* __restrict__ s) {
+  const double beta = s[2] / s[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], __ldg(r + i));
+}
+__global__ void k_cg_roll(double* __restrict__ s) { s[0] = s[2]; }
+
 // ---- FP64 FMA peak microbenchmark ---------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
@@ -976,6 +1021,34 @@ int tatva_reduce_adjoint(const double* d_r_full, const int64_t* d_ptr, const int
   if (n_red == 0) return TATVA_OK;
   if (!d_r_full || !d_ptr || !d_list || !d_out || n_red < 0) return TATVA_E_INVALID;
   k_reduce_adjoint<<<grid_for(n_red, 256), 256, 0, (cudaStream_t)stream>>>(d_r_full, d_ptr, d_list, n_red, d_out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// One CG iteration's vector work, in two calls around the operator application Ap = A p:
+//   tatva_cg_after_matvec: s[1] = p.Ap ; alpha = s[0]/s[1] ; x += alpha p ; r -= alpha Ap ; s[2] = r.r ;
+//                          beta = s[2]/s[0] ; p = r + beta p ; s[0] = s[2]
+// `d_scalars` (>= 4 doubles) and `d_partials` (>= 1184 doubles) are caller-owned device buffers; s[0] must
+// hold r.r on entry (tatva_cg_dot(r, r, ..., slot 0)).  Everything is stream-ordered: no host round trip.
+int tatva_cg_dot(const double* d_a, const double* d_b, int64_t n, double* d_partials, double* d_scalars, int slot,
+                 tatva_stream_t stream) {
+  if (!d_a || !d_b || !d_partials || !d_scalars || n <= 0 || slot < 0 || slot > 3) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_cg_dot<<<kCgBlocks, 256, 0, st>>>(d_a, d_b, n, d_partials);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, slot);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_cg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap, int64_t n, double* d_partials,
+                          double* d_scalars, tatva_stream_t stream) {
+  if (!d_x || !d_r || !d_p || !d_Ap || !d_partials || !d_scalars || n <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_cg_dot<<<kCgBlocks, 256, 0, st>>>(d_p, d_Ap, n, d_partials);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 1);
+  k_cg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, n, d_scalars, d_partials);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 2);
+  k_cg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, n, d_scalars);
+  k_cg_roll<<<1, 1, 0, st>>>(d_scalars);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

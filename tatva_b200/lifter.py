@@ -180,7 +180,7 @@ class Lifter:
         new = type(self).__new__(type(self))
         new.__dict__ = dict(self.__dict__)
         new._runtime_values = {**self._runtime_values, **updates}
-        new._tables, new._dev = None, {}
+        new._tables, new._dev, new._homogeneous = None, {}, None
         return new
 
     # -- composed tables ------------------------------------------------------------------------------
@@ -212,13 +212,15 @@ class Lifter:
         return torch.cuda.current_stream().cuda_stream
 
     # -- reference API -----------------------------------------------------------------------------------
-    def lift(self, u_reduced, u_full):
-        """Full vector with free DOFs = u_reduced and every constraint applied (lifter/base.py:201-229)."""
+    def lift(self, u_reduced, u_full, out=None):
+        """Full vector with free DOFs = u_reduced and every constraint applied (lifter/base.py:201-229).
+        `out` (CUDA only) receives the result without allocating (CUDA-graph friendly)."""
         if torch is not None and isinstance(u_reduced, torch.Tensor) and u_reduced.is_cuda:
             src, consts, _, _, _ = self._device_tables(u_reduced.device)
             ur = u_reduced.contiguous()
             base = None if u_full is None else torch.as_tensor(u_full, device=ur.device, dtype=ur.dtype).contiguous()
-            out = torch.empty(self.size, dtype=ur.dtype, device=ur.device)
+            if out is None:
+                out = torch.empty(self.size, dtype=ur.dtype, device=ur.device)
             with torch.cuda.device(ur.device):
                 _lib.check(_lib.lib().tatva_lift(ur.data_ptr(), src.data_ptr(), consts.data_ptr(), base.data_ptr() if base is not None else None, self.size, out.data_ptr(), self._stream()), "tatva_lift")
             return out
@@ -231,8 +233,8 @@ class Lifter:
         out[cst] = consts[-(src[cst] + 2)]
         return out
 
-    def lift_from_zeros(self, u_reduced):
-        return self.lift(u_reduced, None)
+    def lift_from_zeros(self, u_reduced, out=None):
+        return self.lift(u_reduced, None, out=out) if out is not None else self.lift(u_reduced, None)
 
     def reduce(self, u_full):
         """u_full[free_dofs] (lifter/base.py:231-233)."""
@@ -245,13 +247,14 @@ class Lifter:
             return out
         return _np(u_full)[self.free_dofs]
 
-    def reduce_adjoint(self, r_full):
+    def reduce_adjoint(self, r_full, out=None):
         """Reduced dual vector: constrained contributions folded back onto the DOFs that drive them
         (lifter/base.py:235-251: transposes in reverse order, then [free_dofs])."""
         if torch is not None and isinstance(r_full, torch.Tensor) and r_full.is_cuda:
             _, _, ptr, lst, _ = self._device_tables(r_full.device)
             rf = r_full.contiguous()
-            out = torch.empty(self.size_reduced, dtype=rf.dtype, device=rf.device)
+            if out is None:
+                out = torch.empty(self.size_reduced, dtype=rf.dtype, device=rf.device)
             with torch.cuda.device(rf.device):
                 _lib.check(_lib.lib().tatva_reduce_adjoint(rf.data_ptr(), ptr.data_ptr(), lst.data_ptr(), self.size_reduced, out.data_ptr(), self._stream()), "tatva_reduce_adjoint")
             return out
@@ -259,6 +262,16 @@ class Lifter:
         rf = _np(r_full)
         readers = src >= 0
         return np.bincount(src[readers], weights=rf[readers], minlength=self.size_reduced).astype(rf.dtype)
+
+    def homogeneous(self) -> "Lifter":
+        """Lifter with the same free DOFs whose constrained values are all zero: the lift of a tangent
+        (Newton / CG direction), d(lift)/d(u_reduced)."""
+        if getattr(self, "_homogeneous", None) is None:
+            hom = []
+            for c in self.constraints:
+                hom.append(Fixed(c.dofs, 0.0) if isinstance(c, Fixed) else c)
+            self._homogeneous = Lifter(self.size, *hom)
+        return self._homogeneous
 
     # -- sparsity (lifter/base.py:281-331) ----------------------------------------------------------------
     def augment_sparsity(self, sparsity):

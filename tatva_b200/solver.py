@@ -1,0 +1,148 @@
+"""Device-resident conjugate gradient and Newton step around the matrix-free HVP.
+
+The reference ships no solver: its docstrings hand `H v` to an external one (tatva/mpi.py:594-595, :615-616).
+BASELINE.json's config 3 is "matrix-free HVP inside a CG/Newton step", so this module provides that step in the
+B200 style: every vector stays in HBM, the CG scalars (r.r, p.Ap) stay in device memory, one iteration is
+[operator application] + `tatva_cg_after_matvec` (six small kernels, deterministic two-pass dots), and the whole
+iteration is captured once in a CUDA graph and replayed; the host only looks at the residual norm every
+`check_every` iterations.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable
+
+import torch
+
+from . import _lib
+
+
+class ConjugateGradient:
+    """Solve A x = b for a symmetric positive definite operator given as `matvec(p, out)` (writes A p into `out`
+    in place, on torch's current stream, without allocating)."""
+
+    def __init__(self, matvec: Callable, n: int, device, use_graph: bool = True):
+        self.matvec, self.n, self.device = matvec, int(n), torch.device(device)
+        mk = lambda m: torch.zeros(m, dtype=torch.float64, device=self.device)  # noqa: E731
+        self.x, self.r, self.p, self.Ap = mk(n), mk(n), mk(n), mk(n)
+        self.scalars, self.partials = mk(4), mk(1184)
+        self.use_graph = use_graph
+        self._graph = None
+        self._L = _lib.lib()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dot(self, a, b, slot):
+        _lib.check(self._L.tatva_cg_dot(a.data_ptr(), b.data_ptr(), self.n, self.partials.data_ptr(), self.scalars.data_ptr(), slot, self._stream()), "tatva_cg_dot")
+
+    def _iteration(self):
+        self.matvec(self.p, self.Ap)
+        _lib.check(
+            self._L.tatva_cg_after_matvec(self.x.data_ptr(), self.r.data_ptr(), self.p.data_ptr(), self.Ap.data_ptr(), self.n, self.partials.data_ptr(), self.scalars.data_ptr(), self._stream()),
+            "tatva_cg_after_matvec",
+        )
+
+    def _capture(self):
+        # warm up on a side stream (lazy initialisation must not happen inside the capture), then capture
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            saved = [t.clone() for t in (self.x, self.r, self.p, self.scalars)]
+            self._iteration()
+            for t, s in zip((self.x, self.r, self.p, self.scalars), saved):
+                t.copy_(s)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration()
+        self._graph = g
+
+    def solve(self, b: torch.Tensor, x0: torch.Tensor | None = None, tol: float = 1e-10, maxiter: int = 1000, check_every: int = 10):
+        """Returns (x, info) with info = dict(iterations, residual_norm, converged).  Stops when
+        ||r|| <= tol * ||b||."""
+        with torch.cuda.device(self.device):
+            if x0 is None:
+                self.x.zero_()
+                self.r.copy_(b)
+            else:
+                self.x.copy_(x0)
+                self.matvec(self.x, self.Ap)
+                torch.sub(b, self.Ap, out=self.r)
+            self.p.copy_(self.r)
+            self._dot(self.r, self.r, 0)
+            self._dot(b, b, 3)
+            rr0, bb = (float(v) for v in self.scalars[[0, 3]].tolist())
+            if bb == 0.0 or math.sqrt(rr0) <= tol * math.sqrt(bb):
+                return self.x.clone(), dict(iterations=0, residual_norm=math.sqrt(rr0), converged=True)
+            if self.use_graph and self._graph is None:
+                saved = [t.clone() for t in (self.x, self.r, self.p, self.scalars)]
+                self._capture()  # capturing replays nothing; the first graph launch is iteration 1
+                for t, s in zip((self.x, self.r, self.p, self.scalars), saved):
+                    t.copy_(s)
+            it, rr = 0, rr0
+            while it < maxiter:
+                for _ in range(min(check_every, maxiter - it)):
+                    if self._graph is not None:
+                        self._graph.replay()
+                    else:
+                        self._iteration()
+                    it += 1
+                rr = float(self.scalars[0])
+                if not math.isfinite(rr) or math.sqrt(rr) <= tol * math.sqrt(bb):
+                    break
+            return self.x.clone(), dict(iterations=it, residual_norm=math.sqrt(max(rr, 0.0)), converged=math.isfinite(rr) and math.sqrt(rr) <= tol * math.sqrt(bb))
+
+
+class ReducedOperator:
+    """The constrained tangent and residual of E(u) on the free DOFs of a Lifter:
+        r_red(u_red) = reduce_adjoint(dE/du(lift(u_red))),    K_red v = reduce_adjoint(H(lift(u_red)) lift_0(v)),
+    with work vectors preallocated so that `matvec` can sit inside a CUDA graph."""
+
+    def __init__(self, op, material, lifter):
+        self.op, self.material, self.lifter = op, material, lifter
+        self.hom = lifter.homogeneous()
+        dev = op.device
+        self.u_full = torch.zeros(lifter.size, dtype=torch.float64, device=dev)
+        self.v_full = torch.zeros(lifter.size, dtype=torch.float64, device=dev)
+        self.y_full = torch.zeros(lifter.size, dtype=torch.float64, device=dev)
+
+    def set_state(self, u_reduced: torch.Tensor):
+        self.lifter.lift_from_zeros(u_reduced, out=self.u_full)
+
+    def residual(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        r_full = self.op._raw_residual(self.material, self.u_full)
+        return self.lifter.reduce_adjoint(r_full, out=out)
+
+    def energy(self) -> float:
+        return float(self.op._raw_energy(self.material, self.u_full))
+
+    def matvec(self, v_reduced: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        self.hom.lift_from_zeros(v_reduced, out=self.v_full)
+        self.op._raw_hvp(self.material, self.u_full, self.v_full, out=self.y_full)
+        return self.lifter.reduce_adjoint(self.y_full, out=out)
+
+
+def newton_solve(op, material, lifter, u0_reduced=None, *, tol: float = 1e-8, max_newton: int = 20, cg_tol: float = 1e-10, cg_maxiter: int = 2000, use_graph: bool = True):
+    """Minimise E(lift(u_red)) by Newton's method; every linear solve is a matrix-free CG on the HVP kernel.
+    Returns (u_reduced, history) with history = list of dict(newton, residual_norm, cg_iterations)."""
+    dev = op.device
+    red = ReducedOperator(op, material, lifter)
+    n = lifter.size_reduced
+    u = torch.zeros(n, dtype=torch.float64, device=dev) if u0_reduced is None else torch.as_tensor(u0_reduced, dtype=torch.float64, device=dev).clone()
+    cg = ConjugateGradient(red.matvec, n, dev, use_graph=use_graph)
+    r = torch.empty(n, dtype=torch.float64, device=dev)
+    history = []
+    r0 = None
+    for k in range(max_newton):
+        red.set_state(u)
+        red.residual(out=r)
+        rn = float(r.norm())
+        r0 = rn if r0 is None else r0
+        if rn <= tol * max(r0, 1e-300) or rn == 0.0:
+            history.append(dict(newton=k, residual_norm=rn, cg_iterations=0))
+            break
+        du, info = cg.solve(-r, tol=cg_tol, maxiter=cg_maxiter)
+        history.append(dict(newton=k, residual_norm=rn, cg_iterations=info["iterations"], cg_converged=info["converged"]))
+        u = u + du
+    return u, history

@@ -1,0 +1,75 @@
+"""Device-resident CG / Newton step around the HVP kernel (GPU): against SciPy on the oracle's matrices."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spla
+import torch
+
+from oracle import tatva_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n=5):
+    import tatva_b200
+    from tatva_b200 import element, materials
+    from tatva_b200.lifter import Fixed, Lifter
+
+    rng = np.random.default_rng(0)
+    c, el = orc.mesh_box_hex(n)
+    c = c + 0.01 * rng.uniform(-1, 1, c.shape)
+    fixed = np.where(c[:, 2] < 0.02)[0]
+    top = np.where(c[:, 2] > 0.98)[0]
+    lifter = Lifter(c.size, Fixed((fixed[:, None] * 3 + np.arange(3)).ravel()), Fixed(top * 3 + 2, 0.08), Fixed((top[:, None] * 3 + np.arange(2)).ravel()))
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8())
+    return c, el, lifter, op, materials.NeoHookean(500.0, 1000.0), orc.NeoHookean(500.0, 1000.0)
+
+
+def _oracle_K(c, el, omat, u_full, lifter):
+    ip, ix = orc.pattern_from_mesh(el, len(c), 3)
+    data = orc.assemble_csr_data("hex8", omat, c, el, u_full.reshape(-1, 3), ip, ix)
+    K = sps.csr_matrix((data, ix, ip), shape=(c.size, c.size))
+    f = lifter.free_dofs
+    return K[f][:, f]
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_cg_solves_the_reduced_tangent_system(use_graph):
+    from tatva_b200.solver import ConjugateGradient, ReducedOperator
+
+    c, el, lifter, op, mat, omat = _problem()
+    rng = np.random.default_rng(1)
+    u_red = 0.005 * rng.normal(size=lifter.size_reduced)
+    b = rng.normal(size=lifter.size_reduced)
+    red = ReducedOperator(op, mat, lifter)
+    red.set_state(torch.as_tensor(u_red, device="cuda"))
+    cg = ConjugateGradient(red.matvec, lifter.size_reduced, "cuda", use_graph=use_graph)
+    x, info = cg.solve(torch.as_tensor(b, device="cuda"), tol=1e-12, maxiter=2000, check_every=20)
+    assert info["converged"], info
+    K = _oracle_K(c, el, omat, lifter.lift_from_zeros(u_red), lifter)
+    x_ref = spla.spsolve(K.tocsc(), b)
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) / np.linalg.norm(x_ref) < 1e-9
+    # a second solve reuses the captured graph
+    x2, info2 = cg.solve(torch.as_tensor(2 * b, device="cuda"), tol=1e-12, maxiter=2000, check_every=20)
+    assert info2["converged"] and np.linalg.norm(x2.cpu().numpy() - 2 * x_ref) / np.linalg.norm(x_ref) < 1e-8
+
+
+def test_newton_step_converges_to_the_oracle_minimiser():
+    from tatva_b200.solver import newton_solve
+
+    c, el, lifter, op, mat, omat = _problem(4)
+    u, hist = newton_solve(op, mat, lifter, tol=1e-9, cg_tol=1e-11)
+    assert hist[-1]["residual_norm"] <= 1e-9 * hist[0]["residual_norm"], hist
+    assert len(hist) <= 10
+    # oracle Newton with direct solves
+    ur = np.zeros(lifter.size_reduced)
+    for _ in range(12):
+        uf = lifter.lift_from_zeros(ur)
+        r = lifter.reduce_adjoint(orc.residual("hex8", omat, c, el, uf.reshape(-1, 3)).ravel())
+        if np.linalg.norm(r) < 1e-10:
+            break
+        ur = ur - spla.spsolve(_oracle_K(c, el, omat, uf, lifter).tocsc(), r)
+    assert np.linalg.norm(u.cpu().numpy() - ur) / np.linalg.norm(ur) < 1e-7
+    e_gpu = float(op.energy(mat)(lifter.lift_from_zeros(u).view(-1, 3)))
+    e_ref = orc.energy("hex8", omat, c, el, lifter.lift_from_zeros(ur).reshape(-1, 3))
+    assert abs(e_gpu - e_ref) <= 1e-10 * abs(e_ref)
