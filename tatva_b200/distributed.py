@@ -118,7 +118,7 @@ class PartitionedOperator:
         prm, n = self._prm
         args = (u.data_ptr(), v.data_ptr(), y.data_ptr()) if v is not None else (u.data_ptr(), y.data_ptr())
         with torch.cuda.device(self.device):
-            _lib.check(getattr(self._L, name)(self.op._plan, self.material.material_id, prm, n, *args, begin, count, zero, torch.cuda.current_stream().cuda_stream), name)
+            _lib.check(getattr(self._L, name)(self.op._plan_fused, self.material.material_id, prm, n, *args, begin, count, zero, torch.cuda.current_stream().cuda_stream), name)
 
     def _apply(self, name, u_local, v_local, y_local):
         E, nb = self.op.n_elements, self.n_boundary

@@ -144,3 +144,67 @@ def block_partition(nb_elems, nparts):
     py = (j * grid[1]) // ny
     pz = (k * grid[2]) // nz
     return (px + grid[0] * (py + grid[1] * pz)).ravel().astype(np.int32)
+
+
+def _spread_bits(x: np.ndarray, dim: int) -> np.ndarray:
+    """Insert dim-1 zero bits between the low 21 bits of x (Morton / Z-order interleave)."""
+    x = x.astype(np.uint64) & np.uint64((1 << 21) - 1)
+    if dim == 3:
+        x = (x | (x << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+        x = (x | (x << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x1249249249249249)
+    else:
+        x = (x | (x << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x3333333333333333)
+        x = (x | (x << np.uint64(1))) & np.uint64(0x5555555555555555)
+    return x
+
+
+def locality_order(coords, elements) -> np.ndarray:
+    """Permutation that sorts the elements along a Morton (Z-order) curve through their centroids —
+    the locality-preserving ordering the element-per-thread kernels want: consecutive threads then touch
+    nearby nodes, so the gathers of a warp share L1/L2 lines.  Returns `perm` with new element k = old
+    element perm[k]."""
+    c = _np(coords)
+    el = _np(elements)
+    dim = c.shape[1]
+    cen = c[el].mean(axis=1)
+    lo, hi = cen.min(axis=0), cen.max(axis=0)
+    q = ((cen - lo) / np.where(hi > lo, hi - lo, 1.0) * ((1 << 21) - 1)).astype(np.uint64)
+    key = np.zeros(len(el), dtype=np.uint64)
+    for d in range(min(dim, 3)):
+        key |= _spread_bits(q[:, d], 3 if dim >= 3 else 2) << np.uint64(d)
+    return np.argsort(key, kind="stable")
+
+
+def renumber_nodes_by_first_touch(elements) -> np.ndarray:
+    """node_perm with new node k = old node node_perm[k], nodes numbered in the order the (already
+    locality-sorted) elements first touch them; unreferenced nodes keep their relative order at the end."""
+    el = _np(elements)
+    flat = el.ravel()
+    _, first = np.unique(flat, return_index=True)
+    touched = flat[np.sort(first)]
+    n = int(flat.max()) + 1
+    rest = np.setdiff1d(np.arange(n), touched, assume_unique=False)
+    return np.concatenate([touched, rest])
+
+
+def reorder_mesh(mesh: Mesh, nodes: bool = True):
+    """Locality-reordered copy of `mesh`: elements along a Morton curve and (optionally) nodes by first touch.
+    Returns (new_mesh, elem_perm, node_perm): new element k = old elem_perm[k]; new node k = old node_perm[k]
+    (nodal vectors move as u_new = u_old[node_perm], results back as r_old[node_perm] = r_new)."""
+    c, el = _np(mesh.coords), _np(mesh.elements)
+    elem_perm = locality_order(c, el)
+    el_sorted = el[elem_perm]
+    if not nodes:
+        return Mesh(coords=c, elements=el_sorted), elem_perm, np.arange(c.shape[0])
+    node_perm = renumber_nodes_by_first_touch(el_sorted)
+    if node_perm.size < c.shape[0]:
+        node_perm = np.concatenate([node_perm, np.arange(node_perm.size, c.shape[0])])
+    inv = np.empty(c.shape[0], dtype=np.int64)
+    inv[node_perm] = np.arange(c.shape[0])
+    return Mesh(coords=c[node_perm], elements=inv[el_sorted].astype(el.dtype)), elem_perm, node_perm

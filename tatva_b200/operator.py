@@ -26,12 +26,15 @@ from .element import Element
 from .mesh import Mesh
 
 
+_FUSED_CALLS = {"tatva_energy", "tatva_residual", "tatva_hvp", "tatva_csr_assemble", "tatva_csr_assemble_rows"}
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
 class Operator:
-    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None):
+    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None, sort_elements: bool = False):
         self.mesh = mesh
         self.element = element
         self.cache_weights = bool(cache_weights)
@@ -62,15 +65,29 @@ class Operator:
                 "tatva_plan_create",
             )
         self._plan = handle
+        # Fused energy / residual / HVP / assembly are order-independent sums over elements, so they may run
+        # on a locality-sorted copy of the connectivity (Morton order of centroids); the (E, Q, ...)-shaped
+        # building blocks keep the caller's element order.
+        self._plan_fused, self.elements_fused = self._plan, self.elements
+        if sort_elements:
+            from .mesh import locality_order
+
+            perm = torch.as_tensor(locality_order(self.coords.cpu().numpy(), self.elements.cpu().numpy()), device=self.device)
+            self.elements_fused = self.elements[perm].contiguous()
+            h2 = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.tatva_plan_create(C.byref(h2), element.kind, self.n_nodes, self.n_elements, self.coords.data_ptr(), self.elements_fused.data_ptr(), 0, _stream()), "tatva_plan_create")
+            self._plan_fused = h2
 
     def __del__(self):
-        plan = getattr(self, "_plan", None)
-        if plan is not None and getattr(self, "_L", None) is not None:
+        L = getattr(self, "_L", None)
+        plans = {id(p): p for p in (getattr(self, "_plan", None), getattr(self, "_plan_fused", None)) if p is not None}
+        for plan in plans.values():
             try:
-                self._L.tatva_plan_destroy(plan)
+                L.tatva_plan_destroy(plan)
             except Exception:
                 pass
-            self._plan = None
+        self._plan = self._plan_fused = None
 
     # operator.py:132-170
     @staticmethod
@@ -102,11 +119,13 @@ class Operator:
 
     def set_variant(self, variant: int) -> None:
         """Select the Hex8 neo-Hookean HVP kernel variant (benchmarking aid)."""
-        _lib.check(self._L.tatva_plan_set_variant(self._plan, int(variant)), "tatva_plan_set_variant")
+        for plan in {id(p): p for p in (self._plan, self._plan_fused)}.values():
+            _lib.check(self._L.tatva_plan_set_variant(plan, int(variant)), "tatva_plan_set_variant")
 
     def _call(self, name, *args):
+        plan = self._plan_fused if name in _FUSED_CALLS else self._plan
         with torch.cuda.device(self.device):
-            _lib.check(getattr(self._L, name)(self._plan, *args, _stream()), name)
+            _lib.check(getattr(self._L, name)(plan, *args, _stream()), name)
 
     # raw (non-differentiable) kernel wrappers; nodal arrays are (N, nv) contiguous
     def _k_grad(self, u2):

@@ -179,7 +179,7 @@ class _Assembler:
         indices = np.ascontiguousarray(_np(colored_matrix.indices), dtype=np.int32)
         if indptr.shape[0] - 1 != op.n_nodes * dpn:
             raise ValueError("sparsity pattern size does not match n_nodes * dofs_per_node")
-        conn = np.ascontiguousarray(op.elements.cpu().numpy(), dtype=np.int32)
+        conn = np.ascontiguousarray(op.elements_fused.cpu().numpy(), dtype=np.int32)  # the order the fused kernels run in
         pos = np.empty((conn.shape[0], conn.shape[1], conn.shape[1]), dtype=np.int32)
         _lib.check(
             _lib.lib().tatva_host_csr_element_positions(_i32p(conn), conn.shape[0], conn.shape[1], dpn, _i32p(indptr), _i32p(indices), _i32p(pos)),

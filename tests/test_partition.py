@@ -41,3 +41,30 @@ def test_extract_local_mesh_matches_oracle_restatement():
         np.testing.assert_array_equal(m.elements, el_l)
         np.testing.assert_array_equal(info.nodes_local_to_global, l2g)
         assert info.n_owned_nodes == n_owned
+
+
+def test_locality_reordering_is_a_consistent_permutation():
+    from tatva_b200.mesh import locality_order, reorder_mesh
+
+    rng = np.random.default_rng(0)
+    c, el = orc.mesh_box_tet((1, 1, 1), (8, 8, 8))
+    shuffle_e, shuffle_n = rng.permutation(el.shape[0]), rng.permutation(c.shape[0])
+    inv = np.empty_like(shuffle_n)
+    inv[shuffle_n] = np.arange(len(shuffle_n))
+    bad = Mesh(coords=c[shuffle_n], elements=inv[el[shuffle_e]].astype(np.int32))
+    new, ep, npm = reorder_mesh(bad)
+    assert sorted(ep.tolist()) == list(range(el.shape[0])) and sorted(npm.tolist()) == list(range(c.shape[0]))
+    np.testing.assert_array_equal(new.coords[new.elements], bad.coords[bad.elements[ep]])  # same geometry per element
+    # locality: consecutive elements are close in space, and node ids within an element are close
+    cen = new.coords[new.elements].mean(axis=1)
+    cen_bad = bad.coords[bad.elements].mean(axis=1)
+    assert np.linalg.norm(np.diff(cen, axis=0), axis=1).mean() < 0.35 * np.linalg.norm(np.diff(cen_bad, axis=0), axis=1).mean()
+    span = lambda e: (e.max(axis=1) - e.min(axis=1)).mean()  # noqa: E731
+    assert span(new.elements) < 0.35 * span(bad.elements)
+    # the oracle residual is invariant under the permutation
+    mat = orc.NeoHookean(500.0, 1000.0)
+    u = 0.01 * rng.normal(size=c.shape)
+    r_bad = orc.residual("tet4", mat, bad.coords, bad.elements, u)
+    r_new = orc.residual("tet4", mat, new.coords, new.elements, u[npm])
+    np.testing.assert_allclose(r_new, r_bad[npm], rtol=1e-12, atol=1e-12)
+    assert sorted(locality_order(c, el).tolist()) == list(range(el.shape[0]))

@@ -117,3 +117,50 @@ if want("hex8"):
     report("hex8_op_eval_64", timeit(lambda: op._k_eval(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "qp")
     report("hex8_op_weights_64", timeit(lambda: op.get_integration_weights()), 8 * (3 * N + 8 * E) + 32 * E, E * 8, "qp")
     report("hex8_op_gather_64", timeit(lambda: op._k_gather(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "node-ref")
+
+# ---- config 3 in context: one CG iteration around the HVP (Hex8 128^3, Dirichlet face), CUDA graph on/off ----
+if want("cg"):
+    from bench import synthetic_inputs
+    from tatva_b200.lifter import Fixed, Lifter
+    from tatva_b200.solver import ConjugateGradient, ReducedOperator
+    c, el, u_, v_ = synthetic_inputs(128)
+    op = tatva_b200.Operator(Mesh(coords=c, elements=el), element.Hexahedron8())
+    mat = materials.NeoHookean(500.0, 1000.0)
+    fixed = np.where(c[:, 2] < 0.5 / 128)[0]
+    lifter = Lifter(c.size, Fixed((fixed[:, None] * 3 + np.arange(3)).ravel()))
+    red = ReducedOperator(op, mat, lifter)
+    red.set_state(lifter.reduce(torch.as_tensor(0.02 * u_.ravel(), device="cuda")))  # small strains: SPD tangent
+    n = lifter.size_reduced
+    b = torch.as_tensor(np.random.default_rng(3).normal(size=n), device="cuda")
+    for graph in (False, True):
+        cg = ConjugateGradient(red.matvec, n, "cuda", use_graph=graph)
+        cg.solve(b, tol=0.0, maxiter=20, check_every=20)  # warm-up + capture
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        x, info = cg.solve(b, tol=0.0, maxiter=200, check_every=50)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / info["iterations"]
+        report(f"cg_iteration_hex8_128_{'graph' if graph else 'eager'}", ms, 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 11 * n, n, "DOF", iterations=info["iterations"], residual_norm=info["residual_norm"])
+
+# ---- locality: the same Tet4 config-2 mesh with elements AND nodes randomly shuffled, then re-sorted ----
+if want("locality"):
+    from tatva_b200.mesh import reorder_mesh
+    rng = np.random.default_rng(0)
+    m = Mesh.box_tet((1.0, 1.0, 1.0), (55, 55, 55))
+    c = m.coords + np.array([0.5, 0.5, 0.0]) + 0.1 / 55 * rng.uniform(-1, 1, m.coords.shape)
+    el = m.elements
+    pe, pn = rng.permutation(el.shape[0]), rng.permutation(c.shape[0])
+    inv = np.empty_like(pn); inv[pn] = np.arange(len(pn))
+    shuffled = Mesh(coords=c[pn], elements=inv[el[pe]].astype(np.int32))
+    mat = materials.NeoHookean(500.0, 1000.0)
+    N, E = c.shape[0], el.shape[0]
+    t0 = time.perf_counter(); resorted, ep, npm = reorder_mesh(shuffled); t_sort = time.perf_counter() - t0
+    for name, mesh, kw in (("given_order", Mesh(coords=c, elements=el), {}), ("shuffled", shuffled, {}), ("shuffled_sort_elements", shuffled, dict(sort_elements=True)), ("reordered_elements_and_nodes", resorted, {})):
+        op = tatva_b200.Operator(mesh, element.Tetrahedron4(), **kw)
+        u = torch.as_tensor(smooth_u(_np_coords := np.asarray(mesh.coords)), device="cuda")
+        v = torch.as_tensor(np.random.default_rng(1).normal(size=c.shape), device="cuda")
+        y = torch.empty_like(u)
+        report(f"tet4_nh_hvp_c2_{name}", timeit(lambda: op._raw_hvp(mat, u, v, out=y)), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", host_reorder_s=round(t_sort, 3))
+        del op

@@ -47,6 +47,31 @@ for overlap in (False, True):
     e2 = np.abs(r[: pop.n_owned].cpu().numpy().reshape(-1, 3) - ref_res[l2g[:no]]).max() / np.abs(ref_res).max()
     out[f"overlap={overlap}"] = {"hvp_rel_err": float(e1), "residual_rel_err": float(e2), "n_boundary": pop.n_boundary, "n_global": pop.n_global}
     assert e1 < 1e-12 and e2 < 1e-12, (rank, overlap, e1, e2)
+# ---- public plan API on CUDA tensors across ranks (reference call stack mpi.py:372-409, :479-516, :609-711) ----
+from tatva_b200.mpi import AllreducePlan
+mesh, info = structured_hex_block(n, grid, rank)
+pop = PartitionedOperator(mesh, info, element.Hexahedron8(), mat, device=dev, overlap=False)
+l2g = info.nodes_local_to_global
+shape = (grid[0] * n, grid[1] * n, grid[2] * n)
+n_glob_nodes = (shape[0] + 1) * (shape[1] + 1) * (shape[2] + 1)
+gvals = np.random.default_rng(11).normal(size=(n_glob_nodes, 3))
+x_owned = torch.as_tensor(gvals[l2g[: info.n_owned_nodes]].ravel(), device=dev)
+u_local = pop.plan.make_scatter_fwd_set()(x_owned)
+assert np.array_equal(u_local.cpu().numpy().reshape(-1, 3), gvals[l2g]), "scatter_fwd_set mismatch"
+owned = pop.plan.make_scatter_rev_add(lambda ul: ul)(u_local)
+mult = np.zeros(n_glob_nodes)
+counts = [None] * world
+dist.all_gather_object(counts, l2g)
+for lg in counts:
+    mult[lg] += 1
+ref_owned = (gvals * mult[:, None])[l2g[: info.n_owned_nodes]].ravel()
+assert np.allclose(owned.cpu().numpy(), ref_owned, rtol=1e-14), "scatter_rev_add mismatch"
+ap = AllreducePlan(global_size=1000, comm=dist.group.WORLD)
+full = ap.make_allgather()(torch.full((ap.local_size,), float(rank + 1), device=dev, dtype=torch.float64))
+assert full.numel() == 1000 and float(full[ap.rstart]) == rank + 1
+red = ap.make_allreduce_owned(lambda x: x)(torch.arange(1000, device=dev, dtype=torch.float64) * (rank + 1))
+assert np.allclose(red.cpu().numpy(), np.arange(1000)[ap.rstart : ap.rend] * (world * (world + 1) / 2))
+out["plans_on_gpu"] = "ok"
 allr = [None] * world
 dist.all_gather_object(allr, out)
 if rank == 0:
