@@ -54,7 +54,13 @@ ELEMENT_INFO = {
     "tri3": (2, 3, 1),
     "tet4": (3, 4, 1),
     "hex8": (3, 8, 8),
+    "quad4": (2, 4, 4),
+    "tri6": (2, 6, 3),
+    "quad8": (2, 8, 9),
 }
+
+_Q4_SIGNS = np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0]])  # element/base.py:334-336
+_B = np.sqrt(3.0 / 5.0)
 
 
 def reference_nodes(kind: str) -> np.ndarray:
@@ -64,6 +70,12 @@ def reference_nodes(kind: str) -> np.ndarray:
         return np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
     if kind == "hex8":  # element/base.py:478-491
         return _HEX_SIGNS.copy()
+    if kind == "quad4":  # element/base.py:334-336
+        return _Q4_SIGNS.copy()
+    if kind == "tri6":  # element/base.py:272-276
+        return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.5, 0.0], [0.5, 0.5], [0.0, 0.5]])
+    if kind == "quad8":  # element/base.py:369-382
+        return np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0], [0.0, -1.0], [1.0, 0.0], [0.0, 1.0], [-1.0, 0.0]])
     raise ValueError(kind)
 
 
@@ -75,6 +87,14 @@ def quad_rule(kind: str) -> tuple[np.ndarray, np.ndarray]:
         return np.array([[1.0 / 4, 1.0 / 4, 1.0 / 4]]), np.array([1.0 / 6])
     if kind == "hex8":  # element/base.py:493-513
         return _A * _HEX_SIGNS, np.ones(8)
+    if kind == "quad4":  # element/base.py:338-344: meshgrid('xy') -> x fastest
+        x = np.array([-_A, _A])
+        return np.array([[x[j], x[i]] for i in range(2) for j in range(2)]), np.ones(4)
+    if kind == "tri6":  # element/base.py:278-284
+        return np.array([[1.0 / 6, 1.0 / 6], [2.0 / 3, 1.0 / 6], [1.0 / 6, 2.0 / 3]]), np.full(3, 1.0 / 6)
+    if kind == "quad8":  # element/base.py:384-393
+        x, w = np.array([-_B, 0.0, _B]), np.array([5.0 / 9, 8.0 / 9, 5.0 / 9])
+        return np.array([[x[j], x[i]] for i in range(3) for j in range(3)]), np.kron(w, w)
     raise ValueError(kind)
 
 
@@ -87,6 +107,26 @@ def shape_function(kind: str, xi: np.ndarray) -> np.ndarray:
     if kind == "hex8":  # element/base.py:515-529
         s = _HEX_SIGNS
         return 0.125 * (1 + s[:, 0] * xi[0]) * (1 + s[:, 1] * xi[1]) * (1 + s[:, 2] * xi[2])
+    if kind == "quad4":  # element/base.py:346-350
+        return 0.25 * (1 + _Q4_SIGNS[:, 0] * xi[0]) * (1 + _Q4_SIGNS[:, 1] * xi[1])
+    if kind == "tri6":  # element/base.py:286-298
+        r, t_, = xi[0], xi[1]
+        t = 1.0 - r - t_
+        return np.array([t * (2 * t - 1), r * (2 * r - 1), t_ * (2 * t_ - 1), 4 * r * t, 4 * r * t_, 4 * t_ * t])
+    if kind == "quad8":  # element/base.py:395-407
+        r, t = xi
+        return np.array(
+            [
+                0.25 * (1 - r) * (1 - t) * (-r - t - 1),
+                0.25 * (1 + r) * (1 - t) * (r - t - 1),
+                0.25 * (1 + r) * (1 + t) * (r + t - 1),
+                0.25 * (1 - r) * (1 + t) * (-r + t - 1),
+                0.5 * (1 - r * r) * (1 - t),
+                0.5 * (1 + r) * (1 - t * t),
+                0.5 * (1 - r * r) * (1 + t),
+                0.5 * (1 - r) * (1 - t * t),
+            ]
+        )
     raise ValueError(kind)
 
 
@@ -100,6 +140,23 @@ def shape_function_derivative(kind: str, xi: np.ndarray) -> np.ndarray:
         s = _HEX_SIGNS
         fx, fy, fz = 1 + s[:, 0] * xi[0], 1 + s[:, 1] * xi[1], 1 + s[:, 2] * xi[2]
         return 0.125 * np.stack([s[:, 0] * fy * fz, s[:, 1] * fx * fz, s[:, 2] * fx * fy])
+    if kind == "quad4":  # element/base.py:352-366
+        s = _Q4_SIGNS
+        return 0.25 * np.stack([s[:, 0] * (1 + s[:, 1] * xi[1]), s[:, 1] * (1 + s[:, 0] * xi[0])])
+    if kind == "tri6":  # element/base.py:300-328
+        r, q = xi[0], xi[1]
+        t = 1.0 - r - q
+        return np.array(
+            [
+                [-(4 * t - 1), 4 * r - 1, 0.0, 4 * (t - r), 4 * q, -4 * q],
+                [-(4 * t - 1), 0.0, 4 * q - 1, -4 * r, 4 * r, 4 * (t - q)],
+            ]
+        )
+    if kind == "quad8":  # element/base.py:409-445
+        r, t = xi
+        dr = [0.25 * (-2 * r - t) * (t - 1), 0.25 * (-2 * r + t) * (t - 1), 0.25 * (2 * r + t) * (t + 1), 0.25 * (2 * r - t) * (t + 1), r * (t - 1), 0.5 - 0.5 * t * t, -r * (t + 1), 0.5 * t * t - 0.5]
+        dt = [0.25 * (-r - 2 * t) * (r - 1), 0.25 * (-r + 2 * t) * (r + 1), 0.25 * (r + 1) * (r + 2 * t), 0.25 * (r - 1) * (r - 2 * t), 0.5 * r * r - 0.5, -t * (r + 1), 0.5 - 0.5 * r * r, t * (r - 1)]
+        return np.array([dr, dt])
     raise ValueError(kind)
 
 
@@ -652,3 +709,30 @@ def mesh_box_hex(n, length=1.0):
     n0 = (i * sx + j * sy + k * sz).ravel()
     el = np.stack([n0, n0 + sx, n0 + sx + sy, n0 + sy, n0 + sz, n0 + sz + sx, n0 + sz + sx + sy, n0 + sz + sy], -1)
     return nodes, el.astype(np.int32)
+
+
+def mesh_unit_square_quad(nx, ny):
+    """mesh.py:207-231 (Mesh.unit_square(type="quad") -> _rectangle_quadrilateral)."""
+    xv, yv = np.meshgrid(np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1), indexing="ij")
+    coords = np.stack([xv.ravel(), yv.ravel()], axis=-1)
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    n0 = (i * (ny + 1) + j).ravel()
+    return coords, np.stack([n0, n0 + (ny + 1), n0 + (ny + 1) + 1, n0 + 1], -1).astype(np.int32)
+
+
+def mesh_second_order(kind, nx, ny):
+    """Tri6 / Quad8 meshes (no generator in the reference): mid-edge nodes added to the linear mesh, node order
+    of element/base.py:272-276 / :369-382."""
+    base_c, base_el = mesh_unit_square_tri(nx, ny) if kind == "tri6" else mesh_unit_square_quad(nx, ny)
+    edges = [(0, 1), (1, 2), (2, 0)] if kind == "tri6" else [(0, 1), (1, 2), (2, 3), (3, 0)]
+    mid, coords, el = {}, [tuple(p) for p in base_c], []
+    for e in base_el:
+        extra = []
+        for a, b in edges:
+            key = (min(e[a], e[b]), max(e[a], e[b]))
+            if key not in mid:
+                mid[key] = len(coords)
+                coords.append(tuple(0.5 * (base_c[e[a]] + base_c[e[b]])))
+            extra.append(mid[key])
+        el.append(list(e) + extra)
+    return np.array(coords), np.array(el, dtype=np.int32)

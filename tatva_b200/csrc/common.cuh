@@ -82,6 +82,88 @@ struct Hex8 {  // tatva/element/base.py:475-568
   }
 };
 
+struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:338-344)
+  static constexpr int dim = 2, npe = 4, nq = 4, kind = TATVA_QUAD4;
+  TATVA_HD static constexpr double sgn(int n, int d) { return d == 0 ? ((n == 1 || n == 2) ? 1.0 : -1.0) : ((n >= 2) ? 1.0 : -1.0); }
+  TATVA_D static double weight(int) { return 1.0; }
+  TATVA_D static void xi(int q, double& r, double& s) {
+    const double a = 0.57735026918962576451;
+    r = (q & 1) ? a : -a;
+    s = (q & 2) ? a : -a;
+  }
+  TATVA_D static void N(int q, double (&n)[npe]) {
+    double r, s;
+    xi(q, r, s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] = 0.25 * (1.0 + sgn(k, 0) * r) * (1.0 + sgn(k, 1) * s);
+  }
+  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+    double r, s;
+    xi(q, r, s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      d[0][k] = 0.25 * sgn(k, 0) * (1.0 + sgn(k, 1) * s);
+      d[1][k] = 0.25 * sgn(k, 1) * (1.0 + sgn(k, 0) * r);
+    }
+  }
+};
+
+struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
+  static constexpr int dim = 2, npe = 6, nq = 3, kind = TATVA_TRI6;
+  TATVA_D static double weight(int) { return 1.0 / 6.0; }
+  TATVA_D static void xi(int q, double& r, double& s) {
+    r = (q == 1) ? 2.0 / 3.0 : 1.0 / 6.0;
+    s = (q == 2) ? 2.0 / 3.0 : 1.0 / 6.0;
+  }
+  TATVA_D static void N(int q, double (&n)[npe]) {
+    double r, s;
+    xi(q, r, s);
+    const double t = 1.0 - r - s;
+    n[0] = t * (2 * t - 1); n[1] = r * (2 * r - 1); n[2] = s * (2 * s - 1);
+    n[3] = 4 * r * t; n[4] = 4 * r * s; n[5] = 4 * s * t;
+  }
+  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+    double r, s;
+    xi(q, r, s);
+    const double t = 1.0 - r - s;
+    d[0][0] = -(4 * t - 1); d[0][1] = 4 * r - 1; d[0][2] = 0.0; d[0][3] = 4 * (t - r); d[0][4] = 4 * s; d[0][5] = -4 * s;
+    d[1][0] = -(4 * t - 1); d[1][1] = 0.0; d[1][2] = 4 * s - 1; d[1][3] = -4 * r; d[1][4] = 4 * r; d[1][5] = 4 * (t - s);
+  }
+};
+
+struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:384-393)
+  static constexpr int dim = 2, npe = 8, nq = 9, kind = TATVA_QUAD8;
+  TATVA_D static double w1(int i) { return i == 1 ? 8.0 / 9.0 : 5.0 / 9.0; }
+  TATVA_D static double x1(int i) { return i == 0 ? -0.77459666924148337704 : (i == 1 ? 0.0 : 0.77459666924148337704); }
+  TATVA_D static double weight(int q) { return w1(q / 3) * w1(q % 3); }
+  TATVA_D static void xi(int q, double& r, double& s) {
+    r = x1(q % 3);
+    s = x1(q / 3);
+  }
+  TATVA_D static void N(int q, double (&n)[npe]) {
+    double r, s;
+    xi(q, r, s);
+    n[0] = 0.25 * (1 - r) * (1 - s) * (-r - s - 1);
+    n[1] = 0.25 * (1 + r) * (1 - s) * (r - s - 1);
+    n[2] = 0.25 * (1 + r) * (1 + s) * (r + s - 1);
+    n[3] = 0.25 * (1 - r) * (1 + s) * (-r + s - 1);
+    n[4] = 0.5 * (1 - r * r) * (1 - s);
+    n[5] = 0.5 * (1 + r) * (1 - s * s);
+    n[6] = 0.5 * (1 - r * r) * (1 + s);
+    n[7] = 0.5 * (1 - r) * (1 - s * s);
+  }
+  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+    double r, s;
+    xi(q, r, s);
+    d[0][0] = 0.25 * (-2 * r - s) * (s - 1); d[0][1] = 0.25 * (-2 * r + s) * (s - 1);
+    d[0][2] = 0.25 * (2 * r + s) * (s + 1);  d[0][3] = 0.25 * (2 * r - s) * (s + 1);
+    d[0][4] = r * (s - 1); d[0][5] = 0.5 - 0.5 * s * s; d[0][6] = -r * (s + 1); d[0][7] = 0.5 * s * s - 0.5;
+    d[1][0] = 0.25 * (-r - 2 * s) * (r - 1); d[1][1] = 0.25 * (-r + 2 * s) * (r + 1);
+    d[1][2] = 0.25 * (r + 1) * (r + 2 * s);  d[1][3] = 0.25 * (r - 1) * (r - 2 * s);
+    d[1][4] = 0.5 * r * r - 0.5; d[1][5] = -s * (r + 1); d[1][6] = 0.5 - 0.5 * r * r; d[1][7] = s * (r - 1);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // d x d determinant / inverse (closed form; reference uses jnp.linalg.det / inv on J,
 // tatva/element/base.py:92, :113)

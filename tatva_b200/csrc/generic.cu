@@ -635,6 +635,9 @@ using namespace tatva;
     case TATVA_TRI3: { using El = Tri3; CALL; } break; \
     case TATVA_TET4: { using El = Tet4; CALL; } break; \
     case TATVA_HEX8: { using El = Hex8; CALL; } break; \
+    case TATVA_QUAD4: { using El = Quad4; CALL; } break; \
+    case TATVA_TRI6: { using El = Tri6; CALL; } break; \
+    case TATVA_QUAD8: { using El = Quad8; CALL; } break; \
     default: return TATVA_E_INVALID;              \
   }
 
@@ -674,6 +677,9 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
     case TATVA_TRI3: p->dim = Tri3::dim; p->npe = Tri3::npe; p->nq = Tri3::nq; break;
     case TATVA_TET4: p->dim = Tet4::dim; p->npe = Tet4::npe; p->nq = Tet4::nq; break;
     case TATVA_HEX8: p->dim = Hex8::dim; p->npe = Hex8::npe; p->nq = Hex8::nq; break;
+    case TATVA_QUAD4: p->dim = Quad4::dim; p->npe = Quad4::npe; p->nq = Quad4::nq; break;
+    case TATVA_TRI6: p->dim = Tri6::dim; p->npe = Tri6::npe; p->nq = Tri6::nq; break;
+    case TATVA_QUAD8: p->dim = Quad8::dim; p->npe = Quad8::npe; p->nq = Quad8::nq; break;
     default: delete p; return TATVA_E_INVALID;
   }
   p->n_nodes = n_nodes;
@@ -836,6 +842,9 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
   if (material == TATVA_LINEAR_ELASTIC) {
     if (n_params != 2) return TATVA_E_INVALID;
     if (el == TATVA_TRI3) return launch_fused<Tri3, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_QUAD4) return launch_fused<Quad4, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_TRI6) return launch_fused<Tri6, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_QUAD8) return launch_fused<Quad8, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
     if (el == TATVA_TET4) return launch_fused<Tet4, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
     if (el == TATVA_HEX8) return launch_fused<Hex8, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
   } else if (material == TATVA_NEO_HOOKEAN) {
@@ -931,6 +940,9 @@ int tatva_csr_assemble(tatva_plan_t* p, int material, const double* prm, int n_p
   const int el = p->element;
   if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
     if (el == TATVA_TRI3) return launch_csr<Tri3, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_QUAD4) return launch_csr<Quad4, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_TRI6) return launch_csr<Tri6, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
+    if (el == TATVA_QUAD8) return launch_csr<Quad8, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
     if (el == TATVA_TET4) return launch_csr<Tet4, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
     if (el == TATVA_HEX8) return launch_csr<Hex8, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
   } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {

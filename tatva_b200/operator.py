@@ -41,8 +41,8 @@ class Operator:
         self._check_init(mesh)
         if element.kind is None or not getattr(element, "_default_rule", True):
             raise NotImplementedError(
-                f"{type(element).__name__} with this quadrature rule has no CUDA kernel (Tri3, Tetrahedron4, "
-                "Hexahedron8 with their default rules are supported)"
+                f"{type(element).__name__} with this quadrature rule has no CUDA kernel (Tri3, Tri6, Quad4, Quad8, "
+                "Tetrahedron4, Hexahedron8 with their default rules are supported)"
             )
         if not torch.cuda.is_available():
             raise _lib.TatvaError("tatva_b200.Operator needs a CUDA device (there is no CPU fallback)")

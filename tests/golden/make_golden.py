@@ -42,6 +42,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import tatva_oracle as orc  # noqa: E402  (mesh generators only: inputs, not outputs)
 
 KINDS = {"tri3": element.Tri3, "tet4": element.Tetrahedron4, "hex8": element.Hexahedron8}
+MORE_KINDS = {"quad4": element.Quad4, "tri6": element.Tri6, "quad8": element.Quad8}
 
 
 # -- user energies exactly as the reference tests write them -----------------------------
@@ -102,7 +103,7 @@ def make_case(kind):
 def element_fixtures(out):
     """tatva.element.* on one distorted element per kind."""
     rng = np.random.default_rng(7)
-    for kind, cls in KINDS.items():
+    for kind, cls in {**KINDS, **MORE_KINDS}.items():
         el = cls()
         X = np.asarray(el._reference_nodes(), dtype=float)
         X = X + 0.15 * rng.uniform(-1, 1, X.shape)
@@ -178,6 +179,34 @@ def operator_fixtures(out):
         out[p + "hvp_probe_wHv"] = hv
 
 
+def more_operator_fixtures(out):
+    """Operator.* on Quad4 / Tri6 / Quad8 meshes (reference Operator, shimmed)."""
+    rng = np.random.default_rng(13)
+    for kind, cls in MORE_KINDS.items():
+        if kind == "quad4":
+            c, el = orc.mesh_unit_square_quad(3, 2)
+        else:
+            c, el = orc.mesh_second_order(kind, 2, 2)
+        c = c + 0.02 * rng.uniform(-1, 1, c.shape)
+        op = Operator(Mesh(coords=c, elements=el), cls())
+        u = smooth_u(c) + 0.01 * rng.normal(size=c.shape)
+        s = rng.normal(size=(c.shape[0],))
+        p = f"op_{kind}_"
+        mat = orc.lame_from_youngs_poisson_2d(1.0, 0.3)
+        out[p + "coords"], out[p + "conn"], out[p + "u"], out[p + "s"] = c, el, u, s
+        out[p + "v"] = rng.normal(size=c.shape)
+        out[p + "mat"] = np.array(mat)
+        out[p + "grad_u"], out[p + "grad_s"] = op.grad(u), op.grad(s)
+        out[p + "eval_u"], out[p + "eval_s"] = op.eval(u), op.eval(s)
+        out[p + "weights"] = op.get_integration_weights()
+        out[p + "int_nodal_s"] = op.integrate(s)
+        out[p + "int_nodal_u_per_el"] = op.integrate_per_element(u)
+        q = rng.normal(size=(el.shape[0], len(op.element.quad_points), 2))
+        out[p + "quadvals"] = q
+        out[p + "int_quad_per_el"] = op.integrate_per_element(q)
+        out[p + "energy"] = op.integrate(strain_energy(op.grad(u), mat[0], mat[1]))
+
+
 def sparse_fixtures(out):
     cases = {
         "tri3_8x8_d2": (orc.mesh_unit_square_tri(8, 8), 2),  # tests/test_sparse.py:40-45
@@ -222,6 +251,7 @@ def main():
     out: dict[str, np.ndarray] = {}
     element_fixtures(out)
     operator_fixtures(out)
+    more_operator_fixtures(out)
     sparse_fixtures(out)
     partition_fixtures(out)
     try:
