@@ -632,6 +632,191 @@ __global__ void __launch_bounds__(kBlock, MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
+// v3: the two Gauss points of a tx = -/+ pair are processed together.  They share the xi-derivative and the
+// (ty, tz) partial sums of every field (10 fused ops per field per pair instead of 16) and the modal
+// accumulation (sums / differences of the two fluxes: 18 ops per component per pair instead of 24).
+// ---------------------------------------------------------------------------------------------
+__constant__ double kPairSigns[4][3] = {  // (sy, sz, sy*sz) for (ty, tz) = (-,-), (+,-), (-,+), (+,+)
+    {-kA, -kA, kA * kA}, {kA, -kA, -kA * kA}, {-kA, kA, -kA * kA}, {kA, kA, kA * kA}};
+
+TATVA_D void ref_grad8_pair(const double (&h)[7], double sy, double sz, double (&gm)[3], double (&gp)[3]) {
+  const double s36 = fma(sz, h[6], h[3]);
+  const double g0 = fma(sy, s36, fma(sz, h[5], h[0]));
+  const double b1 = fma(sz, h[4], h[1]);
+  const double s56 = fma(sy, h[6], h[5]);
+  const double b2 = fma(sy, h[4], h[2]);
+  gm[0] = g0;
+  gp[0] = g0;
+  gm[1] = fma(-kA, s36, b1);
+  gp[1] = fma(kA, s36, b1);
+  gm[2] = fma(-kA, s56, b2);
+  gp[2] = fma(kA, s56, b2);
+}
+
+// flux Q[i][d] (scaled by 512) of one Gauss point from J (8 dX/dxi, [d][c]), Fr, Gv ([i][d])
+TATVA_D void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const double (&Gv)[3][3], double mu_s,
+                        double lm_s, double (&Q)[3][3]) {
+  double Kc[3][3], detJ, Ac[3][3], detF;
+  adjugate(J, Kc, detJ);
+  double M[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+      M[b][a] = M[a][b];
+    }
+  adjugate(Fr, Ac, detF);
+  const double r = 1.0 / (detJ * detF);
+  const double rJ = r * detF, rF = r * detJ;
+  const double lnJ = log(detF * rJ);
+  double B[3][3];
+  mat3(Ac, Gv, B);
+  const double wF = detJ * rF * rF;
+  const double w1 = mu_s * rJ, w2 = (mu_s - lm_s * lnJ) * wF, w3 = lm_s * wF * (B[0][0] + B[1][1] + B[2][2]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      M[a][b] *= w1;
+      M[b][a] = M[a][b];
+    }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int f = 0; f < 3; ++f) B[d][f] = (d == f) ? fma(w2, B[d][f], w3) : w2 * B[d][f];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      Q[i][d] = fma(B[d][0], Ac[0][i], fma(B[d][1], Ac[1][i], fma(B[d][2], Ac[2][i],
+                fma(Gv[i][0], M[0][d], fma(Gv[i][1], M[1][d], Gv[i][2] * M[2][d])))));
+}
+
+template <int MINB, int STAGE>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_hvp_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                     double lmbda, const double* __restrict__ u, const double* __restrict__ v,
+                     double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  extern __shared__ double sm[];
+  double* sX0 = sm + threadIdx.x;
+  double* sv0 = sm + 21 * kBlock + threadIdx.x;
+  double* sx0 = sm + 42 * kBlock + threadIdx.x;
+  double hX[STAGE ? 1 : 3][7], hx[STAGE >= 2 ? 1 : 3][7], hv[STAGE ? 1 : 3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8], fv[8], tX[7], tv[7], tx_[7];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal_raw(fX, tX);
+    to_modal_raw(fu, tx_);
+    to_modal_raw(fv, tv);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      tx_[k] += tX[k];
+      if constexpr (STAGE >= 2) sx0[(c * 7 + k) * kBlock] = tx_[k];
+      else hx[c][k] = tx_[k];
+      if constexpr (STAGE) {
+        sX0[(c * 7 + k) * kBlock] = tX[k];
+        sv0[(c * 7 + k) * kBlock] = tv[k];
+      } else {
+        hX[c][k] = tX[k];
+        hv[c][k] = tv[k];
+      }
+    }
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+
+#pragma unroll 1
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
+    int opaque = 0;
+    asm volatile("" : "+r"(opaque));
+    const double* sX = sX0 + opaque;
+    const double* sv = sv0 + opaque;
+    const double* sx = sx0 + opaque;
+    double Jm[3][3], Jp[3][3], Frm[3][3], Frp[3][3], Gvm[3][3], Gvp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double gm[3], gp[3];
+      if constexpr (STAGE) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sX[(c * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, gm, gp);
+      } else {
+        ref_grad8_pair(hX[c], sy, sz, gm, gp);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Jm[d][c] = gm[d];
+        Jp[d][c] = gp[d];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if constexpr (STAGE >= 2) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sx[(i * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, Frm[i], Frp[i]);
+      } else {
+        ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+      }
+      if constexpr (STAGE) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sv[(i * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, Gvm[i], Gvp[i]);
+      } else {
+        ref_grad8_pair(hv[i], sy, sz, Gvm[i], Gvp[i]);
+      }
+    }
+    double Qm[3][3], Qp[3][3];
+    point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
+    point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
+    const double asz = kA * sz, asy = kA * sy;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double S0 = Qp[i][0] + Qm[i][0], S1 = Qp[i][1] + Qm[i][1], S2 = Qp[i][2] + Qm[i][2];
+      const double D1 = Qp[i][1] - Qm[i][1], D2 = Qp[i][2] - Qm[i][2];
+      R[i][0] += S0;
+      R[i][1] += S1;
+      R[i][2] += S2;
+      R[i][3] = fma(sy, S0, fma(kA, D1, R[i][3]));
+      R[i][4] = fma(sz, S1, fma(sy, S2, R[i][4]));
+      R[i][5] = fma(sz, S0, fma(kA, D2, R[i][5]));
+      R[i][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, R[i][6])));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal_raw(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Residual in the same modal / reference-space form:
 //   W P K = W [ mu Fr M + (lambda lnJ - mu) A^T ],   P = mu (F - F^-T) + lambda lnJ F^-T,  F = Fr K^T.
 // ---------------------------------------------------------------------------------------------
@@ -722,6 +907,19 @@ __global__ void __launch_bounds__(kBlock, 2)
 
 }  // namespace
 
+template <int MINB, int STAGE>
+static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                     cudaStream_t st) {
+  constexpr size_t smem = (size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock * sizeof(double);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_v3<MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_hex8_nh_hvp_v3<MINB, STAGE><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  return TATVA_OK;
+}
+
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
@@ -744,10 +942,15 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 17: rc = launch_rolled<1, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 18: rc = launch_rolled<2, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 19: rc = launch_rolled<2, 4, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 22: k_hex8_nh_hvp_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 23: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 24: k_hex8_nh_hvp_v3<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 25: rc = launch_v3<2, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 26: rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st); break;
     case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 20: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 21: k_hex8_nh_hvp_v2<2, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
-    default: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    default: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;  // pair-sharing, X and v staged
   }
   if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();
