@@ -250,6 +250,34 @@ __global__ void __launch_bounds__(256) k_sum_rows_final(const double* __restrict
 
 enum { MODE_ENERGY = 0, MODE_RESIDUAL = 1, MODE_HVP = 2 };
 
+// Sector-grouped scatter-add of the per-element nodal contributions of one warp: the values are re-dealt
+// through shared memory so that consecutive lanes add the DPN consecutive doubles of one node (one 32-byte
+// sector per group instead of DPN separate ones; the L2 atomic units work per sector).  All 32 lanes must call.
+template <int NPE, int DPN>
+TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const double (&Y)[NPE][DPN], bool valid,
+                             double* warp_smem) {
+  constexpr int S = NPE * DPN;
+  const int lane = threadIdx.x & 31;
+  int* snode = reinterpret_cast<int*>(warp_smem + 32 * S);
+#pragma unroll
+  for (int n = 0; n < NPE; ++n) {
+    snode[lane * NPE + n] = valid ? nd[n] : -1;
+#pragma unroll
+    for (int c = 0; c < DPN; ++c) warp_smem[lane * S + n * DPN + c] = Y[n][c];
+  }
+  __syncwarp();
+  for (int t = lane; t < 32 * S; t += 32) {
+    const int j = t / S, r = t - j * S;
+    const int node = snode[j * NPE + r / DPN];
+    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[t]);
+  }
+  __syncwarp();
+}
+template <int NPE, int DPN>
+constexpr size_t grouped_scatter_smem(int warps) {
+  return (size_t)warps * (32 * NPE * DPN + 16 * NPE) * sizeof(double);
+}
+
 template <class El, class Mat>
 TATVA_D void qp_state(const double (&dNdX)[El::dim][El::npe], const double (&N)[El::npe],
                       const double (&U)[El::npe][Mat::dpn], typename Mat::S& s) {
@@ -278,19 +306,23 @@ __global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coo
                                                   double* __restrict__ partials) {
   static_assert(El::dim == Mat::dim, "element / law dimension mismatch");
   constexpr int dpn = Mat::dpn;
+  extern __shared__ double sm_fused[];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double energy = 0.0;
+  int nd[El::npe];
+  double Y[El::npe][dpn];
+#pragma unroll
+  for (int n = 0; n < El::npe; ++n) {
+    nd[n] = 0;
+#pragma unroll
+    for (int c = 0; c < dpn; ++c) Y[n][c] = 0.0;
+  }
   if (e < E) {
-    int nd[El::npe];
     load_conn<El>(conn, e, nd);
-    double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn], Y[El::npe][dpn];
+    double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn];
     gather_rows(coords, nd, X);
     gather_rows(u, nd, U);
     if constexpr (MODE == MODE_HVP) gather_rows(v, nd, V);
-#pragma unroll
-    for (int n = 0; n < El::npe; ++n)
-#pragma unroll
-      for (int c = 0; c < dpn; ++c) Y[n][c] = 0.0;
 
 #pragma unroll 1
     for (int q = 0; q < El::nq; ++q) {
@@ -322,12 +354,10 @@ __global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coo
           }
       }
     }
-    if constexpr (MODE != MODE_ENERGY) {
-#pragma unroll
-      for (int n = 0; n < El::npe; ++n)
-#pragma unroll
-        for (int c = 0; c < dpn; ++c) atomicAdd(y + (int64_t)nd[n] * dpn + c, Y[n][c]);
-    }
+  }
+  if constexpr (MODE != MODE_ENERGY) {
+    double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * (32 * El::npe * dpn + 16 * El::npe);
+    grouped_scatter<El::npe, dpn>(y, nd, Y, e < E, wsm);
   }
   if constexpr (MODE == MODE_ENERGY) {
     energy = block_sum(energy);
@@ -407,6 +437,92 @@ __global__ void __launch_bounds__(kBlock) k_csr(const double* __restrict__ coord
         for (int i = 0; i < dpn; ++i) atomicAdd(data + (int64_t)__ldg(indptr + row0[a] + i) + p, col[a][i]);
       }
     }
+  }
+}
+
+// ---- CSR assembly with sector-grouped REDs --------------------------------------------------------
+// Same arithmetic as k_csr, but the REDs of a warp are re-dealt through shared memory so that consecutive
+// lanes add the dpn consecutive doubles of one (row, column-block): a RED group then touches one 32-byte
+// sector instead of dpn.  The L2 atomic units work per sector (tools/micro/red_sector.cu: 212 G RED/s for
+// scattered doubles, 420-490 G/s when 3-4 lanes share a sector), and assembly is bound by exactly that.
+// Single-quadrature-point elements (the block of one column node fits in registers).
+template <class El, class Mat>
+__global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict__ coords,
+                                                        const int32_t* __restrict__ conn, int64_t E, Mat mat,
+                                                        const double* __restrict__ u,
+                                                        const int32_t* __restrict__ indptr,
+                                                        const int32_t* __restrict__ pos, double* __restrict__ data) {
+  static_assert(El::nq == 1, "grouped assembly is implemented for single-point elements");
+  constexpr int dpn = Mat::dpn, npe = El::npe, S = npe * dpn * dpn, NB = npe * dpn;
+  extern __shared__ double sm_grp[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sblk = sm_grp + (size_t)wib * 32 * (S + NB / 2 + 1);  // [32][S] values, then [32][NB] int32 bases
+  int* sbase = reinterpret_cast<int*>(sblk + 32 * S);
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e < E;
+  int nd[npe];
+  double dNdX[El::dim][npe], N[npe], W = 0.0;
+  typename Mat::S s;
+  typename Mat::Cache cache;
+  if (valid) {
+    load_conn<El>(conn, e, nd);
+    double X[npe][El::dim], U[npe][dpn];
+    gather_rows(coords, nd, X);
+    gather_rows(u, nd, U);
+    W = geometry<El>(0, X, dNdX) * El::weight(0);
+    El::N(0, N);
+    qp_state<El, Mat>(dNdX, N, U, s);
+    mat.prepare(s, cache);
+  }
+#pragma unroll 1
+  for (int b = 0; b < npe; ++b) {
+    if (valid) {
+#pragma unroll 1
+      for (int k = 0; k < dpn; ++k) {
+        typename Mat::S ds, f;
+#pragma unroll
+        for (int c = 0; c < dpn; ++c) {
+#pragma unroll
+          for (int j = 0; j < El::dim; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int n = 0; n < npe; ++n) t += (n == b && c == k) ? dNdX[j][n] : 0.0;
+            ds.G[c][j] = t;
+          }
+          double t = 0.0;
+#pragma unroll
+          for (int n = 0; n < npe; ++n) t += (n == b && c == k) ? N[n] : 0.0;
+          ds.val[c] = t;
+        }
+        mat.second(s, cache, ds, f);
+#pragma unroll
+        for (int a = 0; a < npe; ++a)
+#pragma unroll
+          for (int i = 0; i < dpn; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < El::dim; ++j) t += f.G[i][j] * dNdX[j][a];
+            if (i >= Mat::val_lo) t += f.val[i] * N[a];
+            sblk[lane * S + (a * dpn + i) * dpn + k] = W * t;
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < npe; ++a) {
+        const int p = __ldg(pos + (e * npe + a) * npe + b);
+#pragma unroll
+        for (int i = 0; i < dpn; ++i) sbase[lane * NB + a * dpn + i] = __ldg(indptr + (int64_t)nd[a] * dpn + i) + p;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < NB; ++r) sbase[lane * NB + r] = -1;
+    }
+    __syncwarp();
+    for (int t = lane; t < 32 * S; t += 32) {
+      const int j = t / S, r = t - j * S;
+      const int base = sbase[j * NB + r / dpn];
+      if (base >= 0) atomicAdd(data + (int64_t)base + (r % dpn), sblk[t]);
+    }
+    __syncwarp();
   }
 }
 
@@ -827,7 +943,9 @@ static int launch_fused(tatva_plan* p, const Mat& mat, const double* u, const do
     k_sum_rows_final<<<1, 256, 0, st>>>(p->scratch, grid, 1, out);
   } else {
     if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
-    k_fused<El, Mat, MODE><<<grid, kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, nullptr);
+    constexpr size_t smem = grouped_scatter_smem<El::npe, Mat::dpn>(kBlock / 32);
+    static_assert(smem <= 48 * 1024, "grouped scatter staging exceeds the default shared-memory window");
+    k_fused<El, Mat, MODE><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, nullptr);
   }
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -925,6 +1043,20 @@ template <class El, class Mat>
 static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int32_t* indptr, const int32_t* pos,
                       int64_t nnz, double* data, cudaStream_t st) {
   TATVA_CUDA_TRY(cudaMemsetAsync(data, 0, sizeof(double) * nnz, st));
+  if constexpr (El::nq == 1) {
+    if (p->variant != TATVA_VARIANT_GENERIC) {
+      constexpr int S = El::npe * Mat::dpn * Mat::dpn, NB = El::npe * Mat::dpn;
+      constexpr size_t smem = (size_t)(kBlock / 32) * 32 * (S + NB / 2 + 1) * sizeof(double);
+      static bool configured = false;
+      if (!configured && smem > 48 * 1024) {
+        TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_grouped<El, Mat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+      }
+      k_csr_grouped<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }
+  }
   k_csr<El, Mat><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;

@@ -693,13 +693,15 @@ TATVA_D void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const
                 fma(Gv[i][0], M[0][d], fma(Gv[i][1], M[1][d], Gv[i][2] * M[2][d])))));
 }
 
-template <int MINB, int STAGE>
+template <int MINB, int STAGE, int GROUPED = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                      double lmbda, const double* __restrict__ u, const double* __restrict__ v,
                      double* __restrict__ y) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e0 < E;
+  if (!GROUPED && !valid) return;
+  const int64_t e = valid ? e0 : E - 1;  // GROUPED: out-of-range lanes redo the last element and drop the result
   int nd[8];
   {
     const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
@@ -807,12 +809,35 @@ __global__ void __launch_bounds__(kBlock, MINB)
       R[i][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, R[i][6])));
     }
   }
+  if constexpr (GROUPED) {
+    // sector-grouped scatter: consecutive lanes add the 3 consecutive doubles of one node
+    constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63);
+    double* wsm = sm + (size_t)NS * kBlock + (size_t)(threadIdx.x >> 5) * (32 * 24 + 16 * 8);
+    const int lane = threadIdx.x & 31;
+    int* snode = reinterpret_cast<int*>(wsm + 32 * 24);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    double f[8];
-    from_modal_raw(R[i], f);
+    for (int n = 0; n < 8; ++n) snode[lane * 8 + n] = valid ? nd[n] : -1;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+    for (int i = 0; i < 3; ++i) {
+      double f[8];
+      from_modal_raw(R[i], f);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) wsm[lane * 24 + n * 3 + i] = f[n];
+    }
+    __syncwarp();
+    for (int t = lane; t < 32 * 24; t += 32) {
+      const int j = t / 24, r = t - j * 24;
+      const int node = snode[j * 8 + r / 3];
+      if (node >= 0) atomicAdd(y + (int64_t)node * 3 + (r % 3), wsm[t]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double f[8];
+      from_modal_raw(R[i], f);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+    }
   }
 }
 
@@ -907,16 +932,16 @@ __global__ void __launch_bounds__(kBlock, 2)
 
 }  // namespace
 
-template <int MINB, int STAGE>
+template <int MINB, int STAGE, int GROUPED = 0>
 static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st) {
-  constexpr size_t smem = (size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock * sizeof(double);
+  constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * (32 * 24 + 16 * 8) : 0)) * sizeof(double);
   static bool configured = false;
   if (!configured && smem > 48 * 1024) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_v3<MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  k_hex8_nh_hvp_v3<MINB, STAGE><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
   return TATVA_OK;
 }
 
@@ -945,6 +970,7 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 22: k_hex8_nh_hvp_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 23: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;
     case 24: k_hex8_nh_hvp_v3<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 27: rc = launch_v3<2, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 25: rc = launch_v3<2, 2>(p, mu, lmbda, u, v, y, st); break;
     case 26: rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st); break;
     case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;

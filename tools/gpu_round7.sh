@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/bench_secondary.py tet4,pf,tri3 2>&1 | grep kernel
