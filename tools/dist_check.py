@@ -72,6 +72,30 @@ assert full.numel() == 1000 and float(full[ap.rstart]) == rank + 1
 red = ap.make_allreduce_owned(lambda x: x)(torch.arange(1000, device=dev, dtype=torch.float64) * (rank + 1))
 assert np.allclose(red.cpu().numpy(), np.arange(1000)[ap.rstart : ap.rend] * (world * (world + 1) / 2))
 out["plans_on_gpu"] = "ok"
+# ---- config 5: compound (u, phi) Tet4 phase-field operator on a partitioned mesh (generic extract_local_mesh path) ----
+from tatva_b200.mesh import extract_local_mesh, block_partition
+nt = 6
+gshape = (grid[0] * nt, grid[1] * nt, grid[2] * nt)
+tm = Mesh.box_tet((gshape[0] / max(gshape), gshape[1] / max(gshape), gshape[2] / max(gshape)), gshape)
+tc = tm.coords + np.array([0.5, 0.5, 0.0]) + 0.02 / nt * np.random.default_rng(5).uniform(-1, 1, tm.coords.shape)
+tmesh = Mesh(coords=tc, elements=tm.elements)
+tpart = np.repeat(block_partition(gshape, world), 6)  # 6 tets per cell, cells in x-fastest order
+pf = materials.NeoHookeanPhaseField(500.0, 1000.0, 2.7, 0.1, 1e-6)
+lm, linfo = extract_local_mesh(tmesh, tpart, rank)
+ppop = PartitionedOperator(lm, linfo, element.Tetrahedron4(), pf, device=dev, overlap=True)
+gs = np.concatenate([0.002 * np.random.default_rng(6).normal(size=tc.shape), np.random.default_rng(7).uniform(0, 0.8, size=(len(tc), 1))], axis=1)
+gt = np.random.default_rng(8).normal(size=gs.shape)
+gop5 = tatva_b200.Operator(tmesh, element.Tetrahedron4(), device=dev)
+ref5 = gop5.hvp(pf)(gs, gt).cpu().numpy().reshape(-1, 4)
+tl2g = linfo.nodes_local_to_global
+s_local = torch.as_tensor(gs[tl2g].ravel(), device=dev)
+t_local = torch.as_tensor(gt[tl2g].ravel(), device=dev)
+t_local[ppop.n_owned:] = 0.0
+y5 = ppop.hvp(s_local, t_local)
+torch.cuda.synchronize()
+e5 = np.abs(y5[: ppop.n_owned].cpu().numpy().reshape(-1, 4) - ref5[tl2g[: linfo.n_owned_nodes]]).max() / np.abs(ref5).max()
+assert e5 < 1e-12, (rank, e5)
+out["compound_pf_tet4_hvp_rel_err"] = float(e5)
 allr = [None] * world
 dist.all_gather_object(allr, out)
 if rank == 0:
