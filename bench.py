@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=48, help="cells per side of the CPU sample")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default=os.environ.get("TATVA_HALO", "nccl"), choices=["nccl", "peer"], help="multi-GPU halo transport")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -243,7 +244,7 @@ def main():
 
     from bench_dist import DistributedHex8Problem  # multi-GPU decomposition + halo exchange
 
-    prob = DistributedHex8Problem(args.n, rank, world, dev, materials.NeoHookean(MU, LMBDA), variant=args.variant)
+    prob = DistributedHex8Problem(args.n, rank, world, dev, materials.NeoHookean(MU, LMBDA), variant=args.variant, halo=args.halo)
     n_dofs_global = prob.n_dofs_global
     step = prob.step
 

@@ -26,7 +26,7 @@ def smooth_u(c):
 
 
 class DistributedHex8Problem:
-    def __init__(self, n, rank, world, device, material, variant=0, overlap=True):
+    def __init__(self, n, rank, world, device, material, variant=0, overlap=True, halo="nccl"):
         from bench import synthetic_inputs
 
         self.rank, self.world, self.device, self.material = rank, world, device, material
@@ -42,20 +42,26 @@ class DistributedHex8Problem:
             grid = GRID[world]
             mesh, info = structured_hex_block(n, grid, rank)
             c, el = mesh.coords, mesh.elements
-            self.pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=overlap)
+            self.pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=overlap, halo=halo)
             self.op = self.pop.op
             u = smooth_u(c)  # ghost values consistent by construction (function of the shared coordinates)
             v = np.random.default_rng(1 + rank).normal(size=c.shape)
             self.n_dofs_global = self.pop.n_global
-            self.partition_desc = f"{world} GPUs, {grid[0]}x{grid[1]}x{grid[2]} blocks of {n}^3, NCCL halo exchange ({'overlapped' if overlap else 'serial'})"
+            how = "peer-memory halo over NVLink (own kernels + device barrier)" if halo == "peer" else "NCCL halo exchange"
+            self.partition_desc = f"{world} GPUs, {grid[0]}x{grid[1]}x{grid[2]} blocks of {n}^3, {how} ({'overlapped' if overlap else 'serial'})"
             n_owned = self.pop.n_owned
             self.launches_per_step = 6  # pack, unpack-set, boundary + interior element kernels, pack, unpack-add
         if variant:
             self.op.set_variant(variant)
         self.local_nodes, self.local_elems = c.shape[0], el.shape[0]
-        self.u = torch.as_tensor(u, device=device).reshape(-1)
-        self.v = torch.as_tensor(v, device=device).reshape(-1)
-        self.y = torch.empty_like(self.u)
+        if self.pop is not None and halo == "peer":
+            self.u, self.v, self.y = (self.pop.new_symmetric_vector() for _ in range(3))
+            self.u.copy_(torch.as_tensor(u, device=device).reshape(-1))
+            self.v.copy_(torch.as_tensor(v, device=device).reshape(-1))
+        else:
+            self.u = torch.as_tensor(u, device=device).reshape(-1)
+            self.v = torch.as_tensor(v, device=device).reshape(-1)
+            self.y = torch.empty_like(self.u)
         self.n_owned = n_owned
         # host-side pinned buffers for the end-to-end leg (owned entries only)
         self.h_u = torch.as_tensor(u).reshape(-1)[:n_owned].clone().pin_memory()
@@ -80,7 +86,7 @@ class DistributedHex8Problem:
         if not hasattr(self, "_pipe"):
             mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
             self._pipe = dict(s_in=mk(), s_out=mk(), i=0, sets=[
-                dict(u=self.u.clone(), v=self.v.clone(), y=torch.empty_like(self.u), in_done=torch.cuda.Event(), comp_done=torch.cuda.Event(), out_done=torch.cuda.Event())
+                dict(u=self._clone_vec(self.u), v=self._clone_vec(self.v), y=self._clone_vec(self.u), in_done=torch.cuda.Event(), comp_done=torch.cuda.Event(), out_done=torch.cuda.Event())
                 for _ in range(2)
             ])
         P = self._pipe
@@ -106,6 +112,13 @@ class DistributedHex8Problem:
         with torch.cuda.stream(P["s_out"]):
             self.h_y.copy_(y[:n], non_blocking=True)
             B["out_done"].record()
+
+    def _clone_vec(self, x):
+        if self.pop is not None and self.pop.halo == "peer":
+            y = self.pop.new_symmetric_vector()
+            y.copy_(x)
+            return y
+        return x.clone()
 
     def e2e_finish(self):
         """Join the download stream into the current stream (so a following event covers the last D2H)."""

@@ -162,6 +162,17 @@ int tatva_halo_unpack_set(const double* d_src, const int64_t* d_idx, int64_t n, 
 int tatva_halo_unpack_add(const double* d_src, const int64_t* d_idx, int64_t n, double* d_dst,
                           tatva_stream_t stream);
 
+/* Peer-memory variant of the exchange (one box, NVLink / NVSwitch): local vectors live in peer-mapped memory,
+ * `d_peer_ptrs[r]` is rank r's base address of the same vector, and each ghost entry g knows its owner rank and
+ * its index in the owner's vector.  pull fills the ghosts with remote loads, push_add adds the ghost contributions
+ * into the owners' rows with remote REDs — no pack buffers, no NCCL call.  The caller brackets them with a
+ * cross-rank barrier (owners' data ready / all contributions landed).                                          */
+int tatva_peer_pull(double* d_x_local, int64_t first_ghost, int64_t n_ghost, const uint64_t* d_peer_ptrs,
+                    const int32_t* d_owner, const int64_t* d_owner_idx, tatva_stream_t stream);
+int tatva_peer_push_add(const double* d_y_local, int64_t first_ghost, int64_t n_ghost,
+                        const uint64_t* d_peer_ptrs, const int32_t* d_owner, const int64_t* d_owner_idx,
+                        tatva_stream_t stream);
+
 /* ---- lifter (tatva/lifter/base.py:201-251): reduced <-> full vectors with all constraints composed ----
  * The constraints (Fixed, Periodic, applied in order; lifter/constraints.py:214-221, :312-318) are composed
  * once on the host into one source table, so lift is ONE gather and reduce_adjoint ONE segmented sum:

@@ -49,6 +49,8 @@ SIGNATURES = {
     "tatva_halo_pack": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_halo_unpack_set": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_halo_unpack_add": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "tatva_peer_pull": (C.c_int, [vp, C.c_int64, C.c_int64, vp, vp, vp, vp]),
+    "tatva_peer_push_add": (C.c_int, [vp, C.c_int64, C.c_int64, vp, vp, vp, vp]),
     "tatva_lift": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_reduce_adjoint": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_cg_dot": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp]),

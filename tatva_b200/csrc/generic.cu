@@ -656,6 +656,29 @@ __global__ void __launch_bounds__(256) k_unpack_add(const double* __restrict__ s
   if (i < n) atomicAdd(dst + __ldg(idx + i), __ldg(src + i));
 }
 
+// ---- peer-memory halo over NVLink (no NCCL, no pack buffers) ------------------------------------------
+// Local vectors live in symmetric (peer-mapped) memory; `peers[r]` is rank r's base pointer of the same vector.
+// pull:  x_local[first_ghost + g]            = peers[owner[g]][owner_idx[g]]      (ghost fill, mpi.py:372-409)
+// push:  peers[owner[g]][owner_idx[g]]      += y_local[first_ghost + g]           (ghost contributions to their
+//        owners, mpi.py:479-516; RED over NVLink, performed at the owner's L2)
+__global__ void __launch_bounds__(256) k_peer_pull(double* __restrict__ x_local, int64_t first_ghost, int64_t n_ghost,
+                                                   const uint64_t* __restrict__ peers, const int32_t* __restrict__ owner,
+                                                   const int64_t* __restrict__ owner_idx) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_ghost) return;
+  const double* src = reinterpret_cast<const double*>(peers[owner[g]]);
+  x_local[first_ghost + g] = __ldcv(src + owner_idx[g]);  // peer memory is not cached in the local L2; skip L1 too
+}
+__global__ void __launch_bounds__(256) k_peer_push_add(const double* __restrict__ y_local, int64_t first_ghost,
+                                                       int64_t n_ghost, const uint64_t* __restrict__ peers,
+                                                       const int32_t* __restrict__ owner,
+                                                       const int64_t* __restrict__ owner_idx) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_ghost) return;
+  double* dst = reinterpret_cast<double*>(peers[owner[g]]);
+  atomicAdd_system(dst + owner_idx[g], y_local[first_ghost + g]);
+}
+
 // ---- lifter: reduced <-> full maps --------------------------------------------------------------
 // lift:   out[i] = src[i] >= 0 ? u_red[src[i]] : (src[i] == -1 ? base[i] : consts[-(src[i] + 2)])
 // adjoint: r_red[j] = sum of r_full over the full DOFs that read reduced DOF j (fixed order)
@@ -1148,6 +1171,23 @@ int tatva_halo_unpack_add(const double* s, const int64_t* idx, int64_t n, double
   if (n == 0) return TATVA_OK;
   if (!s || !idx || !d || n < 0) return TATVA_E_INVALID;
   k_unpack_add<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, idx, n, d);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tatva_peer_pull(double* d_x_local, int64_t first_ghost, int64_t n_ghost, const uint64_t* d_peer_ptrs,
+                    const int32_t* d_owner, const int64_t* d_owner_idx, tatva_stream_t stream) {
+  if (n_ghost == 0) return TATVA_OK;
+  if (!d_x_local || !d_peer_ptrs || !d_owner || !d_owner_idx || n_ghost < 0) return TATVA_E_INVALID;
+  k_peer_pull<<<grid_for(n_ghost, 256), 256, 0, (cudaStream_t)stream>>>(d_x_local, first_ghost, n_ghost, d_peer_ptrs, d_owner, d_owner_idx);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_peer_push_add(const double* d_y_local, int64_t first_ghost, int64_t n_ghost, const uint64_t* d_peer_ptrs,
+                        const int32_t* d_owner, const int64_t* d_owner_idx, tatva_stream_t stream) {
+  if (n_ghost == 0) return TATVA_OK;
+  if (!d_y_local || !d_peer_ptrs || !d_owner || !d_owner_idx || n_ghost < 0) return TATVA_E_INVALID;
+  k_peer_push_add<<<grid_for(n_ghost, 256), 256, 0, (cudaStream_t)stream>>>(d_y_local, first_ghost, n_ghost, d_peer_ptrs, d_owner, d_owner_idx);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

@@ -77,7 +77,7 @@ def _hash_uniform(gid, seed):
 class PartitionedOperator:
     """Operator over one partition + its ExchangePlan + the overlapped distributed HVP / residual."""
 
-    def __init__(self, local_mesh: Mesh, partition_info: PartitionInfo, element, material, comm=None, device=None, overlap=True):
+    def __init__(self, local_mesh: Mesh, partition_info: PartitionInfo, element, material, comm=None, device=None, overlap=True, halo="nccl"):
         self.comm = _as_comm(comm)
         self.material = material
         self.info = partition_info
@@ -107,12 +107,62 @@ class PartitionedOperator:
         self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap else None
         self._prm = _lib.params_array(material.params())
         self._L = _lib.lib()
+        # halo = "peer": vectors in symmetric (peer-mapped) memory, ghosts pulled / pushed by our own kernels over
+        # NVLink with a device-side barrier on each side; halo = "nccl": pack -> all_to_all_single -> unpack.
+        self.halo = halo if self.comm.size > 1 else "nccl"
+        self._sym = {}
+        if self.halo == "peer":
+            self._setup_peer_tables()
+
+    # -- peer-memory halo ----------------------------------------------------------------------------------
+    def _setup_peer_tables(self):
+        l2g = np.asarray(self.plan.layout.local_to_global, dtype=np.int64)
+        ranges = self.comm.allgather((self.plan.rstart, self.plan.rend))
+        sizes = self.comm.allgather(self.n_local)
+        self._sym_len = int(max(sizes))
+        ghosts = l2g[self.n_owned :]
+        starts = np.array([r[0] for r in ranges], dtype=np.int64)
+        owner = (np.searchsorted(starts, ghosts, side="right") - 1).astype(np.int32)
+        self._n_ghost = int(ghosts.size)
+        self._ghost_owner = torch.as_tensor(owner, device=self.device)
+        self._ghost_owner_idx = torch.as_tensor(ghosts - starts[owner], device=self.device)  # owned-first: owned block index == local index
+
+    def new_symmetric_vector(self) -> torch.Tensor:
+        """Local vector (n_local doubles, zero-filled) in peer-mapped memory; required for halo="peer"."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        with torch.cuda.device(self.device):
+            buf = symm_mem.empty(self._sym_len, dtype=torch.float64, device=self.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group=self.comm.group if self.comm.group is not None else dist.group.WORLD)
+        vec = buf[: self.n_local]
+        self._sym[vec.data_ptr()] = (buf, hdl, torch.as_tensor(np.asarray(hdl.buffer_ptrs, dtype=np.uint64).view(np.int64), device=self.device))
+        return vec
+
+    def _peer(self, x):
+        try:
+            return self._sym[x.data_ptr()]
+        except KeyError:
+            raise ValueError('halo="peer" needs vectors from new_symmetric_vector()') from None
+
+    def _peer_pull(self, x):
+        _, hdl, ptrs = self._peer(x)
+        hdl.barrier(channel=0)  # every owner's values are in place
+        _lib.check(self._L.tatva_peer_pull(x.data_ptr(), self.n_owned, self._n_ghost, ptrs.data_ptr(), self._ghost_owner.data_ptr(), self._ghost_owner_idx.data_ptr(), torch.cuda.current_stream().cuda_stream), "tatva_peer_pull")
+
+    def _peer_push(self, y):
+        _, hdl, ptrs = self._peer(y)
+        _lib.check(self._L.tatva_peer_push_add(y.data_ptr(), self.n_owned, self._n_ghost, ptrs.data_ptr(), self._ghost_owner.data_ptr(), self._ghost_owner_idx.data_ptr(), torch.cuda.current_stream().cuda_stream), "tatva_peer_push_add")
+        hdl.barrier(channel=1)  # every contribution has landed in its owner's rows
 
     # -- building blocks ------------------------------------------------------------------------------
     def fill_ghosts(self, x_local: torch.Tensor) -> None:
         """In place: ghost entries of a local vector <- owners' values (scatter_fwd_set, mpi.py:372-409)."""
         if self.comm.size > 1:
-            self._exchange(self.plan._fwd, x_local, x_local, add=False)
+            if self.halo == "peer":
+                self._peer_pull(x_local)
+            else:
+                self._exchange(self.plan._fwd, x_local, x_local, add=False)
 
     def _elems(self, name, u, v, y, begin, count, zero):
         prm, n = self._prm
@@ -126,10 +176,17 @@ class PartitionedOperator:
             self._elems(name, u_local, v_local, y_local, 0, E, 1)
             return y_local
         x = v_local if v_local is not None else u_local  # the vector whose ghosts must be refreshed
+        peer = self.halo == "peer"
         if not self.overlap:
-            self._exchange(self.plan._fwd, x, x, add=False)
-            self._elems(name, u_local, v_local, y_local, 0, E, 1)
-            self._exchange(self.plan._rev, y_local, y_local, add=True)
+            if peer:
+                y_local.zero_()
+                self._peer_pull(x)  # its barrier also orders every rank's zeroing before any push
+                self._elems(name, u_local, v_local, y_local, 0, E, 0)
+                self._peer_push(y_local)
+            else:
+                self._exchange(self.plan._fwd, x, x, add=False)
+                self._elems(name, u_local, v_local, y_local, 0, E, 1)
+                self._exchange(self.plan._rev, y_local, y_local, add=True)
             return y_local
         main, side = torch.cuda.current_stream(self.device), self._comm_stream
         y_local.zero_()
@@ -138,10 +195,16 @@ class PartitionedOperator:
         side.wait_stream(main)  # inputs are ready
         self._elems(name, u_local, v_local, y_local, nb, E - nb, 0)  # interior, compute stream
         with torch.cuda.stream(side):
-            self._exchange(self.plan._fwd, x, x, add=False)
-            side.wait_event(zeroed)
-            self._elems(name, u_local, v_local, y_local, 0, nb, 0)  # boundary elements
-            self._exchange(self.plan._rev, y_local, y_local, add=True)
+            if peer:
+                side.wait_event(zeroed)  # the pull's barrier then orders every rank's zeroing before any push
+                self._peer_pull(x)
+                self._elems(name, u_local, v_local, y_local, 0, nb, 0)  # boundary elements
+                self._peer_push(y_local)
+            else:
+                self._exchange(self.plan._fwd, x, x, add=False)
+                side.wait_event(zeroed)
+                self._elems(name, u_local, v_local, y_local, 0, nb, 0)  # boundary elements
+                self._exchange(self.plan._rev, y_local, y_local, add=True)
         main.wait_stream(side)
         return y_local
 

@@ -17,9 +17,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 grid = GRID[world]
 mat = materials.NeoHookean(500.0, 1000.0)
 out = {}
-for overlap in (False, True):
+HALOS = os.environ.get("TATVA_CHECK_HALOS", "nccl,peer").split(",")
+for overlap, halo in [(o, h) for h in HALOS for o in (False, True)]:
     mesh, info = structured_hex_block(n, grid, rank)
-    pop = PartitionedOperator(mesh, info, element.Hexahedron8(), mat, device=dev, overlap=overlap)
+    pop = PartitionedOperator(mesh, info, element.Hexahedron8(), mat, device=dev, overlap=overlap, halo=halo)
     l2g = info.nodes_local_to_global
     # global reference on every rank: same jittered coordinates via the block builder with a 1x1x1 grid
     shape = (grid[0] * n, grid[1] * n, grid[2] * n)
@@ -34,18 +35,29 @@ for overlap in (False, True):
     gv = np.random.default_rng(7).normal(size=gc.shape)
     ref_hvp = gop.hvp(mat)(gu, gv).cpu().numpy()
     ref_res = gop.residual(mat)(gu).cpu().numpy()
-    u_local = torch.as_tensor(gu[l2g].ravel(), device=dev)
-    v_local = torch.as_tensor(gv[l2g].ravel(), device=dev)
+    if halo == "peer":
+        u_local, v_local, y_buf = (pop.new_symmetric_vector() for _ in range(3))
+        u_local.copy_(torch.as_tensor(gu[l2g].ravel(), device=dev))
+        v_local.copy_(torch.as_tensor(gv[l2g].ravel(), device=dev))
+    else:
+        u_local = torch.as_tensor(gu[l2g].ravel(), device=dev)
+        v_local = torch.as_tensor(gv[l2g].ravel(), device=dev)
+        y_buf = None
     v_local[pop.n_owned:] = 0.0  # ghosts must come from the exchange
-    y = pop.hvp(u_local, v_local)
+    y = pop.hvp(u_local, v_local, y_buf)
     torch.cuda.synchronize()
     no = info.n_owned_nodes
     e1 = np.abs(y[: pop.n_owned].cpu().numpy().reshape(-1, 3) - ref_hvp[l2g[:no]]).max() / np.abs(ref_hvp).max()
-    u2 = u_local.clone(); u2[pop.n_owned:] = 0.0
-    r = pop.residual(u2)
+    if halo == "peer":
+        u2, r_buf = pop.new_symmetric_vector(), pop.new_symmetric_vector()
+        u2.copy_(u_local)
+    else:
+        u2, r_buf = u_local.clone(), None
+    u2[pop.n_owned:] = 0.0
+    r = pop.residual(u2, r_buf)
     torch.cuda.synchronize()
     e2 = np.abs(r[: pop.n_owned].cpu().numpy().reshape(-1, 3) - ref_res[l2g[:no]]).max() / np.abs(ref_res).max()
-    out[f"overlap={overlap}"] = {"hvp_rel_err": float(e1), "residual_rel_err": float(e2), "n_boundary": pop.n_boundary, "n_global": pop.n_global}
+    out[f"halo={halo},overlap={overlap}"] = {"hvp_rel_err": float(e1), "residual_rel_err": float(e2), "n_boundary": pop.n_boundary, "n_global": pop.n_global}
     assert e1 < 1e-12 and e2 < 1e-12, (rank, overlap, e1, e2)
 # ---- public plan API on CUDA tensors across ranks (reference call stack mpi.py:372-409, :479-516, :609-711) ----
 from tatva_b200.mpi import AllreducePlan
