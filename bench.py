@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=48, help="cells per side of the CPU sample")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--halo", default=os.environ.get("TATVA_HALO", "nccl"), choices=["nccl", "peer"], help="multi-GPU halo transport")
+    ap.add_argument("--halo", default=os.environ.get("TATVA_HALO", "peer"), choices=["nccl", "peer"], help="multi-GPU halo transport")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -43,6 +43,22 @@ class DistributedHex8Problem:
             mesh, info = structured_hex_block(n, grid, rank)
             c, el = mesh.coords, mesh.elements
             self.pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=overlap, halo=halo)
+            if halo == "peer":
+                # all ranks must agree that peer-mapped memory works; otherwise everybody uses the NCCL path
+                import torch.distributed as dist
+
+                ok = torch.ones(1, device=device)
+                try:
+                    probe = self.pop.new_symmetric_vector()
+                    self.pop._peer_pull(probe)
+                    torch.cuda.synchronize()
+                except Exception as exc:  # noqa: BLE001
+                    ok.zero_()
+                    self._peer_error = repr(exc)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok) == 0.0:
+                    halo = "nccl"
+                    self.pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=overlap, halo="nccl")
             self.op = self.pop.op
             u = smooth_u(c)  # ghost values consistent by construction (function of the shared coordinates)
             v = np.random.default_rng(1 + rank).normal(size=c.shape)

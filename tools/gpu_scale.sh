@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 N=${1:-8}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py 12 > gpurun_out/dist_check_$N.log 2>&1; echo "dist_check rc=$?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py 10 > gpurun_out/dist_check_$N.log 2>&1; echo "dist_check rc=$?"
 tail -2 gpurun_out/dist_check_$N.log | cut -c1-600
 for G in 1 2 4 8; do
   if [ $G -le $N ]; then
