@@ -466,5 +466,6 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
                       cudaStream_t st);
 
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
+int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st);
 
 }  // namespace tatva

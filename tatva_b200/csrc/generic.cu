@@ -109,6 +109,210 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint(const double* __restric
   }
 }
 
+// Sector-grouped scatter-add of the per-element nodal contributions of one warp: the values are re-dealt
+// through shared memory so that consecutive lanes add the DPN consecutive doubles of one node (one 32-byte
+// sector per group instead of DPN separate ones; the L2 atomic units work per sector).  All 32 lanes must call.
+template <int NPE, int DPN>
+TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const double (&Y)[NPE][DPN], bool valid,
+                             double* warp_smem) {
+  constexpr int S = NPE * DPN;
+  const int lane = threadIdx.x & 31;
+  int* snode = reinterpret_cast<int*>(warp_smem + 32 * S);
+#pragma unroll
+  for (int n = 0; n < NPE; ++n) {
+    snode[lane * NPE + n] = valid ? nd[n] : -1;
+#pragma unroll
+    for (int c = 0; c < DPN; ++c) warp_smem[lane * S + n * DPN + c] = Y[n][c];
+  }
+  __syncwarp();
+  for (int t = lane; t < 32 * S; t += 32) {
+    const int j = t / S, r = t - j * S;
+    const int node = snode[j * NPE + r / DPN];
+    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[t]);
+  }
+  __syncwarp();
+}
+template <int NPE, int DPN>
+constexpr size_t grouped_scatter_smem(int warps) {
+  return (size_t)warps * (32 * NPE * DPN + 16 * NPE) * sizeof(double);
+}
+
+// ---- warp-staged variants: element-major (E, Q, v[, d]) arrays are written / read through shared memory ----
+// Each lane produces (or consumes) the CH = nq*nv[*dim] contiguous doubles of its own element; staging them per
+// warp turns 32 strided 8-byte accesses per instruction into one contiguous 32*CH-double block.  Row stride
+// S = CH | 1 keeps the lane-strided side conflict-free.
+
+TATVA_D void warp_block_store(double* __restrict__ dst, const double* st, int S, int CH, int count) {
+  const int lane = threadIdx.x & 31;
+  for (int t = lane; t < count * CH; t += 32) {
+    const int j = t / CH;
+    dst[t] = st[j * S + (t - j * CH)];
+  }
+}
+TATVA_D void warp_block_load(const double* __restrict__ src, double* st, int S, int CH, int count) {
+  const int lane = threadIdx.x & 31;
+  for (int t = lane; t < count * CH; t += 32) {
+    const int j = t / CH;
+    st[j * S + (t - j * CH)] = __ldg(src + t);
+  }
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_grad_staged(const double* __restrict__ coords,
+                                                        const int32_t* __restrict__ conn, int64_t E,
+                                                        const double* __restrict__ u, int nv, double* __restrict__ out) {
+  extern __shared__ double sm_stage[];
+  const int CH = El::nq * nv * El::dim, S = CH | 1;
+  const int lane = threadIdx.x & 31;
+  double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) {
+    int nd[El::npe];
+    load_conn<El>(conn, e, nd);
+    double X[El::npe][El::dim];
+    gather_rows(coords, nd, X);
+#pragma unroll 1
+    for (int q = 0; q < El::nq; ++q) {
+      double dNdX[El::dim][El::npe];
+      geometry<El>(q, X, dNdX);
+      for (int c = 0; c < nv; ++c) {
+        double ue[El::npe];
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
+#pragma unroll
+        for (int j = 0; j < El::dim; ++j) {
+          double t = 0.0;
+#pragma unroll
+          for (int n = 0; n < El::npe; ++n) t += dNdX[j][n] * ue[n];
+          st[lane * S + (q * nv + c) * El::dim + j] = t;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  const int64_t e0 = e - lane;
+  if (e0 < E) warp_block_store(out + e0 * CH, st, S, CH, (int)min((int64_t)32, E - e0));
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_grad_adjoint_staged(const double* __restrict__ coords,
+                                                                const int32_t* __restrict__ conn, int64_t E,
+                                                                const double* __restrict__ g, int nv,
+                                                                double* __restrict__ y) {
+  extern __shared__ double sm_stage[];
+  const int CH = El::nq * nv * El::dim, S = CH | 1;
+  const int lane = threadIdx.x & 31;
+  double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = e - lane;
+  if (e0 < E) warp_block_load(g + e0 * CH, st, S, CH, (int)min((int64_t)32, E - e0));
+  __syncwarp();
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim];
+  gather_rows(coords, nd, X);
+#pragma unroll 1
+  for (int q = 0; q < El::nq; ++q) {
+    double dNdX[El::dim][El::npe];
+    geometry<El>(q, X, dNdX);
+    for (int c = 0; c < nv; ++c) {
+      double gj[El::dim];
+#pragma unroll
+      for (int j = 0; j < El::dim; ++j) gj[j] = st[lane * S + (q * nv + c) * El::dim + j];
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < El::dim; ++j) t += gj[j] * dNdX[j][n];
+        atomicAdd(y + (int64_t)nd[n] * nv + c, t);
+      }
+    }
+  }
+}
+
+// adjoint of grad with the per-node sums kept in registers over the quadrature loop (NV compile-time, <= 4):
+// npe*NV REDs per element instead of nq*npe*NV, issued sector-grouped.
+template <class El, int NV>
+__global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __restrict__ coords,
+                                                             const int32_t* __restrict__ conn, int64_t E,
+                                                             const double* __restrict__ g, double* __restrict__ y) {
+  extern __shared__ double sm_stage[];
+  constexpr int CH = El::nq * NV * El::dim, S = CH | 1;
+  constexpr int SC = 32 * El::npe * NV + 16 * El::npe;  // grouped-scatter staging per warp
+  constexpr int PER_WARP = (32 * S > SC) ? 32 * S : SC;
+  const int lane = threadIdx.x & 31;
+  double* st = sm_stage + (size_t)(threadIdx.x >> 5) * PER_WARP;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = e - lane;
+  if (e0 < E) warp_block_load(g + e0 * CH, st, S, CH, (int)min((int64_t)32, E - e0));
+  __syncwarp();
+  int nd[El::npe];
+  double Y[El::npe][NV];
+#pragma unroll
+  for (int n = 0; n < El::npe; ++n) {
+    nd[n] = 0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) Y[n][c] = 0.0;
+  }
+  if (e < E) {
+    load_conn<El>(conn, e, nd);
+    double X[El::npe][El::dim];
+    gather_rows(coords, nd, X);
+#pragma unroll 1
+    for (int q = 0; q < El::nq; ++q) {
+      double dNdX[El::dim][El::npe];
+      geometry<El>(q, X, dNdX);
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        double gj[El::dim];
+#pragma unroll
+        for (int j = 0; j < El::dim; ++j) gj[j] = st[lane * S + (q * NV + c) * El::dim + j];
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n) {
+          double t = Y[n][c];
+#pragma unroll
+          for (int j = 0; j < El::dim; ++j) t = fma(gj[j], dNdX[j][n], t);
+          Y[n][c] = t;
+        }
+      }
+    }
+  }
+  __syncwarp();  // every lane is done reading its staged g before the buffer is reused
+  grouped_scatter<El::npe, NV>(y, nd, Y, e < E, st);
+}
+
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_eval_staged(const int32_t* __restrict__ conn, int64_t E,
+                                                        const double* __restrict__ u, int nv, double* __restrict__ out) {
+  extern __shared__ double sm_stage[];
+  const int CH = El::nq * nv, S = CH | 1;
+  const int lane = threadIdx.x & 31;
+  double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) {
+    int nd[El::npe];
+    load_conn<El>(conn, e, nd);
+    for (int c = 0; c < nv; ++c) {
+      double ue[El::npe];
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
+#pragma unroll
+      for (int q = 0; q < El::nq; ++q) {
+        double N[El::npe];
+        El::N(q, N);
+        double t = 0.0;
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n) t += N[n] * ue[n];
+        st[lane * S + q * nv + c] = t;
+      }
+    }
+  }
+  __syncwarp();
+  const int64_t e0 = e - lane;
+  if (e0 < E) warp_block_store(out + e0 * CH, st, S, CH, (int)min((int64_t)32, E - e0));
+}
+
 template <class El>
 __global__ void __launch_bounds__(kBlock) k_eval(const int32_t* __restrict__ conn, int64_t E,
                                                  const double* __restrict__ u, int nv, double* __restrict__ out) {
@@ -249,34 +453,6 @@ __global__ void __launch_bounds__(256) k_sum_rows_final(const double* __restrict
 // ---- fused energy / residual / HVP ------------------------------------------------------------
 
 enum { MODE_ENERGY = 0, MODE_RESIDUAL = 1, MODE_HVP = 2 };
-
-// Sector-grouped scatter-add of the per-element nodal contributions of one warp: the values are re-dealt
-// through shared memory so that consecutive lanes add the DPN consecutive doubles of one node (one 32-byte
-// sector per group instead of DPN separate ones; the L2 atomic units work per sector).  All 32 lanes must call.
-template <int NPE, int DPN>
-TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const double (&Y)[NPE][DPN], bool valid,
-                             double* warp_smem) {
-  constexpr int S = NPE * DPN;
-  const int lane = threadIdx.x & 31;
-  int* snode = reinterpret_cast<int*>(warp_smem + 32 * S);
-#pragma unroll
-  for (int n = 0; n < NPE; ++n) {
-    snode[lane * NPE + n] = valid ? nd[n] : -1;
-#pragma unroll
-    for (int c = 0; c < DPN; ++c) warp_smem[lane * S + n * DPN + c] = Y[n][c];
-  }
-  __syncwarp();
-  for (int t = lane; t < 32 * S; t += 32) {
-    const int j = t / S, r = t - j * S;
-    const int node = snode[j * NPE + r / DPN];
-    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[t]);
-  }
-  __syncwarp();
-}
-template <int NPE, int DPN>
-constexpr size_t grouped_scatter_smem(int warps) {
-  return (size_t)warps * (32 * NPE * DPN + 16 * NPE) * sizeof(double);
-}
 
 template <class El, class Mat>
 TATVA_D void qp_state(const double (&dNdX)[El::dim][El::npe], const double (&N)[El::npe],
@@ -769,6 +945,24 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
 // =================================================================================================
 using namespace tatva;
 
+// staged kernels may need more than the default 48 KB of dynamic shared memory (opt-in, once per kernel)
+constexpr size_t kStageMax = 160 * 1024;
+template <class K>
+static int allow_big_smem(K kernel, bool& done) {
+  if (!done) {
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMax));
+    done = true;
+  }
+  return TATVA_OK;
+}
+#define STAGED_OPT_IN(KERNEL)                                   \
+  {                                                             \
+    static bool done_[8] = {false};                             \
+    int rc_ = TATVA_OK;                                         \
+    DISPATCH_ELEMENT(p, (rc_ = allow_big_smem(KERNEL<El>, done_[El::kind]))); \
+    if (rc_ != TATVA_OK) return rc_;                            \
+  }
+
 #define DISPATCH_ELEMENT(p, CALL)                 \
   switch ((p)->element) {                         \
     case TATVA_TRI3: { using El = Tri3; CALL; } break; \
@@ -886,6 +1080,15 @@ int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_str
 int tatva_op_grad(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->dim) | 1) * sizeof(double);
+    if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {
+      STAGED_OPT_IN(k_grad_staged);
+      DISPATCH_ELEMENT(p, (k_grad_staged<El><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }
+  }
   DISPATCH_ELEMENT(p, (k_grad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -895,6 +1098,37 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
   if (!p || !d_g || !d_y || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
+  if (nv <= 4 && p->variant != TATVA_VARIANT_GENERIC) {
+    int rc = TATVA_OK;
+#define ADJ_ACC(NV)                                                                                              \
+  {                                                                                                              \
+    constexpr int CH_ = El::nq * NV * El::dim, S_ = CH_ | 1, SC_ = 32 * El::npe * NV + 16 * El::npe;              \
+    constexpr size_t smem_ = (size_t)(kBlock / 32) * ((32 * S_ > SC_) ? 32 * S_ : SC_) * sizeof(double);         \
+    static bool done_ = false;                                                                                   \
+    rc = allow_big_smem(k_grad_adjoint_acc<El, NV>, done_);                                                      \
+    if (rc == TATVA_OK)                                                                                          \
+      k_grad_adjoint_acc<El, NV><<<grid_for(p->n_elems), kBlock, smem_, st>>>(p->coords, p->conn, p->n_elems, d_g, d_y); \
+  }
+    switch (nv) {
+      case 1: DISPATCH_ELEMENT(p, ADJ_ACC(1)); break;
+      case 2: DISPATCH_ELEMENT(p, ADJ_ACC(2)); break;
+      case 3: DISPATCH_ELEMENT(p, ADJ_ACC(3)); break;
+      default: DISPATCH_ELEMENT(p, ADJ_ACC(4)); break;
+    }
+#undef ADJ_ACC
+    if (rc != TATVA_OK) return rc;
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
+  {
+    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->dim) | 1) * sizeof(double);
+    if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {
+      STAGED_OPT_IN(k_grad_adjoint_staged);
+      DISPATCH_ELEMENT(p, (k_grad_adjoint_staged<El><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_g, nv, d_y)));
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }
+  }
   DISPATCH_ELEMENT(p, (k_grad_adjoint<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_g, nv, d_y)));
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -903,6 +1137,15 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
 int tatva_op_eval(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv) | 1) * sizeof(double);
+    if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {
+      STAGED_OPT_IN(k_eval_staged);
+      DISPATCH_ELEMENT(p, (k_eval_staged<El><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->conn, p->n_elems, d_u, nv, d_out)));
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }
+  }
   DISPATCH_ELEMENT(p, (k_eval<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->conn, p->n_elems, d_u, nv, d_out)));
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -994,6 +1237,13 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
     if (el == TATVA_HEX8) {
       if (MODE == MODE_HVP && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_hvp_modal(p, prm[0], prm[1], u, v, out, st);
       if (MODE == MODE_RESIDUAL && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_residual_modal(p, prm[0], prm[1], u, out, st);
+      if (MODE == MODE_ENERGY && p->variant != TATVA_VARIANT_GENERIC) {
+        int rc = hex8_nh_energy_modal_partials(p, prm[0], prm[1], u, st);
+        if (rc != TATVA_OK) return rc;
+        k_sum_rows_final<<<1, 256, 0, st>>>(p->scratch, grid_for(p->n_elems), 1, out);
+        TATVA_LAUNCH_CHECK();
+        return TATVA_OK;
+      }
       return launch_fused<Hex8, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
     }
   } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD) {

@@ -930,6 +930,88 @@ __global__ void __launch_bounds__(kBlock, 2)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Energy in the same modal / reference-space form: psi W with I1 = |F|^2 = tr(Fr M Fr^T), M = K^T K,
+// J = det Fr / det J.  Per-CTA partial sums, finished by k_sum_rows_final (fixed order).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 3)
+    k_hex8_nh_energy_modal(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                           double lmbda, const double* __restrict__ u, double* __restrict__ partials) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double energy = 0.0;
+  if (e < E) {
+    int nd[8];
+    {
+      const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+      const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+      nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+      nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+    }
+    double rX[3][7], rx[3][7];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double fX[8], fu[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+        fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      }
+      to_modal(fX, rX[c]);
+      to_modal(fu, rx[c]);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) rx[c][k] += rX[c][k];
+    }
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+      const double tx = kSigns[q][0], ty = kSigns[q][1], tz = kSigns[q][2];
+      double J[3][3], Kc[3][3], detJ;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double g[3];
+        ref_grad_s((const double*)rX[c], 1, tx, ty, tz, g);
+        J[0][c] = g[0]; J[1][c] = g[1]; J[2][c] = g[2];
+      }
+      adjugate(J, Kc, detJ);
+      double M[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+          M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+          M[b][a] = M[a][b];
+        }
+      double Fr[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ref_grad_s((const double*)rx[i], 1, tx, ty, tz, Fr[i]);
+      const double detF = Fr[0][0] * (Fr[1][1] * Fr[2][2] - Fr[1][2] * Fr[2][1]) +
+                          Fr[0][1] * (Fr[1][2] * Fr[2][0] - Fr[1][0] * Fr[2][2]) +
+                          Fr[0][2] * (Fr[1][0] * Fr[2][1] - Fr[1][1] * Fr[2][0]);
+      double I1 = 0.0;  // detJ^2 |F|^2
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) I1 = fma(Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d], Fr[i][d], I1);
+      const double rJ = 1.0 / detJ;
+      const double lnJ = log(detF * rJ);
+      energy += detJ * (0.5 * mu * (I1 * rJ * rJ - 3.0 - 2.0 * lnJ) + 0.5 * lmbda * lnJ * lnJ);
+    }
+  }
+  // block reduction (same scheme as the generic energy kernel)
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) energy += __shfl_down_sync(0xffffffffu, energy, o);
+  if (lane == 0) sh[w] = energy;
+  __syncthreads();
+  if (w == 0) {
+    energy = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) energy += __shfl_down_sync(0xffffffffu, energy, o);
+    if (lane == 0) partials[blockIdx.x] = energy;
+  }
+}
+
 }  // namespace
 
 template <int MINB, int STAGE, int GROUPED = 0>
@@ -986,6 +1068,12 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   k_hex8_nh_residual_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st) {
+  k_hex8_nh_energy_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
