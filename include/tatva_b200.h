@@ -140,6 +140,13 @@ int tatva_csr_assemble(tatva_plan_t* plan, int material, const double* params, i
                        const double* d_u, const int32_t* d_indptr, const int32_t* d_elem_pos,
                        int64_t nnz, double* d_data, tatva_stream_t stream);
 
+/* Same matrix, exploiting the symmetry of the energy Hessian: REDs only for the upper triangle (row node <=
+ * column node), then a mirror pass fills the lower one (K[(a,i),(b,k)] = K[(b,k),(a,i)]).  Needs the CSR column
+ * indices.  ~46 % fewer atomics than tatva_csr_assemble; for multi-point elements it falls back to full assembly. */
+int tatva_csr_assemble_sym(tatva_plan_t* plan, int material, const double* params, int n_params,
+                           const double* d_u, const int32_t* d_indptr, const int32_t* d_indices,
+                           const int32_t* d_elem_pos, int64_t nnz, double* d_data, tatva_stream_t stream);
+
 /* Same matrix, assembled BY ROWS without atomics (deterministic): one warp owns the CSR rows of one node,
  * computes the columns (a,i) of the stiffness of every incident element (= the rows, by symmetry of the
  * energy Hessian) and stores each dpn x dpn block once.  Needs the node -> elements table of

@@ -45,6 +45,7 @@ SIGNATURES = {
     "tatva_hvp_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_residual_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_csr_assemble": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, vp]),
+    "tatva_csr_assemble_sym": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_csr_assemble_rows": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "tatva_halo_pack": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
     "tatva_halo_unpack_set": (C.c_int, [vp, vp, C.c_int64, vp, vp]),

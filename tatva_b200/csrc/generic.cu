@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kBlock) k_csr(const double* __restrict__ coord
 // sector instead of dpn.  The L2 atomic units work per sector (tools/micro/red_sector.cu: 212 G RED/s for
 // scattered doubles, 420-490 G/s when 3-4 lanes share a sector), and assembly is bound by exactly that.
 // Single-quadrature-point elements (the block of one column node fits in registers).
-template <class El, class Mat>
+template <class El, class Mat, bool SYM>
 __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict__ coords,
                                                         const int32_t* __restrict__ conn, int64_t E, Mat mat,
                                                         const double* __restrict__ u,
@@ -682,11 +682,16 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
             sblk[lane * S + (a * dpn + i) * dpn + k] = W * t;
           }
       }
+      int nb_node = 0;  // nd[b] without dynamic indexing
+#pragma unroll
+      for (int n = 0; n < npe; ++n) nb_node = (n == b) ? nd[n] : nb_node;
 #pragma unroll
       for (int a = 0; a < npe; ++a) {
+        // SYM: only the upper triangle (row node <= column node) is accumulated; k_csr_mirror fills the rest
+        const bool keep = !SYM || nd[a] <= nb_node;
         const int p = __ldg(pos + (e * npe + a) * npe + b);
 #pragma unroll
-        for (int i = 0; i < dpn; ++i) sbase[lane * NB + a * dpn + i] = __ldg(indptr + (int64_t)nd[a] * dpn + i) + p;
+        for (int i = 0; i < dpn; ++i) sbase[lane * NB + a * dpn + i] = keep ? __ldg(indptr + (int64_t)nd[a] * dpn + i) + p : -1;
       }
     } else {
 #pragma unroll
@@ -699,6 +704,31 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
       if (base >= 0) atomicAdd(data + (int64_t)base + (r % dpn), sblk[t]);
     }
     __syncwarp();
+  }
+}
+
+// Lower triangle from the upper one (the energy Hessian is symmetric): one warp per node row a, one lane per
+// block (a, b) with b < a:  K[(a,i),(b,k)] = K[(b,k),(a,i)].  The position of a in row b is found by binary search.
+__global__ void __launch_bounds__(128) k_csr_mirror(int64_t n_nodes, int dpn, const int32_t* __restrict__ indptr,
+                                                    const int32_t* __restrict__ indices, double* __restrict__ data) {
+  const int lane = threadIdx.x & 31;
+  const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= n_nodes) return;
+  const int r0 = __ldg(indptr + a * dpn);
+  const int nb = (__ldg(indptr + a * dpn + 1) - r0) / dpn;
+  for (int j = lane; j < nb; j += 32) {
+    const int b = __ldg(indices + r0 + j * dpn) / dpn;
+    if (b >= a) break;  // columns are sorted: the rest of the row is the upper triangle
+    const int c0 = __ldg(indptr + (int64_t)b * dpn);
+    int lo = 0, hi = (__ldg(indptr + (int64_t)b * dpn + 1) - c0) / dpn;
+    while (lo < hi) {  // first block of row b whose node is >= a
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(indices + c0 + mid * dpn) / dpn < (int)a) lo = mid + 1; else hi = mid;
+    }
+    for (int i = 0; i < dpn; ++i) {
+      double* dst = data + (int64_t)__ldg(indptr + a * dpn + i) + j * dpn;
+      for (int k = 0; k < dpn; ++k) dst[k] = data[(int64_t)__ldg(indptr + (int64_t)b * dpn + k) + lo * dpn + i];
+    }
   }
 }
 
@@ -1314,7 +1344,7 @@ int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, in
 
 template <class El, class Mat>
 static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int32_t* indptr, const int32_t* pos,
-                      int64_t nnz, double* data, cudaStream_t st) {
+                      int64_t nnz, double* data, cudaStream_t st, const int32_t* indices = nullptr) {
   TATVA_CUDA_TRY(cudaMemsetAsync(data, 0, sizeof(double) * nnz, st));
   if constexpr (El::nq == 1) {
     if (p->variant != TATVA_VARIANT_GENERIC) {
@@ -1322,10 +1352,16 @@ static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int3
       constexpr size_t smem = (size_t)(kBlock / 32) * 32 * (S + NB / 2 + 1) * sizeof(double);
       static bool configured = false;
       if (!configured && smem > 48 * 1024) {
-        TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_grouped<El, Mat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_grouped<El, Mat, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_grouped<El, Mat, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
       }
-      k_csr_grouped<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
+      if (p->variant == 2 || indices == nullptr) {  // full assembly: every entry by REDs
+        k_csr_grouped<El, Mat, false><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
+      } else {  // upper triangle by REDs, lower triangle mirrored (symmetric energy Hessian)
+        k_csr_grouped<El, Mat, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
+        k_csr_mirror<<<(int)((p->n_nodes + 3) / 4), 128, 0, st>>>(p->n_nodes, Mat::dpn, indptr, indices, data);
+      }
       TATVA_LAUNCH_CHECK();
       return TATVA_OK;
     }
@@ -1335,32 +1371,45 @@ static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int3
   return TATVA_OK;
 }
 
+static int csr_dispatch(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
+                        const int32_t* d_indptr, const int32_t* d_indices, const int32_t* d_pos, int64_t nnz,
+                        double* d_data, tatva_stream_t stream) {
+  if (!p || !prm || !d_u || !d_indptr || !d_pos || !d_data || nnz <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int el = p->element;
+  if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
+    if (el == TATVA_TRI3) return launch_csr<Tri3, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_QUAD4) return launch_csr<Quad4, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_TRI6) return launch_csr<Tri6, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_QUAD8) return launch_csr<Quad8, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_TET4) return launch_csr<Tet4, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_HEX8) return launch_csr<Hex8, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+  } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
+    if (el == TATVA_TET4) return launch_csr<Tet4, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_HEX8) return launch_csr<Hex8, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+  } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5) {
+    const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+    if (el == TATVA_TET4) return launch_csr<Tet4, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+    if (el == TATVA_HEX8) return launch_csr<Hex8, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
+  } else {
+    return TATVA_E_INVALID;
+  }
+  return TATVA_E_UNSUPPORTED;
+}
+
 extern "C" {
 
 int tatva_csr_assemble(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
                        const int32_t* d_indptr, const int32_t* d_pos, int64_t nnz, double* d_data,
                        tatva_stream_t stream) {
-  if (!p || !prm || !d_u || !d_indptr || !d_pos || !d_data || nnz <= 0) return TATVA_E_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int el = p->element;
-  if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
-    if (el == TATVA_TRI3) return launch_csr<Tri3, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_QUAD4) return launch_csr<Quad4, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_TRI6) return launch_csr<Tri6, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_QUAD8) return launch_csr<Quad8, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_TET4) return launch_csr<Tet4, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_HEX8) return launch_csr<Hex8, LinearElastic<3>>(p, LinearElastic<3>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-  } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
-    if (el == TATVA_TET4) return launch_csr<Tet4, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_HEX8) return launch_csr<Hex8, NeoHookean>(p, NeoHookean{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st);
-  } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5) {
-    const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
-    if (el == TATVA_TET4) return launch_csr<Tet4, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_pos, nnz, d_data, st);
-    if (el == TATVA_HEX8) return launch_csr<Hex8, NeoHookeanPhaseField>(p, m, d_u, d_indptr, d_pos, nnz, d_data, st);
-  } else {
-    return TATVA_E_INVALID;
-  }
-  return TATVA_E_UNSUPPORTED;
+  return csr_dispatch(p, material, prm, n_params, d_u, d_indptr, nullptr, d_pos, nnz, d_data, stream);
+}
+// Symmetric variant: REDs only for the upper triangle, then a mirror pass (needs the column indices).
+int tatva_csr_assemble_sym(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
+                           const int32_t* d_indptr, const int32_t* d_indices, const int32_t* d_pos, int64_t nnz,
+                           double* d_data, tatva_stream_t stream) {
+  if (!d_indices) return TATVA_E_INVALID;
+  return csr_dispatch(p, material, prm, n_params, d_u, d_indptr, d_indices, d_pos, nnz, d_data, stream);
 }
 
 }  // extern "C"

@@ -173,7 +173,7 @@ class _Assembler:
     """Direct CSR assembly plan for (operator, material, pattern): device copies of indptr and of the
     element -> CSR position table."""
 
-    def __init__(self, op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None):
+    def __init__(self, op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None, symmetric: bool = False):
         dpn = material.dofs_per_node(op.dim)
         indptr = np.ascontiguousarray(_np(colored_matrix.indptr), dtype=np.int32)
         indices = np.ascontiguousarray(_np(colored_matrix.indices), dtype=np.int32)
@@ -202,6 +202,10 @@ class _Assembler:
             self.d_n2e = torch.as_tensor(lst[: int(ptr[-1])], device=op.device)
         else:
             self.d_pos = torch.as_tensor(pos, device=op.device)
+            # symmetric = True: REDs for the upper triangle only + mirror pass (valid: all fused laws are energies)
+            self.symmetric = bool(symmetric)
+            if self.symmetric:
+                self.d_indices = torch.as_tensor(indices, device=op.device)
 
     def __call__(self, u, out=None) -> torch.Tensor:
         op = self.op
@@ -212,16 +216,20 @@ class _Assembler:
         if self.by_rows:
             op._call("tatva_csr_assemble_rows", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_indices.data_ptr(),
                      self.d_n2e_ptr.data_ptr(), self.d_n2e.data_ptr(), out.data_ptr())
+        elif self.symmetric:
+            op._call("tatva_csr_assemble_sym", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_indices.data_ptr(), self.d_pos.data_ptr(), self.nnz, out.data_ptr())
         else:
             op._call("tatva_csr_assemble", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_pos.data_ptr(), self.nnz, out.data_ptr())
         return out
 
 
-def assembler(op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None) -> Callable:
+def assembler(op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None, symmetric: bool = False) -> Callable:
     """u -> CSR data (nnz,) of d^2E/du^2 on the pattern of `colored_matrix` (one kernel).
-    Default: element-per-thread kernel with one FP64 RED per entry (fastest on B200: 0.65 ms at config 2).
+    Default: element-per-thread kernel with sector-grouped FP64 REDs for every entry (0.46 ms at config 2).
+    symmetric=True adds only the upper triangle by RED and mirrors the lower one (measured slower on B200: 0.61 ms —
+    the RED loop is issue-bound, not L2-bound, so halving the active lanes does not pay for the mirror pass).
     by_rows=True selects the atomic-free row-wise kernel (Tri3, Tet4): bitwise reproducible, ~1.6x slower."""
-    return _Assembler(op, material, colored_matrix, by_rows)
+    return _Assembler(op, material, colored_matrix, by_rows, symmetric)
 
 
 def _coloured_columns(fn_jvp, u, colored_matrix, color_batch_size):

@@ -71,6 +71,8 @@ def test_direct_assembly_matches_coloured_oracle(kind, n):
     pat = sparse.pattern_from_mesh(mesh, dpn)
     cm = sparse.ColoredMatrix.from_csr(pat)
     data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
+    sym = sparse.assembler(op, mat, cm, symmetric=True)(u).cpu().numpy()  # upper triangle by RED + mirror pass
+    assert _rel(sym, data) < 1e-13
     if kind != "hex8":  # both kernels: per-entry atomics (default) and the deterministic row-wise one
         rows1 = sparse.assembler(op, mat, cm, by_rows=True)(u).cpu().numpy()
         assert _rel(rows1, data) < 1e-13

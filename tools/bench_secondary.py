@@ -63,6 +63,10 @@ if want("tet4"):
     nnz = asm.nnz
     report("tet4_nh_csr_assemble_c2", timeit(lambda: asm(u, out=data), reps=10), 8 * nnz + 64 * E + 8 * 6 * N + 16 * E, nnz, "nnz", nnz=nnz, n_colors=int(cm.colors.max()) + 1,
            host_pattern_s=round(t1 - t0, 3), host_colouring_s=round(t2 - t1, 3), host_positions_s=round(t3 - t2, 3))
+    asm3 = sparse.assembler(op, mat, cm, symmetric=True)
+    data3 = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    report("tet4_nh_csr_assemble_symmetric_mirror_c2", timeit(lambda: asm3(u, out=data3), reps=10), 8 * nnz + 64 * E + 8 * 6 * N + 16 * E, nnz, "nnz", rel_diff=float((data - data3).norm() / data3.norm()))
+    del data3, asm3
     asm2 = sparse.assembler(op, mat, cm, by_rows=True)
     data2 = torch.empty(nnz, dtype=torch.float64, device="cuda")
     report("tet4_nh_csr_assemble_rows_deterministic_c2", timeit(lambda: asm2(u, out=data2), reps=10), 8 * nnz + 64 * E + 8 * 6 * N + 16 * E, nnz, "nnz", rel_diff=float((data - data2).norm() / data2.norm()))
