@@ -76,9 +76,16 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise TatvaError(
-                f"{LIB_PATH} not found: build it with `python -m tatva_b200.build` (there is no CPU fallback)"
-            )
+            # not built yet (fresh checkout): compile it now if nvcc is around; there is no CPU fallback
+            try:
+                from . import build as _build
+
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise TatvaError(
+                    f"{LIB_PATH} not found and building it failed ({exc}); run `python -m tatva_b200.build` "
+                    "(there is no CPU fallback)"
+                ) from exc
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)

@@ -425,6 +425,34 @@ struct NeoHookeanPhaseField {
   }
 };
 
+// Sector-grouped scatter-add of the per-element nodal contributions of one warp: the values are re-dealt
+// through shared memory so that consecutive lanes add the DPN consecutive doubles of one node (one 32-byte
+// sector per group instead of DPN separate ones; the L2 atomic units work per sector).  All 32 lanes must call.
+template <int NPE, int DPN>
+TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const double (&Y)[NPE][DPN], bool valid,
+                             double* warp_smem) {
+  constexpr int S = NPE * DPN;
+  const int lane = threadIdx.x & 31;
+  int* snode = reinterpret_cast<int*>(warp_smem + 32 * S);
+#pragma unroll
+  for (int n = 0; n < NPE; ++n) {
+    snode[lane * NPE + n] = valid ? nd[n] : -1;
+#pragma unroll
+    for (int c = 0; c < DPN; ++c) warp_smem[lane * S + n * DPN + c] = Y[n][c];
+  }
+  __syncwarp();
+  for (int t = lane; t < 32 * S; t += 32) {
+    const int j = t / S, r = t - j * S;
+    const int node = snode[j * NPE + r / DPN];
+    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[t]);
+  }
+  __syncwarp();
+}
+template <int NPE, int DPN>
+constexpr size_t grouped_scatter_smem(int warps) {
+  return (size_t)warps * (32 * NPE * DPN + 16 * NPE) * sizeof(double);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The plan (opaque to C callers)
 // ---------------------------------------------------------------------------------------------
@@ -467,5 +495,7 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
 
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st);
+int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
+int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
 
 }  // namespace tatva

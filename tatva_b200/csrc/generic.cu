@@ -109,34 +109,6 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint(const double* __restric
   }
 }
 
-// Sector-grouped scatter-add of the per-element nodal contributions of one warp: the values are re-dealt
-// through shared memory so that consecutive lanes add the DPN consecutive doubles of one node (one 32-byte
-// sector per group instead of DPN separate ones; the L2 atomic units work per sector).  All 32 lanes must call.
-template <int NPE, int DPN>
-TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const double (&Y)[NPE][DPN], bool valid,
-                             double* warp_smem) {
-  constexpr int S = NPE * DPN;
-  const int lane = threadIdx.x & 31;
-  int* snode = reinterpret_cast<int*>(warp_smem + 32 * S);
-#pragma unroll
-  for (int n = 0; n < NPE; ++n) {
-    snode[lane * NPE + n] = valid ? nd[n] : -1;
-#pragma unroll
-    for (int c = 0; c < DPN; ++c) warp_smem[lane * S + n * DPN + c] = Y[n][c];
-  }
-  __syncwarp();
-  for (int t = lane; t < 32 * S; t += 32) {
-    const int j = t / S, r = t - j * S;
-    const int node = snode[j * NPE + r / DPN];
-    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[t]);
-  }
-  __syncwarp();
-}
-template <int NPE, int DPN>
-constexpr size_t grouped_scatter_smem(int warps) {
-  return (size_t)warps * (32 * NPE * DPN + 16 * NPE) * sizeof(double);
-}
-
 // ---- warp-staged variants: element-major (E, Q, v[, d]) arrays are written / read through shared memory ----
 // Each lane produces (or consumes) the CH = nq*nv[*dim] contiguous doubles of its own element; staging them per
 // warp turns 32 strided 8-byte accesses per instruction into one contiguous 32*CH-double block.  Row stride
@@ -1263,7 +1235,11 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
     if (el == TATVA_HEX8) return launch_fused<Hex8, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
   } else if (material == TATVA_NEO_HOOKEAN) {
     if (n_params != 2) return TATVA_E_INVALID;
-    if (el == TATVA_TET4) return launch_fused<Tet4, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
+    if (el == TATVA_TET4) {
+      if (MODE == MODE_HVP && p->variant != TATVA_VARIANT_GENERIC) return tet4_nh_hvp_ref(p, prm[0], prm[1], u, v, out, st);
+      if (MODE == MODE_RESIDUAL && p->variant != TATVA_VARIANT_GENERIC) return tet4_nh_residual_ref(p, prm[0], prm[1], u, out, st);
+      return launch_fused<Tet4, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
+    }
     if (el == TATVA_HEX8) {
       if (MODE == MODE_HVP && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_hvp_modal(p, prm[0], prm[1], u, v, out, st);
       if (MODE == MODE_RESIDUAL && p->variant != TATVA_VARIANT_GENERIC) return hex8_nh_residual_modal(p, prm[0], prm[1], u, out, st);

@@ -1012,6 +1012,82 @@ __global__ void __launch_bounds__(kBlock, 3)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tet4 x neo-Hookean in the same reference-space form (one point, constant dN/dxi):
+//   J = [X1-X0, X2-X0, X3-X0]^T,  Fr = J + [u1-u0, ...],  Gv = [v1-v0, ...],  W = det J / 6,
+//   nodal forces f_1..3 = columns of Q = W dP K (resp. W P K), f_0 = -(f_1 + f_2 + f_3).
+// About 290 FP64 instructions per element instead of ~450 for the generic template.
+// ---------------------------------------------------------------------------------------------
+TATVA_D void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3][3], double mu_s, double lm_s,
+                                 double (&Q)[3][3]) {
+  double Kc[3][3], detJ, Ac[3][3], detF;
+  adjugate(J, Kc, detJ);
+  double M[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+      M[b][a] = M[a][b];
+    }
+  adjugate(Fr, Ac, detF);
+  const double r = 1.0 / (detJ * detF);
+  const double rJ = r * detF, rF = r * detJ;
+  const double lnJ = log(detF * rJ);
+  const double w1 = mu_s * rJ, w2 = (lm_s * lnJ - mu_s) * detJ * rF;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      Q[i][d] = fma(w1, Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d], w2 * Ac[d][i]);
+}
+
+template <bool HVP>
+__global__ void __launch_bounds__(kBlock) k_tet4_nh_ref(const double* __restrict__ coords,
+                                                        const int32_t* __restrict__ conn, int64_t E, double mu,
+                                                        double lmbda, const double* __restrict__ u,
+                                                        const double* __restrict__ v, double* __restrict__ y) {
+  extern __shared__ double sm[];
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e0 < E;
+  const int64_t e = valid ? e0 : E - 1;
+  int nd[4];
+  {
+    const int4 t = __ldg(reinterpret_cast<const int4*>(conn) + e);
+    nd[0] = t.x; nd[1] = t.y; nd[2] = t.z; nd[3] = t.w;
+  }
+  double X[4][3], U[4][3], V[4][3];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      X[n][c] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      U[n][c] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      if constexpr (HVP) V[n][c] = __ldg(v + (int64_t)nd[n] * 3 + c);
+    }
+  double J[3][3], Fr[3][3], Gv[3][3], Q[3][3];  // J[d][c] = dX_c/dxi_d ; Fr[i][d] = dx_i/dxi_d
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      J[d][c] = X[d + 1][c] - X[0][c];
+      Fr[c][d] = J[d][c] + (U[d + 1][c] - U[0][c]);
+      if constexpr (HVP) Gv[c][d] = V[d + 1][c] - V[0][c];
+    }
+  if constexpr (HVP) point_flux(J, Fr, Gv, mu * (1.0 / 6.0), lmbda * (1.0 / 6.0), Q);
+  else point_flux_residual(J, Fr, mu * (1.0 / 6.0), lmbda * (1.0 / 6.0), Q);
+  double Y[4][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Y[1][i] = Q[i][0];
+    Y[2][i] = Q[i][1];
+    Y[3][i] = Q[i][2];
+    Y[0][i] = -(Q[i][0] + Q[i][1] + Q[i][2]);
+  }
+  grouped_scatter<4, 3>(y, nd, Y, valid, sm + (size_t)(threadIdx.x >> 5) * (32 * 12 + 16 * 4));
+}
+
 }  // namespace
 
 template <int MINB, int STAGE, int GROUPED = 0>
@@ -1074,6 +1150,19 @@ int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const d
 
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st) {
   k_hex8_nh_energy_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st) {
+  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  k_tet4_nh_ref<true><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
+  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  k_tet4_nh_ref<false><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, nullptr, y);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
