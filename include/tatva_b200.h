@@ -70,6 +70,12 @@ int tatva_plan_destroy(tatva_plan_t* plan);
 int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, int* nq,
                     int64_t* n_nodes, int64_t* n_elems);
 int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
+/* Optional shared-memory staging tiles for gather-bound elements (Tet4 x neo-Hookean residual / HVP): tile t =
+ * elements [128 t, 128 (t+1)); d_tile_nodes[d_tile_ptr[t] .. d_tile_ptr[t+1]) are its sorted unique nodes and
+ * d_tile_conn (n_elems, npe) uint16 its connectivity in tile-local indices (tatva_host_build_tiles).  The CTA
+ * gathers the unique nodes once, coalesced, into shared memory.  Device views, caller-owned; NULL disables.   */
+int tatva_plan_set_tiles(tatva_plan_t* plan, const int32_t* d_tile_ptr, const int32_t* d_tile_nodes,
+                         const uint16_t* d_tile_conn, int max_unique);
 
 /* ---- quadrature-loop building blocks (generic path; any user energy on top) ------------ */
 
@@ -216,6 +222,8 @@ int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, i
  * first to size it (ptr[n_nodes]).                                                                   */
 int tatva_host_node_to_elements(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes,
                                 int32_t* ptr, int32_t* list);
+int tatva_host_build_tiles(const int32_t* conn, int64_t n_elems, int npe, int tile_elems, int32_t* tile_ptr,
+                           int32_t* tile_nodes, uint16_t* local_conn, int32_t* max_unique);
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe,
                                      int dofs_per_node, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos);

@@ -471,6 +471,11 @@ struct tatva_plan {
   double* scratch;  // plan-owned: energy partials / row-sum partials
   int64_t scratch_len;
   double* weights;  // plan-owned (n_elems, nq) when TATVA_PLAN_CACHE_WEIGHTS
+  // optional shared-memory staging tiles (caller-owned device views, see tatva_plan_set_tiles)
+  const int32_t* tile_ptr;
+  const int32_t* tile_nodes;
+  const uint16_t* tile_conn;
+  int tile_max_unique;
 };
 
 namespace tatva {
@@ -497,5 +502,6 @@ int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const d
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st);
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
 int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
+int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
 
 }  // namespace tatva

@@ -1025,6 +1025,10 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->variant = TATVA_VARIANT_DEFAULT;
   p->zero_output = 1;
   p->weights = nullptr;
+  p->tile_ptr = nullptr;
+  p->tile_nodes = nullptr;
+  p->tile_conn = nullptr;
+  p->tile_max_unique = 0;
   p->scratch_len = (int64_t)grid_for(n_elems) > 1024 * 64 ? (int64_t)grid_for(n_elems) : 1024 * 64;
   cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
   if (e != cudaSuccess) { delete p; return (int)e; }
@@ -1058,6 +1062,16 @@ int tatva_plan_info(const tatva_plan_t* p, int* element, int* dim, int* npe, int
   if (nq) *nq = p->nq;
   if (n_nodes) *n_nodes = p->n_nodes;
   if (n_elems) *n_elems = p->n_elems;
+  return TATVA_OK;
+}
+
+int tatva_plan_set_tiles(tatva_plan_t* p, const int32_t* d_tile_ptr, const int32_t* d_tile_nodes,
+                         const uint16_t* d_tile_conn, int max_unique) {
+  if (!p || (d_tile_ptr && (!d_tile_nodes || !d_tile_conn || max_unique <= 0))) return TATVA_E_INVALID;
+  p->tile_ptr = d_tile_ptr;
+  p->tile_nodes = d_tile_nodes;
+  p->tile_conn = d_tile_conn;
+  p->tile_max_unique = d_tile_ptr ? max_unique : 0;
   return TATVA_OK;
 }
 
@@ -1236,6 +1250,8 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
   } else if (material == TATVA_NEO_HOOKEAN) {
     if (n_params != 2) return TATVA_E_INVALID;
     if (el == TATVA_TET4) {
+      if (MODE != MODE_ENERGY && p->tile_ptr && p->variant != TATVA_VARIANT_GENERIC && p->zero_output)
+        return tet4_nh_tiled(p, MODE == MODE_HVP, prm[0], prm[1], u, v, out, st);
       if (MODE == MODE_HVP && p->variant != TATVA_VARIANT_GENERIC) return tet4_nh_hvp_ref(p, prm[0], prm[1], u, v, out, st);
       if (MODE == MODE_RESIDUAL && p->variant != TATVA_VARIANT_GENERIC) return tet4_nh_residual_ref(p, prm[0], prm[1], u, out, st);
       return launch_fused<Tet4, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
@@ -1298,6 +1314,7 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
   sub.conn = p->conn + elem_begin * p->npe;
   sub.n_elems = elem_count;
   sub.zero_output = zero_y ? 1 : 0;
+  sub.tile_ptr = nullptr;  // tiles describe the whole element list, not a sub-range
   return dispatch_fused<MODE_HVP>(&sub, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
 }
 int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,
@@ -1314,6 +1331,7 @@ int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, in
   sub.conn = p->conn + elem_begin * p->npe;
   sub.n_elems = elem_count;
   sub.zero_output = zero_r ? 1 : 0;
+  sub.tile_ptr = nullptr;
   return dispatch_fused<MODE_RESIDUAL>(&sub, material, params, n_params, d_u, nullptr, d_r, (cudaStream_t)stream);
 }
 }  // extern "C"

@@ -141,6 +141,43 @@ int tatva_host_node_to_elements(const int32_t* conn, int64_t n_elems, int npe, i
   return TATVA_OK;
 }
 
+// Shared-memory staging tiles: consecutive groups of `tile_elems` elements (one CTA each), the sorted unique
+// nodes each group touches and the connectivity re-expressed in tile-local node indices.  Two-call protocol:
+// tile_nodes == NULL fills tile_ptr (n_tiles + 1) and *max_unique only.
+int tatva_host_build_tiles(const int32_t* conn, int64_t n_elems, int npe, int tile_elems, int32_t* tile_ptr,
+                           int32_t* tile_nodes, uint16_t* local_conn, int32_t* max_unique) {
+  if (!conn || !tile_ptr || !max_unique || n_elems <= 0 || npe <= 0 || tile_elems <= 0) return TATVA_E_INVALID;
+  const int64_t n_tiles = (n_elems + tile_elems - 1) / tile_elems;
+  std::vector<int32_t> counts(n_tiles, 0);
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    const int64_t e0 = t * tile_elems, e1 = std::min(n_elems, e0 + tile_elems);
+    std::vector<int32_t> nodes(conn + e0 * npe, conn + e1 * npe);
+    std::sort(nodes.begin(), nodes.end());
+    nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+    counts[t] = (int32_t)nodes.size();
+    if (nodes.size() > 65535) bad |= 1;
+    if (tile_nodes) {
+      int32_t* dst = tile_nodes + tile_ptr[t];
+      std::copy(nodes.begin(), nodes.end(), dst);
+      for (int64_t i = e0 * npe; i < e1 * npe; ++i)
+        local_conn[i] = (uint16_t)(std::lower_bound(nodes.begin(), nodes.end(), conn[i]) - nodes.begin());
+    }
+  }
+  if (bad) return TATVA_E_INVALID;
+  if (!tile_nodes) {
+    tile_ptr[0] = 0;
+    int32_t mx = 0;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      tile_ptr[t + 1] = tile_ptr[t] + counts[t];
+      mx = std::max(mx, counts[t]);
+    }
+    *max_unique = mx;
+  }
+  return TATVA_OK;
+}
+
 // elem_pos[e, a, b] = offset of column dpn*conn[e,b] inside CSR row dpn*conn[e,a]
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe, int dpn, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos) {

@@ -34,7 +34,7 @@ def _stream() -> int:
 
 
 class Operator:
-    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None, sort_elements: bool = False):
+    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None, sort_elements: bool = False, stage_tiles: bool = False):
         self.mesh = mesh
         self.element = element
         self.cache_weights = bool(cache_weights)
@@ -78,6 +78,28 @@ class Operator:
             with torch.cuda.device(self.device):
                 _lib.check(self._L.tatva_plan_create(C.byref(h2), element.kind, self.n_nodes, self.n_elements, self.coords.data_ptr(), self.elements_fused.data_ptr(), 0, _stream()), "tatva_plan_create")
             self._plan_fused = h2
+
+        # Shared-memory staging tiles for gather-bound kernels (Tet4 x neo-Hookean): per CTA the unique nodes are
+        # gathered once, coalesced, and elements read them through tile-local uint16 connectivity.
+        self._tiles = None
+        if stage_tiles:
+            self._build_tiles()
+
+    def _build_tiles(self):
+        conn = np.ascontiguousarray(self.elements_fused.cpu().numpy(), dtype=np.int32)
+        E, npe = conn.shape
+        n_tiles = (E + 127) // 128
+        tile_ptr = np.empty(n_tiles + 1, dtype=np.int32)
+        mx = C.c_int32()
+        i32 = lambda a: a.ctypes.data_as(_lib.c_i32p)  # noqa: E731
+        _lib.check(self._L.tatva_host_build_tiles(i32(conn), E, npe, 128, i32(tile_ptr), None, None, C.byref(mx)), "tatva_host_build_tiles")
+        tile_nodes = np.empty(int(tile_ptr[-1]), dtype=np.int32)
+        local = np.empty((E, npe), dtype=np.uint16)
+        _lib.check(self._L.tatva_host_build_tiles(i32(conn), E, npe, 128, i32(tile_ptr), i32(tile_nodes), local.ctypes.data_as(C.POINTER(C.c_uint16)), C.byref(mx)), "tatva_host_build_tiles")
+        dev = lambda a: torch.as_tensor(a, device=self.device)  # noqa: E731
+        self._tiles = (dev(tile_ptr), dev(tile_nodes), torch.as_tensor(local.view(np.int16), device=self.device), int(mx.value))
+        tp, tn, tc, m = self._tiles
+        _lib.check(self._L.tatva_plan_set_tiles(self._plan_fused, tp.data_ptr(), tn.data_ptr(), tc.data_ptr(), m), "tatva_plan_set_tiles")
 
     def __del__(self):
         L = getattr(self, "_L", None)

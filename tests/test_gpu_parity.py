@@ -253,3 +253,14 @@ def test_second_order_and_quad_elements(golden, kind):
     cm = sparse.ColoredMatrix.from_csr(pat)
     data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
     _assert_close(data, orc.assemble_csr_data(kind, omat, c, el, u, pat.indptr, pat.indices))
+
+
+def test_tiled_tet4_kernels_match_oracle():
+    """Operator(stage_tiles=True): Tet4 neo-Hookean residual / HVP through the shared-memory staging tiles."""
+    c, el, u, v, (mname, omat) = _case("tet4", 9)
+    mat = _material(mname, omat)
+    for kw in (dict(stage_tiles=True), dict(stage_tiles=True, sort_elements=True)):
+        op = _make_op("tet4", c, el[np.random.default_rng(4).permutation(el.shape[0])] if "sort_elements" in kw else el, **kw)
+        elx = np.asarray(op.mesh.elements)
+        _assert_close(op.hvp(mat)(u, v), orc.hvp("tet4", omat, c, elx, u, v))
+        _assert_close(op.residual(mat)(u), orc.residual("tet4", omat, c, elx, u))

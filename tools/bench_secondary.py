@@ -51,6 +51,10 @@ if want("tet4"):
     y = torch.empty_like(u)
     report("tet4_nh_hvp_c2", timeit(lambda: op._raw_hvp(mat, u, v, out=y)), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", elems=E)
     report("tet4_nh_residual_c2", timeit(lambda: op._raw_residual(mat, u)), 8 * (6 * N + 3 * N) + 16 * E, 3 * N, "DOF")
+    opt = tatva_b200.Operator(m, element.Tetrahedron4(), stage_tiles=True)
+    report("tet4_nh_hvp_c2_smem_tiles", timeit(lambda: opt._raw_hvp(mat, u, v, out=y)), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", max_unique_per_tile=opt._tiles[3])
+    report("tet4_nh_residual_c2_smem_tiles", timeit(lambda: opt._raw_residual(mat, u)), 8 * (6 * N + 3 * N) + 16 * E, 3 * N, "DOF")
+    del opt
     report("tet4_nh_energy_c2", timeit(lambda: op._raw_energy(mat, u)), 8 * (3 * N + 3 * N) + 16 * E, 3 * N, "DOF")
     t0 = time.perf_counter()
     pat = sparse.pattern_from_mesh(m, 3)
