@@ -12,7 +12,8 @@ Here the constraint chain is composed ONCE on the host into a source table (full
 deterministic segmented sum (`tatva_reduce_adjoint`); `reduce` is one pack kernel.  NumPy inputs take the
 same composed tables through NumPy indexing (host-side set-up and tests).
 
-Not carried over: `PeriodicMPI`, `Lifter.adapt_layout`.
+`Lifter.adapt_layout` and `PeriodicMPI` (lifter/base.py:333-425, constraints.py:223-287) are the distributed
+host logic: `comm` is a torch.distributed process group (see tatva_b200.mpi).
 """
 from __future__ import annotations
 
@@ -72,6 +73,10 @@ class Constraint:
     def _runtime_specs(self):
         return ()
 
+    def _resolve_indices(self, layout):
+        """Re-express the constraint in the local indices of `layout` (only PeriodicMPI needs to)."""
+        return self
+
     # symbolic application to the source table (kind, payload): see Lifter._compose
     def _compose(self, src, consts, runtime_values):
         raise NotImplementedError
@@ -118,6 +123,52 @@ class Periodic(Constraint):
         base = src[self.dofs] == -1
         if base.any():
             raise LifterError("Periodic master DOF is constrained by a later constraint: reorder the constraints")
+
+
+def create_g2l(l2g):
+    """Lookup natural-global -> local index, -1 where absent (tatva/utils.py:265-280)."""
+    l2g = np.asarray(l2g)
+    order = np.argsort(l2g)
+    sorted_l2g = l2g[order]
+
+    def lookup(global_indices):
+        gi = np.asarray(global_indices)
+        if sorted_l2g.size == 0:
+            return np.full_like(gi, -1)
+        pos = np.searchsorted(sorted_l2g, gi)
+        ok = (pos < sorted_l2g.size) & (sorted_l2g[np.minimum(pos, sorted_l2g.size - 1)] == gi)
+        out = np.full_like(gi, -1)
+        out[ok] = order[pos[ok]]
+        return out
+
+    return lookup
+
+
+class PeriodicMPI(Periodic):
+    """Periodicity between natural-global DOF ids that may live on different ranks
+    (lifter/constraints.py:223-287).  Masters of local slaves that this rank does not hold become extra
+    ghost DOFs of the layout (`Lifter.adapt_layout`)."""
+
+    def __init__(self, dofs, master_dofs, layout, *, comm=None):
+        self._comm = comm
+        d = np.asarray(_np(dofs), dtype=np.int64).reshape(-1)
+        m = np.asarray(_np(master_dofs), dtype=np.int64).reshape(-1)
+        lookup = create_g2l(layout.natural_l2g)
+        local = lookup(d)
+        here = local >= 0
+        self._slave_natural_g, self._master_natural_g = d[here], m[here]
+        self._extra_ghost_dofs = self._master_natural_g[lookup(self._master_natural_g) < 0]
+        super().__init__(local[here], np.zeros(int(here.sum()), dtype=np.int64))
+
+    def _resolve_indices(self, layout):
+        lookup = create_g2l(layout.natural_l2g)
+        s_loc, m_loc = lookup(self._slave_natural_g), lookup(self._master_natural_g)
+        if (s_loc < 0).any() or (m_loc < 0).any():
+            raise LifterError("PeriodicMPI: failed to resolve local indices for periodic DOFs; make sure all required masters were added as ghosts to the layout")
+        out = type(self).__new__(type(self))
+        out.__dict__ = dict(self.__dict__)
+        out.dofs, out.master_dofs = s_loc.astype(np.int64), m_loc.astype(np.int64)
+        return out
 
 
 class _Indexer:
@@ -223,7 +274,7 @@ class Lifter:
                 out = torch.empty(self.size, dtype=ur.dtype, device=ur.device)
             with torch.cuda.device(ur.device):
                 _lib.check(_lib.lib().tatva_lift(ur.data_ptr(), src.data_ptr(), consts.data_ptr(), base.data_ptr() if base is not None else None, self.size, out.data_ptr(), self._stream()), "tatva_lift")
-            return out
+            return out[: self._local_size] if self._local_size != self.size else out
         src, consts, _, _ = self._compose()
         ur = _np(u_reduced)
         out = np.zeros(self.size, dtype=ur.dtype) if u_full is None else np.array(_np(u_full), dtype=ur.dtype, copy=True)
@@ -231,7 +282,7 @@ class Lifter:
         out[red] = ur[src[red]]
         cst = src <= -2
         out[cst] = consts[-(src[cst] + 2)]
-        return out
+        return out[: self._local_size]  # extra ghost DOFs added by PeriodicMPI are not part of the result
 
     def lift_from_zeros(self, u_reduced, out=None):
         return self.lift(u_reduced, None, out=out) if out is not None else self.lift(u_reduced, None)
@@ -272,6 +323,49 @@ class Lifter:
                 hom.append(Fixed(c.dofs, 0.0) if isinstance(c, Fixed) else c)
             self._homogeneous = Lifter(self.size, *hom)
         return self._homogeneous
+
+    # -- distributed layouts (lifter/base.py:333-425) ------------------------------------------------------
+    @property
+    def _local_size(self) -> int:
+        return self.size - (getattr(self, "_nb_extra_ghost_dofs", None) or 0)
+
+    def adapt_layout(self, layout, comm):
+        """(reduced layout of the free DOFs, lifter resolved against the possibly ghost-augmented layout).
+        Free owned DOFs get new rank-contiguous global ids; free ghosts are resolved through the all-DOF
+        global ids of the (augmented) full layout."""
+        from .mpi import _LocalLayout, _as_comm, _create_dof_layout
+
+        comm = _as_comm(comm)
+        extra = [c._extra_ghost_dofs for c in self.constraints if hasattr(c, "_extra_ghost_dofs")]
+        if extra:
+            local_extra = np.unique(np.concatenate(extra))
+            full = _create_dof_layout(
+                np.concatenate([np.asarray(layout.natural_l2g), local_extra]).astype(np.int32),
+                np.concatenate([np.asarray(layout.owned_mask), np.zeros(len(local_extra), dtype=bool)]),
+                layout.n_global, comm,
+            )
+        else:
+            local_extra, full = np.zeros(0, dtype=np.int64), layout
+        lifter = type(self)(full.n_total, *(c._resolve_indices(full) for c in self.constraints)).with_values(self._runtime_values)
+        if extra:
+            lifter._nb_extra_ghost_dofs = int(len(local_extra))
+        free = lifter.free_dofs
+        owned_free = np.asarray(full.owned_mask)[free]
+        g_free = np.asarray(full.local_to_global)[free]
+        published = comm.allgather(g_free[owned_free])  # all-DOF global ids of every rank's owned free DOFs
+        counts = [len(p) for p in published]
+        offset = int(sum(counts[: comm.rank]))
+        l2g = np.full(free.size, -1, dtype=np.int32)
+        l2g[owned_free] = offset + np.arange(int(owned_free.sum()), dtype=np.int32)
+        if (~owned_free).any():
+            directory = np.full(full.n_global, -1, dtype=np.int32)
+            start = 0
+            for p in published:
+                directory[p] = start + np.arange(len(p), dtype=np.int32)
+                start += len(p)
+            l2g[~owned_free] = directory[g_free[~owned_free]]
+        reduced = _LocalLayout(l2g, offset, int(owned_free.sum()), int(free.size), int(sum(counts)), owned_free, g_free)
+        return reduced, lifter
 
     # -- sparsity (lifter/base.py:281-331) ----------------------------------------------------------------
     def augment_sparsity(self, sparsity):
@@ -320,4 +414,4 @@ def lifted(fn: Callable | None = None, *, argnums=0, output: str | None = None):
     return lifted_fn
 
 
-__all__ = ["Lifter", "lifted", "Constraint", "Fixed", "Periodic", "RuntimeValue", "LifterError"]
+__all__ = ["Lifter", "lifted", "Constraint", "Fixed", "Periodic", "PeriodicMPI", "RuntimeValue", "LifterError", "create_g2l"]

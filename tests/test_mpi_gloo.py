@@ -198,12 +198,66 @@ def _body_partitioned_residual(rank, world):
     assert plan.global_size == c.size
 
 
+def _body_lifter_adapt_layout(rank, world):
+    """reference tests/test_exchange_plan.py:358-417 (a fixed node drops out of the reduced layout) and :27-94 with
+    `Lifter.adapt_layout` in the chain as the reference's tests use it."""
+    from tatva_b200.compound import FieldType, field
+    from tatva_b200.lifter import Fixed, Lifter
+    from tatva_b200.mpi import ExchangePlan
+
+    S = _mock_state(rank, {"u": field(shape=(2, 1), field_type=FieldType.NODAL)})
+    l2g_nodes = np.array([0, 1] if rank == 0 else [1, 0])
+    fixed = np.where(l2g_nodes == 0)[0].astype(np.int32)  # constrain global node 0
+    lifter = Lifter(S.size, Fixed(fixed, 0.0))
+    layout_reduced, lifter_aug = lifter.adapt_layout(S.get_layout(), dist.group.WORLD)
+    plan = ExchangePlan(layout_reduced, comm=dist.group.WORLD)
+    assert plan.global_size == 1
+    np.testing.assert_array_equal(plan.layout.local_to_global, [0])
+    assert (plan.local_size, plan.rstart, plan.rend) == ((0, 0, 0) if rank == 0 else (1, 0, 1))
+    # unconstrained lifter: adapt_layout is the identity on the layout
+    S2 = _mock_state(rank, {"u": field(shape=(2, 2), field_type=FieldType.NODAL), "s": field(shape=(1,), field_type=FieldType.SHARED), "v": field(shape=(1,), field_type=FieldType.LOCAL)})
+    red, _ = Lifter(S2.size).adapt_layout(S2.get_layout(), dist.group.WORLD)
+    np.testing.assert_array_equal(red.local_to_global, [0, 1, 4, 5, 2, 3] if rank == 0 else [4, 5, 0, 1, 2, 6])
+    assert red.n_global == 7
+
+
+def _body_periodic_mpi(rank, world):
+    """reference tests/test_periodic_mpi.py:24-92: a ghost slave whose master lives on the other rank."""
+    import scipy.sparse as sps
+
+    from tatva_b200.compound import Compound, FieldType, field
+    from tatva_b200.lifter import Lifter, PeriodicMPI
+    from tatva_b200.mesh import Mesh, PartitionInfo
+
+    l2g = np.array([0, 1, 2] if rank == 0 else [1, 2, 0], dtype=np.int32)
+    info = PartitionInfo(nodes_local_to_global=l2g, n_owned_nodes=1 if rank == 0 else 2)
+    mesh = Mesh(coords=np.zeros((3, 1)), elements=np.zeros((0, 2), dtype=np.int32))
+
+    class MyState(Compound, mesh=mesh, partition_info=info, comm=dist.group.WORLD):
+        u = field(shape=(3, 1), field_type=FieldType.NODAL)
+
+    layout = MyState.get_layout()
+    cond = PeriodicMPI(np.array([1]), np.array([2]), layout, comm=dist.group.WORLD)  # global node 1 follows node 2
+    lifter = Lifter(MyState.size, cond)
+    layout_aug, lifter_aug = lifter.adapt_layout(layout, dist.group.WORLD)
+    assert layout_aug.n_global == 2  # nodes 0 and 2 remain
+    full = lifter_aug.lift_from_zeros(np.array([5.0, 7.0]))
+    g = {int(n): float(v) for n, v in zip(l2g, full)}
+    assert g[1] == g[2]
+    if rank == 0:
+        sp_ = sps.lil_matrix((3, 3), dtype=np.int8)
+        for i, j in ((0, 1), (1, 0), (0, 0), (1, 1)):
+            sp_[i, j] = 1
+        aug = lifter_aug.augment_sparsity(sp_.tocsr())
+        assert aug[0, 2] != 0 and aug[2, 0] != 0
+
+
 # ---- pytest entry points -----------------------------------------------------------------------------
 
 
 @pytest.mark.parametrize(
     "body",
-    ["_body_layout", "_body_communication", "_body_incomplete_nodal", "_body_hessian", "_body_allreduce", "_body_partitioned_residual"],
+    ["_body_layout", "_body_communication", "_body_incomplete_nodal", "_body_hessian", "_body_allreduce", "_body_partitioned_residual", "_body_lifter_adapt_layout", "_body_periodic_mpi"],
 )
 def test_two_rank_gloo(body):
     _run(body, world=2)
