@@ -1182,33 +1182,21 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
                       cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   int rc = TATVA_OK;
+  // measurement variants documented in DESIGN.md §3.1 (tatva_plan_set_variant); default = v3 pair kernel
   switch (p->variant) {
     case 2: k_hex8_nh_hvp<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 3: rc = launch_rolled<0, 2>(p, mu, lmbda, u, v, y, st); break;
-    case 4: rc = launch_rolled<1, 3>(p, mu, lmbda, u, v, y, st); break;
-    case 5: rc = launch_rolled<2, 4>(p, mu, lmbda, u, v, y, st); break;
-    case 6: rc = launch_rolled<1, 2>(p, mu, lmbda, u, v, y, st); break;
-    case 7: rc = launch_rolled<2, 3>(p, mu, lmbda, u, v, y, st); break;
     case 8: rc = launch_rolled<0, 2, 1>(p, mu, lmbda, u, v, y, st); break;
     case 9: rc = launch_rolled<0, 2, 2>(p, mu, lmbda, u, v, y, st); break;
-    case 10: rc = launch_rolled<2, 4, 1>(p, mu, lmbda, u, v, y, st); break;
-    case 11: rc = launch_rolled<2, 4, 2>(p, mu, lmbda, u, v, y, st); break;
-    case 12: rc = launch_rolled<1, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
-    case 13: rc = launch_rolled<0, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
-    case 14: rc = launch_rolled<2, 2, 0, 2>(p, mu, lmbda, u, v, y, st); break;
     case 15: rc = launch_rolled<0, 2, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 17: rc = launch_rolled<1, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
-    case 18: rc = launch_rolled<2, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
-    case 19: rc = launch_rolled<2, 4, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 22: k_hex8_nh_hvp_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 23: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;
-    case 24: k_hex8_nh_hvp_v3<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 27: rc = launch_v3<2, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 25: rc = launch_v3<2, 2>(p, mu, lmbda, u, v, y, st); break;
     case 26: rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st); break;
     case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 20: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
-    case 21: k_hex8_nh_hvp_v2<2, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     default: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;  // pair-sharing, X and v staged
   }
   if (rc != TATVA_OK) return rc;

@@ -7,7 +7,7 @@ from tatva_b200 import element, materials
 from bench import synthetic_inputs
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 3, 4, 5, 6, 7]
+variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 3, 15, 16, 17, 20, 22, 23, 25, 26, 27]
 c, el, u, v = synthetic_inputs(n)
 op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8())
 mat = materials.NeoHookean(500.0, 1000.0)
