@@ -197,7 +197,11 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"Hex8 {args.n}^3 neo-Hookean matrix-free HVP (sampled at {n_sample}^3 on CPU)", "mu": MU, "lambda": LMBDA},
+        "config": {
+            "workload": f"Hex8 {args.n}^3 per GPU, neo-Hookean (mu=500, lambda=1000) matrix-free HVP",
+            "sample": f"CPU port of the reference arithmetic on a {n_sample}^3 block of the same mesh family (bounded sample); "
+                      "the reference's JAX path cannot run: jax is not installable in this image",
+        },
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

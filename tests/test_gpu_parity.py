@@ -264,3 +264,45 @@ def test_tiled_tet4_kernels_match_oracle():
         elx = np.asarray(op.mesh.elements)
         _assert_close(op.hvp(mat)(u, v), orc.hvp("tet4", omat, c, elx, u, v))
         _assert_close(op.residual(mat)(u), orc.residual("tet4", omat, c, elx, u))
+
+
+def test_edge_cases_single_element_and_inverted_orientation():
+    """One-element meshes, and an inverted element: the reference takes det J without abs
+    (operator.py:172-192), so the weights (and integrals) are negative."""
+    from tatva_b200 import materials
+
+    X = orc.reference_nodes("tet4")
+    el = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    op = _make_op("tet4", X, el)
+    _assert_close(op.get_integration_weights(), np.array([[1.0 / 6.0]]), 1e-15)
+    inv = np.array([[0, 2, 1, 3]], dtype=np.int32)  # swapped nodes: negative orientation
+    op_inv = _make_op("tet4", X, inv)
+    _assert_close(op_inv.get_integration_weights(), orc.op_integration_weights("tet4", X, inv), 1e-15)
+    assert float(op_inv.integrate(np.ones(4))) < 0
+    rng = np.random.default_rng(0)
+    Xh = orc.reference_nodes("hex8") + 0.1 * rng.uniform(-1, 1, (8, 3))
+    elh = np.arange(8, dtype=np.int32)[None, :]
+    oph = _make_op("hex8", Xh, elh)
+    u, v = 0.05 * rng.normal(size=(8, 3)), rng.normal(size=(8, 3))
+    omat, mat = orc.NeoHookean(500.0, 1000.0), materials.NeoHookean(500.0, 1000.0)
+    _assert_close(oph.hvp(mat)(u, v), orc.hvp("hex8", omat, Xh, elh, u, v))
+    _assert_close(oph.residual(mat)(u), orc.residual("hex8", omat, Xh, elh, u))
+    _assert_close(oph.energy(mat)(u), orc.energy("hex8", omat, Xh, elh, u))
+
+
+def test_invalid_meshes_raise_like_the_reference():
+    """operator.py:132-170 (__check_init__)."""
+    import tatva_b200
+    from tatva_b200 import element
+
+    X = orc.reference_nodes("tri3")
+    with pytest.raises(ValueError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0, 1, 5]], dtype=np.int32)), element.Tri3())
+    with pytest.raises(ValueError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0, 1, -1]], dtype=np.int32)), element.Tri3())
+    with pytest.raises(TypeError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0.0, 1.0, 2.0]])), element.Tri3())
+    with pytest.raises(ValueError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.zeros((0, 3), dtype=np.int32)), element.Tri3())
+    with pytest.raises(NotImplementedError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0, 1, 2]], dtype=np.int32)), element.Tri3(quad_points=np.array([[0.2, 0.2]]), quad_weights=np.array([0.5])))
