@@ -63,6 +63,18 @@ def structured_hex_block(n, grid, rank, lengths=None, jitter=0.1, seed=0):
     return Mesh(coords=coords, elements=new_id[el]), PartitionInfo(nodes_local_to_global=g.astype(np.int64), n_owned_nodes=int((~ghost).sum()))
 
 
+def structured_tet_block(n, grid, rank, lengths=None, jitter=0.1, seed=0):
+    """Same block as `structured_hex_block`, each cell cut into the 6 tetrahedra of the reference's box helper
+    (tests/test_sparse_tracer.py:29-70).  Every cell corner belongs to one of its tets, so node ownership and
+    local numbering are those of the hex block."""
+    mesh, info = structured_hex_block(n, grid, rank, lengths=lengths, jitter=jitter, seed=seed)
+    h = np.asarray(mesh.elements)
+    n0, n1, n2, n3, n4, n5, n6, n7 = h[:, 0], h[:, 1], h[:, 3], h[:, 2], h[:, 4], h[:, 5], h[:, 7], h[:, 6]
+    corner_sets = [(n0, n1, n3, n7), (n0, n1, n7, n5), (n0, n5, n7, n4), (n0, n3, n2, n7), (n0, n2, n6, n7), (n0, n6, n4, n7)]
+    tets = np.stack([np.stack(t, -1) for t in corner_sets], axis=1).reshape(-1, 4)
+    return Mesh(coords=mesh.coords, elements=tets.astype(np.int32)), info
+
+
 def _hash_uniform(gid, seed):
     """Deterministic U(-1,1)^3 per global node id (same value on every rank that holds the node)."""
     x = gid.astype(np.uint64)[:, None] * np.uint64(3) + np.arange(3, dtype=np.uint64)[None, :] + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)

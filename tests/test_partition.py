@@ -68,3 +68,21 @@ def test_locality_reordering_is_a_consistent_permutation():
     r_new = orc.residual("tet4", mat, new.coords, new.elements, u[npm])
     np.testing.assert_allclose(r_new, r_bad[npm], rtol=1e-12, atol=1e-12)
     assert sorted(locality_order(c, el).tolist()) == list(range(el.shape[0]))
+
+
+def test_structured_tet_block_matches_extract_local_mesh():
+    from tatva_b200.distributed import structured_tet_block
+
+    n, grid = 2, (2, 2, 1)
+    shape = (grid[0] * n, grid[1] * n, grid[2] * n)
+    m = max(shape)
+    gm = Mesh.box_tet((shape[0] / m, shape[1] / m, shape[2] / m), shape)
+    part = np.repeat(block_partition(shape, 4), 6)
+    for r in range(4):
+        ref_mesh, ref_info = extract_local_mesh(gm, part, r)
+        mesh, info = structured_tet_block(n, grid, r, jitter=0.0)
+        np.testing.assert_array_equal(info.nodes_local_to_global, ref_info.nodes_local_to_global)
+        assert info.n_owned_nodes == ref_info.n_owned_nodes
+        np.testing.assert_array_equal(mesh.elements, ref_mesh.elements)
+        # box_tet is centred in x, y (tests/test_sparse_tracer.py:35-37); the block builder starts at the origin
+        np.testing.assert_allclose(mesh.coords, ref_mesh.coords + np.array([shape[0] / m / 2, shape[1] / m / 2, 0.0]), atol=1e-15)
