@@ -124,6 +124,12 @@ int tatva_residual(tatva_plan_t* plan, int material, const double* params, int n
 int tatva_hvp(tatva_plan_t* plan, int material, const double* params, int n_params,
               const double* d_u, const double* d_v, double* d_y, tatva_stream_t stream);
 
+/* Diagonal of the energy Hessian at u, diag[dpn*n + k] = d2E/du_{n,k}^2 (n_nodes * dofs_per_node): the Jacobi
+ * preconditioner of the CG around the HVP (the reference ships no solver and
+ * would obtain it as ColoredMatrix.diagonal() after sparse.jacfwd, tatva/sparse/base.py:37-105).           */
+int tatva_hessian_diag(tatva_plan_t* plan, int material, const double* params, int n_params,
+                       const double* d_u, double* d_diag, tatva_stream_t stream);
+
 /* Element sub-range variants: only elements [elem_begin, elem_begin + elem_count) contribute, and the
  * output is zeroed first only if zero_out != 0.  They let the caller run the elements that touch ghost
  * nodes and the interior elements on different streams, so the halo exchange of tatva/mpi.py:372-409,
@@ -199,7 +205,7 @@ int tatva_reduce_adjoint(const double* d_r_full, const int64_t* d_ptr, const int
 
 /* ---- device-resident CG around the matrix-free HVP (the reference has no solver:
  * its docstrings hand H v to an external one, tatva/mpi.py:594-595) ----------------------------------------
- * Scalars stay on the device: d_scalars[0] = r.r, [1] = p.Ap, [2] = next r.r (>= 4 doubles); d_partials holds
+ * Scalars stay on the device: d_scalars[0] = r.r, [1] = p.Ap, [2] = next r.r (>= 8 doubles, slot in 0..7); d_partials holds
  * 1184 per-CTA partial sums.  Dots are two-pass with a fixed summation order (deterministic).
  *   tatva_cg_dot(a, b, ..., slot):  d_scalars[slot] = a.b
  *   tatva_cg_after_matvec:  alpha = s0/(p.Ap); x += alpha p; r -= alpha Ap; beta = (r.r)/s0; p = r + beta p; s0 = r.r */
@@ -207,6 +213,17 @@ int tatva_cg_dot(const double* d_a, const double* d_b, int64_t n, double* d_part
                  double* d_scalars, int slot, tatva_stream_t stream);
 int tatva_cg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap, int64_t n,
                           double* d_partials, double* d_scalars, tatva_stream_t stream);
+/* Jacobi-preconditioned CG, M = diag(H) from tatva_hessian_diag; z = M^-1 r is folded into the vector kernels and
+ * never stored.  d_scalars[0] = r.z, [2] = next r.z, [4] = r.r of the new residual; d_partials >= 2 * 1184 doubles.
+ *   tatva_pcg_reciprocal:    minv = 1 / diag (1 where diag is not a positive finite number)
+ *   tatva_pcg_start:         p = minv * r ; s0 = r.p
+ *   tatva_pcg_after_matvec:  alpha = s0/(p.Ap); x += alpha p; r -= alpha Ap; beta = (r.z)/s0; p = z + beta p; s0 = r.z */
+int tatva_pcg_reciprocal(const double* d_diag, int64_t n, double* d_minv, tatva_stream_t stream);
+int tatva_pcg_start(double* d_p, const double* d_r, const double* d_minv, int64_t n,
+                    double* d_partials, double* d_scalars, tatva_stream_t stream);
+int tatva_pcg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap,
+                           const double* d_minv, int64_t n, double* d_partials, double* d_scalars,
+                           tatva_stream_t stream);
 
 /* ---- host-side setup (C++, no GPU needed) -----------------------------------------------
  * pattern_from_mesh / _create_sparse_structure (tatva/sparse/_extraction.py:37-102):

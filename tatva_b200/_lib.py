@@ -43,6 +43,7 @@ SIGNATURES = {
     "tatva_energy": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
     "tatva_residual": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
     "tatva_hvp": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp]),
+    "tatva_hessian_diag": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
     "tatva_hvp_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_residual_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_csr_assemble": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, vp]),
@@ -57,6 +58,9 @@ SIGNATURES = {
     "tatva_reduce_adjoint": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_cg_dot": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp]),
     "tatva_cg_after_matvec": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "tatva_pcg_reciprocal": (C.c_int, [vp, C.c_int64, vp, vp]),
+    "tatva_pcg_start": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "tatva_pcg_after_matvec": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "tatva_host_pattern_from_mesh": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, C.c_int, c_i32p, c_i32p, c_i64p]),
     "tatva_host_distance2_colors": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p]),
     "tatva_host_node_to_elements": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, c_i32p, c_i32p]),

@@ -513,6 +513,63 @@ __global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coo
   }
 }
 
+// ---- Hessian diagonal (Jacobi preconditioner) -------------------------------------------------------
+// diag[dpn*node_b + k] += sum_q W * (d2psi : unit_(b,k)) . unit_(b,k): the (b,k)/(b,k) entry of the element
+// stiffness, with the geometry and the material state of a point computed once for all npe*dpn unit directions.
+template <class El, class Mat>
+__global__ void __launch_bounds__(kBlock) k_hessian_diag(const double* __restrict__ coords,
+                                                         const int32_t* __restrict__ conn, int64_t E, Mat mat,
+                                                         const double* __restrict__ u, double* __restrict__ diag) {
+  constexpr int dpn = Mat::dpn;
+  extern __shared__ double sm_fused[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int nd[El::npe];
+  double Y[El::npe][dpn];
+#pragma unroll
+  for (int n = 0; n < El::npe; ++n) {
+    nd[n] = 0;
+#pragma unroll
+    for (int c = 0; c < dpn; ++c) Y[n][c] = 0.0;
+  }
+  if (e < E) {
+    load_conn<El>(conn, e, nd);
+    double X[El::npe][El::dim], U[El::npe][dpn];
+    gather_rows(coords, nd, X);
+    gather_rows(u, nd, U);
+#pragma unroll 1
+    for (int q = 0; q < El::nq; ++q) {
+      double dNdX[El::dim][El::npe], N[El::npe];
+      const double W = geometry<El>(q, X, dNdX) * El::weight(q);
+      El::N(q, N);
+      typename Mat::S s;
+      typename Mat::Cache cache;
+      qp_state<El, Mat>(dNdX, N, U, s);
+      mat.prepare(s, cache);
+#pragma unroll
+      for (int b = 0; b < El::npe; ++b) {
+#pragma unroll
+        for (int k = 0; k < dpn; ++k) {
+          typename Mat::S ds, f;
+#pragma unroll
+          for (int c = 0; c < dpn; ++c) {
+#pragma unroll
+            for (int j = 0; j < El::dim; ++j) ds.G[c][j] = (c == k) ? dNdX[j][b] : 0.0;
+            ds.val[c] = (c == k) ? N[b] : 0.0;
+          }
+          mat.second(s, cache, ds, f);
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < El::dim; ++j) t += f.G[k][j] * dNdX[j][b];
+          if (k >= Mat::val_lo) t += f.val[k] * N[b];
+          Y[b][k] += W * t;
+        }
+      }
+    }
+  }
+  double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * (32 * El::npe * dpn + 16 * El::npe);
+  grouped_scatter<El::npe, dpn>(diag, nd, Y, e < E, wsm);
+}
+
 // ---- CSR assembly -----------------------------------------------------------------------------
 // Column (b,k) of the element stiffness is the element-local HVP with the unit direction
 // "component k of node b"; rows (a,i) go to data[indptr[dpn*node_a + i] + pos[e,a,b] + k].
@@ -924,6 +981,55 @@ __global__ void __launch_bounds__(256) k_cg_direction(double* __restrict__ p, co
 }
 __global__ void k_cg_roll(double* __restrict__ s) { s[0] = s[2]; }
 
+// Jacobi-preconditioned variants: z = minv * r is never stored.  s[0] = r.z (current), s[2] = r.z (next), s[4] = r.r.
+__global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, double* __restrict__ r,
+                                                    const double* __restrict__ p, const double* __restrict__ Ap,
+                                                    const double* __restrict__ minv, int64_t n,
+                                                    const double* __restrict__ s, double* __restrict__ part) {
+  const double alpha = s[0] / s[1];
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, __ldg(p + i), x[i]);
+    const double ri = fma(-alpha, __ldg(Ap + i), r[i]);
+    r[i] = ri;
+    rr = fma(ri, ri, rr);
+    rz = fma(ri * __ldg(minv + i), ri, rz);
+  }
+  rz = block_sum(rz);
+  __syncthreads();
+  rr = block_sum(rr);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = rz;
+    part[gridDim.x + blockIdx.x] = rr;
+  }
+}
+__global__ void __launch_bounds__(256) k_pcg_direction(double* __restrict__ p, const double* __restrict__ r,
+                                                       const double* __restrict__ minv, int64_t n,
+                                                       const double* __restrict__ s) {
+  const double beta = s[2] / s[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], __ldg(r + i) * __ldg(minv + i));
+}
+// out[i] = 1 / d[i] (Jacobi), or 1 where d[i] is not a positive finite number
+__global__ void __launch_bounds__(256) k_safe_reciprocal(const double* __restrict__ d, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = d[i];
+    out[i] = (v > 0.0 && v < 1.79e308) ? 1.0 / v : 1.0;
+  }
+}
+// p = minv * r ; partial of r.(minv r)
+__global__ void __launch_bounds__(256) k_pcg_start(double* __restrict__ p, const double* __restrict__ r,
+                                                   const double* __restrict__ minv, int64_t n, double* __restrict__ part) {
+  double rz = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = __ldg(r + i), zi = ri * __ldg(minv + i);
+    p[i] = zi;
+    rz = fma(ri, zi, rz);
+  }
+  rz = block_sum(rz);
+  if (threadIdx.x == 0) part[blockIdx.x] = rz;
+}
+
 // ---- FP64 FMA peak microbenchmark ---------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
@@ -1296,6 +1402,52 @@ int tatva_hvp(tatva_plan_t* p, int material, const double* params, int n_params,
 
 }  // extern "C"
 
+// (element, law) pairs of the fused kernels, as a visitor: f(El{}, mat) for the pair named by the enums.
+template <class F>
+static int for_element_law(int el, int material, const double* prm, int n_params, F&& f) {
+  if (material == TATVA_LINEAR_ELASTIC) {
+    if (n_params != 2) return TATVA_E_INVALID;
+    if (el == TATVA_TRI3) return f(Tri3{}, LinearElastic<2>{prm[0], prm[1]});
+    if (el == TATVA_QUAD4) return f(Quad4{}, LinearElastic<2>{prm[0], prm[1]});
+    if (el == TATVA_TRI6) return f(Tri6{}, LinearElastic<2>{prm[0], prm[1]});
+    if (el == TATVA_QUAD8) return f(Quad8{}, LinearElastic<2>{prm[0], prm[1]});
+    if (el == TATVA_TET4) return f(Tet4{}, LinearElastic<3>{prm[0], prm[1]});
+    if (el == TATVA_HEX8) return f(Hex8{}, LinearElastic<3>{prm[0], prm[1]});
+  } else if (material == TATVA_NEO_HOOKEAN) {
+    if (n_params != 2) return TATVA_E_INVALID;
+    if (el == TATVA_TET4) return f(Tet4{}, NeoHookean{prm[0], prm[1]});
+    if (el == TATVA_HEX8) return f(Hex8{}, NeoHookean{prm[0], prm[1]});
+  } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD) {
+    if (n_params != 5) return TATVA_E_INVALID;
+    const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+    if (el == TATVA_TET4) return f(Tet4{}, m);
+    if (el == TATVA_HEX8) return f(Hex8{}, m);
+  } else {
+    return TATVA_E_INVALID;
+  }
+  return TATVA_E_UNSUPPORTED;
+}
+
+extern "C" {
+
+// Diagonal of the energy Hessian at u (length n_nodes * dofs_per_node), for Jacobi preconditioning.
+int tatva_hessian_diag(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,
+                       double* d_diag, tatva_stream_t stream) {
+  if (!p || !params || !d_u || !d_diag) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_element_law(p->element, material, params, n_params, [&](auto el, auto mat) -> int {
+    using El = decltype(el);
+    using Mat = decltype(mat);
+    if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
+    constexpr size_t smem = grouped_scatter_smem<El::npe, Mat::dpn>(kBlock / 32);
+    k_hessian_diag<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, d_u, d_diag);
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  });
+}
+
+}  // extern "C"
+
 extern "C" {
 // Element sub-range variants (overlap of halo exchange with interior elements): elements
 // [elem_begin, elem_begin + elem_count) only; y is zeroed first iff zero_y != 0.
@@ -1505,11 +1657,11 @@ int tatva_reduce_adjoint(const double* d_r_full, const int64_t* d_ptr, const int
 // One CG iteration's vector work, in two calls around the operator application Ap = A p:
 //   tatva_cg_after_matvec: s[1] = p.Ap ; alpha = s[0]/s[1] ; x += alpha p ; r -= alpha Ap ; s[2] = r.r ;
 //                          beta = s[2]/s[0] ; p = r + beta p ; s[0] = s[2]
-// `d_scalars` (>= 4 doubles) and `d_partials` (>= 1184 doubles) are caller-owned device buffers; s[0] must
+// `d_scalars` (>= 8 doubles) and `d_partials` (>= 1184 doubles) are caller-owned device buffers; s[0] must
 // hold r.r on entry (tatva_cg_dot(r, r, ..., slot 0)).  Everything is stream-ordered: no host round trip.
 int tatva_cg_dot(const double* d_a, const double* d_b, int64_t n, double* d_partials, double* d_scalars, int slot,
                  tatva_stream_t stream) {
-  if (!d_a || !d_b || !d_partials || !d_scalars || n <= 0 || slot < 0 || slot > 3) return TATVA_E_INVALID;
+  if (!d_a || !d_b || !d_partials || !d_scalars || n <= 0 || slot < 0 || slot > 7) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   k_cg_dot<<<kCgBlocks, 256, 0, st>>>(d_a, d_b, n, d_partials);
   k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, slot);
@@ -1525,6 +1677,39 @@ int tatva_cg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d
   k_cg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, n, d_scalars, d_partials);
   k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 2);
   k_cg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, n, d_scalars);
+  k_cg_roll<<<1, 1, 0, st>>>(d_scalars);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// Jacobi-preconditioned CG (M = diag(A), `d_minv` = 1/diag).  tatva_pcg_start: p = M^-1 r, s[0] = r.M^-1 r.
+// tatva_pcg_after_matvec: as tatva_cg_after_matvec with z = M^-1 r folded in (z is never stored); leaves
+// s[0] = r.z and s[4] = r.r of the new residual.  `d_scalars` >= 8 doubles, `d_partials` >= 2 * 1184 doubles.
+int tatva_pcg_reciprocal(const double* d_diag, int64_t n, double* d_minv, tatva_stream_t stream) {
+  if (!d_diag || !d_minv || n <= 0) return TATVA_E_INVALID;
+  k_safe_reciprocal<<<kCgBlocks, 256, 0, (cudaStream_t)stream>>>(d_diag, n, d_minv);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_pcg_start(double* d_p, const double* d_r, const double* d_minv, int64_t n, double* d_partials,
+                    double* d_scalars, tatva_stream_t stream) {
+  if (!d_p || !d_r || !d_minv || !d_partials || !d_scalars || n <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_pcg_start<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, d_minv, n, d_partials);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 0);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_pcg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap, const double* d_minv, int64_t n,
+                           double* d_partials, double* d_scalars, tatva_stream_t stream) {
+  if (!d_x || !d_r || !d_p || !d_Ap || !d_minv || !d_partials || !d_scalars || n <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_cg_dot<<<kCgBlocks, 256, 0, st>>>(d_p, d_Ap, n, d_partials);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 1);
+  k_pcg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, d_minv, n, d_scalars, d_partials);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 2);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials + kCgBlocks, kCgBlocks, d_scalars, 4);
+  k_pcg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, d_minv, n, d_scalars);
   k_cg_roll<<<1, 1, 0, st>>>(d_scalars);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;

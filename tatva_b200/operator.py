@@ -287,6 +287,16 @@ class Operator:
 
         return _hvp
 
+    def hessian_diagonal(self, material, u, out=None) -> torch.Tensor:
+        """diag(d2E/du2) at u, same shape as u: what `ColoredMatrix.diagonal()` would return after `sparse.jacfwd`
+        (tatva/sparse/base.py:37-105), computed element-wise without the matrix (Jacobi preconditioner)."""
+        prm, n = _lib.params_array(material.params())
+        uc = self._as_dev(u).contiguous()
+        if out is None:
+            out = torch.empty_like(uc)
+        self._call("tatva_hessian_diag", material.material_id, prm, n, uc.data_ptr(), out.data_ptr())
+        return out
+
     def _raw_energy(self, material, u):
         prm, n = _lib.params_array(material.params())
         out = torch.empty((), dtype=torch.float64, device=self.device)

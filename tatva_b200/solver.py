@@ -21,14 +21,25 @@ class ConjugateGradient:
     """Solve A x = b for a symmetric positive definite operator given as `matvec(p, out)` (writes A p into `out`
     in place, on torch's current stream, without allocating)."""
 
-    def __init__(self, matvec: Callable, n: int, device, use_graph: bool = True):
+    def __init__(self, matvec: Callable, n: int, device, use_graph: bool = True, jacobi: bool = False):
         self.matvec, self.n, self.device = matvec, int(n), torch.device(device)
         mk = lambda m: torch.zeros(m, dtype=torch.float64, device=self.device)  # noqa: E731
         self.x, self.r, self.p, self.Ap = mk(n), mk(n), mk(n), mk(n)
-        self.scalars, self.partials = mk(4), mk(1184)
+        self.scalars, self.partials = mk(8), mk(2 * 1184)
+        # Jacobi preconditioner: 1 / diag(A), refreshed in place by `set_diagonal` (so a captured graph stays valid)
+        self.minv = torch.ones(n, dtype=torch.float64, device=self.device) if jacobi else None
         self.use_graph = use_graph
         self._graph = None
         self._L = _lib.lib()
+
+    def set_diagonal(self, diag: torch.Tensor) -> None:
+        """minv <- 1 / diag (entries that are not positive and finite fall back to 1)."""
+        if self.minv is None:
+            raise ValueError("ConjugateGradient was built without jacobi=True")
+        d = diag.reshape(-1)
+        if d.numel() != self.n or not d.is_contiguous():
+            raise ValueError("diagonal must be a contiguous vector of the operator's size")
+        _lib.check(self._L.tatva_pcg_reciprocal(d.data_ptr(), self.n, self.minv.data_ptr(), self._stream()), "tatva_pcg_reciprocal")
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -38,6 +49,12 @@ class ConjugateGradient:
 
     def _iteration(self):
         self.matvec(self.p, self.Ap)
+        if self.minv is not None:
+            _lib.check(
+                self._L.tatva_pcg_after_matvec(self.x.data_ptr(), self.r.data_ptr(), self.p.data_ptr(), self.Ap.data_ptr(), self.minv.data_ptr(), self.n, self.partials.data_ptr(), self.scalars.data_ptr(), self._stream()),
+                "tatva_pcg_after_matvec",
+            )
+            return
         _lib.check(
             self._L.tatva_cg_after_matvec(self.x.data_ptr(), self.r.data_ptr(), self.p.data_ptr(), self.Ap.data_ptr(), self.n, self.partials.data_ptr(), self.scalars.data_ptr(), self._stream()),
             "tatva_cg_after_matvec",
@@ -69,10 +86,16 @@ class ConjugateGradient:
                 self.x.copy_(x0)
                 self.matvec(self.x, self.Ap)
                 torch.sub(b, self.Ap, out=self.r)
-            self.p.copy_(self.r)
-            self._dot(self.r, self.r, 0)
             self._dot(b, b, 3)
-            rr0, bb = (float(v) for v in self.scalars[[0, 3]].tolist())
+            if self.minv is not None:
+                self._dot(self.r, self.r, 4)
+                _lib.check(self._L.tatva_pcg_start(self.p.data_ptr(), self.r.data_ptr(), self.minv.data_ptr(), self.n, self.partials.data_ptr(), self.scalars.data_ptr(), self._stream()), "tatva_pcg_start")
+                rr_slot = 4
+            else:
+                self.p.copy_(self.r)
+                self._dot(self.r, self.r, 0)
+                rr_slot = 0
+            rr0, bb = (float(v) for v in self.scalars[[rr_slot, 3]].tolist())
             if bb == 0.0 or math.sqrt(rr0) <= tol * math.sqrt(bb):
                 return self.x.clone(), dict(iterations=0, residual_norm=math.sqrt(rr0), converged=True)
             if self.use_graph and self._graph is None:
@@ -88,7 +111,7 @@ class ConjugateGradient:
                     else:
                         self._iteration()
                     it += 1
-                rr = float(self.scalars[0])
+                rr = float(self.scalars[rr_slot])
                 if not math.isfinite(rr) or math.sqrt(rr) <= tol * math.sqrt(bb):
                     break
             return self.x.clone(), dict(iterations=it, residual_norm=math.sqrt(max(rr, 0.0)), converged=math.isfinite(rr) and math.sqrt(rr) <= tol * math.sqrt(bb))
@@ -117,21 +140,29 @@ class ReducedOperator:
     def energy(self) -> float:
         return float(self.op._raw_energy(self.material, self.u_full))
 
+    def diagonal(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Jacobi diagonal of the reduced tangent: reduce_adjoint(diag H(u)).  Exact for Fixed constraints; for Periodic
+        pairs it omits the coupling between a node and its image (zero unless they share an element), which a
+        preconditioner does not need."""
+        d_full = self.op.hessian_diagonal(self.material, self.u_full)
+        return self.lifter.reduce_adjoint(d_full, out=out)
+
     def matvec(self, v_reduced: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         self.hom.lift_from_zeros(v_reduced, out=self.v_full)
         self.op._raw_hvp(self.material, self.u_full, self.v_full, out=self.y_full)
         return self.lifter.reduce_adjoint(self.y_full, out=out)
 
 
-def newton_solve(op, material, lifter, u0_reduced=None, *, tol: float = 1e-8, max_newton: int = 20, cg_tol: float = 1e-10, cg_maxiter: int = 2000, use_graph: bool = True):
+def newton_solve(op, material, lifter, u0_reduced=None, *, tol: float = 1e-8, max_newton: int = 20, cg_tol: float = 1e-10, cg_maxiter: int = 2000, use_graph: bool = True, jacobi: bool = False):
     """Minimise E(lift(u_red)) by Newton's method; every linear solve is a matrix-free CG on the HVP kernel.
     Returns (u_reduced, history) with history = list of dict(newton, residual_norm, cg_iterations)."""
     dev = op.device
     red = ReducedOperator(op, material, lifter)
     n = lifter.size_reduced
     u = torch.zeros(n, dtype=torch.float64, device=dev) if u0_reduced is None else torch.as_tensor(u0_reduced, dtype=torch.float64, device=dev).clone()
-    cg = ConjugateGradient(red.matvec, n, dev, use_graph=use_graph)
+    cg = ConjugateGradient(red.matvec, n, dev, use_graph=use_graph, jacobi=jacobi)
     r = torch.empty(n, dtype=torch.float64, device=dev)
+    diag = torch.empty(n, dtype=torch.float64, device=dev) if jacobi else None
     history = []
     r0 = None
     for k in range(max_newton):
@@ -142,6 +173,8 @@ def newton_solve(op, material, lifter, u0_reduced=None, *, tol: float = 1e-8, ma
         if rn <= tol * max(r0, 1e-300) or rn == 0.0:
             history.append(dict(newton=k, residual_norm=rn, cg_iterations=0))
             break
+        if jacobi:
+            cg.set_diagonal(red.diagonal(out=diag))
         du, info = cg.solve(-r, tol=cg_tol, maxiter=cg_maxiter)
         history.append(dict(newton=k, residual_norm=rn, cg_iterations=info["iterations"], cg_converged=info["converged"]))
         u = u + du

@@ -54,6 +54,60 @@ def test_cg_solves_the_reduced_tangent_system(use_graph):
     assert info2["converged"] and np.linalg.norm(x2.cpu().numpy() - 2 * x_ref) / np.linalg.norm(x_ref) < 1e-8
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_jacobi_pcg_matches_the_direct_solve_and_needs_fewer_iterations(use_graph):
+    from tatva_b200.solver import ConjugateGradient, ReducedOperator
+
+    c, el, lifter, op, mat, omat = _problem()
+    # a stretched mesh makes the diagonal vary, so Jacobi has something to do
+    rng = np.random.default_rng(2)
+    u_red = 0.005 * rng.normal(size=lifter.size_reduced)
+    b = rng.normal(size=lifter.size_reduced)
+    red = ReducedOperator(op, mat, lifter)
+    red.set_state(torch.as_tensor(u_red, device="cuda"))
+    K = _oracle_K(c, el, omat, lifter.lift_from_zeros(u_red), lifter)
+    diag = red.diagonal()
+    np.testing.assert_allclose(diag.cpu().numpy(), K.diagonal(), rtol=1e-12)
+    pcg = ConjugateGradient(red.matvec, lifter.size_reduced, "cuda", use_graph=use_graph, jacobi=True)
+    pcg.set_diagonal(diag)
+    x, info = pcg.solve(torch.as_tensor(b, device="cuda"), tol=1e-12, maxiter=2000, check_every=5)
+    assert info["converged"], info
+    x_ref = spla.spsolve(K.tocsc(), b)
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) / np.linalg.norm(x_ref) < 1e-9
+    # same iterates as SciPy-free textbook PCG on the oracle matrix (iteration count within the check granularity)
+    M = 1.0 / K.diagonal()
+    xr, r = np.zeros_like(b), b.copy()
+    z = M * r
+    p, rz, it = z.copy(), r @ z, 0
+    while np.linalg.norm(r) > 1e-12 * np.linalg.norm(b) and it < 2000:
+        Ap = K @ p
+        a = rz / (p @ Ap)
+        xr += a * p
+        r -= a * Ap
+        z = M * r
+        rz, rz_old = r @ z, rz
+        p = z + (rz / rz_old) * p
+        it += 1
+    assert abs(info["iterations"] - it) <= 5 + 0.1 * it, (info, it)
+    # identity diagonal == plain CG
+    pcg.set_diagonal(torch.ones_like(diag))
+    x1, info1 = pcg.solve(torch.as_tensor(b, device="cuda"), tol=1e-12, maxiter=2000, check_every=5)
+    cg = ConjugateGradient(red.matvec, lifter.size_reduced, "cuda", use_graph=False)
+    x0, info0 = cg.solve(torch.as_tensor(b, device="cuda"), tol=1e-12, maxiter=2000, check_every=5)
+    assert info1["iterations"] == info0["iterations"]
+    assert np.linalg.norm((x1 - x0).cpu().numpy()) / np.linalg.norm(x_ref) < 1e-9
+
+
+def test_newton_with_jacobi_reaches_the_same_minimiser():
+    from tatva_b200.solver import newton_solve
+
+    c, el, lifter, op, mat, omat = _problem(4)
+    u1, h1 = newton_solve(op, mat, lifter, tol=1e-10, cg_tol=1e-12)
+    u2, h2 = newton_solve(op, mat, lifter, tol=1e-10, cg_tol=1e-12, jacobi=True)
+    assert h2[-1]["residual_norm"] <= 1e-10 * h2[0]["residual_norm"] or h2[-1]["residual_norm"] < 1e-9
+    assert float((u1 - u2).norm() / u1.norm()) < 1e-8
+
+
 def test_newton_step_converges_to_the_oracle_minimiser():
     from tatva_b200.solver import newton_solve
 

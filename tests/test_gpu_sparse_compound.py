@@ -94,6 +94,37 @@ def test_direct_assembly_matches_coloured_oracle(kind, n):
     assert abs(K - K.T).max() < 1e-10 * abs(K).max()
 
 
+@pytest.mark.parametrize("kind,law", [("tri3", "le"), ("tet4", "nh"), ("hex8", "nh"), ("hex8", "le"), ("tet4", "pf"), ("hex8", "pf")])
+def test_hessian_diagonal_matches_the_oracle_matrix(kind, law):
+    """`Operator.hessian_diagonal` (Jacobi preconditioner) == diagonal of the oracle's element-stiffness assembly; for
+    the two-field law, e_i . H e_i by the oracle HVP on a sample of unit vectors."""
+    from tatva_b200 import materials
+
+    rng = np.random.default_rng(3)
+    n = {"tri3": 10, "tet4": 4, "hex8": 3}[kind]
+    c, el = {"tri3": lambda: orc.mesh_unit_square_tri(n, n), "tet4": lambda: orc.mesh_box_tet((1, 1, 1), (n, n, n)), "hex8": lambda: orc.mesh_box_hex(n)}[kind]()
+    c = c + 0.1 / n * rng.uniform(-1, 1, c.shape)
+    mesh, op = _setup(kind, c, el)
+    dim = c.shape[1]
+    if law == "pf":
+        prm = (500.0, 1000.0, 2.7, 0.1, 1e-6)
+        mat, omat = materials.NeoHookeanPhaseField(*prm), orc.NeoHookeanPhaseField(*prm)
+        s = np.concatenate([0.02 * rng.normal(size=(len(c), 3)), rng.uniform(0, 0.8, size=(len(c), 1))], axis=1)
+        d = op.hessian_diagonal(mat, torch.as_tensor(s, device="cuda")).cpu().numpy().ravel()
+        idx = rng.choice(s.size, 40, replace=False)
+        ref = np.array([orc.hvp_pf(kind, omat, c, el, s, np.eye(1, s.size, i).reshape(s.shape)).ravel()[i] for i in idx])
+        assert _rel(d[idx], ref) < 1e-12
+        return
+    mat, omat = (materials.LinearElastic(0.38, 0.58), orc.LinearElastic(0.38, 0.58)) if law == "le" else (materials.NeoHookean(500.0, 1000.0), orc.NeoHookean(500.0, 1000.0))
+    u = 0.02 * rng.normal(size=c.shape)
+    ip, ix = orc.pattern_from_mesh(el, len(c), dim)
+    data = orc.assemble_csr_data(kind, omat, c, el, u, ip, ix)
+    ref = sps.csr_matrix((data, ix, ip), shape=(c.size, c.size)).diagonal()
+    d = op.hessian_diagonal(mat, torch.as_tensor(u, device="cuda"))
+    assert d.shape == u.shape
+    assert _rel(d.reshape(-1), ref) < 1e-12
+
+
 @pytest.mark.parametrize("kind,n", [("tet4", 4), ("hex8", 3)])
 def test_phase_field_two_field_kernels(kind, n):
     """Config 5: compound (u, phi) state, node-interleaved [ux,uy,uz,phi]."""
