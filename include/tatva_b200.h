@@ -130,6 +130,16 @@ int tatva_hvp(tatva_plan_t* plan, int material, const double* params, int n_para
 int tatva_hessian_diag(tatva_plan_t* plan, int material, const double* params, int n_params,
                        const double* d_u, double* d_diag, tatva_stream_t stream);
 
+/* HVP with the Lifter folded into the kernel's gather / scatter (SURVEY.md section 8(f) row 1;
+ * tatva/lifter/base.py:201-251, constraints.py:214-221, :312-318):
+ *     y_red = reduce_adjoint( H(u_full) . lift_0(v_red) )
+ * `d_u_full` is the lifted state (n_nodes * dpn), `d_v_red` / `d_y_red` live on the n_red free DOFs, and
+ * `d_dof_map[i]` (n_nodes * dpn, int32) is the reduced DOF that drives full DOF i (its own for a free DOF, the
+ * master's for a Periodic image), or -1 for a Fixed DOF (tangent value 0, contribution dropped).          */
+int tatva_hvp_lifted(tatva_plan_t* plan, int material, const double* params, int n_params,
+                     const double* d_u_full, const double* d_v_red, const int32_t* d_dof_map,
+                     int64_t n_red, double* d_y_red, tatva_stream_t stream);
+
 /* Element sub-range variants: only elements [elem_begin, elem_begin + elem_count) contribute, and the
  * output is zeroed first only if zero_out != 0.  They let the caller run the elements that touch ghost
  * nodes and the interior elements on different streams, so the halo exchange of tatva/mpi.py:372-409,

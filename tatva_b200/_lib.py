@@ -44,6 +44,7 @@ SIGNATURES = {
     "tatva_residual": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
     "tatva_hvp": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp]),
     "tatva_hessian_diag": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp]),
+    "tatva_hvp_lifted": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_hvp_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_residual_elems": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int, vp]),
     "tatva_csr_assemble": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, vp]),

@@ -513,6 +513,60 @@ __global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coo
   }
 }
 
+// HVP with the Lifter folded in: v and y are REDUCED vectors, `map` (n_nodes*dpn int32) sends a full DOF to its
+// reduced index or to -1 (no driver: the homogeneous lift is 0 there and the contribution is dropped).
+template <class El, class Mat>
+__global__ void __launch_bounds__(kBlock) k_hvp_lifted(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                       int64_t E, Mat mat, const double* __restrict__ u,
+                                                       const double* __restrict__ v, const int32_t* __restrict__ map,
+                                                       double* __restrict__ y) {
+  constexpr int dpn = Mat::dpn;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn], Y[El::npe][dpn];
+  gather_rows(coords, nd, X);
+  gather_rows(u, nd, U);
+#pragma unroll
+  for (int n = 0; n < El::npe; ++n)
+#pragma unroll
+    for (int c = 0; c < dpn; ++c) {
+      const int32_t m = __ldg(map + (int64_t)nd[n] * dpn + c);
+      V[n][c] = m >= 0 ? __ldg(v + m) : 0.0;
+      Y[n][c] = 0.0;
+    }
+#pragma unroll 1
+  for (int q = 0; q < El::nq; ++q) {
+    double dNdX[El::dim][El::npe], N[El::npe];
+    const double W = geometry<El>(q, X, dNdX) * El::weight(q);
+    El::N(q, N);
+    typename Mat::S s, ds, f;
+    typename Mat::Cache cache;
+    qp_state<El, Mat>(dNdX, N, U, s);
+    mat.prepare(s, cache);
+    qp_state<El, Mat>(dNdX, N, V, ds);
+    mat.second(s, cache, ds, f);
+#pragma unroll
+    for (int n = 0; n < El::npe; ++n)
+#pragma unroll
+      for (int c = 0; c < dpn; ++c) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < El::dim; ++j) t += f.G[c][j] * dNdX[j][n];
+        if (c >= Mat::val_lo) t += f.val[c] * N[n];
+        Y[n][c] += W * t;
+      }
+  }
+#pragma unroll
+  for (int n = 0; n < El::npe; ++n)
+#pragma unroll
+    for (int c = 0; c < dpn; ++c) {
+      const int32_t m = __ldg(map + (int64_t)nd[n] * dpn + c);
+      if (m >= 0) atomicAdd(y + m, Y[n][c]);
+    }
+}
+
 // ---- Hessian diagonal (Jacobi preconditioner) -------------------------------------------------------
 // diag[dpn*node_b + k] += sum_q W * (d2psi : unit_(b,k)) . unit_(b,k): the (b,k)/(b,k) entry of the element
 // stiffness, with the geometry and the material state of a point computed once for all npe*dpn unit directions.
@@ -1441,6 +1495,24 @@ int tatva_hessian_diag(tatva_plan_t* p, int material, const double* params, int 
     if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
     constexpr size_t smem = grouped_scatter_smem<El::npe, Mat::dpn>(kBlock / 32);
     k_hessian_diag<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, d_u, d_diag);
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  });
+}
+
+// HVP on the free DOFs of a Lifter in ONE kernel: y_red = reduce_adjoint(H(u_full) lift_0(v_red)).
+int tatva_hvp_lifted(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u_full,
+                     const double* d_v_red, const int32_t* d_dof_map, int64_t n_red, double* d_y_red,
+                     tatva_stream_t stream) {
+  if (!p || !params || !d_u_full || !d_v_red || !d_dof_map || !d_y_red || n_red <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(d_y_red, 0, sizeof(double) * n_red, st));
+  if (p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC)
+    return hex8_nh_hvp_modal_lifted(p, params[0], params[1], d_u_full, d_v_red, d_dof_map, d_y_red, st);
+  return for_element_law(p->element, material, params, n_params, [&](auto el, auto mat) -> int {
+    using El = decltype(el);
+    using Mat = decltype(mat);
+    k_hvp_lifted<El, Mat><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, d_u_full, d_v_red, d_dof_map, d_y_red);
     TATVA_LAUNCH_CHECK();
     return TATVA_OK;
   });

@@ -693,11 +693,14 @@ TATVA_D void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const
                 fma(Gv[i][0], M[0][d], fma(Gv[i][1], M[1][d], Gv[i][2] * M[2][d])))));
 }
 
-template <int MINB, int STAGE, int GROUPED = 0>
+// LIFT: v and y are REDUCED vectors and `map` (n_nodes*3 int32) sends a full DOF to its reduced index, or -1 for a
+// DOF without a driver (Fixed): the homogeneous lift and reduce_adjoint of the Lifter folded into the gather / scatter.
+template <int MINB, int STAGE, int GROUPED = 0, bool LIFT = false>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                      double lmbda, const double* __restrict__ u, const double* __restrict__ v,
-                     double* __restrict__ y) {
+                     double* __restrict__ y, const int32_t* __restrict__ map = nullptr) {
+  static_assert(!(LIFT && GROUPED), "the lifted scatter is per DOF");
   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = e0 < E;
   if (!GROUPED && !valid) return;
@@ -721,7 +724,12 @@ __global__ void __launch_bounds__(kBlock, MINB)
     for (int n = 0; n < 8; ++n) {
       fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
       fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
-      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+      if constexpr (LIFT) {
+        const int32_t m = __ldg(map + (int64_t)nd[n] * 3 + c);
+        fv[n] = m >= 0 ? __ldg(v + m) : 0.0;
+      } else {
+        fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+      }
     }
     to_modal_raw(fX, tX);
     to_modal_raw(fu, tx_);
@@ -836,7 +844,14 @@ __global__ void __launch_bounds__(kBlock, MINB)
       double f[8];
       from_modal_raw(R[i], f);
 #pragma unroll
-      for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+      for (int n = 0; n < 8; ++n) {
+        if constexpr (LIFT) {
+          const int32_t m = __ldg(map + (int64_t)nd[n] * 3 + i);
+          if (m >= 0) atomicAdd(y + m, f[n]);
+        } else {
+          atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+        }
+      }
     }
   }
 }
@@ -1200,6 +1215,19 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     default: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;  // pair-sharing, X and v staged
   }
   if (rc != TATVA_OK) return rc;
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v_red,
+                             const int32_t* map, double* y_red, cudaStream_t st) {
+  constexpr size_t smem = (size_t)42 * kBlock * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_v3<2, 1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_hex8_nh_hvp_v3<2, 1, 0, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v_red, y_red, map);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

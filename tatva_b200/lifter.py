@@ -258,6 +258,20 @@ class Lifter:
             self._dev[device] = (t(src), t(consts if consts.size else np.zeros(1)), t(ptr), t(lst), t(self.free_dofs.astype(np.int64)))
         return self._dev[device]
 
+    def dof_map(self, device=None):
+        """int32 table full DOF -> reduced DOF that drives it (-1: Fixed / untouched base entry): the homogeneous
+        lift and its transpose as one index table, consumed by `tatva_hvp_lifted` inside the HVP kernel."""
+        src = self._compose()[0]
+        if self.size_reduced > np.iinfo(np.int32).max:
+            raise LifterError("dof_map needs int32 reduced indices")
+        m = np.where(src >= 0, src, -1).astype(np.int32)
+        if device is None:
+            return m
+        key = ("dof_map", torch.device(device))
+        if key not in self._dev:
+            self._dev[key] = torch.as_tensor(m, device=device)
+        return self._dev[key]
+
     @staticmethod
     def _stream():
         return torch.cuda.current_stream().cuda_stream

@@ -287,6 +287,13 @@ class Operator:
 
         return _hvp
 
+    def _raw_hvp_lifted(self, material, u_full, v_red, dof_map, out):
+        """out = reduce_adjoint(H(u_full) lift_0(v_red)) in one kernel (`tatva_hvp_lifted`); all arguments are
+        contiguous CUDA tensors, `dof_map` = Lifter.dof_map(device)."""
+        prm, n = _lib.params_array(material.params())
+        self._call("tatva_hvp_lifted", material.material_id, prm, n, u_full.data_ptr(), v_red.data_ptr(), dof_map.data_ptr(), out.numel(), out.data_ptr())
+        return out
+
     def hessian_diagonal(self, material, u, out=None) -> torch.Tensor:
         """diag(d2E/du2) at u, same shape as u: what `ColoredMatrix.diagonal()` would return after `sparse.jacfwd`
         (tatva/sparse/base.py:37-105), computed element-wise without the matrix (Jacobi preconditioner)."""

@@ -122,9 +122,12 @@ class ReducedOperator:
         r_red(u_red) = reduce_adjoint(dE/du(lift(u_red))),    K_red v = reduce_adjoint(H(lift(u_red)) lift_0(v)),
     with work vectors preallocated so that `matvec` can sit inside a CUDA graph."""
 
-    def __init__(self, op, material, lifter):
+    def __init__(self, op, material, lifter, fused: bool = True):
         self.op, self.material, self.lifter = op, material, lifter
         self.hom = lifter.homogeneous()
+        # fused: lift_0 and reduce_adjoint happen inside the HVP kernel's gather / scatter (one launch per matvec)
+        n_nodes, dim = op.mesh.coords.shape
+        self.dof_map = lifter.dof_map(op.device) if fused and lifter.size == n_nodes * material.dofs_per_node(dim) else None
         dev = op.device
         self.u_full = torch.zeros(lifter.size, dtype=torch.float64, device=dev)
         self.v_full = torch.zeros(lifter.size, dtype=torch.float64, device=dev)
@@ -148,6 +151,8 @@ class ReducedOperator:
         return self.lifter.reduce_adjoint(d_full, out=out)
 
     def matvec(self, v_reduced: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        if self.dof_map is not None:
+            return self.op._raw_hvp_lifted(self.material, self.u_full, v_reduced.contiguous(), self.dof_map, out)
         self.hom.lift_from_zeros(v_reduced, out=self.v_full)
         self.op._raw_hvp(self.material, self.u_full, self.v_full, out=self.y_full)
         return self.lifter.reduce_adjoint(self.y_full, out=out)

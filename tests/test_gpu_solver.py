@@ -98,6 +98,70 @@ def test_jacobi_pcg_matches_the_direct_solve_and_needs_fewer_iterations(use_grap
     assert np.linalg.norm((x1 - x0).cpu().numpy()) / np.linalg.norm(x_ref) < 1e-9
 
 
+@pytest.mark.parametrize("case", ["hex8_nh", "hex8_nh_generic", "tet4_pf", "tri3_le"])
+def test_lifter_fused_into_the_hvp_kernel_matches_lift_hvp_reduce(case):
+    """`tatva_hvp_lifted`: Fixed + Periodic folded into the gather / scatter == lift_0 -> HVP -> reduce_adjoint
+    (reference tatva/lifter/base.py:201-251), and == the oracle HVP pushed through the NumPy lifter."""
+    import tatva_b200
+    from tatva_b200 import element, materials
+    from tatva_b200.lifter import Fixed, Lifter, Periodic
+    from tatva_b200.solver import ReducedOperator
+
+    rng = np.random.default_rng(5)
+    if case.startswith("hex8"):
+        c, el = orc.mesh_box_hex(4)
+        cls, kind, dpn = element.Hexahedron8, "hex8", 3
+        mat, omat = materials.NeoHookean(500.0, 1000.0), orc.NeoHookean(500.0, 1000.0)
+    elif case == "tet4_pf":
+        c, el = orc.mesh_box_tet((1, 1, 1), (4, 4, 4))
+        cls, kind, dpn = element.Tetrahedron4, "tet4", 4
+        prm = (500.0, 1000.0, 2.7, 0.1, 1e-6)
+        mat, omat = materials.NeoHookeanPhaseField(*prm), orc.NeoHookeanPhaseField(*prm)
+    else:
+        c, el = orc.mesh_unit_square_tri(6, 6)
+        cls, kind, dpn = element.Tri3, "tri3", 2
+        mat, omat = materials.LinearElastic(0.38, 0.58), orc.LinearElastic(0.38, 0.58)
+    x = c[:, 0]
+    lo, hi = x.min(), x.max()
+    left, right = np.where(np.isclose(x, lo))[0], np.where(np.isclose(x, hi))[0]
+    # pair right-face nodes with the left-face nodes at the same transverse position
+    key = lambda idx: np.lexsort(c[idx][:, ::-1][:, :-1].T) if c.shape[1] > 1 else np.arange(len(idx))  # noqa: E731
+    left, right = left[key(left)], right[key(right)]
+    assert np.allclose(c[left][:, 1:], c[right][:, 1:])
+    bottom = np.where(np.isclose(c[:, -1], c[:, -1].min()))[0]
+    bottom = np.setdiff1d(bottom, np.concatenate([left, right]))
+    lifter = Lifter(
+        c.shape[0] * dpn,
+        Fixed((bottom[:, None] * dpn + np.arange(dpn)).ravel(), 0.0),
+        Fixed(left * dpn, 0.01),
+        Periodic((right[:, None] * dpn + np.arange(1, dpn)).ravel(), (left[:, None] * dpn + np.arange(1, dpn)).ravel()),
+        Fixed(right * dpn, 0.02),
+    )
+    cj = c + 0.02 * rng.uniform(-1, 1, c.shape) * (c.shape[1] == 3)
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=cj, elements=el), cls())
+    if case.endswith("generic"):
+        op.set_variant(1)
+    u_red = 0.01 * rng.normal(size=lifter.size_reduced)
+    if dpn == 4:
+        u_red = np.abs(u_red)
+    v_red = rng.normal(size=lifter.size_reduced)
+    fused, plain = ReducedOperator(op, mat, lifter, fused=True), ReducedOperator(op, mat, lifter, fused=False)
+    assert fused.dof_map is not None and plain.dof_map is None
+    for r in (fused, plain):
+        r.set_state(torch.as_tensor(u_red, device="cuda"))
+    v = torch.as_tensor(v_red, device="cuda")
+    y1 = fused.matvec(v, torch.empty_like(v)).cpu().numpy()
+    y0 = plain.matvec(v, torch.empty_like(v)).cpu().numpy()
+    assert np.linalg.norm(y1 - y0) / np.linalg.norm(y0) < 1e-13
+    # oracle: NumPy lifter around the oracle HVP
+    hom = lifter.homogeneous()
+    u_full = lifter.lift_from_zeros(u_red).reshape(-1, dpn)
+    v_full = hom.lift_from_zeros(v_red).reshape(-1, dpn)
+    Hv = orc.hvp_pf(kind, omat, cj, el, u_full, v_full) if dpn == 4 else orc.hvp(kind, omat, cj, el, u_full, v_full)
+    ref = lifter.reduce_adjoint(Hv.ravel())
+    assert np.linalg.norm(y1 - ref) / np.linalg.norm(ref) < 1e-12
+
+
 def test_newton_with_jacobi_reaches_the_same_minimiser():
     from tatva_b200.solver import newton_solve
 

@@ -140,8 +140,14 @@ if want("cg"):
     red.set_state(lifter.reduce(torch.as_tensor(0.02 * u_.ravel(), device="cuda")))  # small strains: SPD tangent
     n = lifter.size_reduced
     b = torch.as_tensor(np.random.default_rng(3).normal(size=n), device="cuda")
-    for graph in (False, True):
-        cg = ConjugateGradient(red.matvec, n, "cuda", use_graph=graph)
+    red_plain = ReducedOperator(op, mat, lifter, fused=False)  # lift kernel -> HVP -> segmented-sum kernel
+    red_plain.set_state(lifter.reduce(torch.as_tensor(0.02 * u_.ravel(), device="cuda")))
+    vr, yr = b.clone(), torch.empty_like(b)
+    report("hvp_lifted_fused_hex8_128", timeit(lambda: red.matvec(vr, yr)), 8 * (9 * c.shape[0]) + 32 * el.shape[0] + 8 * 2 * n + 4 * 3 * c.shape[0], n, "DOF")
+    report("hvp_lifted_3_kernels_hex8_128", timeit(lambda: red_plain.matvec(vr, yr)), 8 * (9 * c.shape[0]) + 32 * el.shape[0] + 8 * 2 * n + 4 * 3 * c.shape[0], n, "DOF")
+    for graph, r_ in ((True, red_plain), (False, red), (True, red)):
+        tag = "" if r_ is red else "_unfused_lifter"
+        cg = ConjugateGradient(r_.matvec, n, "cuda", use_graph=graph)
         cg.solve(b, tol=0.0, maxiter=20, check_every=20)  # warm-up + capture
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -150,7 +156,28 @@ if want("cg"):
         a1.record()
         torch.cuda.synchronize()
         ms = a0.elapsed_time(a1) / info["iterations"]
-        report(f"cg_iteration_hex8_128_{'graph' if graph else 'eager'}", ms, 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 11 * n, n, "DOF", iterations=info["iterations"], residual_norm=info["residual_norm"])
+        report(f"cg_iteration_hex8_128_{'graph' if graph else 'eager'}{tag}", ms, 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 11 * n, n, "DOF", iterations=info["iterations"], residual_norm=info["residual_norm"])
+
+    # Jacobi: cost of the diagonal kernel, of one preconditioned iteration, and iterations to 1e-8 with / without
+    diag = torch.empty(n, dtype=torch.float64, device="cuda")
+    report("hex8_nh_hessian_diag_c3", timeit(lambda: red.diagonal(out=diag), reps=5, warm=2), 8 * 9 * c.shape[0] + 32 * el.shape[0], n, "DOF")
+    pcg = ConjugateGradient(red.matvec, n, "cuda", use_graph=True, jacobi=True)
+    pcg.set_diagonal(diag)
+    pcg.solve(b, tol=0.0, maxiter=20, check_every=20)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    x, info = pcg.solve(b, tol=0.0, maxiter=200, check_every=50)
+    a1.record()
+    torch.cuda.synchronize()
+    report("pcg_jacobi_iteration_hex8_128_graph", a0.elapsed_time(a1) / info["iterations"], 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 13 * n, n, "DOF", iterations=info["iterations"])
+    its = {}
+    for name, solver in (("cg", cg), ("pcg_jacobi", pcg)):
+        t0 = time.perf_counter()
+        x, info = solver.solve(b, tol=1e-8, maxiter=5000, check_every=25)
+        torch.cuda.synchronize()
+        its[name] = dict(iterations=info["iterations"], converged=info["converged"], wall_s=round(time.perf_counter() - t0, 3))
+    print(json.dumps(dict(kernel="cg_vs_pcg_to_1e-8_hex8_128", **its)), flush=True)
 
 # ---- locality: the same Tet4 config-2 mesh with elements AND nodes randomly shuffled, then re-sorted ----
 if want("locality"):
