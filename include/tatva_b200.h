@@ -28,7 +28,8 @@ typedef void* tatva_stream_t;           /* a cudaStream_t */
 
 /* element kinds — tatva/element/base.py:245-265 (Tri3), :448-472 (Tetrahedron4), :475-568 (Hexahedron8),
  * :331-366 (Quad4), :266-328 (Tri6), :366-445 (Quad8), each with its default quadrature rule */
-enum { TATVA_TRI3 = 0, TATVA_TET4 = 1, TATVA_HEX8 = 2, TATVA_QUAD4 = 3, TATVA_TRI6 = 4, TATVA_QUAD8 = 5 };
+enum { TATVA_TRI3 = 0, TATVA_TET4 = 1, TATVA_HEX8 = 2, TATVA_QUAD4 = 3, TATVA_TRI6 = 4, TATVA_QUAD8 = 5,
+       TATVA_LINE2 = 6, TATVA_LINE3 = 7 };
 
 /* energy densities the configs name (user code in the reference, pinned by its tests):
  *   LINEAR_ELASTIC          psi = 1/2 sigma:eps           params {mu, lambda}          tests/test_sparse.py:20-38

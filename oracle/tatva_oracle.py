@@ -57,7 +57,11 @@ ELEMENT_INFO = {
     "quad4": (2, 4, 4),
     "tri6": (2, 6, 3),
     "quad8": (2, 8, 9),
+    # line elements embedded in the plane: dim = width of a coordinate row (the gradient has 1 component)
+    "line2": (2, 2, 1),
+    "line3": (2, 3, 3),
 }
+_LINES = ("line2", "line3")
 
 _Q4_SIGNS = np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0]])  # element/base.py:334-336
 _B = np.sqrt(3.0 / 5.0)
@@ -76,6 +80,10 @@ def reference_nodes(kind: str) -> np.ndarray:
         return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.5, 0.0], [0.5, 0.5], [0.0, 0.5]])
     if kind == "quad8":  # element/base.py:369-382
         return np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0], [0.0, -1.0], [1.0, 0.0], [0.0, 1.0], [-1.0, 0.0]])
+    if kind == "line2":  # element/base.py:147-149
+        return np.array([[-1.0], [1.0]])
+    if kind == "line3":  # element/base.py:192-194
+        return np.array([[-1.0], [1.0], [0.0]])
     raise ValueError(kind)
 
 
@@ -95,6 +103,10 @@ def quad_rule(kind: str) -> tuple[np.ndarray, np.ndarray]:
     if kind == "quad8":  # element/base.py:384-393
         x, w = np.array([-_B, 0.0, _B]), np.array([5.0 / 9, 8.0 / 9, 5.0 / 9])
         return np.array([[x[j], x[i]] for i in range(3) for j in range(3)]), np.kron(w, w)
+    if kind == "line2":  # element/base.py:151-154
+        return np.array([[0.0]]), np.array([2.0])
+    if kind == "line3":  # element/base.py:196-199
+        return np.array([[-_B], [0.0], [_B]]), np.array([5.0 / 9, 8.0 / 9, 5.0 / 9])
     raise ValueError(kind)
 
 
@@ -127,6 +139,11 @@ def shape_function(kind: str, xi: np.ndarray) -> np.ndarray:
                 0.5 * (1 - r) * (1 - t * t),
             ]
         )
+    if kind == "line2":  # element/base.py:156-158
+        return np.array([0.5 * (1.0 - xi[0]), 0.5 * (1.0 + xi[0])])
+    if kind == "line3":  # element/base.py:201-207
+        r = xi[0]
+        return np.array([0.5 * r * (r - 1.0), 0.5 * r * (r + 1.0), 1.0 - r * r])
     raise ValueError(kind)
 
 
@@ -157,11 +174,21 @@ def shape_function_derivative(kind: str, xi: np.ndarray) -> np.ndarray:
         dr = [0.25 * (-2 * r - t) * (t - 1), 0.25 * (-2 * r + t) * (t - 1), 0.25 * (2 * r + t) * (t + 1), 0.25 * (2 * r - t) * (t + 1), r * (t - 1), 0.5 - 0.5 * t * t, -r * (t + 1), 0.5 * t * t - 0.5]
         dt = [0.25 * (-r - 2 * t) * (r - 1), 0.25 * (-r + 2 * t) * (r + 1), 0.25 * (r + 1) * (r + 2 * t), 0.25 * (r - 1) * (r - 2 * t), 0.5 * r * r - 0.5, -t * (r + 1), 0.5 - 0.5 * r * r, t * (r - 1)]
         return np.array([dr, dt])
+    if kind == "line2":  # element/base.py:160-162 (returned here as (1, npe))
+        return np.array([[-0.5, 0.5]])
+    if kind == "line3":  # element/base.py:209-214
+        r = xi[0]
+        return np.array([[r - 0.5, r + 0.5, -2.0 * r]])
     raise ValueError(kind)
 
 
 def get_jacobian(kind: str, xi, X_e):
-    """element/base.py:90-93: J = dNdr @ X_e, det J."""
+    """element/base.py:90-93: J = dNdr @ X_e, det J.  Line elements (:163-167, :216-222): the arc-length
+    derivative dot(Jvec, Jvec / |Jvec|), returned twice."""
+    if kind in _LINES:
+        Jvec = shape_function_derivative(kind, xi)[0] @ X_e
+        J = np.dot(Jvec, Jvec / np.linalg.norm(Jvec))
+        return J, J
     J = shape_function_derivative(kind, xi) @ X_e
     return J, np.linalg.det(J)
 
@@ -172,7 +199,11 @@ def element_interpolate(kind: str, xi, u_e, X_e=None):
 
 
 def element_gradient(kind: str, xi, u_e, X_e):
-    """element/base.py:99-115: value dims first, spatial dim last."""
+    """element/base.py:99-115: value dims first, spatial dim last.  Line elements (:169-173, :224-228): dNdr / J,
+    no spatial axis."""
+    if kind in _LINES:
+        J, _ = get_jacobian(kind, xi, X_e)
+        return np.einsum("n,n...->...", shape_function_derivative(kind, xi)[0] / J, u_e)
     dNdr = shape_function_derivative(kind, xi)
     J = dNdr @ X_e
     dNdX = np.linalg.inv(J) @ dNdr
@@ -198,6 +229,10 @@ def geometry(kind: str, coords: np.ndarray, conn: np.ndarray):
     """Per (e,q): dNdX (E,Q,d,n) and detJ (E,Q)   [element/base.py:107-114, :90-93]."""
     dNdr = _dNdr_all(kind)
     X_e = coords[conn]  # operator.py:221 gather
+    if kind in _LINES:  # dNdX (E,Q,1,n) = dNdr / |dX/dxi|, "detJ" = |dX/dxi|
+        Jvec = np.einsum("qn,enc->eqc", dNdr[:, 0, :], X_e)
+        J = np.einsum("eqc,eqc->eq", Jvec, Jvec / np.linalg.norm(Jvec, axis=-1, keepdims=True))
+        return dNdr[None, :, :, :] / J[:, :, None, None], J
     J = np.einsum("qdn,enc->eqdc", dNdr, X_e)
     detJ = np.linalg.det(J)
     dNdX = np.einsum("eqdc,qcn->eqdn", np.linalg.inv(J), dNdr)
@@ -214,7 +249,8 @@ def op_integration_weights(kind, coords, conn):
 def op_grad(kind, coords, conn, u):
     """operator.py:379-397 -> (E,Q,*value_dims,d)."""
     dNdX, _ = geometry(kind, coords, conn)
-    return np.einsum("eqdn,en...->eq...d", dNdX, u[conn])
+    g = np.einsum("eqdn,en...->eq...d", dNdX, u[conn])
+    return g[..., 0] if kind in _LINES else g
 
 
 def op_eval(kind, coords, conn, u):

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtatva_b200.so")
 
 # enums mirrored from include/tatva_b200.h
-TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8 = 0, 1, 2, 3, 4, 5
+TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
 PLAN_CACHE_WEIGHTS = 1
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2

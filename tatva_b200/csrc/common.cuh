@@ -20,7 +20,7 @@ constexpr int kBlock = 128;  // threads per CTA for element-per-thread kernels
 // ---------------------------------------------------------------------------------------------
 
 struct Tri3 {  // tatva/element/base.py:245-265
-  static constexpr int dim = 2, npe = 3, nq = 1, kind = TATVA_TRI3;
+  static constexpr int dim = 2, gdim = 2, npe = 3, nq = 1, kind = TATVA_TRI3;
   TATVA_D static double weight(int) { return 0.5; }
   TATVA_D static void N(int, double (&n)[npe]) {
     n[0] = 1.0 - 1.0 / 3 - 1.0 / 3;
@@ -34,7 +34,7 @@ struct Tri3 {  // tatva/element/base.py:245-265
 };
 
 struct Tet4 {  // tatva/element/base.py:448-472
-  static constexpr int dim = 3, npe = 4, nq = 1, kind = TATVA_TET4;
+  static constexpr int dim = 3, gdim = 3, npe = 4, nq = 1, kind = TATVA_TET4;
   TATVA_D static double weight(int) { return 1.0 / 6; }
   TATVA_D static void N(int, double (&n)[npe]) {
     n[0] = 1.0 - 0.25 - 0.25 - 0.25;
@@ -53,7 +53,7 @@ struct Tet4 {  // tatva/element/base.py:448-472
 };
 
 struct Hex8 {  // tatva/element/base.py:475-568
-  static constexpr int dim = 3, npe = 8, nq = 8, kind = TATVA_HEX8;
+  static constexpr int dim = 3, gdim = 3, npe = 8, nq = 8, kind = TATVA_HEX8;
   // sign of reference node n along axis d (bottom face CCW, then top; :478-491); the 2x2x2
   // Gauss points are a * the same table (:493-513), all weights 1.
   TATVA_HD static constexpr double sgn(int n, int d) {
@@ -83,7 +83,7 @@ struct Hex8 {  // tatva/element/base.py:475-568
 };
 
 struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:338-344)
-  static constexpr int dim = 2, npe = 4, nq = 4, kind = TATVA_QUAD4;
+  static constexpr int dim = 2, gdim = 2, npe = 4, nq = 4, kind = TATVA_QUAD4;
   TATVA_HD static constexpr double sgn(int n, int d) { return d == 0 ? ((n == 1 || n == 2) ? 1.0 : -1.0) : ((n >= 2) ? 1.0 : -1.0); }
   TATVA_D static double weight(int) { return 1.0; }
   TATVA_D static void xi(int q, double& r, double& s) {
@@ -109,7 +109,7 @@ struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:
 };
 
 struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
-  static constexpr int dim = 2, npe = 6, nq = 3, kind = TATVA_TRI6;
+  static constexpr int dim = 2, gdim = 2, npe = 6, nq = 3, kind = TATVA_TRI6;
   TATVA_D static double weight(int) { return 1.0 / 6.0; }
   TATVA_D static void xi(int q, double& r, double& s) {
     r = (q == 1) ? 2.0 / 3.0 : 1.0 / 6.0;
@@ -132,7 +132,7 @@ struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
 };
 
 struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:384-393)
-  static constexpr int dim = 2, npe = 8, nq = 9, kind = TATVA_QUAD8;
+  static constexpr int dim = 2, gdim = 2, npe = 8, nq = 9, kind = TATVA_QUAD8;
   TATVA_D static double w1(int i) { return i == 1 ? 8.0 / 9.0 : 5.0 / 9.0; }
   TATVA_D static double x1(int i) { return i == 0 ? -0.77459666924148337704 : (i == 1 ? 0.0 : 0.77459666924148337704); }
   TATVA_D static double weight(int q) { return w1(q / 3) * w1(q % 3); }
@@ -161,6 +161,33 @@ struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:
     d[1][0] = 0.25 * (-r - 2 * s) * (r - 1); d[1][1] = 0.25 * (-r + 2 * s) * (r + 1);
     d[1][2] = 0.25 * (r + 1) * (r + 2 * s);  d[1][3] = 0.25 * (r - 1) * (r - 2 * s);
     d[1][4] = 0.5 * r * r - 0.5; d[1][5] = -s * (r + 1); d[1][6] = 0.5 - 0.5 * r * r; d[1][7] = s * (r - 1);
+  }
+};
+
+// Line elements embedded in the plane (boundary integrals): `dim` is the width of a coordinate row, `gdim` the
+// number of gradient components (1: the derivative along the arc length).  tatva/element/base.py:144-242.
+struct Line2 {  // tatva/element/base.py:144-186
+  static constexpr int dim = 2, gdim = 1, npe = 2, nq = 1, kind = TATVA_LINE2;
+  TATVA_D static double weight(int) { return 2.0; }
+  TATVA_D static void N(int, double (&n)[npe]) { n[0] = 0.5; n[1] = 0.5; }
+  TATVA_D static void dNdr(int, double (&d)[gdim][npe]) { d[0][0] = -0.5; d[0][1] = 0.5; }
+};
+
+struct Line3 {  // tatva/element/base.py:189-242; nodes (-1, 1, 0), 3-point Gauss
+  static constexpr int dim = 2, gdim = 1, npe = 3, nq = 3, kind = TATVA_LINE3;
+  TATVA_D static double xi(int q) { return (q - 1) * 0.77459666924148337704; }  // sqrt(3/5)
+  TATVA_D static double weight(int q) { return q == 1 ? 8.0 / 9 : 5.0 / 9; }
+  TATVA_D static void N(int q, double (&n)[npe]) {
+    const double r = xi(q);
+    n[0] = 0.5 * r * (r - 1.0);
+    n[1] = 0.5 * r * (r + 1.0);
+    n[2] = 1.0 - r * r;
+  }
+  TATVA_D static void dNdr(int q, double (&d)[gdim][npe]) {
+    const double r = xi(q);
+    d[0][0] = r - 0.5;
+    d[0][1] = r + 0.5;
+    d[0][2] = -2.0 * r;
   }
 };
 
@@ -199,52 +226,80 @@ TATVA_D double det_inv(const double (&A)[3][3], double (&Ai)[3][3]) {
 
 // Per-quadrature-point geometry: dNdX = inv(J) @ dNdr with J = dNdr @ X_e
 // (tatva/element/base.py:111-113); returns det J (:92).
+// Arc-length Jacobian of a line element: J = |dNdr @ X_e| (the reference's dot(Jvec, Jvec / |Jvec|),
+// tatva/element/base.py:163-167, :218-224), dNdS = dNdr / J.
 template <class El>
-TATVA_D double geometry(int q, const double (&X)[El::npe][El::dim], double (&dNdX)[El::dim][El::npe]) {
-  double dNdr[El::dim][El::npe];
+TATVA_D double line_jacobian(int q, const double (&X)[El::npe][El::dim], double (&dNdr)[1][El::npe]) {
   El::dNdr(q, dNdr);
-  double J[El::dim][El::dim], Ji[El::dim][El::dim];
+  double n2 = 0.0;
 #pragma unroll
-  for (int d = 0; d < El::dim; ++d)
+  for (int c = 0; c < El::dim; ++c) {
+    double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < El::dim; ++c) {
-      double s = 0.0;
+    for (int n = 0; n < El::npe; ++n) s += dNdr[0][n] * X[n][c];
+    n2 += s * s;
+  }
+  return sqrt(n2);
+}
+
+template <class El>
+TATVA_D double geometry(int q, const double (&X)[El::npe][El::dim], double (&dNdX)[El::gdim][El::npe]) {
+  if constexpr (El::gdim != El::dim) {
+    const double J = line_jacobian<El>(q, X, dNdX);
 #pragma unroll
-      for (int n = 0; n < El::npe; ++n) s += dNdr[d][n] * X[n][c];
-      J[d][c] = s;
-    }
-  const double det = det_inv(J, Ji);
+    for (int n = 0; n < El::npe; ++n) dNdX[0][n] /= J;
+    return J;
+  } else {
+    double dNdr[El::dim][El::npe];
+    El::dNdr(q, dNdr);
+    double J[El::dim][El::dim], Ji[El::dim][El::dim];
 #pragma unroll
-  for (int c = 0; c < El::dim; ++c)
+    for (int d = 0; d < El::dim; ++d)
 #pragma unroll
-    for (int n = 0; n < El::npe; ++n) {
-      double s = 0.0;
+      for (int c = 0; c < El::dim; ++c) {
+        double s = 0.0;
 #pragma unroll
-      for (int d = 0; d < El::dim; ++d) s += Ji[c][d] * dNdr[d][n];
-      dNdX[c][n] = s;
-    }
-  return det;
+        for (int n = 0; n < El::npe; ++n) s += dNdr[d][n] * X[n][c];
+        J[d][c] = s;
+      }
+    const double det = det_inv(J, Ji);
+#pragma unroll
+    for (int c = 0; c < El::dim; ++c)
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < El::dim; ++d) s += Ji[c][d] * dNdr[d][n];
+        dNdX[c][n] = s;
+      }
+    return det;
+  }
 }
 
 template <class El>
 TATVA_D double det_jacobian(int q, const double (&X)[El::npe][El::dim]) {
-  double dNdr[El::dim][El::npe];
-  El::dNdr(q, dNdr);
-  double J[El::dim][El::dim];
-#pragma unroll
-  for (int d = 0; d < El::dim; ++d)
-#pragma unroll
-    for (int c = 0; c < El::dim; ++c) {
-      double s = 0.0;
-#pragma unroll
-      for (int n = 0; n < El::npe; ++n) s += dNdr[d][n] * X[n][c];
-      J[d][c] = s;
-    }
-  if constexpr (El::dim == 2) {
-    return J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  if constexpr (El::gdim != El::dim) {
+    double dNdr[1][El::npe];
+    return line_jacobian<El>(q, X, dNdr);
   } else {
-    return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
-           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    double dNdr[El::dim][El::npe];
+    El::dNdr(q, dNdr);
+    double J[El::dim][El::dim];
+#pragma unroll
+    for (int d = 0; d < El::dim; ++d)
+#pragma unroll
+      for (int c = 0; c < El::dim; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n) s += dNdr[d][n] * X[n][c];
+        J[d][c] = s;
+      }
+    if constexpr (El::dim == 2) {
+      return J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    } else {
+      return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+             J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    }
   }
 }
 
@@ -461,7 +516,7 @@ constexpr size_t grouped_scatter_smem(int warps) {
 
 struct tatva_plan {
   int element;
-  int dim, npe, nq;
+  int dim, gdim, npe, nq;  // dim: width of a coordinate row; gdim: gradient components (1 for line elements)
   int64_t n_nodes, n_elems;
   const double* coords;  // caller-owned device view (n_nodes, dim)
   const int32_t* conn;   // caller-owned device view (n_elems, npe)

@@ -63,18 +63,18 @@ __global__ void __launch_bounds__(kBlock) k_grad(const double* __restrict__ coor
   gather_rows(coords, nd, X);
 #pragma unroll 1
   for (int q = 0; q < El::nq; ++q) {
-    double dNdX[El::dim][El::npe];
+    double dNdX[El::gdim][El::npe];
     geometry<El>(q, X, dNdX);
     for (int c = 0; c < nv; ++c) {
       double ue[El::npe];
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
 #pragma unroll
-      for (int j = 0; j < El::dim; ++j) {
+      for (int j = 0; j < El::gdim; ++j) {
         double s = 0.0;
 #pragma unroll
         for (int n = 0; n < El::npe; ++n) s += dNdX[j][n] * ue[n];
-        out[((e * El::nq + q) * nv + c) * El::dim + j] = s;
+        out[((e * El::nq + q) * nv + c) * El::gdim + j] = s;
       }
     }
   }
@@ -92,17 +92,17 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint(const double* __restric
   gather_rows(coords, nd, X);
 #pragma unroll 1
   for (int q = 0; q < El::nq; ++q) {
-    double dNdX[El::dim][El::npe];
+    double dNdX[El::gdim][El::npe];
     geometry<El>(q, X, dNdX);
     for (int c = 0; c < nv; ++c) {
-      double gj[El::dim];
+      double gj[El::gdim];
 #pragma unroll
-      for (int j = 0; j < El::dim; ++j) gj[j] = __ldg(g + ((e * El::nq + q) * nv + c) * El::dim + j);
+      for (int j = 0; j < El::gdim; ++j) gj[j] = __ldg(g + ((e * El::nq + q) * nv + c) * El::gdim + j);
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < El::dim; ++j) s += gj[j] * dNdX[j][n];
+        for (int j = 0; j < El::gdim; ++j) s += gj[j] * dNdX[j][n];
         atomicAdd(y + (int64_t)nd[n] * nv + c, s);
       }
     }
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_staged(const double* __restrict
                                                         const int32_t* __restrict__ conn, int64_t E,
                                                         const double* __restrict__ u, int nv, double* __restrict__ out) {
   extern __shared__ double sm_stage[];
-  const int CH = El::nq * nv * El::dim, S = CH | 1;
+  const int CH = El::nq * nv * El::gdim, S = CH | 1;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,18 +145,18 @@ __global__ void __launch_bounds__(kBlock) k_grad_staged(const double* __restrict
     gather_rows(coords, nd, X);
 #pragma unroll 1
     for (int q = 0; q < El::nq; ++q) {
-      double dNdX[El::dim][El::npe];
+      double dNdX[El::gdim][El::npe];
       geometry<El>(q, X, dNdX);
       for (int c = 0; c < nv; ++c) {
         double ue[El::npe];
 #pragma unroll
         for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
 #pragma unroll
-        for (int j = 0; j < El::dim; ++j) {
+        for (int j = 0; j < El::gdim; ++j) {
           double t = 0.0;
 #pragma unroll
           for (int n = 0; n < El::npe; ++n) t += dNdX[j][n] * ue[n];
-          st[lane * S + (q * nv + c) * El::dim + j] = t;
+          st[lane * S + (q * nv + c) * El::gdim + j] = t;
         }
       }
     }
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_staged(const double* __
                                                                 const double* __restrict__ g, int nv,
                                                                 double* __restrict__ y) {
   extern __shared__ double sm_stage[];
-  const int CH = El::nq * nv * El::dim, S = CH | 1;
+  const int CH = El::nq * nv * El::gdim, S = CH | 1;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,17 +186,17 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_staged(const double* __
   gather_rows(coords, nd, X);
 #pragma unroll 1
   for (int q = 0; q < El::nq; ++q) {
-    double dNdX[El::dim][El::npe];
+    double dNdX[El::gdim][El::npe];
     geometry<El>(q, X, dNdX);
     for (int c = 0; c < nv; ++c) {
-      double gj[El::dim];
+      double gj[El::gdim];
 #pragma unroll
-      for (int j = 0; j < El::dim; ++j) gj[j] = st[lane * S + (q * nv + c) * El::dim + j];
+      for (int j = 0; j < El::gdim; ++j) gj[j] = st[lane * S + (q * nv + c) * El::gdim + j];
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) {
         double t = 0.0;
 #pragma unroll
-        for (int j = 0; j < El::dim; ++j) t += gj[j] * dNdX[j][n];
+        for (int j = 0; j < El::gdim; ++j) t += gj[j] * dNdX[j][n];
         atomicAdd(y + (int64_t)nd[n] * nv + c, t);
       }
     }
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __res
                                                              const int32_t* __restrict__ conn, int64_t E,
                                                              const double* __restrict__ g, double* __restrict__ y) {
   extern __shared__ double sm_stage[];
-  constexpr int CH = El::nq * NV * El::dim, S = CH | 1;
+  constexpr int CH = El::nq * NV * El::gdim, S = CH | 1;
   constexpr int SC = 32 * El::npe * NV + 16 * El::npe;  // grouped-scatter staging per warp
   constexpr int PER_WARP = (32 * S > SC) ? 32 * S : SC;
   const int lane = threadIdx.x & 31;
@@ -233,18 +233,18 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __res
     gather_rows(coords, nd, X);
 #pragma unroll 1
     for (int q = 0; q < El::nq; ++q) {
-      double dNdX[El::dim][El::npe];
+      double dNdX[El::gdim][El::npe];
       geometry<El>(q, X, dNdX);
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
-        double gj[El::dim];
+        double gj[El::gdim];
 #pragma unroll
-        for (int j = 0; j < El::dim; ++j) gj[j] = st[lane * S + (q * NV + c) * El::dim + j];
+        for (int j = 0; j < El::gdim; ++j) gj[j] = st[lane * S + (q * NV + c) * El::gdim + j];
 #pragma unroll
         for (int n = 0; n < El::npe; ++n) {
           double t = Y[n][c];
 #pragma unroll
-          for (int j = 0; j < El::dim; ++j) t = fma(gj[j], dNdX[j][n], t);
+          for (int j = 0; j < El::gdim; ++j) t = fma(gj[j], dNdX[j][n], t);
           Y[n][c] = t;
         }
       }
@@ -1133,6 +1133,8 @@ static int allow_big_smem(K kernel, bool& done) {
     case TATVA_QUAD4: { using El = Quad4; CALL; } break; \
     case TATVA_TRI6: { using El = Tri6; CALL; } break; \
     case TATVA_QUAD8: { using El = Quad8; CALL; } break; \
+    case TATVA_LINE2: { using El = Line2; CALL; } break; \
+    case TATVA_LINE3: { using El = Line3; CALL; } break; \
     default: return TATVA_E_INVALID;              \
   }
 
@@ -1169,12 +1171,14 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   if (!p) return TATVA_E_NOMEM;
   p->element = element;
   switch (element) {
-    case TATVA_TRI3: p->dim = Tri3::dim; p->npe = Tri3::npe; p->nq = Tri3::nq; break;
-    case TATVA_TET4: p->dim = Tet4::dim; p->npe = Tet4::npe; p->nq = Tet4::nq; break;
-    case TATVA_HEX8: p->dim = Hex8::dim; p->npe = Hex8::npe; p->nq = Hex8::nq; break;
-    case TATVA_QUAD4: p->dim = Quad4::dim; p->npe = Quad4::npe; p->nq = Quad4::nq; break;
-    case TATVA_TRI6: p->dim = Tri6::dim; p->npe = Tri6::npe; p->nq = Tri6::nq; break;
-    case TATVA_QUAD8: p->dim = Quad8::dim; p->npe = Quad8::npe; p->nq = Quad8::nq; break;
+    case TATVA_TRI3: p->dim = Tri3::dim; p->gdim = Tri3::gdim; p->npe = Tri3::npe; p->nq = Tri3::nq; break;
+    case TATVA_TET4: p->dim = Tet4::dim; p->gdim = Tet4::gdim; p->npe = Tet4::npe; p->nq = Tet4::nq; break;
+    case TATVA_HEX8: p->dim = Hex8::dim; p->gdim = Hex8::gdim; p->npe = Hex8::npe; p->nq = Hex8::nq; break;
+    case TATVA_QUAD4: p->dim = Quad4::dim; p->gdim = Quad4::gdim; p->npe = Quad4::npe; p->nq = Quad4::nq; break;
+    case TATVA_TRI6: p->dim = Tri6::dim; p->gdim = Tri6::gdim; p->npe = Tri6::npe; p->nq = Tri6::nq; break;
+    case TATVA_QUAD8: p->dim = Quad8::dim; p->gdim = Quad8::gdim; p->npe = Quad8::npe; p->nq = Quad8::nq; break;
+    case TATVA_LINE2: p->dim = Line2::dim; p->gdim = Line2::gdim; p->npe = Line2::npe; p->nq = Line2::nq; break;
+    case TATVA_LINE3: p->dim = Line3::dim; p->gdim = Line3::gdim; p->npe = Line3::npe; p->nq = Line3::nq; break;
     default: delete p; return TATVA_E_INVALID;
   }
   p->n_nodes = n_nodes;
@@ -1257,7 +1261,7 @@ int tatva_op_grad(const tatva_plan_t* p, const double* d_u, int nv, double* d_ou
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->dim) | 1) * sizeof(double);
+    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->gdim) | 1) * sizeof(double);
     if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {
       STAGED_OPT_IN(k_grad_staged);
       DISPATCH_ELEMENT(p, (k_grad_staged<El><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
@@ -1278,7 +1282,7 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
     int rc = TATVA_OK;
 #define ADJ_ACC(NV)                                                                                              \
   {                                                                                                              \
-    constexpr int CH_ = El::nq * NV * El::dim, S_ = CH_ | 1, SC_ = 32 * El::npe * NV + 16 * El::npe;              \
+    constexpr int CH_ = El::nq * NV * El::gdim, S_ = CH_ | 1, SC_ = 32 * El::npe * NV + 16 * El::npe;              \
     constexpr size_t smem_ = (size_t)(kBlock / 32) * ((32 * S_ > SC_) ? 32 * S_ : SC_) * sizeof(double);         \
     static bool done_ = false;                                                                                   \
     rc = allow_big_smem(k_grad_adjoint_acc<El, NV>, done_);                                                      \
@@ -1297,7 +1301,7 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
     return TATVA_OK;
   }
   {
-    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->dim) | 1) * sizeof(double);
+    const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->gdim) | 1) * sizeof(double);
     if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {
       STAGED_OPT_IN(k_grad_adjoint_staged);
       DISPATCH_ELEMENT(p, (k_grad_adjoint_staged<El><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_g, nv, d_y)));

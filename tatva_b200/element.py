@@ -210,9 +210,11 @@ class Quad8(Element):
 
 class _LineElement(Element):
     """1-D elements embedded in 2-D: the Jacobian is the arc-length derivative |dX/dxi| and the gradient is the
-    derivative along the line (element/base.py:164-188, :216-243).  Host-side only: no CUDA kernel."""
+    derivative along the line (element/base.py:164-188, :216-243).  `Operator.grad` returns (E, Q, *v): no trailing
+    spatial axis."""
 
     kind = None
+    gradient_components = 1
 
     def get_jacobian(self, xi, nodal_coords):
         Jvec = self.shape_function_derivative(xi) @ np.asarray(nodal_coords)
@@ -231,6 +233,8 @@ class _LineElement(Element):
 class Line2(_LineElement):
     """2-node linear interval (element/base.py:144-188)."""
 
+    kind = _lib.LINE2
+
     def _reference_nodes(self):
         return np.array([[-1.0], [1.0]])
 
@@ -246,6 +250,8 @@ class Line2(_LineElement):
 
 class Line3(_LineElement):
     """3-node quadratic interval: end nodes then the midpoint (element/base.py:191-243)."""
+
+    kind = _lib.LINE3
 
     def _reference_nodes(self):
         return np.array([[-1.0], [1.0], [0.0]])

@@ -41,8 +41,8 @@ class Operator:
         self._check_init(mesh)
         if element.kind is None or not getattr(element, "_default_rule", True):
             raise NotImplementedError(
-                f"{type(element).__name__} with this quadrature rule has no CUDA kernel (Tri3, Tri6, Quad4, Quad8, "
-                "Tetrahedron4, Hexahedron8 with their default rules are supported)"
+                f"{type(element).__name__} with this quadrature rule has no CUDA kernel (the eight reference elements "
+                "with their default rules are supported)"
             )
         if not torch.cuda.is_available():
             raise _lib.TatvaError("tatva_b200.Operator needs a CUDA device (there is no CPU fallback)")
@@ -50,6 +50,11 @@ class Operator:
         self.coords = torch.as_tensor(_to_np_or_tensor(mesh.coords), dtype=torch.float64, device=self.device).contiguous()
         self.elements = torch.as_tensor(_to_np_or_tensor(mesh.elements), device=self.device).to(torch.int32).contiguous()
         self.n_nodes, self.dim = self.coords.shape
+        self._line = getattr(element, "gradient_components", None) == 1  # arc-length gradient: no spatial axis
+        expected = 2 if self._line else np.asarray(element.quad_points).shape[1]
+        if self.dim != expected:
+            raise ValueError(f"{type(element).__name__} needs {expected}-D node coordinates, the mesh has {self.dim}-D")
+        self.gdim = 1 if self._line else self.dim
         self.n_elements, self.npe = self.elements.shape
         self.nq = len(element.quad_weights)
         self.batch_size = self.n_elements if batch_size is None else int(batch_size)  # operator.py:116-117
@@ -151,7 +156,7 @@ class Operator:
 
     # raw (non-differentiable) kernel wrappers; nodal arrays are (N, nv) contiguous
     def _k_grad(self, u2):
-        out = torch.empty((self.n_elements, self.nq, u2.shape[1], self.dim), dtype=torch.float64, device=self.device)
+        out = torch.empty((self.n_elements, self.nq, u2.shape[1], self.gdim), dtype=torch.float64, device=self.device)
         self._call("tatva_op_grad", u2.data_ptr(), u2.shape[1], out.data_ptr())
         return out
 
@@ -198,11 +203,11 @@ class Operator:
         return out
 
     def grad(self, nodal_values) -> torch.Tensor:
-        """(N, *v) -> (E, Q, *v, dim) — operator.py:379-397."""
+        """(N, *v) -> (E, Q, *v, dim) — operator.py:379-397; line elements: (E, Q, *v) (element/base.py:169-173)."""
         u = self._as_dev(nodal_values)
         vshape = tuple(u.shape[1:])
         out = _LinearOp.apply(u.reshape(self.n_nodes, -1), self, "grad")
-        return out.reshape((self.n_elements, self.nq) + vshape + (self.dim,))
+        return out.reshape((self.n_elements, self.nq) + vshape + (() if self._line else (self.dim,)))
 
     def eval(self, nodal_values) -> torch.Tensor:
         """(N, *v) -> (E, Q, *v) — operator.py:358-377."""

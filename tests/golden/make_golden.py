@@ -207,6 +207,40 @@ def more_operator_fixtures(out):
         out[p + "energy"] = op.integrate(strain_energy(op.grad(u), mat[0], mat[1]))
 
 
+def line_meshes():
+    """Curved boundary polylines in the plane: a quarter arc of radius 1.3 (Line2: chords; Line3: end nodes then an
+    off-chord midpoint, so |dX/dxi| varies along the element)."""
+    n = 7
+    t = np.linspace(0.1, 1.4, n + 1)
+    ends = 1.3 * np.stack([np.cos(t), np.sin(t)], -1)
+    tm = 0.5 * (t[:-1] + t[1:]) + 0.03
+    mids = 1.3 * np.stack([np.cos(tm), np.sin(tm)], -1)
+    line2 = (ends, np.stack([np.arange(n), np.arange(1, n + 1)], -1).astype(np.int32))
+    line3 = (np.concatenate([ends, mids]), np.stack([np.arange(n), np.arange(1, n + 1), n + 1 + np.arange(n)], -1).astype(np.int32))
+    return {"line2": line2, "line3": line3}
+
+
+def line_fixtures(out):
+    """tatva.element.Line2 / Line3 and tatva.Operator on line meshes (element/base.py:144-242)."""
+    rng = np.random.default_rng(17)
+    for kind, cls in {"line2": element.Line2, "line3": element.Line3}.items():
+        c, el = line_meshes()[kind]
+        op = Operator(Mesh(coords=c, elements=el), cls())
+        u = rng.normal(size=c.shape)
+        s = rng.normal(size=(c.shape[0],))
+        p = f"op_{kind}_"
+        out[p + "coords"], out[p + "conn"], out[p + "u"], out[p + "s"] = c, el, u, s
+        out[p + "qp"], out[p + "qw"] = np.asarray(op.element.quad_points, dtype=float), np.asarray(op.element.quad_weights, dtype=float)
+        out[p + "grad_u"] = op.grad(u)
+        out[p + "grad_s"] = op.grad(s)
+        out[p + "eval_u"] = op.eval(u)
+        out[p + "weights"] = op.get_integration_weights()
+        out[p + "int_nodal_s"] = op.integrate(s)
+        q = rng.normal(size=(el.shape[0], len(op.element.quad_points), 2))
+        out[p + "quadvals"] = q
+        out[p + "int_quad_per_el"] = op.integrate_per_element(q)
+
+
 def sparse_fixtures(out):
     cases = {
         "tri3_8x8_d2": (orc.mesh_unit_square_tri(8, 8), 2),  # tests/test_sparse.py:40-45
@@ -254,6 +288,7 @@ def main():
     more_operator_fixtures(out)
     sparse_fixtures(out)
     partition_fixtures(out)
+    line_fixtures(out)
     try:
         from _fakempi_golden import mpi_fixtures  # type: ignore
 

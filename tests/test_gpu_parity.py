@@ -255,6 +255,70 @@ def test_second_order_and_quad_elements(golden, kind):
     _assert_close(data, orc.assemble_csr_data(kind, omat, c, el, u, pat.indptr, pat.indices))
 
 
+@pytest.mark.parametrize("kind", ["line2", "line3"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_line_elements_on_a_curved_boundary(golden, kind, variant):
+    """Line2 / Line3 kernels (arc-length Jacobian |dX/dxi|, derivative along the line, no spatial axis) against the
+    reference's outputs, plus the adjoint identity <grad u, g> = <u, grad^T g> and a boundary-traction integral by
+    autograd (the way the reference builds Neumann terms: op.integrate(t . op.eval(u)))."""
+    from tatva_b200 import element
+    import tatva_b200
+
+    cls = {"line2": element.Line2, "line3": element.Line3}[kind]
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    c, el, u, s = g("coords"), g("conn"), g("u"), g("s")
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), cls())
+    op.set_variant(variant)  # 1: plain kernels, 0: warp-staged ones
+    _assert_close(op.grad(u), g("grad_u"))
+    _assert_close(op.grad(s), g("grad_s"))
+    _assert_close(op.eval(u), g("eval_u"))
+    _assert_close(op.get_integration_weights(), g("weights"))
+    _assert_close(op.integrate(s), g("int_nodal_s"))
+    _assert_close(op.integrate_per_element(g("quadvals")), g("int_quad_per_el"))
+    # larger closed curve: the oracle at a size with many CTAs, and the adjoint
+    n = 5000
+    t = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    r = 1.0 + 0.2 * np.cos(3 * t)
+    ends = np.stack([r * np.cos(t), r * np.sin(t)], -1)
+    if kind == "line2":
+        cc, ee = ends, np.stack([np.arange(n), (np.arange(n) + 1) % n], -1).astype(np.int32)
+    else:
+        tm = t + np.pi / n
+        rm = 1.0 + 0.2 * np.cos(3 * tm)
+        cc = np.concatenate([ends, np.stack([rm * np.cos(tm), rm * np.sin(tm)], -1)])
+        ee = np.stack([np.arange(n), (np.arange(n) + 1) % n, n + np.arange(n)], -1).astype(np.int32)
+    rng = np.random.default_rng(0)
+    uu = rng.normal(size=(cc.shape[0], 3))
+    op2 = tatva_b200.Operator(tatva_b200.Mesh(coords=cc, elements=ee), cls())
+    op2.set_variant(variant)
+    G = op2.grad(uu)
+    _assert_close(G, orc.op_grad(kind, cc, ee, uu))
+    _assert_close(op2.get_integration_weights(), orc.op_integration_weights(kind, cc, ee))
+    gq = torch.as_tensor(rng.normal(size=tuple(G.shape)), device="cuda")
+    ut = torch.as_tensor(uu, device="cuda", requires_grad=True)
+    (op2.grad(ut) * gq).sum().backward()
+    ref_adj = np.zeros_like(uu)
+    dNdX, _ = orc.geometry(kind, cc, ee)
+    np.add.at(ref_adj, ee, np.einsum("eqn,eqv->env", dNdX[:, :, 0, :], gq.cpu().numpy()))
+    _assert_close(ut.grad, ref_adj)
+    # traction work W(u) = int t . u ds  ->  dW/du = consistent nodal forces; they sum to t * length
+    trac = torch.tensor([0.3, -1.1, 0.7], dtype=torch.float64, device="cuda")
+    ut = torch.as_tensor(uu, device="cuda", requires_grad=True)
+    op2.integrate((op2.eval(ut) * trac).sum(-1)).backward()
+    length = float(op2.get_integration_weights().sum())
+    np.testing.assert_allclose(ut.grad.sum(0).cpu().numpy(), trac.cpu().numpy() * length, rtol=1e-12)
+
+
+def test_line_element_needs_plane_coordinates():
+    from tatva_b200 import element
+    import tatva_b200
+
+    with pytest.raises(ValueError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=np.zeros((3, 3)), elements=np.array([[0, 1]], dtype=np.int32)), element.Line2())
+    with pytest.raises(ValueError):
+        tatva_b200.Operator(tatva_b200.Mesh(coords=np.random.default_rng(0).normal(size=(4, 3)), elements=np.array([[0, 1, 2]], dtype=np.int32)), element.Tri3())
+
+
 def test_tiled_tet4_kernels_match_oracle():
     """Operator(stage_tiles=True): Tet4 neo-Hookean residual / HVP through the shared-memory staging tiles."""
     c, el, u, v, (mname, omat) = _case("tet4", 9)

@@ -72,6 +72,32 @@ def test_operator_matches_reference(golden, kind):
     np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, g("quadvals")), g("int_quad_per_el"), **kw)
 
 
+@pytest.mark.parametrize("kind", ["line2", "line3"])
+def test_line_operator_matches_reference(golden, kind):
+    """Line2 / Line3 on a curved polyline: arc-length Jacobian and derivative (reference element/base.py:144-242)."""
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    c, el, u, s = g("coords"), g("conn"), g("u"), g("s")
+    kw = dict(rtol=1e-13, atol=1e-13)
+    qp, qw = orc.quad_rule(kind)
+    np.testing.assert_allclose(qp, g("qp"), atol=1e-15)
+    np.testing.assert_allclose(qw, g("qw"), atol=1e-15)
+    assert orc.op_grad(kind, c, el, u).shape == g("grad_u").shape  # (E, Q, 2): no spatial axis
+    np.testing.assert_allclose(orc.op_grad(kind, c, el, u), g("grad_u"), **kw)
+    np.testing.assert_allclose(orc.op_grad(kind, c, el, s), g("grad_s"), **kw)
+    np.testing.assert_allclose(orc.op_eval(kind, c, el, u), g("eval_u"), **kw)
+    np.testing.assert_allclose(orc.op_integration_weights(kind, c, el), g("weights"), **kw)
+    np.testing.assert_allclose(orc.op_integrate(kind, c, el, s), g("int_nodal_s"), **kw)
+    np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, g("quadvals")), g("int_quad_per_el"), **kw)
+    # per-point element functions agree with the vectorised ones
+    for e in range(2):
+        for q, xi in enumerate(qp):
+            np.testing.assert_allclose(orc.element_gradient(kind, xi, u[el[e]], c[el[e]]), g("grad_u")[e, q], **kw)
+            np.testing.assert_allclose(orc.get_jacobian(kind, xi, c[el[e]])[1] * qw[q], g("weights")[e, q], **kw)
+    # the arc is 1.3 rad of radius 1.3: Line3 integrates its length to 4 digits, the chords of Line2 to 3
+    length = orc.op_integration_weights(kind, c, el).sum()
+    assert abs(length - 1.3 * 1.3) < (5e-3 if kind == "line2" else 2e-4)
+
+
 @pytest.mark.parametrize("kind", KINDS)
 def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
     g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
