@@ -100,6 +100,11 @@ int tatva_op_integration_weights(const tatva_plan_t* plan, double* d_out, tatva_
  * vals (n_elems, nq, n_val) -> out (n_elems, n_val) = einsum("eq...,eq->e...", vals, W)    */
 int tatva_op_integrate_quad(const tatva_plan_t* plan, const double* d_vals, int n_val,
                             double* d_out, tatva_stream_t stream);
+/* Operator.interpolate (tatva/operator.py:399-463) with mesh.find_containing_polygons (tatva/mesh.py:294-388):
+ * u (n_nodes, n_val) at n_points physical points (n_points, 2) -> out (n_points, n_val).  Plane elements only,
+ * as in the reference.  d_elem (n_points, int32): containing element, -1 (and NaN values) outside the mesh.   */
+int tatva_op_interpolate(const tatva_plan_t* plan, const double* d_u, int n_val, const double* d_points,
+                         int64_t n_points, double* d_out, int32_t* d_elem, tatva_stream_t stream);
 /* the gather `v[self.mesh.elements]` of Operator.map / map_over_elements
  * (tatva/operator.py:254-257, :296-299): u (n_nodes, n_val) -> out (n_elems, npe, n_val)    */
 int tatva_op_gather(const tatva_plan_t* plan, const double* d_u, int n_val, double* d_out,

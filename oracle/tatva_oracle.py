@@ -278,6 +278,50 @@ def op_integrate(kind, coords, conn, arg):
     return np.sum(op_integrate_per_element(kind, coords, conn, arg), axis=0)
 
 
+def find_containing_polygons(points, polygons):
+    """mesh.py:294-388: for every 2-D point the FIRST polygon (vertex loops in the given order) that contains it, -1
+    if none.  Bounding-box reject, then boundary test (|cross| <= 1e-8, jnp.isclose's atol, on the segment's box)
+    OR odd number of crossings of the +x ray."""
+    points, polygons = np.asarray(points, dtype=np.float64), np.asarray(polygons, dtype=np.float64)
+    out = np.full(points.shape[0], -1, dtype=np.int64)
+    lo, hi = polygons.min(axis=1), polygons.max(axis=1)
+    p1, p2 = polygons, np.roll(polygons, -1, axis=1)
+    for i, (px, py) in enumerate(points):
+        cand = np.where((px >= lo[:, 0]) & (px <= hi[:, 0]) & (py >= lo[:, 1]) & (py <= hi[:, 1]))[0]
+        for j in cand:
+            a, b = p1[j], p2[j]
+            cross = (b[:, 0] - a[:, 0]) * (py - a[:, 1]) - (b[:, 1] - a[:, 1]) * (px - a[:, 0])
+            on_seg = (np.minimum(a[:, 0], b[:, 0]) <= px) & (px <= np.maximum(a[:, 0], b[:, 0])) & (np.minimum(a[:, 1], b[:, 1]) <= py) & (py <= np.maximum(a[:, 1], b[:, 1]))
+            on_boundary = np.any((np.abs(cross) <= 1e-8) & on_seg)
+            y_cond = ((a[:, 1] <= py) & (b[:, 1] > py)) | ((b[:, 1] <= py) & (a[:, 1] > py))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                x_int = (b[:, 0] - a[:, 0]) * (py - a[:, 1]) / (b[:, 1] - a[:, 1]) + a[:, 0]
+            if on_boundary or (np.sum(y_cond & (px < x_int)) % 2 == 1):
+                out[i] = j
+                break
+    return out
+
+
+def op_interpolate(kind, coords, conn, u, points):
+    """operator.py:399-463: containing element, then ONE Newton step from the first quadrature point
+    (xi = xi0 - (dx/dxi)^-1 (x(xi0) - p); exact for affine elements), then N(xi) . u_e.  NaN rows where no element
+    contains the point (the reference raises RuntimeError in that case when not traced)."""
+    points = np.asarray(points, dtype=np.float64)
+    idx = find_containing_polygons(points, coords[conn])
+    xi0 = quad_rule(kind)[0][0]
+    u = np.asarray(u, dtype=np.float64)
+    out = np.full((points.shape[0],) + u.shape[1:], np.nan)
+    for i, e in enumerate(idx):
+        if e < 0:
+            continue
+        X_e = coords[conn[e]]
+        x0 = shape_function(kind, xi0) @ X_e
+        lhs = (shape_function_derivative(kind, xi0) @ X_e).T  # d x_i / d xi_j
+        xi = xi0 + np.linalg.solve(lhs, -(x0 - points[i]))
+        out[i] = np.einsum("n,n...->...", shape_function(kind, xi), u[conn[e]])
+    return out, idx
+
+
 # ----------------------------------------------------------------------------------------
 # Constitutive laws used by the configs (user code in the reference, pinned by its tests)
 # ----------------------------------------------------------------------------------------

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tatva_op_eval_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "tatva_op_integration_weights": (C.c_int, [vp, vp, vp]),
     "tatva_op_integrate_quad": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "tatva_op_interpolate": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, vp, vp, vp]),
     "tatva_op_gather": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "tatva_op_gather_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "tatva_op_sum_rows": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp]),

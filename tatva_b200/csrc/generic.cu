@@ -422,6 +422,168 @@ __global__ void __launch_bounds__(256) k_sum_rows_final(const double* __restrict
   }
 }
 
+// ---- Operator.interpolate: point location + one Newton step + shape functions at a free point ----------
+// Shape functions of the plane elements at an arbitrary reference point (the element structs above only carry
+// their quadrature points).  tatva/element/base.py:257-265, :286-328, :346-366, :395-445.
+template <class El> struct PlaneShape;
+template <> struct PlaneShape<Tri3> {
+  TATVA_D static void N(double r, double s, double (&n)[3]) { n[0] = 1.0 - r - s; n[1] = r; n[2] = s; }
+  TATVA_D static void dN(double, double, double (&d)[2][3]) {
+    d[0][0] = -1.0; d[0][1] = 1.0; d[0][2] = 0.0;
+    d[1][0] = -1.0; d[1][1] = 0.0; d[1][2] = 1.0;
+  }
+};
+template <> struct PlaneShape<Quad4> {
+  TATVA_D static void N(double r, double s, double (&n)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] = 0.25 * (1.0 + Quad4::sgn(k, 0) * r) * (1.0 + Quad4::sgn(k, 1) * s);
+  }
+  TATVA_D static void dN(double r, double s, double (&d)[2][4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      d[0][k] = 0.25 * Quad4::sgn(k, 0) * (1.0 + Quad4::sgn(k, 1) * s);
+      d[1][k] = 0.25 * Quad4::sgn(k, 1) * (1.0 + Quad4::sgn(k, 0) * r);
+    }
+  }
+};
+template <> struct PlaneShape<Tri6> {
+  TATVA_D static void N(double r, double s, double (&n)[6]) {
+    const double t = 1.0 - r - s;
+    n[0] = t * (2 * t - 1); n[1] = r * (2 * r - 1); n[2] = s * (2 * s - 1);
+    n[3] = 4 * r * t; n[4] = 4 * r * s; n[5] = 4 * s * t;
+  }
+  TATVA_D static void dN(double r, double s, double (&d)[2][6]) {
+    const double t = 1.0 - r - s;
+    d[0][0] = -(4 * t - 1); d[0][1] = 4 * r - 1; d[0][2] = 0.0; d[0][3] = 4 * (t - r); d[0][4] = 4 * s; d[0][5] = -4 * s;
+    d[1][0] = -(4 * t - 1); d[1][1] = 0.0; d[1][2] = 4 * s - 1; d[1][3] = -4 * r; d[1][4] = 4 * r; d[1][5] = 4 * (t - s);
+  }
+};
+template <> struct PlaneShape<Quad8> {
+  TATVA_D static void N(double r, double s, double (&n)[8]) {
+    n[0] = 0.25 * (1 - r) * (1 - s) * (-r - s - 1);
+    n[1] = 0.25 * (1 + r) * (1 - s) * (r - s - 1);
+    n[2] = 0.25 * (1 + r) * (1 + s) * (r + s - 1);
+    n[3] = 0.25 * (1 - r) * (1 + s) * (-r + s - 1);
+    n[4] = 0.5 * (1 - r * r) * (1 - s);
+    n[5] = 0.5 * (1 + r) * (1 - s * s);
+    n[6] = 0.5 * (1 - r * r) * (1 + s);
+    n[7] = 0.5 * (1 - r) * (1 - s * s);
+  }
+  TATVA_D static void dN(double r, double s, double (&d)[2][8]) {
+    d[0][0] = 0.25 * (-2 * r - s) * (s - 1); d[0][1] = 0.25 * (-2 * r + s) * (s - 1);
+    d[0][2] = 0.25 * (2 * r + s) * (s + 1);  d[0][3] = 0.25 * (2 * r - s) * (s + 1);
+    d[0][4] = r * (s - 1); d[0][5] = 0.5 - 0.5 * s * s; d[0][6] = -r * (s + 1); d[0][7] = 0.5 * s * s - 0.5;
+    d[1][0] = 0.25 * (-r - 2 * s) * (r - 1); d[1][1] = 0.25 * (-r + 2 * s) * (r + 1);
+    d[1][2] = 0.25 * (r + 1) * (r + 2 * s);  d[1][3] = 0.25 * (r - 1) * (r - 2 * s);
+    d[1][4] = 0.5 * r * r - 0.5; d[1][5] = -s * (r + 1); d[1][6] = 0.5 - 0.5 * r * r; d[1][7] = s * (r - 1);
+  }
+};
+TATVA_D void first_quad_point(Tri3, double& r, double& s) { r = 1.0 / 3; s = 1.0 / 3; }
+TATVA_D void first_quad_point(Quad4, double& r, double& s) { Quad4::xi(0, r, s); }
+TATVA_D void first_quad_point(Tri6, double& r, double& s) { Tri6::xi(0, r, s); }
+TATVA_D void first_quad_point(Quad8, double& r, double& s) { Quad8::xi(0, r, s); }
+
+// One thread per point.  Element search exactly as mesh.find_containing_polygons (tatva/mesh.py:294-388): the
+// FIRST element, in element order, whose node loop (connectivity order) contains the point: bounding-box
+// reject, then on-boundary (|cross| <= 1e-8 within the segment's box) OR an odd number of +x ray crossings.
+// Elements are scanned in chunks staged in shared memory as bounding boxes, so the O(P E) scan reads each
+// element's nodes once per CTA.  Then operator.py:411-431: one Newton step from the first quadrature point, and
+// N(xi) . u_e.  Points outside every element get elem = -1 and NaN values.
+template <class El>
+__global__ void __launch_bounds__(128) k_interpolate(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                     int64_t E, const double* __restrict__ u, int nv,
+                                                     const double* __restrict__ pts, int64_t P,
+                                                     double* __restrict__ out, int32_t* __restrict__ elem) {
+  constexpr int npe = El::npe, CH = 128;
+  __shared__ double box[CH][4];
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < P;
+  const double px = live ? pts[2 * p] : 0.0, py = live ? pts[2 * p + 1] : 0.0;
+  int64_t found = -1;
+  for (int64_t base = 0; base < E; base += CH) {
+    __syncthreads();
+    const int64_t e = base + threadIdx.x;
+    if (e < E) {
+      double lx = 1e308, ly = 1e308, hx = -1e308, hy = -1e308;
+#pragma unroll
+      for (int n = 0; n < npe; ++n) {
+        const int64_t nd = __ldg(conn + e * npe + n);
+        const double x = __ldg(coords + 2 * nd), y = __ldg(coords + 2 * nd + 1);
+        lx = fmin(lx, x); hx = fmax(hx, x); ly = fmin(ly, y); hy = fmax(hy, y);
+      }
+      box[threadIdx.x][0] = lx; box[threadIdx.x][1] = hx; box[threadIdx.x][2] = ly; box[threadIdx.x][3] = hy;
+    }
+    __syncthreads();
+    const int cnt = (int)((E - base < CH) ? (E - base) : CH);
+    if (live && found < 0) {
+      for (int k = 0; k < cnt; ++k) {
+        if (!(px >= box[k][0] && px <= box[k][1] && py >= box[k][2] && py <= box[k][3])) continue;
+        const int64_t ee = base + k;
+        double vx[npe], vy[npe];
+#pragma unroll
+        for (int n = 0; n < npe; ++n) {
+          const int64_t nd = __ldg(conn + ee * npe + n);
+          vx[n] = __ldg(coords + 2 * nd);
+          vy[n] = __ldg(coords + 2 * nd + 1);
+        }
+        bool on_boundary = false;
+        int crossings = 0;
+#pragma unroll
+        for (int n = 0; n < npe; ++n) {
+          const double ax = vx[n], ay = vy[n], bx = vx[(n + 1) % npe], by = vy[(n + 1) % npe];
+          const double cross = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+          const bool on_seg = fmin(ax, bx) <= px && px <= fmax(ax, bx) && fmin(ay, by) <= py && py <= fmax(ay, by);
+          on_boundary |= (fabs(cross) <= 1e-8) && on_seg;
+          const bool y_cond = (ay <= py && by > py) || (by <= py && ay > py);
+          if (y_cond && px < (bx - ax) * (py - ay) / (by - ay) + ax) ++crossings;
+        }
+        if (on_boundary || (crossings & 1)) {
+          found = ee;
+          break;
+        }
+      }
+    }
+  }
+  if (!live) return;
+  elem[p] = (int32_t)found;
+  if (found < 0) {
+    for (int c = 0; c < nv; ++c) out[p * nv + c] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  int nd[npe];
+  double X[npe][2];
+#pragma unroll
+  for (int n = 0; n < npe; ++n) {
+    nd[n] = __ldg(conn + found * npe + n);
+    X[n][0] = __ldg(coords + 2 * (int64_t)nd[n]);
+    X[n][1] = __ldg(coords + 2 * (int64_t)nd[n] + 1);
+  }
+  double r0, s0, N0[npe], dN0[2][npe];
+  first_quad_point(El{}, r0, s0);
+  PlaneShape<El>::N(r0, s0, N0);
+  PlaneShape<El>::dN(r0, s0, dN0);
+  double x0 = 0.0, y0 = 0.0, a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;  // a_ij = d x_i / d xi_j
+#pragma unroll
+  for (int n = 0; n < npe; ++n) {
+    x0 += N0[n] * X[n][0];
+    y0 += N0[n] * X[n][1];
+    a00 += dN0[0][n] * X[n][0];
+    a01 += dN0[1][n] * X[n][0];
+    a10 += dN0[0][n] * X[n][1];
+    a11 += dN0[1][n] * X[n][1];
+  }
+  const double bx = px - x0, by = py - y0, det = a00 * a11 - a01 * a10;
+  const double r = r0 + (a11 * bx - a01 * by) / det, s = s0 + (a00 * by - a10 * bx) / det;
+  double N[npe];
+  PlaneShape<El>::N(r, s, N);
+  for (int c = 0; c < nv; ++c) {
+    double t = 0.0;
+#pragma unroll
+    for (int n = 0; n < npe; ++n) t += N[n] * __ldg(u + (int64_t)nd[n] * nv + c);
+    out[p * nv + c] = t;
+  }
+}
+
 // ---- fused energy / residual / HVP ------------------------------------------------------------
 
 enum { MODE_ENERGY = 0, MODE_RESIDUAL = 1, MODE_HVP = 2 };
@@ -1344,6 +1506,25 @@ int tatva_op_integrate_quad(const tatva_plan_t* p, const double* d_vals, int nv,
   if (!p || !d_vals || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_ELEMENT(p, (k_integrate_quad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, p->weights, d_vals, nv, d_out)));
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// Operator.interpolate (tatva/operator.py:399-463) for the plane elements: values of the nodal field u (n_nodes, nv) at
+// `n_points` physical points (n_points, 2) -> d_out (n_points, nv); d_elem (n_points) receives the containing
+// element of every point, -1 (and NaN values) where the point lies outside the mesh.
+int tatva_op_interpolate(const tatva_plan_t* p, const double* d_u, int nv, const double* d_points, int64_t n_points,
+                         double* d_out, int32_t* d_elem, tatva_stream_t stream) {
+  if (!p || !d_u || !d_points || !d_out || !d_elem || nv <= 0 || n_points <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)((n_points + 127) / 128);
+  switch (p->element) {
+    case TATVA_TRI3: k_interpolate<Tri3><<<grid, 128, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_points, n_points, d_out, d_elem); break;
+    case TATVA_QUAD4: k_interpolate<Quad4><<<grid, 128, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_points, n_points, d_out, d_elem); break;
+    case TATVA_TRI6: k_interpolate<Tri6><<<grid, 128, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_points, n_points, d_out, d_elem); break;
+    case TATVA_QUAD8: k_interpolate<Quad8><<<grid, 128, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_points, n_points, d_out, d_elem); break;
+    default: return TATVA_E_UNSUPPORTED;  // the reference's point search is two-dimensional (mesh.py:303)
+  }
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

@@ -266,6 +266,95 @@ class Operator:
 
         return _mapped
 
+    # -- post-processing: point evaluation and L2 projection --------------------------------------
+    def quads(self) -> torch.Tensor:
+        """Quadrature points in physical coordinates, (E, Q, dim) — operator.py:506-516."""
+        return self.eval(self.coords)
+
+    def interpolate(self, arg, points) -> torch.Tensor:
+        """Nodal values (N, *v) at physical points (P, 2) -> (P, *v) — operator.py:399-463.  The containing element is
+        found as mesh.find_containing_polygons does (mesh.py:294-388), the reference point by ONE Newton step from
+        the first quadrature point (exact for affine elements), all inside one kernel.  Raises RuntimeError if a
+        point lies outside the mesh, like the reference outside a trace."""
+        u = self._as_dev(arg)
+        pts = self._as_dev(points).contiguous()
+        if pts.ndim != 2 or pts.shape[1] != 2 or self.dim != 2 or self._line:
+            raise NotImplementedError("interpolate: plane elements and (P, 2) points, as in the reference (mesh.py:303)")
+        vshape = tuple(u.shape[1:])
+        u2 = u.reshape(self.n_nodes, -1).contiguous()
+        out = torch.empty((pts.shape[0], u2.shape[1]), dtype=torch.float64, device=self.device)
+        elem = torch.empty(pts.shape[0], dtype=torch.int32, device=self.device)
+        if pts.shape[0]:
+            self._call("tatva_op_interpolate", u2.data_ptr(), u2.shape[1], pts.data_ptr(), pts.shape[0], out.data_ptr(), elem.data_ptr())
+            if bool((elem < 0).any()):
+                raise RuntimeError("Some points are outside the mesh, revise the points")
+        return out.reshape((pts.shape[0],) + vshape)
+
+    def project(self, field, colored_matrix=None, lifter=None, *, tol: float = 1e-12, maxiter: int = 2000) -> torch.Tensor:
+        """L2 projection of a quadrature field (E, Q, *v) onto the nodal space, (N, *v) — operator.py:518-554,
+        utils.py:118-258: M x = b with M_ab = int N_a N_b, b_a = int N_a f.  The reference assembles M through
+        sparse.jacfwd and calls a direct sparse solve; here M is applied matrix-free (eval kernel, weights, eval-adjoint
+        kernel) inside the device-resident Jacobi-preconditioned CG, all components at once.  `colored_matrix` only
+        selects scalar (multi right-hand side) or coupled layout, which give the same nodal values; a `lifter` pins its
+        Fixed DOFs (utils.py:233-236, :193-201) — constraints that tie DOFs together are not supported here."""
+        from .solver import ConjugateGradient
+
+        f = self._as_dev(field)
+        if f.ndim < 2 or tuple(f.shape[:2]) != (self.n_elements, self.nq):
+            raise ValueError(f"field must be shaped (n_elements, n_quad, ...) = ({self.n_elements}, {self.nq}, ...)")
+        vshape = tuple(f.shape[2:])
+        K = int(np.prod(vshape)) if vshape else 1
+        if lifter is not None:
+            dim_s = max(int(lifter.size) // self.n_nodes, 1)
+        else:
+            dim_s = 1 if colored_matrix is None else max(int(colored_matrix.shape[0]) // self.n_nodes, 1)
+        if lifter is not None and colored_matrix is not None and colored_matrix.shape[0] != lifter.size_reduced:
+            raise ValueError(f"Colored matrix size does not match lifter reduced size. Expected {lifter.size_reduced}, got {colored_matrix.shape[0]}")
+        if dim_s > 1 and K != dim_s:
+            raise ValueError(f"a coupled projection with {dim_s} DOFs per node needs a field with {dim_s} components, got {K}")
+        W = self.get_integration_weights()
+        b = self._k_eval_adj((f.reshape(self.n_elements, self.nq, K) * W[:, :, None]).contiguous())  # (N, K)
+        # Jacobi: the consistent diagonal M_aa = sum_q W N_a^2 (the lumped mass of quadratic elements is not positive)
+        Nq = torch.as_tensor(np.stack([self.element.shape_function(xi) for xi in self.element.quad_points]), dtype=torch.float64, device=self.device)
+        diag = self._k_gather_adj(torch.einsum("eq,qn->en", W, Nq * Nq)[:, :, None].contiguous())  # (N, 1)
+        mask, shift = None, None
+        if lifter is not None:
+            want = self.n_nodes * dim_s
+            if lifter.size != want:
+                raise ValueError(f"lifter.size = {lifter.size}, expected {want}")
+            m = lifter.dof_map()
+            if (m >= 0).sum() != lifter.size_reduced or not np.array_equal(m[lifter.free_dofs], np.arange(lifter.size_reduced)):
+                raise NotImplementedError("project: only lifters made of Fixed constraints are supported")
+            free = torch.as_tensor(m >= 0, device=self.device)
+            const = torch.as_tensor(np.asarray(lifter.lift_from_zeros(np.zeros(lifter.size_reduced))), dtype=torch.float64, device=self.device)
+            if dim_s == 1:
+                mask, shift = free[:, None].expand(self.n_nodes, K), const[:, None].expand(self.n_nodes, K)
+            else:
+                mask, shift = free.reshape(self.n_nodes, K), const.reshape(self.n_nodes, K)
+            mask = mask.to(torch.float64).contiguous()
+        n = self.n_nodes * K
+
+        def matvec(x, out):
+            x2 = x.view(self.n_nodes, K)
+            if mask is not None:
+                x2 = x2 * mask
+            y = self._k_eval_adj((self._k_eval(x2.contiguous()) * W[:, :, None]).contiguous())
+            if mask is not None:
+                y = y * mask + x.view(self.n_nodes, K) * (1.0 - mask)  # identity on the pinned DOFs keeps the system SPD
+            out.copy_(y.reshape(-1))
+            return out
+
+        rhs = b if mask is None else b * mask
+        cg = ConjugateGradient(matvec, n, self.device, use_graph=False, jacobi=True)
+        cg.set_diagonal(diag.expand(self.n_nodes, K).contiguous().reshape(-1))
+        x, info = cg.solve(rhs.reshape(-1).contiguous(), tol=tol, maxiter=maxiter, check_every=5)
+        if not info["converged"]:
+            raise RuntimeError(f"project: CG did not converge ({info})")
+        x = x.view(self.n_nodes, K)
+        if mask is not None:
+            x = x * mask + shift * (1.0 - mask)
+        return x.reshape((self.n_nodes,) + vshape)
+
     # -- fused energy / residual / HVP -----------------------------------------------------------
     def _fused_shape(self, material, u):
         dpn = material.dofs_per_node(self.dim)

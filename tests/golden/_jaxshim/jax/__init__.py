@@ -7,7 +7,8 @@ tatva.sparse._coloring, tatva.compound, tatva.mpi) execute eagerly on NumPy so t
 tests/golden/make_golden.py can record their outputs as fixtures.  Nothing in the
 product package imports this.  Semantics reproduced: vmap == stack of per-item calls,
 lax.map == the same, jit == identity.  No autodiff (derivative goldens use the
-complex-step method on the reference's own energy instead).
+complex-step method on the reference's own energy instead); `jacrev` is the complex-step Jacobian with respect
+to the first argument, which is all Operator.interpolate asks of it (operator.py:419-421).
 """
 import numpy as _np
 
@@ -59,3 +60,29 @@ def vmap(fn, in_axes=0, out_axes=0):
         return _tree_stack(outs)
 
     return mapped
+
+
+def jacrev(fn, argnums=0):
+    """Complex-step Jacobian wrt argument `argnums` (exact to rounding for the polynomial shape functions)."""
+    if argnums != 0:
+        raise NotImplementedError("shim jacrev: argnums=0 only")
+
+    def jac(x, *rest):
+        x = _np.asarray(x, dtype=_np.float64)
+        h = 1e-30
+        cols = []
+        for j in range(x.size):
+            xp = x.astype(_np.complex128).ravel()
+            xp[j] += 1j * h
+            cols.append(_tree_map(lambda o: _np.imag(_np.asarray(o)) / h, fn(xp.reshape(x.shape), *rest)))
+        return _tree_map_stack_last(cols, x.shape)
+
+    return jac
+
+
+def _tree_map_stack_last(cols, xshape):
+    first = cols[0]
+    if isinstance(first, (tuple, list)):
+        return type(first)(_tree_map_stack_last([c[i] for c in cols], xshape) for i in range(len(first)))
+    st = _np.stack([_np.asarray(c) for c in cols], axis=-1)
+    return st.reshape(st.shape[:-1] + tuple(xshape))

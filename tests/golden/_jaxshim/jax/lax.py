@@ -11,3 +11,7 @@ def map(f, xs, batch_size=None):  # noqa: A001
         n = len(xs)
         items = [xs[i] for i in range(n)]
     return _tree_stack([f(it) for it in items])
+
+
+def cond(pred, true_fun, false_fun, *operands):
+    return true_fun(*operands) if bool(pred) else false_fun(*operands)

@@ -241,6 +241,35 @@ def line_fixtures(out):
         out[p + "int_quad_per_el"] = op.integrate_per_element(q)
 
 
+def interpolate_fixtures(out):
+    """Operator.interpolate (operator.py:399-463) and mesh.find_containing_polygons (mesh.py:294-388) on jittered
+    Tri3 and Quad4 meshes: interior points, points on shared edges and on mesh nodes, and points outside."""
+    from tatva.mesh import find_containing_polygons
+
+    rng = np.random.default_rng(23)
+    for kind, cls in {"tri3": element.Tri3, "quad4": element.Quad4}.items():
+        if kind == "tri3":
+            c, el = orc.mesh_unit_square_tri(5, 4)
+        else:
+            c, el = orc.mesh_unit_square_quad(4, 5)
+        interior = (c[:, 0] > 1e-9) & (c[:, 0] < 1 - 1e-9) & (c[:, 1] > 1e-9) & (c[:, 1] < 1 - 1e-9)
+        c = c + 0.04 * rng.uniform(-1, 1, c.shape) * interior[:, None]
+        pts = rng.uniform(0.02, 0.98, size=(40, 2))
+        edge_mid = 0.5 * (c[el[::3, 0]] + c[el[::3, 1]])  # on an edge shared by two elements
+        nodes = c[[0, 7, len(c) - 1]]
+        inside = np.concatenate([pts, edge_mid, nodes])
+        outside = np.array([[1.5, 0.5], [-0.2, 0.3], [0.5, 1.0001]])
+        u = rng.normal(size=(c.shape[0], 3))
+        s = rng.normal(size=(c.shape[0],))
+        p = f"interp_{kind}_"
+        out[p + "coords"], out[p + "conn"], out[p + "u"], out[p + "s"] = c, el, u, s
+        out[p + "points"], out[p + "outside"] = inside, outside
+        out[p + "containing"] = np.asarray(find_containing_polygons(np.concatenate([inside, outside]), c[el]))
+        op = Operator(Mesh(coords=c, elements=el), cls())
+        out[p + "values_u"] = np.asarray(op.interpolate(u, inside))
+        out[p + "values_s"] = np.asarray(op.interpolate(s, inside))
+
+
 def sparse_fixtures(out):
     cases = {
         "tri3_8x8_d2": (orc.mesh_unit_square_tri(8, 8), 2),  # tests/test_sparse.py:40-45
@@ -289,6 +318,7 @@ def main():
     sparse_fixtures(out)
     partition_fixtures(out)
     line_fixtures(out)
+    interpolate_fixtures(out)
     try:
         from _fakempi_golden import mpi_fixtures  # type: ignore
 

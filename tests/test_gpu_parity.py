@@ -295,7 +295,7 @@ def test_line_elements_on_a_curved_boundary(golden, kind, variant):
     _assert_close(G, orc.op_grad(kind, cc, ee, uu))
     _assert_close(op2.get_integration_weights(), orc.op_integration_weights(kind, cc, ee))
     gq = torch.as_tensor(rng.normal(size=tuple(G.shape)), device="cuda")
-    ut = torch.as_tensor(uu, device="cuda", requires_grad=True)
+    ut = torch.tensor(uu, device="cuda", requires_grad=True)
     (op2.grad(ut) * gq).sum().backward()
     ref_adj = np.zeros_like(uu)
     dNdX, _ = orc.geometry(kind, cc, ee)
@@ -303,7 +303,7 @@ def test_line_elements_on_a_curved_boundary(golden, kind, variant):
     _assert_close(ut.grad, ref_adj)
     # traction work W(u) = int t . u ds  ->  dW/du = consistent nodal forces; they sum to t * length
     trac = torch.tensor([0.3, -1.1, 0.7], dtype=torch.float64, device="cuda")
-    ut = torch.as_tensor(uu, device="cuda", requires_grad=True)
+    ut = torch.tensor(uu, device="cuda", requires_grad=True)
     op2.integrate((op2.eval(ut) * trac).sum(-1)).backward()
     length = float(op2.get_integration_weights().sum())
     np.testing.assert_allclose(ut.grad.sum(0).cpu().numpy(), trac.cpu().numpy() * length, rtol=1e-12)
@@ -317,6 +317,127 @@ def test_line_element_needs_plane_coordinates():
         tatva_b200.Operator(tatva_b200.Mesh(coords=np.zeros((3, 3)), elements=np.array([[0, 1]], dtype=np.int32)), element.Line2())
     with pytest.raises(ValueError):
         tatva_b200.Operator(tatva_b200.Mesh(coords=np.random.default_rng(0).normal(size=(4, 3)), elements=np.array([[0, 1, 2]], dtype=np.int32)), element.Tri3())
+
+
+@pytest.mark.parametrize("kind", ["tri3", "quad4"])
+def test_interpolate_matches_reference(golden, kind):
+    """Operator.interpolate against the reference's outputs (operator.py:399-463; tests/test_operator.py:145-166):
+    interior points, points on shared edges and nodes (first containing element wins), points outside."""
+    from tatva_b200 import element
+    import tatva_b200
+
+    g = lambda k: golden[f"interp_{kind}_{k}"]  # noqa: E731
+    c, el = g("coords"), g("conn")
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), {"tri3": element.Tri3, "quad4": element.Quad4}[kind]())
+    _assert_close(op.interpolate(g("u"), g("points")), g("values_u"))
+    _assert_close(op.interpolate(g("s"), g("points")), g("values_s"))
+    with pytest.raises(RuntimeError):
+        op.interpolate(g("s"), g("outside"))
+    # the element index the kernel reports == mesh.find_containing_polygons of the reference, outside points included
+    allp = torch.as_tensor(np.concatenate([g("points"), g("outside")]), device="cuda")
+    out = torch.empty((allp.shape[0], 1), dtype=torch.float64, device="cuda")
+    elem = torch.empty(allp.shape[0], dtype=torch.int32, device="cuda")
+    op._call("tatva_op_interpolate", torch.as_tensor(g("s"), device="cuda").data_ptr(), 1, allp.data_ptr(), allp.shape[0], out.data_ptr(), elem.data_ptr())
+    np.testing.assert_array_equal(elem.cpu().numpy(), g("containing"))
+    assert bool(torch.isnan(out[-3:]).all())
+    # at scale against the oracle: many elements per point (several staging chunks), many points (several CTAs)
+    rng = np.random.default_rng(4)
+    cc, ee = (orc.mesh_unit_square_tri(24, 20) if kind == "tri3" else orc.mesh_unit_square_quad(21, 23))
+    inner = (cc[:, 0] > 1e-9) & (cc[:, 0] < 1 - 1e-9) & (cc[:, 1] > 1e-9) & (cc[:, 1] < 1 - 1e-9)
+    cc = cc + 0.01 * rng.uniform(-1, 1, cc.shape) * inner[:, None]
+    pts = rng.uniform(0, 1, size=(1000, 2))
+    uu = rng.normal(size=(cc.shape[0], 2, 2))
+    op2 = tatva_b200.Operator(tatva_b200.Mesh(coords=cc, elements=ee), {"tri3": element.Tri3, "quad4": element.Quad4}[kind]())
+    ref, idx = orc.op_interpolate(kind, cc, ee, uu, pts)
+    assert (idx >= 0).all()
+    got = op2.interpolate(uu, pts)
+    assert got.shape == (1000, 2, 2)
+    _assert_close(got, ref)
+
+
+def test_interpolate_known_answer_two_triangles():
+    """reference tests/test_operator.py:145-159."""
+    from tatva_b200 import element
+    import tatva_b200
+
+    nodes = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    tris = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=nodes, elements=tris), element.Tri3())
+    pts = np.array([[0.25, 0.25], [0.75, 0.25], [0.25, 0.75], [0.5, 0.5]])
+    np.testing.assert_allclose(op.interpolate(nodes.sum(axis=1), pts).cpu().numpy(), pts.sum(axis=1), rtol=1e-14)
+    with pytest.raises(RuntimeError):
+        op.interpolate(np.ones(4), np.array([[1.5, 0.5]]))
+
+
+@pytest.mark.parametrize("kind", ["quad4", "tri3", "tri6", "hex8"])
+def test_project_quadrature_fields(kind):
+    """Operator.project (operator.py:518-554): the reference's own tests (tests/test_operator_projection.py: linear
+    scalar / vector / tensor fields are reproduced on Quad4 2x2, with scalar, coupled and default matrices), and the
+    oracle's consistent mass matrix solved directly for a non-polynomial field."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    from tatva_b200 import element, sparse
+    from tatva_b200.lifter import Fixed, Lifter
+    import tatva_b200
+
+    rng = np.random.default_rng(9)
+    if kind == "quad4":
+        c, el = orc.mesh_unit_square_quad(2, 2)
+        cls = element.Quad4
+    elif kind == "tri3":
+        c, el = orc.mesh_unit_square_tri(6, 5)
+        cls = element.Tri3
+    elif kind == "tri6":
+        c, el = orc.mesh_second_order("tri6", 4, 3)
+        cls = element.Tri6
+    else:
+        c, el = orc.mesh_box_hex(3)
+        c = c + 0.03 * rng.uniform(-1, 1, c.shape)
+        cls = element.Hexahedron8
+    mesh = tatva_b200.Mesh(coords=c, elements=el)
+    op = tatva_b200.Operator(mesh, cls())
+    dim = c.shape[1]
+    qp = op.quads()
+    _assert_close(qp, orc.op_eval(kind, c, el, c))
+    cm1 = sparse.ColoredMatrix.from_csr(sparse.pattern_from_mesh(mesh, 1))
+    cmd = sparse.ColoredMatrix.from_csr(sparse.pattern_from_mesh(mesh, dim))
+    N = c.shape[0]
+    # linear fields are in the space: reproduced exactly
+    lin = qp[:, :, 0] + 2.0 * qp[:, :, 1]
+    for kw in (dict(colored_matrix=cm1), dict()):
+        got = op.project(lin, **kw)
+        assert got.shape == (N,)
+        np.testing.assert_allclose(got.cpu().numpy(), c[:, 0] + 2.0 * c[:, 1], atol=1e-10)
+    for cm in (cm1, cmd):
+        got = op.project(qp, cm)
+        assert got.shape == (N, dim)
+        np.testing.assert_allclose(got.cpu().numpy(), c, atol=1e-10)
+    T = torch.zeros(qp.shape[:2] + (2, 2), dtype=torch.float64, device="cuda")
+    T[:, :, 0, 0], T[:, :, 1, 1] = qp[:, :, 0], qp[:, :, 1]
+    got = op.project(T, cm1).cpu().numpy()
+    assert got.shape == (N, 2, 2)
+    np.testing.assert_allclose(got[:, 0, 0], c[:, 0], atol=1e-10)
+    np.testing.assert_allclose(got[:, 1, 1], c[:, 1], atol=1e-10)
+    np.testing.assert_allclose(got[:, 0, 1], 0.0, atol=1e-10)
+    # a field outside the space: consistent mass matrix of the oracle, direct solve
+    W = orc.op_integration_weights(kind, c, el)
+    Nq = np.stack([orc.shape_function(kind, x) for x in orc.quad_rule(kind)[0]])
+    Me = np.einsum("eq,qa,qb->eab", W, Nq, Nq)
+    npe = el.shape[1]
+    M = sps.coo_matrix((Me.ravel(), (np.repeat(el, npe, axis=1).ravel(), np.tile(el, (1, npe)).ravel())), shape=(N, N)).tocsc()
+    fq = np.sin(3 * qp.cpu().numpy()[:, :, 0]) * np.exp(qp.cpu().numpy()[:, :, 1])
+    bq = np.zeros(N)
+    np.add.at(bq, el, np.einsum("eq,qa->ea", W * fq, Nq))
+    ref = spla.spsolve(M, bq)
+    _assert_close(op.project(fq), ref, tol=1e-10)
+    # Fixed DOFs through a lifter (utils.py:193-201, :233-236): reduced system + lifted solution
+    fixed = np.where(c[:, 0] < 1e-9)[0]
+    lifter = Lifter(N, Fixed(fixed, 0.25))
+    free = lifter.free_dofs
+    xr = spla.spsolve(M[free][:, free].tocsc(), bq[free])
+    ref_l = np.full(N, 0.25)
+    ref_l[free] = xr
+    _assert_close(op.project(fq, lifter=lifter), ref_l, tol=1e-10)
 
 
 def test_tiled_tet4_kernels_match_oracle():

@@ -72,6 +72,29 @@ def test_operator_matches_reference(golden, kind):
     np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, g("quadvals")), g("int_quad_per_el"), **kw)
 
 
+@pytest.mark.parametrize("kind", ["tri3", "quad4"])
+def test_interpolate_and_point_location_match_reference(golden, kind):
+    """Operator.interpolate / find_containing_polygons (reference operator.py:399-463, mesh.py:294-388), including
+    points on shared edges, on nodes and outside the mesh."""
+    g = lambda k: golden[f"interp_{kind}_{k}"]  # noqa: E731
+    c, el = g("coords"), g("conn")
+    allp = np.concatenate([g("points"), g("outside")])
+    np.testing.assert_array_equal(orc.find_containing_polygons(allp, c[el]), g("containing"))
+    vals, idx = orc.op_interpolate(kind, c, el, g("u"), g("points"))
+    np.testing.assert_allclose(vals, g("values_u"), rtol=1e-12, atol=1e-13)
+    vals_s, _ = orc.op_interpolate(kind, c, el, g("s"), g("points"))
+    np.testing.assert_allclose(vals_s, g("values_s"), rtol=1e-12, atol=1e-13)
+    out, idx = orc.op_interpolate(kind, c, el, g("s"), g("outside"))
+    assert np.all(idx == -1) and np.all(np.isnan(out))
+    # reference tests/test_operator.py:145-159: a linear field is recovered on the two-triangle unit square
+    if kind == "tri3":
+        nodes = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+        tris = np.array([[0, 1, 2], [0, 2, 3]])
+        pts = np.array([[0.25, 0.25], [0.75, 0.25], [0.25, 0.75], [0.5, 0.5]])
+        got, _ = orc.op_interpolate("tri3", nodes, tris, nodes.sum(axis=1), pts)
+        np.testing.assert_allclose(got, pts.sum(axis=1))
+
+
 @pytest.mark.parametrize("kind", ["line2", "line3"])
 def test_line_operator_matches_reference(golden, kind):
     """Line2 / Line3 on a curved polyline: arc-length Jacobian and derivative (reference element/base.py:144-242)."""
