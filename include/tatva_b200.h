@@ -240,6 +240,15 @@ int tatva_pcg_start(double* d_p, const double* d_r, const double* d_minv, int64_
 int tatva_pcg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap,
                            const double* d_minv, int64_t n, double* d_partials, double* d_scalars,
                            tatva_stream_t stream);
+/* The CG iteration split at its two dot products, for a CG distributed over ranks (SURVEY.md section 8(e):
+ * "CG dot products: ncclAllReduce of 1-2 scalars"): the caller all-reduces d_scalars[1] after
+ * tatva_cg_dot(p, Ap, .., slot 1) and d_scalars[2] (and [4] with a preconditioner) after tatva_cg_update, then
+ * calls tatva_cg_direction; everything stays ordered on one stream.  d_minv may be NULL (no preconditioner).  */
+int tatva_cg_update(double* d_x, double* d_r, const double* d_p, const double* d_Ap,
+                    const double* d_minv, int64_t n, double* d_partials, double* d_scalars,
+                    tatva_stream_t stream);
+int tatva_cg_direction(double* d_p, const double* d_r, const double* d_minv, int64_t n,
+                       double* d_scalars, tatva_stream_t stream);
 
 /* ---- host-side setup (C++, no GPU needed) -----------------------------------------------
  * pattern_from_mesh / _create_sparse_structure (tatva/sparse/_extraction.py:37-102):

@@ -60,6 +60,8 @@ SIGNATURES = {
     "tatva_reduce_adjoint": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_cg_dot": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp]),
     "tatva_cg_after_matvec": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "tatva_cg_update": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "tatva_cg_direction": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_pcg_reciprocal": (C.c_int, [vp, C.c_int64, vp, vp]),
     "tatva_pcg_start": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
     "tatva_pcg_after_matvec": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),

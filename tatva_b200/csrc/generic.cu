@@ -1972,6 +1972,35 @@ int tatva_pcg_after_matvec(double* d_x, double* d_r, double* d_p, const double* 
   return TATVA_OK;
 }
 
+// The same iteration split at its two dot products, for a distributed CG: the caller all-reduces d_scalars[1] after
+// tatva_cg_dot(p, Ap, slot 1) and d_scalars[2] after tatva_cg_update, on the same stream, then calls
+// tatva_cg_direction.  d_minv may be NULL (plain CG); with d_minv, s[0]/s[2] hold r.z and s[4] holds r.r.
+int tatva_cg_update(double* d_x, double* d_r, const double* d_p, const double* d_Ap, const double* d_minv, int64_t n,
+                    double* d_partials, double* d_scalars, tatva_stream_t stream) {
+  if (!d_x || !d_r || !d_p || !d_Ap || !d_partials || !d_scalars || n <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_minv) {
+    k_pcg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, d_minv, n, d_scalars, d_partials);
+    k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 2);
+    k_cg_finish<<<1, 256, 0, st>>>(d_partials + kCgBlocks, kCgBlocks, d_scalars, 4);
+  } else {
+    k_cg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, n, d_scalars, d_partials);
+    k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 2);
+  }
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+int tatva_cg_direction(double* d_p, const double* d_r, const double* d_minv, int64_t n, double* d_scalars,
+                       tatva_stream_t stream) {
+  if (!d_p || !d_r || !d_scalars || n <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_minv) k_pcg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, d_minv, n, d_scalars);
+  else k_cg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, n, d_scalars);
+  k_cg_roll<<<1, 1, 0, st>>>(d_scalars);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
 int tatva_fp64_peak_tflops(double* tflops, tatva_stream_t stream) {
   if (!tflops) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;

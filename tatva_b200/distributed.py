@@ -246,6 +246,21 @@ class PartitionedOperator:
             y_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
         return self._apply("tatva_hvp_elems", u_local, v_local, y_local)
 
+    def hessian_diagonal(self, u_local: torch.Tensor, d_local: torch.Tensor | None = None) -> torch.Tensor:
+        """diag H(u) assembled on the owned DOFs (Jacobi preconditioner of the distributed CG): element kernel on the
+        local mesh, then the reverse halo add.  `u_local` holds its ghost values."""
+        peer = self.halo == "peer" and self.comm.size > 1
+        if d_local is None:
+            d_local = self.new_symmetric_vector() if peer else self.new_local_vector()
+        self.op.hessian_diagonal(self.material, u_local, out=d_local)
+        if self.comm.size > 1:
+            if peer:
+                self._peer(d_local)[1].barrier(channel=0)  # every rank has zeroed and filled its own rows
+                self._peer_push(d_local)
+            else:
+                self._exchange(self.plan._rev, d_local, d_local, add=True)
+        return d_local
+
     def residual(self, u_local: torch.Tensor, r_local: torch.Tensor | None = None) -> torch.Tensor:
         if r_local is None:
             r_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)

@@ -26,7 +26,7 @@ from .element import Element
 from .mesh import Mesh
 
 
-_FUSED_CALLS = {"tatva_energy", "tatva_residual", "tatva_hvp", "tatva_csr_assemble", "tatva_csr_assemble_sym", "tatva_csr_assemble_rows"}
+_FUSED_CALLS = {"tatva_energy", "tatva_residual", "tatva_hvp", "tatva_hvp_lifted", "tatva_hessian_diag", "tatva_csr_assemble", "tatva_csr_assemble_sym", "tatva_csr_assemble_rows"}
 
 
 def _stream() -> int:
@@ -296,7 +296,9 @@ class Operator:
         sparse.jacfwd and calls a direct sparse solve; here M is applied matrix-free (eval kernel, weights, eval-adjoint
         kernel) inside the device-resident Jacobi-preconditioned CG, all components at once.  `colored_matrix` only
         selects scalar (multi right-hand side) or coupled layout, which give the same nodal values; a `lifter` pins its
-        Fixed DOFs (utils.py:233-236, :193-201) — constraints that tie DOFs together are not supported here."""
+        Fixed DOFs (utils.py:233-236, :193-201) — constraints that tie DOFs together are not supported here.  As in the
+        reference, M is integrated with the element's own rule: rules that under-integrate N_a N_b (the one-point
+        Tri3 / Tetrahedron4 rules) give a singular M."""
         from .solver import ConjugateGradient
 
         f = self._as_dev(field)

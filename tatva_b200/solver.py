@@ -117,6 +117,97 @@ class ConjugateGradient:
             return self.x.clone(), dict(iterations=it, residual_norm=math.sqrt(max(rr, 0.0)), converged=math.isfinite(rr) and math.sqrt(rr) <= tol * math.sqrt(bb))
 
 
+class DistributedConjugateGradient:
+    """CG over the ranks of a `PartitionedOperator`: A = H(u) restricted to the DOFs that are not pinned, every rank
+    holding its owned block.  Per iteration: one distributed HVP (halo exchange inside) and two one-scalar
+    all-reduces on the device; nothing returns to the host except the residual norm every
+    `check_every` iterations, which is identical on all ranks, so they stop together.
+
+    `pinned_owned`: bool mask (n_owned) of Dirichlet DOFs (their solution entries stay 0, like the homogeneous lift).
+    """
+
+    def __init__(self, pop, pinned_owned=None, jacobi_diagonal=None):
+        import torch.distributed as dist
+
+        self.pop, self.dist = pop, dist
+        dev, n = pop.device, pop.n_owned
+        self.n, self.device = n, dev
+        mk = lambda m: torch.zeros(m, dtype=torch.float64, device=dev)  # noqa: E731
+        peer = pop.halo == "peer" and pop.comm.size > 1
+        # p and Ap are LOCAL vectors (owned + ghosts): the operator refreshes the ghosts of p and assembles Ap
+        self.p = pop.new_symmetric_vector() if peer else pop.new_local_vector()
+        self.Ap = pop.new_symmetric_vector() if peer else pop.new_local_vector()
+        self.x, self.r = mk(n), mk(n)
+        self.scalars, self.partials = mk(8), mk(2 * 1184)
+        self.free = None if pinned_owned is None else (~torch.as_tensor(pinned_owned, device=dev).bool()).to(torch.float64)
+        self.minv = None
+        if jacobi_diagonal is not None:
+            self.minv = mk(n)
+            _lib.check(_lib.lib().tatva_pcg_reciprocal(jacobi_diagonal.contiguous().data_ptr(), n, self.minv.data_ptr(), self._stream()), "tatva_pcg_reciprocal")
+        self._L = _lib.lib()
+        self.u_local = None
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _allreduce(self, lo, hi):
+        if self.pop.comm.size > 1:
+            self.dist.all_reduce(self.scalars[lo:hi], group=self.pop.comm.group)
+
+    def set_state(self, u_local: torch.Tensor):
+        """`u_local`: the state with its ghost values in place (PartitionedOperator.fill_ghosts)."""
+        self.u_local = u_local
+
+    def _matvec(self):
+        self.pop.hvp(self.u_local, self.p, self.Ap)
+        if self.free is not None:
+            self.Ap[: self.n].mul_(self.free)
+
+    def solve(self, b_owned: torch.Tensor, tol: float = 1e-10, maxiter: int = 1000, check_every: int = 10):
+        L, n, s = self._L, self.n, self.scalars
+        mv = self.minv.data_ptr() if self.minv is not None else None
+        rr_slot = 4 if self.minv is not None else 0
+        with torch.cuda.device(self.device):
+            self.x.zero_()
+            self.r.copy_(b_owned)
+            if self.free is not None:
+                self.r.mul_(self.free)
+            st = self._stream()
+            _lib.check(L.tatva_cg_dot(self.r.data_ptr(), self.r.data_ptr(), n, self.partials.data_ptr(), s.data_ptr(), 5, st), "tatva_cg_dot")
+            self._allreduce(5, 6)  # slot 5 = b.b (global)
+            s[3:4].zero_()
+            self.p.zero_()
+            if self.minv is not None:
+                _lib.check(L.tatva_pcg_start(self.p.data_ptr(), self.r.data_ptr(), mv, n, self.partials.data_ptr(), s.data_ptr(), st), "tatva_pcg_start")
+                self._allreduce(0, 1)
+                s[4:5].copy_(s[5:6])
+            else:
+                self.p[:n].copy_(self.r)
+                s[0:1].copy_(s[5:6])
+            bb = float(s[5])
+            if bb == 0.0:
+                return self.x.clone(), dict(iterations=0, residual_norm=0.0, converged=True)
+            it, rr = 0, bb
+            while it < maxiter:
+                for _ in range(min(check_every, maxiter - it)):
+                    self._matvec()
+                    st = self._stream()
+                    _lib.check(L.tatva_cg_dot(self.p.data_ptr(), self.Ap.data_ptr(), n, self.partials.data_ptr(), s.data_ptr(), 1, st), "tatva_cg_dot")
+                    self._allreduce(1, 2)
+                    _lib.check(L.tatva_cg_update(self.x.data_ptr(), self.r.data_ptr(), self.p.data_ptr(), self.Ap.data_ptr(), mv, n, self.partials.data_ptr(), s.data_ptr(), st), "tatva_cg_update")
+                    if self.minv is not None:
+                        self._allreduce(2, 5)  # r.z (slot 2) and r.r (slot 4) in one call; slot 3 is kept at 0
+                    else:
+                        self._allreduce(2, 3)
+                    _lib.check(L.tatva_cg_direction(self.p.data_ptr(), self.r.data_ptr(), mv, n, s.data_ptr(), st), "tatva_cg_direction")
+                    it += 1
+                rr = float(s[rr_slot])
+                if not math.isfinite(rr) or math.sqrt(rr) <= tol * math.sqrt(bb):
+                    break
+            ok = math.isfinite(rr) and math.sqrt(rr) <= tol * math.sqrt(bb)
+            return self.x.clone(), dict(iterations=it, residual_norm=math.sqrt(max(rr, 0.0)), converged=ok)
+
+
 class ReducedOperator:
     """The constrained tangent and residual of E(u) on the free DOFs of a Lifter:
         r_red(u_red) = reduce_adjoint(dE/du(lift(u_red))),    K_red v = reduce_adjoint(H(lift(u_red)) lift_0(v)),

@@ -59,6 +59,46 @@ for overlap, halo in [(o, h) for h in HALOS for o in (False, True)]:
     e2 = np.abs(r[: pop.n_owned].cpu().numpy().reshape(-1, 3) - ref_res[l2g[:no]]).max() / np.abs(ref_res).max()
     out[f"halo={halo},overlap={overlap}"] = {"hvp_rel_err": float(e1), "residual_rel_err": float(e2), "n_boundary": pop.n_boundary, "n_global": pop.n_global}
     assert e1 < 1e-12 and e2 < 1e-12, (rank, overlap, e1, e2)
+# ---- distributed CG (plain and Jacobi) on the free DOFs == single-GPU CG on the global mesh ----
+# ("CG dot products: ncclAllReduce of 1-2 scalars"; uses the last pop: halo=HALOS[-1], overlap on)
+from tatva_b200.solver import ConjugateGradient, DistributedConjugateGradient
+nz0 = (shape[0] + 1) * (shape[1] + 1)  # global node ids of the z = 0 layer come first
+g_pinned = np.zeros(gc.shape, dtype=bool)
+g_pinned[:nz0] = True
+gus = 0.02 * gu  # small strains: SPD tangent
+gb = np.random.default_rng(21).normal(size=gc.shape)
+gfree = torch.as_tensor((~g_pinned).ravel(), device=dev).to(torch.float64)
+gu_t = torch.as_tensor(gus.ravel(), device=dev)
+tmp = torch.empty_like(gu_t)
+
+
+def g_matvec(p, o):
+    gop._raw_hvp(mat, gu_t, p, out=tmp)
+    torch.mul(tmp, gfree, out=o)
+    return o
+
+
+gcg = ConjugateGradient(g_matvec, gc.size, dev, use_graph=False)
+x_ref, ginfo = gcg.solve(torch.as_tensor(gb.ravel(), device=dev) * gfree, tol=1e-11, maxiter=5000, check_every=10)
+x_ref = x_ref.cpu().numpy().reshape(-1, 3)
+peer = pop.halo == "peer"
+us = pop.new_symmetric_vector() if peer else pop.new_local_vector()
+us.copy_(torch.as_tensor(gus[l2g].ravel(), device=dev))
+pinned_owned = g_pinned[l2g[:no]].ravel()
+b_owned = torch.as_tensor(gb[l2g[:no]].ravel(), device=dev)
+for jac in (False, True):
+    diag = pop.hessian_diagonal(us)[: pop.n_owned].clone() if jac else None
+    if jac:  # the assembled diagonal == the single-GPU one
+        gd = gop.hessian_diagonal(mat, gu_t.view(-1, 3)).cpu().numpy()
+        ed = np.abs(diag.cpu().numpy().reshape(-1, 3) - gd[l2g[:no]]).max() / np.abs(gd).max()
+        assert ed < 1e-12, (rank, ed)
+        out["hessian_diag_rel_err"] = float(ed)
+    dcg = DistributedConjugateGradient(pop, pinned_owned=pinned_owned, jacobi_diagonal=diag)
+    dcg.set_state(us)
+    x_own, dinfo = dcg.solve(b_owned, tol=1e-11, maxiter=5000, check_every=10)
+    ex = np.abs(x_own.cpu().numpy().reshape(-1, 3) - x_ref[l2g[:no]]).max() / np.abs(x_ref).max()
+    assert dinfo["converged"] and ex < 1e-8, (rank, jac, dinfo, ex)
+    out[f"distributed_cg_jacobi={jac}"] = {"rel_err_vs_single_gpu": float(ex), "iterations": dinfo["iterations"], "single_gpu_iterations": ginfo["iterations"]}
 # ---- public plan API on CUDA tensors across ranks (reference call stack mpi.py:372-409, :479-516, :609-711) ----
 from tatva_b200.mpi import AllreducePlan
 mesh, info = structured_hex_block(n, grid, rank)

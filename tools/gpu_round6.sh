@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/bench_secondary.py tet4 2>&1 | grep csr
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log

@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/bench_secondary.py tet4,pf,tri3 2>&1 | grep kernel
+N=${1:-2}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 tools/dist_check.py 8 > gpurun_out/dist_check_$N.log 2>&1; echo "dist_check rc=$?"; tail -5 gpurun_out/dist_check_$N.log | cut -c1-1500
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -15 gpurun_out/pytest_gpu.log
