@@ -535,6 +535,24 @@ struct tatva_plan {
 
 namespace tatva {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember the opt-in per (call site, device), so a
+// process driving several GPUs configures the kernel on each of them.
+struct SmemOptIn {
+  bool done[64] = {};
+};
+template <class K>
+inline int opt_in_smem(K kernel, size_t bytes, SmemOptIn& flags) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && flags.done[dev]) return TATVA_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (tracked) flags.done[dev] = true;
+  return TATVA_OK;
+}
+
 inline int grid_for(int64_t n, int block = kBlock) { return (int)((n + block - 1) / block); }
 
 #define TATVA_CUDA_TRY(expr)                \

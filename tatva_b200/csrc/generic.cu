@@ -1272,16 +1272,12 @@ using namespace tatva;
 // staged kernels may need more than the default 48 KB of dynamic shared memory (opt-in, once per kernel)
 constexpr size_t kStageMax = 160 * 1024;
 template <class K>
-static int allow_big_smem(K kernel, bool& done) {
-  if (!done) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageMax));
-    done = true;
-  }
-  return TATVA_OK;
+static int allow_big_smem(K kernel, SmemOptIn& done) {
+  return opt_in_smem(kernel, kStageMax, done);
 }
 #define STAGED_OPT_IN(KERNEL)                                   \
   {                                                             \
-    static bool done_[8] = {false};                             \
+    static SmemOptIn done_[8];                                  \
     int rc_ = TATVA_OK;                                         \
     DISPATCH_ELEMENT(p, (rc_ = allow_big_smem(KERNEL<El>, done_[El::kind]))); \
     if (rc_ != TATVA_OK) return rc_;                            \
@@ -1446,7 +1442,7 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
   {                                                                                                              \
     constexpr int CH_ = El::nq * NV * El::gdim, S_ = CH_ | 1, SC_ = 32 * El::npe * NV + 16 * El::npe;              \
     constexpr size_t smem_ = (size_t)(kBlock / 32) * ((32 * S_ > SC_) ? 32 * S_ : SC_) * sizeof(double);         \
-    static bool done_ = false;                                                                                   \
+    static SmemOptIn done_;                                                                                      \
     rc = allow_big_smem(k_grad_adjoint_acc<El, NV>, done_);                                                      \
     if (rc == TATVA_OK)                                                                                          \
       k_grad_adjoint_acc<El, NV><<<grid_for(p->n_elems), kBlock, smem_, st>>>(p->coords, p->conn, p->n_elems, d_g, d_y); \
@@ -1753,11 +1749,11 @@ static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int3
     if (p->variant != TATVA_VARIANT_GENERIC) {
       constexpr int S = El::npe * Mat::dpn * Mat::dpn, NB = El::npe * Mat::dpn;
       constexpr size_t smem = (size_t)(kBlock / 32) * 32 * (S + NB / 2 + 1) * sizeof(double);
-      static bool configured = false;
-      if (!configured && smem > 48 * 1024) {
-        TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_grouped<El, Mat, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_grouped<El, Mat, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+      static SmemOptIn full, sym;
+      if (smem > 48 * 1024) {
+        int rc = opt_in_smem(k_csr_grouped<El, Mat, false>, smem, full);
+        if (rc == TATVA_OK) rc = opt_in_smem(k_csr_grouped<El, Mat, true>, smem, sym);
+        if (rc != TATVA_OK) return rc;
       }
       if (p->variant == 2 || indices == nullptr) {  // full assembly: every entry by REDs
         k_csr_grouped<El, Mat, false><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, indptr, pos, data);
@@ -1822,10 +1818,10 @@ static int launch_csr_rows(tatva_plan* p, const Mat& mat, const double* u, const
                            const int32_t* n2e_ptr, const int32_t* n2e, double* data, cudaStream_t st) {
   constexpr int warps = 4, SLAB = Mat::dpn * El::npe * Mat::dpn;
   constexpr size_t smem = (size_t)warps * 32 * (SLAB + El::npe / 2 + 1) * sizeof(double);
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_csr_rows<El, Mat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  static SmemOptIn configured;
+  if (smem > 48 * 1024) {
+    const int rc = opt_in_smem(k_csr_rows<El, Mat>, smem, configured);
+    if (rc != TATVA_OK) return rc;
   }
   const int grid = (int)((p->n_nodes + warps - 1) / warps);
   k_csr_rows<El, Mat><<<grid, warps * 32, smem, st>>>(p->coords, p->conn, p->n_nodes, mat, u, indptr, indices, n2e_ptr, n2e, data);

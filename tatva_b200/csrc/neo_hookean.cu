@@ -410,11 +410,10 @@ int launch_rolled(const tatva_plan* p, double mu, double lmbda, const double* u,
                   cudaStream_t st) {
   constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 2 : 3);
   constexpr size_t smem = (size_t)NS * 21 * kBlock * sizeof(double);
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG, UNROLL, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = true;
+  static SmemOptIn configured;
+  if (smem > 48 * 1024) {
+    const int rc = opt_in_smem(k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG, UNROLL, FOLD>, smem, configured);
+    if (rc != TATVA_OK) return rc;
   }
   k_hex8_nh_hvp_rolled<STAGE, MINB, DEBUG, UNROLL, FOLD><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu,
                                                                                lmbda, u, v, y);
@@ -1184,10 +1183,10 @@ template <int MINB, int STAGE, int GROUPED = 0>
 static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st) {
   constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * (32 * 24 + 16 * 8) : 0)) * sizeof(double);
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  static SmemOptIn configured;
+  if (smem > 48 * 1024) {
+    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED>, smem, configured);
+    if (rc != TATVA_OK) return rc;
   }
   k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
   return TATVA_OK;
@@ -1222,10 +1221,10 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
 int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v_red,
                              const int32_t* map, double* y_red, cudaStream_t st) {
   constexpr size_t smem = (size_t)42 * kBlock * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    TATVA_CUDA_TRY(cudaFuncSetAttribute(k_hex8_nh_hvp_v3<2, 1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  static SmemOptIn configured;
+  {
+    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<2, 1, 0, true>, smem, configured);
+    if (rc != TATVA_OK) return rc;
   }
   k_hex8_nh_hvp_v3<2, 1, 0, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v_red, y_red, map);
   TATVA_LAUNCH_CHECK();
@@ -1265,11 +1264,10 @@ int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const 
   const size_t scat = grouped_scatter_smem<4, 3>(kBlock / 32);
   const size_t smem = ((stage > scat ? stage : scat) + 15) / 16 * 16;
   if (smem > 200 * 1024) return TATVA_E_UNSUPPORTED;
-  static bool configured[2] = {false, false};
-  if (!configured[hvp] && smem > 48 * 1024) {
-    if (hvp) TATVA_CUDA_TRY(cudaFuncSetAttribute(k_tet4_nh_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    else TATVA_CUDA_TRY(cudaFuncSetAttribute(k_tet4_nh_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured[hvp] = true;
+  static SmemOptIn configured[2];
+  if (smem > 48 * 1024) {
+    const int rc = hvp ? opt_in_smem(k_tet4_nh_tiled<true>, 200 * 1024, configured[1]) : opt_in_smem(k_tet4_nh_tiled<false>, 200 * 1024, configured[0]);
+    if (rc != TATVA_OK) return rc;
   }
   const int grid = grid_for(p->n_elems);
   if (hvp) k_tet4_nh_tiled<true><<<grid, kBlock, smem, st>>>(p->coords, p->tile_ptr, p->tile_nodes, p->tile_conn, p->n_elems, p->tile_max_unique, mu, lmbda, u, v, y);
