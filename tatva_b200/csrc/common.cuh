@@ -192,6 +192,49 @@ struct Line3 {  // tatva/element/base.py:189-242; nodes (-1, 1, 0), 3-point Gaus
 };
 
 // ---------------------------------------------------------------------------------------------
+// Nodal row gather.  A node's W doubles are contiguous; fetching them with 16-byte loads where alignment allows
+// cuts the load instructions (and the L1 tag lookups of a scattered gather) from W to ceil(W/2).  Rows of 3 doubles
+// alternate between 16-byte aligned and 8-off, so each row is one aligned double2 plus one double, picked by the
+// parity of (node + base misalignment); no divergence, two selects per row.
+// MEASURED SLOWER on B200 and therefore off (r01: Hex8 HVP 0.490 vs 0.453 ms, Tri3 HVP 20.7 vs 16.7 us, Tet4 energy
+// 36.6 vs 32.8 us, Tet4 HVP unchanged): the gathers are latency- not instruction-bound and the extra selects and
+// address arithmetic cost more issue slots than the saved loads.  Kept behind the macro as a record of the experiment.
+// ---------------------------------------------------------------------------------------------
+#ifndef TATVA_WIDE_GATHER
+#define TATVA_WIDE_GATHER 0
+#endif
+
+template <int W>
+TATVA_D void load_row(const double* __restrict__ src, int64_t node, double (&dst)[W]) {
+#if TATVA_WIDE_GATHER
+  const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);  // base is 8 mod 16 (uniform)
+  if constexpr (W == 3) {
+    const int64_t o = node * 3;
+    const unsigned odd = ((unsigned)node + mis) & 1u;  // row start is 8 mod 16
+    const double2 v = __ldg(reinterpret_cast<const double2*>(src + o + odd));
+    const double s = __ldg(src + o + (odd ? 0 : 2));
+    dst[0] = odd ? s : v.x;
+    dst[1] = odd ? v.x : v.y;
+    dst[2] = odd ? v.y : s;
+    return;
+  } else if constexpr (W == 2 || W == 4) {
+    if (!mis) {
+      const double2* q = reinterpret_cast<const double2*>(src + node * W);
+#pragma unroll
+      for (int k = 0; k < W / 2; ++k) {
+        const double2 v = __ldg(q + k);
+        dst[2 * k] = v.x;
+        dst[2 * k + 1] = v.y;
+      }
+      return;
+    }
+  }
+#endif
+#pragma unroll
+  for (int c = 0; c < W; ++c) dst[c] = __ldg(src + node * W + c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // d x d determinant / inverse (closed form; reference uses jnp.linalg.det / inv on J,
 // tatva/element/base.py:92, :113)
 // ---------------------------------------------------------------------------------------------

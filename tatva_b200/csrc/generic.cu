@@ -31,9 +31,7 @@ TATVA_D void load_conn(const int32_t* __restrict__ conn, int64_t e, int (&nd)[El
 template <int NPE, int W>
 TATVA_D void gather_rows(const double* __restrict__ src, const int (&nd)[NPE], double (&dst)[NPE][W]) {
 #pragma unroll
-  for (int n = 0; n < NPE; ++n)
-#pragma unroll
-    for (int c = 0; c < W; ++c) dst[n][c] = __ldg(src + (int64_t)nd[n] * W + c);
+  for (int n = 0; n < NPE; ++n) load_row<W>(src, nd[n], dst[n]);
 }
 
 // ---- Operator building blocks (runtime number of value components) -----------------------------
