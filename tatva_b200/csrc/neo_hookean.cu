@@ -1185,6 +1185,63 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_ref(const double* __restrict
 
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant with the connectivity prefetched one element ahead.  The one-point Tet4 kernels are latency
+// bound (two dependent trips to memory per element: connectivity, then the nodal rows; ~300 FP64 instructions in
+// between do not cover them).  Here every warp walks a strided list of 32-element groups and loads the NEXT group's
+// connectivity before gathering the current one, so an element costs one trip instead of two.
+// ---------------------------------------------------------------------------------------------
+template <bool HVP>
+__global__ void __launch_bounds__(kBlock) k_tet4_nh_pipe(const double* __restrict__ coords,
+                                                         const int32_t* __restrict__ conn, int64_t E, double mu,
+                                                         double lmbda, const double* __restrict__ u,
+                                                         const double* __restrict__ v, double* __restrict__ y) {
+  extern __shared__ double sm[];
+  double* wsm = sm + (size_t)(threadIdx.x >> 5) * (32 * 12 + 16 * 4);
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // elements per sweep, a multiple of 32
+  int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  if (base >= E) return;  // whole warp
+  const int4* c4 = reinterpret_cast<const int4*>(conn);
+  const double mu_s = mu * (1.0 / 6.0), lm_s = lmbda * (1.0 / 6.0);
+  int4 next = __ldg(c4 + ((base + lane < E) ? base + lane : E - 1));
+#pragma unroll 1
+  for (; base < E; base += stride) {
+    const bool valid = base + lane < E;
+    const int4 t = next;
+    const int64_t nb = base + stride;
+    if (nb < E) next = __ldg(c4 + ((nb + lane < E) ? nb + lane : E - 1));
+    int nd[4] = {t.x, t.y, t.z, t.w};
+    double X[4][3], U[4][3], V[4][3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      load_row<3>(coords, nd[n], X[n]);
+      load_row<3>(u, nd[n], U[n]);
+      if constexpr (HVP) load_row<3>(v, nd[n], V[n]);
+    }
+    double J[3][3], Fr[3][3], Gv[3][3], Q[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        J[d][c] = X[d + 1][c] - X[0][c];
+        Fr[c][d] = J[d][c] + (U[d + 1][c] - U[0][c]);
+        if constexpr (HVP) Gv[c][d] = V[d + 1][c] - V[0][c];
+      }
+    if constexpr (HVP) point_flux(J, Fr, Gv, mu_s, lm_s, Q);
+    else point_flux_residual(J, Fr, mu_s, lm_s, Q);
+    double Y[4][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      Y[1][i] = Q[i][0];
+      Y[2][i] = Q[i][1];
+      Y[3][i] = Q[i][2];
+      Y[0][i] = -(Q[i][0] + Q[i][1] + Q[i][2]);
+    }
+    grouped_scatter<4, 3>(y, nd, Y, valid, wsm);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tiled variant: one CTA = one tile of kBlock consecutive elements.  The tile's unique nodes (plan-time table)
 // are gathered ONCE, coalesced, into shared memory (coordinates, u, v: 9 doubles per node); elements then read
 // their nodal rows with LDS through tile-local uint16 connectivity.  On the 6-tets-per-cell box a tile touches
@@ -1326,14 +1383,51 @@ int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, 
   return TATVA_OK;
 }
 
+// persistent grid: as many CTAs as fit on the device at once (queried once per device)
+template <class K>
+static int resident_grid(K kernel, size_t smem, int64_t n_elems, int (&cache)[64], int* grid) {
+  int dev = 0;
+  TATVA_CUDA_TRY(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  int g = tracked ? cache[dev] : 0;
+  if (g == 0) {
+    int sms = 0, per_sm = 0;
+    TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TATVA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
+    g = sms * (per_sm > 0 ? per_sm : 1);
+    if (tracked) cache[dev] = g;
+  }
+  const int need = grid_for(n_elems);
+  *grid = g < need ? g : need;
+  return TATVA_OK;
+}
+
+static int tet4_nh_pipe(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y,
+                        cudaStream_t st) {
+  constexpr size_t smem = grouped_scatter_smem<4, 3>(kBlock / 32);
+  static int cache[2][64];
+  int grid = 0, rc;
+  if (hvp) {
+    if ((rc = resident_grid(k_tet4_nh_pipe<true>, smem, p->n_elems, cache[1], &grid)) != TATVA_OK) return rc;
+    k_tet4_nh_pipe<true><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  } else {
+    if ((rc = resident_grid(k_tet4_nh_pipe<false>, smem, p->n_elems, cache[0], &grid)) != TATVA_OK) return rc;
+    k_tet4_nh_pipe<false><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, nullptr, y);
+  }
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  if (p->variant == 30) return tet4_nh_pipe(p, true, mu, lmbda, u, v, y, st);
   k_tet4_nh_ref<true><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
 int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+  if (p->variant == 30) return tet4_nh_pipe(p, false, mu, lmbda, u, nullptr, y, st);
   k_tet4_nh_ref<false><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, nullptr, y);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
