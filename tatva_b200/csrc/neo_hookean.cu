@@ -1140,6 +1140,101 @@ TATVA_D void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3][
       Q[i][d] = fma(w1, Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d], w2 * Ac[d][i]);
 }
 
+// Hex8 residual with the structure of the v3 HVP kernel: raw (unnormalised) modal coefficients, the two Gauss points
+// of a tx pair evaluated together from shared partial sums, signs from the constant table, scalings folded into
+// mu/512 and lambda/512, and (STAGE) the modal coordinates parked in shared memory between iterations.
+template <int MINB, int STAGE>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_residual_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                          double lmbda, const double* __restrict__ u, double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  extern __shared__ double sm[];
+  double* sX0 = sm + threadIdx.x;
+  double hX[STAGE ? 1 : 3][7], hx[3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8], tX[7];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+      fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal_raw(fX, tX);
+    to_modal_raw(fu, hx[c]);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      hx[c][k] += tX[k];
+      if constexpr (STAGE) sX0[(c * 7 + k) * kBlock] = tX[k];
+      else hX[c][k] = tX[k];
+    }
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+
+#pragma unroll 1
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
+    int opaque = 0;
+    asm volatile("" : "+r"(opaque));
+    const double* sX = sX0 + opaque;
+    double Jm[3][3], Jp[3][3], Frm[3][3], Frp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double gm[3], gp[3];
+      if constexpr (STAGE) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sX[(c * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, gm, gp);
+      } else {
+        ref_grad8_pair(hX[c], sy, sz, gm, gp);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Jm[d][c] = gm[d];
+        Jp[d][c] = gp[d];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+    double Qm[3][3], Qp[3][3];
+    point_flux_residual(Jm, Frm, mu_s, lm_s, Qm);
+    point_flux_residual(Jp, Frp, mu_s, lm_s, Qp);
+    const double asz = kA * sz, asy = kA * sy;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double S0 = Qp[i][0] + Qm[i][0], S1 = Qp[i][1] + Qm[i][1], S2 = Qp[i][2] + Qm[i][2];
+      const double D1 = Qp[i][1] - Qm[i][1], D2 = Qp[i][2] - Qm[i][2];
+      R[i][0] += S0;
+      R[i][1] += S1;
+      R[i][2] += S2;
+      R[i][3] = fma(sy, S0, fma(kA, D1, R[i][3]));
+      R[i][4] = fma(sz, S1, fma(sy, S2, R[i][4]));
+      R[i][5] = fma(sz, S0, fma(kA, D2, R[i][5]));
+      R[i][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, R[i][6])));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal_raw(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
+}
+
 template <bool HVP>
 __global__ void __launch_bounds__(kBlock) k_tet4_nh_ref(const double* __restrict__ coords,
                                                         const int32_t* __restrict__ conn, int64_t E, double mu,
@@ -1372,7 +1467,15 @@ int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const
 
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
-  k_hex8_nh_residual_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y);
+  // variants (tatva_plan_set_variant), r01 at 128^3: 2 = first modal kernel, 8 rolled points (0.422 ms); 3 = pair
+  // kernel, all in registers (0.382); 4 = pair kernel, modal coordinates staged, 2 CTAs / SM (0.394);
+  // default = staged, 3 CTAs / SM (0.369)
+  switch (p->variant) {
+    case 2: k_hex8_nh_residual_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
+    case 3: k_hex8_nh_residual_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
+    case 4: k_hex8_nh_residual_v3<2, 1><<<grid_for(p->n_elems), kBlock, 21 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
+    default: k_hex8_nh_residual_v3<3, 1><<<grid_for(p->n_elems), kBlock, 21 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
+  }
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
