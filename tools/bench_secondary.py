@@ -179,6 +179,37 @@ if want("cg"):
         its[name] = dict(iterations=info["iterations"], converged=info["converged"], wall_s=round(time.perf_counter() - t0, 3))
     print(json.dumps(dict(kernel="cg_vs_pcg_to_1e-8_hex8_128", **its)), flush=True)
 
+# ---- post-processing and boundary elements: interpolate (point location), project (mass CG), Line2 traction ----
+if want("post"):
+    rng = np.random.default_rng(0)
+    m = Mesh.unit_square(256, 256)
+    op = tatva_b200.Operator(m, element.Tri3())
+    P = 100_000
+    pts = torch.as_tensor(rng.uniform(0.001, 0.999, size=(P, 2)), device="cuda")
+    un = torch.as_tensor(rng.normal(size=(m.coords.shape[0], 2)), device="cuda")
+    t0 = time.perf_counter()
+    op.interpolate(un, pts)
+    torch.cuda.synchronize()
+    ms = timeit(lambda: op.interpolate(un, pts), reps=5, warm=1)
+    report("tri3_interpolate_100k_points_c1", ms, 8 * (4 * P) + 8 * 4 * m.coords.shape[0] + 12 * m.elements.shape[0], P, "point", elements=int(m.elements.shape[0]))
+    mq = Mesh.unit_square(256, 256, type="quad")
+    cq = np.asarray(mq.coords)
+    opq = tatva_b200.Operator(mq, element.Quad4())
+    qp = opq.quads()
+    fq = torch.sin(3 * qp[:, :, 0]) * torch.exp(qp[:, :, 1])
+    t0 = time.perf_counter()
+    xq = opq.project(fq)
+    torch.cuda.synchronize()
+    t_proj = time.perf_counter() - t0
+    print(json.dumps(dict(kernel="quad4_project_scalar_256x256", wall_ms=round(1e3 * t_proj, 2), nodes=int(cq.shape[0]), max_abs_err_vs_field=float((xq - torch.sin(3 * torch.as_tensor(cq[:, 0], device="cuda")) * torch.exp(torch.as_tensor(cq[:, 1], device="cuda"))).abs().max()))), flush=True)
+    nb = 1_000_000
+    tt = np.linspace(0, 2 * np.pi, nb, endpoint=False)
+    cl = np.stack([np.cos(tt), np.sin(tt)], -1)
+    opl = tatva_b200.Operator(Mesh(coords=cl, elements=np.stack([np.arange(nb), (np.arange(nb) + 1) % nb], -1).astype(np.int32)), element.Line2())
+    ul = torch.as_tensor(rng.normal(size=(nb, 2)), device="cuda")
+    report("line2_grad_1M", timeit(lambda: opl._k_grad(ul)), 8 * (4 * nb + 2 * nb) + 8 * nb, nb, "qp")
+    report("line2_weights_1M", timeit(lambda: opl.get_integration_weights()), 8 * (2 * nb + nb) + 8 * nb, nb, "qp", length=float(opl.get_integration_weights().sum()))
+
 # ---- locality: the same Tet4 config-2 mesh with elements AND nodes randomly shuffled, then re-sorted ----
 if want("locality"):
     from tatva_b200.mesh import reorder_mesh
