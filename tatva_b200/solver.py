@@ -208,6 +208,41 @@ class DistributedConjugateGradient:
             return self.x.clone(), dict(iterations=it, residual_norm=math.sqrt(max(rr, 0.0)), converged=ok)
 
 
+def distributed_newton_solve(pop, u_local, pinned_owned=None, *, tol: float = 1e-8, max_newton: int = 20, cg_tol: float = 1e-10, cg_maxiter: int = 2000, jacobi: bool = False):
+    """Newton's method on E(u) over the ranks of a `PartitionedOperator`.  `u_local` (local vector: symmetric memory
+    for halo="peer") holds the initial state INCLUDING the prescribed values on the pinned DOFs, which stay fixed;
+    every linear solve is a `DistributedConjugateGradient` on the free DOFs.  Updates `u_local` in place and returns
+    (u_local, history); the residual norms are global (all-reduced), so every rank takes the same decisions."""
+    import torch.distributed as dist
+
+    n = pop.n_owned
+    dev = pop.device
+    peer = pop.halo == "peer" and pop.comm.size > 1
+    r_local = pop.new_symmetric_vector() if peer else pop.new_local_vector()
+    free = None if pinned_owned is None else (~torch.as_tensor(pinned_owned, device=dev).bool()).to(torch.float64)
+    history, r0 = [], None
+    cg = None
+    for k in range(max_newton):
+        pop.fill_ghosts(u_local)
+        pop.residual(u_local, r_local)
+        r = r_local[:n] * free if free is not None else r_local[:n].clone()
+        rr = (r * r).sum().reshape(1)
+        if pop.comm.size > 1:
+            dist.all_reduce(rr, group=pop.comm.group)
+        rn = math.sqrt(float(rr))
+        r0 = rn if r0 is None else r0
+        if rn <= tol * max(r0, 1e-300) or rn == 0.0:
+            history.append(dict(newton=k, residual_norm=rn, cg_iterations=0))
+            break
+        diag = pop.hessian_diagonal(u_local)[:n].clone() if jacobi else None
+        cg = DistributedConjugateGradient(pop, pinned_owned=pinned_owned, jacobi_diagonal=diag) if (cg is None or jacobi) else cg
+        cg.set_state(u_local)
+        du, info = cg.solve(-r, tol=cg_tol, maxiter=cg_maxiter)
+        history.append(dict(newton=k, residual_norm=rn, cg_iterations=info["iterations"], cg_converged=info["converged"]))
+        u_local[:n].add_(du)
+    return u_local, history
+
+
 class ReducedOperator:
     """The constrained tangent and residual of E(u) on the free DOFs of a Lifter:
         r_red(u_red) = reduce_adjoint(dE/du(lift(u_red))),    K_red v = reduce_adjoint(H(lift(u_red)) lift_0(v)),

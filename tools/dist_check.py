@@ -99,6 +99,24 @@ for jac in (False, True):
     ex = np.abs(x_own.cpu().numpy().reshape(-1, 3) - x_ref[l2g[:no]]).max() / np.abs(x_ref).max()
     assert dinfo["converged"] and ex < 1e-8, (rank, jac, dinfo, ex)
     out[f"distributed_cg_jacobi={jac}"] = {"rel_err_vs_single_gpu": float(ex), "iterations": dinfo["iterations"], "single_gpu_iterations": ginfo["iterations"]}
+# ---- distributed Newton: same minimiser as the single-GPU Newton with a Lifter on the global mesh ----
+from tatva_b200.solver import distributed_newton_solve, newton_solve
+from tatva_b200.lifter import Fixed, Lifter
+top = np.arange(gc.shape[0] - nz0, gc.shape[0])  # global node ids of the top layer
+glift = Lifter(gc.size, Fixed((np.arange(nz0)[:, None] * 3 + np.arange(3)).ravel(), 0.0), Fixed(top * 3 + 2, 0.03), Fixed((top[:, None] * 3 + np.arange(2)).ravel(), 0.0))
+u_red, ghist = newton_solve(gop, mat, glift, tol=1e-10, cg_tol=1e-12)
+u_glob = glift.lift_from_zeros(u_red).cpu().numpy().reshape(-1, 3)
+g_pin = np.zeros(gc.shape, dtype=bool)
+g_pin[:nz0] = True
+g_pin[top] = True
+g_init = np.zeros(gc.shape)
+g_init[top, 2] = 0.03
+un = pop.new_symmetric_vector() if peer else pop.new_local_vector()
+un.copy_(torch.as_tensor(g_init[l2g].ravel(), device=dev))
+un, dhist = distributed_newton_solve(pop, un, pinned_owned=g_pin[l2g[:no]].ravel(), tol=1e-10, cg_tol=1e-12)
+en = np.abs(un[: pop.n_owned].cpu().numpy().reshape(-1, 3) - u_glob[l2g[:no]]).max() / np.abs(u_glob).max()
+assert en < 1e-7, (rank, en, dhist)
+out["distributed_newton"] = {"rel_err_vs_single_gpu": float(en), "newton_steps": len(dhist), "single_gpu_newton_steps": len(ghist)}
 # ---- public plan API on CUDA tensors across ranks (reference call stack mpi.py:372-409, :479-516, :609-711) ----
 from tatva_b200.mpi import AllreducePlan
 mesh, info = structured_hex_block(n, grid, rank)
