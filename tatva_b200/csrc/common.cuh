@@ -526,29 +526,36 @@ struct NeoHookeanPhaseField {
 // Sector-grouped scatter-add of the per-element nodal contributions of one warp: the values are re-dealt
 // through shared memory so that consecutive lanes add the DPN consecutive doubles of one node (one 32-byte
 // sector per group instead of DPN separate ones; the L2 atomic units work per sector).  All 32 lanes must call.
+// doubles of shared memory per warp.  Per-lane row strides are ODD (values: S | 1 doubles, node ids: NPE | 1 ints) so
+// that the lane-strided staging stores are free of bank conflicts (an even stride such as 12 or 24 doubles puts
+// every 4th / 2nd lane on the same bank).
+template <int NPE, int DPN>
+constexpr int grouped_scatter_words() {
+  return 32 * ((NPE * DPN) | 1) + 16 * (NPE | 1);
+}
 template <int NPE, int DPN>
 TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const double (&Y)[NPE][DPN], bool valid,
                              double* warp_smem) {
-  constexpr int S = NPE * DPN;
+  constexpr int S = NPE * DPN, SP = S | 1, NP = NPE | 1;
   const int lane = threadIdx.x & 31;
-  int* snode = reinterpret_cast<int*>(warp_smem + 32 * S);
+  int* snode = reinterpret_cast<int*>(warp_smem + 32 * SP);
 #pragma unroll
   for (int n = 0; n < NPE; ++n) {
-    snode[lane * NPE + n] = valid ? nd[n] : -1;
+    snode[lane * NP + n] = valid ? nd[n] : -1;
 #pragma unroll
-    for (int c = 0; c < DPN; ++c) warp_smem[lane * S + n * DPN + c] = Y[n][c];
+    for (int c = 0; c < DPN; ++c) warp_smem[lane * SP + n * DPN + c] = Y[n][c];
   }
   __syncwarp();
   for (int t = lane; t < 32 * S; t += 32) {
     const int j = t / S, r = t - j * S;
-    const int node = snode[j * NPE + r / DPN];
-    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[t]);
+    const int node = snode[j * NP + r / DPN];
+    if (node >= 0) atomicAdd(y + (int64_t)node * DPN + (r % DPN), warp_smem[j * SP + r]);
   }
   __syncwarp();
 }
 template <int NPE, int DPN>
 constexpr size_t grouped_scatter_smem(int warps) {
-  return (size_t)warps * (32 * NPE * DPN + 16 * NPE) * sizeof(double);
+  return (size_t)warps * grouped_scatter_words<NPE, DPN>() * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------

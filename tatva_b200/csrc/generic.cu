@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __res
                                                              const double* __restrict__ g, double* __restrict__ y) {
   extern __shared__ double sm_stage[];
   constexpr int CH = El::nq * NV * El::gdim, S = CH | 1;
-  constexpr int SC = 32 * El::npe * NV + 16 * El::npe;  // grouped-scatter staging per warp
+  constexpr int SC = grouped_scatter_words<El::npe, NV>();  // grouped-scatter staging per warp
   constexpr int PER_WARP = (32 * S > SC) ? 32 * S : SC;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * PER_WARP;
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coo
     }
   }
   if constexpr (MODE != MODE_ENERGY) {
-    double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * (32 * El::npe * dpn + 16 * El::npe);
+    double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<El::npe, dpn>();
     grouped_scatter<El::npe, dpn>(y, nd, Y, e < E, wsm);
   }
   if constexpr (MODE == MODE_ENERGY) {
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(kBlock) k_hessian_diag(const double* __restric
       }
     }
   }
-  double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * (32 * El::npe * dpn + 16 * El::npe);
+  double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<El::npe, dpn>();
   grouped_scatter<El::npe, dpn>(diag, nd, Y, e < E, wsm);
 }
 
@@ -873,10 +873,11 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
                                                         const int32_t* __restrict__ pos, double* __restrict__ data) {
   static_assert(El::nq == 1, "grouped assembly is implemented for single-point elements");
   constexpr int dpn = Mat::dpn, npe = El::npe, S = npe * dpn * dpn, NB = npe * dpn;
+  constexpr int SP = S | 1, NBP = NB | 1;  // odd per-lane strides: conflict-free lane-strided stores
   extern __shared__ double sm_grp[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* sblk = sm_grp + (size_t)wib * 32 * (S + NB / 2 + 1);  // [32][S] values, then [32][NB] int32 bases
-  int* sbase = reinterpret_cast<int*>(sblk + 32 * S);
+  double* sblk = sm_grp + (size_t)wib * (32 * SP + 16 * NBP);  // [32][SP] values, then [32][NBP] int32 bases
+  int* sbase = reinterpret_cast<int*>(sblk + 32 * SP);
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = e < E;
   int nd[npe];
@@ -922,7 +923,7 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
 #pragma unroll
             for (int j = 0; j < El::dim; ++j) t += f.G[i][j] * dNdX[j][a];
             if (i >= Mat::val_lo) t += f.val[i] * N[a];
-            sblk[lane * S + (a * dpn + i) * dpn + k] = W * t;
+            sblk[lane * SP + (a * dpn + i) * dpn + k] = W * t;
           }
       }
       int nb_node = 0;  // nd[b] without dynamic indexing
@@ -934,17 +935,17 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
         const bool keep = !SYM || nd[a] <= nb_node;
         const int p = __ldg(pos + (e * npe + a) * npe + b);
 #pragma unroll
-        for (int i = 0; i < dpn; ++i) sbase[lane * NB + a * dpn + i] = keep ? __ldg(indptr + (int64_t)nd[a] * dpn + i) + p : -1;
+        for (int i = 0; i < dpn; ++i) sbase[lane * NBP + a * dpn + i] = keep ? __ldg(indptr + (int64_t)nd[a] * dpn + i) + p : -1;
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < NB; ++r) sbase[lane * NB + r] = -1;
+      for (int r = 0; r < NB; ++r) sbase[lane * NBP + r] = -1;
     }
     __syncwarp();
     for (int t = lane; t < 32 * S; t += 32) {
       const int j = t / S, r = t - j * S;
-      const int base = sbase[j * NB + r / dpn];
-      if (base >= 0) atomicAdd(data + (int64_t)base + (r % dpn), sblk[t]);
+      const int base = sbase[j * NBP + r / dpn];
+      if (base >= 0) atomicAdd(data + (int64_t)base + (r % dpn), sblk[j * SP + r]);
     }
     __syncwarp();
   }
@@ -1438,7 +1439,7 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
     int rc = TATVA_OK;
 #define ADJ_ACC(NV)                                                                                              \
   {                                                                                                              \
-    constexpr int CH_ = El::nq * NV * El::gdim, S_ = CH_ | 1, SC_ = 32 * El::npe * NV + 16 * El::npe;              \
+    constexpr int CH_ = El::nq * NV * El::gdim, S_ = CH_ | 1, SC_ = grouped_scatter_words<El::npe, NV>();            \
     constexpr size_t smem_ = (size_t)(kBlock / 32) * ((32 * S_ > SC_) ? 32 * S_ : SC_) * sizeof(double);         \
     static SmemOptIn done_;                                                                                      \
     rc = allow_big_smem(k_grad_adjoint_acc<El, NV>, done_);                                                      \
@@ -1746,7 +1747,7 @@ static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int3
   if constexpr (El::nq == 1) {
     if (p->variant != TATVA_VARIANT_GENERIC) {
       constexpr int S = El::npe * Mat::dpn * Mat::dpn, NB = El::npe * Mat::dpn;
-      constexpr size_t smem = (size_t)(kBlock / 32) * 32 * (S + NB / 2 + 1) * sizeof(double);
+      constexpr size_t smem = (size_t)(kBlock / 32) * (32 * (S | 1) + 16 * (NB | 1)) * sizeof(double);
       static SmemOptIn full, sym;
       if (smem > 48 * 1024) {
         int rc = opt_in_smem(k_csr_grouped<El, Mat, false>, smem, full);

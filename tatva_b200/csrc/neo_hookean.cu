@@ -902,23 +902,23 @@ __global__ void __launch_bounds__(kBlock, MINB)
   if constexpr (GROUPED) {
     // sector-grouped scatter: consecutive lanes add the 3 consecutive doubles of one node
     constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63);
-    double* wsm = sm + (size_t)NS * kBlock + (size_t)(threadIdx.x >> 5) * (32 * 24 + 16 * 8);
+    double* wsm = sm + (size_t)NS * kBlock + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<8, 3>();
     const int lane = threadIdx.x & 31;
-    int* snode = reinterpret_cast<int*>(wsm + 32 * 24);
+    int* snode = reinterpret_cast<int*>(wsm + 32 * 25);  // odd strides (25 doubles, 9 ints): conflict-free staging
 #pragma unroll
-    for (int n = 0; n < 8; ++n) snode[lane * 8 + n] = valid ? nd[n] : -1;
+    for (int n = 0; n < 8; ++n) snode[lane * 9 + n] = valid ? nd[n] : -1;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double f[8];
       from_modal_raw(R[i], f);
 #pragma unroll
-      for (int n = 0; n < 8; ++n) wsm[lane * 24 + n * 3 + i] = f[n];
+      for (int n = 0; n < 8; ++n) wsm[lane * 25 + n * 3 + i] = f[n];
     }
     __syncwarp();
     for (int t = lane; t < 32 * 24; t += 32) {
       const int j = t / 24, r = t - j * 24;
-      const int node = snode[j * 8 + r / 3];
-      if (node >= 0) atomicAdd(y + (int64_t)node * 3 + (r % 3), wsm[t]);
+      const int node = snode[j * 9 + r / 3];
+      if (node >= 0) atomicAdd(y + (int64_t)node * 3 + (r % 3), wsm[j * 25 + r]);
     }
   } else {
 #pragma unroll
@@ -1275,7 +1275,7 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_ref(const double* __restrict
     Y[3][i] = Q[i][2];
     Y[0][i] = -(Q[i][0] + Q[i][1] + Q[i][2]);
   }
-  grouped_scatter<4, 3>(y, nd, Y, valid, sm + (size_t)(threadIdx.x >> 5) * (32 * 12 + 16 * 4));
+  grouped_scatter<4, 3>(y, nd, Y, valid, sm + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<4, 3>());
 }
 
 
@@ -1291,7 +1291,7 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_pipe(const double* __restric
                                                          double lmbda, const double* __restrict__ u,
                                                          const double* __restrict__ v, double* __restrict__ y) {
   extern __shared__ double sm[];
-  double* wsm = sm + (size_t)(threadIdx.x >> 5) * (32 * 12 + 16 * 4);
+  double* wsm = sm + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<4, 3>();
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // elements per sweep, a multiple of 32
   int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
@@ -1407,7 +1407,7 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_tiled(const double* __restri
   }
   // tile-local accumulation is not needed for correctness: the sector-grouped REDs go straight to y
   __syncthreads();  // everybody is done with the staged inputs; reuse the buffer for the grouped scatter
-  grouped_scatter<4, 3>(y, nd, Y, valid, sm + (size_t)(threadIdx.x >> 5) * (32 * 12 + 16 * 4));
+  grouped_scatter<4, 3>(y, nd, Y, valid, sm + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<4, 3>());
 }
 
 }  // namespace
@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_tiled(const double* __restri
 template <int MINB, int STAGE, int GROUPED = 0, int WIDE = 0>
 static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st) {
-  constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * (32 * 24 + 16 * 8) : 0)) * sizeof(double);
+  constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * grouped_scatter_words<8, 3>() : 0)) * sizeof(double);
   static SmemOptIn configured;
   if (smem > 48 * 1024) {
     const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE>, smem, configured);
