@@ -252,6 +252,69 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __res
   grouped_scatter<El::npe, NV>(y, nd, Y, e < E, st);
 }
 
+// ---- one thread per (element, quadrature point) --------------------------------------------------------
+// The (E, Q, ...) outputs are flat in t = e * nq + q, so thread t owns CH contiguous doubles and a warp owns 32 * CH:
+// nq times more threads than element-per-thread (short dependent chains, full occupancy), the nq lanes of an
+// element gather the same node rows (L1 broadcast), and the staging buffer is 32 * CH doubles per warp instead of
+// 32 * nq * CH.  MEASURED SLOWER on B200 (r01, Hex8 64^3: grad 0.097 vs 0.086 ms, eval 0.038 vs 0.018, weights 0.026 vs
+// 0.016): the nq-fold repeated gathers cost more L1 wavefronts than the shorter chains save.  Kept as plan variant 3.
+template <class El>
+__global__ void __launch_bounds__(kBlock) k_weights_qp(const double* __restrict__ coords,
+                                                       const int32_t* __restrict__ conn, int64_t E,
+                                                       double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= E * El::nq) return;
+  const int64_t e = t / El::nq;
+  const int q = (int)(t - e * El::nq);
+  int nd[El::npe];
+  load_conn<El>(conn, e, nd);
+  double X[El::npe][El::dim];
+  gather_rows(coords, nd, X);
+  out[t] = det_jacobian<El>(q, X) * El::weight(q);
+}
+
+template <class El, bool GRAD>
+__global__ void __launch_bounds__(kBlock) k_field_qp(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                     int64_t E, const double* __restrict__ u, int nv,
+                                                     double* __restrict__ out) {
+  extern __shared__ double sm_stage[];
+  constexpr int G = GRAD ? El::gdim : 1;
+  const int CH = nv * G, S = CH | 1;
+  const int lane = threadIdx.x & 31;
+  double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
+  const int64_t T = E * El::nq;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) {
+    const int64_t e = t / El::nq;
+    const int q = (int)(t - e * El::nq);
+    int nd[El::npe];
+    load_conn<El>(conn, e, nd);
+    double B[G][El::npe];  // dNdX (GRAD) or N
+    if constexpr (GRAD) {
+      double X[El::npe][El::dim];
+      gather_rows(coords, nd, X);
+      geometry<El>(q, X, B);
+    } else {
+      El::N(q, B[0]);
+    }
+    for (int c = 0; c < nv; ++c) {
+      double ue[El::npe];
+#pragma unroll
+      for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < El::npe; ++n) acc += B[j][n] * ue[n];
+        st[lane * S + c * G + j] = acc;
+      }
+    }
+  }
+  __syncwarp();
+  const int64_t t0 = t - lane;
+  if (t0 < T) warp_block_store(out + t0 * CH, st, S, CH, (int)min((int64_t)32, T - t0));
+}
+
 template <class El>
 __global__ void __launch_bounds__(kBlock) k_eval_staged(const int32_t* __restrict__ conn, int64_t E,
                                                         const double* __restrict__ u, int nv, double* __restrict__ out) {
@@ -1409,6 +1472,11 @@ int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_str
     TATVA_CUDA_TRY(cudaMemcpyAsync(d_out, p->weights, sizeof(double) * p->n_elems * p->nq, cudaMemcpyDeviceToDevice, st));
     return TATVA_OK;
   }
+  if (p->nq > 1 && p->variant == 3) {  // thread per quadrature point: measured slower (see k_weights_qp)
+    DISPATCH_ELEMENT(p, (k_weights_qp<El><<<grid_for(p->n_elems * El::nq), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_out)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   DISPATCH_ELEMENT(p, (k_weights<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_out)));
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -1417,6 +1485,14 @@ int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_str
 int tatva_op_grad(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->nq > 1 && p->variant == 3) {  // one thread per quadrature point: measured slower, kept as variant 3
+    const size_t smem = (size_t)(kBlock / 32) * 32 * ((nv * p->gdim) | 1) * sizeof(double);
+    if (smem <= 48 * 1024) {
+      DISPATCH_ELEMENT(p, (k_field_qp<El, true><<<grid_for(p->n_elems * El::nq), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }
+  }
   {
     const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv * p->gdim) | 1) * sizeof(double);
     if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {
@@ -1474,6 +1550,14 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
 int tatva_op_eval(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->nq > 1 && p->variant == 3) {  // one thread per quadrature point: measured slower, kept as variant 3
+    const size_t smem = (size_t)(kBlock / 32) * 32 * (nv | 1) * sizeof(double);
+    if (smem <= 48 * 1024) {
+      DISPATCH_ELEMENT(p, (k_field_qp<El, false><<<grid_for(p->n_elems * El::nq), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }
+  }
   {
     const size_t smem = (size_t)(kBlock / 32) * 32 * ((p->nq * nv) | 1) * sizeof(double);
     if (smem <= kStageMax && p->variant != TATVA_VARIANT_GENERIC) {

@@ -115,16 +115,18 @@ if want("hex8"):
     report("hex8_nh_residual_c3", timeit(lambda: op._raw_residual(mat, u)), 8 * (9 * N) + 32 * E, 3 * N, "DOF")
     report("hex8_nh_energy_c3", timeit(lambda: op._raw_energy(mat, u)), 8 * (6 * N) + 32 * E, 3 * N, "DOF")
     del op
-    c, el, u_, v_ = synthetic_inputs(64)
-    op = tatva_b200.Operator(Mesh(coords=c, elements=el), element.Hexahedron8())
-    N, E = c.shape[0], el.shape[0]
-    u = torch.as_tensor(u_, device="cuda")
-    g = op._k_grad(u)
-    report("hex8_op_grad_64", timeit(lambda: op._k_grad(u)), 8 * (6 * N + 72 * E) + 32 * E, E * 8, "qp")
-    report("hex8_op_grad_adjoint_64", timeit(lambda: op._k_grad_adj(g)), 8 * (6 * N + 72 * E) + 32 * E, E * 8, "qp")
-    report("hex8_op_eval_64", timeit(lambda: op._k_eval(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "qp")
-    report("hex8_op_weights_64", timeit(lambda: op.get_integration_weights()), 8 * (3 * N + 8 * E) + 32 * E, E * 8, "qp")
-    report("hex8_op_gather_64", timeit(lambda: op._k_gather(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "node-ref")
+    for nb in (64, 128):
+        c, el, u_, v_ = synthetic_inputs(nb)
+        op = tatva_b200.Operator(Mesh(coords=c, elements=el), element.Hexahedron8())
+        N, E = c.shape[0], el.shape[0]
+        u = torch.as_tensor(u_, device="cuda")
+        g = op._k_grad(u)
+        report(f"hex8_op_grad_{nb}", timeit(lambda: op._k_grad(u)), 8 * (6 * N + 72 * E) + 32 * E, E * 8, "qp")
+        report(f"hex8_op_grad_adjoint_{nb}", timeit(lambda: op._k_grad_adj(g)), 8 * (6 * N + 72 * E) + 32 * E, E * 8, "qp")
+        report(f"hex8_op_eval_{nb}", timeit(lambda: op._k_eval(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "qp")
+        report(f"hex8_op_weights_{nb}", timeit(lambda: op.get_integration_weights()), 8 * (3 * N + 8 * E) + 32 * E, E * 8, "qp")
+        report(f"hex8_op_gather_{nb}", timeit(lambda: op._k_gather(u)), 8 * (3 * N + 24 * E) + 32 * E, E * 8, "node-ref")
+        del op, g
 
 # ---- config 3 in context: one CG iteration around the HVP (Hex8 128^3, Dirichlet face), CUDA graph on/off ----
 if want("cg"):
