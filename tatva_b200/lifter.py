@@ -429,3 +429,16 @@ def lifted(fn: Callable | None = None, *, argnums=0, output: str | None = None):
 
 
 __all__ = ["Lifter", "lifted", "Constraint", "Fixed", "Periodic", "PeriodicMPI", "RuntimeValue", "LifterError", "create_g2l"]
+
+
+def __getattr__(name: str):
+    """Deprecated aliases of the reference (tatva/lifter/__init__.py): DirichletBC -> Fixed, PeriodicMap -> Periodic."""
+    from warnings import warn
+
+    if name == "DirichletBC":
+        warn("`DirichletBC` is deprecated; use `Fixed` instead.", DeprecationWarning, stacklevel=2)
+        return Fixed
+    if name == "PeriodicMap":
+        warn("`PeriodicMap` is deprecated; use `Periodic` instead.", DeprecationWarning, stacklevel=2)
+        return Periodic
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -140,12 +140,21 @@ class DistributedConjugateGradient:
         self.x, self.r = mk(n), mk(n)
         self.scalars, self.partials = mk(8), mk(2 * 1184)
         self.free = None if pinned_owned is None else (~torch.as_tensor(pinned_owned, device=dev).bool()).to(torch.float64)
+        self._L = _lib.lib()
         self.minv = None
         if jacobi_diagonal is not None:
             self.minv = mk(n)
-            _lib.check(_lib.lib().tatva_pcg_reciprocal(jacobi_diagonal.contiguous().data_ptr(), n, self.minv.data_ptr(), self._stream()), "tatva_pcg_reciprocal")
-        self._L = _lib.lib()
+            self.set_diagonal(jacobi_diagonal)
         self.u_local = None
+
+    def set_diagonal(self, diag_owned: torch.Tensor) -> None:
+        """Refresh the Jacobi preconditioner in place (minv <- 1 / diag on the owned DOFs)."""
+        if self.minv is None:
+            raise ValueError("DistributedConjugateGradient was built without a Jacobi diagonal")
+        d = diag_owned.contiguous()
+        if d.numel() != self.n:
+            raise ValueError("the diagonal must cover the owned DOFs")
+        _lib.check(self._L.tatva_pcg_reciprocal(d.data_ptr(), self.n, self.minv.data_ptr(), self._stream()), "tatva_pcg_reciprocal")
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -221,7 +230,7 @@ def distributed_newton_solve(pop, u_local, pinned_owned=None, *, tol: float = 1e
     r_local = pop.new_symmetric_vector() if peer else pop.new_local_vector()
     free = None if pinned_owned is None else (~torch.as_tensor(pinned_owned, device=dev).bool()).to(torch.float64)
     history, r0 = [], None
-    cg = None
+    cg, d_local = None, None
     for k in range(max_newton):
         pop.fill_ghosts(u_local)
         pop.residual(u_local, r_local)
@@ -234,8 +243,12 @@ def distributed_newton_solve(pop, u_local, pinned_owned=None, *, tol: float = 1e
         if rn <= tol * max(r0, 1e-300) or rn == 0.0:
             history.append(dict(newton=k, residual_norm=rn, cg_iterations=0))
             break
-        diag = pop.hessian_diagonal(u_local)[:n].clone() if jacobi else None
-        cg = DistributedConjugateGradient(pop, pinned_owned=pinned_owned, jacobi_diagonal=diag) if (cg is None or jacobi) else cg
+        if jacobi:
+            d_local = pop.hessian_diagonal(u_local, d_local)
+        if cg is None:
+            cg = DistributedConjugateGradient(pop, pinned_owned=pinned_owned, jacobi_diagonal=d_local[:n] if jacobi else None)
+        elif jacobi:
+            cg.set_diagonal(d_local[:n])
         cg.set_state(u_local)
         du, info = cg.solve(-r, tol=cg_tol, maxiter=cg_maxiter)
         history.append(dict(newton=k, residual_norm=rn, cg_iterations=info["iterations"], cg_converged=info["converged"]))

@@ -133,3 +133,30 @@ def test_reduced_hvp_through_lifter_matches_oracle():
     Hv = lifter.reduce_adjoint(op.hvp(mat)(u_full.view(-1, 3), v_full.view(-1, 3)).reshape(-1))
     ref = lifter.reduce_adjoint(orc.hvp("hex8", omat, c, el, lifter.lift_from_zeros(u_red).reshape(-1, 3), zero_bc.lift_from_zeros(v_red).reshape(-1, 3)).ravel())
     assert np.linalg.norm(Hv.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def test_dof_map_is_the_homogeneous_lift_and_its_transpose():
+    """`Lifter.dof_map` (consumed by tatva_hvp_lifted inside the HVP kernel): full DOF -> driving reduced DOF or -1,
+    equivalent to homogeneous().lift_from_zeros and reduce_adjoint (reference lifter/base.py:201-251)."""
+    import numpy as np
+    from tatva_b200.lifter import Fixed, Lifter, Periodic
+
+    rng = np.random.default_rng(0)
+    lifter = Lifter(12, Fixed([0, 5], [1.0, -2.0]), Periodic([7, 9], [2, 3]), Fixed([11], 4.0))
+    m = lifter.dof_map()
+    assert m.dtype == np.int32 and m.shape == (12,)
+    assert (m[[0, 5, 11]] == -1).all() and m[7] == m[2] and m[9] == m[3]
+    v = rng.normal(size=lifter.size_reduced)
+    np.testing.assert_array_equal(lifter.homogeneous().lift_from_zeros(v), np.where(m >= 0, v[np.maximum(m, 0)], 0.0))
+    r = rng.normal(size=12)
+    np.testing.assert_allclose(lifter.reduce_adjoint(r), np.bincount(m[m >= 0], weights=r[m >= 0], minlength=lifter.size_reduced))
+
+
+def test_deprecated_aliases_warn_like_the_reference():
+    import warnings
+    from tatva_b200 import lifter as L
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert L.DirichletBC is L.Fixed and L.PeriodicMap is L.Periodic
+    assert sum(issubclass(x.category, DeprecationWarning) for x in w) == 2
