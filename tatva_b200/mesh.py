@@ -208,3 +208,46 @@ def reorder_mesh(mesh: Mesh, nodes: bool = True):
     inv = np.empty(c.shape[0], dtype=np.int64)
     inv[node_perm] = np.arange(c.shape[0])
     return Mesh(coords=c[node_perm], elements=inv[el_sorted].astype(el.dtype)), elem_perm, node_perm
+
+
+def find_containing_polygons(points, polygons, device=None):
+    """Index of the first polygon (vertex loops, shape (n_polygons, n_vertices, 2)) containing each 2-D point, -1 if
+    none — tatva/mesh.py:294-388 (bounding box, then on-boundary OR odd ray crossings).  Runs the point-location
+    part of the `tatva_op_interpolate` kernel on the polygons as a stand-alone mesh; loops of 3, 4, 6 or 8 vertices
+    (the plane elements).  Returns an int32 CUDA tensor."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    if not torch.cuda.is_available():
+        raise _lib.TatvaError("find_containing_polygons needs a CUDA device (there is no CPU fallback)")
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    poly = torch.as_tensor(polygons, dtype=torch.float64, device=dev)
+    pts = torch.as_tensor(points, dtype=torch.float64, device=dev).contiguous()
+    if poly.ndim != 3 or poly.shape[2] != 2 or pts.ndim != 2 or pts.shape[1] != 2:
+        raise ValueError("points must be (n_points, 2) and polygons (n_polygons, n_vertices, 2)")
+    kinds = {3: _lib.TRI3, 4: _lib.QUAD4, 6: _lib.TRI6, 8: _lib.QUAD8}
+    nv = int(poly.shape[1])
+    if nv not in kinds:
+        raise NotImplementedError("polygons with 3, 4, 6 or 8 vertices are supported")
+    n_poly = int(poly.shape[0])
+    out = torch.full((pts.shape[0],), -1, dtype=torch.int32, device=dev)
+    if n_poly == 0 or pts.shape[0] == 0:
+        return out
+    coords = poly.reshape(-1, 2).contiguous()
+    conn = torch.arange(n_poly * nv, dtype=torch.int32, device=dev).reshape(n_poly, nv)
+    L = _lib.lib()
+    handle = C.c_void_p()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(L.tatva_plan_create(C.byref(handle), kinds[nv], coords.shape[0], n_poly, coords.data_ptr(), conn.data_ptr(), 0, st), "tatva_plan_create")
+        try:
+            u = torch.zeros((coords.shape[0], 1), dtype=torch.float64, device=dev)
+            vals = torch.empty((pts.shape[0], 1), dtype=torch.float64, device=dev)
+            _lib.check(L.tatva_op_interpolate(handle, u.data_ptr(), 1, pts.data_ptr(), pts.shape[0], vals.data_ptr(), out.data_ptr(), st), "tatva_op_interpolate")
+            torch.cuda.current_stream().synchronize()  # coords / conn are temporaries of this call
+        finally:
+            L.tatva_plan_destroy(handle)
+    return out

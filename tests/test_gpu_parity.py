@@ -355,6 +355,17 @@ def test_interpolate_matches_reference(golden, kind):
     _assert_close(got, ref)
 
 
+@pytest.mark.parametrize("kind", ["tri3", "quad4"])
+def test_find_containing_polygons_matches_reference(golden, kind):
+    """tatva.mesh.find_containing_polygons (mesh.py:294-388) as a stand-alone function."""
+    from tatva_b200.mesh import find_containing_polygons
+
+    g = lambda k: golden[f"interp_{kind}_{k}"]  # noqa: E731
+    allp = np.concatenate([g("points"), g("outside")])
+    got = find_containing_polygons(allp, g("coords")[g("conn")])
+    np.testing.assert_array_equal(got.cpu().numpy(), g("containing"))
+
+
 def test_interpolate_known_answer_two_triangles():
     """reference tests/test_operator.py:145-159."""
     from tatva_b200 import element

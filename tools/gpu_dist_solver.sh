@@ -1,4 +1,6 @@
 #!/bin/bash
+# multi-GPU parity (HVP / residual / plans / compound / distributed CG and Newton) and the distributed CG iteration bench
+# usage: gpurun --gpus N -- './tools/gpu_dist_solver.sh N [cells per side per GPU]'
 mkdir -p gpurun_out
 N=${1:-2}
 NB=${2:-64}
