@@ -78,6 +78,14 @@ int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
 int tatva_plan_set_tiles(tatva_plan_t* plan, const int32_t* d_tile_ptr, const int32_t* d_tile_nodes,
                          const uint16_t* d_tile_conn, int max_unique);
 
+/* Optional uniform background grid for tatva_op_interpolate (plane meshes): bin (ix, iy), row-major iy * nx + ix, with
+ * ix = clamp((int)((x - lo[0]) * inv[0]), 0, nx - 1); d_bin_elems[d_bin_ptr[b] .. d_bin_ptr[b+1]) lists, ascending,
+ * the elements whose bounding box overlaps bin b (tatva_host_build_point_grid), so the first containing element of the
+ * point's bin is the one mesh.find_containing_polygons returns (tatva/mesh.py:294-388).  Device views, caller-owned;
+ * d_bin_ptr == NULL disables the grid (every element is scanned).                                              */
+int tatva_plan_set_point_grid(tatva_plan_t* plan, int nx, int ny, const double* lo, const double* inv,
+                              const int32_t* d_bin_ptr, const int32_t* d_bin_elems);
+
 /* ---- quadrature-loop building blocks (generic path; any user energy on top) ------------ */
 
 /* Operator.grad -> Element.gradient  (tatva/operator.py:379-397, tatva/element/base.py:99-115)
@@ -260,6 +268,12 @@ int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, 
  * greedy first-fit in natural order on the pattern of A@A.                                  */
 int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, int64_t n,
                                 int32_t* colors, int32_t* n_colors);
+/* Background grid for point location on a plane mesh (HOST arrays).  Two-call protocol: bin_elems == NULL computes
+ * lo / inv from the mesh bounding box and fills bin_ptr (nx*ny + 1 prefix sums); the second call fills bin_elems.  */
+int tatva_host_build_point_grid(const double* coords, int64_t n_nodes, const int32_t* conn, int64_t n_elems,
+                                int npe, int nx, int ny, double* lo, double* inv, int32_t* bin_ptr,
+                                int32_t* bin_elems);
+
 /* node -> incident elements in CSR form (ptr: n_nodes+1, list: sum of incidences); pass list == NULL
  * first to size it (ptr[n_nodes]).                                                                   */
 int tatva_host_node_to_elements(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes,

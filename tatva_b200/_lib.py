@@ -31,6 +31,7 @@ SIGNATURES = {
     "tatva_plan_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_i64p, c_i64p]),
     "tatva_plan_set_variant": (C.c_int, [vp, C.c_int]),
     "tatva_plan_set_tiles": (C.c_int, [vp, vp, vp, vp, C.c_int]),
+    "tatva_plan_set_point_grid": (C.c_int, [vp, C.c_int, C.c_int, c_f64p, c_f64p, vp, vp]),
     "tatva_op_grad": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "tatva_op_grad_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "tatva_op_eval": (C.c_int, [vp, vp, C.c_int, vp, vp]),
@@ -70,6 +71,7 @@ SIGNATURES = {
     "tatva_host_node_to_elements": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, c_i32p, c_i32p]),
     "tatva_host_build_tiles": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, C.POINTER(C.c_uint16), c_i32p]),
     "tatva_host_csr_element_positions": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p]),
+    "tatva_host_build_point_grid": (C.c_int, [c_f64p, C.c_int64, c_i32p, C.c_int64, C.c_int, C.c_int, C.c_int, c_f64p, c_f64p, c_i32p, c_i32p]),
     "tatva_fp64_peak_tflops": (C.c_int, [c_f64p, vp]),
 }
 

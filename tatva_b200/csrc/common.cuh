@@ -581,6 +581,11 @@ struct tatva_plan {
   const int32_t* tile_nodes;
   const uint16_t* tile_conn;
   int tile_max_unique;
+  // optional uniform background grid for point location (see tatva_plan_set_point_grid)
+  int grid_nx, grid_ny;
+  double grid_lo[2], grid_inv[2];  // bin = clamp(floor((x - lo) * inv), 0, n - 1)
+  const int32_t* grid_ptr;         // caller-owned device views
+  const int32_t* grid_elems;
 };
 
 namespace tatva {

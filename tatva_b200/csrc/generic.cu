@@ -544,71 +544,50 @@ TATVA_D void first_quad_point(Quad4, double& r, double& s) { Quad4::xi(0, r, s);
 TATVA_D void first_quad_point(Tri6, double& r, double& s) { Tri6::xi(0, r, s); }
 TATVA_D void first_quad_point(Quad8, double& r, double& s) { Quad8::xi(0, r, s); }
 
-// One thread per point.  Element search exactly as mesh.find_containing_polygons (tatva/mesh.py:294-388): the
-// FIRST element, in element order, whose node loop (connectivity order) contains the point: bounding-box
-// reject, then on-boundary (|cross| <= 1e-8 within the segment's box) OR an odd number of +x ray crossings.
-// Elements are scanned in chunks staged in shared memory as bounding boxes, so the O(P E) scan reads each
-// element's nodes once per CTA.  Then operator.py:411-431: one Newton step from the first quadrature point, and
-// N(xi) . u_e.  Points outside every element get elem = -1 and NaN values.
+// Element search exactly as mesh.find_containing_polygons (tatva/mesh.py:294-388): the FIRST element, in element
+// order, whose node loop (connectivity order) contains the point: bounding-box reject, then on-boundary
+// (|cross| <= 1e-8 within the segment's box) OR an odd number of +x ray crossings.
 template <class El>
-__global__ void __launch_bounds__(128) k_interpolate(const double* __restrict__ coords, const int32_t* __restrict__ conn,
-                                                     int64_t E, const double* __restrict__ u, int nv,
-                                                     const double* __restrict__ pts, int64_t P,
-                                                     double* __restrict__ out, int32_t* __restrict__ elem) {
-  constexpr int npe = El::npe, CH = 128;
-  __shared__ double box[CH][4];
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = p < P;
-  const double px = live ? pts[2 * p] : 0.0, py = live ? pts[2 * p + 1] : 0.0;
-  int64_t found = -1;
-  for (int64_t base = 0; base < E; base += CH) {
-    __syncthreads();
-    const int64_t e = base + threadIdx.x;
-    if (e < E) {
-      double lx = 1e308, ly = 1e308, hx = -1e308, hy = -1e308;
+TATVA_D bool loop_contains(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t e, double px,
+                           double py, bool check_box) {
+  constexpr int npe = El::npe;
+  double vx[npe], vy[npe];
 #pragma unroll
-      for (int n = 0; n < npe; ++n) {
-        const int64_t nd = __ldg(conn + e * npe + n);
-        const double x = __ldg(coords + 2 * nd), y = __ldg(coords + 2 * nd + 1);
-        lx = fmin(lx, x); hx = fmax(hx, x); ly = fmin(ly, y); hy = fmax(hy, y);
-      }
-      box[threadIdx.x][0] = lx; box[threadIdx.x][1] = hx; box[threadIdx.x][2] = ly; box[threadIdx.x][3] = hy;
-    }
-    __syncthreads();
-    const int cnt = (int)((E - base < CH) ? (E - base) : CH);
-    if (live && found < 0) {
-      for (int k = 0; k < cnt; ++k) {
-        if (!(px >= box[k][0] && px <= box[k][1] && py >= box[k][2] && py <= box[k][3])) continue;
-        const int64_t ee = base + k;
-        double vx[npe], vy[npe];
-#pragma unroll
-        for (int n = 0; n < npe; ++n) {
-          const int64_t nd = __ldg(conn + ee * npe + n);
-          vx[n] = __ldg(coords + 2 * nd);
-          vy[n] = __ldg(coords + 2 * nd + 1);
-        }
-        bool on_boundary = false;
-        int crossings = 0;
-#pragma unroll
-        for (int n = 0; n < npe; ++n) {
-          const double ax = vx[n], ay = vy[n], bx = vx[(n + 1) % npe], by = vy[(n + 1) % npe];
-          const double cross = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
-          const bool on_seg = fmin(ax, bx) <= px && px <= fmax(ax, bx) && fmin(ay, by) <= py && py <= fmax(ay, by);
-          on_boundary |= (fabs(cross) <= 1e-8) && on_seg;
-          const bool y_cond = (ay <= py && by > py) || (by <= py && ay > py);
-          if (y_cond && px < (bx - ax) * (py - ay) / (by - ay) + ax) ++crossings;
-        }
-        if (on_boundary || (crossings & 1)) {
-          found = ee;
-          break;
-        }
-      }
-    }
+  for (int n = 0; n < npe; ++n) {
+    const int64_t nd = __ldg(conn + e * npe + n);
+    vx[n] = __ldg(coords + 2 * nd);
+    vy[n] = __ldg(coords + 2 * nd + 1);
   }
-  if (!live) return;
-  elem[p] = (int32_t)found;
+  if (check_box) {
+    double lx = vx[0], hx = vx[0], ly = vy[0], hy = vy[0];
+#pragma unroll
+    for (int n = 1; n < npe; ++n) {
+      lx = fmin(lx, vx[n]); hx = fmax(hx, vx[n]); ly = fmin(ly, vy[n]); hy = fmax(hy, vy[n]);
+    }
+    if (!(px >= lx && px <= hx && py >= ly && py <= hy)) return false;
+  }
+  bool on_boundary = false;
+  int crossings = 0;
+#pragma unroll
+  for (int n = 0; n < npe; ++n) {
+    const double ax = vx[n], ay = vy[n], bx = vx[(n + 1) % npe], by = vy[(n + 1) % npe];
+    const double cross = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+    const bool on_seg = fmin(ax, bx) <= px && px <= fmax(ax, bx) && fmin(ay, by) <= py && py <= fmax(ay, by);
+    on_boundary |= (fabs(cross) <= 1e-8) && on_seg;
+    const bool y_cond = (ay <= py && by > py) || (by <= py && ay > py);
+    if (y_cond && px < (bx - ax) * (py - ay) / (by - ay) + ax) ++crossings;
+  }
+  return on_boundary || (crossings & 1);
+}
+
+// operator.py:411-431: one Newton step from the first quadrature point, then N(xi) . u_e.  found < 0: NaN.
+template <class El>
+TATVA_D void interpolate_in_element(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t found,
+                                    const double* __restrict__ u, int nv, double px, double py,
+                                    double* __restrict__ out_row) {
+  constexpr int npe = El::npe;
   if (found < 0) {
-    for (int c = 0; c < nv; ++c) out[p * nv + c] = __longlong_as_double(0x7ff8000000000000LL);
+    for (int c = 0; c < nv; ++c) out_row[c] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
   int nd[npe];
@@ -641,8 +620,88 @@ __global__ void __launch_bounds__(128) k_interpolate(const double* __restrict__ 
     double t = 0.0;
 #pragma unroll
     for (int n = 0; n < npe; ++n) t += N[n] * __ldg(u + (int64_t)nd[n] * nv + c);
-    out[p * nv + c] = t;
+    out_row[c] = t;
   }
+}
+
+// One thread per point, every element scanned: bounding boxes staged per CTA in shared memory, so the O(P E) scan
+// reads each element's nodes once per CTA.  Used when the plan has no point grid.
+template <class El>
+__global__ void __launch_bounds__(128) k_interpolate(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                     int64_t E, const double* __restrict__ u, int nv,
+                                                     const double* __restrict__ pts, int64_t P,
+                                                     double* __restrict__ out, int32_t* __restrict__ elem) {
+  constexpr int npe = El::npe, CH = 128;
+  __shared__ double box[CH][4];
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < P;
+  const double px = live ? pts[2 * p] : 0.0, py = live ? pts[2 * p + 1] : 0.0;
+  int64_t found = -1;
+  for (int64_t base = 0; base < E; base += CH) {
+    __syncthreads();
+    const int64_t e = base + threadIdx.x;
+    if (e < E) {
+      double lx = 1e308, ly = 1e308, hx = -1e308, hy = -1e308;
+#pragma unroll
+      for (int n = 0; n < npe; ++n) {
+        const int64_t nd = __ldg(conn + e * npe + n);
+        const double x = __ldg(coords + 2 * nd), y = __ldg(coords + 2 * nd + 1);
+        lx = fmin(lx, x); hx = fmax(hx, x); ly = fmin(ly, y); hy = fmax(hy, y);
+      }
+      box[threadIdx.x][0] = lx; box[threadIdx.x][1] = hx; box[threadIdx.x][2] = ly; box[threadIdx.x][3] = hy;
+    }
+    __syncthreads();
+    const int cnt = (int)((E - base < CH) ? (E - base) : CH);
+    if (live && found < 0) {
+      for (int k = 0; k < cnt; ++k) {
+        if (!(px >= box[k][0] && px <= box[k][1] && py >= box[k][2] && py <= box[k][3])) continue;
+        if (loop_contains<El>(coords, conn, base + k, px, py, false)) {
+          found = base + k;
+          break;
+        }
+      }
+    }
+  }
+  if (!live) return;
+  elem[p] = (int32_t)found;
+  interpolate_in_element<El>(coords, conn, found, u, nv, px, py, out + p * nv);
+}
+
+// Same result through a uniform background grid (tatva_plan_set_point_grid): a bin lists, in ascending order, the
+// elements whose bounding box overlaps it, so the first hit in the point's bin is the first hit overall.
+struct PointGrid {
+  int nx, ny;
+  double lo[2], inv[2];
+  const int32_t* ptr;
+  const int32_t* elems;
+};
+TATVA_HD int grid_bin(double x, double lo, double inv, int n) {
+  const double t = (x - lo) * inv;
+  int b = t > 0.0 ? (t < (double)n ? (int)t : n - 1) : 0;
+  return b;
+}
+template <class El>
+__global__ void __launch_bounds__(128) k_interpolate_grid(const double* __restrict__ coords,
+                                                          const int32_t* __restrict__ conn, PointGrid g,
+                                                          const double* __restrict__ u, int nv,
+                                                          const double* __restrict__ pts, int64_t P,
+                                                          double* __restrict__ out, int32_t* __restrict__ elem) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double px = pts[2 * p], py = pts[2 * p + 1];
+  int64_t found = -1;
+  if (px == px && py == py) {  // NaN coordinates are in no element
+    const int b = grid_bin(py, g.lo[1], g.inv[1], g.ny) * g.nx + grid_bin(px, g.lo[0], g.inv[0], g.nx);
+    for (int k = __ldg(g.ptr + b), k1 = __ldg(g.ptr + b + 1); k < k1; ++k) {
+      const int e = __ldg(g.elems + k);
+      if (loop_contains<El>(coords, conn, e, px, py, true)) {
+        found = e;
+        break;
+      }
+    }
+  }
+  elem[p] = (int32_t)found;
+  interpolate_in_element<El>(coords, conn, found, u, nv, px, py, out + p * nv);
 }
 
 // ---- fused energy / residual / HVP ------------------------------------------------------------
@@ -1459,6 +1518,26 @@ int tatva_plan_set_tiles(tatva_plan_t* p, const int32_t* d_tile_ptr, const int32
   return TATVA_OK;
 }
 
+// Uniform background grid for point location: bin (ix, iy) = (clamp(floor((x - lo_x) * inv_x)), ...), row-major
+// iy * nx + ix; d_bin_elems[d_bin_ptr[b] .. d_bin_ptr[b+1]) = the elements whose bounding box overlaps bin b, ascending
+// (tatva_host_build_point_grid).  Device views, caller-owned; NULL disables (every element is scanned).
+int tatva_plan_set_point_grid(tatva_plan_t* p, int nx, int ny, const double* lo, const double* inv,
+                              const int32_t* d_bin_ptr, const int32_t* d_bin_elems) {
+  if (!p) return TATVA_E_INVALID;
+  if (!d_bin_ptr) {
+    p->grid_ptr = p->grid_elems = nullptr;
+    return TATVA_OK;
+  }
+  if (!d_bin_elems || !lo || !inv || nx <= 0 || ny <= 0 || p->dim != 2) return TATVA_E_INVALID;
+  p->grid_nx = nx;
+  p->grid_ny = ny;
+  p->grid_lo[0] = lo[0]; p->grid_lo[1] = lo[1];
+  p->grid_inv[0] = inv[0]; p->grid_inv[1] = inv[1];
+  p->grid_ptr = d_bin_ptr;
+  p->grid_elems = d_bin_elems;
+  return TATVA_OK;
+}
+
 int tatva_plan_set_variant(tatva_plan_t* p, int variant) {
   if (!p || variant < 0 || variant > 63) return TATVA_E_INVALID;
   p->variant = variant;
@@ -1597,6 +1676,18 @@ int tatva_op_interpolate(const tatva_plan_t* p, const double* d_u, int nv, const
   if (!p || !d_u || !d_points || !d_out || !d_elem || nv <= 0 || n_points <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)((n_points + 127) / 128);
+  if (p->grid_ptr && p->variant != TATVA_VARIANT_GENERIC) {
+    PointGrid g{p->grid_nx, p->grid_ny, {p->grid_lo[0], p->grid_lo[1]}, {p->grid_inv[0], p->grid_inv[1]}, p->grid_ptr, p->grid_elems};
+    switch (p->element) {
+      case TATVA_TRI3: k_interpolate_grid<Tri3><<<grid, 128, 0, st>>>(p->coords, p->conn, g, d_u, nv, d_points, n_points, d_out, d_elem); break;
+      case TATVA_QUAD4: k_interpolate_grid<Quad4><<<grid, 128, 0, st>>>(p->coords, p->conn, g, d_u, nv, d_points, n_points, d_out, d_elem); break;
+      case TATVA_TRI6: k_interpolate_grid<Tri6><<<grid, 128, 0, st>>>(p->coords, p->conn, g, d_u, nv, d_points, n_points, d_out, d_elem); break;
+      case TATVA_QUAD8: k_interpolate_grid<Quad8><<<grid, 128, 0, st>>>(p->coords, p->conn, g, d_u, nv, d_points, n_points, d_out, d_elem); break;
+      default: return TATVA_E_UNSUPPORTED;
+    }
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   switch (p->element) {
     case TATVA_TRI3: k_interpolate<Tri3><<<grid, 128, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_points, n_points, d_out, d_elem); break;
     case TATVA_QUAD4: k_interpolate<Quad4><<<grid, 128, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_points, n_points, d_out, d_elem); break;

@@ -178,6 +178,68 @@ int tatva_host_build_tiles(const int32_t* conn, int64_t n_elems, int npe, int ti
   return TATVA_OK;
 }
 
+// Uniform background grid over the bounding box of a plane mesh, for point location.  Bin of a coordinate:
+// clamp((int)((x - lo) * inv), 0, n - 1) — the same expression the kernel evaluates, and monotone in x, so an element
+// is listed in every bin its bounding box can share a point with.  Two-call protocol: bin_elems == NULL fills lo,
+// inv and bin_ptr (nx*ny + 1) only.  Elements are appended in ascending order.
+static inline int grid_bin_host(double x, double lo, double inv, int n) {
+  const double t = (x - lo) * inv;
+  return t > 0.0 ? (t < (double)n ? (int)t : n - 1) : 0;
+}
+int tatva_host_build_point_grid(const double* coords, int64_t n_nodes, const int32_t* conn, int64_t n_elems, int npe,
+                                int nx, int ny, double* lo, double* inv, int32_t* bin_ptr, int32_t* bin_elems) {
+  if (!coords || !conn || !lo || !inv || !bin_ptr || n_nodes <= 0 || n_elems <= 0 || npe <= 0 || nx <= 0 || ny <= 0)
+    return TATVA_E_INVALID;
+  if (!bin_elems) {
+    double l[2] = {coords[0], coords[1]}, h[2] = {coords[0], coords[1]};
+    for (int64_t i = 0; i < n_nodes; ++i)
+      for (int d = 0; d < 2; ++d) {
+        l[d] = std::min(l[d], coords[2 * i + d]);
+        h[d] = std::max(h[d], coords[2 * i + d]);
+      }
+    for (int d = 0; d < 2; ++d) {
+      lo[d] = l[d];
+      inv[d] = h[d] > l[d] ? (d == 0 ? nx : ny) / (h[d] - l[d]) : 0.0;
+    }
+  }
+  const int64_t nb = (int64_t)nx * ny;
+  std::vector<int32_t> fill;
+  if (!bin_elems) std::fill(bin_ptr, bin_ptr + nb + 1, 0);
+  else fill.assign(bin_ptr, bin_ptr + nb);
+  for (int64_t e = 0; e < n_elems; ++e) {
+    double l[2] = {1e308, 1e308}, h[2] = {-1e308, -1e308};
+    for (int a = 0; a < npe; ++a) {
+      const int32_t n = conn[e * npe + a];
+      if (n < 0 || n >= n_nodes) return TATVA_E_INVALID;
+      for (int d = 0; d < 2; ++d) {
+        l[d] = std::min(l[d], coords[2 * (int64_t)n + d]);
+        h[d] = std::max(h[d], coords[2 * (int64_t)n + d]);
+      }
+    }
+    const int x0 = grid_bin_host(l[0], lo[0], inv[0], nx), x1 = grid_bin_host(h[0], lo[0], inv[0], nx);
+    const int y0 = grid_bin_host(l[1], lo[1], inv[1], ny), y1 = grid_bin_host(h[1], lo[1], inv[1], ny);
+    for (int iy = y0; iy <= y1; ++iy)
+      for (int ix = x0; ix <= x1; ++ix) {
+        const int64_t b = (int64_t)iy * nx + ix;
+        if (!bin_elems) {
+          if (bin_ptr[b + 1] == INT32_MAX) return TATVA_E_INVALID;
+          bin_ptr[b + 1]++;
+        } else {
+          bin_elems[fill[b]++] = (int32_t)e;
+        }
+      }
+  }
+  if (!bin_elems) {
+    int64_t total = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+      total += bin_ptr[b + 1];
+      if (total > INT32_MAX) return TATVA_E_INVALID;
+      bin_ptr[b + 1] = (int32_t)total;
+    }
+  }
+  return TATVA_OK;
+}
+
 // elem_pos[e, a, b] = offset of column dpn*conn[e,b] inside CSR row dpn*conn[e,a]
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe, int dpn, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos) {

@@ -86,6 +86,7 @@ class Operator:
 
         # Shared-memory staging tiles for gather-bound kernels (Tet4 x neo-Hookean): per CTA the unique nodes are
         # gathered once, coalesced, and elements read them through tile-local uint16 connectivity.
+        self._point_grid = None
         self._tiles = None
         if stage_tiles:
             self._build_tiles()
@@ -282,6 +283,8 @@ class Operator:
             raise NotImplementedError("interpolate: plane elements and (P, 2) points, as in the reference (mesh.py:303)")
         vshape = tuple(u.shape[1:])
         u2 = u.reshape(self.n_nodes, -1).contiguous()
+        if self._point_grid is None:
+            self._build_point_grid()
         out = torch.empty((pts.shape[0], u2.shape[1]), dtype=torch.float64, device=self.device)
         elem = torch.empty(pts.shape[0], dtype=torch.int32, device=self.device)
         if pts.shape[0]:
@@ -289,6 +292,24 @@ class Operator:
             if bool((elem < 0).any()):
                 raise RuntimeError("Some points are outside the mesh, revise the points")
         return out.reshape((pts.shape[0],) + vshape)
+
+    def _build_point_grid(self):
+        """Uniform background grid for point location, ~1 element per bin, built once on the host (C++) and attached
+        to the plan; the search then visits only the elements whose bounding box overlaps the point's bin."""
+        coords = np.ascontiguousarray(self.coords.cpu().numpy(), dtype=np.float64)
+        conn = np.ascontiguousarray(self.elements.cpu().numpy(), dtype=np.int32)
+        side = int(min(4096, max(1, round(np.sqrt(self.n_elements)))))
+        lo, inv = np.zeros(2), np.zeros(2)
+        ptr = np.zeros(side * side + 1, dtype=np.int32)
+        f64 = lambda a: a.ctypes.data_as(_lib.c_f64p)  # noqa: E731
+        i32 = lambda a: a.ctypes.data_as(_lib.c_i32p)  # noqa: E731
+        args = (f64(coords), self.n_nodes, i32(conn), self.n_elements, self.npe, side, side, f64(lo), f64(inv), i32(ptr))
+        _lib.check(self._L.tatva_host_build_point_grid(*args, None), "tatva_host_build_point_grid")
+        elems = np.empty(max(int(ptr[-1]), 1), dtype=np.int32)
+        _lib.check(self._L.tatva_host_build_point_grid(*args, i32(elems)), "tatva_host_build_point_grid")
+        d_ptr, d_elems = torch.as_tensor(ptr, device=self.device), torch.as_tensor(elems, device=self.device)
+        self._point_grid = (d_ptr, d_elems, lo, inv, side)  # keeps the device views alive
+        _lib.check(self._L.tatva_plan_set_point_grid(self._plan, side, side, f64(lo), f64(inv), d_ptr.data_ptr(), d_elems.data_ptr()), "tatva_plan_set_point_grid")
 
     def project(self, field, colored_matrix=None, lifter=None, *, tol: float = 1e-12, maxiter: int = 2000) -> torch.Tensor:
         """L2 projection of a quadrature field (E, Q, *v) onto the nodal space, (N, *v) — operator.py:518-554,
