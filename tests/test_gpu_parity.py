@@ -350,9 +350,12 @@ def test_interpolate_matches_reference(golden, kind):
     op2 = tatva_b200.Operator(tatva_b200.Mesh(coords=cc, elements=ee), {"tri3": element.Tri3, "quad4": element.Quad4}[kind]())
     ref, idx = orc.op_interpolate(kind, cc, ee, uu, pts)
     assert (idx >= 0).all()
-    got = op2.interpolate(uu, pts)
-    assert got.shape == (1000, 2, 2)
+    got = op2.interpolate(uu, pts)  # background grid
+    assert got.shape == (1000, 2, 2) and op2._point_grid is not None
     _assert_close(got, ref)
+    op2.set_variant(1)  # full scan of every element
+    full = op2.interpolate(uu, pts)
+    assert torch.equal(full, got)
 
 
 @pytest.mark.parametrize("kind", ["tri3", "quad4"])
