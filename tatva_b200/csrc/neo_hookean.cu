@@ -1140,6 +1140,94 @@ TATVA_D void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3][
       Q[i][d] = fma(w1, Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d], w2 * Ac[d][i]);
 }
 
+// Energy in the same raw-modal / tx-pair form.  Gradients are carried at 8x their value: I1 and lnJ are ratios and do
+// not notice, the weight det J picks up 8^3, removed once at the end.
+TATVA_D double point_energy(const double (&J)[3][3], const double (&Fr)[3][3], double mu, double lmbda) {
+  double Kc[3][3], detJ;
+  adjugate(J, Kc, detJ);
+  double M[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      M[a][b] = Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b];
+      M[b][a] = M[a][b];
+    }
+  const double detF = Fr[0][0] * (Fr[1][1] * Fr[2][2] - Fr[1][2] * Fr[2][1]) +
+                      Fr[0][1] * (Fr[1][2] * Fr[2][0] - Fr[1][0] * Fr[2][2]) +
+                      Fr[0][2] * (Fr[1][0] * Fr[2][1] - Fr[1][1] * Fr[2][0]);
+  double I1 = 0.0;  // detJ^2 |F|^2
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) I1 = fma(Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d], Fr[i][d], I1);
+  const double rJ = 1.0 / detJ;
+  const double lnJ = log(detF * rJ);
+  return detJ * (0.5 * mu * (I1 * rJ * rJ - 3.0 - 2.0 * lnJ) + 0.5 * lmbda * lnJ * lnJ);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_energy_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                        double lmbda, const double* __restrict__ u, double* __restrict__ partials) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double energy = 0.0;
+  if (e < E) {
+    int nd[8];
+    {
+      const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+      const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+      nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+      nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+    }
+    double hX[3][7], hx[3][7];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double fX[8], fu[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+        fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+      }
+      to_modal_raw(fX, hX[c]);
+      to_modal_raw(fu, hx[c]);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) hx[c][k] += hX[c][k];
+    }
+#pragma unroll 1
+    for (int pq = 0; pq < 4; ++pq) {
+      const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1];
+      double Jm[3][3], Jp[3][3], Frm[3][3], Frp[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double gm[3], gp[3];
+        ref_grad8_pair(hX[c], sy, sz, gm, gp);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          Jm[d][c] = gm[d];
+          Jp[d][c] = gp[d];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+      energy += point_energy(Jm, Frm, mu, lmbda) + point_energy(Jp, Frp, mu, lmbda);
+    }
+    energy *= 1.0 / 512.0;
+  }
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) energy += __shfl_down_sync(0xffffffffu, energy, o);
+  if (lane == 0) sh[w] = energy;
+  __syncthreads();
+  if (w == 0) {
+    energy = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) energy += __shfl_down_sync(0xffffffffu, energy, o);
+    if (lane == 0) partials[blockIdx.x] = energy;
+  }
+}
+
 // Hex8 residual with the structure of the v3 HVP kernel: raw (unnormalised) modal coefficients, the two Gauss points
 // of a tx pair evaluated together from shared partial sums, signs from the constant table, scalings folded into
 // mu/512 and lambda/512, and (STAGE) the modal coordinates parked in shared memory between iterations.
@@ -1481,7 +1569,11 @@ int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const d
 }
 
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st) {
-  k_hex8_nh_energy_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch);
+  switch (p->variant) {  // 2 = first modal kernel (8 rolled points), 3 = pair kernel at 2 CTAs / SM, default = pair kernel, 3 CTAs / SM
+    case 2: k_hex8_nh_energy_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch); break;
+    case 3: k_hex8_nh_energy_v3<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch); break;
+    default: k_hex8_nh_energy_v3<3><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch); break;
+  }
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
