@@ -311,7 +311,7 @@ class Operator:
         self._point_grid = (d_ptr, d_elems, lo, inv, side)  # keeps the device views alive
         _lib.check(self._L.tatva_plan_set_point_grid(self._plan, side, side, f64(lo), f64(inv), d_ptr.data_ptr(), d_elems.data_ptr()), "tatva_plan_set_point_grid")
 
-    def project(self, field, colored_matrix=None, lifter=None, *, tol: float = 1e-12, maxiter: int = 2000, use_graph: bool = True) -> torch.Tensor:
+    def project(self, field, colored_matrix=None, lifter=None, *, tol: float = 1e-12, maxiter: int = 2000, use_graph: bool = False) -> torch.Tensor:
         """L2 projection of a quadrature field (E, Q, *v) onto the nodal space, (N, *v) — operator.py:518-554,
         utils.py:118-258: M x = b with M_ab = int N_a N_b, b_a = int N_a f.  The reference assembles M through
         sparse.jacfwd and calls a direct sparse solve; here M is applied matrix-free (eval kernel, weights, eval-adjoint
@@ -368,7 +368,7 @@ class Operator:
             return out
 
         rhs = b if mask is None else b * mask
-        cg = ConjugateGradient(matvec, n, self.device, use_graph=use_graph, jacobi=True)  # the iteration is replayed as one CUDA graph
+        cg = ConjugateGradient(matvec, n, self.device, use_graph=use_graph, jacobi=True)  # graph capture costs ~0.5 s: only pays for very long solves
         cg.set_diagonal(diag.expand(self.n_nodes, K).contiguous().reshape(-1))
         x, info = cg.solve(rhs.reshape(-1).contiguous(), tol=tol, maxiter=maxiter, check_every=5)
         if not info["converged"]:
