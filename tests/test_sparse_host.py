@@ -22,6 +22,32 @@ def test_library_exports_every_declared_symbol():
     assert L.tatva_abi_version() == 1
 
 
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (what cgo / an XLA-FFI shim / ctypes stubs
+    bind) and a C program must link against libtatva_b200.so and call a GPU-free entry point."""
+    import os, shutil, subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.abspath(os.path.join(os.path.dirname(_lib.__file__), ".."))
+    lib = os.path.join(root, "tatva_b200", "libtatva_b200.so")
+    _lib.lib()  # builds the library if it is missing
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "tatva_b200.h"\n'
+        "int main(void) {\n"
+        "  int32_t conn[6] = {0, 1, 2, 0, 2, 3}, indptr[9], indices[64]; int64_t nnz = 0;\n"
+        "  if (tatva_host_pattern_from_mesh(conn, 2, 3, 4, 2, indptr, 0, &nnz) != TATVA_OK) return 2;\n"
+        "  if (tatva_host_pattern_from_mesh(conn, 2, 3, 4, 2, indptr, indices, &nnz) != TATVA_OK) return 3;\n"
+        '  printf("%d %lld %s\\n", tatva_abi_version(), (long long)nnz, tatva_error_string(TATVA_E_INVALID));\n'
+        "  return 0;\n}\n"
+    )
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), lib, f"-Wl,-rpath,{os.path.dirname(lib)}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(maxsplit=2)
+    assert out[0] == "1" and out[1] == "56"  # two triangles sharing an edge, 2 DOFs per node: (3+4+3+4 node pairs) * 4
+
+
 @pytest.mark.parametrize("name,dpn", [("tri3_8x8_d2", 2), ("tet4_3_d3", 3), ("tet4_2_d4", 4), ("hex8_3_d3", 3)])
 def test_pattern_and_colours_bit_exact_with_reference(golden, name, dpn):
     conn, n_nodes = golden[f"sp_{name}_conn"], int(golden[f"sp_{name}_nnodes"])
