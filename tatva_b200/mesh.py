@@ -48,6 +48,38 @@ class Mesh:
     def set_coords(self, new_coords):
         return replace(self, coords=new_coords)
 
+    # -- element sizes (mesh.py:87-144): setup-time host arithmetic -------------------------------
+    def _element_circumdiameters(self) -> np.ndarray:
+        """Circumscribed-sphere diameter of simplices (triangles in 2-D or embedded in 3-D, tetrahedra); for every
+        other element the largest vertex-to-vertex distance."""
+        X = _np(self.coords).astype(np.float64)[_np(self.elements)]  # (E, npe, dim)
+        npe, dim = X.shape[1], X.shape[2]
+        tiny = 1e-12
+        if npe == 3:
+            e01, e02, e12 = X[:, 1] - X[:, 0], X[:, 2] - X[:, 0], X[:, 2] - X[:, 1]
+            edge_product = np.linalg.norm(e01, axis=1) * np.linalg.norm(e02, axis=1) * np.linalg.norm(e12, axis=1)
+            if dim == 2:
+                twice_area = np.abs(e01[:, 0] * e02[:, 1] - e01[:, 1] * e02[:, 0])
+            else:
+                twice_area = np.linalg.norm(np.cross(e01, e02), axis=1)
+            return edge_product / np.maximum(twice_area, tiny)  # 2R = abc / (2 area)
+        if npe == 4 and dim == 3:
+            p, q, r = X[:, 1] - X[:, 0], X[:, 2] - X[:, 0], X[:, 3] - X[:, 0]
+            qr, rp, pq = np.cross(q, r), np.cross(r, p), np.cross(p, q)
+            six_volume = np.abs(np.einsum("ei,ei->e", p, qr))
+            w = (p * p).sum(1)[:, None] * qr + (q * q).sum(1)[:, None] * rp + (r * r).sum(1)[:, None] * pq
+            return np.linalg.norm(w, axis=1) / np.maximum(six_volume, tiny)  # 2R = |p^2 (q x r) + ...| / (6 V)
+        i, j = np.triu_indices(npe, k=1)
+        return np.sqrt(((X[:, j] - X[:, i]) ** 2).sum(-1).max(axis=1))
+
+    def hmin(self):
+        """Smallest element diameter (mesh.py:138-140)."""
+        return self._element_circumdiameters().min()
+
+    def hmax(self):
+        """Largest element diameter (mesh.py:142-144)."""
+        return self._element_circumdiameters().max()
+
     # -- generators ---------------------------------------------------------------------------
     @classmethod
     def unit_square(cls, n_x, n_y, *, type=ElementType.TRIANGLE, dim=2):

@@ -310,6 +310,26 @@ def partition_fixtures(out):
         out[f"part_tri_r{r}_nowned"] = np.array(info.n_owned_nodes)
 
 
+def mesh_size_fixtures(out):
+    """Mesh.hmin / hmax / _element_circumdiameters (mesh.py:87-144) on jittered meshes of every branch: triangles in
+    2-D and embedded in 3-D, tetrahedra, and the max-vertex-distance fallback (quads, hexes)."""
+    rng = np.random.default_rng(29)
+    ct, et = orc.mesh_unit_square_tri(4, 3)
+    ct = ct + 0.03 * rng.uniform(-1, 1, ct.shape)
+    ct3 = np.concatenate([ct, 0.2 * np.sin(3 * ct[:, :1]) + 0.1 * ct[:, 1:2]], axis=1)
+    cq, eq = orc.mesh_unit_square_quad(3, 4)
+    cq = cq + 0.03 * rng.uniform(-1, 1, cq.shape)
+    cT, eT = orc.mesh_box_tet((1.0, 0.7, 0.4), (3, 2, 2))
+    cT = cT + 0.03 * rng.uniform(-1, 1, cT.shape)
+    cH, eH = orc.mesh_box_hex((3, 2, 2))
+    cH = cH + 0.03 * rng.uniform(-1, 1, cH.shape)
+    for name, (c, el) in {"tri2d": (ct, et), "tri3d": (ct3, et), "quad": (cq, eq), "tet": (cT, eT), "hex": (cH, eH)}.items():
+        m = Mesh(coords=jnp.asarray(c), elements=jnp.asarray(el))
+        out[f"h_{name}_coords"], out[f"h_{name}_conn"] = c, el
+        out[f"h_{name}_diam"] = np.asarray(m._element_circumdiameters())
+        out[f"h_{name}_hmin"], out[f"h_{name}_hmax"] = np.asarray(m.hmin()), np.asarray(m.hmax())
+
+
 def main():
     out: dict[str, np.ndarray] = {}
     element_fixtures(out)
@@ -319,6 +339,7 @@ def main():
     partition_fixtures(out)
     line_fixtures(out)
     interpolate_fixtures(out)
+    mesh_size_fixtures(out)
     try:
         from _fakempi_golden import mpi_fixtures  # type: ignore
 

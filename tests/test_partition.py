@@ -86,3 +86,15 @@ def test_structured_tet_block_matches_extract_local_mesh():
         np.testing.assert_array_equal(mesh.elements, ref_mesh.elements)
         # box_tet is centred in x, y (tests/test_sparse_tracer.py:35-37); the block builder starts at the origin
         np.testing.assert_allclose(mesh.coords, ref_mesh.coords + np.array([shape[0] / m / 2, shape[1] / m / 2, 0.0]), atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["tri2d", "tri3d", "quad", "tet", "hex"])
+def test_mesh_hmin_hmax_match_reference(golden, name):
+    """Mesh.hmin / hmax / _element_circumdiameters against the reference's outputs (tatva/mesh.py:87-144): both
+    simplex formulas and the max-vertex-distance fallback."""
+    from tatva_b200.mesh import Mesh
+
+    m = Mesh(coords=golden[f"h_{name}_coords"], elements=golden[f"h_{name}_conn"])
+    np.testing.assert_allclose(m._element_circumdiameters(), golden[f"h_{name}_diam"], rtol=1e-13)
+    np.testing.assert_allclose(m.hmin(), golden[f"h_{name}_hmin"], rtol=1e-13)
+    np.testing.assert_allclose(m.hmax(), golden[f"h_{name}_hmax"], rtol=1e-13)
