@@ -198,8 +198,107 @@ def _stack(items, offset, axis):
     return out, total
 
 
+class _GlobalFieldIndices:
+    """Natural (mesh-global) DOF ids of a field, indexed like the field itself (compound/mpi.py:113-202).  For a
+    field on a node subset the first index is a GLOBAL node id, translated to its position in the subset."""
+
+    def __init__(self, info):
+        self.shape, self._base_offset, self._strides, self.global_subset = tuple(info.global_shape), int(info.global_base_offset), tuple(info.global_strides), info.global_subset
+
+    def _subset_position(self, first):
+        sub = self.global_subset
+        if isinstance(first, (int, np.integer)):
+            pos = int(np.searchsorted(sub, first))
+            if pos >= len(sub) or sub[pos] != first:
+                raise IndexError(f"Global node ID {first} not in field subset.")
+            return pos
+        if isinstance(first, slice):
+            if first.step is not None and first.step != 1:
+                raise NotImplementedError("Slicing with step on global subset not supported yet.")
+            lo = int(np.searchsorted(sub, first.start)) if first.start is not None else 0
+            hi = int(np.searchsorted(sub, first.stop)) if first.stop is not None else len(sub)
+            return slice(lo, hi)
+        ids = np.asarray(first.cpu() if _is_torch(first) else first)
+        pos = np.searchsorted(sub, ids)
+        ok = (pos < len(sub)) & (sub[np.minimum(pos, len(sub) - 1)] == ids)
+        if not np.all(ok):
+            raise IndexError(f"Global node IDs {ids[~ok]} not found in field subset.")
+        return pos.astype(np.int64)
+
+    def __getitem__(self, arg) -> np.ndarray:
+        if not isinstance(arg, tuple):
+            arg = (arg,)
+        arg = arg + (slice(None),) * (len(self.shape) - len(arg))
+        if self.global_subset is not None and arg:
+            arg = (self._subset_position(arg[0]),) + arg[1:]
+        # same affine index arithmetic as the local Field
+        return Field(self.shape, self._base_offset, self._strides).indices(arg)
+
+
+class _GlobalIndicesView:
+    """`MyState._g.<field>[...]`: natural global DOF ids (compound/mpi.py:86-110)."""
+
+    def __init__(self, compound_cls):
+        self._compound = compound_cls
+
+    def __getattr__(self, name):
+        info = self._compound._global_field_info
+        if info is None or name not in info:
+            raise AttributeError(f"'{self._compound.__name__}' has no field '{name}' or layout not initialized.")
+        return _GlobalFieldIndices(info[name])
+
+
+class _GlobalDataView:
+    """`state._g.<field>`: the field assembled over all ranks in natural global order (compound/mpi.py:205-276).
+    Owned entries are placed at their natural ids in a zero vector of the global size and summed over the ranks
+    (one all-reduce, cached per view)."""
+
+    def __init__(self, instance):
+        self._state = instance
+        self._full = None
+
+    def _gather(self):
+        if self._full is None:
+            from .mpi import _as_comm
+
+            st = self._state
+            layout, comm = st._layout, _as_comm(st._comm)
+            arr = st.arr if _is_torch(st.arr) else torch.as_tensor(np.asarray(st.arr))
+            owned = torch.as_tensor(layout.owned_mask, device=arr.device)
+            l2g = torch.as_tensor(np.asarray(layout.natural_l2g, dtype=np.int64), device=arr.device)
+            full = torch.zeros(int(layout.n_global), dtype=arr.dtype, device=arr.device)
+            full[l2g[owned]] = arr.reshape(-1)[owned]
+            if comm.size > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(full, group=comm.group)
+            self._full = full if _is_torch(st.arr) else full.numpy()
+        return self._full
+
+    def __getattr__(self, name):
+        st = self._state
+        info = st._global_field_info
+        if name.startswith("_") or info is None or name not in dict(st.fields):
+            raise AttributeError(f"'{type(st).__name__}' has no field '{name}'")
+        idx = _GlobalFieldIndices(info[name])[(slice(None),) * len(info[name].global_shape)]
+        full = self._gather()
+        picked = full[torch.as_tensor(idx, device=full.device)] if _is_torch(full) else full[idx]
+        return picked.reshape(tuple(info[name].global_shape))
+
+
+class _GlobalView:
+    """Descriptor behind `Compound._g` (compound/mpi.py:58-83): indices on the class, gathered data on an instance."""
+
+    def __get__(self, instance, owner):
+        if owner._layout is None:
+            raise ValueError(f"Compound class '{owner.__name__}' is missing a DOF layout. Global view requires a complete MPI layout.")
+        return _GlobalIndicesView(owner) if instance is None else _GlobalDataView(instance)
+
+
 class Compound:
     """Flat state with named fields; see the module docstring."""
+
+    _g = _GlobalView()
 
     fields: tuple = ()
     size: int = 0

@@ -74,6 +74,15 @@ def _as_comm(comm):
     return Comm(comm)  # a torch.distributed ProcessGroup
 
 
+class FieldGlobalInfo(NamedTuple):
+    """compound/mpi.py:48-52: where a field lives in the natural (mesh-global) DOF numbering."""
+
+    global_shape: tuple
+    global_base_offset: int
+    global_strides: tuple
+    global_subset: np.ndarray | None = None
+
+
 class _NeighborRoute(NamedTuple):
     """mpi.py:40-57 (_NeighborDofRoute / _NeighborNnzRoute)."""
 
@@ -138,7 +147,7 @@ def layout_from_compound(compound_cls, partition_info, comm):
     """compound/mpi.py:288-494 (`_layout_from_compound`): natural DOF ids and owned mask for every field
     of a Compound on a partitioned mesh, then `_create_dof_layout`.  Nodal (full and incomplete), Local
     and Shared fields follow the reference's rules; the returned info dict maps field name ->
-    (global shape, global base offset)."""
+    FieldGlobalInfo (global shape, base offset, strides, node subset), the data behind `Compound._g`."""
     from .compound import Local, Nodal, Shared
 
     comm = _as_comm(comm)
@@ -149,6 +158,12 @@ def layout_from_compound(compound_cls, partition_info, comm):
     local_max = int(l2g_nodes.max()) if l2g_nodes.size else -1
     n_nodes_global = max(comm.allgather(local_max)) + 1
     cursor, done, info = 0, {}, {}
+
+    def describe(f, n_items_global, base, subset):
+        # a field is an affine window of its root block; per-item layout is the same locally and globally, so the
+        # strides carry over and only the origin moves
+        return FieldGlobalInfo((n_items_global, *f.shape[1:]), base + (f._base_offset - f._root_slice.start), tuple(f._strides), subset)
+
     for name, f in compound_cls.fields:
         sl = f._root_slice
         key = (sl.start, sl.stop)
@@ -157,8 +172,9 @@ def layout_from_compound(compound_cls, partition_info, comm):
         per_item = int(np.prod(root_shape[1:])) if len(root_shape) > 1 else 1
         size_local = sl.stop - sl.start
         if key in done:
-            info[name] = done[key]
+            info[name] = describe(f, *done[key])
             continue
+        g_subset = None
         if isinstance(ft, Local):
             sizes = comm.allgather(size_local)
             n_items_global = sum(sizes) // per_item
@@ -185,8 +201,8 @@ def layout_from_compound(compound_cls, partition_info, comm):
                 owned[sl] = True
         else:
             raise TypeError(f"Unsupported field type: {type(ft)}")
-        done[key] = ((n_items_global, *root_shape[1:]), cursor)
-        info[name] = done[key]
+        done[key] = (n_items_global, cursor, g_subset)
+        info[name] = describe(f, *done[key])
         cursor += n_items_global * per_item
     return _create_dof_layout(natural, owned, cursor, comm), info
 

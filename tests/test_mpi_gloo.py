@@ -252,12 +252,81 @@ def _body_periodic_mpi(rank, world):
         assert aug[0, 2] != 0 and aug[2, 0] != 0
 
 
+def _body_global_views(rank, world):
+    """reference tests/test_compound_mpi.py:22-80 (global indices, full and incomplete nodal fields) and :83-167
+    (stacked fields: global indices and the gathered global data of `state._g`)."""
+    from tatva_b200.compound import Compound, FieldSize, Nodal, field, stack_fields
+    from tatva_b200.mesh import Mesh, PartitionInfo
+
+    comm = dist.group.WORLD
+    if rank == 0:
+        l2g, n_owned, l_nodes = np.array([0, 1, 2], dtype=np.int32), 2, np.array([1])
+    else:
+        l2g, n_owned, l_nodes = np.array([2, 3, 1], dtype=np.int32), 2, np.array([2, 1])
+    mesh = Mesh(coords=np.zeros((len(l2g), 1)), elements=np.zeros((0, 2), dtype=np.int32))
+
+    class A(Compound, mesh=mesh, partition_info=PartitionInfo(l2g, n_owned), comm=comm):
+        u = field(shape=(FieldSize.AUTO, 2))
+        l = field(shape=(FieldSize.AUTO, 1), field_type=Nodal(node_ids=l_nodes))  # noqa: E741
+
+    np.testing.assert_array_equal(A._g.u[0], [0, 1])
+    np.testing.assert_array_equal(A._g.u[3, 1], [7])
+    np.testing.assert_array_equal(A._g.l[1], [8])  # l lives on global nodes {1, 3}, after the 8 DOFs of u
+    np.testing.assert_array_equal(A._g.l[3], [9])
+    np.testing.assert_array_equal(A._g.l[:], [8, 9])
+    np.testing.assert_array_equal(A._g.l[1:2], [8])
+    np.testing.assert_array_equal(A._g.l[2:4], [9])
+    np.testing.assert_array_equal(A._g.l[:2], [8])
+    np.testing.assert_array_equal(A._g.l[2:], [9])
+    np.testing.assert_array_equal(A._g.l[np.array([3, 1])], [9, 8])
+    with pytest.raises(NotImplementedError):
+        A._g.l[::2]
+    with pytest.raises(IndexError):
+        A._g.l[0]
+    with pytest.raises(AttributeError):
+        A._g.nope
+
+    # stacked fields: 3 global nodes; rank 0 owns 0 and 1, rank 1 owns 2
+    if rank == 0:
+        l2g, n_owned = np.array([0, 1, 2], dtype=np.int32), 2
+    else:
+        l2g, n_owned = np.array([2, 0, 1], dtype=np.int32), 1
+    mesh = Mesh(coords=np.zeros((3, 1)), elements=np.zeros((0, 2), dtype=np.int32))
+
+    @stack_fields("u", "v")
+    class B(Compound, mesh=mesh, partition_info=PartitionInfo(l2g, n_owned), comm=comm):
+        u = field(shape=(FieldSize.AUTO, 1), field_type=Nodal())
+        v = field(shape=(FieldSize.AUTO, 2), field_type=Nodal())
+
+    np.testing.assert_array_equal(B._g.u[:], [0, 3, 6])
+    np.testing.assert_array_equal(B._g.v[:], [1, 2, 4, 5, 7, 8])
+    assert B._g.u[1, 0] == 3 and B._g.v[2, 1] == 8
+    for as_torch in (False, True):
+        if rank == 0:
+            st = B(u=np.array([[10.0], [20.0], [-1.0]]), v=np.array([[1.0, 2.0], [3.0, 4.0], [-1.0, -1.0]]))  # last row: ghost
+        else:
+            st = B(u=np.array([[30.0], [-1.0], [-1.0]]), v=np.array([[5.0, 6.0], [-1.0, -1.0], [-1.0, -1.0]]))
+        if as_torch:
+            st = B(torch.as_tensor(st.arr))
+        view = st._g
+        g_u, g_v = view.u, view.v  # one all-reduce, cached in the view
+        np.testing.assert_allclose(np.asarray(g_u), [[10.0], [20.0], [30.0]])
+        np.testing.assert_allclose(np.asarray(g_v), [[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]])
+        assert isinstance(g_u, torch.Tensor) == as_torch
+
+    class NoLayout(Compound):
+        w = field(shape=(2,))
+
+    with pytest.raises(ValueError):
+        NoLayout._g
+
+
 # ---- pytest entry points -----------------------------------------------------------------------------
 
 
 @pytest.mark.parametrize(
     "body",
-    ["_body_layout", "_body_communication", "_body_incomplete_nodal", "_body_hessian", "_body_allreduce", "_body_partitioned_residual", "_body_lifter_adapt_layout", "_body_periodic_mpi"],
+    ["_body_layout", "_body_communication", "_body_incomplete_nodal", "_body_hessian", "_body_allreduce", "_body_partitioned_residual", "_body_lifter_adapt_layout", "_body_periodic_mpi", "_body_global_views"],
 )
 def test_two_rank_gloo(body):
     _run(body, world=2)
