@@ -369,6 +369,15 @@ def test_find_containing_polygons_matches_reference(golden, kind):
     np.testing.assert_array_equal(got.cpu().numpy(), g("containing"))
 
 
+def test_find_containing_polygons_includes_boundary_points():
+    """reference tests/test_mesh.py:7-24."""
+    from tatva_b200.mesh import find_containing_polygons
+
+    polygons = np.array([[[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]], [[1.0, 0.0], [2.0, 0.0], [2.0, 1.0], [1.0, 1.0]]])
+    points = np.array([[0.5, 0.5], [1.0, 0.5], [1.5, 0.5]])
+    np.testing.assert_array_equal(find_containing_polygons(points, polygons).cpu().numpy(), [0, 0, 1])
+
+
 def test_interpolate_known_answer_two_triangles():
     """reference tests/test_operator.py:145-159."""
     from tatva_b200 import element

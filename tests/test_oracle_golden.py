@@ -95,6 +95,13 @@ def test_interpolate_and_point_location_match_reference(golden, kind):
         np.testing.assert_allclose(got, pts.sum(axis=1))
 
 
+def test_find_containing_polygons_includes_boundary_points():
+    """reference tests/test_mesh.py:7-24: a point on the edge shared by two polygons belongs to the first one."""
+    polygons = np.array([[[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]], [[1.0, 0.0], [2.0, 0.0], [2.0, 1.0], [1.0, 1.0]]])
+    points = np.array([[0.5, 0.5], [1.0, 0.5], [1.5, 0.5]])
+    np.testing.assert_array_equal(orc.find_containing_polygons(points, polygons), [0, 0, 1])
+
+
 @pytest.mark.parametrize("kind", ["line2", "line3"])
 def test_line_operator_matches_reference(golden, kind):
     """Line2 / Line3 on a curved polyline: arc-length Jacobian and derivative (reference element/base.py:144-242)."""
