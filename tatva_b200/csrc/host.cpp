@@ -76,6 +76,33 @@ int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, 
   return TATVA_OK;
 }
 
+// Block structure of a mesh pattern: the b rows of a node are identical and made of full, aligned b-wide column
+// blocks, the diagonal block included (pattern_from_mesh with b DOFs per node; rows of nodes that belong to no element
+// are empty).  Returns the largest such b in [2, 8], or 1.
+static int detect_block_size(const int32_t* indptr, const int32_t* indices, int64_t n) {
+  for (int b = 8; b >= 2; --b) {
+    if (n % b) continue;
+    bool ok = true;
+    for (int64_t r = 0; r < n && ok; r += b) {
+      const int32_t p0 = indptr[r], len = indptr[r + 1] - p0;
+      if (len % b) ok = false;
+      for (int j = 1; j < b && ok; ++j)
+        ok = (indptr[r + j + 1] - indptr[r + j] == len) &&
+             std::equal(indices + p0, indices + p0 + len, indices + indptr[r + j]);
+      bool diagonal = (len == 0);
+      for (int32_t k = 0; k < len && ok; k += b) {
+        const int32_t c0 = indices[p0 + k];
+        ok = (c0 % b == 0);
+        diagonal |= (c0 == r);
+        for (int j = 1; j < b && ok; ++j) ok = indices[p0 + k + j] == c0 + j;
+      }
+      ok = ok && diagonal;
+    }
+    if (ok) return b;
+  }
+  return 1;
+}
+
 // tatva/sparse/_coloring.py:270-283 -> :27-48 (pattern of A@A) -> :136-153 (first-fit, natural order).
 // The squared graph is never materialised: the distance-2 neighbours of i are the columns of the rows
 // named by row i.  `stamp[c] == i` marks colour c as used by a neighbour of i.
@@ -86,11 +113,49 @@ int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, i
   std::vector<int64_t> stamp;
   stamp.reserve(256);
   int32_t maxc = -1;
+  const int b = detect_block_size(indptr, indices, n);
+  if (b > 1) {
+    // Node-level sweep, identical to the per-DOF greedy: the b DOFs of a node see the same distance-2 set, and between
+    // two of them only the node's own previous DOF gets coloured, so the forbidden set is built once per node and
+    // the next DOF continues the search above the colour just given.  (b^2 fewer pattern entries are visited.)
+    const int64_t n_nodes = n / b;
+    for (int64_t r = 0; r < n_nodes; ++r) {
+      const int32_t p0 = indptr[r * b], p1 = indptr[r * b + 1];
+      if (p0 == p1) {  // node in no element: its DOFs have no neighbours at all, each takes colour 0
+        for (int j = 0; j < b; ++j) colors[r * b + j] = 0;
+        if (maxc < 0) maxc = 0;
+        continue;
+      }
+      for (int32_t a = p0; a < p1; a += b) {
+        const int64_t m = indices[a] / b;  // neighbour node
+        const int32_t q0 = indptr[m * b], q1 = indptr[m * b + 1];
+        for (int32_t t = q0; t < q1; t += b) {
+          const int32_t* cc = colors + indices[t];  // the b DOFs of a node two hops away
+          for (int j = 0; j < b; ++j) {
+            const int32_t c = cc[j];
+            if (c >= 0) {
+              if ((size_t)c >= stamp.size()) stamp.resize(c + 1, -1);
+              stamp[c] = r;
+            }
+          }
+        }
+      }
+      int32_t c = 0;
+      for (int j = 0; j < b; ++j) {
+        while ((size_t)c < stamp.size() && stamp[c] == r) ++c;
+        colors[r * b + j] = c;
+        if (c > maxc) maxc = c;
+        ++c;  // the colour just used is now forbidden, and every smaller one already was
+      }
+    }
+    if (n_colors) *n_colors = maxc + 1;
+    return TATVA_OK;
+  }
   for (int64_t i = 0; i < n; ++i) {
     for (int32_t a = indptr[i]; a < indptr[i + 1]; ++a) {
       const int32_t k = indices[a];
-      for (int32_t b = indptr[k]; b < indptr[k + 1]; ++b) {
-        const int32_t c = colors[indices[b]];
+      for (int32_t bb = indptr[k]; bb < indptr[k + 1]; ++bb) {
+        const int32_t c = colors[indices[bb]];
         if (c >= 0) {
           if ((size_t)c >= stamp.size()) stamp.resize(c + 1, -1);
           stamp[c] = i;

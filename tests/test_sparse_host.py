@@ -114,3 +114,40 @@ def test_invalid_arguments_return_error_codes():
     assert L.tatva_host_pattern_from_mesh(bad.ctypes.data_as(_lib.c_i32p), 1, 3, 3, 2, ip.ctypes.data_as(_lib.c_i32p), None, C.byref(nnz)) == -1
     assert L.tatva_error_string(-1) == b"invalid argument"
     assert L.tatva_plan_destroy(None) == 0
+
+
+@pytest.mark.parametrize("case", ["tri3_d1", "tri3_d3", "tet4_d4", "hex8_d3", "shuffled_isolated_d2", "shuffled_isolated_d3", "random"])
+def test_colouring_node_level_sweep_is_bit_exact_with_the_per_dof_greedy(case):
+    """The C++ colouring detects the block structure of mesh patterns (dpn identical rows per node) and sweeps node
+    by node; the colours must equal the per-DOF first-fit of the in-tree reference algorithm
+    (tatva/sparse/_coloring.py:27-48, :136-153, :270-283) restated in the oracle — also with nodes that belong to no
+    element, shuffled node numbering, and patterns without block structure (generic path)."""
+    import scipy.sparse as sps
+    from oracle import tatva_oracle as orc
+
+    rng = np.random.default_rng(0)
+    if case == "random":
+        A = sps.random(80, 80, density=0.06, random_state=1, format="csr")
+        A = (A + A.T + sps.eye(80)).tocsr()
+        A.sort_indices()
+        ip, ix, n = A.indptr, A.indices, 80
+    else:
+        dpn = int(case[-1])
+        if case.startswith("tri3"):
+            c, el = orc.mesh_unit_square_tri(7, 5)
+            nn = len(c)
+        elif case.startswith("tet4"):
+            c, el = orc.mesh_box_tet((1, 1, 1), (3, 3, 2))
+            nn = len(c)
+        elif case.startswith("hex8"):
+            c, el = orc.mesh_box_hex(3)
+            nn = len(c)
+        else:
+            c, el = orc.mesh_unit_square_tri(6, 6)
+            nn = len(c) + 5
+            el = rng.permutation(nn)[el]
+        ip, ix = orc.pattern_from_mesh(el, nn, dpn)
+        n = nn * dpn
+    ref = orc.distance2_colors(ip, ix, n)
+    got = sparse.distance2_colors(np.asarray(ip, dtype=np.int32), np.asarray(ix, dtype=np.int32), n)
+    np.testing.assert_array_equal(got, ref)
