@@ -264,6 +264,13 @@ int tatva_cg_direction(double* d_p, const double* d_r, const double* d_minv, int
 int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, int64_t n_nodes,
                                  int dofs_per_node, int32_t* indptr, int32_t* indices,
                                  int64_t* nnz);
+/* pattern_from_compound (tatva/sparse/_extraction.py:118-245) for any field layout: every element couples all the
+ * DOFs of its row of elem_dofs (n_elems, width; -1 = absent); the DOFs listed in `diag` get a diagonal entry (fields
+ * that are not nodal).  Sorted unique pairs as CSR; two-call protocol (indices == NULL: indptr and *nnz only).   */
+int tatva_host_pattern_from_element_dofs(const int32_t* elem_dofs, int64_t n_elems, int width,
+                                         const int32_t* diag, int64_t n_diag, int64_t n_dofs,
+                                         int32_t* indptr, int32_t* indices, int64_t* nnz);
+
 /* distance2_colors (tatva-coloring; in-tree spec tatva/sparse/_coloring.py:27-48,:136-153,:270-283):
  * greedy first-fit in natural order on the pattern of A@A.                                  */
 int tatva_host_distance2_colors(const int32_t* indptr, const int32_t* indices, int64_t n,

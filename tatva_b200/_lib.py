@@ -68,6 +68,7 @@ SIGNATURES = {
     "tatva_pcg_after_matvec": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "tatva_host_pattern_from_mesh": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, C.c_int, c_i32p, c_i32p, c_i64p]),
     "tatva_host_distance2_colors": (C.c_int, [c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p]),
+    "tatva_host_pattern_from_element_dofs": (C.c_int, [c_i32p, C.c_int64, C.c_int, c_i32p, C.c_int64, C.c_int64, c_i32p, c_i32p, C.POINTER(C.c_int64)]),
     "tatva_host_node_to_elements": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, c_i32p, c_i32p]),
     "tatva_host_build_tiles": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, C.POINTER(C.c_uint16), c_i32p]),
     "tatva_host_csr_element_positions": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p]),

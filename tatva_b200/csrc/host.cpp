@@ -76,6 +76,66 @@ int tatva_host_pattern_from_mesh(const int32_t* conn, int64_t n_elems, int npe, 
   return TATVA_OK;
 }
 
+// General pattern of tatva/sparse/_extraction.py:118-245 (pattern_from_compound): every element couples all the
+// DOFs listed in its row of `elem_dofs` (n_elems, width; -1 = absent), and the DOFs in `diag` (n_diag) get their
+// diagonal entry.  Result = sorted unique (row, col) pairs as CSR, identical to the reference's
+// np.unique(row * n + col).  Two-call protocol: indices == NULL fills indptr and *nnz only.
+int tatva_host_pattern_from_element_dofs(const int32_t* elem_dofs, int64_t n_elems, int width, const int32_t* diag,
+                                         int64_t n_diag, int64_t n, int32_t* indptr, int32_t* indices, int64_t* nnz_out) {
+  if (!indptr || !nnz_out || n <= 0 || n_elems < 0 || width < 0 || n_diag < 0 || (n_elems * width > 0 && !elem_dofs) ||
+      (n_diag > 0 && !diag))
+    return TATVA_E_INVALID;
+  const int64_t total = n_elems * width;
+  std::vector<int64_t> d2e_ptr(n + 1, 0);
+  for (int64_t i = 0; i < total; ++i) {
+    const int32_t d = elem_dofs[i];
+    if (d >= n) return TATVA_E_INVALID;
+    if (d >= 0) d2e_ptr[d + 1]++;
+  }
+  for (int64_t d = 0; d < n; ++d) d2e_ptr[d + 1] += d2e_ptr[d];
+  std::vector<int32_t> d2e(d2e_ptr[n]);
+  {
+    std::vector<int64_t> fill(d2e_ptr.begin(), d2e_ptr.end() - 1);
+    for (int64_t e = 0; e < n_elems; ++e)
+      for (int a = 0; a < width; ++a) {
+        const int32_t d = elem_dofs[e * width + a];
+        if (d >= 0) d2e[fill[d]++] = (int32_t)e;
+      }
+  }
+  std::vector<char> on_diag(n, 0);
+  for (int64_t i = 0; i < n_diag; ++i) {
+    if (diag[i] < 0 || diag[i] >= n) return TATVA_E_INVALID;
+    on_diag[diag[i]] = 1;
+  }
+  std::vector<std::vector<int32_t>> rows(n);
+#pragma omp parallel for schedule(dynamic, 2048)
+  for (int64_t d = 0; d < n; ++d) {
+    std::vector<int32_t>& r = rows[d];
+    r.reserve((d2e_ptr[d + 1] - d2e_ptr[d]) * width + 1);
+    int32_t last = -1;
+    for (int64_t k = d2e_ptr[d]; k < d2e_ptr[d + 1]; ++k) {
+      if (d2e[k] == last) continue;  // an element listing the DOF twice appears twice in a row: skip the repeat
+      last = d2e[k];
+      const int32_t* el = elem_dofs + (int64_t)last * width;
+      for (int a = 0; a < width; ++a)
+        if (el[a] >= 0) r.push_back(el[a]);
+    }
+    if (on_diag[d]) r.push_back((int32_t)d);
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+  }
+  int64_t nnz = 0;
+  for (int64_t d = 0; d < n; ++d) nnz += (int64_t)rows[d].size();
+  *nnz_out = nnz;
+  if (nnz > INT32_MAX) return TATVA_E_INVALID;
+  indptr[0] = 0;
+  for (int64_t d = 0; d < n; ++d) indptr[d + 1] = indptr[d] + (int32_t)rows[d].size();
+  if (!indices) return TATVA_OK;
+#pragma omp parallel for schedule(static)
+  for (int64_t d = 0; d < n; ++d) std::copy(rows[d].begin(), rows[d].end(), indices + indptr[d]);
+  return TATVA_OK;
+}
+
 // Block structure of a mesh pattern: the b rows of a node are identical and made of full, aligned b-wide column
 // blocks, the diagonal block included (pattern_from_mesh with b DOFs per node; rows of nodes that belong to no element
 // are empty).  Returns the largest such b in [2, 8], or 1.

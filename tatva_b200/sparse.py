@@ -51,10 +51,27 @@ def pattern_from_mesh(mesh: Mesh, n_dofs_per_node: int) -> sp.csr_matrix:
     return sp.csr_matrix((np.ones(indices.shape[0], dtype=np.int8), indices, indptr), shape=(n, n))
 
 
+def _pattern_from_element_dofs(elem_dofs: np.ndarray, diag: np.ndarray, n: int):
+    """CSR (indptr, indices) of the pattern coupling, per element, all DOFs of its row (-1 = absent), plus diagonal
+    entries for `diag`: the result of np.unique(row * n + col) over all pairs (_extraction.py:74-79, :207-216)."""
+    L = _lib.lib()
+    i32 = lambda a: a.ctypes.data_as(_lib.c_i32p)  # noqa: E731
+    E, w = (int(elem_dofs.shape[0]), int(elem_dofs.shape[1])) if elem_dofs.size else (0, 0)
+    indptr = np.zeros(n + 1, dtype=np.int32)
+    nnz = C.c_int64()
+    args = (i32(elem_dofs) if E * w else None, E, w, i32(diag) if diag.size else None, int(diag.size), n, i32(indptr))
+    _lib.check(L.tatva_host_pattern_from_element_dofs(*args, None, C.byref(nnz)), "tatva_host_pattern_from_element_dofs")
+    indices = np.empty(nnz.value, dtype=np.int32)
+    if nnz.value:
+        _lib.check(L.tatva_host_pattern_from_element_dofs(*args, i32(indices), C.byref(nnz)), "tatva_host_pattern_from_element_dofs")
+    return indptr, indices
+
+
 def pattern_from_compound(compound_cls, block_wise: bool = False):
     """tatva/sparse/_extraction.py:118-245: nodal fields coupled within elements, every other field
-    diagonal.  The all-full-Nodal stacked layout (node-interleaved, compound/__init__.py:334-389) takes the
-    fast C++ path; anything else goes through the general pair-list construction."""
+    diagonal.  The element -> DOF lists are assembled here; the sorted unique pair set is built in C++
+    (`tatva_host_pattern_from_element_dofs`, one sorted row per DOF in parallel) instead of sorting all
+    (npe * dpn)^2 * E pairs (38 s -> 0.5 s at config 5)."""
     from .compound import CompoundError, Nodal
 
     if compound_cls._mesh is None:
@@ -89,23 +106,10 @@ def pattern_from_compound(compound_cls, block_wise: bool = False):
             )
             diagonal.append(idx.ravel())
     n = compound_cls.size
-    rows, cols = [], []
-    if coupled:
-        ed = np.concatenate(coupled, axis=1)
-        w = ed.shape[1]
-        r, c = np.repeat(ed, w, axis=1).ravel(), np.tile(ed, (1, w)).ravel()
-        ok = (r >= 0) & (c >= 0)
-        rows.append(r[ok])
-        cols.append(c[ok])
-    if diagonal:
-        d = np.concatenate(diagonal)
-        rows.append(d)
-        cols.append(d)
-    if not rows:
-        full = sp.csr_matrix((n, n), dtype=np.int8)
-    else:
-        lin = np.unique(np.concatenate(rows).astype(np.int64) * n + np.concatenate(cols).astype(np.int64))
-        full = sp.csr_matrix((np.ones(lin.shape[0], dtype=np.int8), (lin // n, lin % n)), shape=(n, n))
+    ed = np.ascontiguousarray(np.concatenate(coupled, axis=1), dtype=np.int32) if coupled else np.zeros((0, 0), dtype=np.int32)
+    dg = np.ascontiguousarray(np.concatenate(diagonal), dtype=np.int32) if diagonal else np.zeros(0, dtype=np.int32)
+    indptr, indices = _pattern_from_element_dofs(ed, dg, n)
+    full = sp.csr_matrix((np.ones(indices.shape[0], dtype=np.int8), indices, indptr), shape=(n, n))
     if not block_wise:
         return full
     slices, seen = [], set()

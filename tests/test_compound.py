@@ -134,3 +134,46 @@ def test_pattern_from_compound_matches_mesh_pattern_for_stacked_nodal():
     np.testing.assert_array_equal(a.indices, b.indices)
     blocks = sparse.pattern_from_compound(S, block_wise=True)
     assert len(blocks) == 1 and blocks[0][0].shape == (S.size, S.size)
+
+
+def test_pattern_from_compound_mixed_layout_equals_the_pair_list_construction():
+    """A full nodal field, a nodal field on a node subset and a shared field: the C++ pattern builder must give
+    exactly the unique (row, col) pairs the reference's construction produces (sparse/_extraction.py:118-245:
+    nodal fields coupled within elements, every other field diagonal)."""
+    import warnings
+
+    import scipy.sparse as sp
+
+    from oracle import tatva_oracle as orc
+    from tatva_b200 import sparse
+    from tatva_b200.compound import Compound, FieldSize, FieldType, Nodal, field
+    from tatva_b200.mesh import Mesh
+
+    c, el = orc.mesh_unit_square_tri(5, 4)
+    mesh = Mesh(coords=c, elements=el.astype(np.int32))
+    sub = np.array([0, 3, 7, 8, 20])
+
+    class Mixed(Compound, mesh=mesh):
+        u = field(shape=(FieldSize.AUTO, 2))
+        lam = field(shape=(FieldSize.AUTO, 1), field_type=Nodal(node_ids=sub))
+        g = field(shape=(3,), field_type=FieldType.SHARED)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # "Custom space detected ..." for the shared field
+        pat = sparse.pattern_from_compound(Mixed)
+    fields = dict(Mixed.fields)
+    nd_u = np.asarray(fields["u"].indices(slice(None))).reshape(len(c), 2)
+    nd_l = np.full((len(c), 1), -1)
+    nd_l[sub] = np.asarray(fields["lam"].indices(slice(None))).reshape(-1, 1)
+    ed = np.concatenate([nd_u[el].reshape(len(el), -1), nd_l[el].reshape(len(el), -1)], axis=1)
+    pairs = set()
+    for row in ed:
+        v = row[row >= 0]
+        pairs.update((int(a), int(b)) for a in v for b in v)
+    pairs.update((int(d), int(d)) for d in np.asarray(fields["g"].indices(slice(None))))
+    rows, cols = zip(*sorted(pairs))
+    ref = sp.csr_matrix((np.ones(len(pairs), dtype=np.int8), (rows, cols)), shape=(Mixed.size, Mixed.size))
+    ref.sort_indices()
+    assert pat.dtype == np.int8 and pat.indptr.dtype == np.int32
+    np.testing.assert_array_equal(pat.indptr, ref.indptr)
+    np.testing.assert_array_equal(pat.indices, ref.indices)
