@@ -57,6 +57,7 @@ class Operator:
         self.gdim = 1 if self._line else self.dim
         self.n_elements, self.npe = self.elements.shape
         self.nq = len(element.quad_weights)
+        self._batch_size_arg, self._sort_elements = batch_size, bool(sort_elements)
         self.batch_size = self.n_elements if batch_size is None else int(batch_size)  # operator.py:116-117
         self.quad_points = torch.as_tensor(element.quad_points, dtype=torch.float64, device=self.device)
         self._L = _lib.lib()
@@ -90,6 +91,16 @@ class Operator:
         self._tiles = None
         if stage_tiles:
             self._build_tiles()
+
+    def _replace(self, **changes) -> "Operator":
+        """A new Operator with the given constructor arguments changed (operator.py:497-504, `dataclasses.replace`);
+        a new plan is created, nothing is shared with `self`."""
+        kw = dict(mesh=self.mesh, element=self.element, batch_size=self._batch_size_arg, cache_weights=self.cache_weights, device=self.device, sort_elements=self._sort_elements, stage_tiles=self._tiles is not None)
+        unknown = set(changes) - set(kw)
+        if unknown:
+            raise TypeError(f"Operator._replace() got unexpected field(s): {sorted(unknown)}")
+        kw.update(changes)
+        return type(self)(kw.pop("mesh"), kw.pop("element"), kw.pop("batch_size"), kw.pop("cache_weights"), **kw)
 
     def _build_tiles(self):
         conn = np.ascontiguousarray(self.elements_fused.cpu().numpy(), dtype=np.int32)

@@ -309,6 +309,19 @@ def test_line_elements_on_a_curved_boundary(golden, kind, variant):
     np.testing.assert_allclose(ut.grad.sum(0).cpu().numpy(), trac.cpu().numpy() * length, rtol=1e-12)
 
 
+def test_operator_replace_builds_an_independent_operator():
+    """Operator._replace (reference operator.py:497-504)."""
+    from tatva_b200 import element
+
+    c, el, u, _, _ = _case("hex8", 3)
+    op = _make_op("hex8", c, el)
+    op2 = op._replace(cache_weights=True)
+    assert op2 is not op and op2.cache_weights and not op.cache_weights and op2.element == element.Hexahedron8()
+    _assert_close(op2.grad(u), op.grad(u).cpu().numpy())
+    with pytest.raises(TypeError):
+        op._replace(nope=1)
+
+
 def test_line_element_needs_plane_coordinates():
     from tatva_b200 import element
     import tatva_b200
