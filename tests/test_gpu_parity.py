@@ -176,6 +176,57 @@ def test_hvp_is_linear_and_symmetric_at_scale():
     assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
 
 
+def test_full_size_properties_config3_hex8_128():
+    """BASELINE config 3 at its full size (Hex8 128^3, 6.44 M DOFs; far beyond the NumPy oracle): size-independent
+    properties of the fused kernels.  Linearity and symmetry of the HVP, and consistency of the three kernels with
+    each other by central differences: dE(u)[v] = r.v and dr(u)[v] = H v."""
+    c, el, u, v, (mname, omat) = _case("hex8", 128)
+    op = _make_op("hex8", c, el)
+    mat = _material(mname, omat)
+    E, R, H = op.energy(mat), op.residual(mat), op.hvp(mat)
+    ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
+    wt = torch.as_tensor(np.random.default_rng(5).normal(size=v.shape), device="cuda")
+    Hv, Hw = H(ut, vt), H(ut, wt)
+    comb = H(ut, 0.3 * vt - 1.7 * wt)
+    assert float((comb - (0.3 * Hv - 1.7 * Hw)).norm() / comb.norm()) < 1e-12
+    a, b = float((wt * Hv).sum()), float((vt * Hw).sum())
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    r = R(ut)
+    assert bool(torch.isfinite(r).all()) and bool(torch.isfinite(Hv).all())
+    # energy vs residual along the steepest direction (no cancellation in r.d)
+    d = r / r.norm()
+    eps = 1e-6
+    fd = (float(E(ut + eps * d)) - float(E(ut - eps * d))) / (2 * eps)
+    assert abs(fd - float((r * d).sum())) <= 1e-5 * float(r.norm())
+    # residual vs HVP
+    fd_h = (R(ut + eps * vt) - R(ut - eps * vt)) / (2 * eps)
+    assert float((fd_h - Hv).norm() / Hv.norm()) < 1e-5
+
+
+def test_full_size_assembled_matrix_config2_tet4():
+    """BASELINE config 2 at its full size (Tet4 box n = 55: 998 250 elements, 23 036 814 nnz): the assembled CSR
+    matrix applied to a vector equals the matrix-free HVP, the pattern has the surveyed nnz, and it is symmetric
+    in action (<w, K v> = <v, K w>)."""
+    import scipy.sparse as sps
+
+    from tatva_b200 import sparse
+
+    c, el, u, v, (mname, omat) = _case("tet4", 55)
+    op = _make_op("tet4", c, el)
+    mat = _material(mname, omat)
+    pat = sparse.pattern_from_mesh(op.mesh, 3)
+    assert pat.nnz == 23036814 and el.shape[0] == 998250  # SURVEY section 8, config table
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
+    K = sps.csr_matrix((data, pat.indices, pat.indptr), shape=pat.shape)
+    Hv = op.hvp(mat)(u, v).cpu().numpy().ravel()
+    Kv = K @ v.ravel()
+    assert np.linalg.norm(Kv - Hv) / np.linalg.norm(Hv) < 1e-12
+    w = np.random.default_rng(9).normal(size=v.size)
+    a, b = float(w @ Kv), float(v.ravel() @ (K @ w))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+
+
 # ---- autograd route: user energy on the building blocks == fused kernels ------------------------
 
 
