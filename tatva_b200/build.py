@@ -41,11 +41,27 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if needed) and return the library path.  Safe to call from several processes at once (one rank per
+    GPU importing a fresh checkout): an exclusive file lock serialises them, the late comers find the library up to
+    date, and the link goes to a temporary name that is renamed into place."""
+    import fcntl
+
     if not force and not needs_build():
         return LIB
-    nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return LIB
+            return _build_locked(verbose, objdir)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, objdir: str) -> str:
+    nvcc = _nvcc()
     objs = []
     procs = []
     for s in SOURCES:
@@ -61,8 +77,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
     subprocess.run(link, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 
