@@ -70,6 +70,15 @@ int tatva_plan_create(tatva_plan_t** plan, int element, int64_t n_nodes, int64_t
 int tatva_plan_destroy(tatva_plan_t* plan);
 int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, int* nq,
                     int64_t* n_nodes, int64_t* n_elems);
+/* Measurement switch, not part of the drop-in surface: 0 (default) = the tuned kernels; 1 = the generic element /
+ * law templates everywhere (TATVA_VARIANT_GENERIC, the parity cross-check of every specialised kernel); other
+ * values select alternative implementations kept for A/B timing, per kernel family (DESIGN.md sections 3.1-3.3):
+ *   Hex8 x neo-Hookean HVP   2, 3, 8, 9, 15, 16, 17, 20, 22, 23, 25, 26, 27 (sector-grouped scatter), 28 (16-byte gathers)
+ *   Hex8 residual / energy   2 = first modal kernel, 3 / 4 = pair kernel at other register / occupancy points
+ *   Tet4 x neo-Hookean       30 = persistent kernel with connectivity prefetch
+ *   building blocks          2 = element-per-thread staged kernels (same as 0), 3 = one thread per quadrature point
+ *   CSR assembly             2 = full assembly also where the symmetric entry point was called
+ * Every variant computes the same result to rounding; unknown values fall back to the default.                  */
 int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
 /* Optional shared-memory staging tiles for gather-bound elements (Tet4 x neo-Hookean residual / HVP): tile t =
  * elements [128 t, 128 (t+1)); d_tile_nodes[d_tile_ptr[t] .. d_tile_ptr[t+1]) are its sorted unique nodes and
