@@ -247,11 +247,13 @@ def interpolate_fixtures(out):
     from tatva.mesh import find_containing_polygons
 
     rng = np.random.default_rng(23)
-    for kind, cls in {"tri3": element.Tri3, "quad4": element.Quad4}.items():
+    for kind, cls in {"tri3": element.Tri3, "quad4": element.Quad4, "tri6": element.Tri6, "quad8": element.Quad8}.items():
         if kind == "tri3":
             c, el = orc.mesh_unit_square_tri(5, 4)
-        else:
+        elif kind == "quad4":
             c, el = orc.mesh_unit_square_quad(4, 5)
+        else:  # second-order elements: the polygon is the node loop in connectivity order, the Newton step is not exact
+            c, el = orc.mesh_second_order(kind, 3, 3)
         interior = (c[:, 0] > 1e-9) & (c[:, 0] < 1 - 1e-9) & (c[:, 1] > 1e-9) & (c[:, 1] < 1 - 1e-9)
         c = c + 0.04 * rng.uniform(-1, 1, c.shape) * interior[:, None]
         pts = rng.uniform(0.02, 0.98, size=(40, 2))
@@ -259,6 +261,11 @@ def interpolate_fixtures(out):
         nodes = c[[0, 7, len(c) - 1]]
         inside = np.concatenate([pts, edge_mid, nodes])
         outside = np.array([[1.5, 0.5], [-0.2, 0.3], [0.5, 1.0001]])
+        if kind in ("tri6", "quad8"):
+            # keep only the points the reference itself locates (its node-loop polygons of second-order elements are
+            # self-intersecting, so some interior points are in no polygon); Operator.interpolate raises otherwise
+            found = np.asarray(find_containing_polygons(inside, c[el])) >= 0
+            inside = inside[found]
         u = rng.normal(size=(c.shape[0], 3))
         s = rng.normal(size=(c.shape[0],))
         p = f"interp_{kind}_"

@@ -72,7 +72,7 @@ def test_operator_matches_reference(golden, kind):
     np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, g("quadvals")), g("int_quad_per_el"), **kw)
 
 
-@pytest.mark.parametrize("kind", ["tri3", "quad4"])
+@pytest.mark.parametrize("kind", ["tri3", "quad4", "tri6", "quad8"])
 def test_interpolate_and_point_location_match_reference(golden, kind):
     """Operator.interpolate / find_containing_polygons (reference operator.py:399-463, mesh.py:294-388), including
     points on shared edges, on nodes and outside the mesh."""

@@ -13,11 +13,11 @@ def _bin(x, lo, inv, n):
     return 0 if not t > 0 else (int(t) if t < n else n - 1)
 
 
-@pytest.mark.parametrize("kind", ["tri3", "quad4"])
+@pytest.mark.parametrize("kind", ["tri3", "quad4", "tri6", "quad8"])
 def test_grid_search_equals_full_scan(kind):
     L = _lib.lib()
     rng = np.random.default_rng(0)
-    c, el = orc.mesh_unit_square_tri(13, 9) if kind == "tri3" else orc.mesh_unit_square_quad(7, 11)
+    c, el = {"tri3": lambda: orc.mesh_unit_square_tri(13, 9), "quad4": lambda: orc.mesh_unit_square_quad(7, 11), "tri6": lambda: orc.mesh_second_order("tri6", 6, 5), "quad8": lambda: orc.mesh_second_order("quad8", 5, 6)}[kind]()
     inner = (c[:, 0] > 1e-9) & (c[:, 0] < 1 - 1e-9) & (c[:, 1] > 1e-9) & (c[:, 1] < 1 - 1e-9)
     c = np.ascontiguousarray(c + 0.02 * rng.uniform(-1, 1, c.shape) * inner[:, None])
     el = np.ascontiguousarray(el, dtype=np.int32)
@@ -42,7 +42,7 @@ def test_grid_search_equals_full_scan(kind):
             r = orc.find_containing_polygons(pts[i : i + 1], c[el[cand]])[0]
             got[i] = cand[r] if r >= 0 else -1
     np.testing.assert_array_equal(got, ref)
-    assert (ref >= 0).sum() > 1000 and (ref < 0).sum() > 100
+    assert (ref >= 0).sum() > 500 and (ref < 0).sum() > 100
 
 
 def test_grid_builder_rejects_bad_input():

@@ -1,0 +1,106 @@
+"""GPU tests added at the end of round 1 AFTER the GPU budget was spent: they exercise code paths that are covered by
+the parity suite at other sizes / through other entry points, but these exact tests have not run on a B200 yet.
+The file name sorts last so that they run after the suites that have (pytest -x stops at the first failure)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tatva_oracle as orc
+from test_gpu_parity import _assert_close, _case, _make_op, _material
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_size_properties_config3_hex8_128():
+    """BASELINE config 3 at its full size (Hex8 128^3, 6.44 M DOFs; far beyond the NumPy oracle): size-independent
+    properties of the fused kernels.  Linearity and symmetry of the HVP, and consistency of the three kernels with
+    each other by central differences: dE(u)[v] = r.v and dr(u)[v] = H v."""
+    c, el, u, v, (mname, omat) = _case("hex8", 128)
+    op = _make_op("hex8", c, el)
+    mat = _material(mname, omat)
+    E, R, H = op.energy(mat), op.residual(mat), op.hvp(mat)
+    ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
+    wt = torch.as_tensor(np.random.default_rng(5).normal(size=v.shape), device="cuda")
+    Hv, Hw = H(ut, vt), H(ut, wt)
+    comb = H(ut, 0.3 * vt - 1.7 * wt)
+    assert float((comb - (0.3 * Hv - 1.7 * Hw)).norm() / comb.norm()) < 1e-12
+    a, b = float((wt * Hv).sum()), float((vt * Hw).sum())
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    r = R(ut)
+    assert bool(torch.isfinite(r).all()) and bool(torch.isfinite(Hv).all())
+    # energy vs residual along the steepest direction (no cancellation in r.d)
+    d = r / r.norm()
+    eps = 1e-6
+    fd = (float(E(ut + eps * d)) - float(E(ut - eps * d))) / (2 * eps)
+    assert abs(fd - float((r * d).sum())) <= 1e-5 * float(r.norm())
+    # residual vs HVP
+    fd_h = (R(ut + eps * vt) - R(ut - eps * vt)) / (2 * eps)
+    assert float((fd_h - Hv).norm() / Hv.norm()) < 1e-5
+
+
+def test_full_size_assembled_matrix_config2_tet4():
+    """BASELINE config 2 at its full size (Tet4 box n = 55: 998 250 elements, 23 036 814 nnz): the assembled CSR
+    matrix applied to a vector equals the matrix-free HVP, the pattern has the surveyed nnz, and it is symmetric
+    in action (<w, K v> = <v, K w>)."""
+    import scipy.sparse as sps
+
+    from tatva_b200 import sparse
+
+    c, el, u, v, (mname, omat) = _case("tet4", 55)
+    op = _make_op("tet4", c, el)
+    mat = _material(mname, omat)
+    pat = sparse.pattern_from_mesh(op.mesh, 3)
+    assert pat.nnz == 23036814 and el.shape[0] == 998250
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
+    K = sps.csr_matrix((data, pat.indices, pat.indptr), shape=pat.shape)
+    Hv = op.hvp(mat)(u, v).cpu().numpy().ravel()
+    Kv = K @ v.ravel()
+    assert np.linalg.norm(Kv - Hv) / np.linalg.norm(Hv) < 1e-12
+    w = np.random.default_rng(9).normal(size=v.size)
+    a, b = float(w @ Kv), float(v.ravel() @ (K @ w))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+
+
+def test_operator_replace_builds_an_independent_operator():
+    """Operator._replace (reference operator.py:497-504)."""
+    from tatva_b200 import element
+
+    c, el, u, _, _ = _case("hex8", 3)
+    op = _make_op("hex8", c, el)
+    op2 = op._replace(cache_weights=True)
+    assert op2 is not op and op2.cache_weights and not op.cache_weights and op2.element == element.Hexahedron8()
+    _assert_close(op2.grad(u), op.grad(u).cpu().numpy())
+    with pytest.raises(TypeError):
+        op._replace(nope=1)
+
+
+def test_find_containing_polygons_includes_boundary_points():
+    """reference tests/test_mesh.py:7-24."""
+    from tatva_b200.mesh import find_containing_polygons
+
+    polygons = np.array([[[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]], [[1.0, 0.0], [2.0, 0.0], [2.0, 1.0], [1.0, 1.0]]])
+    points = np.array([[0.5, 0.5], [1.0, 0.5], [1.5, 0.5]])
+    np.testing.assert_array_equal(find_containing_polygons(points, polygons).cpu().numpy(), [0, 0, 1])
+
+
+
+
+@pytest.mark.parametrize("kind", ["tri6", "quad8"])
+def test_interpolate_second_order_elements_match_reference(golden, kind):
+    """Operator.interpolate on Tri6 / Quad8 against the reference's outputs: the search polygon is the node loop in
+    connectivity order (corners, then mid-side nodes) and the single Newton step is not exact, exactly as the
+    reference behaves (operator.py:399-463)."""
+    import tatva_b200
+    from tatva_b200 import element
+
+    g = lambda k: golden[f"interp_{kind}_{k}"]  # noqa: E731
+    c, el = g("coords"), g("conn")
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), {"tri6": element.Tri6, "quad8": element.Quad8}[kind]())
+    _assert_close(op.interpolate(g("u"), g("points")), g("values_u"))
+    _assert_close(op.interpolate(g("s"), g("points")), g("values_s"))
+    allp = torch.as_tensor(np.concatenate([g("points"), g("outside")]), device="cuda")
+    out = torch.empty((allp.shape[0], 1), dtype=torch.float64, device="cuda")
+    elem = torch.empty(allp.shape[0], dtype=torch.int32, device="cuda")
+    op._call("tatva_op_interpolate", torch.as_tensor(g("s"), device="cuda").data_ptr(), 1, allp.data_ptr(), allp.shape[0], out.data_ptr(), elem.data_ptr())
+    np.testing.assert_array_equal(elem.cpu().numpy(), g("containing"))
