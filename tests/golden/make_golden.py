@@ -206,6 +206,25 @@ def more_operator_fixtures(out):
         out[p + "int_quad_per_el"] = op.integrate_per_element(q)
         out[p + "energy"] = op.integrate(strain_energy(op.grad(u), mat[0], mat[1]))
 
+        # derivatives of the reference's own energy, as for the three main kinds: complex-step residual and
+        # w . H v probes (complex step in w, 4th-order central difference in v)
+        def E(uu, op=op, mat=mat):
+            return op.integrate(strain_energy(op.grad(uu), mat[0], mat[1]))
+
+        h, dim, v = 1e-30, c.shape[1], out[p + "v"]
+        r = np.zeros(u.shape)
+        for n in range(u.shape[0]):
+            for i in range(dim):
+                uc = u.astype(complex)
+                uc[n, i] += 1j * h
+                r[n, i] = np.imag(E(uc)) / h
+        out[p + "residual_cs"] = r
+        ws = np.random.default_rng(31).normal(size=(3,) + u.shape)  # own stream: the inputs above keep their draws
+        d = 1e-3
+        dE = lambda uu, w: np.imag(E(uu.astype(complex) + 1j * h * w)) / h  # noqa: E731
+        out[p + "hvp_probe_w"] = ws
+        out[p + "hvp_probe_wHv"] = np.array([(-dE(u + 2 * d * v, w) + 8 * dE(u + d * v, w) - 8 * dE(u - d * v, w) + dE(u - 2 * d * v, w)) / (12 * d) for w in ws])
+
 
 def line_meshes():
     """Curved boundary polylines in the plane: a quarter arc of radius 1.3 (Line2: chords; Line3: end nodes then an

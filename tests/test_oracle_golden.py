@@ -142,6 +142,20 @@ def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
 
 
+@pytest.mark.parametrize("kind", ["quad4", "tri6", "quad8"])
+def test_energy_derivatives_of_the_other_plane_elements(golden, kind):
+    """Quad4 / Tri6 / Quad8 with the reference's linear-elastic density (tests/test_sparse.py:20-38): oracle energy,
+    residual and HVP against the reference's energy and its complex-step derivatives."""
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    c, el, u, v = g("coords"), g("conn"), g("u"), g("v")
+    mat = orc.LinearElastic(*g("mat"))
+    np.testing.assert_allclose(orc.energy(kind, mat, c, el, u), g("energy"), rtol=1e-13)
+    r = orc.residual(kind, mat, c, el, u)
+    np.testing.assert_allclose(r, g("residual_cs"), rtol=1e-11, atol=1e-12 * np.abs(r).max())
+    wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), orc.hvp(kind, mat, c, el, u, v))
+    np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-9)  # quadratic energy: the difference quotient is exact
+
+
 @pytest.mark.parametrize("name,dpn", [("tri3_8x8_d2", 2), ("tet4_3_d3", 3), ("tet4_2_d4", 4), ("hex8_3_d3", 3)])
 def test_pattern_and_colouring_bit_exact(golden, name, dpn):
     conn, n_nodes = golden[f"sp_{name}_conn"], int(golden[f"sp_{name}_nnodes"])
