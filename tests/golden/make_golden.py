@@ -62,6 +62,12 @@ def neo_hookean_density(grad_u, mu, lmbda):  # tests/test_sparse_tracer.py:103-1
     return (mu / 2) * (I1 - 3 - 2 * jnp.log(J)) + (lmbda / 2) * (jnp.log(J)) ** 2
 
 
+@autovmap(grad_u=2, phi=0, grad_phi=1, mu=0, lmbda=0, Gc=0, ell=0, k=0)
+def phase_field_density(grad_u, phi, grad_phi, mu, lmbda, Gc, ell, k):
+    """Config 5: builder-defined AT2 law on top of the reference's neo-Hookean density (no counterpart in the reference)."""
+    return ((1 - phi) ** 2 + k) * neo_hookean_density(grad_u, mu, lmbda) + Gc * (phi**2 / (2 * ell) + 0.5 * ell * jnp.dot(grad_phi, grad_phi))
+
+
 def jitter(coords, h, seed=0):
     rng = np.random.default_rng(seed)
     return coords + 0.1 * h * rng.uniform(-1, 1, coords.shape)
@@ -336,6 +342,40 @@ def partition_fixtures(out):
         out[f"part_tri_r{r}_nowned"] = np.array(info.n_owned_nodes)
 
 
+def phase_field_fixtures(out):
+    """The two-field energy of config 5 evaluated with the REFERENCE's Operator (grad of u, eval and grad of phi,
+    integrate) on the compound-stacked state [ux, uy, uz, phi], with complex-step derivatives.  The density itself is
+    ours (parity unpinned as a law); what this pins is everything around it: quadrature, gather, scatter, layout."""
+    rng = np.random.default_rng(37)
+    prm = (500.0, 1000.0, 2.7, 0.1, 1e-6)
+    for kind, cls in {"tet4": element.Tetrahedron4, "hex8": element.Hexahedron8}.items():
+        c, el = (orc.mesh_box_tet((1.0, 1.0, 1.0), (2, 2, 2)) if kind == "tet4" else orc.mesh_box_hex(2))
+        c = c + 0.05 * rng.uniform(-1, 1, c.shape)
+        op = Operator(Mesh(coords=c, elements=el), cls())
+        st = np.concatenate([0.02 * rng.normal(size=c.shape), rng.uniform(0.0, 0.8, size=(c.shape[0], 1))], axis=1)
+        t = rng.normal(size=st.shape)
+
+        def E(ss, op=op):
+            return op.integrate(phase_field_density(op.grad(ss[:, :3]), op.eval(ss[:, 3]), op.grad(ss[:, 3]), *prm))
+
+        p = f"pf_{kind}_"
+        out[p + "coords"], out[p + "conn"], out[p + "s"], out[p + "t"], out[p + "params"] = c, el, st, t, np.array(prm)
+        out[p + "energy"] = E(st)
+        h = 1e-30
+        r = np.zeros(st.shape)
+        for n in range(st.shape[0]):
+            for i in range(4):
+                sc = st.astype(complex)
+                sc[n, i] += 1j * h
+                r[n, i] = np.imag(E(sc)) / h
+        out[p + "residual_cs"] = r
+        ws = rng.normal(size=(3,) + st.shape)
+        d = 1e-4
+        dE = lambda ss, w: np.imag(E(ss.astype(complex) + 1j * h * w)) / h  # noqa: E731
+        out[p + "hvp_probe_w"] = ws
+        out[p + "hvp_probe_wHv"] = np.array([(-dE(st + 2 * d * t, w) + 8 * dE(st + d * t, w) - 8 * dE(st - d * t, w) + dE(st - 2 * d * t, w)) / (12 * d) for w in ws])
+
+
 def mesh_size_fixtures(out):
     """Mesh.hmin / hmax / _element_circumdiameters (mesh.py:87-144) on jittered meshes of every branch: triangles in
     2-D and embedded in 3-D, tetrahedra, and the max-vertex-distance fallback (quads, hexes)."""
@@ -366,6 +406,7 @@ def main():
     line_fixtures(out)
     interpolate_fixtures(out)
     mesh_size_fixtures(out)
+    phase_field_fixtures(out)
     try:
         from _fakempi_golden import mpi_fixtures  # type: ignore
 

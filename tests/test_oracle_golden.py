@@ -142,6 +142,21 @@ def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
 
 
+@pytest.mark.parametrize("kind", ["tet4", "hex8"])
+def test_phase_field_energy_through_the_reference_operator(golden, kind):
+    """Config 5: the builder-defined AT2 density evaluated with the REFERENCE's Operator on the stacked state
+    [ux, uy, uz, phi]; the oracle's closed-form energy / residual / HVP must match it and its complex-step
+    derivatives.  (The law itself has no counterpart in the reference; everything around it is pinned here.)"""
+    g = lambda k: golden[f"pf_{kind}_{k}"]  # noqa: E731
+    c, el, s, t = g("coords"), g("conn"), g("s"), g("t")
+    mat = orc.NeoHookeanPhaseField(*g("params"))
+    np.testing.assert_allclose(orc.energy_pf(kind, mat, c, el, s), g("energy"), rtol=1e-13)
+    r = orc.residual_pf(kind, mat, c, el, s)
+    np.testing.assert_allclose(r, g("residual_cs"), rtol=1e-10, atol=1e-12 * np.abs(r).max())
+    wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), orc.hvp_pf(kind, mat, c, el, s, t))
+    np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
+
+
 @pytest.mark.parametrize("kind", ["quad4", "tri6", "quad8"])
 def test_energy_derivatives_of_the_other_plane_elements(golden, kind):
     """Quad4 / Tri6 / Quad8 with the reference's linear-elastic density (tests/test_sparse.py:20-38): oracle energy,
