@@ -86,3 +86,12 @@ def _tree_map_stack_last(cols, xshape):
         return type(first)(_tree_map_stack_last([c[i] for c in cols], xshape) for i in range(len(first)))
     st = _np.stack([_np.asarray(c) for c in cols], axis=-1)
     return st.reshape(st.shape[:-1] + tuple(xshape))
+
+
+def jvp(fn, primals, tangents):
+    """Complex-step directional derivative (exact to rounding for real-analytic `fn`): what sparse.jacfwd asks of
+    jax.jvp (sparse/base.py:264)."""
+    (x,), (v,) = primals, tangents
+    h = 1e-30
+    out = fn(_np.asarray(x, dtype=_np.float64).astype(_np.complex128) + 1j * h * _np.asarray(v, dtype=_np.float64))
+    return _np.real(out), _np.imag(out) / h

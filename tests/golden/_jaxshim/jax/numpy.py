@@ -12,3 +12,7 @@ def array(obj, dtype=None, **kw):
 
 def asarray(obj, dtype=None, **kw):
     return _np.asarray(obj, dtype=dtype)
+
+
+def repeat(a, repeats, axis=None, total_repeat_length=None):
+    return _np.repeat(a, repeats, axis=axis)

@@ -376,6 +376,34 @@ def phase_field_fixtures(out):
         out[p + "hvp_probe_wHv"] = np.array([(-dE(st + 2 * d * t, w) + 8 * dE(st + d * t, w) - 8 * dE(st - d * t, w) + dE(st - 2 * d * t, w)) / (12 * d) for w in ws])
 
 
+def colored_jacobian_fixtures(out):
+    """sparse.jacfwd / colored_jacobian_batch / compute_rows_cols (sparse/base.py:108-176, :230-270) on the Tri3 8x8
+    two-DOF pattern with the reference colouring, for an analytic residual whose Jacobian has exactly that pattern:
+    fn(u) = A u + 0.1 (A u)^2.  The shim's jax.jvp is a complex-step derivative, exact for this fn."""
+    import scipy.sparse as sps
+
+    rng = np.random.default_rng(41)
+    c, el = orc.mesh_unit_square_tri(8, 8)
+    mesh = Mesh(coords=jnp.asarray(c), elements=jnp.asarray(el))
+    pat = sparse.pattern_from_mesh(mesh, 2)
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    A = sps.csr_matrix((rng.normal(size=pat.indices.shape[0]), np.asarray(pat.indices), np.asarray(pat.indptr)), shape=pat.shape)
+    u0 = rng.normal(size=pat.shape[0])
+
+    def fn(u):
+        y = A @ u
+        return y + 0.1 * y * y
+
+    for batch in (None, 5):
+        K = sparse.jacfwd(fn, cm, color_batch_size=batch)(u0)
+        out[f"jac_data_batch{batch}"] = np.asarray(K.data)
+    out["jac_A_data"], out["jac_u0"] = A.data, u0
+    out["jac_indptr"], out["jac_indices"], out["jac_colors"] = np.asarray(cm.indptr), np.asarray(cm.indices), np.asarray(cm.colors)
+    rows, col_colors = sparse.base.compute_rows_cols(cm) if hasattr(sparse, "base") else (None, None)
+    if rows is not None:
+        out["jac_rows"], out["jac_col_colors"] = np.asarray(rows), np.asarray(col_colors)
+
+
 def mesh_size_fixtures(out):
     """Mesh.hmin / hmax / _element_circumdiameters (mesh.py:87-144) on jittered meshes of every branch: triangles in
     2-D and embedded in 3-D, tetrahedra, and the max-vertex-distance fallback (quads, hexes)."""
@@ -407,6 +435,7 @@ def main():
     interpolate_fixtures(out)
     mesh_size_fixtures(out)
     phase_field_fixtures(out)
+    colored_jacobian_fixtures(out)
     try:
         from _fakempi_golden import mpi_fixtures  # type: ignore
 

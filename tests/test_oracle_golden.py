@@ -142,6 +142,47 @@ def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
 
 
+def test_coloured_jacobian_matches_the_reference_jacfwd(golden):
+    """sparse.jacfwd / colored_jacobian_batch / compute_rows_cols of the reference (sparse/base.py:108-176, :230-270),
+    run unmodified on fn(u) = A u + 0.1 (A u)^2 over the Tri3 8x8 two-DOF pattern: the oracle's decompression and
+    the product's coloured path (torch forward-mode AD, here on CPU tensors) must give the same `data`."""
+    import scipy.sparse as sps
+    import torch
+
+    from tatva_b200 import sparse
+
+    g = lambda k: golden[f"jac_{k}"]  # noqa: E731
+    ip, ix, colors, u0 = g("indptr"), g("indices"), g("colors"), g("u0")
+    n = len(u0)
+    A = sps.csr_matrix((g("A_data"), ix, ip), shape=(n, n))
+    rows, col_colors = orc.compute_rows_cols(ip, ix, colors)
+    np.testing.assert_array_equal(rows, g("rows"))
+    np.testing.assert_array_equal(col_colors, g("col_colors"))
+    np.testing.assert_array_equal(orc.distance2_colors(ip, ix, n), colors)
+    y = A @ u0
+    jvp = lambda seed: (1 + 0.2 * y) * (A @ seed)  # noqa: E731
+    np.testing.assert_allclose(orc.colored_jacobian_data(jvp, n, ip, ix, colors), g("data_batchNone"), rtol=1e-13, atol=1e-14)
+    np.testing.assert_array_equal(g("data_batchNone"), g("data_batch5"))
+    # the product's reference-algorithm path on a plain callable
+    pat = sps.csr_matrix((np.ones(len(ix), dtype=np.int8), ix, ip), shape=(n, n))
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    np.testing.assert_array_equal(cm.colors, colors)
+    r2, c2 = sparse.compute_rows_cols(cm)
+    np.testing.assert_array_equal(r2, g("rows"))
+    np.testing.assert_array_equal(c2, g("col_colors"))
+    At = torch.as_tensor(A.toarray())
+
+    def fn(u):
+        yy = At @ u
+        return yy + 0.1 * yy * yy
+
+    K = sparse.jacfwd(fn, cm, color_batch_size=5)(torch.as_tensor(u0))
+    np.testing.assert_allclose(np.asarray(K.data), g("data_batchNone"), rtol=1e-13, atol=1e-14)
+    primal, K2 = sparse.linearized_jacfwd(fn, cm)(torch.as_tensor(u0))
+    np.testing.assert_allclose(np.asarray(K2.data), g("data_batchNone"), rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(np.asarray(primal), y + 0.1 * y * y, rtol=1e-14)
+
+
 @pytest.mark.parametrize("kind", ["tet4", "hex8"])
 def test_phase_field_energy_through_the_reference_operator(golden, kind):
     """Config 5: the builder-defined AT2 density evaluated with the REFERENCE's Operator on the stacked state
