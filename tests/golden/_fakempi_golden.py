@@ -1,0 +1,64 @@
+"""MPI fixtures: the UNMODIFIED tatva.mpi._create_dof_layout and ExchangePlan (routing tables for vectors and for
+Hessian nonzeros) built for every rank of a partitioned mesh, on the thread-based mpi4py stand-in (_fakempi)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_fakempi"))
+
+from mpi4py import run_ranks  # noqa: E402  (the stand-in)
+
+
+def mpi_fixtures(out):
+    from tatva import Mesh, sparse
+    from tatva.mesh import extract_local_mesh
+    from tatva.mpi import ExchangePlan, _create_dof_layout
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import tatva_oracle as orc
+
+    cases = {}
+    c, el = orc.mesh_box_hex((4, 3, 2))
+    cen = c[el].mean(axis=1)
+    cases["hex3"] = (c, el, ((cen[:, 0] > 0.26).astype(np.int32) + (cen[:, 0] > 0.74).astype(np.int32)).astype(np.int32), 3, 3)
+    c, el = orc.mesh_unit_square_tri(5, 4)
+    cen = c[el].mean(axis=1)
+    cases["tri4"] = (c, el, ((cen[:, 0] > 0.5).astype(np.int32) + 2 * (cen[:, 1] > 0.5).astype(np.int32)).astype(np.int32), 4, 2)
+    for name, (c, el, part, size, dpn) in cases.items():
+        n_nat = c.shape[0] * dpn
+        out[f"mpi_{name}_coords"], out[f"mpi_{name}_conn"], out[f"mpi_{name}_partition"] = c, el, part
+        out[f"mpi_{name}_size_dpn"] = np.array([size, dpn])
+
+        def per_rank(comm, c=c, el=el, part=part, dpn=dpn, n_nat=n_nat):
+            mesh, info = extract_local_mesh(Mesh(coords=c, elements=el), part, comm.rank)
+            l2g_nodes = np.asarray(info.nodes_local_to_global)
+            natural = (l2g_nodes[:, None] * dpn + np.arange(dpn)).ravel().astype(np.int32)
+            owned = np.zeros(natural.size, dtype=bool)
+            owned[: int(info.n_owned_nodes) * dpn] = True
+            layout = _create_dof_layout(natural, owned, n_nat, comm)
+            pat = sparse.pattern_from_mesh(mesh, dpn)
+            plan = ExchangePlan(layout, pat, comm=comm)
+            return layout, plan, (np.asarray(pat.indptr), np.asarray(pat.indices))
+
+        res = run_ranks(size, per_rank)
+        for r, (layout, plan, (ip, ix)) in enumerate(res):
+            p = f"mpi_{name}_r{r}_"
+            out[p + "natural"], out[p + "owned_mask"] = np.asarray(layout.natural_l2g), np.asarray(layout.owned_mask)
+            out[p + "l2g"] = np.asarray(layout.local_to_global)
+            out[p + "offset_nowned_ntotal_nglobal"] = np.array([layout.offset, layout.n_owned, layout.n_total, layout.n_global])
+            out[p + "self_send"], out[p + "self_recv"] = np.asarray(plan._send_dof), np.asarray(plan._recv_dof)
+            out[p + "nbr_ranks"] = np.array([d.rank for d in plan._neighbor_dof_data], dtype=np.int32)
+            for d in plan._neighbor_dof_data:
+                out[p + f"nbr{d.rank}_send"], out[p + f"nbr{d.rank}_recv"] = np.asarray(d.local_send_idx), np.asarray(d.recv_local_idx)
+            h = plan.hessian_layout
+            out[p + "pat_indptr"], out[p + "pat_indices"] = ip, ix
+            out[p + "h_owned_nnz"] = np.array(h.owned_nnz)
+            out[p + "h_owned_ptr"], out[p + "h_owned_indices"] = np.asarray(h.owned_ptr), np.asarray(h.owned_indices)
+            out[p + "h_self_send"], out[p + "h_self_recv"] = np.asarray(h.local_send_idx), np.asarray(h.recv_local_idx)
+            out[p + "h_nbr_ranks"] = np.array([d.rank for d in h.neighbor_data], dtype=np.int32)
+            for d in h.neighbor_data:
+                out[p + f"h_nbr{d.rank}_send"], out[p + f"h_nbr{d.rank}_recv"] = np.asarray(d.local_send_idx), np.asarray(d.recv_local_idx)

@@ -9,8 +9,8 @@ stand-in under tests/golden/_jaxshim (vmap / lax.map -> loops, jnp -> numpy).  E
 written below is the output of reference code: tatva.element.*, tatva.Operator.{grad, eval,
 integrate, integrate_per_element, get_integration_weights}, tatva.sparse.pattern_from_mesh,
 tatva/sparse/_coloring.py:distance2_colors, tatva.mesh.extract_local_mesh, and (with an
-in-process thread-based stand-in for mpi4py, see _fakempi.py) tatva.mpi._create_dof_layout /
-ExchangePlan routing tables.
+in-process thread-based stand-in for mpi4py, tests/golden/_fakempi) tatva.mpi._create_dof_layout /
+ExchangePlan routing tables for vectors and Hessian nonzeros (tests/golden/_fakempi_golden.py).
 
 Derivative fixtures: the reference has no residual/HVP code (they are jax.grad / jax.jvp of a
 user energy).  We differentiate the reference's *own* energy E(u) = op.integrate(psi(op.grad(u)))
@@ -436,12 +436,9 @@ def main():
     mesh_size_fixtures(out)
     phase_field_fixtures(out)
     colored_jacobian_fixtures(out)
-    try:
-        from _fakempi_golden import mpi_fixtures  # type: ignore
+    from _fakempi_golden import mpi_fixtures
 
-        mpi_fixtures(out)
-    except ImportError:
-        pass
+    mpi_fixtures(out)
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")

@@ -321,6 +321,64 @@ def _body_global_views(rank, world):
         NoLayout._g
 
 
+def _reference_plan_body(rank, world, name):
+    """The product's layout + ExchangePlan (vector and Hessian-nnz routing) on `world` gloo ranks against the tables
+    the UNMODIFIED reference builds for the same partitioned mesh (fixtures `mpi_*`, tests/golden/_fakempi_golden.py)."""
+    from scipy.sparse import csr_matrix as csr
+
+    from tatva_b200 import sparse
+    from tatva_b200.mesh import Mesh, extract_local_mesh
+    from tatva_b200.mpi import ExchangePlan, _create_dof_layout
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    size, dpn = (int(x) for x in G[f"mpi_{name}_size_dpn"])
+    assert size == world
+    g = lambda k: G[f"mpi_{name}_r{rank}_{k}"]  # noqa: E731
+    c, el, part = G[f"mpi_{name}_coords"], G[f"mpi_{name}_conn"], G[f"mpi_{name}_partition"]
+    mesh, info = extract_local_mesh(Mesh(coords=c, elements=el), part, rank)
+    l2g_nodes = np.asarray(info.nodes_local_to_global)
+    natural = (l2g_nodes[:, None] * dpn + np.arange(dpn)).ravel().astype(np.int32)
+    np.testing.assert_array_equal(natural, g("natural"))
+    owned = np.zeros(natural.size, dtype=bool)
+    owned[: int(info.n_owned_nodes) * dpn] = True
+    layout = _create_dof_layout(natural, owned, c.shape[0] * dpn, dist.group.WORLD)
+    off, n_owned, n_total, n_global = (int(x) for x in g("offset_nowned_ntotal_nglobal"))
+    assert (layout.offset, layout.n_owned, layout.n_total, layout.n_global) == (off, n_owned, n_total, n_global)
+    np.testing.assert_array_equal(layout.local_to_global, g("l2g"))
+    pat = sparse.pattern_from_mesh(mesh, dpn)
+    np.testing.assert_array_equal(pat.indptr, g("pat_indptr"))
+    np.testing.assert_array_equal(pat.indices, g("pat_indices"))
+    plan = ExchangePlan(layout, csr((np.ones(pat.nnz), pat.indices, pat.indptr), shape=pat.shape), comm=dist.group.WORLD)
+    np.testing.assert_array_equal(plan._send_dof, g("self_send"))
+    np.testing.assert_array_equal(plan._recv_dof, g("self_recv"))
+    np.testing.assert_array_equal([d.rank for d in plan._neighbor_dof_data], g("nbr_ranks"))
+    for d in plan._neighbor_dof_data:
+        np.testing.assert_array_equal(d.local_send_idx, g(f"nbr{d.rank}_send"))
+        np.testing.assert_array_equal(d.recv_local_idx, g(f"nbr{d.rank}_recv"))
+    h = plan.hessian_layout
+    assert h.owned_nnz == int(g("h_owned_nnz"))
+    np.testing.assert_array_equal(h.owned_ptr, g("h_owned_ptr"))
+    np.testing.assert_array_equal(h.owned_indices, g("h_owned_indices"))
+    np.testing.assert_array_equal(h.local_send_idx, g("h_self_send"))
+    np.testing.assert_array_equal(h.recv_local_idx, g("h_self_recv"))
+    np.testing.assert_array_equal([d.rank for d in h.neighbor_data], g("h_nbr_ranks"))
+    for d in h.neighbor_data:
+        np.testing.assert_array_equal(d.local_send_idx, g(f"h_nbr{d.rank}_send"))
+        np.testing.assert_array_equal(d.recv_local_idx, g(f"h_nbr{d.rank}_recv"))
+    # and the plan moves data the way those tables say: ghosts receive the owners' values
+    x_owned = torch.as_tensor(np.arange(off, off + n_owned, dtype=np.float64))  # value = global DOF id
+    u_local = plan.make_scatter_fwd_set()(x_owned)
+    np.testing.assert_array_equal(u_local.numpy(), np.asarray(layout.local_to_global, dtype=np.float64))
+
+
+def _body_reference_plan_hex3(rank, world):
+    _reference_plan_body(rank, world, "hex3")
+
+
+def _body_reference_plan_tri4(rank, world):
+    _reference_plan_body(rank, world, "tri4")
+
+
 # ---- pytest entry points -----------------------------------------------------------------------------
 
 
@@ -330,6 +388,11 @@ def _body_global_views(rank, world):
 )
 def test_two_rank_gloo(body):
     _run(body, world=2)
+
+
+@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4)])
+def test_plans_match_the_reference_on_more_ranks(body, world):
+    _run(body, world=world)
 
 
 def test_dof_range_and_single_process_plan():

@@ -142,6 +142,36 @@ def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
 
 
+@pytest.mark.parametrize("name", ["hex3", "tri4"])
+def test_layouts_and_routing_match_the_reference_plans(golden, name):
+    """tatva.mpi._create_dof_layout and ExchangePlan routing tables of the UNMODIFIED reference, built for every rank
+    of a partitioned mesh on a thread-based mpi4py stand-in (3 ranks on a Hex8 box with 3 DOFs per node, 4 ranks on
+    a Tri3 square with 2): the oracle's all-ranks-at-once restatement must reproduce them bit for bit."""
+    size, dpn = (int(x) for x in golden[f"mpi_{name}_size_dpn"])
+    g = lambda r, k: golden[f"mpi_{name}_r{r}_{k}"]  # noqa: E731
+    naturals = [g(r, "natural") for r in range(size)]
+    masks = [g(r, "owned_mask") for r in range(size)]
+    n_nat = golden[f"mpi_{name}_coords"].shape[0] * dpn
+    # the natural maps themselves follow from extract_local_mesh, restated in the oracle
+    for r in range(size):
+        _, _, l2g_nodes, n_owned = orc.extract_local_mesh(golden[f"mpi_{name}_coords"], golden[f"mpi_{name}_conn"], golden[f"mpi_{name}_partition"], r)
+        np.testing.assert_array_equal(orc.dof_map_from_node_map(l2g_nodes, dpn), naturals[r])
+        assert masks[r][: n_owned * dpn].all() and not masks[r][n_owned * dpn :].any()
+    layouts = orc.create_dof_layouts(naturals, masks, n_nat)
+    plans = orc.exchange_routing(layouts)
+    for r in range(size):
+        off, n_owned, n_total, n_global = (int(x) for x in g(r, "offset_nowned_ntotal_nglobal"))
+        L = layouts[r]
+        assert (L["offset"], L["n_owned"], L["n_total"], L["n_global"]) == (off, n_owned, n_total, n_global)
+        np.testing.assert_array_equal(L["local_to_global"], g(r, "l2g"))
+        np.testing.assert_array_equal(plans[r]["self_send"], g(r, "self_send"))
+        np.testing.assert_array_equal(plans[r]["self_recv"], g(r, "self_recv"))
+        np.testing.assert_array_equal([nb["rank"] for nb in plans[r]["neighbors"]], g(r, "nbr_ranks"))
+        for nb in plans[r]["neighbors"]:
+            np.testing.assert_array_equal(nb["local_send_idx"], g(r, f"nbr{nb['rank']}_send"))
+            np.testing.assert_array_equal(nb["recv_local_idx"], g(r, f"nbr{nb['rank']}_recv"))
+
+
 def test_coloured_jacobian_matches_the_reference_jacfwd(golden):
     """sparse.jacfwd / colored_jacobian_batch / compute_rows_cols of the reference (sparse/base.py:108-176, :230-270),
     run unmodified on fn(u) = A u + 0.1 (A u)^2 over the Tri3 8x8 two-DOF pattern: the oracle's decompression and
