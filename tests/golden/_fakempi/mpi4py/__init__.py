@@ -3,7 +3,7 @@ built for several ranks inside one process (tests/golden/make_golden.py).  TEST 
 
 Every rank is a thread holding a `Comm`; collectives rendezvous on a shared barrier, point-to-point `Sendrecv` goes
 through per-(source, dest) mailboxes.  Only blocking semantics and the calls listed below exist: rank / Get_rank /
-Get_size / allreduce / allgather / Allreduce / Alltoall / Sendrecv / Allgatherv / Barrier."""
+Get_size / allreduce / allgather / exscan / Allreduce / Alltoall / Sendrecv / Allgatherv / Barrier."""
 from __future__ import annotations
 
 import queue
@@ -49,6 +49,11 @@ class Comm:
     def allreduce(self, value, op=None):
         vals = self.allgather(value)
         return (op or MPI.SUM).fn(vals)
+
+    def exscan(self, value, op=None):
+        """Exclusive prefix reduction: rank 0 gets None (as mpi4py does), rank r the reduction over ranks < r."""
+        vals = self.allgather(value)
+        return None if self.rank == 0 else (op or MPI.SUM).fn(vals[: self.rank])
 
     def Allreduce(self, sendbuf, recvbuf, op=None):
         vals = self.allgather(np.array(sendbuf, copy=True))

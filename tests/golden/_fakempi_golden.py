@@ -14,6 +14,7 @@ from mpi4py import run_ranks  # noqa: E402  (the stand-in)
 
 
 def mpi_fixtures(out):
+    compound_fixtures(out)
     from tatva import Mesh, sparse
     from tatva.mesh import extract_local_mesh
     from tatva.mpi import ExchangePlan, _create_dof_layout
@@ -62,3 +63,48 @@ def mpi_fixtures(out):
             out[p + "h_nbr_ranks"] = np.array([d.rank for d in h.neighbor_data], dtype=np.int32)
             for d in h.neighbor_data:
                 out[p + f"h_nbr{d.rank}_send"], out[p + f"h_nbr{d.rank}_recv"] = np.asarray(d.local_send_idx), np.asarray(d.recv_local_idx)
+
+
+def compound_fixtures(out):
+    """tatva.compound.mpi._layout_from_compound of the UNMODIFIED reference on 3 ranks: stacked full nodal fields, a
+    nodal field on a node subset, a shared and a local field (compound/mpi.py:288-494), with the per-field global
+    info behind `Compound._g`."""
+    from tatva import Mesh
+    from tatva.compound import Compound, FieldSize, field
+    from tatva.compound.field_types import Local, Nodal, Shared
+    from tatva.mesh import extract_local_mesh
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import tatva_oracle as orc
+
+    c, el = orc.mesh_box_hex((4, 3, 2))
+    cen = c[el].mean(axis=1)
+    part = ((cen[:, 0] > 0.26).astype(np.int32) + (cen[:, 0] > 0.74).astype(np.int32)).astype(np.int32)
+    out["cmp_coords"], out["cmp_conn"], out["cmp_partition"] = c, el, part
+
+    def per_rank(comm):
+        mesh, info = extract_local_mesh(Mesh(coords=c, elements=el), part, comm.rank)
+        sub = np.arange(0, mesh.coords.shape[0], 3)
+
+        class S(Compound, mesh=mesh, partition_info=info, comm=comm):
+            u = field(shape=(FieldSize.AUTO, 3))
+            p = field(shape=(FieldSize.AUTO,))
+            lam = field(shape=(FieldSize.AUTO, 2), field_type=Nodal(node_ids=sub))
+            g = field(shape=(2,), field_type=Shared())
+            w = field(shape=(comm.rank + 1, 2), field_type=Local())
+
+        return S, sub
+
+    for r, (S, sub) in enumerate(run_ranks(3, per_rank)):
+        L = S.get_layout()
+        p = f"cmp_r{r}_"
+        out[p + "subset_local_nodes"] = sub
+        out[p + "size"] = np.array(S.size)
+        out[p + "natural"], out[p + "owned_mask"], out[p + "l2g"] = np.asarray(L.natural_l2g), np.asarray(L.owned_mask), np.asarray(L.local_to_global)
+        out[p + "offset_nowned_ntotal_nglobal"] = np.array([L.offset, L.n_owned, L.n_total, L.n_global])
+        for name, info in S._global_field_info.items():
+            out[p + f"{name}_gshape"] = np.array(info.global_shape, dtype=np.int64)
+            out[p + f"{name}_goffset_strides"] = np.array([info.global_base_offset, *info.global_strides], dtype=np.int64)
+            if info.global_subset is not None:
+                out[p + f"{name}_gsubset"] = np.asarray(info.global_subset)
+            out[p + f"{name}_gindices"] = np.asarray(getattr(S._g, name)[(slice(None),) * len(info.global_shape)] if info.global_subset is None else getattr(S._g, name)[info.global_subset])

@@ -371,6 +371,45 @@ def _reference_plan_body(rank, world, name):
     np.testing.assert_array_equal(u_local.numpy(), np.asarray(layout.local_to_global, dtype=np.float64))
 
 
+def _body_reference_compound_layout(rank, world):
+    """The product's `layout_from_compound` and `Compound._g` on 3 gloo ranks against the UNMODIFIED reference
+    (compound/mpi.py:288-494, fixtures `cmp_*`): stacked nodal fields, a nodal field on a node subset, a shared and
+    a local field."""
+    from tatva_b200.compound import Compound, FieldSize, Local, Nodal, Shared, field
+    from tatva_b200.mesh import Mesh, extract_local_mesh
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    g = lambda k: G[f"cmp_r{rank}_{k}"]  # noqa: E731
+    mesh, info = extract_local_mesh(Mesh(coords=G["cmp_coords"], elements=G["cmp_conn"]), G["cmp_partition"], rank)
+    sub = g("subset_local_nodes")
+
+    class S(Compound, mesh=mesh, partition_info=info, comm=dist.group.WORLD):
+        u = field(shape=(FieldSize.AUTO, 3))
+        p = field(shape=(FieldSize.AUTO,))
+        lam = field(shape=(FieldSize.AUTO, 2), field_type=Nodal(node_ids=sub))
+        g = field(shape=(2,), field_type=Shared())
+        w = field(shape=(rank + 1, 2), field_type=Local())
+
+    assert S.size == int(g("size"))
+    L = S.get_layout()
+    np.testing.assert_array_equal(L.natural_l2g, g("natural"))
+    np.testing.assert_array_equal(L.owned_mask, g("owned_mask"))
+    np.testing.assert_array_equal(L.local_to_global, g("l2g"))
+    off, n_owned, n_total, n_global = (int(x) for x in g("offset_nowned_ntotal_nglobal"))
+    assert (L.offset, L.n_owned, L.n_total, L.n_global) == (off, n_owned, n_total, n_global)
+    for name in ("u", "p", "lam", "g", "w"):
+        fi = S._global_field_info[name]
+        np.testing.assert_array_equal(np.array(fi.global_shape), g(f"{name}_gshape"))
+        np.testing.assert_array_equal(np.array([fi.global_base_offset, *fi.global_strides]), g(f"{name}_goffset_strides"))
+        view = getattr(S._g, name)
+        if fi.global_subset is None:
+            got = view[(slice(None),) * len(fi.global_shape)]
+        else:
+            np.testing.assert_array_equal(fi.global_subset, g(f"{name}_gsubset"))
+            got = view[fi.global_subset]
+        np.testing.assert_array_equal(got, g(f"{name}_gindices"))
+
+
 def _body_reference_plan_hex3(rank, world):
     _reference_plan_body(rank, world, "hex3")
 
@@ -390,7 +429,7 @@ def test_two_rank_gloo(body):
     _run(body, world=2)
 
 
-@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4)])
+@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4), ("_body_reference_compound_layout", 3)])
 def test_plans_match_the_reference_on_more_ranks(body, world):
     _run(body, world=world)
 
