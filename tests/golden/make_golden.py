@@ -404,6 +404,47 @@ def colored_jacobian_fixtures(out):
         out["jac_rows"], out["jac_col_colors"] = np.asarray(rows), np.asarray(col_colors)
 
 
+def lifter_fixtures(out):
+    """tatva.lifter (Lifter, Fixed, Periodic, RuntimeValue, lifted; lifter/base.py:201-251, constraints.py:184-318) run
+    unmodified on a chain of constraints over the DOFs of a Tri3 6x6 mesh with 2 DOFs per node: a fixed bottom edge,
+    a prescribed (runtime) top displacement, left/right periodicity.  Records free DOFs, lift / lift_from_zeros /
+    reduce / reduce_adjoint of random vectors, and the lifted-decorator outputs."""
+    from tatva.lifter import Fixed, Lifter, Periodic, RuntimeValue, lifted
+
+    rng = np.random.default_rng(43)
+    c, el = orc.mesh_unit_square_tri(6, 6)
+    n = 2 * c.shape[0]
+    bottom = np.where(c[:, 1] < 1e-12)[0]
+    top = np.where(c[:, 1] > 1 - 1e-12)[0]
+    inner = (c[:, 1] > 1e-12) & (c[:, 1] < 1 - 1e-12)
+    left = np.where((c[:, 0] < 1e-12) & inner)[0]
+    right = np.where((c[:, 0] > 1 - 1e-12) & inner)[0]
+    left, right = left[np.argsort(c[left, 1])], right[np.argsort(c[right, 1])]
+    dofs = lambda nodes: (np.asarray(nodes)[:, None] * 2 + np.arange(2)).ravel()  # noqa: E731
+    lifter = Lifter(
+        n,
+        Fixed(jnp.asarray(dofs(bottom)), 0.0),
+        Fixed(jnp.asarray(top * 2 + 1), RuntimeValue("top_uy")),
+        Fixed(jnp.asarray(top * 2), jnp.asarray(0.01 * np.arange(len(top)))),
+        Periodic(dofs=jnp.asarray(dofs(right)), master_dofs=jnp.asarray(dofs(left))),
+    )
+    lifter = lifter.with_values({"top_uy": 0.07})
+    out["lift_n"], out["lift_bottom"], out["lift_top"], out["lift_left"], out["lift_right"] = np.array(n), bottom, top, left, right
+    out["lift_free_dofs"] = np.asarray(lifter.free_dofs)
+    u_red = rng.normal(size=lifter.size_reduced)
+    base = rng.normal(size=n)
+    r_full = rng.normal(size=n)
+    out["lift_u_red"], out["lift_base"], out["lift_r_full"] = u_red, base, r_full
+    out["lift_from_zeros"] = np.asarray(lifter.lift_from_zeros(jnp.asarray(u_red)))
+    out["lift_on_base"] = np.asarray(lifter.lift(jnp.asarray(u_red), jnp.asarray(base)))
+    out["lift_reduce"] = np.asarray(lifter.reduce(jnp.asarray(base)))
+    out["lift_reduce_adjoint"] = np.asarray(lifter.reduce_adjoint(jnp.asarray(r_full)))
+    A = rng.normal(size=(n, n))
+    out["lift_A"] = A
+    out["lifted_dual"] = np.asarray(lifted(lambda uf: jnp.asarray(A @ uf), argnums=0, output="dual")(lifter, jnp.asarray(u_red)))
+    out["lifted_primal"] = np.asarray(lifted(lambda uf: uf * 2.0, argnums=0, output="primal")(lifter, jnp.asarray(u_red)))
+
+
 def mesh_size_fixtures(out):
     """Mesh.hmin / hmax / _element_circumdiameters (mesh.py:87-144) on jittered meshes of every branch: triangles in
     2-D and embedded in 3-D, tetrahedra, and the max-vertex-distance fallback (quads, hexes)."""
@@ -436,6 +477,7 @@ def main():
     mesh_size_fixtures(out)
     phase_field_fixtures(out)
     colored_jacobian_fixtures(out)
+    lifter_fixtures(out)
     from _fakempi_golden import mpi_fixtures
 
     mpi_fixtures(out)

@@ -160,3 +160,37 @@ def test_deprecated_aliases_warn_like_the_reference():
         warnings.simplefilter("always")
         assert L.DirichletBC is L.Fixed and L.PeriodicMap is L.Periodic
     assert sum(issubclass(x.category, DeprecationWarning) for x in w) == 2
+
+
+def test_lifter_matches_the_reference_on_a_constraint_chain(golden):
+    """The UNMODIFIED reference lifter (lifter/base.py:201-251, constraints.py:184-318) on a Tri3 6x6 mesh with 2 DOFs per
+    node: fixed bottom edge, runtime-valued and array-valued Fixed constraints on the top edge, left/right periodicity.
+    Free DOFs, lift, lift_from_zeros, reduce, reduce_adjoint and the `lifted` decorator must reproduce its outputs;
+    `dof_map` (what the fused HVP kernel consumes) is checked against the same data."""
+    import numpy as np
+    from tatva_b200.lifter import Fixed, Lifter, Periodic, RuntimeValue, lifted
+
+    g = lambda k: golden[f"lift_{k}"]  # noqa: E731
+    n, bottom, top, left, right = int(g("n")), g("bottom"), g("top"), g("left"), g("right")
+    dofs = lambda nodes: (np.asarray(nodes)[:, None] * 2 + np.arange(2)).ravel()  # noqa: E731
+    lifter = Lifter(
+        n,
+        Fixed(dofs(bottom), 0.0),
+        Fixed(top * 2 + 1, RuntimeValue("top_uy")),
+        Fixed(top * 2, 0.01 * np.arange(len(top))),
+        Periodic(dofs=dofs(right), master_dofs=dofs(left)),
+    ).with_values({"top_uy": 0.07})
+    np.testing.assert_array_equal(lifter.free_dofs, g("free_dofs"))
+    u_red, base, r_full = g("u_red"), g("base"), g("r_full")
+    np.testing.assert_array_equal(lifter.lift_from_zeros(u_red), g("from_zeros"))
+    np.testing.assert_array_equal(lifter.lift(u_red, base), g("on_base"))
+    np.testing.assert_array_equal(lifter.reduce(base), g("reduce"))
+    np.testing.assert_allclose(lifter.reduce_adjoint(r_full), g("reduce_adjoint"), rtol=1e-15, atol=1e-15)
+    A = golden["lift_A"]
+    np.testing.assert_allclose(lifted(lambda uf: A @ uf, argnums=0, output="dual")(lifter, u_red), golden["lifted_dual"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_array_equal(lifted(lambda uf: uf * 2.0, argnums=0, output="primal")(lifter, u_red), golden["lifted_primal"])
+    # dof_map == the homogeneous part of the reference's lift and the adjoint of its transpose chain
+    m = lifter.dof_map()
+    hom = lifter.homogeneous().lift_from_zeros(u_red)
+    np.testing.assert_array_equal(hom, np.where(m >= 0, u_red[np.maximum(m, 0)], 0.0))
+    np.testing.assert_allclose(np.bincount(m[m >= 0], weights=r_full[m >= 0], minlength=lifter.size_reduced), g("reduce_adjoint"), rtol=1e-15, atol=1e-15)
