@@ -15,6 +15,7 @@ from mpi4py import run_ranks  # noqa: E402  (the stand-in)
 
 def mpi_fixtures(out):
     compound_fixtures(out)
+    periodic_mpi_fixtures(out)
     from tatva import Mesh, sparse
     from tatva.mesh import extract_local_mesh
     from tatva.mpi import ExchangePlan, _create_dof_layout
@@ -108,3 +109,58 @@ def compound_fixtures(out):
             if info.global_subset is not None:
                 out[p + f"{name}_gsubset"] = np.asarray(info.global_subset)
             out[p + f"{name}_gindices"] = np.asarray(getattr(S._g, name)[(slice(None),) * len(info.global_shape)] if info.global_subset is None else getattr(S._g, name)[info.global_subset])
+
+
+def periodic_mpi_fixtures(out):
+    """Lifter.adapt_layout with PeriodicMPI and Fixed (lifter/base.py:333-425, constraints.py:223-287) run unmodified on
+    3 ranks of the Hex8 4x3x2 box with 3 DOFs per node: the x = 1 face follows the x = 0 face (slaves and masters live on
+    different ranks, so masters become extra ghosts), the z = 0 layer is fixed except on those two faces."""
+    from tatva import Mesh
+    from tatva.lifter import Fixed, Lifter, PeriodicMPI
+    from tatva.mesh import extract_local_mesh
+    from tatva.mpi import _create_dof_layout
+
+    import jax.numpy as jnp
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import tatva_oracle as orc
+
+    dpn = 3
+    c, el = orc.mesh_box_hex((4, 3, 2))
+    cen = c[el].mean(axis=1)
+    part = ((cen[:, 0] > 0.26).astype(np.int32) + (cen[:, 0] > 0.74).astype(np.int32)).astype(np.int32)
+    x0 = np.where(c[:, 0] < 1e-12)[0]
+    x1 = np.where(c[:, 0] > c[:, 0].max() - 1e-12)[0]
+    key = lambda idx: np.lexsort((c[idx, 1], c[idx, 2]))  # noqa: E731
+    x0, x1 = x0[key(x0)], x1[key(x1)]
+    assert np.allclose(c[x0][:, 1:], c[x1][:, 1:])
+    g_slaves = (x1[:, None] * dpn + np.arange(dpn)).ravel()
+    g_masters = (x0[:, None] * dpn + np.arange(dpn)).ravel()
+    out["pmpi_coords"], out["pmpi_conn"], out["pmpi_partition"] = c, el, part
+    out["pmpi_slaves"], out["pmpi_masters"] = g_slaves, g_masters
+
+    def per_rank(comm):
+        mesh, info = extract_local_mesh(Mesh(coords=c, elements=el), part, comm.rank)
+        l2g_nodes = np.asarray(info.nodes_local_to_global)
+        natural = (l2g_nodes[:, None] * dpn + np.arange(dpn)).ravel().astype(np.int32)
+        owned = np.zeros(natural.size, dtype=bool)
+        owned[: int(info.n_owned_nodes) * dpn] = True
+        layout = _create_dof_layout(natural, owned, c.shape[0] * dpn, comm)
+        lc = np.asarray(mesh.coords)
+        fixed_nodes = np.where((lc[:, 2] < 1e-12) & (lc[:, 0] > 1e-12) & (lc[:, 0] < c[:, 0].max() - 1e-12))[0]
+        fixed = (fixed_nodes[:, None] * dpn + np.arange(dpn)).ravel()
+        lifter = Lifter(layout.n_total, Fixed(jnp.asarray(fixed), 0.25), PeriodicMPI(jnp.asarray(g_slaves), jnp.asarray(g_masters), layout, comm=comm))
+        reduced, lifter2 = lifter.adapt_layout(layout, comm)
+        u_red = np.sin(1.0 + np.arange(lifter2.size_reduced) + 100.0 * comm.rank)
+        return fixed, reduced, lifter2, u_red, np.asarray(lifter2.lift_from_zeros(jnp.asarray(u_red)))
+
+    for r, (fixed, reduced, lifter2, u_red, lifted_full) in enumerate(run_ranks(3, per_rank)):
+        p = f"pmpi_r{r}_"
+        out[p + "fixed_local_dofs"] = fixed
+        out[p + "red_l2g"], out[p + "red_owned_mask"], out[p + "red_natural"] = np.asarray(reduced.local_to_global), np.asarray(reduced.owned_mask), np.asarray(reduced.natural_l2g)
+        out[p + "red_offset_nowned_ntotal_nglobal"] = np.array([reduced.offset, reduced.n_owned, reduced.n_total, reduced.n_global])
+        out[p + "lifter_size_extra"] = np.array([lifter2.size, getattr(lifter2, "_nb_extra_ghost_dofs", 0)])
+        out[p + "free_dofs"] = np.asarray(lifter2.free_dofs)
+        per = lifter2.constraints[1]
+        out[p + "periodic_dofs"], out[p + "periodic_masters"] = np.asarray(per.dofs), np.asarray(per.master_dofs)
+        out[p + "u_red"], out[p + "lift_from_zeros"] = u_red, lifted_full

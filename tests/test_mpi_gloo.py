@@ -410,6 +410,40 @@ def _body_reference_compound_layout(rank, world):
         np.testing.assert_array_equal(got, g(f"{name}_gindices"))
 
 
+def _body_reference_periodic_mpi(rank, world):
+    """Lifter.adapt_layout with PeriodicMPI + Fixed on 3 gloo ranks against the UNMODIFIED reference (lifter/base.py:
+    333-425, constraints.py:223-287; fixtures `pmpi_*`): masters on another rank become extra ghosts, the reduced
+    layout renumbers the free DOFs, the resolved lifter lifts like the reference's."""
+    from tatva_b200.lifter import Fixed, Lifter, PeriodicMPI
+    from tatva_b200.mesh import Mesh, extract_local_mesh
+    from tatva_b200.mpi import _create_dof_layout
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    g = lambda k: G[f"pmpi_r{rank}_{k}"]  # noqa: E731
+    dpn = 3
+    c = G["pmpi_coords"]
+    mesh, info = extract_local_mesh(Mesh(coords=c, elements=G["pmpi_conn"]), G["pmpi_partition"], rank)
+    l2g_nodes = np.asarray(info.nodes_local_to_global)
+    natural = (l2g_nodes[:, None] * dpn + np.arange(dpn)).ravel().astype(np.int32)
+    owned = np.zeros(natural.size, dtype=bool)
+    owned[: int(info.n_owned_nodes) * dpn] = True
+    layout = _create_dof_layout(natural, owned, c.shape[0] * dpn, dist.group.WORLD)
+    lifter = Lifter(layout.n_total, Fixed(g("fixed_local_dofs"), 0.25), PeriodicMPI(G["pmpi_slaves"], G["pmpi_masters"], layout, comm=dist.group.WORLD))
+    reduced, lifter2 = lifter.adapt_layout(layout, dist.group.WORLD)
+    off, n_owned, n_total, n_global = (int(x) for x in g("red_offset_nowned_ntotal_nglobal"))
+    assert (reduced.offset, reduced.n_owned, reduced.n_total, reduced.n_global) == (off, n_owned, n_total, n_global)
+    np.testing.assert_array_equal(reduced.local_to_global, g("red_l2g"))
+    np.testing.assert_array_equal(reduced.owned_mask, g("red_owned_mask"))
+    np.testing.assert_array_equal(reduced.natural_l2g, g("red_natural"))
+    size, extra = (int(x) for x in g("lifter_size_extra"))
+    assert lifter2.size == size and getattr(lifter2, "_nb_extra_ghost_dofs", 0) == extra
+    np.testing.assert_array_equal(lifter2.free_dofs, g("free_dofs"))
+    per = lifter2.constraints[1]
+    np.testing.assert_array_equal(per.dofs, g("periodic_dofs"))
+    np.testing.assert_array_equal(per.master_dofs, g("periodic_masters"))
+    np.testing.assert_array_equal(lifter2.lift_from_zeros(g("u_red")), g("lift_from_zeros"))
+
+
 def _body_reference_plan_hex3(rank, world):
     _reference_plan_body(rank, world, "hex3")
 
@@ -429,7 +463,7 @@ def test_two_rank_gloo(body):
     _run(body, world=2)
 
 
-@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4), ("_body_reference_compound_layout", 3)])
+@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4), ("_body_reference_compound_layout", 3), ("_body_reference_periodic_mpi", 3)])
 def test_plans_match_the_reference_on_more_ranks(body, world):
     _run(body, world=world)
 
