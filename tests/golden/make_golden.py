@@ -443,6 +443,13 @@ def lifter_fixtures(out):
     out["lift_A"] = A
     out["lifted_dual"] = np.asarray(lifted(lambda uf: jnp.asarray(A @ uf), argnums=0, output="dual")(lifter, jnp.asarray(u_red)))
     out["lifted_primal"] = np.asarray(lifted(lambda uf: uf * 2.0, argnums=0, output="primal")(lifter, jnp.asarray(u_red)))
+    # sparsity adaptation (lifter/base.py:281-331, constraints.py:195-212): augmented by the periodic coupling, then
+    # reduced to the free DOFs
+    pat = sparse.pattern_from_mesh(Mesh(coords=jnp.asarray(c), elements=jnp.asarray(el)), 2)
+    for name, m in (("augmented", lifter.augment_sparsity(pat)), ("adapted", lifter.adapt_sparsity(pat))):
+        m = m.tocsr()
+        m.sort_indices()
+        out[f"lift_sp_{name}_indptr"], out[f"lift_sp_{name}_indices"] = np.asarray(m.indptr), np.asarray(m.indices)
 
 
 def mesh_size_fixtures(out):

@@ -189,6 +189,18 @@ def test_lifter_matches_the_reference_on_a_constraint_chain(golden):
     A = golden["lift_A"]
     np.testing.assert_allclose(lifted(lambda uf: A @ uf, argnums=0, output="dual")(lifter, u_red), golden["lifted_dual"], rtol=1e-13, atol=1e-13)
     np.testing.assert_array_equal(lifted(lambda uf: uf * 2.0, argnums=0, output="primal")(lifter, u_red), golden["lifted_primal"])
+    # sparsity adaptation on the mesh pattern: augmented by the periodic coupling, then reduced to the free DOFs
+    from oracle import tatva_oracle as orc
+    from tatva_b200 import sparse
+    from tatva_b200.mesh import Mesh
+
+    c, el = orc.mesh_unit_square_tri(6, 6)
+    pat = sparse.pattern_from_mesh(Mesh(coords=c, elements=el), 2)
+    for name, mtx in (("augmented", lifter.augment_sparsity(pat)), ("adapted", lifter.adapt_sparsity(pat))):
+        mtx = mtx.tocsr()
+        mtx.sort_indices()
+        np.testing.assert_array_equal(mtx.indptr, golden[f"lift_sp_{name}_indptr"])
+        np.testing.assert_array_equal(mtx.indices, golden[f"lift_sp_{name}_indices"])
     # dof_map == the homogeneous part of the reference's lift and the adjoint of its transpose chain
     m = lifter.dof_map()
     hom = lifter.homogeneous().lift_from_zeros(u_red)
