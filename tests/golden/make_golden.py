@@ -452,6 +452,39 @@ def lifter_fixtures(out):
         out[f"lift_sp_{name}_indptr"], out[f"lift_sp_{name}_indices"] = np.asarray(m.indptr), np.asarray(m.indices)
 
 
+def compound_pattern_fixtures(out):
+    """sparse.pattern_from_compound (sparse/_extraction.py:118-245) of the unmodified reference for a mixed layout: a full
+    nodal field, a nodal field on a node subset and a shared field (diagonal only), flat and block-wise."""
+    import warnings
+
+    from tatva.compound import Compound, FieldSize, field
+    from tatva.compound.field_types import Nodal, Shared
+
+    c, el = orc.mesh_unit_square_tri(5, 4)
+    mesh = Mesh(coords=jnp.asarray(c), elements=jnp.asarray(el))
+    sub = np.array([0, 3, 7, 8, 20])
+
+    class Mixed(Compound, mesh=mesh):
+        u = field(shape=(FieldSize.AUTO, 2))
+        lam = field(shape=(FieldSize.AUTO, 1), field_type=Nodal(node_ids=jnp.asarray(sub)))
+        g = field(shape=(3,), field_type=Shared())
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pat = sparse.pattern_from_compound(Mixed).tocsr()
+        blocks = sparse.pattern_from_compound(Mixed, block_wise=True)
+    pat.sort_indices()
+    out["cpat_subset"], out["cpat_size"] = sub, np.array(Mixed.size)
+    out["cpat_indptr"], out["cpat_indices"] = np.asarray(pat.indptr), np.asarray(pat.indices)
+    out["cpat_block_grid"] = np.array([len(blocks), len(blocks[0])])
+    for i, row in enumerate(blocks):
+        for j, b in enumerate(row):
+            b = b.tocsr()
+            b.sort_indices()
+            out[f"cpat_block_{i}{j}_shape"] = np.array(b.shape)
+            out[f"cpat_block_{i}{j}_indptr"], out[f"cpat_block_{i}{j}_indices"] = np.asarray(b.indptr), np.asarray(b.indices)
+
+
 def mesh_size_fixtures(out):
     """Mesh.hmin / hmax / _element_circumdiameters (mesh.py:87-144) on jittered meshes of every branch: triangles in
     2-D and embedded in 3-D, tetrahedra, and the max-vertex-distance fallback (quads, hexes)."""
@@ -485,6 +518,7 @@ def main():
     phase_field_fixtures(out)
     colored_jacobian_fixtures(out)
     lifter_fixtures(out)
+    compound_pattern_fixtures(out)
     from _fakempi_golden import mpi_fixtures
 
     mpi_fixtures(out)

@@ -177,3 +177,39 @@ def test_pattern_from_compound_mixed_layout_equals_the_pair_list_construction():
     assert pat.dtype == np.int8 and pat.indptr.dtype == np.int32
     np.testing.assert_array_equal(pat.indptr, ref.indptr)
     np.testing.assert_array_equal(pat.indices, ref.indices)
+
+
+def test_pattern_from_compound_matches_the_reference_flat_and_block_wise(golden):
+    """sparse.pattern_from_compound of the unmodified reference (sparse/_extraction.py:118-245) for a full nodal field, a
+    nodal field on a node subset and a shared field: same CSR, and the same block-wise decomposition."""
+    import warnings
+
+    from oracle import tatva_oracle as orc
+    from tatva_b200 import sparse
+    from tatva_b200.compound import Compound, FieldSize, FieldType, Nodal, field
+    from tatva_b200.mesh import Mesh
+
+    c, el = orc.mesh_unit_square_tri(5, 4)
+    mesh = Mesh(coords=c, elements=el.astype(np.int32))
+
+    class Mixed(Compound, mesh=mesh):
+        u = field(shape=(FieldSize.AUTO, 2))
+        lam = field(shape=(FieldSize.AUTO, 1), field_type=Nodal(node_ids=golden["cpat_subset"]))
+        g = field(shape=(3,), field_type=FieldType.SHARED)
+
+    assert Mixed.size == int(golden["cpat_size"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pat = sparse.pattern_from_compound(Mixed)
+        blocks = sparse.pattern_from_compound(Mixed, block_wise=True)
+    np.testing.assert_array_equal(pat.indptr, golden["cpat_indptr"])
+    np.testing.assert_array_equal(pat.indices, golden["cpat_indices"])
+    ni, nj = (int(x) for x in golden["cpat_block_grid"])
+    assert len(blocks) == ni and all(len(row) == nj for row in blocks)
+    for i in range(ni):
+        for j in range(nj):
+            b = blocks[i][j].tocsr()
+            b.sort_indices()
+            assert tuple(b.shape) == tuple(golden[f"cpat_block_{i}{j}_shape"])
+            np.testing.assert_array_equal(b.indptr, golden[f"cpat_block_{i}{j}_indptr"])
+            np.testing.assert_array_equal(b.indices, golden[f"cpat_block_{i}{j}_indices"])
