@@ -46,6 +46,33 @@ def mpi_fixtures(out):
             plan = ExchangePlan(layout, pat, comm=comm)
             return layout, plan, (np.asarray(pat.indptr), np.asarray(pat.indices))
 
+        n_global_dofs = None
+
+        def per_rank_exchange(comm, c=c, el=el, part=part, dpn=dpn, n_nat=n_nat):
+            """The reference's exchange functions at work: forward ghost fill, reverse add of a vector, reverse add of
+            Hessian nonzeros (mpi.py:372-516), with inputs that are functions of global ids so every rank can build them."""
+            from dataclasses import replace
+
+            import jax.numpy as jnp
+
+            layout, plan, (ip, ix) = per_rank(comm)
+            l2g = np.asarray(layout.local_to_global)
+            x_owned = np.sin(0.37 * np.arange(layout.offset, layout.offset + layout.n_owned))
+            u_local = np.asarray(plan.make_scatter_fwd_set()(jnp.asarray(x_owned)))
+            contrib = np.cos(0.11 * l2g + 0.5 * comm.rank)  # local (owned + ghost) contributions, rank dependent
+            owned = np.asarray(plan.make_scatter_rev_add(lambda: jnp.asarray(contrib))())
+            pat = sparse.pattern_from_mesh(extract_local_mesh(Mesh(coords=c, elements=el), part, comm.rank)[0], dpn)
+            cm = sparse.ColoredMatrix.from_csr(pat)
+            nnz_vals = np.sin(0.013 * np.arange(len(ix)) + comm.rank)
+            owned_nnz = np.asarray(plan.make_scatter_rev_add(lambda: replace(cm, data=jnp.asarray(nnz_vals)), is_hessian=True)().data)
+            return x_owned, u_local, contrib, owned, nnz_vals, owned_nnz
+
+        for r, (x_owned, u_local, contrib, owned, nnz_vals, owned_nnz) in enumerate(run_ranks(size, per_rank_exchange)):
+            p = f"mpi_{name}_r{r}_"
+            out[p + "x_owned"], out[p + "fwd_u_local"] = x_owned, u_local
+            out[p + "rev_contrib"], out[p + "rev_owned"] = contrib, owned
+            out[p + "rev_nnz_vals"], out[p + "rev_owned_nnz"] = nnz_vals, owned_nnz
+
         res = run_ranks(size, per_rank)
         for r, (layout, plan, (ip, ix)) in enumerate(res):
             p = f"mpi_{name}_r{r}_"

@@ -369,6 +369,16 @@ def _reference_plan_body(rank, world, name):
     x_owned = torch.as_tensor(np.arange(off, off + n_owned, dtype=np.float64))  # value = global DOF id
     u_local = plan.make_scatter_fwd_set()(x_owned)
     np.testing.assert_array_equal(u_local.numpy(), np.asarray(layout.local_to_global, dtype=np.float64))
+    # the reference's own exchange functions on the same inputs (mpi.py:372-516, run on the stand-in): forward ghost
+    # fill, reverse add of a local vector, reverse add of Hessian nonzeros
+    from dataclasses import replace as dc_replace
+
+    np.testing.assert_array_equal(plan.make_scatter_fwd_set()(torch.as_tensor(g("x_owned"))).numpy(), g("fwd_u_local"))
+    contrib = torch.as_tensor(g("rev_contrib"))
+    np.testing.assert_allclose(plan.make_scatter_rev_add(lambda: contrib)().numpy(), g("rev_owned"), rtol=1e-14, atol=1e-14)
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    Kd = plan.make_scatter_rev_add(lambda: dc_replace(cm, data=torch.as_tensor(g("rev_nnz_vals"))), is_hessian=True)()
+    np.testing.assert_allclose(np.asarray(Kd.data), g("rev_owned_nnz"), rtol=1e-14, atol=1e-14)
 
 
 def _body_reference_compound_layout(rank, world):
