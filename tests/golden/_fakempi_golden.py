@@ -16,6 +16,7 @@ from mpi4py import run_ranks  # noqa: E402  (the stand-in)
 def mpi_fixtures(out):
     compound_fixtures(out)
     periodic_mpi_fixtures(out)
+    allreduce_plan_fixtures(out)
     from tatva import Mesh, sparse
     from tatva.mesh import extract_local_mesh
     from tatva.mpi import ExchangePlan, _create_dof_layout
@@ -191,3 +192,41 @@ def periodic_mpi_fixtures(out):
         per = lifter2.constraints[1]
         out[p + "periodic_dofs"], out[p + "periodic_masters"] = np.asarray(per.dofs), np.asarray(per.master_dofs)
         out[p + "u_red"], out[p + "lift_from_zeros"] = u_red, lifted_full
+
+
+def allreduce_plan_fixtures(out):
+    """AllreducePlan (mpi.py:519-711) of the unmodified reference on 4 ranks over the Tri3 5x4 global pattern with 2 DOFs
+    per node: block ranges, owned CSR slices, allgather of the owned blocks, all-reduced owned vector and Hessian."""
+    from dataclasses import replace
+
+    import jax.numpy as jnp
+    from tatva import Mesh, sparse
+    from tatva.mpi import AllreducePlan
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import tatva_oracle as orc
+
+    c, el = orc.mesh_unit_square_tri(5, 4)
+    pat = sparse.pattern_from_mesh(Mesh(coords=jnp.asarray(c), elements=jnp.asarray(el)), 2)
+    n = pat.shape[0]
+    out["arp_coords"], out["arp_conn"] = c, el
+
+    def per_rank(comm):
+        plan = AllreducePlan(n, pat, comm=comm)
+        x_owned = np.sin(0.3 * np.arange(plan.rstart, plan.rend))
+        full = np.asarray(plan.make_allgather()(x_owned))
+        vec = np.cos(0.07 * np.arange(n) * (comm.rank + 1))
+        owned_vec = np.asarray(plan.make_allreduce_owned(lambda: jnp.asarray(vec))())
+        cm = sparse.ColoredMatrix.from_csr(pat)
+        vals = np.sin(0.01 * np.arange(pat.indices.shape[0]) + comm.rank)
+        K = plan.make_allreduce_owned(lambda: replace(cm, data=jnp.asarray(vals)), is_hessian=True)()
+        return plan, x_owned, full, vec, owned_vec, vals, K
+
+    for r, (plan, x_owned, full, vec, owned_vec, vals, K) in enumerate(run_ranks(4, per_rank)):
+        p = f"arp_r{r}_"
+        out[p + "range_nnz"] = np.array([plan.rstart, plan.rend, plan.owned_nnz])
+        out[p + "owned_ptr"], out[p + "owned_indices"] = (np.asarray(a) for a in plan.owned_csr)
+        out[p + "x_owned"], out[p + "allgather"] = x_owned, full
+        out[p + "vec"], out[p + "owned_vec"] = vec, owned_vec
+        out[p + "vals"], out[p + "K_data"], out[p + "K_shape"] = vals, np.asarray(K.data), np.array(K.shape)
+        out[p + "K_indptr"], out[p + "K_indices"] = np.asarray(K.indptr), np.asarray(K.indices)

@@ -454,6 +454,33 @@ def _body_reference_periodic_mpi(rank, world):
     np.testing.assert_array_equal(lifter2.lift_from_zeros(g("u_red")), g("lift_from_zeros"))
 
 
+def _body_reference_allreduce_plan(rank, world):
+    """AllreducePlan on 4 gloo ranks against the UNMODIFIED reference (mpi.py:519-711, fixtures `arp_*`)."""
+    from dataclasses import replace as dc_replace
+
+    from tatva_b200 import sparse
+    from tatva_b200.mesh import Mesh
+    from tatva_b200.mpi import AllreducePlan
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    g = lambda k: G[f"arp_r{rank}_{k}"]  # noqa: E731
+    pat = sparse.pattern_from_mesh(Mesh(coords=G["arp_coords"], elements=G["arp_conn"]), 2)
+    plan = AllreducePlan(pat.shape[0], pat, comm=dist.group.WORLD)
+    rs, re, nnz = (int(x) for x in g("range_nnz"))
+    assert (plan.rstart, plan.rend, plan.owned_nnz) == (rs, re, nnz)
+    np.testing.assert_array_equal(plan.owned_csr[0], g("owned_ptr"))
+    np.testing.assert_array_equal(plan.owned_csr[1], g("owned_indices"))
+    np.testing.assert_array_equal(np.asarray(plan.make_allgather()(torch.as_tensor(g("x_owned")))), g("allgather"))
+    vec = torch.as_tensor(g("vec"))
+    np.testing.assert_allclose(np.asarray(plan.make_allreduce_owned(lambda: vec)()), g("owned_vec"), rtol=1e-14, atol=1e-14)
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    K = plan.make_allreduce_owned(lambda: dc_replace(cm, data=torch.as_tensor(g("vals"))), is_hessian=True)()
+    np.testing.assert_allclose(np.asarray(K.data), g("K_data"), rtol=1e-14, atol=1e-14)
+    assert tuple(K.shape) == tuple(g("K_shape"))
+    np.testing.assert_array_equal(K.indptr, g("K_indptr"))
+    np.testing.assert_array_equal(K.indices, g("K_indices"))
+
+
 def _body_reference_plan_hex3(rank, world):
     _reference_plan_body(rank, world, "hex3")
 
@@ -473,7 +500,7 @@ def test_two_rank_gloo(body):
     _run(body, world=2)
 
 
-@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4), ("_body_reference_compound_layout", 3), ("_body_reference_periodic_mpi", 3)])
+@pytest.mark.parametrize("body,world", [("_body_reference_plan_hex3", 3), ("_body_reference_plan_tri4", 4), ("_body_reference_compound_layout", 3), ("_body_reference_periodic_mpi", 3), ("_body_reference_allreduce_plan", 4)])
 def test_plans_match_the_reference_on_more_ranks(body, world):
     _run(body, world=world)
 
