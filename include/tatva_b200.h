@@ -300,6 +300,19 @@ int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int n
                                      int dofs_per_node, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos);
 
+/* ---- host probes (no GPU): the kernels' per-element arithmetic executed on the CPU -----------------------------
+ * The element tables, geometry, constitutive laws and the modal / pair functions of the Hex8 kernels are compiled for
+ * host and device from the same source; these two entry points run one element through them on the CPU so that the
+ * kernels' formulas can be verified against the oracle where no GPU is available.  All pointers are HOST pointers.
+ *   tatva_probe_element:        generic element body (k_fused / k_hessian_diag): X (npe, dim), u, v (npe, dpn);
+ *                               mode 0 energy -> out[0]; 1 residual, 2 HVP, 3 Hessian diagonal -> out (npe, dpn)
+ *   tatva_probe_hex8_nh_modal:  the pair kernels of the Hex8 x neo-Hookean path (HVP v3, residual v3, energy v3):
+ *                               X, u, v (8, 3); mode 0 energy, 1 residual, 2 HVP -> out[0] or out (8, 3)          */
+int tatva_probe_element(int element, int material, const double* params, int n_params, int mode,
+                        const double* X, const double* u, const double* v, double* out);
+int tatva_probe_hex8_nh_modal(int mode, const double* X, const double* u, const double* v, double mu,
+                              double lmbda, double* out);
+
 /* ---- measurement helper: sustained FP64 FMA rate of the device (DFMA microbenchmark) ---- */
 int tatva_fp64_peak_tflops(double* tflops, tatva_stream_t stream);
 

@@ -21,13 +21,13 @@ constexpr int kBlock = 128;  // threads per CTA for element-per-thread kernels
 
 struct Tri3 {  // tatva/element/base.py:245-265
   static constexpr int dim = 2, gdim = 2, npe = 3, nq = 1, kind = TATVA_TRI3;
-  TATVA_D static double weight(int) { return 0.5; }
-  TATVA_D static void N(int, double (&n)[npe]) {
+  TATVA_HD static double weight(int) { return 0.5; }
+  TATVA_HD static void N(int, double (&n)[npe]) {
     n[0] = 1.0 - 1.0 / 3 - 1.0 / 3;
     n[1] = 1.0 / 3;
     n[2] = 1.0 / 3;
   }
-  TATVA_D static void dNdr(int, double (&d)[dim][npe]) {
+  TATVA_HD static void dNdr(int, double (&d)[dim][npe]) {
     d[0][0] = -1.0; d[0][1] = 1.0; d[0][2] = 0.0;
     d[1][0] = -1.0; d[1][1] = 0.0; d[1][2] = 1.0;
   }
@@ -35,14 +35,14 @@ struct Tri3 {  // tatva/element/base.py:245-265
 
 struct Tet4 {  // tatva/element/base.py:448-472
   static constexpr int dim = 3, gdim = 3, npe = 4, nq = 1, kind = TATVA_TET4;
-  TATVA_D static double weight(int) { return 1.0 / 6; }
-  TATVA_D static void N(int, double (&n)[npe]) {
+  TATVA_HD static double weight(int) { return 1.0 / 6; }
+  TATVA_HD static void N(int, double (&n)[npe]) {
     n[0] = 1.0 - 0.25 - 0.25 - 0.25;
     n[1] = 0.25;
     n[2] = 0.25;
     n[3] = 0.25;
   }
-  TATVA_D static void dNdr(int, double (&d)[dim][npe]) {
+  TATVA_HD static void dNdr(int, double (&d)[dim][npe]) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       d[j][0] = -1.0;
@@ -61,15 +61,15 @@ struct Hex8 {  // tatva/element/base.py:475-568
          : d == 1 ? (((n & 3) >= 2) ? 1.0 : -1.0)
                   : ((n >= 4) ? 1.0 : -1.0);
   }
-  TATVA_D static double weight(int) { return 1.0; }
-  TATVA_D static void N(int q, double (&n)[npe]) {
+  TATVA_HD static double weight(int) { return 1.0; }
+  TATVA_HD static void N(int q, double (&n)[npe]) {
     const double a = 0.57735026918962576451;  // 1/sqrt(3)
     const double x = a * sgn(q, 0), y = a * sgn(q, 1), z = a * sgn(q, 2);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       n[k] = 0.125 * (1.0 + sgn(k, 0) * x) * (1.0 + sgn(k, 1) * y) * (1.0 + sgn(k, 2) * z);
   }
-  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
     const double a = 0.57735026918962576451;
     const double x = a * sgn(q, 0), y = a * sgn(q, 1), z = a * sgn(q, 2);
 #pragma unroll
@@ -85,19 +85,19 @@ struct Hex8 {  // tatva/element/base.py:475-568
 struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:338-344)
   static constexpr int dim = 2, gdim = 2, npe = 4, nq = 4, kind = TATVA_QUAD4;
   TATVA_HD static constexpr double sgn(int n, int d) { return d == 0 ? ((n == 1 || n == 2) ? 1.0 : -1.0) : ((n >= 2) ? 1.0 : -1.0); }
-  TATVA_D static double weight(int) { return 1.0; }
-  TATVA_D static void xi(int q, double& r, double& s) {
+  TATVA_HD static double weight(int) { return 1.0; }
+  TATVA_HD static void xi(int q, double& r, double& s) {
     const double a = 0.57735026918962576451;
     r = (q & 1) ? a : -a;
     s = (q & 2) ? a : -a;
   }
-  TATVA_D static void N(int q, double (&n)[npe]) {
+  TATVA_HD static void N(int q, double (&n)[npe]) {
     double r, s;
     xi(q, r, s);
 #pragma unroll
     for (int k = 0; k < 4; ++k) n[k] = 0.25 * (1.0 + sgn(k, 0) * r) * (1.0 + sgn(k, 1) * s);
   }
-  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
     double r, s;
     xi(q, r, s);
 #pragma unroll
@@ -110,19 +110,19 @@ struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:
 
 struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
   static constexpr int dim = 2, gdim = 2, npe = 6, nq = 3, kind = TATVA_TRI6;
-  TATVA_D static double weight(int) { return 1.0 / 6.0; }
-  TATVA_D static void xi(int q, double& r, double& s) {
+  TATVA_HD static double weight(int) { return 1.0 / 6.0; }
+  TATVA_HD static void xi(int q, double& r, double& s) {
     r = (q == 1) ? 2.0 / 3.0 : 1.0 / 6.0;
     s = (q == 2) ? 2.0 / 3.0 : 1.0 / 6.0;
   }
-  TATVA_D static void N(int q, double (&n)[npe]) {
+  TATVA_HD static void N(int q, double (&n)[npe]) {
     double r, s;
     xi(q, r, s);
     const double t = 1.0 - r - s;
     n[0] = t * (2 * t - 1); n[1] = r * (2 * r - 1); n[2] = s * (2 * s - 1);
     n[3] = 4 * r * t; n[4] = 4 * r * s; n[5] = 4 * s * t;
   }
-  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
     double r, s;
     xi(q, r, s);
     const double t = 1.0 - r - s;
@@ -133,14 +133,14 @@ struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
 
 struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:384-393)
   static constexpr int dim = 2, gdim = 2, npe = 8, nq = 9, kind = TATVA_QUAD8;
-  TATVA_D static double w1(int i) { return i == 1 ? 8.0 / 9.0 : 5.0 / 9.0; }
-  TATVA_D static double x1(int i) { return i == 0 ? -0.77459666924148337704 : (i == 1 ? 0.0 : 0.77459666924148337704); }
-  TATVA_D static double weight(int q) { return w1(q / 3) * w1(q % 3); }
-  TATVA_D static void xi(int q, double& r, double& s) {
+  TATVA_HD static double w1(int i) { return i == 1 ? 8.0 / 9.0 : 5.0 / 9.0; }
+  TATVA_HD static double x1(int i) { return i == 0 ? -0.77459666924148337704 : (i == 1 ? 0.0 : 0.77459666924148337704); }
+  TATVA_HD static double weight(int q) { return w1(q / 3) * w1(q % 3); }
+  TATVA_HD static void xi(int q, double& r, double& s) {
     r = x1(q % 3);
     s = x1(q / 3);
   }
-  TATVA_D static void N(int q, double (&n)[npe]) {
+  TATVA_HD static void N(int q, double (&n)[npe]) {
     double r, s;
     xi(q, r, s);
     n[0] = 0.25 * (1 - r) * (1 - s) * (-r - s - 1);
@@ -152,7 +152,7 @@ struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:
     n[6] = 0.5 * (1 - r * r) * (1 + s);
     n[7] = 0.5 * (1 - r) * (1 - s * s);
   }
-  TATVA_D static void dNdr(int q, double (&d)[dim][npe]) {
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
     double r, s;
     xi(q, r, s);
     d[0][0] = 0.25 * (-2 * r - s) * (s - 1); d[0][1] = 0.25 * (-2 * r + s) * (s - 1);
@@ -168,22 +168,22 @@ struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:
 // number of gradient components (1: the derivative along the arc length).  tatva/element/base.py:144-242.
 struct Line2 {  // tatva/element/base.py:144-186
   static constexpr int dim = 2, gdim = 1, npe = 2, nq = 1, kind = TATVA_LINE2;
-  TATVA_D static double weight(int) { return 2.0; }
-  TATVA_D static void N(int, double (&n)[npe]) { n[0] = 0.5; n[1] = 0.5; }
-  TATVA_D static void dNdr(int, double (&d)[gdim][npe]) { d[0][0] = -0.5; d[0][1] = 0.5; }
+  TATVA_HD static double weight(int) { return 2.0; }
+  TATVA_HD static void N(int, double (&n)[npe]) { n[0] = 0.5; n[1] = 0.5; }
+  TATVA_HD static void dNdr(int, double (&d)[gdim][npe]) { d[0][0] = -0.5; d[0][1] = 0.5; }
 };
 
 struct Line3 {  // tatva/element/base.py:189-242; nodes (-1, 1, 0), 3-point Gauss
   static constexpr int dim = 2, gdim = 1, npe = 3, nq = 3, kind = TATVA_LINE3;
-  TATVA_D static double xi(int q) { return (q - 1) * 0.77459666924148337704; }  // sqrt(3/5)
-  TATVA_D static double weight(int q) { return q == 1 ? 8.0 / 9 : 5.0 / 9; }
-  TATVA_D static void N(int q, double (&n)[npe]) {
+  TATVA_HD static double xi(int q) { return (q - 1) * 0.77459666924148337704; }  // sqrt(3/5)
+  TATVA_HD static double weight(int q) { return q == 1 ? 8.0 / 9 : 5.0 / 9; }
+  TATVA_HD static void N(int q, double (&n)[npe]) {
     const double r = xi(q);
     n[0] = 0.5 * r * (r - 1.0);
     n[1] = 0.5 * r * (r + 1.0);
     n[2] = 1.0 - r * r;
   }
-  TATVA_D static void dNdr(int q, double (&d)[gdim][npe]) {
+  TATVA_HD static void dNdr(int q, double (&d)[gdim][npe]) {
     const double r = xi(q);
     d[0][0] = r - 0.5;
     d[0][1] = r + 0.5;
@@ -239,7 +239,7 @@ TATVA_D void load_row(const double* __restrict__ src, int64_t node, double (&dst
 // tatva/element/base.py:92, :113)
 // ---------------------------------------------------------------------------------------------
 
-TATVA_D double det_inv(const double (&A)[2][2], double (&Ai)[2][2]) {
+TATVA_HD double det_inv(const double (&A)[2][2], double (&Ai)[2][2]) {
   const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
   const double r = 1.0 / det;
   Ai[0][0] = A[1][1] * r;
@@ -249,7 +249,7 @@ TATVA_D double det_inv(const double (&A)[2][2], double (&Ai)[2][2]) {
   return det;
 }
 
-TATVA_D double det_inv(const double (&A)[3][3], double (&Ai)[3][3]) {
+TATVA_HD double det_inv(const double (&A)[3][3], double (&Ai)[3][3]) {
   const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
   const double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
   const double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
@@ -272,7 +272,7 @@ TATVA_D double det_inv(const double (&A)[3][3], double (&Ai)[3][3]) {
 // Arc-length Jacobian of a line element: J = |dNdr @ X_e| (the reference's dot(Jvec, Jvec / |Jvec|),
 // tatva/element/base.py:163-167, :218-224), dNdS = dNdr / J.
 template <class El>
-TATVA_D double line_jacobian(int q, const double (&X)[El::npe][El::dim], double (&dNdr)[1][El::npe]) {
+TATVA_HD double line_jacobian(int q, const double (&X)[El::npe][El::dim], double (&dNdr)[1][El::npe]) {
   El::dNdr(q, dNdr);
   double n2 = 0.0;
 #pragma unroll
@@ -286,7 +286,7 @@ TATVA_D double line_jacobian(int q, const double (&X)[El::npe][El::dim], double 
 }
 
 template <class El>
-TATVA_D double geometry(int q, const double (&X)[El::npe][El::dim], double (&dNdX)[El::gdim][El::npe]) {
+TATVA_HD double geometry(int q, const double (&X)[El::npe][El::dim], double (&dNdX)[El::gdim][El::npe]) {
   if constexpr (El::gdim != El::dim) {
     const double J = line_jacobian<El>(q, X, dNdX);
 #pragma unroll
@@ -320,7 +320,7 @@ TATVA_D double geometry(int q, const double (&X)[El::npe][El::dim], double (&dNd
 }
 
 template <class El>
-TATVA_D double det_jacobian(int q, const double (&X)[El::npe][El::dim]) {
+TATVA_HD double det_jacobian(int q, const double (&X)[El::npe][El::dim]) {
   if constexpr (El::gdim != El::dim) {
     double dNdr[1][El::npe];
     return line_jacobian<El>(q, X, dNdr);
@@ -366,8 +366,8 @@ struct LinearElastic {  // tests/test_sparse.py:20-38
   double mu, lmbda;
   struct Cache {};
   using S = QState<dpn, dim>;
-  TATVA_D void prepare(const S&, Cache&) const {}
-  TATVA_D double psi(const S& s, const Cache&) const {
+  TATVA_HD void prepare(const S&, Cache&) const {}
+  TATVA_HD double psi(const S& s, const Cache&) const {
     double tr = 0.0, ee = 0.0;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) {
@@ -380,7 +380,7 @@ struct LinearElastic {  // tests/test_sparse.py:20-38
     }
     return mu * ee + 0.5 * lmbda * tr * tr;
   }
-  TATVA_D void first(const S& s, const Cache&, S& f) const {
+  TATVA_HD void first(const S& s, const Cache&, S& f) const {
     double tr = 0.0;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) tr += s.G[i][i];
@@ -389,7 +389,7 @@ struct LinearElastic {  // tests/test_sparse.py:20-38
 #pragma unroll
       for (int j = 0; j < DIM; ++j) f.G[i][j] = mu * (s.G[i][j] + s.G[j][i]) + (i == j ? lmbda * tr : 0.0);
   }
-  TATVA_D void second(const S&, const Cache& c, const S& ds, S& f) const { first(ds, c, f); }
+  TATVA_HD void second(const S&, const Cache& c, const S& ds, S& f) const { first(ds, c, f); }
 };
 
 struct NeoHookean {  // tests/test_sparse_tracer.py:103-115 (mu=500, lambda=1000 at :126)
@@ -402,7 +402,7 @@ struct NeoHookean {  // tests/test_sparse_tracer.py:103-115 (mu=500, lambda=1000
     double I1;
   };
   using S = QState<3, 3>;
-  TATVA_D void prepare(const S& s, Cache& c) const {
+  TATVA_HD void prepare(const S& s, Cache& c) const {
     double F[3][3];
     double I1 = 0.0;
 #pragma unroll
@@ -416,11 +416,11 @@ struct NeoHookean {  // tests/test_sparse_tracer.py:103-115 (mu=500, lambda=1000
     c.lnJ = log(J);
     c.I1 = I1;
   }
-  TATVA_D double psi(const S&, const Cache& c) const {
+  TATVA_HD double psi(const S&, const Cache& c) const {
     return 0.5 * mu * (c.I1 - 3.0 - 2.0 * c.lnJ) + 0.5 * lmbda * c.lnJ * c.lnJ;
   }
   // P = mu (F - F^-T) + lambda lnJ F^-T
-  TATVA_D void first(const S& s, const Cache& c, S& f) const {
+  TATVA_HD void first(const S& s, const Cache& c, S& f) const {
     const double k = lmbda * c.lnJ - mu;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -428,7 +428,7 @@ struct NeoHookean {  // tests/test_sparse_tracer.py:103-115 (mu=500, lambda=1000
       for (int j = 0; j < 3; ++j) f.G[i][j] = mu * (s.G[i][j] + (i == j ? 1.0 : 0.0)) + k * c.Fi[j][i];
   }
   // dP = mu dG + (mu - lambda lnJ) F^-T dG^T F^-T + lambda tr(F^-1 dG) F^-T
-  TATVA_D void second(const S&, const Cache& c, const S& ds, S& f) const {
+  TATVA_HD void second(const S&, const Cache& c, const S& ds, S& f) const {
     double B[3][3];  // F^-1 dG
     double tr = 0.0;
 #pragma unroll
@@ -466,14 +466,14 @@ struct NeoHookeanPhaseField {
     double P[3][3];
   };
   using S = QState<4, 3>;
-  TATVA_D NeoHookean nh() const { return NeoHookean{mu, lmbda}; }
-  TATVA_D static void sub(const S& s, NeoHookean::S& t) {
+  TATVA_HD NeoHookean nh() const { return NeoHookean{mu, lmbda}; }
+  TATVA_HD static void sub(const S& s, NeoHookean::S& t) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 3; ++j) t.G[i][j] = s.G[i][j];
   }
-  TATVA_D void prepare(const S& s, Cache& c) const {
+  TATVA_HD void prepare(const S& s, Cache& c) const {
     NeoHookean::S t, P;
     sub(s, t);
     const NeoHookean m = nh();
@@ -485,13 +485,13 @@ struct NeoHookeanPhaseField {
 #pragma unroll
       for (int j = 0; j < 3; ++j) c.P[i][j] = P.G[i][j];
   }
-  TATVA_D double psi(const S& s, const Cache& c) const {
+  TATVA_HD double psi(const S& s, const Cache& c) const {
     const double phi = s.val[3];
     const double g = (1.0 - phi) * (1.0 - phi) + k;
     const double gg = s.G[3][0] * s.G[3][0] + s.G[3][1] * s.G[3][1] + s.G[3][2] * s.G[3][2];
     return g * c.psi_nh + Gc * (phi * phi / (2.0 * ell) + 0.5 * ell * gg);
   }
-  TATVA_D void first(const S& s, const Cache& c, S& f) const {
+  TATVA_HD void first(const S& s, const Cache& c, S& f) const {
     const double phi = s.val[3];
     const double g = (1.0 - phi) * (1.0 - phi) + k, dg = -2.0 * (1.0 - phi);
 #pragma unroll
@@ -502,7 +502,7 @@ struct NeoHookeanPhaseField {
     for (int j = 0; j < 3; ++j) f.G[3][j] = Gc * ell * s.G[3][j];
     f.val[3] = dg * c.psi_nh + Gc * phi / ell;
   }
-  TATVA_D void second(const S& s, const Cache& c, const S& ds, S& f) const {
+  TATVA_HD void second(const S& s, const Cache& c, const S& ds, S& f) const {
     const double phi = s.val[3], dphi = ds.val[3];
     const double g = (1.0 - phi) * (1.0 - phi) + k, dg = -2.0 * (1.0 - phi);
     NeoHookean::S t, dt, dP;

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(128) k_interpolate_grid(const double* __restri
 enum { MODE_ENERGY = 0, MODE_RESIDUAL = 1, MODE_HVP = 2 };
 
 template <class El, class Mat>
-TATVA_D void qp_state(const double (&dNdX)[El::dim][El::npe], const double (&N)[El::npe],
+TATVA_HD void qp_state(const double (&dNdX)[El::dim][El::npe], const double (&N)[El::npe],
                       const double (&U)[El::npe][Mat::dpn], typename Mat::S& s) {
 #pragma unroll
   for (int c = 0; c < Mat::dpn; ++c) {
@@ -1874,6 +1874,81 @@ int tatva_hvp_lifted(tatva_plan_t* p, int material, const double* params, int n_
 }
 
 }  // extern "C"
+
+// ---- host probe of the generic element body ---------------------------------------------------------
+// The arithmetic of k_fused / k_hessian_diag for ONE element on the CPU, through the same element tables, geometry and
+// constitutive-law functions compiled for the host: lets the CPU test suite check the kernels' formulas against the
+// oracle.  mode 0 energy (out[0]), 1 residual, 2 HVP, 3 Hessian diagonal (out[npe][dpn]).  HOST pointers.
+template <class El, class Mat>
+static int probe_element(const Mat& mat, int mode, const double* Xp, const double* up, const double* vp, double* out) {
+  constexpr int dpn = Mat::dpn;
+  double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn], Y[El::npe][dpn];
+  for (int n = 0; n < El::npe; ++n) {
+    for (int c = 0; c < El::dim; ++c) X[n][c] = Xp[n * El::dim + c];
+    for (int c = 0; c < dpn; ++c) {
+      U[n][c] = up[n * dpn + c];
+      V[n][c] = vp ? vp[n * dpn + c] : 0.0;
+      Y[n][c] = 0.0;
+    }
+  }
+  double energy = 0.0;
+  for (int q = 0; q < El::nq; ++q) {
+    double dNdX[El::dim][El::npe], N[El::npe];
+    const double W = geometry<El>(q, X, dNdX) * El::weight(q);
+    El::N(q, N);
+    typename Mat::S s, ds, f;
+    typename Mat::Cache cache;
+    qp_state<El, Mat>(dNdX, N, U, s);
+    mat.prepare(s, cache);
+    if (mode == 0) {
+      energy += W * mat.psi(s, cache);
+      continue;
+    }
+    if (mode == 3) {
+      for (int b = 0; b < El::npe; ++b)
+        for (int k = 0; k < dpn; ++k) {
+          for (int c = 0; c < dpn; ++c) {
+            for (int j = 0; j < El::dim; ++j) ds.G[c][j] = (c == k) ? dNdX[j][b] : 0.0;
+            ds.val[c] = (c == k) ? N[b] : 0.0;
+          }
+          mat.second(s, cache, ds, f);
+          double t = 0.0;
+          for (int j = 0; j < El::dim; ++j) t += f.G[k][j] * dNdX[j][b];
+          if (k >= Mat::val_lo) t += f.val[k] * N[b];
+          Y[b][k] += W * t;
+        }
+      continue;
+    }
+    if (mode == 1) {
+      mat.first(s, cache, f);
+    } else {
+      qp_state<El, Mat>(dNdX, N, V, ds);
+      mat.second(s, cache, ds, f);
+    }
+    for (int n = 0; n < El::npe; ++n)
+      for (int c = 0; c < dpn; ++c) {
+        double t = 0.0;
+        for (int j = 0; j < El::dim; ++j) t += f.G[c][j] * dNdX[j][n];
+        if (c >= Mat::val_lo) t += f.val[c] * N[n];
+        Y[n][c] += W * t;
+      }
+  }
+  if (mode == 0) {
+    out[0] = energy;
+  } else {
+    for (int n = 0; n < El::npe; ++n)
+      for (int c = 0; c < dpn; ++c) out[n * dpn + c] = Y[n][c];
+  }
+  return TATVA_OK;
+}
+
+extern "C" int tatva_probe_element(int element, int material, const double* params, int n_params, int mode, const double* X,
+                                   const double* u, const double* v, double* out) {
+  if (!params || !X || !u || !out || mode < 0 || mode > 3 || (mode == 2 && !v)) return TATVA_E_INVALID;
+  return for_element_law(element, material, params, n_params, [&](auto el, auto mat) -> int {
+    return probe_element<decltype(el), decltype(mat)>(mat, mode, X, u, v, out);
+  });
+}
 
 extern "C" {
 // Element sub-range variants (overlap of halo exchange with interior elements): elements

@@ -224,7 +224,7 @@ TATVA_D void ref_grad_s(Ptr c, int stride, double tx, double ty, double tz, doub
   g[2] = fma(tx, fma(ty, c6, c5), fma(ty, c4, c2));
 }
 
-TATVA_D void adjugate(const double (&A)[3][3], double (&C)[3][3], double& det) {
+TATVA_HD void adjugate(const double (&A)[3][3], double (&C)[3][3], double& det) {
   C[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
   C[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2];
   C[2][0] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
@@ -435,7 +435,7 @@ __constant__ double kScaledSigns[8][6] = {
 #undef TATVA_S
 };
 
-TATVA_D void to_modal_raw(const double (&f)[8], double (&h)[7]) {
+TATVA_HD void to_modal_raw(const double (&f)[8], double (&h)[7]) {
   const double s01 = f[0] + f[1], d01 = f[1] - f[0];
   const double s23 = f[3] + f[2], d23 = f[2] - f[3];
   const double s45 = f[4] + f[5], d45 = f[5] - f[4];
@@ -451,7 +451,7 @@ TATVA_D void to_modal_raw(const double (&f)[8], double (&h)[7]) {
   h[6] = dd1 - dd0;  // xyz
 }
 
-TATVA_D void from_modal_raw(const double (&r)[7], double (&f)[8]) {
+TATVA_HD void from_modal_raw(const double (&r)[7], double (&f)[8]) {
   const double xm = r[0] - r[5], xp = r[0] + r[5];
   const double ym = r[1] - r[4], yp = r[1] + r[4];
   const double xym = r[3] - r[6], xyp = r[3] + r[6];
@@ -477,7 +477,7 @@ TATVA_D void ref_grad8(const double (&h)[7], double sx, double sy, double sz, do
 }
 
 // C = A * B (3x3), written k-outer: consecutive DFMAs share A[i][k]
-TATVA_D void mat3(const double (&A)[3][3], const double (&Bm)[3][3], double (&C)[3][3]) {
+TATVA_HD void mat3(const double (&A)[3][3], const double (&Bm)[3][3], double (&C)[3][3]) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -635,10 +635,13 @@ __global__ void __launch_bounds__(kBlock, MINB)
 // (ty, tz) partial sums of every field (10 fused ops per field per pair instead of 16) and the modal
 // accumulation (sums / differences of the two fluxes: 18 ops per component per pair instead of 24).
 // ---------------------------------------------------------------------------------------------
-__constant__ double kPairSigns[4][3] = {  // (sy, sz, sy*sz) for (ty, tz) = (-,-), (+,-), (-,+), (+,+)
-    {-kA, -kA, kA * kA}, {kA, -kA, -kA * kA}, {-kA, kA, -kA * kA}, {kA, kA, kA * kA}};
+// (sy, sz, sy*sz) for (ty, tz) = (-,-), (+,-), (-,+), (+,+); one initializer for the device table and its host twin
+#define TATVA_PAIR_SIGNS \
+  { {-kA, -kA, kA * kA}, {kA, -kA, -kA * kA}, {-kA, kA, -kA * kA}, {kA, kA, kA * kA} }
+__constant__ double kPairSigns[4][3] = TATVA_PAIR_SIGNS;
+static const double kPairSignsHost[4][3] = TATVA_PAIR_SIGNS;  // for the host probe (tatva_probe_hex8_nh_modal)
 
-TATVA_D void ref_grad8_pair(const double (&h)[7], double sy, double sz, double (&gm)[3], double (&gp)[3]) {
+TATVA_HD void ref_grad8_pair(const double (&h)[7], double sy, double sz, double (&gm)[3], double (&gp)[3]) {
   const double s36 = fma(sz, h[6], h[3]);
   const double g0 = fma(sy, s36, fma(sz, h[5], h[0]));
   const double b1 = fma(sz, h[4], h[1]);
@@ -653,7 +656,7 @@ TATVA_D void ref_grad8_pair(const double (&h)[7], double sy, double sz, double (
 }
 
 // flux Q[i][d] (scaled by 512) of one Gauss point from J (8 dX/dxi, [d][c]), Fr, Gv ([i][d])
-TATVA_D void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const double (&Gv)[3][3], double mu_s,
+TATVA_HD void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const double (&Gv)[3][3], double mu_s,
                         double lm_s, double (&Q)[3][3]) {
   double Kc[3][3], detJ, Ac[3][3], detF;
   adjugate(J, Kc, detJ);
@@ -690,6 +693,25 @@ TATVA_D void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const
     for (int d = 0; d < 3; ++d)
       Q[i][d] = fma(B[d][0], Ac[0][i], fma(B[d][1], Ac[1][i], fma(B[d][2], Ac[2][i],
                 fma(Gv[i][0], M[0][d], fma(Gv[i][1], M[1][d], Gv[i][2] * M[2][d])))));
+}
+
+// Transposed reference gradient of a tx pair: the fluxes of the two Gauss points (xi = -a and +a) enter the 7 modal
+// residuals through their sums and differences (18 fused ops per component instead of 24).
+TATVA_HD void accumulate_pair(const double (&Qm)[3][3], const double (&Qp)[3][3], double sy, double sz, double syz,
+                              double (&R)[3][7]) {
+  const double asz = kA * sz, asy = kA * sy;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double S0 = Qp[i][0] + Qm[i][0], S1 = Qp[i][1] + Qm[i][1], S2 = Qp[i][2] + Qm[i][2];
+    const double D1 = Qp[i][1] - Qm[i][1], D2 = Qp[i][2] - Qm[i][2];
+    R[i][0] += S0;
+    R[i][1] += S1;
+    R[i][2] += S2;
+    R[i][3] = fma(sy, S0, fma(kA, D1, R[i][3]));
+    R[i][4] = fma(sz, S1, fma(sy, S2, R[i][4]));
+    R[i][5] = fma(sz, S0, fma(kA, D2, R[i][5]));
+    R[i][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, R[i][6])));
+  }
 }
 
 // LIFT: v and y are REDUCED vectors and `map` (n_nodes*3 int32) sends a full DOF to its reduced index, or -1 for a
@@ -885,19 +907,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
     double Qm[3][3], Qp[3][3];
     point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
     point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
-    const double asz = kA * sz, asy = kA * sy;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double S0 = Qp[i][0] + Qm[i][0], S1 = Qp[i][1] + Qm[i][1], S2 = Qp[i][2] + Qm[i][2];
-      const double D1 = Qp[i][1] - Qm[i][1], D2 = Qp[i][2] - Qm[i][2];
-      R[i][0] += S0;
-      R[i][1] += S1;
-      R[i][2] += S2;
-      R[i][3] = fma(sy, S0, fma(kA, D1, R[i][3]));
-      R[i][4] = fma(sz, S1, fma(sy, S2, R[i][4]));
-      R[i][5] = fma(sz, S0, fma(kA, D2, R[i][5]));
-      R[i][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, R[i][6])));
-    }
+    accumulate_pair(Qm, Qp, sy, sz, syz, R);
   }
   if constexpr (GROUPED) {
     // sector-grouped scatter: consecutive lanes add the 3 consecutive doubles of one node
@@ -1116,7 +1126,7 @@ __global__ void __launch_bounds__(kBlock, 3)
 //   nodal forces f_1..3 = columns of Q = W dP K (resp. W P K), f_0 = -(f_1 + f_2 + f_3).
 // About 290 FP64 instructions per element instead of ~450 for the generic template.
 // ---------------------------------------------------------------------------------------------
-TATVA_D void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3][3], double mu_s, double lm_s,
+TATVA_HD void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3][3], double mu_s, double lm_s,
                                  double (&Q)[3][3]) {
   double Kc[3][3], detJ, Ac[3][3], detF;
   adjugate(J, Kc, detJ);
@@ -1142,7 +1152,7 @@ TATVA_D void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3][
 
 // Energy in the same raw-modal / tx-pair form.  Gradients are carried at 8x their value: I1 and lnJ are ratios and do
 // not notice, the weight det J picks up 8^3, removed once at the end.
-TATVA_D double point_energy(const double (&J)[3][3], const double (&Fr)[3][3], double mu, double lmbda) {
+TATVA_HD double point_energy(const double (&J)[3][3], const double (&Fr)[3][3], double mu, double lmbda) {
   double Kc[3][3], detJ;
   adjugate(J, Kc, detJ);
   double M[3][3];
@@ -1300,19 +1310,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
     double Qm[3][3], Qp[3][3];
     point_flux_residual(Jm, Frm, mu_s, lm_s, Qm);
     point_flux_residual(Jp, Frp, mu_s, lm_s, Qp);
-    const double asz = kA * sz, asy = kA * sy;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double S0 = Qp[i][0] + Qm[i][0], S1 = Qp[i][1] + Qm[i][1], S2 = Qp[i][2] + Qm[i][2];
-      const double D1 = Qp[i][1] - Qm[i][1], D2 = Qp[i][2] - Qm[i][2];
-      R[i][0] += S0;
-      R[i][1] += S1;
-      R[i][2] += S2;
-      R[i][3] = fma(sy, S0, fma(kA, D1, R[i][3]));
-      R[i][4] = fma(sz, S1, fma(sy, S2, R[i][4]));
-      R[i][5] = fma(sz, S0, fma(kA, D2, R[i][5]));
-      R[i][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, R[i][6])));
-    }
+    accumulate_pair(Qm, Qp, sy, sz, syz, R);
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -1647,4 +1645,77 @@ int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const 
   return TATVA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Host probe: the per-element arithmetic of the pair kernels (k_hex8_nh_hvp_v3, k_hex8_nh_residual_v3,
+// k_hex8_nh_energy_v3) executed on the CPU with the SAME device functions compiled for the host (to_modal_raw,
+// ref_grad8_pair, point_flux, point_flux_residual, point_energy, accumulate_pair, from_modal_raw), so the kernels'
+// arithmetic can be checked against the oracle without a GPU.  Staging and gather / scatter are data movement and are
+// not part of it.  mode: 0 energy (out[0]), 1 residual, 2 HVP (out[8][3], node-major like the nodal vectors).
+// ---------------------------------------------------------------------------------------------
+namespace {
+void probe_hex8_pairs(int mode, const double* X, const double* u, const double* v, double mu, double lmbda, double* out) {
+  double hX[3][7], hx[3][7], hv[3][7];
+  for (int c = 0; c < 3; ++c) {
+    double fX[8], fu[8], fv[8];
+    for (int n = 0; n < 8; ++n) {
+      fX[n] = X[n * 3 + c];
+      fu[n] = u[n * 3 + c];
+      fv[n] = v ? v[n * 3 + c] : 0.0;
+    }
+    to_modal_raw(fX, hX[c]);
+    to_modal_raw(fu, hx[c]);
+    to_modal_raw(fv, hv[c]);
+    for (int k = 0; k < 7; ++k) hx[c][k] += hX[c][k];
+  }
+  double R[3][7] = {};
+  double energy = 0.0;
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSignsHost[pq][0], sz = kPairSignsHost[pq][1], syz = kPairSignsHost[pq][2];
+    double Jm[3][3], Jp[3][3], Frm[3][3], Frp[3][3], Gvm[3][3], Gvp[3][3];
+    for (int c = 0; c < 3; ++c) {
+      double gm[3], gp[3];
+      ref_grad8_pair(hX[c], sy, sz, gm, gp);
+      for (int d = 0; d < 3; ++d) {
+        Jm[d][c] = gm[d];
+        Jp[d][c] = gp[d];
+      }
+    }
+    for (int i = 0; i < 3; ++i) {
+      ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+      ref_grad8_pair(hv[i], sy, sz, Gvm[i], Gvp[i]);
+    }
+    if (mode == 0) {
+      energy += point_energy(Jm, Frm, mu, lmbda) + point_energy(Jp, Frp, mu, lmbda);
+      continue;
+    }
+    double Qm[3][3], Qp[3][3];
+    if (mode == 2) {
+      point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
+      point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
+    } else {
+      point_flux_residual(Jm, Frm, mu_s, lm_s, Qm);
+      point_flux_residual(Jp, Frp, mu_s, lm_s, Qp);
+    }
+    accumulate_pair(Qm, Qp, sy, sz, syz, R);
+  }
+  if (mode == 0) {
+    out[0] = energy * (1.0 / 512.0);
+    return;
+  }
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal_raw(R[i], f);
+    for (int n = 0; n < 8; ++n) out[n * 3 + i] = f[n];
+  }
+}
+}  // namespace
+
 }  // namespace tatva
+
+extern "C" int tatva_probe_hex8_nh_modal(int mode, const double* X, const double* u, const double* v, double mu, double lmbda,
+                                         double* out) {
+  if (!X || !u || !out || mode < 0 || mode > 2 || (mode == 2 && !v)) return TATVA_E_INVALID;
+  tatva::probe_hex8_pairs(mode, X, u, v, mu, lmbda, out);
+  return TATVA_OK;
+}
