@@ -307,11 +307,15 @@ int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int n
  *   tatva_probe_element:        generic element body (k_fused / k_hessian_diag): X (npe, dim), u, v (npe, dpn);
  *                               mode 0 energy -> out[0]; 1 residual, 2 HVP, 3 Hessian diagonal -> out (npe, dpn)
  *   tatva_probe_hex8_nh_modal:  the pair kernels of the Hex8 x neo-Hookean path (HVP v3, residual v3, energy v3):
- *                               X, u, v (8, 3); mode 0 energy, 1 residual, 2 HVP -> out[0] or out (8, 3)          */
+ *                               X, u, v (8, 3); mode 0 energy, 1 residual, 2 HVP -> out[0] or out (8, 3)
+ *   tatva_probe_tet4_nh_ref:    the reference-space Tet4 x neo-Hookean kernels: X, u, v (4, 3); mode 1 residual,
+ *                               2 HVP -> out (4, 3)                                                               */
 int tatva_probe_element(int element, int material, const double* params, int n_params, int mode,
                         const double* X, const double* u, const double* v, double* out);
 int tatva_probe_hex8_nh_modal(int mode, const double* X, const double* u, const double* v, double mu,
                               double lmbda, double* out);
+int tatva_probe_tet4_nh_ref(int mode, const double* X, const double* u, const double* v, double mu,
+                            double lmbda, double* out);
 
 /* ---- measurement helper: sustained FP64 FMA rate of the device (DFMA microbenchmark) ---- */
 int tatva_fp64_peak_tflops(double* tflops, tatva_stream_t stream);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "tatva_host_build_point_grid": (C.c_int, [c_f64p, C.c_int64, c_i32p, C.c_int64, C.c_int, C.c_int, C.c_int, c_f64p, c_f64p, c_i32p, c_i32p]),
     "tatva_probe_element": (C.c_int, [C.c_int, C.c_int, c_f64p, C.c_int, C.c_int, c_f64p, c_f64p, c_f64p, c_f64p]),
     "tatva_probe_hex8_nh_modal": (C.c_int, [C.c_int, c_f64p, c_f64p, c_f64p, C.c_double, C.c_double, c_f64p]),
+    "tatva_probe_tet4_nh_ref": (C.c_int, [C.c_int, c_f64p, c_f64p, c_f64p, C.c_double, C.c_double, c_f64p]),
     "tatva_fp64_peak_tflops": (C.c_int, [c_f64p, vp]),
 }
 

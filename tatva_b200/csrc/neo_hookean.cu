@@ -1709,9 +1709,34 @@ void probe_hex8_pairs(int mode, const double* X, const double* u, const double* 
     for (int n = 0; n < 8; ++n) out[n * 3 + i] = f[n];
   }
 }
+// the body of k_tet4_nh_ref / k_tet4_nh_pipe / k_tet4_nh_tiled for one element (mode 1 residual, 2 HVP)
+void probe_tet4_ref(int mode, const double* X, const double* u, const double* v, double mu, double lmbda, double* out) {
+  double J[3][3], Fr[3][3], Gv[3][3], Q[3][3];
+  for (int d = 0; d < 3; ++d)
+    for (int c = 0; c < 3; ++c) {
+      J[d][c] = X[(d + 1) * 3 + c] - X[c];
+      Fr[c][d] = J[d][c] + (u[(d + 1) * 3 + c] - u[c]);
+      Gv[c][d] = v ? v[(d + 1) * 3 + c] - v[c] : 0.0;
+    }
+  if (mode == 2) point_flux(J, Fr, Gv, mu * (1.0 / 6.0), lmbda * (1.0 / 6.0), Q);
+  else point_flux_residual(J, Fr, mu * (1.0 / 6.0), lmbda * (1.0 / 6.0), Q);
+  for (int i = 0; i < 3; ++i) {
+    out[3 + i] = Q[i][0];
+    out[6 + i] = Q[i][1];
+    out[9 + i] = Q[i][2];
+    out[i] = -(Q[i][0] + Q[i][1] + Q[i][2]);
+  }
+}
 }  // namespace
 
 }  // namespace tatva
+
+extern "C" int tatva_probe_tet4_nh_ref(int mode, const double* X, const double* u, const double* v, double mu, double lmbda,
+                                       double* out) {
+  if (!X || !u || !out || mode < 1 || mode > 2 || (mode == 2 && !v)) return TATVA_E_INVALID;
+  tatva::probe_tet4_ref(mode, X, u, v, mu, lmbda, out);
+  return TATVA_OK;
+}
 
 extern "C" int tatva_probe_hex8_nh_modal(int mode, const double* X, const double* u, const double* v, double mu, double lmbda,
                                          double* out) {

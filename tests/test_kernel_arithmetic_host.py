@@ -113,6 +113,26 @@ def test_hex8_pair_kernels_arithmetic_matches_the_oracle():
     np.testing.assert_allclose(hv, h_ref, rtol=1e-10, atol=1e-13 * np.abs(h_ref).max())
 
 
+def test_tet4_reference_space_kernels_arithmetic_matches_the_oracle():
+    """The default Tet4 x neo-Hookean kernels (one point, J = edge vectors, f_0 = -(f_1 + f_2 + f_3))."""
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    c, el = orc.mesh_box_tet((1, 1, 1), (3, 3, 3))
+    c = c + 0.02 * rng.uniform(-1, 1, c.shape)
+    u, v = 0.02 * rng.normal(size=c.shape), rng.normal(size=c.shape)
+    omat = orc.NeoHookean(500.0, 1000.0)
+    res, hv, buf = np.zeros_like(c), np.zeros_like(c), np.zeros(12)
+    for e in el:
+        X, ue, ve = (np.ascontiguousarray(a[e]) for a in (c, u, v))
+        assert L.tatva_probe_tet4_nh_ref(1, f64(X), f64(ue), None, 500.0, 1000.0, f64(buf)) == 0
+        np.add.at(res, e, buf.reshape(4, 3))
+        assert L.tatva_probe_tet4_nh_ref(2, f64(X), f64(ue), f64(ve), 500.0, 1000.0, f64(buf)) == 0
+        np.add.at(hv, e, buf.reshape(4, 3))
+    r_ref, h_ref = orc.residual("tet4", omat, c, el, u), orc.hvp("tet4", omat, c, el, u, v)
+    np.testing.assert_allclose(res, r_ref, rtol=1e-10, atol=1e-13 * np.abs(r_ref).max())
+    np.testing.assert_allclose(hv, h_ref, rtol=1e-10, atol=1e-13 * np.abs(h_ref).max())
+
+
 def test_probes_reject_bad_arguments():
     L = _lib.lib()
     z = np.zeros(24)
