@@ -230,8 +230,7 @@ def main():
 
     import torch
 
-    import tatva_b200
-    from tatva_b200 import element, materials
+    from tatva_b200 import materials
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -17,7 +17,7 @@ host logic: `comm` is a torch.distributed process group (see tatva_b200.mpi).
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Hashable
+from typing import Callable, Hashable
 from uuid import uuid4
 
 import numpy as np

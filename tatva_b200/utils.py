@@ -10,7 +10,6 @@ from __future__ import annotations
 from functools import wraps
 from typing import Callable
 
-import numpy as np
 import torch
 
 from .lifter import create_g2l  # noqa: F401  (tatva/utils.py:265-280)
