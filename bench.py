@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: matrix-free Hex8 neo-Hookean HVP, DOFs/s (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n CELLS] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n CELLS] [--impl ours|reference] [--scaling weak|strong]
 
 A "step" is one application y = H(u) v of the hot path over the whole mesh (config 3: Hex8 128^3,
 6 440 067 DOFs per GPU).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
@@ -140,67 +140,91 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable"]}
 
 
-def cpu_port_baseline(n_sample, threads=None):
-    """Time the oracle (CPU restatement of the reference's arithmetic) on a bounded sample."""
+def _cpu_hvp_fn(n, threads=None):
+    """(callable running ONE CPU HVP over the whole Hex8 n^3 mesh, n_dofs, cores, description).  The C/OpenMP oracle
+    (oracle/tatva_oracle.c) on all host cores; torchrun exports OMP_NUM_THREADS=1 to its workers, so the thread count
+    is set explicitly."""
     from oracle import tatva_oracle as orc
 
-    c, el, u, v = synthetic_inputs(n_sample)
-    mat = orc.NeoHookean(MU, LMBDA)
+    c, el, u, v = synthetic_inputs(n)
     try:
         from oracle import c_oracle
 
+        c_oracle.set_num_threads(threads or os.cpu_count() or 1)
         fn = lambda: c_oracle.hvp("hex8", (MU, LMBDA), c, el, u, v)  # noqa: E731
         cores = c_oracle.num_threads()
-        kind_note = "C/OpenMP port (oracle/tatva_oracle.c)"
-    except Exception:
+        note = "C/OpenMP port (oracle/tatva_oracle.c)"
+    except Exception:  # noqa: BLE001
+        mat = orc.NeoHookean(MU, LMBDA)
         fn = lambda: orc.hvp("hex8", mat, c, el, u, v)  # noqa: E731
         cores = 1
-        kind_note = "NumPy port (oracle/tatva_oracle.py)"
+        note = "NumPy port (oracle/tatva_oracle.py)"
+    return fn, 3 * c.shape[0], cores, note
+
+
+def cpu_port_baseline(n, budget_s=12.0):
+    """cpu_baseline of our own arm: the oracle timed on the host cores over the SAME mesh (Hex8 n^3), as many whole-mesh
+    repetitions as fit in ~`budget_s` seconds (at least 3)."""
+    fn, n_dofs, cores, note = _cpu_hvp_fn(n)
     fn()
     reps, t_total = 0, 0.0
-    while reps < 3 or (t_total < 10.0 and reps < 50):
+    while reps < 3 or (t_total < budget_s and reps < 50):
         t0 = time.perf_counter()
         fn()
         t_total += time.perf_counter() - t0
         reps += 1
     t = t_total / reps
     return {
-        "value": 3 * c.shape[0] / t,
+        "value": n_dofs / t,
         "unit": "DOF/s",
         "cores": cores,
         "kind": "port",
-        "sample": f"Hex8 {n_sample}^3 ({3 * c.shape[0]} DOFs), mean of {reps} reps, {kind_note}; os.cpu_count()={os.cpu_count()}",
+        "sample": f"Hex8 {n}^3 ({n_dofs} DOFs, the whole config-3 mesh), mean of {reps} reps, {note}; os.cpu_count()={os.cpu_count()}",
         "ms_per_step": t * 1e3,
     }
 
 
 def run_reference(args):
-    """Reference arm: the reference's JAX path cannot run (no jax in the image); the CPU port of its
-    arithmetic is timed on the host cores instead, on a bounded sample of the same workload."""
+    """Reference arm.  The reference's JAX path cannot run (jax is not installable in this image), so the
+    CPU port of its arithmetic is timed on ALL host cores, on the same workload as our arm (the Hex8 `--n`^3 mesh,
+    128^3 by default; `--scaling strong`: the fixed `--strong-n`^3 mesh), `--warmup` untimed and `--steps` timed
+    whole-mesh applications.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = args.ref_n
-    base = cpu_port_baseline(n_sample)
-    ms = base.pop("ms_per_step")
+    n = args.strong_n if args.scaling == "strong" else args.n
+    fn, n_dofs, cores, note = _cpu_hvp_fn(n)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        fn()
+        done += 1
+        if time.perf_counter() - t0 > args.ref_budget_s:  # safety valve; `steps` below reports what was timed
+            break
+    t = (time.perf_counter() - t0) / done
+    base = {"value": n_dofs / t, "unit": "DOF/s", "cores": cores, "kind": "port",
+            "sample": f"Hex8 {n}^3 ({n_dofs} DOFs): the whole mesh of one GPU's workload, every step; {note}; os.cpu_count()={os.cpu_count()}"}
     line = {
         "impl": "reference",
         "metric": METRIC,
         "value": base["value"],
         "unit": "DOF/s",
         "n_gpus": args.gpus,
-        "steps": args.steps,
+        "steps": done,
         "warmup": args.warmup,
-        "ms_per_step": ms,
+        "ms_per_step": t * 1e3,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"Hex8 {args.n}^3 per GPU, neo-Hookean (mu=500, lambda=1000) matrix-free HVP",
-            "sample": f"CPU port of the reference arithmetic on a {n_sample}^3 block of the same mesh family (bounded sample); "
-                      "the reference's JAX path cannot run: jax is not installable in this image",
+            "workload": f"Hex8 {n}^3, neo-Hookean (mu=500, lambda=1000) matrix-free HVP",
+            "same_config": True,
+            "note": "CPU port of the reference arithmetic (the reference's JAX path cannot run: jax is not installable in this image); "
+                    "one host, all cores; at N > 1 GPUs the CPU arm still processes one GPU's mesh per step (there is one host)",
         },
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -209,16 +233,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _timed_steps(step, steps, barrier, torch):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--n", type=int, default=128, help="cells per side of the per-GPU Hex8 block")
+    ap.add_argument("--n", type=int, default=128, help="cells per side of the per-GPU Hex8 block (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-n", type=int, default=48, help="cells per side of the CPU sample")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: a FIXED --strong-n^3 mesh cut into 1/2/4/8 blocks (config 4)")
+    ap.add_argument("--strong-n", type=int, default=256, help="cells per side of the fixed global mesh for strong scaling")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-clock cap of the reference arm's timed loop")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` (configs 1, 2, 5) and `strong_scaling` blocks")
     ap.add_argument("--halo", default=os.environ.get("TATVA_HALO", "peer"), choices=["nccl", "peer"], help="multi-GPU halo transport")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -245,16 +283,35 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    from bench_dist import DistributedHex8Problem  # multi-GPU decomposition + halo exchange
+    from bench_dist import GRID, DistributedHex8Problem, distributed_parity, numa_pin, secondary_c5, secondary_single_gpu
 
-    prob = DistributedHex8Problem(args.n, rank, world, dev, materials.NeoHookean(MU, LMBDA), variant=args.variant, halo=args.halo)
-    n_dofs_global = prob.n_dofs_global
-    step = prob.step
+    numa = numa_pin(local_rank)  # before any pinned host allocation
+    mat = materials.NeoHookean(MU, LMBDA)
+    grid = GRID[world]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def strong_block():
+        N = args.strong_n
+        return (N // grid[0], N // grid[1], N // grid[2])
+
+    parity = None
+    if world > 1:  # multi-GPU correctness as part of the run: distributed == single GPU on the global mesh
+        parity = distributed_parity(12, rank, world, dev, mat, halo=args.halo)
+        if parity["hvp_rel_err"] > 1e-12 or parity["residual_rel_err"] > 1e-12:
+            raise SystemExit(f"multi-GPU parity check failed: {parity}")
+
+    if args.scaling == "strong":
+        prob = DistributedHex8Problem(strong_block(), rank, world, dev, mat, variant=args.variant, halo=args.halo, hashed_mesh=True)
+        workload = f"Hex8 {args.strong_n}^3 FIXED global mesh (config 4), neo-Hookean (mu=500, lambda=1000) matrix-free HVP, {prob.partition_desc}"
+    else:
+        prob = DistributedHex8Problem(args.n, rank, world, dev, mat, variant=args.variant, halo=args.halo)
+        workload = f"Hex8 {args.n}^3 per GPU, neo-Hookean (mu=500, lambda=1000) matrix-free HVP, {prob.partition_desc}"
+    n_dofs_global = prob.n_dofs_global
+    step = prob.step
 
     for _ in range(args.warmup):
         step()
@@ -262,25 +319,19 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = _timed_steps(step, args.steps, barrier, torch)
     # kernel-only duration of the element kernel (per launch), events on the launching stream
     k_ms = prob.time_kernel_only(args.steps)
     # end-to-end through the public API with host buffers
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         prob.step_e2e()
     prob.e2e_finish()
+    n_e2e = max(3, min(args.steps, 20))
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    n_e2e = max(3, min(args.steps, 20))
     for _ in range(n_e2e):
         prob.step_e2e()
     prob.e2e_finish()
@@ -295,26 +346,60 @@ def main():
     ms_total, ms_e2e, k_ms = (float(x) for x in t.tolist())
     ms_step = ms_total / args.steps
     ms_e2e_step = ms_e2e / n_e2e
+    h2d, d2h = prob.h2d_bytes, prob.d2h_bytes
+    local_nodes, local_elems, launches = prob.local_nodes, prob.local_elems, prob.launches_per_step
+    fp64_peak = prob.fp64_peak_tflops() if rank == 0 else None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # ---- extra blocks: strong scaling of config 4 and the secondary configurations ---------------------------------
+    strong = secondary = None
+    if not args.no_secondary:
+        del prob, step
+        torch.cuda.empty_cache()
+        if args.scaling == "weak":
+            sp = DistributedHex8Problem(strong_block(), rank, world, dev, mat, variant=args.variant, halo=args.halo, hashed_mesh=True)
+            for _ in range(5):
+                sp.step()
+            k_strong = 20
+            ms_s = torch.tensor([_timed_steps(sp.step, k_strong, barrier, torch)], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+            ms_s = float(ms_s) / k_strong
+            strong = {"workload": f"Hex8 {args.strong_n}^3 FIXED global mesh (config 4): {sp.partition_desc}", "scaling": "strong", "n_gpus": world,
+                      "dofs_global": sp.n_dofs_global, "steps": k_strong, "ms_per_step": ms_s, "value": sp.n_dofs_global / (ms_s * 1e-3), "unit": "DOF/s"}
+            del sp
+            torch.cuda.empty_cache()
+        secondary = secondary_c5(rank, world, dev, args.halo)
+        if rank == 0:
+            secondary.update(secondary_single_gpu(dev, hbm_peak))
+        barrier()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        traffic = None
-        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (1-GPU, 128^3)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_hvp_traffic.json")))
-            if args.n == 128:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        except (OSError, KeyError, ValueError):
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = None, None
+        for name in ("r02_hvp_traffic.json", "r01_hvp_traffic.json"):  # DRAM bytes per launch from the committed ncu --set full capture (1 GPU, 128^3)
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+                if local_elems == 128**3:
+                    traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                    traffic_src = f"profiles/{name} (ncu --set full of the same kernel and size; not re-measured in this run)"
+                break
+            except (OSError, KeyError, ValueError):
+                continue
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        alg_bytes = algorithmic_bytes(prob.local_nodes, prob.local_elems)
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        fp64_peak = prob.fp64_peak_tflops()
-        fp64_ach = FLOP_PER_ELEMENT * prob.local_elems / (k_ms * 1e-3) / 1e12
+        alg_bytes = algorithmic_bytes(local_nodes, local_elems)
+        hbm_ach = alg_bytes / (k_ms * 1e-3) / 1e9
+        flops = FLOP_PER_ELEMENT * local_elems
+        fp64_ach = flops / (k_ms * 1e-3) / 1e12
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        fp64_spec = 148 * 64 * 2 * sm_max * 1e6 / 1e12  # 148 SMs x 64 DFMA/clk x 2 flop x clock
+        fp64_frac = fp64_ach / fp64_spec
+        hbm_frac = hbm_ach / hbm_peak
         line = {
             "metric": METRIC,
             "value": n_dofs_global / (ms_step * 1e-3),
@@ -324,48 +409,62 @@ def main():
             "warmup": args.warmup,
             "ms_per_step": ms_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": f"Hex8 {args.n}^3 per GPU, neo-Hookean (mu=500, lambda=1000) matrix-free HVP, {prob.partition_desc}",
+                "workload": workload,
                 "dofs_global": n_dofs_global,
-                "dofs_per_gpu": 3 * prob.local_nodes,
+                "dofs_per_gpu": 3 * local_nodes,
                 "l2_policy": "inputs larger than L2 (273 MB working set per GPU vs 126 MB L2)",
-                "parallelism": prob.partition_desc,
+                "parallelism": workload.split(", ", 2)[-1],
             },
+            # achieved = max(HBM term, FP64 term); the binding roof of this operator is FP64 (AI ~ 61 flop/B)
             "roofline": {
-                "bound": "hbm",
-                "achieved": achieved,
-                "peak": hbm_peak,
-                "unit": "GB/s",
-                "frac": achieved / hbm_peak,
+                "bound": "fp64" if fp64_frac >= hbm_frac else "hbm",
+                "achieved": fp64_ach if fp64_frac >= hbm_frac else hbm_ach,
+                "peak": fp64_spec if fp64_frac >= hbm_frac else hbm_peak,
+                "unit": "TFLOP/s" if fp64_frac >= hbm_frac else "GB/s",
+                "frac": max(fp64_frac, hbm_frac),
                 "traffic": traffic,
-                "peak_source": peak_src,
+                "traffic_source": traffic_src,
                 "kernel": "k_hex8_nh_hvp",
                 "kernel_ms": k_ms,
                 "algorithmic_bytes": alg_bytes,
-                "note": "binding roof is FP64 (AI ~ 61 flop/B), see fp64 block",
-                "fp64": {
-                    "achieved_tflops_nominal": fp64_ach,
-                    "peak_tflops_measured_dfma": fp64_peak,
-                    "frac": fp64_ach / fp64_peak if fp64_peak else None,
-                    "flop_per_element_nominal": FLOP_PER_ELEMENT,
-                },
+                "algorithmic_flops": flops,
+                "flop_per_element_nominal": FLOP_PER_ELEMENT,
+                "peak_source": f"FP64: spec-derived 148 SM x 64 DFMA/clk x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP64 entry); HBM: {peak_src}",
+                "fp64_peak_tflops_dfma_microbenchmark_this_run": fp64_peak,
+                "fp64_frac_of_microbenchmark": fp64_ach / fp64_peak if fp64_peak else None,
+                "hbm_achieved_gbs": hbm_ach,
+                "hbm_peak_gbs": hbm_peak,
+                "hbm_frac": hbm_frac,
+                "note": "flops are the NOMINAL textbook count of SURVEY §8(d) (7944 per element); the kernel executes ~2500 FP64 instructions per element (modal form), so frac measures time against the textbook-work roof, not pipe occupancy (ncu: profiles/)",
             },
             "e2e": {
                 "value": n_dofs_global / (ms_e2e_step * 1e-3),
                 "unit": "DOF/s",
                 "ms_per_step": ms_e2e_step,
-                "h2d_bytes_per_step": prob.h2d_bytes,
-                "d2h_bytes_per_step": prob.d2h_bytes,
+                "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "h2d_gbs_per_gpu": h2d / (ms_e2e_step * 1e-3) / 1e9,
+                "d2h_gbs_per_gpu": d2h / (ms_e2e_step * 1e-3) / 1e9,
+                "host_numa": numa,
+                "note": "PCIe-bound: u and v up, y down every step through pinned buffers, three streams, two buffer sets",
             },
-            "gpu_launches": prob.launches_per_step * args.steps,
+            "gpu_launches": launches * args.steps,
             "clocks": clocks,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if secondary is not None:
+            line["secondary"] = secondary
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port_baseline(args.ref_n)
+            n_cpu = args.n if args.scaling == "weak" else args.strong_n
+            line["cpu_baseline"] = cpu_port_baseline(n_cpu)
             line["cpu_baseline"].pop("ms_per_step", None)
         print(json.dumps(line))
     if dist is not None:

@@ -25,12 +25,65 @@ def smooth_u(c):
     )
 
 
+def numa_pin(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE the pinned host buffers are allocated
+    (first touch places them on that node): with one rank per GPU the end-to-end leg otherwise funnels every rank's
+    H2D / D2H traffic through whichever socket the launcher started the process on.  Returns a small report."""
+    import os
+
+    info = {"numa_node": None, "cpus": None}
+    try:
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id.lower()
+    except Exception:  # noqa: BLE001
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device_index]) if vis else device_index
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+            bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        except Exception:  # noqa: BLE001
+            return info
+    if len(bdf.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs uses 4
+        bdf = bdf[4:]
+    try:
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["numa_node"] = node
+        if node >= 0:
+            cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            cpus = set()
+            for part in cpulist.split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus"] = len(cpus)
+    except (OSError, ValueError):
+        pass
+    return info
+
+
 class DistributedHex8Problem:
-    def __init__(self, n, rank, world, device, material, variant=0, overlap=True, halo="nccl"):
+    def __init__(self, n, rank, world, device, material, variant=0, overlap=True, halo="nccl", grid=None, hashed_mesh=False):
+        """`n`: cells per side of this rank's block (int) or a (nx, ny, nz) triple; `grid`: blocks per direction
+        (default GRID[world]).  `hashed_mesh` builds the 1-GPU mesh with the block builder too (strong scaling: the
+        same mesh family at every N)."""
         from bench import synthetic_inputs
 
         self.rank, self.world, self.device, self.material = rank, world, device, material
-        if world == 1:
+        if world == 1 and hashed_mesh:
+            mesh, _ = structured_hex_block(n, (1, 1, 1), 0)
+            c, el = mesh.coords, mesh.elements
+            u, v = smooth_u(c), np.random.default_rng(1).normal(size=c.shape)
+            self.op = tatva_b200.Operator(mesh, element.Hexahedron8(), device=device)
+            self.pop = None
+            self.n_dofs_global = 3 * c.shape[0]
+            self.partition_desc = "1 GPU, whole mesh"
+            n_owned = u.size
+            self.launches_per_step = 1
+        elif world == 1:
             c, el, u, v = synthetic_inputs(n, rank)
             self.op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8(), device=device)
             self.pop = None
@@ -39,7 +92,7 @@ class DistributedHex8Problem:
             n_owned = u.size
             self.launches_per_step = 1
         else:
-            grid = GRID[world]
+            grid = grid or GRID[world]
             mesh, info = structured_hex_block(n, grid, rank)
             c, el = mesh.coords, mesh.elements
             self.pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=overlap, halo=halo)
@@ -64,7 +117,8 @@ class DistributedHex8Problem:
             v = np.random.default_rng(1 + rank).normal(size=c.shape)
             self.n_dofs_global = self.pop.n_global
             how = "peer-memory halo over NVLink (own kernels + device barrier)" if halo == "peer" else "NCCL halo exchange"
-            self.partition_desc = f"{world} GPUs, {grid[0]}x{grid[1]}x{grid[2]} blocks of {n}^3, {how} ({'overlapped' if overlap else 'serial'})"
+            shape = f"{n}^3" if np.isscalar(n) else "x".join(str(a) for a in n)
+            self.partition_desc = f"{world} GPUs, {grid[0]}x{grid[1]}x{grid[2]} blocks of {shape}, {how} ({'overlapped' if overlap else 'serial'})"
             n_owned = self.pop.n_owned
             self.launches_per_step = 6  # pack, unpack-set, boundary + interior element kernels, pack, unpack-add
         if variant:
@@ -157,3 +211,165 @@ class DistributedHex8Problem:
         out = C.c_double()
         _lib.check(_lib.lib().tatva_fp64_peak_tflops(C.byref(out), torch.cuda.current_stream().cuda_stream))
         return out.value
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Multi-GPU correctness inside the bench run: distributed == single GPU on the global mesh (small n)
+# ------------------------------------------------------------------------------------------------------------------
+def distributed_parity(n, rank, world, device, material, halo="peer", grid=None):
+    """The partitioned HVP / residual of a (gx n) x (gy n) x (gz n) box over `world` GPUs against the SAME box on this
+    rank's GPU alone, compared on the owned rows in the plan's numbering (max-abs / max).  Every rank calls it; the
+    returned errors are the maxima over ranks.  Also used by tests/test_gpu_multi.py."""
+    import torch.distributed as dist
+
+    from tatva_b200.distributed import _hash_uniform
+    from tatva_b200.mesh import Mesh
+
+    grid = grid or GRID[world]
+    mesh, info = structured_hex_block(n, grid, rank)
+    pop = PartitionedOperator(mesh, info, element.Hexahedron8(), material, device=device, overlap=True, halo=halo)
+    l2g = info.nodes_local_to_global
+    shape = (grid[0] * n, grid[1] * n, grid[2] * n)
+    gm = Mesh.box_hex(shape)
+    gc = gm.coords + 0.1 * (1.0 / max(shape)) * _hash_uniform(np.arange(gm.coords.shape[0]), 0)
+    assert np.abs(gc[l2g] - mesh.coords).max() < 1e-14
+    gop = tatva_b200.Operator(Mesh(coords=gc, elements=gm.elements), element.Hexahedron8(), device=device)
+    gu, gv = smooth_u(gc), np.random.default_rng(7).normal(size=gc.shape)
+    ref_hvp = gop.hvp(material)(gu, gv).cpu().numpy()
+    ref_res = gop.residual(material)(gu).cpu().numpy()
+    mk = pop.new_symmetric_vector if pop.halo == "peer" else pop.new_local_vector
+    u_l, v_l, y_l, r_l = mk(), mk(), mk(), mk()
+    u_l.copy_(torch.as_tensor(gu[l2g].ravel(), device=device))
+    v_l.copy_(torch.as_tensor(gv[l2g].ravel(), device=device))
+    v_l[pop.n_owned:] = 0.0  # the ghosts must come from the exchange
+    y = pop.hvp(u_l, v_l, y_l)
+    torch.cuda.synchronize()
+    no = info.n_owned_nodes
+    e_h = np.abs(y[: pop.n_owned].cpu().numpy().reshape(-1, 3) - ref_hvp[l2g[:no]]).max() / np.abs(ref_hvp).max()
+    u2 = mk()
+    u2.copy_(u_l)
+    u2[pop.n_owned:] = 0.0
+    r = pop.residual(u2, r_l)
+    torch.cuda.synchronize()
+    e_r = np.abs(r[: pop.n_owned].cpu().numpy().reshape(-1, 3) - ref_res[l2g[:no]]).max() / np.abs(ref_res).max()
+    t = torch.tensor([e_h, e_r], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {
+        "hvp_rel_err": float(t[0]), "residual_rel_err": float(t[1]), "tolerance": 1e-12,
+        "what": f"distributed ({pop.halo} halo, overlapped) vs single-GPU on the global Hex8 {shape[0]}x{shape[1]}x{shape[2]} box, owned rows, max over ranks",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Secondary configurations (BASELINE.json configs 1, 2, 5) for the bench line's `secondary` block
+# ------------------------------------------------------------------------------------------------------------------
+def _timeit(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def _smooth(c):
+    t = 2 * np.pi
+    if c.shape[1] == 2:
+        return 0.05 * np.stack([np.sin(t * c[:, 0]) * np.cos(t * c[:, 1]), np.sin(t * c[:, 1]) * np.cos(t * c[:, 0])], -1)
+    return smooth_u(c)
+
+
+def secondary_single_gpu(device, hbm_peak_gbs):
+    """Configs 1 and 2 on ONE GPU (rank 0): device-timed kernels, algorithmic bytes / time against the HBM peak."""
+    from tatva_b200 import materials, sparse
+    from tatva_b200.mesh import Mesh
+
+    out = {}
+
+    def rec(name, ms, alg_bytes, units, unit, **extra):
+        out[name] = dict(ms=round(ms, 5), value=units / (ms * 1e-3), unit=unit + "/s", algorithmic_bytes=alg_bytes,
+                         hbm_gbs=round(alg_bytes / ms / 1e6, 1), hbm_frac=round(alg_bytes / ms / 1e6 / hbm_peak_gbs, 4), **extra)
+
+    with torch.cuda.device(device):
+        # config 1: Tri3 256^2, plane-strain linear elasticity (E = 1, nu = 0.3): residual + matrix-free HVP
+        m = Mesh.unit_square(256, 256)
+        op = tatva_b200.Operator(m, element.Tri3(), device=device)
+        mat = materials.LinearElastic.from_youngs_poisson_2d(1.0, 0.3)
+        N, E = m.coords.shape[0], m.elements.shape[0]
+        u = torch.as_tensor(_smooth(np.asarray(m.coords)), device=device)
+        v = torch.as_tensor(np.random.default_rng(1).normal(size=m.coords.shape), device=device)
+        y = torch.empty_like(u)
+        note = "4.7 MB working set: L2-resident, launch-latency sized"
+        rec("c1_tri3_le_hvp", _timeit(lambda: op._raw_hvp(mat, u, v, out=y), reps=200, warm=10), 8 * (2 * 2 * N + 2 * N) + 12 * E, 2 * N, "DOF", note=note)
+        rec("c1_tri3_le_residual", _timeit(lambda: op._raw_residual(mat, u), reps=200, warm=10), 8 * (2 * 2 * N + 2 * N) + 12 * E, 2 * N, "DOF", note=note)
+        del op
+        # config 2: Tet4 box n = 55 (998 250 tets), neo-Hookean: residual + CSR assembly into the fixed pattern
+        m = Mesh.box_tet((1.0, 1.0, 1.0), (55, 55, 55))
+        c = m.coords + np.array([0.5, 0.5, 0.0]) + 0.1 / 55 * np.random.default_rng(0).uniform(-1, 1, m.coords.shape)
+        m = Mesh(coords=c, elements=m.elements)
+        op = tatva_b200.Operator(m, element.Tetrahedron4(), device=device)
+        mat = materials.NeoHookean(500.0, 1000.0)
+        N, E = c.shape[0], m.elements.shape[0]
+        u = torch.as_tensor(smooth_u(c), device=device)
+        v = torch.as_tensor(np.random.default_rng(1).normal(size=c.shape), device=device)
+        y = torch.empty_like(u)
+        rec("c2_tet4_nh_residual", _timeit(lambda: op._raw_residual(mat, u)), 8 * (6 * N + 3 * N) + 16 * E, 3 * N, "DOF", fp64_floor_us=17.0)
+        rec("c2_tet4_nh_hvp", _timeit(lambda: op._raw_hvp(mat, u, v, out=y)), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", fp64_floor_us=17.0)
+        pat = sparse.pattern_from_mesh(m, 3)
+        cm = sparse.ColoredMatrix.from_csr(pat)
+        asm = sparse.assembler(op, mat, cm)
+        data = torch.empty(asm.nnz, dtype=torch.float64, device=device)
+        rec("c2_tet4_nh_csr_assemble", _timeit(lambda: asm(u, out=data), reps=10), 8 * asm.nnz + 64 * E + 8 * 6 * N + 16 * E, asm.nnz, "nnz", nnz=asm.nnz, n_colors=int(np.asarray(cm.colors).max()) + 1)
+        del asm, data, op
+    return out
+
+
+def secondary_c5(rank, world, device, halo, n=55):
+    """Config 5: compound (u, phi) Tet4 phase-field operator, one n^3-cell block (6 n^3 tets, 4 DOFs per node) per GPU
+    (8 GPUs = the n = 110 box of SURVEY §8), coupled residual + HVP with the halo exchange.  All ranks call it."""
+    import torch.distributed as dist
+
+    from tatva_b200 import materials
+    from tatva_b200.distributed import structured_tet_block
+
+    mesh, info = structured_tet_block(n, GRID[world], rank)
+    mat = materials.NeoHookeanPhaseField(500.0, 1000.0, 2.7, 0.05, 1e-6)
+    pop = PartitionedOperator(mesh, info, element.Tetrahedron4(), mat, device=device, overlap=True, halo=halo)
+    c = np.asarray(mesh.coords)
+    s0 = np.concatenate([0.4 * smooth_u(c), 0.5 + 0.3 * np.sin(6 * c[:, :1])], axis=1)
+    mk = pop.new_symmetric_vector if (pop.halo == "peer" and world > 1) else pop.new_local_vector
+    s, d, y = mk(), mk(), mk()
+    s.copy_(torch.as_tensor(s0.ravel(), device=device))
+    d.copy_(torch.as_tensor(np.random.default_rng(1 + rank).normal(size=s0.shape).ravel(), device=device))
+    pop.fill_ghosts(s)
+
+    def timed(fn, reps=50, warm=5):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / reps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    ms_h = timed(lambda: pop.hvp(s, d, y))
+    ms_r = timed(lambda: pop.residual(s, y))
+    return {
+        "c5_compound_tet4_pf": dict(n_gpus=world, tets_per_gpu=6 * n**3, dofs_global=int(pop.n_global), halo=pop.halo if world > 1 else None,
+                                    hvp_ms=round(ms_h, 5), hvp_value=pop.n_global / (ms_h * 1e-3), residual_ms=round(ms_r, 5),
+                                    residual_value=pop.n_global / (ms_r * 1e-3), unit="DOF/s", scaling="weak (one 55^3-cell block per GPU)")
+    }

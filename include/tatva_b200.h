@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 1
+#define TATVA_B200_ABI_VERSION 2  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */

@@ -23,11 +23,48 @@ def _load():
         _lib.oracle_fused.restype = C.c_int
         _lib.oracle_fused.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 5
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_fused_pf.restype = C.c_int
+        _lib.oracle_fused_pf.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5
+        _lib.oracle_set_num_threads.restype = None
+        _lib.oracle_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
 def num_threads() -> int:
     return _load().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline legs ask for all host cores explicitly."""
+    _load().oracle_set_num_threads(int(n))
+
+
+def _run_pf(kind, mode, params, coords, conn, s, t=None):
+    """Two-field (u, phi) law: s, t (N,4) = [ux,uy,uz,phi]; params = (mu, lambda, Gc, ell, k)."""
+    L = _load()
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1, 4)
+    tt = np.ascontiguousarray(t, dtype=np.float64).reshape(-1, 4) if t is not None else None
+    prm = np.ascontiguousarray(params, dtype=np.float64)
+    out = np.zeros(1) if mode == 0 else np.empty_like(s)
+    rc = L.oracle_fused_pf(_KIND[kind], mode, prm.ctypes.data, coords.shape[0], conn.shape[0], coords.ctypes.data, conn.ctypes.data,
+                           s.ctypes.data, tt.ctypes.data if tt is not None else None, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("oracle_fused_pf: unsupported element")
+    return float(out[0]) if mode == 0 else out
+
+
+def energy_pf(kind, params, coords, conn, s):
+    return _run_pf(kind, 0, params, coords, conn, s)
+
+
+def residual_pf(kind, params, coords, conn, s):
+    return _run_pf(kind, 1, params, coords, conn, s)
+
+
+def hvp_pf(kind, params, coords, conn, s, t):
+    return _run_pf(kind, 2, params, coords, conn, s, t)
 
 
 def _run(kind, material, mode, params, coords, conn, u, v=None):

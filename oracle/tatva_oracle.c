@@ -215,3 +215,114 @@ int oracle_fused(int kind, int material, int mode, double mu, double lm, int64_t
   if (mode == MODE_ENERGY) *out = energy;
   return 0;
 }
+
+/* ---- Compound (u, phi) two-field law of config 5 (builder-defined AT2 density; no counterpart in the reference, see
+ * oracle/tatva_oracle.py NeoHookeanPhaseField).  Nodal state s (N,4) = [ux,uy,uz,phi] (compound/__init__.py:334-389);
+ * the fields enter through Operator.grad (u, phi) and Operator.eval (phi): operator.py:358-397, element/base.py:95-115. */
+static void shape_fn(int kind, int q, double* N) {
+  if (kind == TET4) {
+    for (int n = 0; n < 4; ++n) N[n] = 0.25; /* centroid: 1-xi-eta-zeta = xi = eta = zeta = 1/4  (base.py:448-466) */
+  } else {
+    const double a = 1.0 / sqrt(3.0);
+    for (int n = 0; n < 8; ++n)
+      N[n] = 0.125 * (1 + HEX_S[n][0] * a * HEX_S[q][0]) * (1 + HEX_S[n][1] * a * HEX_S[q][1]) * (1 + HEX_S[n][2] * a * HEX_S[q][2]);
+  }
+}
+
+/* prm = {mu, lambda, Gc, ell, k}.  mode as oracle_fused; s, t, out are (N,4). */
+int oracle_fused_pf(int kind, int mode, const double* prm, int64_t n_nodes, int64_t n_elems, const double* coords,
+                    const int32_t* conn, const double* s, const double* t, double* out) {
+  int dim, npe, nq;
+  elem_info(kind, &dim, &npe, &nq);
+  if (dim != 3) return -1;
+  const double mu = prm[0], lm = prm[1], Gc = prm[2], ell = prm[3], kk = prm[4];
+  const double wq = quad_weight(kind);
+  double energy = 0.0;
+  if (mode != MODE_ENERGY) memset(out, 0, sizeof(double) * n_nodes * 4);
+#pragma omp parallel for schedule(static) reduction(+ : energy)
+  for (int64_t e = 0; e < n_elems; ++e) {
+    double X[24], S[32], T[32], Y[32] = {0}, dNdX[24], N[8];
+    const int32_t* nd = conn + e * npe;
+    for (int n = 0; n < npe; ++n) {
+      for (int c = 0; c < 3; ++c) X[n * 3 + c] = coords[(int64_t)nd[n] * 3 + c];
+      for (int c = 0; c < 4; ++c) {
+        S[n * 4 + c] = s[(int64_t)nd[n] * 4 + c];
+        if (mode == MODE_HVP) T[n * 4 + c] = t[(int64_t)nd[n] * 4 + c];
+      }
+    }
+    for (int q = 0; q < nq; ++q) {
+      const double W = geometry(kind, dim, npe, q, X, dNdX) * wq;
+      shape_fn(kind, q, N);
+      double G[9], dG[9], gphi[3], dgphi[3], phi = 0, dphi = 0;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double a = 0, b = 0;
+          for (int n = 0; n < npe; ++n) {
+            a += dNdX[j * npe + n] * S[n * 4 + i];
+            if (mode == MODE_HVP) b += dNdX[j * npe + n] * T[n * 4 + i];
+          }
+          G[i * 3 + j] = a;
+          dG[i * 3 + j] = b;
+        }
+      for (int j = 0; j < 3; ++j) {
+        double a = 0, b = 0;
+        for (int n = 0; n < npe; ++n) {
+          a += dNdX[j * npe + n] * S[n * 4 + 3];
+          if (mode == MODE_HVP) b += dNdX[j * npe + n] * T[n * 4 + 3];
+        }
+        gphi[j] = a;
+        dgphi[j] = b;
+      }
+      for (int n = 0; n < npe; ++n) {
+        phi += N[n] * S[n * 4 + 3];
+        if (mode == MODE_HVP) dphi += N[n] * T[n * 4 + 3];
+      }
+      const double g = (1 - phi) * (1 - phi) + kk, dg = -2 * (1 - phi);
+      const double psi = psi_nh(G, mu, lm);
+      if (mode == MODE_ENERGY) {
+        energy += W * (g * psi + Gc * (phi * phi / (2 * ell) + 0.5 * ell * (gphi[0] * gphi[0] + gphi[1] * gphi[1] + gphi[2] * gphi[2])));
+        continue;
+      }
+      double P[9], A[9], b, c[3];
+      P_nh(G, mu, lm, P);
+      if (mode == MODE_RESIDUAL) {
+        for (int k = 0; k < 9; ++k) A[k] = g * P[k];
+        b = dg * psi + Gc * phi / ell;
+        for (int j = 0; j < 3; ++j) c[j] = Gc * ell * gphi[j];
+      } else {
+        double dP[9], PdG = 0;
+        dP_nh(G, dG, mu, lm, dP);
+        for (int k = 0; k < 9; ++k) PdG += P[k] * dG[k];
+        for (int k = 0; k < 9; ++k) A[k] = g * dP[k] + dg * dphi * P[k];
+        b = dg * PdG + 2 * dphi * psi + Gc * dphi / ell;
+        for (int j = 0; j < 3; ++j) c[j] = Gc * ell * dgphi[j];
+      }
+      for (int n = 0; n < npe; ++n) {
+        for (int i = 0; i < 3; ++i) {
+          double a = 0;
+          for (int j = 0; j < 3; ++j) a += A[i * 3 + j] * dNdX[j * npe + n];
+          Y[n * 4 + i] += W * a;
+        }
+        double a = b * N[n];
+        for (int j = 0; j < 3; ++j) a += c[j] * dNdX[j * npe + n];
+        Y[n * 4 + 3] += W * a;
+      }
+    }
+    if (mode != MODE_ENERGY)
+      for (int n = 0; n < npe; ++n)
+        for (int i = 0; i < 4; ++i) {
+#pragma omp atomic
+          out[(int64_t)nd[n] * 4 + i] += Y[n * 4 + i];
+        }
+  }
+  if (mode == MODE_ENERGY) *out = energy;
+  return 0;
+}
+
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtatva_b200.so")
 TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
 PLAN_CACHE_WEIGHTS = 1
+ABI_VERSION = 2  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
@@ -91,18 +92,29 @@ def lib() -> C.CDLL:
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            # not built yet (fresh checkout): compile it now if nvcc is around; there is no CPU fallback
-            try:
-                from . import build as _build
+        from . import build as _build
 
+        stale = os.path.exists(LIB_PATH) and _build.needs_build()
+        if not os.path.exists(LIB_PATH) or stale:
+            # not built yet (fresh checkout) or older than its sources: compile it now if nvcc is around (cheap when up
+            # to date); there is no CPU fallback
+            try:
                 _build.build()
             except Exception as exc:  # noqa: BLE001
-                raise TatvaError(
-                    f"{LIB_PATH} not found and building it failed ({exc}); run `python -m tatva_b200.build` "
-                    "(there is no CPU fallback)"
-                ) from exc
+                if not os.path.exists(LIB_PATH):
+                    raise TatvaError(
+                        f"{LIB_PATH} not found and building it failed ({exc}); run `python -m tatva_b200.build` "
+                        "(there is no CPU fallback)"
+                    ) from exc
+                # a box without nvcc (the GPU box uses the prebuilt library): the ABI check below decides
         L = C.CDLL(LIB_PATH)
+        L.tatva_abi_version.restype = C.c_int
+        have = L.tatva_abi_version()
+        if have != ABI_VERSION:
+            raise TatvaError(f"{LIB_PATH} has ABI version {have}, this package expects {ABI_VERSION}: rebuild with `python -m tatva_b200.build --force`")
+        missing = [name for name in SIGNATURES if not hasattr(L, name)]
+        if missing:
+            raise TatvaError(f"{LIB_PATH} lacks {missing}: rebuild with `python -m tatva_b200.build --force`")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

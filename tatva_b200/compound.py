@@ -150,11 +150,11 @@ class Field:
         if _is_torch(arr):
             out = arr.clone()
             out.as_strided(self.shape, self._strides, out.storage_offset() + self._base_offset).copy_(
-                torch.as_tensor(value, dtype=arr.dtype, device=arr.device).reshape(self.shape)
+                torch.broadcast_to(torch.as_tensor(value, dtype=arr.dtype, device=arr.device), self.shape)  # Array | float, as arr.at[...].set
             )
             return out
         out = np.array(arr, copy=True)
-        out[self.indices(slice(None))] = np.asarray(value, dtype=out.dtype).reshape(-1)
+        out[self.indices(slice(None))] = np.broadcast_to(np.asarray(value, dtype=out.dtype), self.shape).reshape(-1)
         return out
 
     def __get__(self, instance, owner=None):

@@ -365,7 +365,12 @@ int tatva_host_build_point_grid(const double* coords, int64_t n_nodes, const int
   return TATVA_OK;
 }
 
-// elem_pos[e, a, b] = offset of column dpn*conn[e,b] inside CSR row dpn*conn[e,a]
+// elem_pos[e, a, b] = offset of column dpn*conn[e,b] inside CSR row dpn*conn[e,a].
+// The assembly kernels write entry (i, k) of the (a, b) block at indptr[dpn*node_a + i] + pos + k, so the pattern must
+// be NODE-BLOCKED: in EVERY component row dpn*node_a + i the dpn columns dpn*node_b .. dpn*node_b + dpn-1 must sit
+// contiguously at the same offset `pos`.  Patterns that are not (a per-component Periodic in lifter.augment_sparsity, a
+// user-supplied pattern, a non-interleaved compound layout) are rejected with TATVA_E_INVALID; sparse.jacfwd then
+// takes the coloured-JVP route of the reference (sparse/base.py:230-270) instead of the direct kernel.
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe, int dpn, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos) {
   if (!conn || !indptr || !indices || !elem_pos || n_elems <= 0 || npe <= 0 || dpn <= 0) return TATVA_E_INVALID;
@@ -379,12 +384,18 @@ int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int n
       for (int b = 0; b < npe; ++b) {
         const int32_t col = conn[e * npe + b] * dpn;
         const int32_t* it = std::lower_bound(lo, hi, col);
-        if (it == hi || *it != col) {
-          bad |= 1;
-          elem_pos[(e * npe + a) * npe + b] = -1;
-        } else {
-          elem_pos[(e * npe + a) * npe + b] = (int32_t)(it - lo);
+        int32_t pos = -1;
+        if (it != hi && *it == col) {
+          pos = (int32_t)(it - lo);
+          for (int i = 0; i < dpn && pos >= 0; ++i) {  // every component row: same offset, dpn contiguous columns
+            const int64_t r0 = indptr[row + i], r1 = indptr[row + i + 1];
+            if (r0 + pos + dpn > r1) { pos = -1; break; }
+            for (int k = 0; k < dpn; ++k)
+              if (indices[r0 + pos + k] != col + k) { pos = -1; break; }
+          }
         }
+        if (pos < 0) bad |= 1;
+        elem_pos[(e * npe + a) * npe + b] = pos;
       }
     }
   }

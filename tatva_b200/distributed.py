@@ -31,17 +31,19 @@ from .operator import Operator
 
 def structured_hex_block(n, grid, rank, lengths=None, jitter=0.1, seed=0):
     """Local mesh of block `rank` of a (gx*n) x (gy*n) x (gz*n) Hex8 box split into gx x gy x gz blocks
-    of n^3 elements (partition id = px + gx (py + gy pz)), WITHOUT materialising the global mesh.
+    of n^3 elements (partition id = px + gx (py + gy pz)), WITHOUT materialising the global mesh.  `n` may be a
+    triple (nx, ny, nz) of cells per block (strong scaling: a fixed global box cut into non-cubic blocks).
 
     Returns (Mesh, PartitionInfo) identical to `extract_local_mesh(global_mesh, block_partition, rank)`:
     nodes owned by the smallest touching partition id, owned nodes first, each group ascending in global
     node id (mesh.py:258-273); elements in global (x-fastest) order.  Coordinates carry the same
     deterministic jitter a global generator would apply (hash of the global node id)."""
     gx, gy, gz = grid
+    nx, ny, nz = (n, n, n) if np.isscalar(n) else (int(a) for a in n)
     px, py, pz = rank % gx, (rank // gx) % gy, rank // (gx * gy)
-    NX, NY, NZ = gx * n, gy * n, gz * n
-    i0, j0, k0 = px * n, py * n, pz * n
-    ii, jj, kk = np.arange(i0, i0 + n + 1), np.arange(j0, j0 + n + 1), np.arange(k0, k0 + n + 1)
+    NX, NY, NZ = gx * nx, gy * ny, gz * nz
+    i0, j0, k0 = px * nx, py * ny, pz * nz
+    ii, jj, kk = np.arange(i0, i0 + nx + 1), np.arange(j0, j0 + ny + 1), np.arange(k0, k0 + nz + 1)
     K, J, I = np.meshgrid(kk, jj, ii, indexing="ij")
     gid = (I + (NX + 1) * (J + (NY + 1) * K)).ravel()  # ascending along the local lexicographic order
     ghost = ((I == i0) & (px > 0)) | ((J == j0) & (py > 0)) | ((K == k0) & (pz > 0))
@@ -56,8 +58,8 @@ def structured_hex_block(n, grid, rank, lengths=None, jitter=0.1, seed=0):
     coords = np.stack([gi * (lengths[0] / NX), gj * (lengths[1] / NY), gk * (lengths[2] / NZ)], axis=-1).astype(np.float64)
     if jitter:
         coords = coords + jitter * (lengths[0] / NX) * _hash_uniform(g, seed)
-    sx, sy, sz = 1, n + 1, (n + 1) * (n + 1)
-    k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     n0 = (i * sx + j * sy + k * sz).ravel()
     el = np.stack([n0, n0 + sx, n0 + sx + sy, n0 + sy, n0 + sz, n0 + sz + sx, n0 + sz + sx + sy, n0 + sz + sy], -1)
     return Mesh(coords=coords, elements=new_id[el]), PartitionInfo(nodes_local_to_global=g.astype(np.int64), n_owned_nodes=int((~ghost).sum()))

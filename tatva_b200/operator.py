@@ -156,6 +156,13 @@ class Operator:
             t = t.to(device=self.device, dtype=torch.float64)
         return t
 
+    # Hex8 x neo-Hookean HVP kernels kept for measurement; 0 = default.  8 / 9 are timing experiments
+    # (no scatter / no gather) and do not compute the HVP.
+    HEX8_NH_HVP_VARIANTS = (0, 1, 2, 3, 15, 16, 17, 20, 22, 23, 25, 26, 27, 28)
+
+    def hvp_variants(self) -> tuple:
+        return self.HEX8_NH_HVP_VARIANTS
+
     def set_variant(self, variant: int) -> None:
         """Select the Hex8 neo-Hookean HVP kernel variant (benchmarking aid)."""
         for plan in {id(p): p for p in (self._plan, self._plan_fused)}.values():
@@ -203,8 +210,11 @@ class Operator:
         return out
 
     def _k_sum_rows(self, a2):
-        out = torch.empty((a2.shape[1],), dtype=torch.float64, device=self.device)
-        self._call("tatva_op_sum_rows", a2.data_ptr(), a2.shape[0], a2.shape[1], out.data_ptr())
+        nv = a2.shape[1]
+        if nv > 64:  # the kernel sums up to 64 columns per launch; wider value shapes go in column chunks
+            return torch.cat([self._k_sum_rows(a2[:, c : c + 64].contiguous()) for c in range(0, nv, 64)])
+        out = torch.empty((nv,), dtype=torch.float64, device=self.device)
+        self._call("tatva_op_sum_rows", a2.data_ptr(), a2.shape[0], nv, out.data_ptr())
         return out
 
     # -- reference API ------------------------------------------------------------------------

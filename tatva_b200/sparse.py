@@ -271,14 +271,25 @@ def _forward_mode(f, u):
     return jvp
 
 
+def _direct_assembler(fn, colored_matrix):
+    """The one-kernel assembler for a fused residual, or None when the pattern is not node-blocked (the direct kernel
+    writes (a, b) blocks at one offset in all dpn rows of node a; `tatva_host_csr_element_positions` verifies that).
+    The caller then runs the reference's coloured algorithm: one fused HVP kernel per colour (sparse/base.py:230-270)."""
+    try:
+        return _Assembler(fn.op, fn.material, colored_matrix)
+    except (_lib.TatvaError, ValueError):
+        return None
+
+
 def jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batch_size: int | None = None) -> Callable:
     """tatva/sparse/base.py:139-176.  `fn(u, *args)` returns the residual; the result is a new
     ColoredMatrix whose `data` holds d fn / d u on the pattern."""
     from .operator import FusedResidual
 
     if isinstance(fn, FusedResidual):
-        asm = _Assembler(fn.op, fn.material, colored_matrix)
-        return lambda u: replace(colored_matrix, data=asm(u))
+        asm = _direct_assembler(fn, colored_matrix)
+        if asm is not None:
+            return lambda u: replace(colored_matrix, data=asm(u))
 
     def _wrapped(u, *args, **kwargs):
         ut = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u), device="cuda")
@@ -294,8 +305,9 @@ def linearized_jacfwd(fn: Callable, colored_matrix: ColoredMatrix, *, color_batc
     from .operator import FusedResidual
 
     if isinstance(fn, FusedResidual):
-        asm = _Assembler(fn.op, fn.material, colored_matrix)
-        return lambda u: (fn(u), replace(colored_matrix, data=asm(u)))
+        asm = _direct_assembler(fn, colored_matrix)
+        if asm is not None:
+            return lambda u: (fn(u), replace(colored_matrix, data=asm(u)))
 
     def _wrapped(u, *args, **kwargs):
         ut = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.asarray(u), device="cuda")

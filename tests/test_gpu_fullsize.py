@@ -1,0 +1,113 @@
+"""GPU parity at the BASELINE.json config sizes, directly against the C oracle (oracle/tatva_oracle.c, the OpenMP
+restatement of the reference's arithmetic, itself pinned to the NumPy oracle and through it to the reference's outputs).
+
+Tolerance 1e-12 relative (l2 and max-norm), as the north star states.  Sizes: config 1 Tri3 256^2, config 2 Tet4 n = 55
+(residual, HVP and the assembled CSR values), config 3 Hex8 128^3 (and 32^3), config 5 compound
+(u, phi) Tet4 n = 55.  The C oracle finishes each of them in well under a second per call on the box's host cores.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import tatva_oracle as orc
+from test_gpu_parity import _assert_close, _case, _make_op, _material, _rel
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _all_host_cores():
+    c_oracle.set_num_threads(os.cpu_count() or 1)
+    yield
+
+
+@pytest.mark.parametrize("n", [32, 128])
+def test_config3_hex8_neo_hookean_vs_c_oracle(n):
+    """Config 3 (Hex8 128^3, 6.44 M DOFs) and the 32^3 size of SURVEY §8(d): energy, residual, HVP."""
+    c, el, u, v, (mname, omat) = _case("hex8", n)
+    op = _make_op("hex8", c, el)
+    mat = _material(mname, omat)
+    prm = (omat.mu, omat.lmbda)
+    e_ref = c_oracle.energy("hex8", prm, c, el, u)
+    assert abs(float(op.energy(mat)(u)) - e_ref) <= RTOL * abs(e_ref)
+    _assert_close(op.residual(mat)(u), c_oracle.residual("hex8", prm, c, el, u), RTOL)
+    _assert_close(op.hvp(mat)(u, v), c_oracle.hvp("hex8", prm, c, el, u, v), RTOL)
+
+
+def test_config3_hex8_every_hvp_variant_vs_c_oracle():
+    """Every kernel variant kept for measurement computes the same HVP (Hex8 32^3)."""
+    c, el, u, v, (mname, omat) = _case("hex8", 32)
+    ref = c_oracle.hvp("hex8", (omat.mu, omat.lmbda), c, el, u, v)
+    mat = _material(mname, omat)
+    op = _make_op("hex8", c, el)
+    for variant in op.hvp_variants():
+        op.set_variant(variant)
+        _assert_close(op.hvp(mat)(u, v), ref, RTOL)
+    op.set_variant(0)
+
+
+def test_config1_tri3_linear_elastic_256_vs_c_oracle():
+    """Config 1: Tri3 256 x 256, plane-strain linear elasticity (E = 1, nu = 0.3)."""
+    c, el, u, v, (mname, omat) = _case("tri3", 256)
+    assert el.shape[0] == 131072 and c.shape[0] == 66049
+    op = _make_op("tri3", c, el)
+    mat = _material(mname, omat)
+    prm = (omat.mu, omat.lmbda)
+    e_ref = c_oracle.energy("tri3", prm, c, el, u, "linear_elastic")
+    assert abs(float(op.energy(mat)(u)) - e_ref) <= RTOL * abs(e_ref)
+    _assert_close(op.residual(mat)(u), c_oracle.residual("tri3", prm, c, el, u, "linear_elastic"), RTOL)
+    _assert_close(op.hvp(mat)(u, v), c_oracle.hvp("tri3", prm, c, el, u, v, "linear_elastic"), RTOL)
+
+
+def test_config2_tet4_residual_hvp_and_csr_values_vs_c_oracle():
+    """Config 2: Tet4 box n = 55 (998 250 elements).  Residual and HVP against the C oracle; the assembled CSR `data`
+    (23 036 814 values) against the REFERENCE ALGORITHM (sparse/base.py:139-176, :230-270) driven by the C oracle:
+    one oracle HVP per colour with a 0/1 seed, then data[k] = J_c[row(k), colors[indices[k]]]."""
+    from tatva_b200 import sparse
+
+    c, el, u, v, (mname, omat) = _case("tet4", 55)
+    assert el.shape[0] == 998250
+    op = _make_op("tet4", c, el)
+    mat = _material(mname, omat)
+    prm = (omat.mu, omat.lmbda)
+    _assert_close(op.residual(mat)(u), c_oracle.residual("tet4", prm, c, el, u), RTOL)
+    _assert_close(op.hvp(mat)(u, v), c_oracle.hvp("tet4", prm, c, el, u, v), RTOL)
+    pat = sparse.pattern_from_mesh(op.mesh, 3)
+    assert pat.nnz == 23036814
+    cm = sparse.ColoredMatrix.from_csr(pat)
+    colors = np.asarray(cm.colors)
+    n = 3 * c.shape[0]
+    jvp = lambda seed: c_oracle.hvp("tet4", prm, c, el, u, seed.reshape(-1, 3)).ravel()  # noqa: E731
+    ref = orc.colored_jacobian_data(jvp, n, pat.indptr, pat.indices, colors)
+    data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
+    assert data.shape == ref.shape
+    assert _rel(data, ref) <= RTOL
+    rows = sparse.assembler(op, mat, cm, by_rows=True)(u).cpu().numpy()  # the bitwise-reproducible kernel
+    assert _rel(rows, ref) <= RTOL
+    # and the public reference-shaped entry point
+    K = sparse.jacfwd(op.residual(mat), cm)(u)
+    assert _rel(K.data.cpu().numpy() if isinstance(K.data, torch.Tensor) else K.data, ref) <= RTOL
+
+
+def test_config5_compound_phase_field_tet4_55_vs_c_oracle():
+    """Config 5 at its parity size (n = 55): the compound (u, phi) state, node-interleaved [ux,uy,uz,phi]."""
+    from tatva_b200 import materials
+
+    rng = np.random.default_rng(1)
+    c, el, u, _, _ = _case("tet4", 55)
+    prm = (500.0, 1000.0, 2.7, 0.1, 1e-6)
+    mat = materials.NeoHookeanPhaseField(*prm)
+    op = _make_op("tet4", c, el)
+    phi = 0.4 + 0.4 * np.sin(2 * np.pi * c[:, 0]) * np.cos(2 * np.pi * c[:, 1])
+    s = np.concatenate([u, phi[:, None]], axis=1)
+    t = rng.normal(size=s.shape)
+    arr, tt = torch.as_tensor(s.ravel(), device="cuda"), torch.as_tensor(t.ravel(), device="cuda")
+    e_ref = c_oracle.energy_pf("tet4", prm, c, el, s)
+    assert abs(float(op.energy(mat)(arr)) - e_ref) <= RTOL * abs(e_ref)
+    _assert_close(op.residual(mat)(arr).reshape(-1, 4), c_oracle.residual_pf("tet4", prm, c, el, s), RTOL)
+    _assert_close(op.hvp(mat)(arr, tt).reshape(-1, 4), c_oracle.hvp_pf("tet4", prm, c, el, s, t), RTOL)

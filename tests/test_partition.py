@@ -23,6 +23,23 @@ def test_structured_block_matches_extract_local_mesh(grid):
         np.testing.assert_allclose(mesh.coords, ref_mesh.coords, atol=1e-15)
 
 
+@pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 1), (2, 2, 2)])
+def test_structured_block_non_cubic_matches_extract_local_mesh(grid):
+    """Strong scaling cuts a FIXED cube into non-cubic blocks (256^3 -> 128 x 256 x 256 at 2 GPUs)."""
+    N = 4
+    nparts = grid[0] * grid[1] * grid[2]
+    per = (N // grid[0], N // grid[1], N // grid[2])
+    gm = Mesh.box_hex((N, N, N))
+    part = block_partition((N, N, N), nparts)
+    for r in range(nparts):
+        ref_mesh, ref_info = extract_local_mesh(gm, part, r)
+        mesh, info = structured_hex_block(per, grid, r, jitter=0.0)
+        np.testing.assert_array_equal(info.nodes_local_to_global, ref_info.nodes_local_to_global)
+        assert info.n_owned_nodes == ref_info.n_owned_nodes
+        np.testing.assert_array_equal(mesh.elements, ref_mesh.elements)
+        np.testing.assert_allclose(mesh.coords, ref_mesh.coords, atol=1e-15)
+
+
 def test_block_jitter_is_consistent_across_ranks():
     a, ia = structured_hex_block(3, (2, 1, 1), 0)
     b, ib = structured_hex_block(3, (2, 1, 1), 1)

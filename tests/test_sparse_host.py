@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.tatva_abi_version() == 1
+    assert L.tatva_abi_version() == _lib.ABI_VERSION
 
 
 def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
@@ -104,6 +104,31 @@ def test_csr_element_positions():
                 row = el[e, a] * dpn
                 assert ix[ip[row] + pos[e, a, b]] == el[e, b] * dpn
                 assert ix[ip[row + 2] + pos[e, a, b] + 2] == el[e, b] * dpn + 2
+
+
+def test_csr_element_positions_reject_patterns_that_are_not_node_blocked():
+    """A same-size pattern whose component rows of one node differ (here: one extra column in the SECOND component row
+    of node 0, as a per-component Periodic adds through lifter.augment_sparsity) must be refused: the direct assembly
+    kernels write (a, b) blocks at one offset in every component row of node a."""
+    import scipy.sparse as sps
+
+    c, el = orc.mesh_box_tet((1, 1, 1), (2, 2, 2))
+    dpn = 3
+    ip, ix = sparse.pattern_arrays(el, len(c), dpn)
+    n = dpn * len(c)
+    A = sps.csr_matrix((np.ones(len(ix), dtype=np.int8), ix, ip), shape=(n, n)).tolil()
+    row = 1  # second component row of node 0
+    last = int(ix[ip[row + 1] - 1])
+    missing = [j for j in range(last) if A[row, j] == 0]  # a column in front of at least one block of the row
+    A[row, missing[0]] = 1  # shifts the offsets of the later blocks in this row only
+    A = A.tocsr()
+    A.sort_indices()
+    ip2, ix2 = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    pos = np.empty((el.shape[0], 4, 4), dtype=np.int32)
+    args = (el.ctypes.data_as(_lib.c_i32p), el.shape[0], 4, dpn)
+    rc = _lib.lib().tatva_host_csr_element_positions(*args, ip2.ctypes.data_as(_lib.c_i32p), ix2.ctypes.data_as(_lib.c_i32p), pos.ctypes.data_as(_lib.c_i32p))
+    assert rc == -1  # TATVA_E_INVALID
+    assert (pos < 0).any()
 
 
 def test_invalid_arguments_return_error_codes():
