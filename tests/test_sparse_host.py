@@ -45,7 +45,7 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
     exe = tmp_path / "abi"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), lib, f"-Wl,-rpath,{os.path.dirname(lib)}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(maxsplit=2)
-    assert out[0] == "1" and out[1] == "56"  # two triangles sharing an edge, 2 DOFs per node: (3+4+3+4 node pairs) * 4
+    assert out[0] == str(_lib.ABI_VERSION) and out[1] == "56"  # two triangles sharing an edge, 2 DOFs per node: (3+4+3+4 node pairs) * 4
 
 
 @pytest.mark.parametrize("name,dpn", [("tri3_8x8_d2", 2), ("tet4_3_d3", 3), ("tet4_2_d4", 4), ("hex8_3_d3", 3)])
