@@ -310,7 +310,7 @@ def main():
     else:
         prob = DistributedHex8Problem(args.n, rank, world, dev, mat, variant=args.variant, halo=args.halo)
         workload = f"Hex8 {args.n}^3 per GPU, neo-Hookean (mu=500, lambda=1000) matrix-free HVP, {prob.partition_desc}"
-    n_dofs_global = prob.n_dofs_global
+    n_dofs_global, partition_desc = prob.n_dofs_global, prob.partition_desc
     step = prob.step
 
     for _ in range(args.warmup):
@@ -418,7 +418,7 @@ def main():
                 "dofs_global": n_dofs_global,
                 "dofs_per_gpu": 3 * local_nodes,
                 "l2_policy": "inputs larger than L2 (273 MB working set per GPU vs 126 MB L2)",
-                "parallelism": workload.split(", ", 2)[-1],
+                "parallelism": partition_desc,
             },
             # achieved = max(HBM term, FP64 term); the binding roof of this operator is FP64 (AI ~ 61 flop/B)
             "roofline": {

@@ -224,6 +224,59 @@ TATVA_D void ref_grad_s(Ptr c, int stride, double tx, double ty, double tz, doub
   g[2] = fma(tx, fma(ty, c6, c5), fma(ty, c4, c2));
 }
 
+// Branch-free reciprocal and logarithm for the Gauss-point loops.  CUDA's `1.0 / x` and `log(x)` carry slow-path branches
+// (denormals, infinities, NaNs) that cut the loop body into several basic blocks; ptxas schedules within a block, so the
+// two independent Gauss points of a tx pair could not be interleaved across them and each warp sat in fixed-latency
+// dependency stalls ("wait": 45 % of its time inside the loop, profiles/r02_hvp_ncu_stalls.md).  The arguments here are
+// determinants of non-degenerate elements (finite, normal, and positive for the logarithm; an inverted element gives a
+// NaN either way), so the special cases are not needed.
+//   fast_rcp: MUFU.RCP64H seed (rel. error <= 2^-20) + two Newton steps                -> <= 1 ulp
+//   log_pos : x = 2^e m, m in [sqrt(1/2), sqrt(2)), f = (m-1)/(m+1), log m = 2 f sum_k f^(2k) / (2k+1), k <= 10
+//             (|f| <= 0.1716: truncation 1e-18), relative error ~2e-16 near x = 1 (e = 0), absolute ~1e-16 |e| ln 2 elsewhere.
+// The host twins (kernel-arithmetic probes) use the C library.
+TATVA_HD double fast_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double t = fma(-x, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-x, r, 1.0);
+  return fma(r, t, r);
+#else
+  return 1.0 / x;
+#endif
+}
+
+TATVA_HD double log_pos(double x) {
+#ifdef __CUDA_ARCH__
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;           // m in [1, 2)
+  const int up = hi >= 0x3ff6a09f ? 1 : 0;       // m >= sqrt(2) (to 2^-20): halve it
+  hi -= up << 20;
+  e += up;
+  const double m = __hiloint2double(hi, lo);
+  const double f = (m - 1.0) * fast_rcp(m + 1.0);
+  const double g = f * f;
+  double p = 1.0 / 21.0;
+  p = fma(p, g, 1.0 / 19.0);
+  p = fma(p, g, 1.0 / 17.0);
+  p = fma(p, g, 1.0 / 15.0);
+  p = fma(p, g, 1.0 / 13.0);
+  p = fma(p, g, 1.0 / 11.0);
+  p = fma(p, g, 1.0 / 9.0);
+  p = fma(p, g, 1.0 / 7.0);
+  p = fma(p, g, 1.0 / 5.0);
+  p = fma(p, g, 1.0 / 3.0);
+  p = p * g;                                       // log m = 2 f (1 + p)
+  const double two_f = f + f;
+  return fma((double)e, 0.69314718055994530942, fma(two_f, p, two_f));
+#else
+  return log(x);
+#endif
+}
+
 TATVA_HD void adjugate(const double (&A)[3][3], double (&C)[3][3], double& det) {
   C[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
   C[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2];
@@ -669,9 +722,9 @@ TATVA_HD void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], cons
       M[b][a] = M[a][b];
     }
   adjugate(Fr, Ac, detF);
-  const double r = 1.0 / (detJ * detF);
+  const double r = fast_rcp(detJ * detF);
   const double rJ = r * detF, rF = r * detJ;
-  const double lnJ = log(detF * rJ);
+  const double lnJ = log_pos(detF * rJ);
   double B[3][3];
   mat3(Ac, Gv, B);
   const double wF = detJ * rF * rF;
@@ -949,6 +1002,136 @@ __global__ void __launch_bounds__(kBlock, MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
+// v4: the v3 arithmetic in a PERSISTENT kernel that hides the gather and scatter phases.
+// ncu (profiles/r02_hvp_ncu_stalls.md): a v3 warp spends 29 % of its life in the gather / modal-transform prologue (41 %
+// of that waiting on the dependent connectivity -> nodal-row round trips to L2 / HBM) and 9 % in the scatter epilogue
+// (56 % of that draining its REDs before the CTA may exit); the FP64 pipe only saturates while BOTH warps of a scheduler
+// are inside the Gauss-point loop.  Here every thread walks a grid-strided list of elements:
+//   * the NEXT element's connectivity is loaded during the first pair iteration and its 24 nodal rows are prefetched
+//     (PF = 1: into L2, PF = 2: into L1) during the second one, so the gather after the loop finds them on chip;
+//   * the connectivity lines one more element ahead are prefetched into L2;
+//   * the REDs of an element are fire-and-forget: the thread goes on with the next element, nothing drains until the end.
+// ---------------------------------------------------------------------------------------------
+template <int PF>
+TATVA_D void prefetch_row(const double* p) {
+  if constexpr (PF == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if constexpr (PF == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+template <int MINB, int PF>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_hvp_v4(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                     double lmbda, const double* __restrict__ u, const double* __restrict__ v,
+                     double* __restrict__ y) {
+  extern __shared__ double sm[];
+  double* sX0 = sm + threadIdx.x;
+  double* sv0 = sm + 21 * kBlock + threadIdx.x;
+  int4* snd = reinterpret_cast<int4*>(sm + 42 * kBlock) + threadIdx.x;  // next connectivity: [2][kBlock] int4
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (e >= E) return;
+  const int4* c4 = reinterpret_cast<const int4*>(conn);
+  int4 t0 = __ldg(c4 + 2 * e), t1 = __ldg(c4 + 2 * e + 1);
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+#pragma unroll 1
+  for (;;) {
+    const int nd[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    double hx[3][7];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double fX[8], fu[8], fv[8], tX[7], tv[7];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        fX[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+        fu[n] = __ldg(u + (int64_t)nd[n] * 3 + c);
+        fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+      }
+      to_modal_raw(fX, tX);
+      to_modal_raw(fu, hx[c]);
+      to_modal_raw(fv, tv);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        hx[c][k] += tX[k];
+        sX0[(c * 7 + k) * kBlock] = tX[k];
+        sv0[(c * 7 + k) * kBlock] = tv[k];
+      }
+    }
+    double R[3][7];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+    const int64_t en = e + stride;
+    const bool more = en < E;
+    int4 n0 = t0, n1 = t1;
+
+#pragma unroll 1
+    for (int pq = 0; pq < 4; ++pq) {
+      const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
+      int opaque = 0;
+      asm volatile("" : "+r"(opaque));
+      const double* sX = sX0 + opaque;
+      const double* sv = sv0 + opaque;
+      if (more) {
+        if (pq == 0) {  // next element's connectivity (its lines were prefetched into L2 one element ago)
+          n0 = __ldg(c4 + 2 * en);
+          n1 = __ldg(c4 + 2 * en + 1);
+          if (en + stride < E) asm volatile("prefetch.global.L2 [%0];" ::"l"(c4 + 2 * (en + stride)));
+        } else if (pq == 1) {  // ... has arrived: park it in shared memory and prefetch its nodal rows
+          snd[0] = n0;
+          snd[kBlock] = n1;
+          if constexpr (PF != 0) {
+            const int nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              prefetch_row<PF>(coords + (int64_t)nn[n] * 3);
+              prefetch_row<PF>(u + (int64_t)nn[n] * 3);
+              prefetch_row<PF>(v + (int64_t)nn[n] * 3);
+            }
+          }
+        }
+      }
+      double Jm[3][3], Jp[3][3], Frm[3][3], Frp[3][3], Gvm[3][3], Gvp[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double gm[3], gp[3], t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sX[(c * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, gm, gp);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          Jm[d][c] = gm[d];
+          Jp[d][c] = gp[d];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sv[(i * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, Gvm[i], Gvp[i]);
+      }
+      double Qm[3][3], Qp[3][3];
+      point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
+      point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
+      accumulate_pair(Qm, Qp, sy, sz, syz, R);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double f[8];
+      from_modal_raw(R[i], f);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+    }
+    if (!more) break;
+    e = en;
+    t0 = snd[0];
+    t1 = snd[kBlock];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Residual in the same modal / reference-space form:
 //   W P K = W [ mu Fr M + (lambda lnJ - mu) A^T ],   P = mu (F - F^-T) + lambda lnJ F^-T,  F = Fr K^T.
 // ---------------------------------------------------------------------------------------------
@@ -1139,9 +1322,9 @@ TATVA_HD void point_flux_residual(const double (&J)[3][3], const double (&Fr)[3]
       M[b][a] = M[a][b];
     }
   adjugate(Fr, Ac, detF);
-  const double r = 1.0 / (detJ * detF);
+  const double r = fast_rcp(detJ * detF);
   const double rJ = r * detF, rF = r * detJ;
-  const double lnJ = log(detF * rJ);
+  const double lnJ = log_pos(detF * rJ);
   const double w1 = mu_s * rJ, w2 = (lm_s * lnJ - mu_s) * detJ * rF;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -1171,8 +1354,8 @@ TATVA_HD double point_energy(const double (&J)[3][3], const double (&Fr)[3][3], 
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int d = 0; d < 3; ++d) I1 = fma(Fr[i][0] * M[0][d] + Fr[i][1] * M[1][d] + Fr[i][2] * M[2][d], Fr[i][d], I1);
-  const double rJ = 1.0 / detJ;
-  const double lnJ = log(detF * rJ);
+  const double rJ = fast_rcp(detJ);
+  const double lnJ = log_pos(detF * rJ);
   return detJ * (0.5 * mu * (I1 * rJ * rJ - 3.0 - 2.0 * lnJ) + 0.5 * lmbda * lnJ * lnJ);
 }
 
@@ -1511,6 +1694,39 @@ static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double*
   return TATVA_OK;
 }
 
+// persistent grid: as many CTAs as fit on the device at once (queried once per device)
+template <class K>
+static int resident_grid(K kernel, size_t smem, int64_t n_elems, int (&cache)[64], int* grid) {
+  int dev = 0;
+  TATVA_CUDA_TRY(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  int g = tracked ? cache[dev] : 0;
+  if (g == 0) {
+    int sms = 0, per_sm = 0;
+    TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TATVA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
+    g = sms * (per_sm > 0 ? per_sm : 1);
+    if (tracked) cache[dev] = g;
+  }
+  const int need = grid_for(n_elems);
+  *grid = g < need ? g : need;
+  return TATVA_OK;
+}
+
+template <int MINB, int PF>
+static int launch_v4(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                     cudaStream_t st) {
+  constexpr size_t smem = (size_t)42 * kBlock * sizeof(double) + (size_t)2 * kBlock * sizeof(int4);
+  static SmemOptIn configured;
+  static int cache[64];
+  int rc = opt_in_smem(k_hex8_nh_hvp_v4<MINB, PF>, smem, configured);
+  if (rc != TATVA_OK) return rc;
+  int grid = 0;
+  if ((rc = resident_grid(k_hex8_nh_hvp_v4<MINB, PF>, smem, p->n_elems, cache, &grid)) != TATVA_OK) return rc;
+  k_hex8_nh_hvp_v4<MINB, PF><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  return TATVA_OK;
+}
+
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
@@ -1529,6 +1745,9 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 27: rc = launch_v3<2, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 25: rc = launch_v3<2, 2>(p, mu, lmbda, u, v, y, st); break;
     case 26: rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st); break;
+    case 31: rc = launch_v4<2, 0>(p, mu, lmbda, u, v, y, st); break;  // persistent, no prefetch
+    case 32: rc = launch_v4<2, 1>(p, mu, lmbda, u, v, y, st); break;  // persistent + L2 prefetch of the next rows
+    case 33: rc = launch_v4<2, 2>(p, mu, lmbda, u, v, y, st); break;  // persistent + L1 prefetch
     case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 20: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     default: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;  // pair-sharing, X and v staged
@@ -1573,25 +1792,6 @@ int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, 
     default: k_hex8_nh_energy_v3<3><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, p->scratch); break;
   }
   TATVA_LAUNCH_CHECK();
-  return TATVA_OK;
-}
-
-// persistent grid: as many CTAs as fit on the device at once (queried once per device)
-template <class K>
-static int resident_grid(K kernel, size_t smem, int64_t n_elems, int (&cache)[64], int* grid) {
-  int dev = 0;
-  TATVA_CUDA_TRY(cudaGetDevice(&dev));
-  const bool tracked = dev >= 0 && dev < 64;
-  int g = tracked ? cache[dev] : 0;
-  if (g == 0) {
-    int sms = 0, per_sm = 0;
-    TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TATVA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
-    g = sms * (per_sm > 0 ? per_sm : 1);
-    if (tracked) cache[dev] = g;
-  }
-  const int need = grid_for(n_elems);
-  *grid = g < need ? g : need;
   return TATVA_OK;
 }
 
