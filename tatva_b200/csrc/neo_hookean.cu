@@ -709,6 +709,9 @@ TATVA_HD void ref_grad8_pair(const double (&h)[7], double sy, double sz, double 
 }
 
 // flux Q[i][d] (scaled by 512) of one Gauss point from J (8 dX/dxi, [d][c]), Fr, Gv ([i][d])
+#ifndef TATVA_FLUX_CHAINS
+#define TATVA_FLUX_CHAINS 0
+#endif
 TATVA_HD void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], const double (&Gv)[3][3], double mu_s,
                         double lm_s, double (&Q)[3][3]) {
   double Kc[3][3], detJ, Ac[3][3], detF;
@@ -740,12 +743,34 @@ TATVA_HD void point_flux(const double (&J)[3][3], const double (&Fr)[3][3], cons
   for (int d = 0; d < 3; ++d)
 #pragma unroll
     for (int f = 0; f < 3; ++f) B[d][f] = (d == f) ? fma(w2, B[d][f], w3) : w2 * B[d][f];
+#if TATVA_FLUX_CHAINS
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int d = 0; d < 3; ++d)
       Q[i][d] = fma(B[d][0], Ac[0][i], fma(B[d][1], Ac[1][i], fma(B[d][2], Ac[2][i],
                 fma(Gv[i][0], M[0][d], fma(Gv[i][1], M[1][d], Gv[i][2] * M[2][d])))));
+#else
+  // Q = Gv M' + (B' Ac)^T accumulated k-outer: three consecutive DFMAs share one vector-register operand (operand
+  // reuse), which is what a DFMA with three distinct register sources needs to issue at full rate
+  // (tools/micro/fp64_mix.cu: 3.0 cycles with three distinct register sources, 2.4 with one of them reused, 2.0 with two).
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Q[i][d] = Gv[i][0] * M[0][d];
+#pragma unroll
+  for (int k = 1; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Q[i][d] = fma(Gv[i][k], M[k][d], Q[i][d]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Q[i][d] = fma(B[d][k], Ac[k][i], Q[i][d]);
+#endif
 }
 
 // Transposed reference gradient of a tx pair: the fluxes of the two Gauss points (xi = -a and +a) enter the 7 modal
@@ -784,7 +809,7 @@ TATVA_D void wide_row(const double* __restrict__ src, int64_t node, double (&dst
 // WIDE: node rows are fetched whole (one double2 + one double each) array by array, instead of component by component
 // with 8-byte loads: 48 instead of 72 gather instructions per element, but ~400 more integer / select instructions.
 // Measured slower (0.490 vs 0.453 ms, variant 28), so the default stays component-wise.
-template <int MINB, int STAGE, int GROUPED = 0, bool LIFT = false, int WIDE = 0>
+template <int MINB, int STAGE, int GROUPED = 0, bool LIFT = false, int WIDE = 0, int UNR = 1, int CPF = 0, int NDS = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                      double lmbda, const double* __restrict__ u, const double* __restrict__ v,
@@ -800,6 +825,12 @@ __global__ void __launch_bounds__(kBlock, MINB)
     const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
     nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
     nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  if constexpr (CPF > 0) {
+    // The connectivity is a pure stream and the first of the two dependent round trips of the gather: pull the lines
+    // of the CTA that will run CPF CTAs from now (about one wave later on this SM) into L2 with one instruction.
+    const int64_t ea = e + (int64_t)CPF * kBlock;
+    if (ea < E) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const int4*>(conn) + 2 * ea));
   }
   extern __shared__ double sm[];
   double* sX0 = sm + threadIdx.x;
@@ -905,14 +936,21 @@ __global__ void __launch_bounds__(kBlock, MINB)
     }
   }
   }
+  // NDS: the node ids are only needed again by the scatter; park them in shared memory across the Gauss-point loop
+  // (8 registers less to carry through it: the 168-register / 3-CTA build then runs without spills).
+  int4* snd = reinterpret_cast<int4*>(sm + (size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock) + threadIdx.x;
+  if constexpr (NDS) {
+    snd[0] = make_int4(nd[0], nd[1], nd[2], nd[3]);
+    snd[kBlock] = make_int4(nd[4], nd[5], nd[6], nd[7]);
+  }
   double R[3][7];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
-  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+  const double mu_s = mu, lm_s = lmbda;  // already scaled by 1/512 on the host: used straight from the constant bank
 
-#pragma unroll 1
+#pragma unroll UNR
   for (int pq = 0; pq < 4; ++pq) {
     const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
     int opaque = 0;
@@ -961,6 +999,11 @@ __global__ void __launch_bounds__(kBlock, MINB)
     point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
     point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
     accumulate_pair(Qm, Qp, sy, sz, syz, R);
+  }
+  if constexpr (NDS) {
+    const int4 a = snd[0], b = snd[kBlock];
+    nd[0] = a.x; nd[1] = a.y; nd[2] = a.z; nd[3] = a.w;
+    nd[4] = b.x; nd[5] = b.y; nd[6] = b.z; nd[7] = b.w;
   }
   if constexpr (GROUPED) {
     // sector-grouped scatter: consecutive lanes add the 3 consecutive doubles of one node
@@ -1018,7 +1061,7 @@ TATVA_D void prefetch_row(const double* p) {
   if constexpr (PF == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
-template <int MINB, int PF>
+template <int MINB, int PF, int DELAY = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_v4(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                      double lmbda, const double* __restrict__ u, const double* __restrict__ v,
@@ -1031,6 +1074,16 @@ __global__ void __launch_bounds__(kBlock, MINB)
   int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (e >= E) return;
   const int4* c4 = reinterpret_cast<const int4*>(conn);
+  if constexpr (DELAY > 0) {
+    // All CTAs of a persistent grid start together and every element takes the same time, so the two warps of a
+    // scheduler would sit in the same phase for the whole launch (both gathering, then both in the loop).  The second
+    // half of the grid (the second CTA of every SM) starts DELAY cycles late and stays out of phase.
+    if (blockIdx.x >= (gridDim.x >> 1)) {
+      const long long t_start = clock64();
+      while (clock64() - t_start < DELAY) {
+      }
+    }
+  }
   int4 t0 = __ldg(c4 + 2 * e), t1 = __ldg(c4 + 2 * e + 1);
   const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
 #pragma unroll 1
@@ -1128,6 +1181,167 @@ __global__ void __launch_bounds__(kBlock, MINB)
     e = en;
     t0 = snd[0];
     t1 = snd[kBlock];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v5: three warpgroups per SM that trade registers (setmaxnreg) so that two of them are always inside the Gauss-point
+// loop while the third gathers / scatters.
+//
+// ncu of v3 (profiles/r02_hvp_ncu_stalls.md): with 244 registers only two warps fit per scheduler, and they fall into
+// anti-phase — one runs the loop alone (it nearly saturates the FP64 pipe once the three-register-source DFMAs are
+// counted at 3 cycles) while the other gathers; for ~19 % of the time NEITHER is in the loop and the pipe idles.  A third
+// warp per scheduler needs <= 168 registers, which the loop cannot do without spilling (variant 26).  But only the loop
+// needs many registers: the gather / modal transform / scatter phases need < 80.  So one persistent 384-thread CTA per
+// SM holds three warpgroups which each cycle through
+//     thin (THIN regs): scatter the previous tile, gather + transform the next one into shared memory
+//     setmaxnreg.inc FAT  (blocks until another warpgroup has released its registers)
+//     fat  (FAT regs):  the four tx-pair iterations, modal coefficients read from shared memory
+//     setmaxnreg.dec THIN
+// with 2 FAT + THIN = 3 x 168 = the CTA's register pool.  The gather is cp.async (global -> shared, no registers, ONE
+// round trip for the 72 nodal values); the modal transform works in place on the thread's own shared-memory column,
+// so no thread ever reads another thread's data and the kernel needs no barrier at all.
+// ---------------------------------------------------------------------------------------------
+constexpr int kV5Threads = 384;
+constexpr int kV5Slots = 72;  // doubles per thread: 9 field components x 8 (7 modal coefficients + 1 spare)
+
+TATVA_D void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <int FAT, int THIN>
+__global__ void __launch_bounds__(kV5Threads, 1)
+    k_hex8_nh_hvp_v5(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
+                     double lmbda, const double* __restrict__ u, const double* __restrict__ v,
+                     double* __restrict__ y) {
+  static_assert(2 * FAT + THIN == 3 * 168, "the CTA's register pool is 3 warpgroups x 168");
+  extern __shared__ double sm[];
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(THIN));
+  double* col = sm + threadIdx.x;  // slot (f, c, k) = col[((f * 3 + c) * 8 + k) * kV5Threads]
+  const int wg = threadIdx.x >> 7;
+  const int64_t n_tiles = (E + 127) >> 7;
+  const int64_t tile_stride = (int64_t)gridDim.x * 3;
+  const int4* c4 = reinterpret_cast<const int4*>(conn);
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+  int* snd = reinterpret_cast<int*>(col + (size_t)(3 * 8 + 7) * kV5Threads);  // spare slot of (u, c = 0): node ids 0, 1
+  // node ids are parked in the spare (k = 7) slots of the u field: ints (2n, 2n+1) in slot (1, n >> 1 ... ) -- see nd_slot
+  auto nd_slot = [&](int n) -> int* { return reinterpret_cast<int*>(col + (size_t)((3 + (n >> 1)) * 8 + 7) * kV5Threads) + (n & 1); };
+  (void)snd;
+  bool have_prev = false, prev_valid = false;
+#pragma unroll 1
+  for (int64_t tile = (int64_t)blockIdx.x * 3 + wg; tile < n_tiles + tile_stride; tile += tile_stride) {
+    // ---------------- thin: scatter the previous tile (its modal residuals sit in the X slots) ----------------
+    if (have_prev) {
+      int nd[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) nd[n] = *nd_slot(n);
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        double r[7], f[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) r[k] = col[(size_t)(i * 8 + k) * kV5Threads];
+        from_modal_raw(r, f);
+        if (prev_valid) {
+#pragma unroll
+          for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+        }
+      }
+    }
+    if (tile >= n_tiles) break;  // uniform over the warpgroup
+    // ---------------- thin: gather the next tile (cp.async, one round trip) and transform it in place ----------------
+    const int64_t e0 = tile * 128 + (threadIdx.x & 127);
+    const bool valid = e0 < E;
+    const int64_t e = valid ? e0 : E - 1;
+    {
+      const int4 t0 = __ldg(c4 + 2 * e), t1 = __ldg(c4 + 2 * e + 1);
+      const int nd[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int64_t o = (int64_t)nd[n] * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          cp_async8(col + (size_t)((0 + c) * 8 + n) * kV5Threads, coords + o + c);
+          cp_async8(col + (size_t)((3 + c) * 8 + n) * kV5Threads, u + o + c);
+          cp_async8(col + (size_t)((6 + c) * 8 + n) * kV5Threads, v + o + c);
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        double f[8], tX[7], t[7];
+        double* cX = col + (size_t)((0 + c) * 8) * kV5Threads;
+        double* cu = col + (size_t)((3 + c) * 8) * kV5Threads;
+        double* cv = col + (size_t)((6 + c) * 8) * kV5Threads;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) f[n] = cX[(size_t)n * kV5Threads];
+        to_modal_raw(f, tX);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) cX[(size_t)k * kV5Threads] = tX[k];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) f[n] = cu[(size_t)n * kV5Threads];
+        to_modal_raw(f, t);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) cu[(size_t)k * kV5Threads] = t[k] + tX[k];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) f[n] = cv[(size_t)n * kV5Threads];
+        to_modal_raw(f, t);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) cv[(size_t)k * kV5Threads] = t[k];
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) *nd_slot(n) = nd[n];
+    }
+    // ---------------- fat: the Gauss-point loop ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FAT));
+    {
+      double R[3][7];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+#pragma unroll 1
+      for (int pq = 0; pq < 4; ++pq) {
+        const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
+        int opaque = 0;
+        asm volatile("" : "+r"(opaque));
+        const double* cc = col + opaque;
+        double Jm[3][3], Jp[3][3], Frm[3][3], Frp[3][3], Gvm[3][3], Gvp[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          double gm[3], gp[3], t[7];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) t[k] = cc[(size_t)((0 + c) * 8 + k) * kV5Threads];
+          ref_grad8_pair(t, sy, sz, gm, gp);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            Jm[d][c] = gm[d];
+            Jp[d][c] = gp[d];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double t[7];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) t[k] = cc[(size_t)((3 + i) * 8 + k) * kV5Threads];
+          ref_grad8_pair(t, sy, sz, Frm[i], Frp[i]);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) t[k] = cc[(size_t)((6 + i) * 8 + k) * kV5Threads];
+          ref_grad8_pair(t, sy, sz, Gvm[i], Gvp[i]);
+        }
+        double Qm[3][3], Qp[3][3];
+        point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
+        point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
+        accumulate_pair(Qm, Qp, sy, sz, syz, R);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) col[(size_t)(i * 8 + k) * kV5Threads] = R[i][k];
+    }
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(THIN));
+    have_prev = true;
+    prev_valid = valid;
   }
 }
 
@@ -1681,16 +1895,17 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_tiled(const double* __restri
 
 }  // namespace
 
-template <int MINB, int STAGE, int GROUPED = 0, int WIDE = 0>
+template <int MINB, int STAGE, int GROUPED = 0, int WIDE = 0, int UNR = 1, int CPF = 0, int NDS = 0>
 static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st) {
-  constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * grouped_scatter_words<8, 3>() : 0)) * sizeof(double);
+  static_assert(!(NDS && GROUPED), "the grouped scatter has its own staging area");
+  constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * grouped_scatter_words<8, 3>() : 0)) * sizeof(double) + (NDS ? 2 * kBlock * sizeof(int4) : 0);
   static SmemOptIn configured;
   if (smem > 48 * 1024) {
-    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE>, smem, configured);
+    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, smem, configured);
     if (rc != TATVA_OK) return rc;
   }
-  k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y);
   return TATVA_OK;
 }
 
@@ -1713,17 +1928,33 @@ static int resident_grid(K kernel, size_t smem, int64_t n_elems, int (&cache)[64
   return TATVA_OK;
 }
 
-template <int MINB, int PF>
+template <int MINB, int PF, int DELAY = 0>
 static int launch_v4(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st) {
   constexpr size_t smem = (size_t)42 * kBlock * sizeof(double) + (size_t)2 * kBlock * sizeof(int4);
   static SmemOptIn configured;
   static int cache[64];
-  int rc = opt_in_smem(k_hex8_nh_hvp_v4<MINB, PF>, smem, configured);
+  int rc = opt_in_smem(k_hex8_nh_hvp_v4<MINB, PF, DELAY>, smem, configured);
   if (rc != TATVA_OK) return rc;
   int grid = 0;
-  if ((rc = resident_grid(k_hex8_nh_hvp_v4<MINB, PF>, smem, p->n_elems, cache, &grid)) != TATVA_OK) return rc;
-  k_hex8_nh_hvp_v4<MINB, PF><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  if ((rc = resident_grid(k_hex8_nh_hvp_v4<MINB, PF, DELAY>, smem, p->n_elems, cache, &grid)) != TATVA_OK) return rc;
+  k_hex8_nh_hvp_v4<MINB, PF, DELAY><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  return TATVA_OK;
+}
+
+template <int FAT, int THIN>
+static int launch_v5(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                     cudaStream_t st) {
+  constexpr size_t smem = (size_t)kV5Slots * kV5Threads * sizeof(double);  // 216 KB: one CTA per SM
+  static SmemOptIn configured;
+  int rc = opt_in_smem(k_hex8_nh_hvp_v5<FAT, THIN>, smem, configured);
+  if (rc != TATVA_OK) return rc;
+  int dev = 0, sms = 0;
+  TATVA_CUDA_TRY(cudaGetDevice(&dev));
+  TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t tiles = (p->n_elems + 127) / 128;
+  const int grid = (int)((tiles + 2) / 3 < sms ? (tiles + 2) / 3 : sms);
+  k_hex8_nh_hvp_v5<FAT, THIN><<<grid, kV5Threads, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
   return TATVA_OK;
 }
 
@@ -1739,7 +1970,7 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 9: rc = launch_rolled<0, 2, 2>(p, mu, lmbda, u, v, y, st); break;
     case 15: rc = launch_rolled<0, 2, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
     case 17: rc = launch_rolled<1, 3, 0, 1, 1>(p, mu, lmbda, u, v, y, st); break;
-    case 22: k_hex8_nh_hvp_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
+    case 22: rc = launch_v3<2, 0>(p, mu, lmbda, u, v, y, st); break;
     case 23: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;
     case 28: rc = launch_v3<2, 1, 0, 1>(p, mu, lmbda, u, v, y, st); break;  // whole-row 16-byte gather (slower)
     case 27: rc = launch_v3<2, 1, 1>(p, mu, lmbda, u, v, y, st); break;
@@ -1748,9 +1979,24 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 31: rc = launch_v4<2, 0>(p, mu, lmbda, u, v, y, st); break;  // persistent, no prefetch
     case 32: rc = launch_v4<2, 1>(p, mu, lmbda, u, v, y, st); break;  // persistent + L2 prefetch of the next rows
     case 33: rc = launch_v4<2, 2>(p, mu, lmbda, u, v, y, st); break;  // persistent + L1 prefetch
+    case 34: rc = launch_v4<2, 0, 2000>(p, mu, lmbda, u, v, y, st); break;  // persistent, second CTA of each SM out of phase
+    case 35: rc = launch_v4<2, 0, 3500>(p, mu, lmbda, u, v, y, st); break;
+    case 36: rc = launch_v4<2, 0, 5000>(p, mu, lmbda, u, v, y, st); break;
+    case 37: rc = launch_v3<2, 1, 0, 0, 2>(p, mu, lmbda, u, v, y, st); break;  // two tx pairs per loop body
+    case 43: rc = launch_v3<3, 2, 0, 0, 1, 0, 1>(p, mu, lmbda, u, v, y, st); break;  // 3 CTAs / SM, all staged, node ids parked
+    case 44: rc = launch_v3<2, 1, 0, 0, 1, 0, 1>(p, mu, lmbda, u, v, y, st); break;  // 2 CTAs / SM, X and v staged, node ids parked
+    case 45: rc = launch_v3<3, 1>(p, mu, lmbda, u, v, y, st); break;  // 3 CTAs / SM, X and v staged
+    case 46: rc = launch_v3<4, 2>(p, mu, lmbda, u, v, y, st); break;  // 4 CTAs / SM (128 registers)
+    case 38: rc = launch_v3<2, 1, 0, 0, 1, 296>(p, mu, lmbda, u, v, y, st); break;  // + connectivity prefetch one wave ahead
+    case 39: rc = launch_v3<2, 1, 0, 0, 1, 592>(p, mu, lmbda, u, v, y, st); break;  // two waves ahead
+    case 40: rc = launch_v5<216, 72>(p, mu, lmbda, u, v, y, st); break;  // rotating warpgroups (setmaxnreg)
+    case 41: rc = launch_v5<208, 88>(p, mu, lmbda, u, v, y, st); break;
+    case 42: rc = launch_v5<200, 104>(p, mu, lmbda, u, v, y, st); break;
     case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 20: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
-    default: rc = launch_v3<2, 1>(p, mu, lmbda, u, v, y, st); break;  // pair-sharing, X and v staged
+    // r02 default: pair kernel, all three modal fields staged, 168 registers -> 3 CTAs (12 warps) per SM: 0.397 ms at 128^3
+    // (r01 default, variant 23: X and v staged, 244 registers, 2 CTAs per SM: 0.414 ms with the r02 loop body)
+    default: rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st); break;
   }
   if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();
@@ -1765,7 +2011,7 @@ int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const
     const int rc = opt_in_smem(k_hex8_nh_hvp_v3<2, 1, 0, true>, smem, configured);
     if (rc != TATVA_OK) return rc;
   }
-  k_hex8_nh_hvp_v3<2, 1, 0, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v_red, y_red, map);
+  k_hex8_nh_hvp_v3<2, 1, 0, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v_red, y_red, map);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
@@ -1774,12 +2020,14 @@ int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const d
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   // variants (tatva_plan_set_variant), r01 at 128^3: 2 = first modal kernel, 8 rolled points (0.422 ms); 3 = pair
   // kernel, all in registers (0.382); 4 = pair kernel, modal coordinates staged, 2 CTAs / SM (0.394);
-  // default = staged, 3 CTAs / SM (0.369)
+  // 5 = staged, 3 CTAs / SM (0.369, the r01 default).  r02, with the branch-free log / reciprocal: registers 0.3205,
+  // staged at 3 CTAs 0.345 -> default = all in registers, 2 CTAs / SM
   switch (p->variant) {
     case 2: k_hex8_nh_residual_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
     case 3: k_hex8_nh_residual_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
     case 4: k_hex8_nh_residual_v3<2, 1><<<grid_for(p->n_elems), kBlock, 21 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
-    default: k_hex8_nh_residual_v3<3, 1><<<grid_for(p->n_elems), kBlock, 21 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
+    case 5: k_hex8_nh_residual_v3<3, 1><<<grid_for(p->n_elems), kBlock, 21 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
+    default: k_hex8_nh_residual_v3<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, y); break;
   }
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
