@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 2  /* bumped on every signature change; the Python loader refuses a mismatch */
+#define TATVA_B200_ABI_VERSION 3  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */
@@ -162,6 +162,13 @@ int tatva_hessian_diag(tatva_plan_t* plan, int material, const double* params, i
 int tatva_hvp_lifted(tatva_plan_t* plan, int material, const double* params, int n_params,
                      const double* d_u_full, const double* d_v_red, const int32_t* d_dof_map,
                      int64_t n_red, double* d_y_red, tatva_stream_t stream);
+/* tatva_hvp_lifted that also leaves v_red . y_red in d_scalars[slot] (CG: p.Ap for free — the Hex8 x neo-Hookean kernel
+ * sums it element by element before the scatter; other pairs add a two-pass dot).  roll != 0: d_scalars[0] <- d_scalars[2]
+ * in the same final-sum kernel.  zero_y = 0: y_red is already zero (see tatva_cg_after_dot).  d_partials >= 1184 doubles. */
+int tatva_hvp_lifted_dot(tatva_plan_t* plan, int material, const double* params, int n_params,
+                         const double* d_u_full, const double* d_v_red, const int32_t* d_dof_map, int64_t n_red,
+                         double* d_y_red, int zero_y, double* d_partials, double* d_scalars, int slot, int roll,
+                         tatva_stream_t stream);
 
 /* Element sub-range variants: only elements [elem_begin, elem_begin + elem_count) contribute, and the
  * output is zeroed first only if zero_out != 0.  They let the caller run the elements that touch ghost
@@ -246,6 +253,18 @@ int tatva_cg_dot(const double* d_a, const double* d_b, int64_t n, double* d_part
                  double* d_scalars, int slot, tatva_stream_t stream);
 int tatva_cg_after_matvec(double* d_x, double* d_r, double* d_p, const double* d_Ap, int64_t n,
                           double* d_partials, double* d_scalars, tatva_stream_t stream);
+/* Leaner iteration (r02): the operator application itself delivers p.Ap (tatva_hvp_lifted_dot) and the direction pass
+ * clears the next application's output, so one iteration is  [tatva_hvp_lifted_dot(roll = 1)] + tatva_cg_after_dot:
+ * 6 launches and 9 vector passes instead of 8 + memset and 11.  Same arithmetic and summation orders for x, r, p; p.Ap is
+ * summed element by element instead of entry by entry (agrees to rounding).  d_minv / d_zero may be NULL.              */
+int tatva_cg_after_dot(double* d_x, double* d_r, double* d_p, const double* d_Ap, const double* d_minv, double* d_zero,
+                       const int32_t* d_fixed_map, int64_t n, double* d_partials, double* d_scalars,
+                       tatva_stream_t stream);
+/* d_fixed_map (may be NULL): n int32, < 0 marks a Fixed DOF (Lifter.dof_map) — the iteration then runs on FULL-size
+ * vectors with those rows of r held at zero, around the unconstrained kernel:                                          */
+int tatva_hvp_dot(tatva_plan_t* plan, int material, const double* params, int n_params, const double* d_u,
+                  const double* d_v, double* d_y, int zero_y, int fuse_dot, double* d_partials, double* d_scalars,
+                  int slot, int roll, tatva_stream_t stream);
 /* Jacobi-preconditioned CG, M = diag(H) from tatva_hessian_diag; z = M^-1 r is folded into the vector kernels and
  * never stored.  d_scalars[0] = r.z, [2] = next r.z, [4] = r.r of the new residual; d_partials >= 2 * 1184 doubles.
  *   tatva_pcg_reciprocal:    minv = 1 / diag (1 where diag is not a positive finite number)

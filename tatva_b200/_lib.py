@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libtatva_b200.so")
 TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
 PLAN_CACHE_WEIGHTS = 1
-ABI_VERSION = 2  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
+ABI_VERSION = 3  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
@@ -77,6 +77,9 @@ SIGNATURES = {
     "tatva_probe_element": (C.c_int, [C.c_int, C.c_int, c_f64p, C.c_int, C.c_int, c_f64p, c_f64p, c_f64p, c_f64p]),
     "tatva_probe_hex8_nh_modal": (C.c_int, [C.c_int, c_f64p, c_f64p, c_f64p, C.c_double, C.c_double, c_f64p]),
     "tatva_probe_tet4_nh_ref": (C.c_int, [C.c_int, c_f64p, c_f64p, c_f64p, C.c_double, C.c_double, c_f64p]),
+    "tatva_hvp_lifted_dot": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
+    "tatva_cg_after_dot": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "tatva_hvp_dot": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
     "tatva_fp64_peak_tflops": (C.c_int, [c_f64p, vp]),
 }
 

@@ -626,8 +626,10 @@ inline int grid_for(int64_t n, int block = kBlock) { return (int)((n + block - 1
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st);
 int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v_red,
-                             const int32_t* map, double* y_red, cudaStream_t st);
+                             const int32_t* map, double* y_red, cudaStream_t st, double* dot_partials = nullptr);
 
+int hex8_nh_hvp_modal_dot(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                          double* dot_partials, cudaStream_t st);
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st);
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);

@@ -1308,6 +1308,32 @@ __global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, doubl
   acc = block_sum(acc);
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
+// k_cg_update / k_pcg_update on FULL-size vectors with Dirichlet rows masked out: map[i] < 0 marks a Fixed DOF (its
+// residual entry stays 0, so p and x stay 0 there).  minv may be NULL.
+__global__ void __launch_bounds__(256) k_cg_update_masked(double* __restrict__ x, double* __restrict__ r,
+                                                          const double* __restrict__ p, const double* __restrict__ Ap,
+                                                          const double* __restrict__ minv, const int32_t* __restrict__ map,
+                                                          int64_t n, const double* __restrict__ s, double* __restrict__ part) {
+  const double alpha = s[0] / s[1];
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, __ldg(p + i), x[i]);
+    double ri = fma(-alpha, __ldg(Ap + i), r[i]);
+    if (__ldg(map + i) < 0) ri = 0.0;
+    r[i] = ri;
+    rr = fma(ri, ri, rr);
+    if (minv) rz = fma(ri * __ldg(minv + i), ri, rz);
+  }
+  rr = block_sum(rr);
+  if (minv) {
+    __syncthreads();
+    rz = block_sum(rz);
+  }
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = minv ? rz : rr;
+    if (minv) part[gridDim.x + blockIdx.x] = rr;
+  }
+}
 // beta = s[2] / s[0];  p = r + beta p;  then s[0] <- s[2] (done by CTA 0 after its own work; readers use the
 // value loaded at entry)
 __global__ void __launch_bounds__(256) k_cg_direction(double* __restrict__ p, const double* __restrict__ r, int64_t n,
@@ -1317,6 +1343,32 @@ __global__ void __launch_bounds__(256) k_cg_direction(double* __restrict__ p, co
     p[i] = fma(beta, p[i], __ldg(r + i));
 }
 __global__ void k_cg_roll(double* __restrict__ s) { s[0] = s[2]; }
+// s[slot] = sum(part[0..nblocks)) in a fixed order (any nblocks, one CTA of 1024 threads); roll: s[0] <- s[2] first
+__global__ void __launch_bounds__(1024) k_cg_finish_roll(const double* __restrict__ part, int nblocks, double* __restrict__ s,
+                                                         int slot, int roll) {
+  double t = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) t += part[b];
+  t = block_sum(t);
+  if (threadIdx.x == 0) {
+    if (roll) s[0] = s[2];
+    s[slot] = t;
+  }
+}
+// beta = s[2] / s[0];  p = r + beta p  walking the vectors BACKWARDS (the tail of r, written last by k_cg_update, is
+// still in L2), and zero = 0 written alongside (the next operator application accumulates into it: no memset launch).
+// s[0] is NOT rolled here: the final-sum kernel of the next p.Ap does it (k_cg_finish_roll).
+__global__ void __launch_bounds__(256) k_cg_direction_zero(double* __restrict__ p, const double* __restrict__ r,
+                                                           const double* __restrict__ minv, int64_t n,
+                                                           const double* __restrict__ s, double* __restrict__ zero) {
+  const double beta = s[2] / s[0];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const int64_t i = n - 1 - j;
+    const double z = minv ? __ldg(r + i) * __ldg(minv + i) : __ldg(r + i);
+    p[i] = fma(beta, p[i], z);
+    if (zero) zero[i] = 0.0;
+  }
+}
 
 // Jacobi-preconditioned variants: z = minv * r is never stored.  s[0] = r.z (current), s[2] = r.z (next), s[4] = r.r.
 __global__ void __launch_bounds__(256) k_pcg_update(double* __restrict__ x, double* __restrict__ r,
@@ -1472,7 +1524,7 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->tile_nodes = nullptr;
   p->tile_conn = nullptr;
   p->tile_max_unique = 0;
-  p->scratch_len = (int64_t)grid_for(n_elems) > 1024 * 64 ? (int64_t)grid_for(n_elems) : 1024 * 64;
+  p->scratch_len = (int64_t)grid_for(n_elems) * (kBlock / 32) > 1024 * 64 ? (int64_t)grid_for(n_elems) * (kBlock / 32) : 1024 * 64;
   cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
   if (e != cudaSuccess) { delete p; return (int)e; }
   if (flags & TATVA_PLAN_CACHE_WEIGHTS) {
@@ -1873,6 +1925,66 @@ int tatva_hvp_lifted(tatva_plan_t* p, int material, const double* params, int n_
   });
 }
 
+// The same with v_red . y_red computed on the way (CG: p . A p without a pass over the two vectors): the Hex8 x
+// neo-Hookean kernel sums v_e . y_e per element before the scatter (one partial per CTA in the plan's scratch, then a
+// fixed-order final sum); every other (element, law) pair runs the kernel above followed by a two-pass dot.  The scalar
+// lands in d_scalars[slot]; with roll != 0 the final-sum kernel also copies d_scalars[2] to d_scalars[0] (the CG's
+// "r.r <- next r.r" step of the previous iteration).  zero_y = 0 skips the memset (the caller's previous vector pass
+// left y zeroed, see tatva_cg_direction_zero).
+int tatva_hvp_lifted_dot(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u_full,
+                         const double* d_v_red, const int32_t* d_dof_map, int64_t n_red, double* d_y_red, int zero_y,
+                         double* d_partials, double* d_scalars, int slot, int roll, tatva_stream_t stream) {
+  if (!p || !params || !d_u_full || !d_v_red || !d_dof_map || !d_y_red || !d_scalars || !d_partials || n_red <= 0 || slot < 0 || slot > 7) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y_red, 0, sizeof(double) * n_red, st));
+  if (p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
+    const int grid = grid_for(p->n_elems) * (kBlock / 32);  // one partial per warp
+    if (grid > p->scratch_len) return TATVA_E_INVALID;
+    const int rc = hex8_nh_hvp_modal_lifted(p, params[0], params[1], d_u_full, d_v_red, d_dof_map, d_y_red, st, p->scratch);
+    if (rc != TATVA_OK) return rc;
+    k_cg_finish_roll<<<1, 1024, 0, st>>>(p->scratch, grid, d_scalars, slot, roll);
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
+  tatva_plan q = *p;
+  q.zero_output = 0;
+  const int rc = tatva_hvp_lifted(&q, material, params, n_params, d_u_full, d_v_red, d_dof_map, n_red, d_y_red, stream);
+  if (rc != TATVA_OK) return rc;
+  k_cg_dot<<<kCgBlocks, 256, 0, st>>>(d_v_red, d_y_red, n_red, d_partials);
+  k_cg_finish_roll<<<1, 1024, 0, st>>>(d_partials, kCgBlocks, d_scalars, slot, roll);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// Unconstrained counterpart of tatva_hvp_lifted_dot: y (+)= H(u) v and d_scalars[slot] = v . H v.  fuse_dot != 0 asks the
+// Hex8 x neo-Hookean kernel to sum v_e . y_e itself; otherwise (and for every other pair) a two-pass dot follows.
+int tatva_hvp_dot(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u, const double* d_v,
+                  double* d_y, int zero_y, int fuse_dot, double* d_partials, double* d_scalars, int slot, int roll,
+                  tatva_stream_t stream) {
+  if (!p || !params || !d_u || !d_v || !d_y || !d_scalars || !d_partials || slot < 0 || slot > 7) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+  const int64_t n = p->n_nodes * dpn;
+  if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * n, st));
+  if (fuse_dot && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
+    const int grid = grid_for(p->n_elems) * (kBlock / 32);  // one partial per warp
+    if (grid > p->scratch_len) return TATVA_E_INVALID;
+    const int rc = hex8_nh_hvp_modal_dot(p, params[0], params[1], d_u, d_v, d_y, p->scratch, st);
+    if (rc != TATVA_OK) return rc;
+    k_cg_finish_roll<<<1, 1024, 0, st>>>(p->scratch, grid, d_scalars, slot, roll);
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
+  tatva_plan q = *p;
+  q.zero_output = 0;
+  const int rc = dispatch_fused<MODE_HVP>(&q, material, params, n_params, d_u, d_v, d_y, st);
+  if (rc != TATVA_OK) return rc;
+  k_cg_dot<<<kCgBlocks, 256, 0, st>>>(d_v, d_y, n, d_partials);
+  k_cg_finish_roll<<<1, 1024, 0, st>>>(d_partials, kCgBlocks, d_scalars, slot, roll);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
 }  // extern "C"
 
 // ---- host probe of the generic element body ---------------------------------------------------------
@@ -2242,6 +2354,26 @@ int tatva_cg_direction(double* d_p, const double* d_r, const double* d_minv, int
   if (d_minv) k_pcg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, d_minv, n, d_scalars);
   else k_cg_direction<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, n, d_scalars);
   k_cg_roll<<<1, 1, 0, st>>>(d_scalars);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// One CG iteration AFTER an operator application that already left p.Ap in d_scalars[1] (tatva_hvp_lifted_dot with
+// roll = 1): alpha = s0/s1; x += alpha p; r -= alpha Ap; s2 = r.r (and s4 with d_minv); beta = s2/s0; p = r + beta p (or
+// M^-1 r); d_zero (may be NULL) is cleared in the same pass for the next application.  s0 <- s2 is left to the next
+// tatva_hvp[_lifted]_dot(..., roll = 1).  d_fixed_map (may be NULL; n int32, < 0 = Fixed DOF, e.g. Lifter.dof_map) runs the
+// iteration on FULL-size vectors with the Dirichlet rows of r kept at zero, so that the unconstrained HVP kernel can be
+// used instead of the lifted one when a lifter holds only Fixed constraints.
+int tatva_cg_after_dot(double* d_x, double* d_r, double* d_p, const double* d_Ap, const double* d_minv, double* d_zero,
+                       const int32_t* d_fixed_map, int64_t n, double* d_partials, double* d_scalars, tatva_stream_t stream) {
+  if (!d_x || !d_r || !d_p || !d_Ap || !d_partials || !d_scalars || n <= 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_fixed_map) k_cg_update_masked<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, d_minv, d_fixed_map, n, d_scalars, d_partials);
+  else if (d_minv) k_pcg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, d_minv, n, d_scalars, d_partials);
+  else k_cg_update<<<kCgBlocks, 256, 0, st>>>(d_x, d_r, d_p, d_Ap, n, d_scalars, d_partials);
+  if (d_minv) k_cg_finish<<<1, 256, 0, st>>>(d_partials + kCgBlocks, kCgBlocks, d_scalars, 4);
+  k_cg_finish<<<1, 256, 0, st>>>(d_partials, kCgBlocks, d_scalars, 2);
+  k_cg_direction_zero<<<kCgBlocks, 256, 0, st>>>(d_p, d_r, d_minv, n, d_scalars, d_zero);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

@@ -809,15 +809,17 @@ TATVA_D void wide_row(const double* __restrict__ src, int64_t node, double (&dst
 // WIDE: node rows are fetched whole (one double2 + one double each) array by array, instead of component by component
 // with 8-byte loads: 48 instead of 72 gather instructions per element, but ~400 more integer / select instructions.
 // Measured slower (0.490 vs 0.453 ms, variant 28), so the default stays component-wise.
-template <int MINB, int STAGE, int GROUPED = 0, bool LIFT = false, int WIDE = 0, int UNR = 1, int CPF = 0, int NDS = 0>
+template <int MINB, int STAGE, int GROUPED = 0, bool LIFT = false, int WIDE = 0, int UNR = 1, int CPF = 0, int NDS = 0, int DOT = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_v3(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                      double lmbda, const double* __restrict__ u, const double* __restrict__ v,
-                     double* __restrict__ y, const int32_t* __restrict__ map = nullptr) {
+                     double* __restrict__ y, const int32_t* __restrict__ map = nullptr,
+                     double* __restrict__ dot_partials = nullptr) {
   static_assert(!(LIFT && GROUPED), "the lifted scatter is per DOF");
+  static_assert(!DOT || (STAGE >= 1 && !GROUPED), "the fused v.Hv needs the modal direction in shared memory");
   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = e0 < E;
-  if (!GROUPED && !valid) return;
+  if (!GROUPED && !DOT && !valid) return;
   const int64_t e = valid ? e0 : E - 1;  // GROUPED: out-of-range lanes redo the last element and drop the result
   int nd[8];
   {
@@ -1027,10 +1029,19 @@ __global__ void __launch_bounds__(kBlock, MINB)
       if (node >= 0) atomicAdd(y + (int64_t)node * 3 + (r % 3), wsm[j * 25 + r]);
     }
   } else {
+    // DOT: v . (H v) summed element by element on the way to the scatter: the 8-point transforms are transposes of each
+    // other, so sum_n v_e[n] y_e[n] = sum_k modal(v)[k] R[k].  With a Lifter this is v_red . y_red exactly (a Fixed DOF has
+    // v = 0, a Periodic image reads its master's entry and adds into it).  One partial per warp, fixed reduction order.
+    double dot = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
+      if constexpr (DOT) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) dot = fma(sv0[(i * 7 + k) * kBlock], R[i][k], dot);
+      }
       double f[8];
       from_modal_raw(R[i], f);
+      if (DOT && !valid) continue;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         if constexpr (LIFT) {
@@ -1040,6 +1051,12 @@ __global__ void __launch_bounds__(kBlock, MINB)
           atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
         }
       }
+    }
+    if constexpr (DOT) {
+      if (!valid) dot = 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_down_sync(0xffffffffu, dot, o);
+      if ((threadIdx.x & 31) == 0) dot_partials[(size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)] = dot;
     }
   }
 }
@@ -2003,15 +2020,34 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
   return TATVA_OK;
 }
 
-int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v_red,
-                             const int32_t* map, double* y_red, cudaStream_t st) {
-  constexpr size_t smem = (size_t)42 * kBlock * sizeof(double);
+// y += H(u) v (y is NOT zeroed here) with the per-CTA partial sums of v . H v written to dot_partials (see DOT in
+// k_hex8_nh_hvp_v3): the CG's p . A p for free.
+int hex8_nh_hvp_modal_dot(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
+                          double* dot_partials, cudaStream_t st) {
+  constexpr size_t smem = (size_t)63 * kBlock * sizeof(double);
   static SmemOptIn configured;
-  {
-    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<2, 1, 0, true>, smem, configured);
+  const int rc = opt_in_smem(k_hex8_nh_hvp_v3<3, 2, 0, false, 0, 1, 0, 0, 1>, smem, configured);
+  if (rc != TATVA_OK) return rc;
+  k_hex8_nh_hvp_v3<3, 2, 0, false, 0, 1, 0, 0, 1><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y, nullptr, dot_partials);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v_red,
+                             const int32_t* map, double* y_red, cudaStream_t st, double* dot_partials) {
+  // all three modal fields staged, 3 CTAs per SM (the r02 default of the unconstrained kernel)
+  constexpr size_t smem = (size_t)63 * kBlock * sizeof(double);
+  static SmemOptIn configured[2];
+  const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+  if (dot_partials) {
+    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<3, 2, 0, true, 0, 1, 0, 0, 1>, smem, configured[1]);
     if (rc != TATVA_OK) return rc;
+    k_hex8_nh_hvp_v3<3, 2, 0, true, 0, 1, 0, 0, 1><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu_s, lm_s, u, v_red, y_red, map, dot_partials);
+  } else {
+    const int rc = opt_in_smem(k_hex8_nh_hvp_v3<3, 2, 0, true>, smem, configured[0]);
+    if (rc != TATVA_OK) return rc;
+    k_hex8_nh_hvp_v3<3, 2, 0, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu_s, lm_s, u, v_red, y_red, map);
   }
-  k_hex8_nh_hvp_v3<2, 1, 0, true><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v_red, y_red, map);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

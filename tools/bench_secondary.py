@@ -160,6 +160,36 @@ if want("cg"):
         ms = a0.elapsed_time(a1) / info["iterations"]
         report(f"cg_iteration_hex8_128_{'graph' if graph else 'eager'}{tag}", ms, 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 11 * n, n, "DOF", iterations=info["iterations"], residual_norm=info["residual_norm"])
 
+    # r02: p.Ap summed inside the HVP kernel, direction pass clears Ap (no memset), 6 launches per iteration
+    x_ref = x.clone()
+    cgf = ConjugateGradient(red.matvec, n, "cuda", use_graph=True, matvec_dot=red.matvec_dot)
+    cgf.solve(b, tol=0.0, maxiter=20, check_every=20)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    xf, info = cgf.solve(b, tol=0.0, maxiter=200, check_every=50)
+    a1.record()
+    torch.cuda.synchronize()
+    report("cg_iteration_hex8_128_graph_fused_dot", a0.elapsed_time(a1) / info["iterations"], 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 9 * n, n, "DOF", iterations=info["iterations"],
+           residual_norm=info["residual_norm"], iterate_rel_diff_vs_unfused_after_200=float((xf - x_ref).norm() / x_ref.norm()))
+    pcgf = ConjugateGradient(red.matvec, n, "cuda", use_graph=True, jacobi=True, matvec_dot=red.matvec_dot)
+    # r02: Fixed-only lifter -> full-size vectors around the UNCONSTRAINED kernel, Dirichlet rows masked in the update pass
+    from tatva_b200.solver import MaskedOperator
+    for fuse in (False, True):
+        mo = MaskedOperator(op, mat, lifter, fuse_dot=fuse)
+        mo.set_state(lifter.reduce(torch.as_tensor(0.02 * u_.ravel(), device="cuda")))
+        cgm = mo.solver(use_graph=True)
+        bf = mo.expand(b)
+        cgm.solve(bf, tol=0.0, maxiter=20, check_every=20)
+        torch.cuda.synchronize()
+        a0.record()
+        xm, info = cgm.solve(bf, tol=0.0, maxiter=200, check_every=50)
+        a1.record()
+        torch.cuda.synchronize()
+        report(f"cg_iteration_hex8_128_graph_masked_full_space{'_kernel_dot' if fuse else ''}", a0.elapsed_time(a1) / info["iterations"], 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * (11 - 2 * fuse) * c.size + 4 * c.size, n, "DOF",
+               iterations=info["iterations"], iterate_rel_diff_vs_reduced_after_200=float((mo.restrict(xm) - x_ref).norm() / x_ref.norm()))
+        del cgm, mo
+
     # Jacobi: cost of the diagonal kernel, of one preconditioned iteration, and iterations to 1e-8 with / without
     diag = torch.empty(n, dtype=torch.float64, device="cuda")
     report("hex8_nh_hessian_diag_c3", timeit(lambda: red.diagonal(out=diag), reps=5, warm=2), 8 * 9 * c.shape[0] + 32 * el.shape[0], n, "DOF")
@@ -173,8 +203,16 @@ if want("cg"):
     a1.record()
     torch.cuda.synchronize()
     report("pcg_jacobi_iteration_hex8_128_graph", a0.elapsed_time(a1) / info["iterations"], 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 13 * n, n, "DOF", iterations=info["iterations"])
+    pcgf.set_diagonal(diag)
+    pcgf.solve(b, tol=0.0, maxiter=20, check_every=20)
+    torch.cuda.synchronize()
+    a0.record()
+    x, info = pcgf.solve(b, tol=0.0, maxiter=200, check_every=50)
+    a1.record()
+    torch.cuda.synchronize()
+    report("pcg_jacobi_iteration_hex8_128_graph_fused_dot", a0.elapsed_time(a1) / info["iterations"], 8 * (12 * c.shape[0]) + 32 * el.shape[0] + 8 * 11 * n, n, "DOF", iterations=info["iterations"])
     its = {}
-    for name, solver in (("cg", cg), ("pcg_jacobi", pcg)):
+    for name, solver in (("cg", cg), ("pcg_jacobi", pcg), ("cg_fused_dot", cgf)):
         t0 = time.perf_counter()
         x, info = solver.solve(b, tol=1e-8, maxiter=5000, check_every=25)
         torch.cuda.synchronize()
