@@ -80,6 +80,16 @@ int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, 
  *   CSR assembly             2 = full assembly also where the symmetric entry point was called
  * Every variant computes the same result to rounding; unknown values fall back to the default.                  */
 int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
+
+/* User-supplied quadrature rule — Element(quad_points, quad_weights), tatva/element/base.py:37-51.  `points` is
+ * (nq, reference dimension) row-major HOST memory, `weights` (nq) HOST memory, nq <= 64; nq = 0 restores the element's
+ * default rule.  Every Operator building block (weights, grad, eval, integrate and their adjoints) and the fused
+ * energy / residual / HVP / lifted HVP / Hessian diagonal / CSR assembly then run the GENERIC kernels with the rule in
+ * constant memory (the modal Hex8 and reference-space Tet4 kernels are default-rule only).  One rule slot per process
+ * and device: plans with different custom rules must not launch concurrently on different streams.
+ * tatva_op_interpolate returns TATVA_E_UNSUPPORTED with a custom rule.                                              */
+int tatva_plan_set_quadrature(tatva_plan_t* plan, int nq, const double* points, const double* weights,
+                              tatva_stream_t stream);
 /* Optional shared-memory staging tiles for gather-bound elements (Tet4 x neo-Hookean residual / HVP): tile t =
  * elements [128 t, 128 (t+1)); d_tile_nodes[d_tile_ptr[t] .. d_tile_ptr[t+1]) are its sorted unique nodes and
  * d_tile_conn (n_elems, npe) uint16 its connectivity in tile-local indices (tatva_host_build_tiles).  The CTA

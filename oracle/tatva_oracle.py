@@ -87,8 +87,50 @@ def reference_nodes(kind: str) -> np.ndarray:
     raise ValueError(kind)
 
 
+_RULE_OVERRIDE: dict = {}
+
+
+class custom_rule:
+    """Context manager: run the oracle with a user quadrature rule for `kind`, as Element(quad_points, quad_weights)
+    does in the reference (element/base.py:37-51): `with custom_rule("hex8", points, weights): ...`."""
+
+    def __init__(self, kind, points, weights):
+        self.kind, self.rule = kind, (np.asarray(points, dtype=np.float64), np.asarray(weights, dtype=np.float64))
+
+    def __enter__(self):
+        self.prev = _RULE_OVERRIDE.get(self.kind)
+        _RULE_OVERRIDE[self.kind] = self.rule
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is None:
+            _RULE_OVERRIDE.pop(self.kind, None)
+        else:
+            _RULE_OVERRIDE[self.kind] = self.prev
+        return False
+
+
+def gauss_rule(kind: str, order: int) -> tuple[np.ndarray, np.ndarray]:
+    """Tensor Gauss-Legendre rules with `order` points per direction for hex8 / quad4 (x fastest, like the reference's
+    defaults), and the 4-point degree-2 rule for tet4 (order = 2): the rules of the custom-quadrature tests."""
+    if kind in ("hex8", "quad4"):
+        x, w = np.polynomial.legendre.leggauss(order)
+        if kind == "quad4":
+            return np.array([[x[j], x[i]] for i in range(order) for j in range(order)]), np.array([w[i] * w[j] for i in range(order) for j in range(order)])
+        idx = [(i, j, k) for k in range(order) for j in range(order) for i in range(order)]
+        return np.array([[x[i], x[j], x[k]] for i, j, k in idx]), np.array([w[i] * w[j] * w[k] for i, j, k in idx])
+    if kind == "tet4" and order == 2:
+        a, b = 0.58541019662496845446, 0.13819660112501051518
+        return np.array([[b, b, b], [a, b, b], [b, a, b], [b, b, a]]), np.full(4, 1.0 / 24)
+    if kind == "tri3" and order == 2:
+        return np.array([[1.0 / 6, 1.0 / 6], [2.0 / 3, 1.0 / 6], [1.0 / 6, 2.0 / 3]]), np.full(3, 1.0 / 6)
+    raise ValueError((kind, order))
+
+
 def quad_rule(kind: str) -> tuple[np.ndarray, np.ndarray]:
-    """Default quadrature (points (Q,dim), weights (Q,))."""
+    """Default quadrature (points (Q,dim), weights (Q,)), or the rule installed by `custom_rule`."""
+    if kind in _RULE_OVERRIDE:
+        return _RULE_OVERRIDE[kind]
     if kind == "tri3":  # element/base.py:252-255
         return np.array([[1.0 / 3, 1.0 / 3]]), np.array([1.0 / 2])
     if kind == "tet4":  # element/base.py:457-460

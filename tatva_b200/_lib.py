@@ -31,6 +31,7 @@ SIGNATURES = {
     "tatva_plan_destroy": (C.c_int, [vp]),
     "tatva_plan_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_i64p, c_i64p]),
     "tatva_plan_set_variant": (C.c_int, [vp, C.c_int]),
+    "tatva_plan_set_quadrature": (C.c_int, [vp, C.c_int, c_f64p, c_f64p, vp]),
     "tatva_plan_set_tiles": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "tatva_plan_set_point_grid": (C.c_int, [vp, C.c_int, C.c_int, c_f64p, c_f64p, vp, vp]),
     "tatva_op_grad": (C.c_int, [vp, vp, C.c_int, vp, vp]),

@@ -32,12 +32,26 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libtatva_b200.so")
 
 
+STAMP = LIB + ".stamp"
+
+
+def _source_hash() -> str:
+    """Content hash of every source, header and flag that goes into the library.  File times do not survive the copy to
+    the GPU box, so staleness is decided by content: the stamp written next to the library travels with it."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))):
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -81,6 +95,8 @@ def _build_locked(verbose: bool, objdir: str) -> str:
     link = [nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
     subprocess.run(link, check=True)
     os.replace(tmp, LIB)
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     return LIB
 
 

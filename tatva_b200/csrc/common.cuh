@@ -21,6 +21,10 @@ constexpr int kBlock = 128;  // threads per CTA for element-per-thread kernels
 
 struct Tri3 {  // tatva/element/base.py:245-265
   static constexpr int dim = 2, gdim = 2, npe = 3, nq = 1, kind = TATVA_TRI3;
+  static constexpr int max_nq = nq, rdim = 2;
+  TATVA_HD static constexpr int num_q() { return nq; }
+  TATVA_HD static void N_at(const double* xi, double (&n)[npe]) { n[0] = 1.0 - xi[0] - xi[1]; n[1] = xi[0]; n[2] = xi[1]; }
+  TATVA_HD static void dNdr_at(const double*, double (&d)[dim][npe]) { dNdr(0, d); }
   TATVA_HD static double weight(int) { return 0.5; }
   TATVA_HD static void N(int, double (&n)[npe]) {
     n[0] = 1.0 - 1.0 / 3 - 1.0 / 3;
@@ -35,6 +39,10 @@ struct Tri3 {  // tatva/element/base.py:245-265
 
 struct Tet4 {  // tatva/element/base.py:448-472
   static constexpr int dim = 3, gdim = 3, npe = 4, nq = 1, kind = TATVA_TET4;
+  static constexpr int max_nq = nq, rdim = 3;
+  TATVA_HD static constexpr int num_q() { return nq; }
+  TATVA_HD static void N_at(const double* xi, double (&n)[npe]) { n[0] = 1.0 - xi[0] - xi[1] - xi[2]; n[1] = xi[0]; n[2] = xi[1]; n[3] = xi[2]; }
+  TATVA_HD static void dNdr_at(const double*, double (&d)[dim][npe]) { dNdr(0, d); }
   TATVA_HD static double weight(int) { return 1.0 / 6; }
   TATVA_HD static void N(int, double (&n)[npe]) {
     n[0] = 1.0 - 0.25 - 0.25 - 0.25;
@@ -54,6 +62,8 @@ struct Tet4 {  // tatva/element/base.py:448-472
 
 struct Hex8 {  // tatva/element/base.py:475-568
   static constexpr int dim = 3, gdim = 3, npe = 8, nq = 8, kind = TATVA_HEX8;
+  static constexpr int max_nq = nq, rdim = 3;
+  TATVA_HD static constexpr int num_q() { return nq; }
   // sign of reference node n along axis d (bottom face CCW, then top; :478-491); the 2x2x2
   // Gauss points are a * the same table (:493-513), all weights 1.
   TATVA_HD static constexpr double sgn(int n, int d) {
@@ -80,10 +90,25 @@ struct Hex8 {  // tatva/element/base.py:475-568
       d[2][k] = 0.125 * sgn(k, 2) * fx * fy;
     }
   }
+  TATVA_HD static void N_at(const double* xi, double (&n)[npe]) {  // :515-529 at an arbitrary point
+#pragma unroll
+    for (int k = 0; k < 8; ++k) n[k] = 0.125 * (1.0 + sgn(k, 0) * xi[0]) * (1.0 + sgn(k, 1) * xi[1]) * (1.0 + sgn(k, 2) * xi[2]);
+  }
+  TATVA_HD static void dNdr_at(const double* xi, double (&d)[dim][npe]) {  // :531-568
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double fx = 1.0 + sgn(k, 0) * xi[0], fy = 1.0 + sgn(k, 1) * xi[1], fz = 1.0 + sgn(k, 2) * xi[2];
+      d[0][k] = 0.125 * sgn(k, 0) * fy * fz;
+      d[1][k] = 0.125 * sgn(k, 1) * fx * fz;
+      d[2][k] = 0.125 * sgn(k, 2) * fx * fy;
+    }
+  }
 };
 
 struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:338-344)
   static constexpr int dim = 2, gdim = 2, npe = 4, nq = 4, kind = TATVA_QUAD4;
+  static constexpr int max_nq = nq, rdim = 2;
+  TATVA_HD static constexpr int num_q() { return nq; }
   TATVA_HD static constexpr double sgn(int n, int d) { return d == 0 ? ((n == 1 || n == 2) ? 1.0 : -1.0) : ((n >= 2) ? 1.0 : -1.0); }
   TATVA_HD static double weight(int) { return 1.0; }
   TATVA_HD static void xi(int q, double& r, double& s) {
@@ -91,40 +116,58 @@ struct Quad4 {  // tatva/element/base.py:331-366; 2x2 Gauss points, x fastest (:
     r = (q & 1) ? a : -a;
     s = (q & 2) ? a : -a;
   }
-  TATVA_HD static void N(int q, double (&n)[npe]) {
-    double r, s;
-    xi(q, r, s);
+  TATVA_HD static void N_at(const double* x, double (&n)[npe]) {
+    const double r = x[0], s = x[1];
 #pragma unroll
     for (int k = 0; k < 4; ++k) n[k] = 0.25 * (1.0 + sgn(k, 0) * r) * (1.0 + sgn(k, 1) * s);
   }
-  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
-    double r, s;
-    xi(q, r, s);
+  TATVA_HD static void dNdr_at(const double* x, double (&d)[dim][npe]) {
+    const double r = x[0], s = x[1];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       d[0][k] = 0.25 * sgn(k, 0) * (1.0 + sgn(k, 1) * s);
       d[1][k] = 0.25 * sgn(k, 1) * (1.0 + sgn(k, 0) * r);
     }
   }
+  TATVA_HD static void N(int q, double (&n)[npe]) {
+    double x[2];
+    xi(q, x[0], x[1]);
+    N_at(x, n);
+  }
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
+    double x[2];
+    xi(q, x[0], x[1]);
+    dNdr_at(x, d);
+  }
 };
 
 struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
   static constexpr int dim = 2, gdim = 2, npe = 6, nq = 3, kind = TATVA_TRI6;
+  static constexpr int max_nq = nq, rdim = 2;
+  TATVA_HD static constexpr int num_q() { return nq; }
   TATVA_HD static double weight(int) { return 1.0 / 6.0; }
   TATVA_HD static void xi(int q, double& r, double& s) {
     r = (q == 1) ? 2.0 / 3.0 : 1.0 / 6.0;
     s = (q == 2) ? 2.0 / 3.0 : 1.0 / 6.0;
   }
   TATVA_HD static void N(int q, double (&n)[npe]) {
-    double r, s;
-    xi(q, r, s);
+    double x[2];
+    xi(q, x[0], x[1]);
+    N_at(x, n);
+  }
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
+    double x[2];
+    xi(q, x[0], x[1]);
+    dNdr_at(x, d);
+  }
+  TATVA_HD static void N_at(const double* x, double (&n)[npe]) {
+    const double r = x[0], s = x[1];
     const double t = 1.0 - r - s;
     n[0] = t * (2 * t - 1); n[1] = r * (2 * r - 1); n[2] = s * (2 * s - 1);
     n[3] = 4 * r * t; n[4] = 4 * r * s; n[5] = 4 * s * t;
   }
-  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
-    double r, s;
-    xi(q, r, s);
+  TATVA_HD static void dNdr_at(const double* x, double (&d)[dim][npe]) {
+    const double r = x[0], s = x[1];
     const double t = 1.0 - r - s;
     d[0][0] = -(4 * t - 1); d[0][1] = 4 * r - 1; d[0][2] = 0.0; d[0][3] = 4 * (t - r); d[0][4] = 4 * s; d[0][5] = -4 * s;
     d[1][0] = -(4 * t - 1); d[1][1] = 0.0; d[1][2] = 4 * s - 1; d[1][3] = -4 * r; d[1][4] = 4 * r; d[1][5] = 4 * (t - s);
@@ -133,6 +176,8 @@ struct Tri6 {  // tatva/element/base.py:266-328; 3-point rule (:278-284)
 
 struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:384-393)
   static constexpr int dim = 2, gdim = 2, npe = 8, nq = 9, kind = TATVA_QUAD8;
+  static constexpr int max_nq = nq, rdim = 2;
+  TATVA_HD static constexpr int num_q() { return nq; }
   TATVA_HD static double w1(int i) { return i == 1 ? 8.0 / 9.0 : 5.0 / 9.0; }
   TATVA_HD static double x1(int i) { return i == 0 ? -0.77459666924148337704 : (i == 1 ? 0.0 : 0.77459666924148337704); }
   TATVA_HD static double weight(int q) { return w1(q / 3) * w1(q % 3); }
@@ -141,8 +186,17 @@ struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:
     s = x1(q / 3);
   }
   TATVA_HD static void N(int q, double (&n)[npe]) {
-    double r, s;
-    xi(q, r, s);
+    double x[2];
+    xi(q, x[0], x[1]);
+    N_at(x, n);
+  }
+  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
+    double x[2];
+    xi(q, x[0], x[1]);
+    dNdr_at(x, d);
+  }
+  TATVA_HD static void N_at(const double* x, double (&n)[npe]) {
+    const double r = x[0], s = x[1];
     n[0] = 0.25 * (1 - r) * (1 - s) * (-r - s - 1);
     n[1] = 0.25 * (1 + r) * (1 - s) * (r - s - 1);
     n[2] = 0.25 * (1 + r) * (1 + s) * (r + s - 1);
@@ -152,9 +206,8 @@ struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:
     n[6] = 0.5 * (1 - r * r) * (1 + s);
     n[7] = 0.5 * (1 - r) * (1 - s * s);
   }
-  TATVA_HD static void dNdr(int q, double (&d)[dim][npe]) {
-    double r, s;
-    xi(q, r, s);
+  TATVA_HD static void dNdr_at(const double* x, double (&d)[dim][npe]) {
+    const double r = x[0], s = x[1];
     d[0][0] = 0.25 * (-2 * r - s) * (s - 1); d[0][1] = 0.25 * (-2 * r + s) * (s - 1);
     d[0][2] = 0.25 * (2 * r + s) * (s + 1);  d[0][3] = 0.25 * (2 * r - s) * (s + 1);
     d[0][4] = r * (s - 1); d[0][5] = 0.5 - 0.5 * s * s; d[0][6] = -r * (s + 1); d[0][7] = 0.5 * s * s - 0.5;
@@ -168,6 +221,10 @@ struct Quad8 {  // tatva/element/base.py:366-445; 3x3 Gauss points, x fastest (:
 // number of gradient components (1: the derivative along the arc length).  tatva/element/base.py:144-242.
 struct Line2 {  // tatva/element/base.py:144-186
   static constexpr int dim = 2, gdim = 1, npe = 2, nq = 1, kind = TATVA_LINE2;
+  static constexpr int max_nq = nq, rdim = 1;
+  TATVA_HD static constexpr int num_q() { return nq; }
+  TATVA_HD static void N_at(const double* x, double (&n)[npe]) { n[0] = 0.5 * (1.0 - x[0]); n[1] = 0.5 * (1.0 + x[0]); }
+  TATVA_HD static void dNdr_at(const double*, double (&d)[gdim][npe]) { d[0][0] = -0.5; d[0][1] = 0.5; }
   TATVA_HD static double weight(int) { return 2.0; }
   TATVA_HD static void N(int, double (&n)[npe]) { n[0] = 0.5; n[1] = 0.5; }
   TATVA_HD static void dNdr(int, double (&d)[gdim][npe]) { d[0][0] = -0.5; d[0][1] = 0.5; }
@@ -175,6 +232,20 @@ struct Line2 {  // tatva/element/base.py:144-186
 
 struct Line3 {  // tatva/element/base.py:189-242; nodes (-1, 1, 0), 3-point Gauss
   static constexpr int dim = 2, gdim = 1, npe = 3, nq = 3, kind = TATVA_LINE3;
+  static constexpr int max_nq = nq, rdim = 1;
+  TATVA_HD static constexpr int num_q() { return nq; }
+  TATVA_HD static void N_at(const double* x, double (&n)[npe]) {
+    const double r = x[0];
+    n[0] = 0.5 * r * (r - 1.0);
+    n[1] = 0.5 * r * (r + 1.0);
+    n[2] = 1.0 - r * r;
+  }
+  TATVA_HD static void dNdr_at(const double* x, double (&d)[gdim][npe]) {
+    const double r = x[0];
+    d[0][0] = r - 0.5;
+    d[0][1] = r + 0.5;
+    d[0][2] = -2.0 * r;
+  }
   TATVA_HD static double xi(int q) { return (q - 1) * 0.77459666924148337704; }  // sqrt(3/5)
   TATVA_HD static double weight(int q) { return q == 1 ? 8.0 / 9 : 5.0 / 9; }
   TATVA_HD static void N(int q, double (&n)[npe]) {
@@ -189,6 +260,39 @@ struct Line3 {  // tatva/element/base.py:189-242; nodes (-1, 1, 0), 3-point Gaus
     d[0][1] = r + 0.5;
     d[0][2] = -2.0 * r;
   }
+};
+
+// ---------------------------------------------------------------------------------------------
+// User-supplied quadrature rule (Element(quad_points, quad_weights), tatva/element/base.py:37-51): the points and
+// weights sit in constant memory (installed stream-ordered before each launch from the plan's host copy) and the shape
+// functions are evaluated at them.  The generic kernels take it as `Custom<El>`; the specialised kernels (modal Hex8,
+// reference-space Tet4) carry their element's default rule and are not used with a custom one.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxQ = 64;
+struct QuadRule {
+  int nq;
+  double xi[kMaxQ][3];
+  double w[kMaxQ];
+};
+#ifdef __CUDACC__
+static __constant__ QuadRule c_rule;  // one copy per translation unit; generic.cu installs and uses its own
+#endif
+
+template <class B>
+struct Custom {
+  static constexpr int dim = B::dim, gdim = B::gdim, npe = B::npe, kind = B::kind, max_nq = kMaxQ, rdim = B::rdim;
+  static constexpr int nq = -1;  // not a compile-time constant: use num_q()
+#ifdef __CUDA_ARCH__
+  TATVA_HD static int num_q() { return c_rule.nq; }
+  TATVA_HD static double weight(int q) { return c_rule.w[q]; }
+  TATVA_HD static void N(int q, double (&n)[npe]) { B::N_at(c_rule.xi[q], n); }
+  TATVA_HD static void dNdr(int q, double (&d)[gdim][npe]) { B::dNdr_at(c_rule.xi[q], d); }
+#else  // the kernels run on the device only; the host twins exist so that __host__ __device__ templates compile
+  TATVA_HD static int num_q() { return 0; }
+  TATVA_HD static double weight(int) { return 0.0; }
+  TATVA_HD static void N(int, double (&)[npe]) {}
+  TATVA_HD static void dNdr(int, double (&)[gdim][npe]) {}
+#endif
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -586,6 +690,9 @@ struct tatva_plan {
   double grid_lo[2], grid_inv[2];  // bin = clamp(floor((x - lo) * inv), 0, n - 1)
   const int32_t* grid_ptr;         // caller-owned device views
   const int32_t* grid_elems;
+  // optional user quadrature rule (tatva_plan_set_quadrature): host copy, installed in constant memory before a launch
+  int custom;
+  tatva::QuadRule rule;
 };
 
 namespace tatva {

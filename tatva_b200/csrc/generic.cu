@@ -7,32 +7,9 @@
 #include <new>
 
 #include "common.cuh"
+#include "fused.cuh"
 
 namespace tatva {
-
-// ---- gather helpers ---------------------------------------------------------------------------
-
-template <class El>
-TATVA_D void load_conn(const int32_t* __restrict__ conn, int64_t e, int (&nd)[El::npe]) {
-  if constexpr (El::npe == 4) {
-    const int4 t = __ldg(reinterpret_cast<const int4*>(conn) + e);
-    nd[0] = t.x; nd[1] = t.y; nd[2] = t.z; nd[3] = t.w;
-  } else if constexpr (El::npe == 8) {
-    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
-    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
-    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
-    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
-  } else {
-#pragma unroll
-    for (int n = 0; n < El::npe; ++n) nd[n] = __ldg(conn + e * El::npe + n);
-  }
-}
-
-template <int NPE, int W>
-TATVA_D void gather_rows(const double* __restrict__ src, const int (&nd)[NPE], double (&dst)[NPE][W]) {
-#pragma unroll
-  for (int n = 0; n < NPE; ++n) load_row<W>(src, nd[n], dst[n]);
-}
 
 // ---- Operator building blocks (runtime number of value components) -----------------------------
 
@@ -46,7 +23,7 @@ __global__ void __launch_bounds__(kBlock) k_weights(const double* __restrict__ c
   double X[El::npe][El::dim];
   gather_rows(coords, nd, X);
 #pragma unroll
-  for (int q = 0; q < El::nq; ++q) out[e * El::nq + q] = det_jacobian<El>(q, X) * El::weight(q);
+  for (int q = 0; q < El::num_q(); ++q) out[e * El::num_q() + q] = det_jacobian<El>(q, X) * El::weight(q);
 }
 
 template <class El>
@@ -60,7 +37,7 @@ __global__ void __launch_bounds__(kBlock) k_grad(const double* __restrict__ coor
   double X[El::npe][El::dim];
   gather_rows(coords, nd, X);
 #pragma unroll 1
-  for (int q = 0; q < El::nq; ++q) {
+  for (int q = 0; q < El::num_q(); ++q) {
     double dNdX[El::gdim][El::npe];
     geometry<El>(q, X, dNdX);
     for (int c = 0; c < nv; ++c) {
@@ -72,7 +49,7 @@ __global__ void __launch_bounds__(kBlock) k_grad(const double* __restrict__ coor
         double s = 0.0;
 #pragma unroll
         for (int n = 0; n < El::npe; ++n) s += dNdX[j][n] * ue[n];
-        out[((e * El::nq + q) * nv + c) * El::gdim + j] = s;
+        out[((e * El::num_q() + q) * nv + c) * El::gdim + j] = s;
       }
     }
   }
@@ -89,13 +66,13 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint(const double* __restric
   double X[El::npe][El::dim];
   gather_rows(coords, nd, X);
 #pragma unroll 1
-  for (int q = 0; q < El::nq; ++q) {
+  for (int q = 0; q < El::num_q(); ++q) {
     double dNdX[El::gdim][El::npe];
     geometry<El>(q, X, dNdX);
     for (int c = 0; c < nv; ++c) {
       double gj[El::gdim];
 #pragma unroll
-      for (int j = 0; j < El::gdim; ++j) gj[j] = __ldg(g + ((e * El::nq + q) * nv + c) * El::gdim + j);
+      for (int j = 0; j < El::gdim; ++j) gj[j] = __ldg(g + ((e * El::num_q() + q) * nv + c) * El::gdim + j);
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) {
         double s = 0.0;
@@ -132,7 +109,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_staged(const double* __restrict
                                                         const int32_t* __restrict__ conn, int64_t E,
                                                         const double* __restrict__ u, int nv, double* __restrict__ out) {
   extern __shared__ double sm_stage[];
-  const int CH = El::nq * nv * El::gdim, S = CH | 1;
+  const int CH = El::num_q() * nv * El::gdim, S = CH | 1;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,7 +119,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_staged(const double* __restrict
     double X[El::npe][El::dim];
     gather_rows(coords, nd, X);
 #pragma unroll 1
-    for (int q = 0; q < El::nq; ++q) {
+    for (int q = 0; q < El::num_q(); ++q) {
       double dNdX[El::gdim][El::npe];
       geometry<El>(q, X, dNdX);
       for (int c = 0; c < nv; ++c) {
@@ -170,7 +147,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_staged(const double* __
                                                                 const double* __restrict__ g, int nv,
                                                                 double* __restrict__ y) {
   extern __shared__ double sm_stage[];
-  const int CH = El::nq * nv * El::gdim, S = CH | 1;
+  const int CH = El::num_q() * nv * El::gdim, S = CH | 1;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,7 +160,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_staged(const double* __
   double X[El::npe][El::dim];
   gather_rows(coords, nd, X);
 #pragma unroll 1
-  for (int q = 0; q < El::nq; ++q) {
+  for (int q = 0; q < El::num_q(); ++q) {
     double dNdX[El::gdim][El::npe];
     geometry<El>(q, X, dNdX);
     for (int c = 0; c < nv; ++c) {
@@ -208,7 +185,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __res
                                                              const int32_t* __restrict__ conn, int64_t E,
                                                              const double* __restrict__ g, double* __restrict__ y) {
   extern __shared__ double sm_stage[];
-  constexpr int CH = El::nq * NV * El::gdim, S = CH | 1;
+  constexpr int CH = El::max_nq * NV * El::gdim, S = CH | 1;
   constexpr int SC = grouped_scatter_words<El::npe, NV>();  // grouped-scatter staging per warp
   constexpr int PER_WARP = (32 * S > SC) ? 32 * S : SC;
   const int lane = threadIdx.x & 31;
@@ -230,7 +207,7 @@ __global__ void __launch_bounds__(kBlock) k_grad_adjoint_acc(const double* __res
     double X[El::npe][El::dim];
     gather_rows(coords, nd, X);
 #pragma unroll 1
-    for (int q = 0; q < El::nq; ++q) {
+    for (int q = 0; q < El::num_q(); ++q) {
       double dNdX[El::gdim][El::npe];
       geometry<El>(q, X, dNdX);
 #pragma unroll
@@ -263,9 +240,9 @@ __global__ void __launch_bounds__(kBlock) k_weights_qp(const double* __restrict_
                                                        const int32_t* __restrict__ conn, int64_t E,
                                                        double* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= E * El::nq) return;
-  const int64_t e = t / El::nq;
-  const int q = (int)(t - e * El::nq);
+  if (t >= E * El::num_q()) return;
+  const int64_t e = t / El::num_q();
+  const int q = (int)(t - e * El::num_q());
   int nd[El::npe];
   load_conn<El>(conn, e, nd);
   double X[El::npe][El::dim];
@@ -282,11 +259,11 @@ __global__ void __launch_bounds__(kBlock) k_field_qp(const double* __restrict__ 
   const int CH = nv * G, S = CH | 1;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
-  const int64_t T = E * El::nq;
+  const int64_t T = E * El::num_q();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < T) {
-    const int64_t e = t / El::nq;
-    const int q = (int)(t - e * El::nq);
+    const int64_t e = t / El::num_q();
+    const int q = (int)(t - e * El::num_q());
     int nd[El::npe];
     load_conn<El>(conn, e, nd);
     double B[G][El::npe];  // dNdX (GRAD) or N
@@ -319,7 +296,7 @@ template <class El>
 __global__ void __launch_bounds__(kBlock) k_eval_staged(const int32_t* __restrict__ conn, int64_t E,
                                                         const double* __restrict__ u, int nv, double* __restrict__ out) {
   extern __shared__ double sm_stage[];
-  const int CH = El::nq * nv, S = CH | 1;
+  const int CH = El::num_q() * nv, S = CH | 1;
   const int lane = threadIdx.x & 31;
   double* st = sm_stage + (size_t)(threadIdx.x >> 5) * 32 * S;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -331,7 +308,7 @@ __global__ void __launch_bounds__(kBlock) k_eval_staged(const int32_t* __restric
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
 #pragma unroll
-      for (int q = 0; q < El::nq; ++q) {
+      for (int q = 0; q < El::num_q(); ++q) {
         double N[El::npe];
         El::N(q, N);
         double t = 0.0;
@@ -358,13 +335,13 @@ __global__ void __launch_bounds__(kBlock) k_eval(const int32_t* __restrict__ con
 #pragma unroll
     for (int n = 0; n < El::npe; ++n) ue[n] = __ldg(u + (int64_t)nd[n] * nv + c);
 #pragma unroll
-    for (int q = 0; q < El::nq; ++q) {
+    for (int q = 0; q < El::num_q(); ++q) {
       double N[El::npe];
       El::N(q, N);
       double s = 0.0;
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) s += N[n] * ue[n];
-      out[(e * El::nq + q) * nv + c] = s;
+      out[(e * El::num_q() + q) * nv + c] = s;
     }
   }
 }
@@ -381,10 +358,10 @@ __global__ void __launch_bounds__(kBlock) k_eval_adjoint(const int32_t* __restri
 #pragma unroll
     for (int n = 0; n < El::npe; ++n) acc[n] = 0.0;
 #pragma unroll
-    for (int q = 0; q < El::nq; ++q) {
+    for (int q = 0; q < El::num_q(); ++q) {
       double N[El::npe];
       El::N(q, N);
-      const double gq = __ldg(g + (e * El::nq + q) * nv + c);
+      const double gq = __ldg(g + (e * El::num_q() + q) * nv + c);
 #pragma unroll
       for (int n = 0; n < El::npe; ++n) acc[n] += N[n] * gq;
     }
@@ -401,22 +378,22 @@ __global__ void __launch_bounds__(kBlock) k_integrate_quad(const double* __restr
                                                            double* __restrict__ out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  double W[El::nq];
+  double W[El::max_nq];
   if (cachedW) {
 #pragma unroll
-    for (int q = 0; q < El::nq; ++q) W[q] = __ldg(cachedW + e * El::nq + q);
+    for (int q = 0; q < El::num_q(); ++q) W[q] = __ldg(cachedW + e * El::num_q() + q);
   } else {
     int nd[El::npe];
     load_conn<El>(conn, e, nd);
     double X[El::npe][El::dim];
     gather_rows(coords, nd, X);
 #pragma unroll
-    for (int q = 0; q < El::nq; ++q) W[q] = det_jacobian<El>(q, X) * El::weight(q);
+    for (int q = 0; q < El::num_q(); ++q) W[q] = det_jacobian<El>(q, X) * El::weight(q);
   }
   for (int c = 0; c < nv; ++c) {
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < El::nq; ++q) s += __ldg(vals + (e * El::nq + q) * nv + c) * W[q];
+    for (int q = 0; q < El::num_q(); ++q) s += __ldg(vals + (e * El::num_q() + q) * nv + c) * W[q];
     out[e * nv + c] = s;
   }
 }
@@ -439,25 +416,6 @@ __global__ void __launch_bounds__(256) k_gather_adjoint(const int32_t* __restric
   const int64_t en = i / nv;
   const int c = (int)(i - en * nv);
   atomicAdd(y + (int64_t)__ldg(conn + en) * nv + c, __ldg(g + i));
-}
-
-// ---- deterministic reductions -----------------------------------------------------------------
-
-TATVA_D double block_sum(double v) {
-  __shared__ double sh[32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
-  if (w == 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  }
-  __syncthreads();
-  return v;  // valid on thread 0
 }
 
 // partial[b*nv + c] = sum over rows of chunk b; rows strided by blockDim
@@ -704,212 +662,6 @@ __global__ void __launch_bounds__(128) k_interpolate_grid(const double* __restri
   interpolate_in_element<El>(coords, conn, found, u, nv, px, py, out + p * nv);
 }
 
-// ---- fused energy / residual / HVP ------------------------------------------------------------
-
-enum { MODE_ENERGY = 0, MODE_RESIDUAL = 1, MODE_HVP = 2 };
-
-template <class El, class Mat>
-TATVA_HD void qp_state(const double (&dNdX)[El::dim][El::npe], const double (&N)[El::npe],
-                      const double (&U)[El::npe][Mat::dpn], typename Mat::S& s) {
-#pragma unroll
-  for (int c = 0; c < Mat::dpn; ++c) {
-#pragma unroll
-    for (int j = 0; j < El::dim; ++j) {
-      double t = 0.0;
-#pragma unroll
-      for (int n = 0; n < El::npe; ++n) t += dNdX[j][n] * U[n][c];
-      s.G[c][j] = t;
-    }
-    if (c >= Mat::val_lo) {
-      double t = 0.0;
-#pragma unroll
-      for (int n = 0; n < El::npe; ++n) t += N[n] * U[n][c];
-      s.val[c] = t;
-    }
-  }
-}
-
-template <class El, class Mat, int MODE>
-__global__ void __launch_bounds__(kBlock) k_fused(const double* __restrict__ coords, const int32_t* __restrict__ conn,
-                                                  int64_t E, Mat mat, const double* __restrict__ u,
-                                                  const double* __restrict__ v, double* __restrict__ y,
-                                                  double* __restrict__ partials) {
-  static_assert(El::dim == Mat::dim, "element / law dimension mismatch");
-  constexpr int dpn = Mat::dpn;
-  extern __shared__ double sm_fused[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double energy = 0.0;
-  int nd[El::npe];
-  double Y[El::npe][dpn];
-#pragma unroll
-  for (int n = 0; n < El::npe; ++n) {
-    nd[n] = 0;
-#pragma unroll
-    for (int c = 0; c < dpn; ++c) Y[n][c] = 0.0;
-  }
-  if (e < E) {
-    load_conn<El>(conn, e, nd);
-    double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn];
-    gather_rows(coords, nd, X);
-    gather_rows(u, nd, U);
-    if constexpr (MODE == MODE_HVP) gather_rows(v, nd, V);
-
-#pragma unroll 1
-    for (int q = 0; q < El::nq; ++q) {
-      double dNdX[El::dim][El::npe], N[El::npe];
-      const double W = geometry<El>(q, X, dNdX) * El::weight(q);
-      El::N(q, N);
-      typename Mat::S s, ds, f;
-      typename Mat::Cache cache;
-      qp_state<El, Mat>(dNdX, N, U, s);
-      mat.prepare(s, cache);
-      if constexpr (MODE == MODE_ENERGY) {
-        energy += W * mat.psi(s, cache);
-      } else {
-        if constexpr (MODE == MODE_RESIDUAL) {
-          mat.first(s, cache, f);
-        } else {
-          qp_state<El, Mat>(dNdX, N, V, ds);
-          mat.second(s, cache, ds, f);
-        }
-#pragma unroll
-        for (int n = 0; n < El::npe; ++n)
-#pragma unroll
-          for (int c = 0; c < dpn; ++c) {
-            double t = 0.0;
-#pragma unroll
-            for (int j = 0; j < El::dim; ++j) t += f.G[c][j] * dNdX[j][n];
-            if (c >= Mat::val_lo) t += f.val[c] * N[n];
-            Y[n][c] += W * t;
-          }
-      }
-    }
-  }
-  if constexpr (MODE != MODE_ENERGY) {
-    double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<El::npe, dpn>();
-    grouped_scatter<El::npe, dpn>(y, nd, Y, e < E, wsm);
-  }
-  if constexpr (MODE == MODE_ENERGY) {
-    energy = block_sum(energy);
-    if (threadIdx.x == 0) partials[blockIdx.x] = energy;
-  }
-}
-
-// HVP with the Lifter folded in: v and y are REDUCED vectors, `map` (n_nodes*dpn int32) sends a full DOF to its
-// reduced index or to -1 (no driver: the homogeneous lift is 0 there and the contribution is dropped).
-template <class El, class Mat>
-__global__ void __launch_bounds__(kBlock) k_hvp_lifted(const double* __restrict__ coords, const int32_t* __restrict__ conn,
-                                                       int64_t E, Mat mat, const double* __restrict__ u,
-                                                       const double* __restrict__ v, const int32_t* __restrict__ map,
-                                                       double* __restrict__ y) {
-  constexpr int dpn = Mat::dpn;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int nd[El::npe];
-  load_conn<El>(conn, e, nd);
-  double X[El::npe][El::dim], U[El::npe][dpn], V[El::npe][dpn], Y[El::npe][dpn];
-  gather_rows(coords, nd, X);
-  gather_rows(u, nd, U);
-#pragma unroll
-  for (int n = 0; n < El::npe; ++n)
-#pragma unroll
-    for (int c = 0; c < dpn; ++c) {
-      const int32_t m = __ldg(map + (int64_t)nd[n] * dpn + c);
-      V[n][c] = m >= 0 ? __ldg(v + m) : 0.0;
-      Y[n][c] = 0.0;
-    }
-#pragma unroll 1
-  for (int q = 0; q < El::nq; ++q) {
-    double dNdX[El::dim][El::npe], N[El::npe];
-    const double W = geometry<El>(q, X, dNdX) * El::weight(q);
-    El::N(q, N);
-    typename Mat::S s, ds, f;
-    typename Mat::Cache cache;
-    qp_state<El, Mat>(dNdX, N, U, s);
-    mat.prepare(s, cache);
-    qp_state<El, Mat>(dNdX, N, V, ds);
-    mat.second(s, cache, ds, f);
-#pragma unroll
-    for (int n = 0; n < El::npe; ++n)
-#pragma unroll
-      for (int c = 0; c < dpn; ++c) {
-        double t = 0.0;
-#pragma unroll
-        for (int j = 0; j < El::dim; ++j) t += f.G[c][j] * dNdX[j][n];
-        if (c >= Mat::val_lo) t += f.val[c] * N[n];
-        Y[n][c] += W * t;
-      }
-  }
-#pragma unroll
-  for (int n = 0; n < El::npe; ++n)
-#pragma unroll
-    for (int c = 0; c < dpn; ++c) {
-      const int32_t m = __ldg(map + (int64_t)nd[n] * dpn + c);
-      if (m >= 0) atomicAdd(y + m, Y[n][c]);
-    }
-}
-
-// ---- Hessian diagonal (Jacobi preconditioner) -------------------------------------------------------
-// diag[dpn*node_b + k] += sum_q W * (d2psi : unit_(b,k)) . unit_(b,k): the (b,k)/(b,k) entry of the element
-// stiffness, with the geometry and the material state of a point computed once for all npe*dpn unit directions.
-template <class El, class Mat>
-__global__ void __launch_bounds__(kBlock) k_hessian_diag(const double* __restrict__ coords,
-                                                         const int32_t* __restrict__ conn, int64_t E, Mat mat,
-                                                         const double* __restrict__ u, double* __restrict__ diag) {
-  constexpr int dpn = Mat::dpn;
-  extern __shared__ double sm_fused[];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int nd[El::npe];
-  double Y[El::npe][dpn];
-#pragma unroll
-  for (int n = 0; n < El::npe; ++n) {
-    nd[n] = 0;
-#pragma unroll
-    for (int c = 0; c < dpn; ++c) Y[n][c] = 0.0;
-  }
-  if (e < E) {
-    load_conn<El>(conn, e, nd);
-    double X[El::npe][El::dim], U[El::npe][dpn];
-    gather_rows(coords, nd, X);
-    gather_rows(u, nd, U);
-#pragma unroll 1
-    for (int q = 0; q < El::nq; ++q) {
-      double dNdX[El::dim][El::npe], N[El::npe];
-      const double W = geometry<El>(q, X, dNdX) * El::weight(q);
-      El::N(q, N);
-      typename Mat::S s;
-      typename Mat::Cache cache;
-      qp_state<El, Mat>(dNdX, N, U, s);
-      mat.prepare(s, cache);
-#pragma unroll
-      for (int b = 0; b < El::npe; ++b) {
-#pragma unroll
-        for (int k = 0; k < dpn; ++k) {
-          typename Mat::S ds, f;
-#pragma unroll
-          for (int c = 0; c < dpn; ++c) {
-#pragma unroll
-            for (int j = 0; j < El::dim; ++j) ds.G[c][j] = (c == k) ? dNdX[j][b] : 0.0;
-            ds.val[c] = (c == k) ? N[b] : 0.0;
-          }
-          mat.second(s, cache, ds, f);
-          double t = 0.0;
-#pragma unroll
-          for (int j = 0; j < El::dim; ++j) t += f.G[k][j] * dNdX[j][b];
-          if (k >= Mat::val_lo) t += f.val[k] * N[b];
-          Y[b][k] += W * t;
-        }
-      }
-    }
-  }
-  double* wsm = sm_fused + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<El::npe, dpn>();
-  grouped_scatter<El::npe, dpn>(diag, nd, Y, e < E, wsm);
-}
-
-// ---- CSR assembly -----------------------------------------------------------------------------
-// Column (b,k) of the element stiffness is the element-local HVP with the unit direction
-// "component k of node b"; rows (a,i) go to data[indptr[dpn*node_a + i] + pos[e,a,b] + k].
-
 template <class El, class Mat>
 __global__ void __launch_bounds__(kBlock) k_csr(const double* __restrict__ coords, const int32_t* __restrict__ conn,
                                                 int64_t E, Mat mat, const double* __restrict__ u,
@@ -937,7 +689,7 @@ __global__ void __launch_bounds__(kBlock) k_csr(const double* __restrict__ coord
 #pragma unroll
         for (int i = 0; i < dpn; ++i) col[a][i] = 0.0;
 #pragma unroll 1
-      for (int q = 0; q < El::nq; ++q) {
+      for (int q = 0; q < El::num_q(); ++q) {
         double dNdX[El::dim][El::npe], N[El::npe];
         const double W = geometry<El>(q, X, dNdX) * El::weight(q);
         El::N(q, N);
@@ -993,7 +745,7 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
                                                         const double* __restrict__ u,
                                                         const int32_t* __restrict__ indptr,
                                                         const int32_t* __restrict__ pos, double* __restrict__ data) {
-  static_assert(El::nq == 1, "grouped assembly is implemented for single-point elements");
+  static_assert(El::max_nq == 1, "grouped assembly is implemented for single-point elements");
   constexpr int dpn = Mat::dpn, npe = El::npe, S = npe * dpn * dpn, NB = npe * dpn;
   constexpr int SP = S | 1, NBP = NB | 1;  // odd per-lane strides: conflict-free lane-strided stores
   extern __shared__ double sm_grp[];
@@ -1113,7 +865,7 @@ __global__ void __launch_bounds__(128) k_csr_rows(const double* __restrict__ coo
                                                   const int32_t* __restrict__ indices,
                                                   const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
                                                   double* __restrict__ data) {
-  static_assert(El::nq == 1, "row-wise assembly is implemented for single-point elements");
+  static_assert(El::max_nq == 1, "row-wise assembly is implemented for single-point elements");
   constexpr int dpn = Mat::dpn, npe = El::npe, SLAB = dpn * npe * dpn;
   extern __shared__ double sm_rows[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1469,6 +1221,26 @@ static int allow_big_smem(K kernel, SmemOptIn& done) {
     default: return TATVA_E_INVALID;              \
   }
 
+// ---- user-supplied quadrature rules -------------------------------------------------------------------------
+#define DISPATCH_CUSTOM(p, CALL)                 \
+  switch ((p)->element) {                         \
+    case TATVA_TRI3: { using El = Custom<Tri3>; CALL; } break; \
+    case TATVA_TET4: { using El = Custom<Tet4>; CALL; } break; \
+    case TATVA_HEX8: { using El = Custom<Hex8>; CALL; } break; \
+    case TATVA_QUAD4: { using El = Custom<Quad4>; CALL; } break; \
+    case TATVA_TRI6: { using El = Custom<Tri6>; CALL; } break; \
+    case TATVA_QUAD8: { using El = Custom<Quad8>; CALL; } break; \
+    case TATVA_LINE2: { using El = Custom<Line2>; CALL; } break; \
+    case TATVA_LINE3: { using El = Custom<Line3>; CALL; } break; \
+    default: return TATVA_E_INVALID;              \
+  }
+
+// Stream-ordered: the copy precedes the kernel that reads it.  Two plans with DIFFERENT custom rules must not launch
+// concurrently on different streams (one constant-memory slot per process and device) — documented in the header.
+static cudaError_t install_rule(const tatva_plan* p, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(tatva::c_rule, &p->rule, sizeof(QuadRule), 0, cudaMemcpyHostToDevice, st);
+}
+
 extern "C" {
 
 const char* tatva_error_string(int code) {
@@ -1524,6 +1296,7 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->tile_nodes = nullptr;
   p->tile_conn = nullptr;
   p->tile_max_unique = 0;
+  p->custom = 0;
   p->scratch_len = (int64_t)grid_for(n_elems) * (kBlock / 32) > 1024 * 64 ? (int64_t)grid_for(n_elems) * (kBlock / 32) : 1024 * 64;
   cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
   if (e != cudaSuccess) { delete p; return (int)e; }
@@ -1596,6 +1369,35 @@ int tatva_plan_set_variant(tatva_plan_t* p, int variant) {
   return TATVA_OK;
 }
 
+int tatva_plan_set_quadrature(tatva_plan_t* p, int nq, const double* points, const double* weights, tatva_stream_t stream) {
+  if (!p) return TATVA_E_INVALID;
+  int rdim = 0, def_nq = 0;
+  DISPATCH_ELEMENT(p, (rdim = El::rdim, def_nq = El::nq));
+  if (nq == 0) {  // back to the element's default rule
+    p->custom = 0;
+    p->nq = def_nq;
+  } else {
+    if (!points || !weights || nq < 0 || nq > kMaxQ) return TATVA_E_INVALID;
+    p->custom = 1;
+    p->nq = nq;
+    p->rule.nq = nq;
+    for (int q = 0; q < kMaxQ; ++q) {
+      p->rule.w[q] = q < nq ? weights[q] : 0.0;
+      for (int d = 0; d < 3; ++d) p->rule.xi[q][d] = (q < nq && d < rdim) ? points[q * rdim + d] : 0.0;
+    }
+  }
+  if (p->weights) {  // cached det J * w: recompute with the new rule
+    cudaFree(p->weights);
+    p->weights = nullptr;
+    double* w = nullptr;
+    TATVA_CUDA_TRY(cudaMalloc(&w, sizeof(double) * p->n_elems * p->nq));
+    const int rc = tatva_op_integration_weights(p, w, stream);
+    p->weights = w;
+    if (rc != TATVA_OK) return rc;
+  }
+  return TATVA_OK;
+}
+
 int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_stream_t stream) {
   if (!p || !d_out) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1603,8 +1405,14 @@ int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_str
     TATVA_CUDA_TRY(cudaMemcpyAsync(d_out, p->weights, sizeof(double) * p->n_elems * p->nq, cudaMemcpyDeviceToDevice, st));
     return TATVA_OK;
   }
+  if (p->custom) {
+    TATVA_CUDA_TRY(install_rule(p, st));
+    DISPATCH_CUSTOM(p, (k_weights<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_out)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   if (p->nq > 1 && p->variant == 3) {  // thread per quadrature point: measured slower (see k_weights_qp)
-    DISPATCH_ELEMENT(p, (k_weights_qp<El><<<grid_for(p->n_elems * El::nq), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_out)));
+    DISPATCH_ELEMENT(p, (k_weights_qp<El><<<grid_for(p->n_elems * p->nq), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_out)));
     TATVA_LAUNCH_CHECK();
     return TATVA_OK;
   }
@@ -1616,10 +1424,16 @@ int tatva_op_integration_weights(const tatva_plan_t* p, double* d_out, tatva_str
 int tatva_op_grad(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->custom) {
+    TATVA_CUDA_TRY(install_rule(p, st));
+    DISPATCH_CUSTOM(p, (k_grad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   if (p->nq > 1 && p->variant == 3) {  // one thread per quadrature point: measured slower, kept as variant 3
     const size_t smem = (size_t)(kBlock / 32) * 32 * ((nv * p->gdim) | 1) * sizeof(double);
     if (smem <= 48 * 1024) {
-      DISPATCH_ELEMENT(p, (k_field_qp<El, true><<<grid_for(p->n_elems * El::nq), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+      DISPATCH_ELEMENT(p, (k_field_qp<El, true><<<grid_for(p->n_elems * p->nq), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
       TATVA_LAUNCH_CHECK();
       return TATVA_OK;
     }
@@ -1642,11 +1456,17 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
   if (!p || !d_g || !d_y || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
+  if (p->custom) {
+    TATVA_CUDA_TRY(install_rule(p, st));
+    DISPATCH_CUSTOM(p, (k_grad_adjoint<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, d_g, nv, d_y)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   if (nv <= 4 && p->variant != TATVA_VARIANT_GENERIC) {
     int rc = TATVA_OK;
 #define ADJ_ACC(NV)                                                                                              \
   {                                                                                                              \
-    constexpr int CH_ = El::nq * NV * El::gdim, S_ = CH_ | 1, SC_ = grouped_scatter_words<El::npe, NV>();            \
+    constexpr int CH_ = El::max_nq * NV * El::gdim, S_ = CH_ | 1, SC_ = grouped_scatter_words<El::npe, NV>();            \
     constexpr size_t smem_ = (size_t)(kBlock / 32) * ((32 * S_ > SC_) ? 32 * S_ : SC_) * sizeof(double);         \
     static SmemOptIn done_;                                                                                      \
     rc = allow_big_smem(k_grad_adjoint_acc<El, NV>, done_);                                                      \
@@ -1681,10 +1501,16 @@ int tatva_op_grad_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
 int tatva_op_eval(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->custom) {
+    TATVA_CUDA_TRY(install_rule(p, st));
+    DISPATCH_CUSTOM(p, (k_eval<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->conn, p->n_elems, d_u, nv, d_out)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   if (p->nq > 1 && p->variant == 3) {  // one thread per quadrature point: measured slower, kept as variant 3
     const size_t smem = (size_t)(kBlock / 32) * 32 * (nv | 1) * sizeof(double);
     if (smem <= 48 * 1024) {
-      DISPATCH_ELEMENT(p, (k_field_qp<El, false><<<grid_for(p->n_elems * El::nq), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
+      DISPATCH_ELEMENT(p, (k_field_qp<El, false><<<grid_for(p->n_elems * p->nq), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, d_u, nv, d_out)));
       TATVA_LAUNCH_CHECK();
       return TATVA_OK;
     }
@@ -1707,6 +1533,12 @@ int tatva_op_eval_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
   if (!p || !d_g || !d_y || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
+  if (p->custom) {
+    TATVA_CUDA_TRY(install_rule(p, st));
+    DISPATCH_CUSTOM(p, (k_eval_adjoint<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->conn, p->n_elems, d_g, nv, d_y)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   DISPATCH_ELEMENT(p, (k_eval_adjoint<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->conn, p->n_elems, d_g, nv, d_y)));
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -1715,6 +1547,12 @@ int tatva_op_eval_adjoint(const tatva_plan_t* p, const double* d_g, int nv, doub
 int tatva_op_integrate_quad(const tatva_plan_t* p, const double* d_vals, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_vals || !d_out || nv <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->custom) {
+    TATVA_CUDA_TRY(install_rule(p, st));
+    DISPATCH_CUSTOM(p, (k_integrate_quad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, p->weights, d_vals, nv, d_out)));
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   DISPATCH_ELEMENT(p, (k_integrate_quad<El><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, p->weights, d_vals, nv, d_out)));
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -1725,6 +1563,7 @@ int tatva_op_integrate_quad(const tatva_plan_t* p, const double* d_vals, int nv,
 // element of every point, -1 (and NaN values) where the point lies outside the mesh.
 int tatva_op_interpolate(const tatva_plan_t* p, const double* d_u, int nv, const double* d_points, int64_t n_points,
                          double* d_out, int32_t* d_elem, tatva_stream_t stream) {
+  if (p && p->custom) return TATVA_E_UNSUPPORTED;  // the Newton start is the element's first DEFAULT point
   if (!p || !d_u || !d_points || !d_out || !d_elem || nv <= 0 || n_points <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)((n_points + 127) / 128);
@@ -1806,6 +1645,25 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
   if (!p || !prm || !u || !out) return TATVA_E_INVALID;
   if (MODE == MODE_HVP && !v) return TATVA_E_INVALID;
   const int el = p->element;
+  if (p->custom) {  // user quadrature rule: the generic template over Custom<El> (the specialised kernels carry the default rule)
+    TATVA_CUDA_TRY(install_rule(p, st));
+    if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
+      if (el == TATVA_TRI3) return launch_fused<Custom<Tri3>, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+      if (el == TATVA_QUAD4) return launch_fused<Custom<Quad4>, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+      if (el == TATVA_TRI6) return launch_fused<Custom<Tri6>, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+      if (el == TATVA_QUAD8) return launch_fused<Custom<Quad8>, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+      if (el == TATVA_TET4) return launch_fused<Custom<Tet4>, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
+      if (el == TATVA_HEX8) return launch_fused<Custom<Hex8>, LinearElastic<3>, MODE>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
+    } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
+      if (el == TATVA_TET4) return launch_fused<Custom<Tet4>, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
+      if (el == TATVA_HEX8) return launch_fused<Custom<Hex8>, NeoHookean, MODE>(p, NeoHookean{prm[0], prm[1]}, u, v, out, st);
+    } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5) {
+      const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+      if (el == TATVA_TET4) return launch_fused<Custom<Tet4>, NeoHookeanPhaseField, MODE>(p, m, u, v, out, st);
+      if (el == TATVA_HEX8) return launch_fused<Custom<Hex8>, NeoHookeanPhaseField, MODE>(p, m, u, v, out, st);
+    }
+    return TATVA_E_UNSUPPORTED;
+  }
   if (material == TATVA_LINEAR_ELASTIC) {
     if (n_params != 2) return TATVA_E_INVALID;
     if (el == TATVA_TRI3) return launch_fused<Tri3, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
@@ -1865,27 +1723,33 @@ int tatva_hvp(tatva_plan_t* p, int material, const double* params, int n_params,
 
 // (element, law) pairs of the fused kernels, as a visitor: f(El{}, mat) for the pair named by the enums.
 template <class F>
-static int for_element_law(int el, int material, const double* prm, int n_params, F&& f) {
+static int for_element_law(int el, int material, const double* prm, int n_params, F&& f, bool custom = false) {
+#define TATVA_EL_LAW(ID, B, LAW) \
+  if (el == ID) return custom ? f(Custom<B>{}, LAW) : f(B{}, LAW);
   if (material == TATVA_LINEAR_ELASTIC) {
     if (n_params != 2) return TATVA_E_INVALID;
-    if (el == TATVA_TRI3) return f(Tri3{}, LinearElastic<2>{prm[0], prm[1]});
-    if (el == TATVA_QUAD4) return f(Quad4{}, LinearElastic<2>{prm[0], prm[1]});
-    if (el == TATVA_TRI6) return f(Tri6{}, LinearElastic<2>{prm[0], prm[1]});
-    if (el == TATVA_QUAD8) return f(Quad8{}, LinearElastic<2>{prm[0], prm[1]});
-    if (el == TATVA_TET4) return f(Tet4{}, LinearElastic<3>{prm[0], prm[1]});
-    if (el == TATVA_HEX8) return f(Hex8{}, LinearElastic<3>{prm[0], prm[1]});
+    const LinearElastic<2> m2{prm[0], prm[1]};
+    const LinearElastic<3> m3{prm[0], prm[1]};
+    TATVA_EL_LAW(TATVA_TRI3, Tri3, m2)
+    TATVA_EL_LAW(TATVA_QUAD4, Quad4, m2)
+    TATVA_EL_LAW(TATVA_TRI6, Tri6, m2)
+    TATVA_EL_LAW(TATVA_QUAD8, Quad8, m2)
+    TATVA_EL_LAW(TATVA_TET4, Tet4, m3)
+    TATVA_EL_LAW(TATVA_HEX8, Hex8, m3)
   } else if (material == TATVA_NEO_HOOKEAN) {
     if (n_params != 2) return TATVA_E_INVALID;
-    if (el == TATVA_TET4) return f(Tet4{}, NeoHookean{prm[0], prm[1]});
-    if (el == TATVA_HEX8) return f(Hex8{}, NeoHookean{prm[0], prm[1]});
+    const NeoHookean m{prm[0], prm[1]};
+    TATVA_EL_LAW(TATVA_TET4, Tet4, m)
+    TATVA_EL_LAW(TATVA_HEX8, Hex8, m)
   } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD) {
     if (n_params != 5) return TATVA_E_INVALID;
     const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
-    if (el == TATVA_TET4) return f(Tet4{}, m);
-    if (el == TATVA_HEX8) return f(Hex8{}, m);
+    TATVA_EL_LAW(TATVA_TET4, Tet4, m)
+    TATVA_EL_LAW(TATVA_HEX8, Hex8, m)
   } else {
     return TATVA_E_INVALID;
   }
+#undef TATVA_EL_LAW
   return TATVA_E_UNSUPPORTED;
 }
 
@@ -1896,6 +1760,7 @@ int tatva_hessian_diag(tatva_plan_t* p, int material, const double* params, int 
                        double* d_diag, tatva_stream_t stream) {
   if (!p || !params || !d_u || !d_diag) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->custom) TATVA_CUDA_TRY(install_rule(p, st));
   return for_element_law(p->element, material, params, n_params, [&](auto el, auto mat) -> int {
     using El = decltype(el);
     using Mat = decltype(mat);
@@ -1904,7 +1769,7 @@ int tatva_hessian_diag(tatva_plan_t* p, int material, const double* params, int 
     k_hessian_diag<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, d_u, d_diag);
     TATVA_LAUNCH_CHECK();
     return TATVA_OK;
-  });
+  }, p->custom != 0);
 }
 
 // HVP on the free DOFs of a Lifter in ONE kernel: y_red = reduce_adjoint(H(u_full) lift_0(v_red)).
@@ -1914,15 +1779,16 @@ int tatva_hvp_lifted(tatva_plan_t* p, int material, const double* params, int n_
   if (!p || !params || !d_u_full || !d_v_red || !d_dof_map || !d_y_red || n_red <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(d_y_red, 0, sizeof(double) * n_red, st));
-  if (p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC)
+  if (!p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC)
     return hex8_nh_hvp_modal_lifted(p, params[0], params[1], d_u_full, d_v_red, d_dof_map, d_y_red, st);
+  if (p->custom) TATVA_CUDA_TRY(install_rule(p, st));
   return for_element_law(p->element, material, params, n_params, [&](auto el, auto mat) -> int {
     using El = decltype(el);
     using Mat = decltype(mat);
     k_hvp_lifted<El, Mat><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, d_u_full, d_v_red, d_dof_map, d_y_red);
     TATVA_LAUNCH_CHECK();
     return TATVA_OK;
-  });
+  }, p->custom != 0);
 }
 
 // The same with v_red . y_red computed on the way (CG: p . A p without a pass over the two vectors): the Hex8 x
@@ -1937,7 +1803,7 @@ int tatva_hvp_lifted_dot(tatva_plan_t* p, int material, const double* params, in
   if (!p || !params || !d_u_full || !d_v_red || !d_dof_map || !d_y_red || !d_scalars || !d_partials || n_red <= 0 || slot < 0 || slot > 7) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y_red, 0, sizeof(double) * n_red, st));
-  if (p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
+  if (!p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
     const int grid = grid_for(p->n_elems) * (kBlock / 32);  // one partial per warp
     if (grid > p->scratch_len) return TATVA_E_INVALID;
     const int rc = hex8_nh_hvp_modal_lifted(p, params[0], params[1], d_u_full, d_v_red, d_dof_map, d_y_red, st, p->scratch);
@@ -1966,7 +1832,7 @@ int tatva_hvp_dot(tatva_plan_t* p, int material, const double* params, int n_par
   const int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
   const int64_t n = p->n_nodes * dpn;
   if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * n, st));
-  if (fuse_dot && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
+  if (fuse_dot && !p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
     const int grid = grid_for(p->n_elems) * (kBlock / 32);  // one partial per warp
     if (grid > p->scratch_len) return TATVA_E_INVALID;
     const int rc = hex8_nh_hvp_modal_dot(p, params[0], params[1], d_u, d_v, d_y, p->scratch, st);
@@ -2004,7 +1870,7 @@ static int probe_element(const Mat& mat, int mode, const double* Xp, const doubl
     }
   }
   double energy = 0.0;
-  for (int q = 0; q < El::nq; ++q) {
+  for (int q = 0; q < El::num_q(); ++q) {
     double dNdX[El::dim][El::npe], N[El::npe];
     const double W = geometry<El>(q, X, dNdX) * El::weight(q);
     El::N(q, N);
@@ -2106,7 +1972,7 @@ template <class El, class Mat>
 static int launch_csr(tatva_plan* p, const Mat& mat, const double* u, const int32_t* indptr, const int32_t* pos,
                       int64_t nnz, double* data, cudaStream_t st, const int32_t* indices = nullptr) {
   TATVA_CUDA_TRY(cudaMemsetAsync(data, 0, sizeof(double) * nnz, st));
-  if constexpr (El::nq == 1) {
+  if constexpr (El::max_nq == 1) {
     if (p->variant != TATVA_VARIANT_GENERIC) {
       constexpr int S = El::npe * Mat::dpn * Mat::dpn, NB = El::npe * Mat::dpn;
       constexpr size_t smem = (size_t)(kBlock / 32) * (32 * (S | 1) + 16 * (NB | 1)) * sizeof(double);
@@ -2137,6 +2003,17 @@ static int csr_dispatch(tatva_plan_t* p, int material, const double* prm, int n_
   if (!p || !prm || !d_u || !d_indptr || !d_pos || !d_data || nnz <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int el = p->element;
+  if (p->custom) {  // user quadrature rule: the generic per-entry kernel over Custom<El>
+    TATVA_CUDA_TRY(install_rule(p, st));
+    return for_element_law(el, material, prm, n_params, [&](auto e, auto mat) -> int {
+      using El = decltype(e);
+      using Mat = decltype(mat);
+      TATVA_CUDA_TRY(cudaMemsetAsync(d_data, 0, sizeof(double) * nnz, st));
+      k_csr<El, Mat><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, d_u, d_indptr, d_pos, d_data);
+      TATVA_LAUNCH_CHECK();
+      return TATVA_OK;
+    }, true);
+  }
   if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
     if (el == TATVA_TRI3) return launch_csr<Tri3, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
     if (el == TATVA_QUAD4) return launch_csr<Quad4, LinearElastic<2>>(p, LinearElastic<2>{prm[0], prm[1]}, d_u, d_indptr, d_pos, nnz, d_data, st, d_indices);
@@ -2196,6 +2073,7 @@ int tatva_csr_assemble_rows(tatva_plan_t* p, int material, const double* prm, in
                             const int32_t* d_indptr, const int32_t* d_indices, const int32_t* d_n2e_ptr,
                             const int32_t* d_n2e, double* d_data, tatva_stream_t stream) {
   if (!p || !prm || !d_u || !d_indptr || !d_indices || !d_n2e_ptr || !d_n2e || !d_data) return TATVA_E_INVALID;
+  if (p->custom) return TATVA_E_UNSUPPORTED;  // the row-wise kernel carries the default one-point rule
   cudaStream_t st = (cudaStream_t)stream;
   const int el = p->element;
   if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {

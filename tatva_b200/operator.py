@@ -39,11 +39,11 @@ class Operator:
         self.element = element
         self.cache_weights = bool(cache_weights)
         self._check_init(mesh)
-        if element.kind is None or not getattr(element, "_default_rule", True):
-            raise NotImplementedError(
-                f"{type(element).__name__} with this quadrature rule has no CUDA kernel (the eight reference elements "
-                "with their default rules are supported)"
-            )
+        if element.kind is None:
+            raise NotImplementedError(f"{type(element).__name__} has no CUDA kernel (the eight reference elements are supported)")
+        self._custom_rule = not getattr(element, "_default_rule", True)  # Element(quad_points, quad_weights), element/base.py:37-51
+        if self._custom_rule and len(element.quad_weights) > 64:
+            raise NotImplementedError("custom quadrature rules hold at most 64 points")
         if not torch.cuda.is_available():
             raise _lib.TatvaError("tatva_b200.Operator needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -71,6 +71,8 @@ class Operator:
                 "tatva_plan_create",
             )
         self._plan = handle
+        if self._custom_rule:
+            self._set_rule(handle)
         # Fused energy / residual / HVP / assembly are order-independent sums over elements, so they may run
         # on a locality-sorted copy of the connectivity (Morton order of centroids); the (E, Q, ...)-shaped
         # building blocks keep the caller's element order.
@@ -84,6 +86,8 @@ class Operator:
             with torch.cuda.device(self.device):
                 _lib.check(self._L.tatva_plan_create(C.byref(h2), element.kind, self.n_nodes, self.n_elements, self.coords.data_ptr(), self.elements_fused.data_ptr(), 0, _stream()), "tatva_plan_create")
             self._plan_fused = h2
+            if self._custom_rule:
+                self._set_rule(h2)
 
         # Shared-memory staging tiles for gather-bound kernels (Tet4 x neo-Hookean): per CTA the unique nodes are
         # gathered once, coalesced, and elements read them through tile-local uint16 connectivity.
@@ -91,6 +95,16 @@ class Operator:
         self._tiles = None
         if stage_tiles:
             self._build_tiles()
+
+    def _set_rule(self, plan):
+        """Install the element's own quadrature rule in the plan: the generic kernels then evaluate the shape functions
+        at these points (the specialised Hex8 / Tet4 kernels are default-rule only and are bypassed)."""
+        pts = np.ascontiguousarray(self.element.quad_points, dtype=np.float64)
+        wts = np.ascontiguousarray(self.element.quad_weights, dtype=np.float64)
+        if pts.ndim != 2 or pts.shape[0] != wts.shape[0]:
+            raise ValueError("quad_points must be (n_quad, reference dimension) and quad_weights (n_quad,)")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tatva_plan_set_quadrature(plan, wts.shape[0], pts.ctypes.data_as(_lib.c_f64p), wts.ctypes.data_as(_lib.c_f64p), _stream()), "tatva_plan_set_quadrature")
 
     def _replace(self, **changes) -> "Operator":
         """A new Operator with the given constructor arguments changed (operator.py:497-504, `dataclasses.replace`);

@@ -185,6 +185,49 @@ def operator_fixtures(out):
         out[p + "hvp_probe_wHv"] = hv
 
 
+def custom_rule_fixtures(out):
+    """Element(quad_points, quad_weights) — user quadrature rules (tatva/element/base.py:37-51) — through the
+    reference's Operator: Hex8 with the 3x3x3 Gauss rule, Tet4 with the 4-point degree-2 rule, Quad4 with 3x3 Gauss."""
+    rng = np.random.default_rng(17)
+    cases = {
+        "hex8": (element.Hexahedron8, orc.gauss_rule("hex8", 3), neo_hookean_density, (500.0, 1000.0)),
+        "tet4": (element.Tetrahedron4, orc.gauss_rule("tet4", 2), neo_hookean_density, (500.0, 1000.0)),
+        "quad4": (element.Quad4, orc.gauss_rule("quad4", 3), strain_energy, (0.4, 0.6)),
+    }
+    for kind, (cls, (qp, qw), psi, prm) in cases.items():
+        if kind == "quad4":
+            c, el = orc.mesh_unit_square_quad(3, 3)
+            c = jitter(c, 1.0 / 3)
+        else:
+            c, el, _, _ = make_case(kind)
+        op = Operator(Mesh(coords=c, elements=el), cls(quad_points=jnp.asarray(qp), quad_weights=jnp.asarray(qw)))
+        u = (smooth_u(c) if c.shape[1] == 3 else 0.05 * np.stack([np.sin(2 * np.pi * c[:, 0]) * np.cos(2 * np.pi * c[:, 1]), np.sin(2 * np.pi * c[:, 1]) * np.cos(2 * np.pi * c[:, 0])], -1)) + 0.01 * rng.normal(size=c.shape)
+        s = rng.normal(size=(c.shape[0],))
+        p = f"cq_{kind}_"
+        out[p + "coords"], out[p + "conn"], out[p + "qp"], out[p + "qw"] = c, el, qp, qw
+        out[p + "u"], out[p + "s"], out[p + "prm"] = u, s, np.array(prm)
+        out[p + "grad_u"] = op.grad(u)
+        out[p + "eval_s"] = op.eval(s)
+        out[p + "weights"] = op.get_integration_weights()
+        out[p + "int_nodal_s"] = op.integrate(s)
+        q = rng.normal(size=(el.shape[0], len(qw), 2))
+        out[p + "quadvals"] = q
+        out[p + "int_quad_per_el"] = op.integrate_per_element(q)
+
+        def E(uu):
+            return op.integrate(psi(op.grad(uu), prm[0], prm[1]))
+
+        out[p + "energy"] = E(u)
+        h = 1e-30
+        r = np.zeros(u.shape)
+        for n in range(u.shape[0]):
+            for i in range(u.shape[1]):
+                uc = u.astype(complex)
+                uc[n, i] += 1j * h
+                r[n, i] = np.imag(E(uc)) / h
+        out[p + "residual_cs"] = r
+
+
 def more_operator_fixtures(out):
     """Operator.* on Quad4 / Tri6 / Quad8 meshes (reference Operator, shimmed)."""
     rng = np.random.default_rng(13)
@@ -510,6 +553,7 @@ def main():
     element_fixtures(out)
     operator_fixtures(out)
     more_operator_fixtures(out)
+    custom_rule_fixtures(out)
     sparse_fixtures(out)
     partition_fixtures(out)
     line_fixtures(out)

@@ -325,3 +325,23 @@ def test_exchange_plan_layout_two_dofs_per_node():
     np.testing.assert_array_equal(layouts[0]["local_to_global"], [0, 1, 2, 3])
     np.testing.assert_array_equal(layouts[1]["local_to_global"], [2, 3, 0, 1])
     assert layouts[1]["offset"] == 2 and layouts[0]["n_global"] == 4
+
+
+@pytest.mark.parametrize("kind", ["hex8", "tet4", "quad4"])
+def test_oracle_with_a_custom_quadrature_rule_matches_the_reference(golden, kind):
+    """Element(quad_points, quad_weights) (reference element/base.py:37-51): the oracle run under `custom_rule`
+    reproduces the reference Operator with the Hex8 3x3x3, Tet4 4-point and Quad4 3x3 rules."""
+    g = lambda k: golden[f"cq_{kind}_{k}"]  # noqa: E731
+    c, el, u, s = g("coords"), g("conn"), g("u"), g("s")
+    mat = orc.LinearElastic(*g("prm")) if kind == "quad4" else orc.NeoHookean(*g("prm"))
+    with orc.custom_rule(kind, g("qp"), g("qw")):
+        np.testing.assert_allclose(orc.op_grad(kind, c, el, u), g("grad_u"), rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(orc.op_eval(kind, c, el, s), g("eval_s"), rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(orc.op_integration_weights(kind, c, el), g("weights"), rtol=1e-13)
+        np.testing.assert_allclose(orc.op_integrate(kind, c, el, s), g("int_nodal_s"), rtol=1e-12)
+        np.testing.assert_allclose(orc.op_integrate_per_element(kind, c, el, g("quadvals")), g("int_quad_per_el"), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(orc.energy(kind, mat, c, el, u), g("energy"), rtol=1e-13)
+        r = orc.residual(kind, mat, c, el, u)
+        assert np.linalg.norm(r - g("residual_cs")) <= 1e-12 * np.linalg.norm(r)
+    # the override is gone
+    assert len(orc.quad_rule(kind)[1]) == {"hex8": 8, "tet4": 1, "quad4": 4}[kind]
