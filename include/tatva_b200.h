@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 3  /* bumped on every signature change; the Python loader refuses a mismatch */
+#define TATVA_B200_ABI_VERSION 4  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */
@@ -37,6 +37,7 @@ enum { TATVA_TRI3 = 0, TATVA_TET4 = 1, TATVA_HEX8 = 2, TATVA_QUAD4 = 3, TATVA_TR
  *   NEO_HOOKEAN_PHASE_FIELD ((1-phi)^2+k) psi_NH + Gc (phi^2/(2l) + l/2 |grad phi|^2),   params {mu, lambda, Gc, l, k}
  *                           nodal state interleaved [ux,uy,uz,phi] (tatva/compound/__init__.py:334-389)   */
 enum { TATVA_LINEAR_ELASTIC = 0, TATVA_NEO_HOOKEAN = 1, TATVA_NEO_HOOKEAN_PHASE_FIELD = 2 };
+#define TATVA_USER_LAW_BASE 1000 /* material ids handed out by tatva_law_register */
 
 /* error codes (negative); positive return values are cudaError_t */
 enum {
@@ -90,6 +91,20 @@ int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
  * tatva_op_interpolate returns TATVA_E_UNSUPPORTED with a custom rule.                                              */
 int tatva_plan_set_quadrature(tatva_plan_t* plan, int nq, const double* points, const double* weights,
                               tatva_stream_t stream);
+
+/* ---- user-supplied energy densities (README.md:93: in the reference the density is user code differentiated by JAX) ----
+ * `cuda_source` is the CUDA text of  `struct UserLaw { static constexpr int dim, dpn, val_lo, n_params; double prm[..];
+ * struct Cache; using S = tatva::QState<dpn, dim>; prepare / psi / first / second }`  — the `Mat` interface of
+ * csrc/common.cuh; tatva_b200/lawgen.py writes it from a density given once on symbols (forward-over-reverse AD of its
+ * straight-line program).  The returned material id (>= TATVA_USER_LAW_BASE) is accepted by tatva_energy / _residual /
+ * _hvp / _hvp_elems / _residual_elems / _hvp_lifted / _hessian_diag / _hvp_dot: at first use with a plan the source is
+ * compiled by NVRTC into the same fused kernel templates as the built-in laws (per element kind and device, cached)
+ * and launched on the caller's stream.  `params` of those calls fill prm[0..n_params).  tatva_csr_assemble returns
+ * TATVA_E_UNSUPPORTED for a user law (sparse.jacfwd then runs one fused HVP per colour).  A failed compilation
+ * returns TATVA_E_INVALID; its log is in tatva_law_compile_log.                                                    */
+int tatva_law_register(const char* cuda_source, int dim, int dofs_per_node, int n_params, int uses_values,
+                       int* material_id);
+int tatva_law_compile_log(char* buf, int len);
 /* Optional shared-memory staging tiles for gather-bound elements (Tet4 x neo-Hookean residual / HVP): tile t =
  * elements [128 t, 128 (t+1)); d_tile_nodes[d_tile_ptr[t] .. d_tile_ptr[t+1]) are its sorted unique nodes and
  * d_tile_conn (n_elems, npe) uint16 its connectivity in tile-local indices (tatva_host_build_tiles).  The CTA

@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libtatva_b200.so")
 # enums mirrored from include/tatva_b200.h
 TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
+USER_LAW_BASE = 1000
 PLAN_CACHE_WEIGHTS = 1
-ABI_VERSION = 3  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
+ABI_VERSION = 4  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
@@ -31,6 +32,8 @@ SIGNATURES = {
     "tatva_plan_destroy": (C.c_int, [vp]),
     "tatva_plan_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_i64p, c_i64p]),
     "tatva_plan_set_variant": (C.c_int, [vp, C.c_int]),
+    "tatva_law_register": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "tatva_law_compile_log": (C.c_int, [C.c_char_p, C.c_int]),
     "tatva_plan_set_quadrature": (C.c_int, [vp, C.c_int, c_f64p, c_f64p, vp]),
     "tatva_plan_set_tiles": (C.c_int, [vp, vp, vp, vp, C.c_int]),
     "tatva_plan_set_point_grid": (C.c_int, [vp, C.c_int, C.c_int, c_f64p, c_f64p, vp, vp]),

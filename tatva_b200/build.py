@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtatva_b200.so")
-SOURCES = ["generic.cu", "neo_hookean.cu", "host.cpp", "xla_ffi_shim.cc"]  # the shim is empty without jaxlib headers
+SOURCES = ["generic.cu", "neo_hookean.cu", "user_law.cu", "host.cpp", "xla_ffi_shim.cc"]  # the shim is empty without jaxlib headers
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "tatva_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -74,13 +74,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
+def _embed_sources(objdir: str) -> None:
+    """The text of the kernel-template headers as C string literals (build/embedded_sources.inc): user_law.cu hands them
+    to NVRTC when it compiles a user-supplied constitutive law into the same fused kernel templates."""
+    out = []
+    for var, name in (("kSrcCommon", "common.cuh"), ("kSrcFused", "fused.cuh")):
+        with open(os.path.join(CSRC, name)) as f:
+            text = f.read()
+        assert ')TATVA_SRC"' not in text
+        # string literals are limited to 64 KiB by some front ends: emit adjacent raw literals of <= 16 KiB
+        chunks = [text[i : i + 16000] for i in range(0, len(text), 16000)]
+        out.append(f"static const char {var}[] =\n" + "\n".join(f'R"TATVA_SRC({c})TATVA_SRC"' for c in chunks) + ";\n")
+    path = os.path.join(objdir, "embedded_sources.inc")
+    new = "".join(out)
+    if not os.path.exists(path) or open(path).read() != new:
+        with open(path, "w") as f:
+            f.write(new)
+
+
 def _build_locked(verbose: bool, objdir: str) -> str:
     nvcc = _nvcc()
+    _embed_sources(objdir)
     objs = []
     procs = []
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, "-I", objdir, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -92,7 +111,7 @@ def _build_locked(verbose: bool, objdir: str) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
     tmp = LIB + f".tmp{os.getpid()}"
-    link = [nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fopenmp", "-lgomp"]
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
     subprocess.run(link, check=True)
     os.replace(tmp, LIB)
     with open(STAMP, "w") as f:

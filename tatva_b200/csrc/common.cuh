@@ -2,10 +2,21 @@
 // All arithmetic is FP64; nothing here touches tensor cores (the per-element contractions
 // are 2x2 / 3x3 / 3x8).  Reference citations are relative to the tatva v0.11.1 tree.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/tatva_b200.h"
+#else
+// Run-time compilation (NVRTC, csrc/user_law.cu): no host headers; the few names the device code needs.
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned short uint16_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+typedef unsigned long size_t;
+enum { TATVA_TRI3 = 0, TATVA_TET4 = 1, TATVA_HEX8 = 2, TATVA_QUAD4 = 3, TATVA_TRI6 = 4, TATVA_QUAD8 = 5, TATVA_LINE2 = 6, TATVA_LINE3 = 7 };
+#endif
 
 #define TATVA_HD __host__ __device__ __forceinline__
 #define TATVA_D __device__ __forceinline__
@@ -634,7 +645,7 @@ struct NeoHookeanPhaseField {
 // that the lane-strided staging stores are free of bank conflicts (an even stride such as 12 or 24 doubles puts
 // every 4th / 2nd lane on the same bank).
 template <int NPE, int DPN>
-constexpr int grouped_scatter_words() {
+TATVA_HD constexpr int grouped_scatter_words() {
   return 32 * ((NPE * DPN) | 1) + 16 * (NPE | 1);
 }
 template <int NPE, int DPN>
@@ -658,15 +669,16 @@ TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const
   __syncwarp();
 }
 template <int NPE, int DPN>
-constexpr size_t grouped_scatter_smem(int warps) {
+TATVA_HD constexpr size_t grouped_scatter_smem(int warps) {
   return (size_t)warps * grouped_scatter_words<NPE, DPN>() * sizeof(double);
 }
 
+}  // namespace tatva
+
+#ifndef __CUDACC_RTC__  // everything below is host code
 // ---------------------------------------------------------------------------------------------
 // The plan (opaque to C callers)
 // ---------------------------------------------------------------------------------------------
-
-}  // namespace tatva
 
 struct tatva_plan {
   int element;
@@ -729,6 +741,13 @@ inline int grid_for(int64_t n, int block = kBlock) { return (int)((n + block - 1
     if (_e != cudaSuccess) return (int)_e;  \
   } while (0)
 
+// user-supplied laws compiled at run time (user_law.cu); material ids >= TATVA_USER_LAW_BASE
+bool is_user_law(int material);
+int user_law_info(int material, int* dpn);
+int user_law_launch(const tatva_plan* p, int material, int what, const double* prm, int n_params, const double* u,
+                    const double* v, const int32_t* map, double* out, cudaStream_t st);
+int sum_partials(const double* partials, int n, double* out, cudaStream_t st);  // fixed-order sum (generic.cu)
+
 // entry points implemented in the per-topic translation units
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st);
@@ -744,3 +763,4 @@ int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const dou
 int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
 
 }  // namespace tatva
+#endif  // !__CUDACC_RTC__

@@ -1623,6 +1623,14 @@ int tatva_op_sum_rows(tatva_plan_t* p, const double* d_in, int64_t rows, int nv,
 // ---- fused dispatch ------------------------------------------------------------------------------
 }  // extern "C"
 
+namespace tatva {
+int sum_partials(const double* partials, int n, double* out, cudaStream_t st) {
+  k_sum_rows_final<<<1, 256, 0, st>>>(partials, n, 1, out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+}  // namespace tatva
+
 template <class El, class Mat, int MODE>
 static int launch_fused(tatva_plan* p, const Mat& mat, const double* u, const double* v, double* out, cudaStream_t st) {
   const int grid = grid_for(p->n_elems);
@@ -1645,6 +1653,7 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
   if (!p || !prm || !u || !out) return TATVA_E_INVALID;
   if (MODE == MODE_HVP && !v) return TATVA_E_INVALID;
   const int el = p->element;
+  if (is_user_law(material)) return user_law_launch(p, material, MODE, prm, n_params, u, v, nullptr, out, st);
   if (p->custom) {  // user quadrature rule: the generic template over Custom<El> (the specialised kernels carry the default rule)
     TATVA_CUDA_TRY(install_rule(p, st));
     if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
@@ -1760,6 +1769,7 @@ int tatva_hessian_diag(tatva_plan_t* p, int material, const double* params, int 
                        double* d_diag, tatva_stream_t stream) {
   if (!p || !params || !d_u || !d_diag) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
+  if (is_user_law(material)) return user_law_launch(p, material, 3, params, n_params, d_u, nullptr, nullptr, d_diag, st);
   if (p->custom) TATVA_CUDA_TRY(install_rule(p, st));
   return for_element_law(p->element, material, params, n_params, [&](auto el, auto mat) -> int {
     using El = decltype(el);
@@ -1779,6 +1789,7 @@ int tatva_hvp_lifted(tatva_plan_t* p, int material, const double* params, int n_
   if (!p || !params || !d_u_full || !d_v_red || !d_dof_map || !d_y_red || n_red <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(d_y_red, 0, sizeof(double) * n_red, st));
+  if (is_user_law(material)) return user_law_launch(p, material, 4, params, n_params, d_u_full, d_v_red, d_dof_map, d_y_red, st);
   if (!p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC)
     return hex8_nh_hvp_modal_lifted(p, params[0], params[1], d_u_full, d_v_red, d_dof_map, d_y_red, st);
   if (p->custom) TATVA_CUDA_TRY(install_rule(p, st));
@@ -1829,7 +1840,9 @@ int tatva_hvp_dot(tatva_plan_t* p, int material, const double* params, int n_par
                   tatva_stream_t stream) {
   if (!p || !params || !d_u || !d_v || !d_y || !d_scalars || !d_partials || slot < 0 || slot > 7) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  const int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+  int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+  if (is_user_law(material)) user_law_info(material, &dpn);
+      if (is_user_law(material)) user_law_info(material, &dpn);
   const int64_t n = p->n_nodes * dpn;
   if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * n, st));
   if (fuse_dot && !p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
@@ -1938,6 +1951,7 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
   if (elem_count == 0) {
     if (zero_y) {
       int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+      if (is_user_law(material)) user_law_info(material, &dpn);
       TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * dpn, (cudaStream_t)stream));
     }
     return TATVA_OK;
@@ -1955,6 +1969,7 @@ int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, in
   if (elem_count == 0) {
     if (zero_r) {
       int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
+      if (is_user_law(material)) user_law_info(material, &dpn);
       TATVA_CUDA_TRY(cudaMemsetAsync(d_r, 0, sizeof(double) * p->n_nodes * dpn, (cudaStream_t)stream));
     }
     return TATVA_OK;
@@ -2003,6 +2018,7 @@ static int csr_dispatch(tatva_plan_t* p, int material, const double* prm, int n_
   if (!p || !prm || !d_u || !d_indptr || !d_pos || !d_data || nnz <= 0) return TATVA_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int el = p->element;
+  if (is_user_law(material)) return TATVA_E_UNSUPPORTED;  // sparse.jacfwd then runs the coloured route on the fused HVP
   if (p->custom) {  // user quadrature rule: the generic per-entry kernel over Custom<El>
     TATVA_CUDA_TRY(install_rule(p, st));
     return for_element_law(el, material, prm, n_params, [&](auto e, auto mat) -> int {

@@ -275,6 +275,8 @@ def _direct_assembler(fn, colored_matrix):
     """The one-kernel assembler for a fused residual, or None when the pattern is not node-blocked (the direct kernel
     writes (a, b) blocks at one offset in all dpn rows of node a; `tatva_host_csr_element_positions` verifies that).
     The caller then runs the reference's coloured algorithm: one fused HVP kernel per colour (sparse/base.py:230-270)."""
+    if fn.material.material_id >= _lib.USER_LAW_BASE:  # run-time compiled laws have no assembly kernel: coloured route
+        return None
     try:
         return _Assembler(fn.op, fn.material, colored_matrix)
     except (_lib.TatvaError, ValueError):
