@@ -356,7 +356,59 @@ def secondary_single_gpu(device, hbm_peak_gbs):
         ms_r, x_r = cg_ms(ConjugateGradient(red.matvec, n, device, use_graph=True), b)
         out["c3_cg_iteration_hex8_128"] = dict(ms=round(ms_m, 5), value=n / (ms_m * 1e-3), unit="DOF/s", how="CUDA graph; full-size vectors around the unconstrained HVP kernel, Dirichlet rows masked in the update pass (MaskedOperator)",
                                                ms_reduced_space_lifted_kernel=round(ms_r, 5), iterate_rel_diff_after_100=float((mo.restrict(x_m) - x_r).norm() / x_r.norm()))
-        del op, mo, red
+        del mo, red
+        # user-supplied densities at config 3 (README.md:93: the density is user code): written once on symbols, compiled
+        # at run time into the fused kernel template; beside them the built-in law through the same generic template and
+        # the r01 route for a density without a kernel (autograd through the Operator building blocks)
+        try:
+            import sympy as sp
+
+            def psi_nh(G, mu, lam):
+                F = sp.eye(3) + G
+                lnJ = sp.log(F.det())
+                return mu / 2 * ((F.T * F).trace() - 3 - 2 * lnJ) + lam / 2 * lnJ**2
+
+            def psi_mr(G, c1, c2, kappa):
+                F = sp.eye(3) + G
+                Cm = F.T * F
+                J = F.det()
+                I1 = Cm.trace()
+                I2 = (I1**2 - (Cm * Cm).trace()) / 2
+                return c1 * (J ** sp.Rational(-2, 3) * I1 - 3) + c2 * (J ** sp.Rational(-4, 3) * I2 - 3) + kappa / 2 * (J - 1) ** 2
+
+            N, E = c.shape[0], el.shape[0]
+            u = torch.as_tensor(u_, device=device)
+            v = torch.as_tensor(np.random.default_rng(1).normal(size=c.shape), device=device)
+            y = torch.empty_like(u)
+            nb = 8 * 12 * N + 32 * E
+            op.set_variant(1)
+            rec("c3_hvp_generic_template_builtin_neo_hookean", _timeit(lambda: op._raw_hvp(mat, u, v, out=y), reps=10), nb, 3 * N, "DOF")
+            ref = y.clone()
+            op.set_variant(0)
+            law_nh = materials.UserLaw.from_psi(psi_nh, (500.0, 1000.0))
+            law_mr = materials.UserLaw.from_psi(psi_mr, (120.0, 30.0, 900.0))
+            ms = _timeit(lambda: op._raw_hvp(law_nh, u, v, out=y), reps=10)
+            rec("c3_hvp_user_law_neo_hookean", ms, nb, 3 * N, "DOF", rel_err_vs_builtin=float((y - ref).norm() / ref.norm()), ops=law_nh.generated.op_counts(),
+                how="density written once on symbols -> source-to-source AD (lawgen) -> NVRTC -> k_fused<Hex8, UserLaw, HVP>")
+            rec("c3_hvp_user_law_mooney_rivlin", _timeit(lambda: op._raw_hvp(law_mr, u, v, out=y), reps=10), nb, 3 * N, "DOF", ops=law_mr.generated.op_counts())
+
+            def hv_autograd():
+                uu = u.detach().requires_grad_(True)
+                F = op.grad(uu) + torch.eye(3, dtype=torch.float64, device=device)
+                lnJ = torch.log(torch.linalg.det(F))
+                psi = 250.0 * ((F * F).sum((-1, -2)) - 3 - 2 * lnJ) + 500.0 * lnJ * lnJ
+                (g,) = torch.autograd.grad(op.integrate(psi), uu, create_graph=True)
+                (hv,) = torch.autograd.grad(g, uu, grad_outputs=v)
+                return hv
+
+            hv = hv_autograd()
+            rec("c3_hvp_autograd_route_neo_hookean", _timeit(hv_autograd, reps=3, warm=1), nb, 3 * N, "DOF", rel_err_vs_builtin=float((hv - ref).norm() / ref.norm()),
+                how="torch double backward through op.grad / op.integrate with (E, Q, 3, 3) temporaries in HBM: the r01 route for a density without a kernel")
+            del hv
+        except ImportError:
+            out["c3_user_law"] = "sympy not available"
+        del op
+        torch.cuda.empty_cache()
     return out
 
 

@@ -142,8 +142,12 @@ def _lower(expr, prog, env):
         elif e.is_Number:
             if e.is_negative:
                 r = prog.new("div", ONE, _lower(sp.Pow(expr.base, -e), prog, env))
-            else:
+            elif e.is_Integer:
                 r = prog.new("powc", b, _c(float(e)))
+            else:
+                # b ** k for a non-integer constant k (b > 0, e.g. J ** (-2/3)): exp(k log b).  Several powers of one base
+                # share the logarithm, and exp / log cost a fraction of the general pow() with its special cases.
+                r = prog.new("exp", prog.new("mul", _c(float(e)), prog.new("log", b)))
         else:
             r = prog.new("exp", prog.new("mul", _lower(e, prog, env), prog.new("log", b)))
     elif isinstance(expr, sp.log):

@@ -87,6 +87,21 @@ def smooth_u(coords):
     )
 
 
+def hvp_probe_hi(dE, x, v, ws, d):
+    """w . H v to ~1e-13: the reference energy's complex-step directional derivative dE(x)[w] (exact to rounding)
+    differentiated along v by the 8th-order central difference, at step d AND d/2 — the second value is the fixture,
+    their difference the recorded error estimate (truncation ~ (d / R)^8 with R the distance to det F = 0, rounding
+    ~ eps |dE| / d: both far below 1e-12 for the steps used here)."""
+    cf = (4.0 / 5, -1.0 / 5, 4.0 / 105, -1.0 / 280)
+
+    def diff(w, dd):
+        return sum(cf[k] * (dE(x + (k + 1) * dd * v, w) - dE(x - (k + 1) * dd * v, w)) for k in range(4)) / dd
+
+    a = np.array([diff(w, d) for w in ws])
+    b = np.array([diff(w, d / 2) for w in ws])
+    return b, np.abs(a - b) / np.abs(b)
+
+
 def make_case(kind):
     if kind == "tri3":
         c, el = orc.mesh_unit_square_tri(4, 3)
@@ -183,6 +198,7 @@ def operator_fixtures(out):
             hv[k] = (-dE(u + 2 * d * v, ws[k]) + 8 * dE(u + d * v, ws[k]) - 8 * dE(u - d * v, ws[k]) + dE(u - 2 * d * v, ws[k])) / (12 * d)
         out[p + "hvp_probe_w"] = ws
         out[p + "hvp_probe_wHv"] = hv
+        out[p + "hvp_probe_wHv_hi"], out[p + "hvp_probe_wHv_hi_err"] = hvp_probe_hi(dE, u, v, ws, 2e-3)
 
 
 def custom_rule_fixtures(out):
@@ -273,6 +289,7 @@ def more_operator_fixtures(out):
         dE = lambda uu, w: np.imag(E(uu.astype(complex) + 1j * h * w)) / h  # noqa: E731
         out[p + "hvp_probe_w"] = ws
         out[p + "hvp_probe_wHv"] = np.array([(-dE(u + 2 * d * v, w) + 8 * dE(u + d * v, w) - 8 * dE(u - d * v, w) + dE(u - 2 * d * v, w)) / (12 * d) for w in ws])
+        out[p + "hvp_probe_wHv_hi"], out[p + "hvp_probe_wHv_hi_err"] = hvp_probe_hi(dE, u, v, ws, 2e-3)
 
 
 def line_meshes():
@@ -417,6 +434,7 @@ def phase_field_fixtures(out):
         dE = lambda ss, w: np.imag(E(ss.astype(complex) + 1j * h * w)) / h  # noqa: E731
         out[p + "hvp_probe_w"] = ws
         out[p + "hvp_probe_wHv"] = np.array([(-dE(st + 2 * d * t, w) + 8 * dE(st + d * t, w) - 8 * dE(st - d * t, w) + dE(st - 2 * d * t, w)) / (12 * d) for w in ws])
+        out[p + "hvp_probe_wHv_hi"], out[p + "hvp_probe_wHv_hi_err"] = hvp_probe_hi(dE, st, t, ws, 1e-3)
 
 
 def colored_jacobian_fixtures(out):

@@ -572,3 +572,26 @@ def test_custom_quadrature_rule_fused_kernels_vs_oracle(kind, order, n):
     if kind == "hex8":
         op0 = _make_op(kind, c, el)
         assert _rel(op0.hvp(mat)(u, v).cpu().numpy(), Hv) > 1e-8
+
+
+@pytest.mark.parametrize("kind", ["tri3", "tet4", "hex8"])
+def test_fused_kernels_against_derivatives_of_the_reference_energy(golden, kind):
+    """The CUDA energy / residual / HVP directly against quantities derived from the REFERENCE's own energy
+    op.integrate(psi(op.grad(u))) (tests/golden/make_golden.py): E itself, dE/du by complex step (~1e-16), and
+    w . H v by complex step x 8th-order central differences (~1e-13), tolerance 1e-12 — no oracle in between.
+    Every Hex8 HVP kernel variant is held to the same fixture."""
+    g = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    c, el, u, v = g("coords"), g("conn"), g("u"), g("v")
+    _, _, materials = _tb()
+    mat = materials.LinearElastic(*g("mat")) if kind == "tri3" else materials.NeoHookean(*g("mat"))
+    op = _make_op(kind, c, el)
+    assert abs(float(op.energy(mat)(u)) - float(g("energy"))) <= 1e-12 * abs(float(g("energy")))
+    r = op.residual(mat)(u).cpu().numpy()
+    assert np.abs(r - g("residual_cs")).max() <= 1e-11 * np.abs(r).max()
+    variants = op.hvp_variants() if kind == "hex8" else (0,)
+    for variant in variants:
+        op.set_variant(variant)
+        Hv = op.hvp(mat)(u, v).cpu().numpy()
+        wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), Hv)
+        np.testing.assert_allclose(wHv, g("hvp_probe_wHv_hi"), rtol=1e-12, err_msg=f"variant {variant}")
+    op.set_variant(0)

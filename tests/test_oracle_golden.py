@@ -140,6 +140,9 @@ def test_energy_residual_hvp_match_reference_energy_derivatives(golden, kind):
     wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), Hv)
     # complex step x 4th-order central difference: ~1e-9 relative
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
+    # r02: complex step x 8th-order central difference at two steps (recorded estimate <= 2e-10 at the coarse step, /256
+    # at the fine one): the oracle's HVP is pinned by the REFERENCE's own energy to 1e-12
+    np.testing.assert_allclose(wHv, g("hvp_probe_wHv_hi"), rtol=1e-12)
 
 
 @pytest.mark.parametrize("name", ["hex3", "tri4"])
@@ -226,6 +229,7 @@ def test_phase_field_energy_through_the_reference_operator(golden, kind):
     np.testing.assert_allclose(r, g("residual_cs"), rtol=1e-10, atol=1e-12 * np.abs(r).max())
     wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), orc.hvp_pf(kind, mat, c, el, s, t))
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-7)
+    np.testing.assert_allclose(wHv, g("hvp_probe_wHv_hi"), rtol=1e-12)  # 8th-order probe, see make_golden.hvp_probe_hi
 
 
 @pytest.mark.parametrize("kind", ["quad4", "tri6", "quad8"])
@@ -240,6 +244,7 @@ def test_energy_derivatives_of_the_other_plane_elements(golden, kind):
     np.testing.assert_allclose(r, g("residual_cs"), rtol=1e-11, atol=1e-12 * np.abs(r).max())
     wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), orc.hvp(kind, mat, c, el, u, v))
     np.testing.assert_allclose(wHv, g("hvp_probe_wHv"), rtol=1e-9)  # quadratic energy: the difference quotient is exact
+    np.testing.assert_allclose(wHv, g("hvp_probe_wHv_hi"), rtol=1e-12)
 
 
 @pytest.mark.parametrize("name,dpn", [("tri3_8x8_d2", 2), ("tet4_3_d3", 3), ("tet4_2_d4", 4), ("hex8_3_d3", 3)])

@@ -219,6 +219,63 @@ if want("cg"):
         its[name] = dict(iterations=info["iterations"], converged=info["converged"], wall_s=round(time.perf_counter() - t0, 3))
     print(json.dumps(dict(kernel="cg_vs_pcg_to_1e-8_hex8_128", **its)), flush=True)
 
+# ---- user-supplied densities at config 3: run-time compiled fused kernels vs the generic template vs the autograd route ----
+if want("userlaw"):
+    import sympy as sp
+    from bench import synthetic_inputs
+    c, el, u_, v_ = synthetic_inputs(128)
+    op = tatva_b200.Operator(Mesh(coords=c, elements=el), element.Hexahedron8())
+    N, E = c.shape[0], el.shape[0]
+    u, v = torch.as_tensor(u_, device="cuda"), torch.as_tensor(v_, device="cuda")
+    y = torch.empty_like(u)
+    nh = materials.NeoHookean(500.0, 1000.0)
+
+    def psi_nh(G, mu, lam):
+        F = sp.eye(3) + G
+        lnJ = sp.log(F.det())
+        return mu / 2 * ((F.T * F).trace() - 3 - 2 * lnJ) + lam / 2 * lnJ**2
+
+    def psi_mr(G, c1, c2, kappa):
+        F = sp.eye(3) + G
+        Cm = F.T * F
+        J = F.det()
+        I1 = Cm.trace()
+        I2 = (I1**2 - (Cm * Cm).trace()) / 2
+        return c1 * (J ** sp.Rational(-2, 3) * I1 - 3) + c2 * (J ** sp.Rational(-4, 3) * I2 - 3) + kappa / 2 * (J - 1) ** 2
+
+    bytes_hvp = 8 * (12 * N) + 32 * E
+    op.set_variant(1)
+    report("hex8_nh_hvp_c3_generic_template_builtin_law", timeit(lambda: op._raw_hvp(nh, u, v, out=y)), bytes_hvp, 3 * N, "DOF")
+    ref = y.clone()
+    op.set_variant(0)
+    t0 = time.perf_counter()
+    law_nh = materials.UserLaw.from_psi(psi_nh, (500.0, 1000.0))
+    law_mr = materials.UserLaw.from_psi(psi_mr, (120.0, 30.0, 900.0))
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    op._raw_hvp(law_nh, u, v, out=y)
+    torch.cuda.synchronize()
+    t_jit = time.perf_counter() - t0
+    report("hex8_user_law_neo_hookean_hvp_c3", timeit(lambda: op._raw_hvp(law_nh, u, v, out=y)), bytes_hvp, 3 * N, "DOF", rel_err_vs_builtin=float((y - ref).norm() / ref.norm()),
+           ops=law_nh.generated.op_counts(), codegen_s=round(t_gen, 2), nvrtc_first_call_s=round(t_jit, 2))
+    report("hex8_user_law_neo_hookean_residual_c3", timeit(lambda: op._raw_residual(law_nh, u)), 8 * (9 * N) + 32 * E, 3 * N, "DOF")
+    report("hex8_user_law_mooney_rivlin_hvp_c3", timeit(lambda: op._raw_hvp(law_mr, u, v, out=y)), bytes_hvp, 3 * N, "DOF", ops=law_mr.generated.op_counts())
+    report("hex8_user_law_mooney_rivlin_residual_c3", timeit(lambda: op._raw_residual(law_mr, u)), 8 * (9 * N) + 32 * E, 3 * N, "DOF")
+    # the r01 route for a density without a kernel: autograd (double backward) through the Operator building blocks,
+    # (E, Q, 3, 3) temporaries in HBM
+    def hv_autograd():
+        uu = u.detach().requires_grad_(True)
+        F = op.grad(uu) + torch.eye(3, dtype=torch.float64, device="cuda")
+        lnJ = torch.log(torch.linalg.det(F))
+        psi = 250.0 * ((F * F).sum((-1, -2)) - 3 - 2 * lnJ) + 500.0 * lnJ * lnJ
+        (g,) = torch.autograd.grad(op.integrate(psi), uu, create_graph=True)
+        (hv,) = torch.autograd.grad(g, uu, grad_outputs=v)
+        return hv
+    hv = hv_autograd()
+    report("hex8_neo_hookean_hvp_c3_autograd_route", timeit(hv_autograd, reps=5, warm=2), bytes_hvp, 3 * N, "DOF", rel_err_vs_builtin=float((hv - ref).norm() / ref.norm()),
+           peak_mem_GB=round(torch.cuda.max_memory_allocated() / 1e9, 2))
+    del op
+
 # ---- post-processing and boundary elements: interpolate (point location), project (mass CG), Line2 traction ----
 if want("post"):
     rng = np.random.default_rng(0)
