@@ -501,8 +501,11 @@ def test_invalid_meshes_raise_like_the_reference():
         tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0.0, 1.0, 2.0]])), element.Tri3())
     with pytest.raises(ValueError):
         tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.zeros((0, 3), dtype=np.int32)), element.Tri3())
+    # a user quadrature rule is accepted (r02); more than 64 points is not
+    op = tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0, 1, 2]], dtype=np.int32)), element.Tri3(quad_points=np.array([[0.2, 0.2]]), quad_weights=np.array([0.5])))
+    _assert_close(op.get_integration_weights(), np.array([[0.5]]), 1e-15)
     with pytest.raises(NotImplementedError):
-        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0, 1, 2]], dtype=np.int32)), element.Tri3(quad_points=np.array([[0.2, 0.2]]), quad_weights=np.array([0.5])))
+        tatva_b200.Operator(tatva_b200.Mesh(coords=X, elements=np.array([[0, 1, 2]], dtype=np.int32)), element.Tri3(quad_points=np.full((65, 2), 0.2), quad_weights=np.full(65, 0.5 / 65)))
 
 
 # ---- user quadrature rules: Element(quad_points, quad_weights), reference element/base.py:37-51 -----------------
