@@ -120,7 +120,9 @@ class DistributedHex8Problem:
             shape = f"{n}^3" if np.isscalar(n) else "x".join(str(a) for a in n)
             self.partition_desc = f"{world} GPUs, {grid[0]}x{grid[1]}x{grid[2]} blocks of {shape}, {how} ({'overlapped' if overlap else 'serial'})"
             n_owned = self.pop.n_owned
-            self.launches_per_step = 6  # pack, unpack-set, boundary + interior element kernels, pack, unpack-add
+            # own kernels per step: peer halo = pull, boundary + interior element kernels, push (replayed from one CUDA
+            # graph); NCCL halo = pack, unpack-set, boundary + interior element kernels, pack, unpack-add
+            self.launches_per_step = 4 if halo == "peer" else 6
         if variant:
             self.op.set_variant(variant)
         self.local_nodes, self.local_elems = c.shape[0], el.shape[0]
