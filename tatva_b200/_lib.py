@@ -15,7 +15,7 @@ TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
 USER_LAW_BASE = 1000
 PLAN_CACHE_WEIGHTS = 1
-ABI_VERSION = 4  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
+ABI_VERSION = 5  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
@@ -84,6 +84,8 @@ SIGNATURES = {
     "tatva_hvp_lifted_dot": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
     "tatva_cg_after_dot": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "tatva_hvp_dot": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
+    "tatva_host_csr_tile_schedule": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_i64p, c_i64p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.POINTER(C.c_uint32)]),
+    "tatva_csr_assemble_tiled": (C.c_int, [vp, C.c_int, c_f64p, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp]),
     "tatva_fp64_peak_tflops": (C.c_int, [c_f64p, vp]),
 }
 
@@ -101,6 +103,15 @@ def lib() -> C.CDLL:
     if _lib is None:
         from . import build as _build
 
+        override = os.environ.get("TATVA_B200_LIB")  # measurement aid: load an experimental build of the same ABI
+        if override:
+            L = C.CDLL(override)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+            return _lib
         stale = os.path.exists(LIB_PATH) and _build.needs_build()
         if not os.path.exists(LIB_PATH) or stale:
             # not built yet (fresh checkout) or older than its sources: compile it now if nvcc is around (cheap when up

@@ -819,7 +819,180 @@ __global__ void __launch_bounds__(kBlock) k_csr_grouped(const double* __restrict
     for (int t = lane; t < 32 * S; t += 32) {
       const int j = t / S, r = t - j * S;
       const int base = sbase[j * NBP + r / dpn];
+#ifdef TATVA_CSR_EXPERIMENT  // timing experiment: issue only every TATVA_CSR_EXPERIMENT-th RED group (wrong result)
+      if (base >= 0 && ((t / dpn) % TATVA_CSR_EXPERIMENT) == 0) atomicAdd(data + (int64_t)base + (r % dpn), sblk[j * SP + r]);
+#else
       if (base >= 0) atomicAdd(data + (int64_t)base + (r % dpn), sblk[j * SP + r]);
+#endif
+    }
+    __syncwarp();
+  }
+}
+
+// ---- tiled CSR assembly with on-chip combination of duplicate blocks ----------------------------------------
+// ncu of k_csr_grouped at config 2 (profiles/r02_csr_ncu.md): 8300 instructions per element (12 generic tangent
+// evaluations with select-built unit directions, a 144-entry staging / re-deal loop), LSU wavefronts 79 %, and 144 M
+// REDs of which most are duplicates: the 16 (row node, column node) blocks of a tet are shared with its neighbours.
+// Here a CTA owns a tile of kTile consecutive (locality-sorted) elements:
+//   phase 1  one thread per element: geometry and the law's rank structure — for the isotropic laws below the tangent
+//            block of nodes (a, b) is   K_ab = w1 (dNa . dNb) I + w2 g_b g_a^T + w3 g_a g_b^T   with per-element
+//            vectors dN_a, g_a and three scalars (27 doubles per tet) — parked in shared memory;
+//   phase 2  one thread per distinct block of the tile: sums the block's contributors from shared memory (plan-time
+//            schedule, tatva_host_csr_tile_schedule); the sums are re-dealt through a chunk buffer so that ONE RED per entry
+//            is issued with dpn consecutive lanes adding dpn consecutive doubles (one 32-byte sector).
+// ~3 x fewer REDs and ~4 x fewer instructions than k_csr_grouped.  Laws: neo-Hookean (g = F^-T dN, w2 = W (mu -
+// lambda lnJ), w3 = W lambda) and linear elasticity (g = dN, w2 = W mu, w3 = W lambda); w1 = W mu for both.
+constexpr int kTile = 128;
+
+template <class Mat>
+struct RankLaw;
+template <int DIM>
+struct RankLaw<LinearElastic<DIM>> {
+  template <int NPE>
+  TATVA_D static void eval(const LinearElastic<DIM>& m, double W, const double (&dN)[DIM][NPE], const double (&)[NPE][DIM],
+                           double (&g)[DIM][NPE], double (&w)[3]) {
+#pragma unroll
+    for (int j = 0; j < DIM; ++j)
+#pragma unroll
+      for (int n = 0; n < NPE; ++n) g[j][n] = dN[j][n];
+    w[0] = W * m.mu;
+    w[1] = W * m.mu;
+    w[2] = W * m.lmbda;
+  }
+};
+template <>
+struct RankLaw<NeoHookean> {
+  template <int NPE>
+  TATVA_D static void eval(const NeoHookean& m, double W, const double (&dN)[3][NPE], const double (&U)[NPE][3], double (&g)[3][NPE],
+                           double (&w)[3]) {
+    double F[3][3], Fi[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int n = 0; n < NPE; ++n) t = fma(U[n][i], dN[j][n], t);
+        F[i][j] = t;
+      }
+    const double lnJ = log(det_inv(F, Fi));
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int n = 0; n < NPE; ++n) g[c][n] = Fi[0][c] * dN[0][n] + Fi[1][c] * dN[1][n] + Fi[2][c] * dN[2][n];  // F^-T dN
+    w[0] = W * m.mu;
+    w[1] = W * (m.mu - m.lmbda * lnJ);
+    w[2] = W * m.lmbda;
+  }
+};
+
+template <class El, class Mat>
+__global__ void __launch_bounds__(kTile) k_csr_tiled(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                     int64_t E, Mat mat, const double* __restrict__ u,
+                                                     const int32_t* __restrict__ blk_ptr, const int32_t* __restrict__ blk_base,
+                                                     const int32_t* __restrict__ blk_rowlen, const int32_t* __restrict__ blk_base_t,
+                                                     const int32_t* __restrict__ blk_rowlen_t, const int32_t* __restrict__ con_ptr,
+                                                     const uint32_t* __restrict__ con, double* __restrict__ data) {
+  static_assert(El::max_nq == 1 && Mat::dpn == El::dim, "constant-gradient elements, one DOF per direction");
+  constexpr int D = El::dim, NPE = El::npe, NV = 2 * NPE * D + 3, NVP = NV | 1;
+  // [kTile][NVP], element-major with an odd stride: phase 1 (lane = element) and phase 2 (lanes read different fields of
+  // the same or of neighbouring elements) are both free of bank conflicts; a field-major layout puts every field of one
+  // element on the same bank, and the lanes of phase 2 mostly visit the same few elements (28 M conflicts, ncu).
+  extern __shared__ double sm_tile[];
+  const int64_t e = (int64_t)blockIdx.x * kTile + threadIdx.x;
+  if (e < E) {
+    int nd[NPE];
+    load_conn<El>(conn, e, nd);
+    double X[NPE][D], U[NPE][D], dN[D][NPE], g[D][NPE], w[3];
+    gather_rows(coords, nd, X);
+    gather_rows(u, nd, U);
+    const double W = geometry<El>(0, X, dN) * El::weight(0);
+    RankLaw<Mat>::template eval<NPE>(mat, W, dN, U, g, w);
+    double* row = sm_tile + threadIdx.x * NVP;
+#pragma unroll
+    for (int a = 0; a < NPE; ++a)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        row[a * D + j] = dN[j][a];
+        row[NPE * D + a * D + j] = g[j][a];
+      }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) row[2 * NPE * D + k] = w[k];
+  }
+  __syncthreads();
+  // phase 2: one thread per distinct block sums ALL D x D entries over the block's contributors (each contributor's
+  // vectors are read once), parks them in a chunk buffer, and the CTA re-deals the chunk so that D consecutive lanes add
+  // D consecutive doubles of one CSR row (one 32-byte sector per RED group).
+  constexpr int DD = D * D;
+  double* buf = sm_tile + NVP * kTile;                      // [kTile][DD], lane-major with an odd stride: conflict-free
+  int* sbase = reinterpret_cast<int*>(buf + DD * kTile);    // [kTile] block base position, -1 = none
+  int* srl = sbase + kTile;                                 // [kTile] row length of the block's row node
+  int* sbase_t = srl + kTile;                               // the same for the mirror block (b, a): K_ba = K_ab^T
+  int* srl_t = sbase_t + kTile;
+  const int b0 = __ldg(blk_ptr + blockIdx.x), nb = __ldg(blk_ptr + blockIdx.x + 1) - b0;
+  // every WARP walks its own chunks of 32 blocks (the schedule lists the blocks by decreasing contributor count, so the
+  // lanes of a warp loop about equally long) and re-deals them with warp-level synchronisation only
+  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+  double* wbuf = buf + wbase * DD;
+  for (int chunk = wbase; chunk < nb; chunk += kTile) {
+    const int bl = chunk + lane;
+    double acc[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc[i][k] = 0.0;
+    if (bl < nb) {
+      const int d = b0 + bl;
+      const int c0 = __ldg(con_ptr + d), c1 = __ldg(con_ptr + d + 1);
+      // the block's CSR positions are fetched now and consumed after the contributor loop (latency hidden behind it)
+      const int pb0 = __ldg(blk_base + d), pr0 = __ldg(blk_rowlen + d), pb1 = __ldg(blk_base_t + d), pr1 = __ldg(blk_rowlen_t + d);
+      uint32_t src_next = __ldg(con + c0);
+      for (int c = c0; c < c1; ++c) {
+        const uint32_t src = src_next;
+        if (c + 1 < c1) src_next = __ldg(con + c + 1);
+        const double* row = sm_tile + (src >> 8) * NVP;
+        const double* pa = row + ((src >> 4) & 15) * D;
+        const double* pb = row + (src & 15) * D;
+        double dNa[D], dNb[D], ga[D], gb[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          dNa[j] = pa[j];
+          dNb[j] = pb[j];
+          ga[j] = pa[NPE * D + j];
+          gb[j] = pb[NPE * D + j];
+        }
+        const double w1 = row[2 * NPE * D], w2 = row[2 * NPE * D + 1], w3 = row[2 * NPE * D + 2];
+        double dot = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) dot = fma(dNa[j], dNb[j], dot);
+        const double a1 = w1 * dot;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double a2 = w2 * ga[k], a3 = w3 * gb[k];
+#pragma unroll
+          for (int i = 0; i < D; ++i) acc[i][k] += fma(a2, gb[i], fma(a3, ga[i], (i == k) ? a1 : 0.0));
+        }
+      }
+      sbase[threadIdx.x] = pb0;
+      srl[threadIdx.x] = pr0;
+      sbase_t[threadIdx.x] = pb1;
+      srl_t[threadIdx.x] = pr1;
+    } else {
+      sbase[threadIdx.x] = -1;
+      sbase_t[threadIdx.x] = -1;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) wbuf[lane * DD + i * D + k] = acc[i][k];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < DD; ++j) {
+      const int q = lane + j * 32, owner = q / DD, r = q - owner * DD, hi = r / D, lo = r - hi * D;
+      // block (a, b): entry (i, k) = (hi, lo); mirror block (b, a): entry (k, i) = (hi, lo) holds acc[i = lo][k = hi]
+      const int base = sbase[wbase + owner], base_t = sbase_t[wbase + owner];
+      if (base >= 0) atomicAdd(data + (int64_t)base + (int64_t)hi * srl[wbase + owner] + lo, wbuf[q]);
+      if (base_t >= 0) atomicAdd(data + (int64_t)base_t + (int64_t)hi * srl_t[wbase + owner] + lo, wbuf[owner * DD + lo * D + hi]);
     }
     __syncwarp();
   }
@@ -2058,6 +2231,34 @@ int tatva_csr_assemble(tatva_plan_t* p, int material, const double* prm, int n_p
   return csr_dispatch(p, material, prm, n_params, d_u, d_indptr, nullptr, d_pos, nnz, d_data, stream);
 }
 // Symmetric variant: REDs only for the upper triangle, then a mirror pass (needs the column indices).
+// Tiled assembly with on-chip combination of duplicate blocks (k_csr_tiled): Tri3 / Tet4 with the neo-Hookean or the
+// linear-elastic law.  `d_conn` is the element list the schedule was built for (tatva_host_csr_tile_schedule, tile = 128),
+// normally a locality-sorted copy of the plan's connectivity.  TATVA_E_UNSUPPORTED for other (element, law) pairs.
+int tatva_csr_assemble_tiled(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
+                             const int32_t* d_conn, const int32_t* d_blk_ptr, const int32_t* d_blk_base,
+                             const int32_t* d_blk_rowlen, const int32_t* d_blk_base_t, const int32_t* d_blk_rowlen_t,
+                             const int32_t* d_con_ptr, const uint32_t* d_con, int64_t nnz, double* d_data,
+                             tatva_stream_t stream) {
+  if (!p || !prm || !d_u || !d_conn || !d_blk_ptr || !d_blk_base || !d_blk_rowlen || !d_blk_base_t || !d_blk_rowlen_t || !d_con_ptr || !d_con || !d_data || nnz <= 0) return TATVA_E_INVALID;
+  if (p->custom || n_params != 2) return TATVA_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)((p->n_elems + kTile - 1) / kTile);
+#define TATVA_TILED(EL, MAT, ...)                                                                                     \
+  {                                                                                                                   \
+    constexpr size_t smem = (size_t)(((2 * EL::npe * EL::dim + 3) | 1) + EL::dim * EL::dim + 2) * kTile * sizeof(double);     \
+    TATVA_CUDA_TRY(cudaMemsetAsync(d_data, 0, sizeof(double) * nnz, st));                                              \
+    k_csr_tiled<EL, MAT><<<grid, kTile, smem, st>>>(p->coords, d_conn, p->n_elems, MAT __VA_ARGS__, d_u, d_blk_ptr, d_blk_base, \
+                                                    d_blk_rowlen, d_blk_base_t, d_blk_rowlen_t, d_con_ptr, d_con, d_data); \
+    TATVA_LAUNCH_CHECK();                                                                                             \
+    return TATVA_OK;                                                                                                  \
+  }
+  if (material == TATVA_NEO_HOOKEAN && p->element == TATVA_TET4) TATVA_TILED(Tet4, NeoHookean, {prm[0], prm[1]})
+  if (material == TATVA_LINEAR_ELASTIC && p->element == TATVA_TET4) TATVA_TILED(Tet4, LinearElastic<3>, {prm[0], prm[1]})
+  if (material == TATVA_LINEAR_ELASTIC && p->element == TATVA_TRI3) TATVA_TILED(Tri3, LinearElastic<2>, {prm[0], prm[1]})
+#undef TATVA_TILED
+  return TATVA_E_UNSUPPORTED;
+}
+
 int tatva_csr_assemble_sym(tatva_plan_t* p, int material, const double* prm, int n_params, const double* d_u,
                            const int32_t* d_indptr, const int32_t* d_indices, const int32_t* d_pos, int64_t nnz,
                            double* d_data, tatva_stream_t stream) {

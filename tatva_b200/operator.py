@@ -26,7 +26,7 @@ from .element import Element
 from .mesh import Mesh
 
 
-_FUSED_CALLS = {"tatva_energy", "tatva_residual", "tatva_hvp", "tatva_hvp_lifted", "tatva_hvp_lifted_dot", "tatva_hvp_dot", "tatva_hessian_diag", "tatva_csr_assemble", "tatva_csr_assemble_sym", "tatva_csr_assemble_rows"}
+_FUSED_CALLS = {"tatva_energy", "tatva_residual", "tatva_hvp", "tatva_hvp_lifted", "tatva_hvp_lifted_dot", "tatva_hvp_dot", "tatva_hessian_diag", "tatva_csr_assemble", "tatva_csr_assemble_tiled", "tatva_csr_assemble_sym", "tatva_csr_assemble_rows"}
 
 
 def _stream() -> int:

@@ -177,7 +177,7 @@ class _Assembler:
     """Direct CSR assembly plan for (operator, material, pattern): device copies of indptr and of the
     element -> CSR position table."""
 
-    def __init__(self, op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None, symmetric: bool = False):
+    def __init__(self, op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None, symmetric: bool = False, tiled: bool | None = None):
         dpn = material.dofs_per_node(op.dim)
         indptr = np.ascontiguousarray(_np(colored_matrix.indptr), dtype=np.int32)
         indices = np.ascontiguousarray(_np(colored_matrix.indices), dtype=np.int32)
@@ -191,6 +191,17 @@ class _Assembler:
         )
         self.op, self.material, self.nnz = op, material, int(indices.shape[0])
         self.d_indptr = torch.as_tensor(indptr, device=op.device)
+        # Tiled kernel with on-chip combination of duplicate blocks (r02 default where it exists): constant-gradient
+        # elements with the neo-Hookean / linear-elastic law, default quadrature rule.
+        can_tile = (
+            op.element.kind in (_lib.TRI3, _lib.TET4) and not getattr(op, "_custom_rule", False) and not by_rows and not symmetric
+            and ((material.material_id == _lib.NEO_HOOKEAN and op.element.kind == _lib.TET4) or material.material_id == _lib.LINEAR_ELASTIC)
+        )
+        self.tiled = can_tile if tiled is None else (bool(tiled) and can_tile)
+        if tiled and not can_tile:
+            raise NotImplementedError("tiled assembly: Tri3 / Tet4 with NeoHookean or LinearElastic, default rule")
+        if self.tiled:
+            self._build_tiles(op, conn, dpn, indptr, indices)
         # Row-wise (atomic-free, deterministic) kernel for single-point elements; per-entry atomics otherwise.
         self.by_rows = False if by_rows is None else bool(by_rows)
         if self.by_rows and op.nq != 1:
@@ -211,12 +222,42 @@ class _Assembler:
             if self.symmetric:
                 self.d_indices = torch.as_tensor(indices, device=op.device)
 
+    def _build_tiles(self, op, conn, dpn, indptr, indices):
+        """Locality-sorted element list + the per-tile combine schedule (host C++, once per pattern)."""
+        from .mesh import locality_order
+
+        L = _lib.lib()
+        perm = locality_order(op.coords.cpu().numpy(), conn)
+        csort = np.ascontiguousarray(conn[perm], dtype=np.int32)
+        E, npe = csort.shape
+        pos = np.empty((E, npe, npe), dtype=np.int32)
+        _lib.check(L.tatva_host_csr_element_positions(_i32p(csort), E, npe, dpn, _i32p(indptr), _i32p(indices), _i32p(pos)), "csr_element_positions")
+        tile = 128
+        n_tiles = (E + tile - 1) // tile
+        blk_ptr = np.empty(n_tiles + 1, dtype=np.int32)
+        n_blk, n_con = C.c_int64(), C.c_int64()
+        args = (_i32p(csort), E, npe, dpn, tile, _i32p(indptr), _i32p(pos), _i32p(blk_ptr), C.byref(n_blk), C.byref(n_con))
+        _lib.check(L.tatva_host_csr_tile_schedule(*args, None, None, None, None, None, None), "csr_tile_schedule")
+        nb, nc = int(n_blk.value), int(n_con.value)
+        base, rl, base_t, rl_t = (np.empty(nb, dtype=np.int32) for _ in range(4))
+        con_ptr = np.empty(nb + 1, dtype=np.int32)
+        con = np.empty(nc, dtype=np.uint32)
+        _lib.check(L.tatva_host_csr_tile_schedule(*args, _i32p(base), _i32p(rl), _i32p(base_t), _i32p(rl_t), _i32p(con_ptr), con.ctypes.data_as(C.POINTER(C.c_uint32))), "csr_tile_schedule")
+        dev = lambda a: torch.as_tensor(a.view(np.int32) if a.dtype == np.uint32 else a, device=op.device)  # noqa: E731
+        self._tile = dict(conn=dev(csort), blk_ptr=dev(blk_ptr), blk_base=dev(base), blk_rowlen=dev(rl), blk_base_t=dev(base_t), blk_rowlen_t=dev(rl_t), con_ptr=dev(con_ptr), con=dev(con))
+        self.tile_stats = dict(n_tiles=n_tiles, distinct_blocks_upper=nb, contributions_upper=nc, contributions_all=int(E * npe * npe), combine_ratio=nc / nb)
+
     def __call__(self, u, out=None) -> torch.Tensor:
         op = self.op
         uc = op._as_dev(u).contiguous()
         if out is None:
             out = torch.empty(self.nnz, dtype=torch.float64, device=op.device)
         prm, n = _lib.params_array(self.material.params())
+        if self.tiled:
+            t = self._tile
+            op._call("tatva_csr_assemble_tiled", self.material.material_id, prm, n, uc.data_ptr(), t["conn"].data_ptr(), t["blk_ptr"].data_ptr(), t["blk_base"].data_ptr(),
+                     t["blk_rowlen"].data_ptr(), t["blk_base_t"].data_ptr(), t["blk_rowlen_t"].data_ptr(), t["con_ptr"].data_ptr(), t["con"].data_ptr(), self.nnz, out.data_ptr())
+            return out
         if self.by_rows:
             op._call("tatva_csr_assemble_rows", self.material.material_id, prm, n, uc.data_ptr(), self.d_indptr.data_ptr(), self.d_indices.data_ptr(),
                      self.d_n2e_ptr.data_ptr(), self.d_n2e.data_ptr(), out.data_ptr())
@@ -227,13 +268,13 @@ class _Assembler:
         return out
 
 
-def assembler(op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None, symmetric: bool = False) -> Callable:
+def assembler(op, material, colored_matrix: ColoredMatrix, by_rows: bool | None = None, symmetric: bool = False, tiled: bool | None = None) -> Callable:
     """u -> CSR data (nnz,) of d^2E/du^2 on the pattern of `colored_matrix` (one kernel).
     Default: element-per-thread kernel with sector-grouped FP64 REDs for every entry (0.46 ms at config 2).
     symmetric=True adds only the upper triangle by RED and mirrors the lower one (measured slower on B200: 0.61 ms —
     the RED loop is issue-bound, not L2-bound, so halving the active lanes does not pay for the mirror pass).
     by_rows=True selects the atomic-free row-wise kernel (Tri3, Tet4): bitwise reproducible, ~1.6x slower."""
-    return _Assembler(op, material, colored_matrix, by_rows, symmetric)
+    return _Assembler(op, material, colored_matrix, by_rows, symmetric, tiled)
 
 
 def _coloured_columns(fn_jvp, u, colored_matrix, color_batch_size):

@@ -70,7 +70,15 @@ def test_direct_assembly_matches_coloured_oracle(kind, n):
     mesh, op = _setup(kind, c, el)
     pat = sparse.pattern_from_mesh(mesh, dpn)
     cm = sparse.ColoredMatrix.from_csr(pat)
-    data = sparse.assembler(op, mat, cm)(u).cpu().numpy()
+    asm = sparse.assembler(op, mat, cm)
+    data = asm(u).cpu().numpy()
+    # r02 default for Tri3 / Tet4: the tiled kernel (duplicate blocks combined on chip); the element-per-thread kernel
+    # with one RED group per element block must give the same matrix
+    assert asm.tiled == (kind != "hex8")
+    if asm.tiled:
+        assert asm.tile_stats["combine_ratio"] > 1.5
+        plain = sparse.assembler(op, mat, cm, tiled=False)(u).cpu().numpy()
+        assert _rel(plain, data) < 1e-13
     sym = sparse.assembler(op, mat, cm, symmetric=True)(u).cpu().numpy()  # upper triangle by RED + mirror pass
     assert _rel(sym, data) < 1e-13
     if kind != "hex8":  # both kernels: per-entry atomics (default) and the deterministic row-wise one

@@ -176,3 +176,47 @@ def test_colouring_node_level_sweep_is_bit_exact_with_the_per_dof_greedy(case):
     ref = orc.distance2_colors(ip, ix, n)
     got = sparse.distance2_colors(np.asarray(ip, dtype=np.int32), np.asarray(ix, dtype=np.int32), n)
     np.testing.assert_array_equal(got, ref)
+
+
+def test_csr_tile_schedule_lists_every_upper_contribution_once():
+    """Combine schedule of the tiled assembly (tatva_host_csr_tile_schedule): every (element, a, b) with row node <=
+    column node appears exactly once, under the block that holds its CSR position and that of its mirror; blocks of a
+    tile are ordered by decreasing contributor count."""
+    c, el = orc.mesh_box_tet((1, 1, 1), (5, 4, 3))
+    dpn = 3
+    ip, ix = sparse.pattern_arrays(el, len(c), dpn)
+    L = _lib.lib()
+    i32 = lambda a: a.ctypes.data_as(_lib.c_i32p)  # noqa: E731
+    E, npe = el.shape
+    pos = np.empty((E, npe, npe), dtype=np.int32)
+    assert L.tatva_host_csr_element_positions(i32(el), E, npe, dpn, i32(ip), i32(ix), i32(pos)) == 0
+    tile = 128
+    nt = (E + tile - 1) // tile
+    bp = np.empty(nt + 1, dtype=np.int32)
+    nb, nc = C.c_int64(), C.c_int64()
+    args = (i32(el), E, npe, dpn, tile, i32(ip), i32(pos), i32(bp), C.byref(nb), C.byref(nc))
+    assert L.tatva_host_csr_tile_schedule(*args, None, None, None, None, None, None) == 0
+    n = nb.value
+    base, rl, base_t, rl_t = (np.empty(n, dtype=np.int32) for _ in range(4))
+    cp = np.empty(n + 1, dtype=np.int32)
+    con = np.empty(nc.value, dtype=np.uint32)
+    assert L.tatva_host_csr_tile_schedule(*args, i32(base), i32(rl), i32(base_t), i32(rl_t), i32(cp), con.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+    assert cp[0] == 0 and cp[-1] == nc.value and (np.diff(cp) > 0).all()
+    upper = el[:, :, None] <= el[:, None, :]
+    assert nc.value == int(upper.sum())
+    seen = np.zeros((E, npe, npe), dtype=int)
+    for t in range(nt):
+        counts = np.diff(cp[bp[t] : bp[t + 1] + 1])
+        assert (np.diff(counts) <= 0).all()
+        for d in range(bp[t], bp[t + 1]):
+            for k in range(cp[d], cp[d + 1]):
+                s = int(con[k])
+                e, a, b = t * tile + (s >> 8), (s >> 4) & 15, s & 15
+                seen[e, a, b] += 1
+                row, rowt = el[e, a] * dpn, el[e, b] * dpn
+                assert base[d] == ip[row] + pos[e, a, b] and rl[d] == ip[row + 1] - ip[row]
+                if el[e, a] == el[e, b]:
+                    assert base_t[d] == -1
+                else:
+                    assert base_t[d] == ip[rowt] + pos[e, b, a] and rl_t[d] == ip[rowt + 1] - ip[rowt]
+    assert np.array_equal(seen, upper.astype(int))
