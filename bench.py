@@ -381,13 +381,14 @@ def main():
         barrier()
 
     if rank == 0:
-        traffic, traffic_src = None, None
+        traffic, traffic_src, ncu_pipe = None, None, None
         for name in ("r02_hvp_traffic.json", "r01_hvp_traffic.json"):  # DRAM bytes per launch from the committed ncu --set full capture (1 GPU, 128^3)
             try:
                 tr = json.load(open(os.path.join(ROOT, "profiles", name)))
                 if local_elems == 128**3:
                     traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
                     traffic_src = f"profiles/{name} (ncu --set full of the same kernel and size; not re-measured in this run)"
+                    ncu_pipe = {k: tr[k] for k in ("fp64_pipe_active_pct_at_2_cycles_per_instruction", "fp64_instructions_per_element_sass", "issue_active_pct", "registers_per_thread") if k in tr} or None
                 break
             except (OSError, KeyError, ValueError):
                 continue
@@ -440,7 +441,8 @@ def main():
                 "hbm_achieved_gbs": hbm_ach,
                 "hbm_peak_gbs": hbm_peak,
                 "hbm_frac": hbm_frac,
-                "note": "flops are the NOMINAL textbook count of SURVEY §8(d) (7944 per element); the kernel executes ~2500 FP64 instructions per element (modal form), so frac measures time against the textbook-work roof, not pipe occupancy (ncu: profiles/)",
+                "ncu_same_kernel": ncu_pipe,
+                "note": "flops are the NOMINAL textbook count of SURVEY §8(d) (7944 per element); the kernel executes ~2400 FP64 instructions per element (modal, reference-space form), so frac measures time against the textbook-work roof and can exceed 1; pipe occupancy is in ncu_same_kernel (profiles/r02_hvp_ncu_full_summary.md)",
             },
             "e2e": {
                 "value": n_dofs_global / (ms_e2e_step * 1e-3),

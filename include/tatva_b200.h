@@ -80,6 +80,11 @@ int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, 
  *   building blocks          2 = element-per-thread staged kernels (same as 0), 3 = one thread per quadrature point
  *   CSR assembly             2 = full assembly also where the symmetric entry point was called
  * Every variant computes the same result to rounding; unknown values fall back to the default.                  */
+/* Re-point a plan at other device buffers of the SAME sizes (no allocation, no synchronisation): what a caller whose
+ * runtime re-allocates buffers between executions needs (the XLA-FFI shim caches plans by sizes and rebinds per call).
+ * TATVA_E_UNSUPPORTED for a plan with cached integration weights and different coordinates.                           */
+int tatva_plan_rebind(tatva_plan_t* plan, const double* d_coords, const int32_t* d_conn);
+
 int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
 
 /* User-supplied quadrature rule — Element(quad_points, quad_weights), tatva/element/base.py:37-51.  `points` is

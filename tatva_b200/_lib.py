@@ -31,6 +31,7 @@ SIGNATURES = {
     "tatva_plan_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]),
     "tatva_plan_destroy": (C.c_int, [vp]),
     "tatva_plan_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_i64p, c_i64p]),
+    "tatva_plan_rebind": (C.c_int, [vp, vp, vp]),
     "tatva_plan_set_variant": (C.c_int, [vp, C.c_int]),
     "tatva_law_register": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "tatva_law_compile_log": (C.c_int, [C.c_char_p, C.c_int]),

@@ -1536,6 +1536,14 @@ int tatva_plan_set_point_grid(tatva_plan_t* p, int nx, int ny, const double* lo,
   return TATVA_OK;
 }
 
+int tatva_plan_rebind(tatva_plan_t* p, const double* d_coords, const int32_t* d_conn) {
+  if (!p || !d_coords || !d_conn) return TATVA_E_INVALID;
+  if (p->weights && d_coords != p->coords) return TATVA_E_UNSUPPORTED;  // cached weights belong to the old coordinates
+  p->coords = d_coords;
+  p->conn = d_conn;
+  return TATVA_OK;
+}
+
 int tatva_plan_set_variant(tatva_plan_t* p, int variant) {
   if (!p || variant < 0 || variant > 63) return TATVA_E_INVALID;
   p->variant = variant;

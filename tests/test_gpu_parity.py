@@ -598,3 +598,24 @@ def test_fused_kernels_against_derivatives_of_the_reference_energy(golden, kind)
         wHv = np.einsum("kni,ni->k", g("hvp_probe_w"), Hv)
         np.testing.assert_allclose(wHv, g("hvp_probe_wHv_hi"), rtol=1e-12, err_msg=f"variant {variant}")
     op.set_variant(0)
+
+
+def test_plan_rebind_points_a_plan_at_other_buffers_of_the_same_sizes():
+    """`tatva_plan_rebind` (what the XLA-FFI shim does per call: XLA re-allocates buffers between executions)."""
+    tb, element, materials = _tb()
+    c, el, u, v, (mname, omat) = _case("hex8", 4)
+    mat = _material(mname, omat)
+    op = _make_op("hex8", c, el)
+    ref = op.hvp(mat)(u, v).cpu().numpy()
+    c2 = c + 0.01 * np.random.default_rng(3).uniform(-1, 1, c.shape)
+    coords2 = torch.as_tensor(c2, device="cuda").contiguous()
+    conn2 = torch.as_tensor(el, device="cuda").to(torch.int32).contiguous().clone()
+    from tatva_b200 import _lib
+
+    for plan in {id(p): p for p in (op._plan, op._plan_fused)}.values():
+        _lib.check(op._L.tatva_plan_rebind(plan, coords2.data_ptr(), conn2.data_ptr()), "tatva_plan_rebind")
+    got = op.hvp(mat)(u, v).cpu().numpy()
+    want = _make_op("hex8", c2, el).hvp(mat)(u, v).cpu().numpy()
+    assert _rel(got, want) < 1e-14 and _rel(got, ref) > 1e-6
+    opw = _make_op("hex8", c, el, cache_weights=True)
+    assert op._L.tatva_plan_rebind(opw._plan, coords2.data_ptr(), conn2.data_ptr()) == -2  # cached weights: unsupported
