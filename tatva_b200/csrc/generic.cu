@@ -1184,8 +1184,11 @@ __global__ void __launch_bounds__(256) k_lift(const double* __restrict__ u_red, 
                                               int64_t n, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // s >= 0: reduced index; s <= -2^40: entry -(s + 2^40) of the base vector (a Periodic slave may read its master's);
+  // otherwise consts[-(s + 2)]
+  constexpr int64_t kBaseOff = (int64_t)1 << 40;
   const int64_t s = __ldg(src + i);
-  out[i] = s >= 0 ? __ldg(u_red + s) : (s == -1 ? (base ? __ldg(base + i) : 0.0) : __ldg(consts - (s + 2)));
+  out[i] = s >= 0 ? __ldg(u_red + s) : (s <= -kBaseOff ? (base ? __ldg(base - (s + kBaseOff)) : 0.0) : __ldg(consts - (s + 2)));
 }
 __global__ void __launch_bounds__(256) k_reduce_adjoint(const double* __restrict__ r_full,
                                                         const int64_t* __restrict__ ptr,

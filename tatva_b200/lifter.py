@@ -31,6 +31,9 @@ except ImportError:  # pragma: no cover
 from . import _lib
 
 
+BASE_OFF = 1 << 40  # source-table codes <= -BASE_OFF mean "entry -(code + BASE_OFF) of the base vector"
+
+
 class LifterError(ValueError):
     """Problem with the lifter, e.g. a missing runtime value (lifter/common.py:41-42)."""
 
@@ -118,11 +121,10 @@ class Periodic(Constraint):
         return S
 
     def _compose(self, src, consts, runtime_values):
-        src[self.dofs] = src[self.master_dofs]  # RHS gathered before the set, like u.at[dofs].set(u[master])
-        # a slave whose master still reads the base vector must read the MASTER's base entry
-        base = src[self.dofs] == -1
-        if base.any():
-            raise LifterError("Periodic master DOF is constrained by a later constraint: reorder the constraints")
+        # RHS gathered before the set, like u.at[dofs].set(u[master]) (lifter/constraints.py:214-221).  A master that
+        # still reads the base vector (it is constrained by a LATER constraint, or is itself a slave of this one) hands
+        # its slave the code "base entry of the master" — what the reference's sequential application gives.
+        src[self.dofs] = src[self.master_dofs]
 
 
 def create_g2l(l2g):
@@ -236,10 +238,10 @@ class Lifter:
 
     # -- composed tables ------------------------------------------------------------------------------
     def _compose(self):
-        """src[i] >= 0: reduced index; -1: base vector entry; <= -2: consts[-(src+2)].  inverse (ptr, list):
-        for every reduced DOF the full DOFs that read it, ascending."""
+        """src[i] >= 0: reduced index; <= -BASE_OFF: entry -(src + BASE_OFF) of the base vector (initially its own);
+        -2 ... : consts[-(src+2)].  inverse (ptr, list): for every reduced DOF the full DOFs that read it, ascending."""
         if self._tables is None:
-            src = np.full(self.size, -1, dtype=np.int64)
+            src = -(BASE_OFF + np.arange(self.size, dtype=np.int64))
             src[self.free_dofs] = np.arange(self.size_reduced, dtype=np.int64)
             consts: list[float] = []
             for c in self.constraints:
@@ -292,10 +294,13 @@ class Lifter:
         src, consts, _, _ = self._compose()
         ur = _np(u_reduced)
         out = np.zeros(self.size, dtype=ur.dtype) if u_full is None else np.array(_np(u_full), dtype=ur.dtype, copy=True)
+        base = None if u_full is None else np.array(_np(u_full), dtype=ur.dtype, copy=True)
         red = src >= 0
         out[red] = ur[src[red]]
-        cst = src <= -2
+        cst = (src <= -2) & (src > -BASE_OFF)
         out[cst] = consts[-(src[cst] + 2)]
+        bas = src <= -BASE_OFF
+        out[bas] = 0.0 if base is None else base[-(src[bas] + BASE_OFF)]
         return out[: self._local_size]  # extra ghost DOFs added by PeriodicMPI are not part of the result
 
     def lift_from_zeros(self, u_reduced, out=None):
@@ -336,6 +341,7 @@ class Lifter:
             for c in self.constraints:
                 hom.append(Fixed(c.dofs, 0.0) if isinstance(c, Fixed) else c)
             self._homogeneous = Lifter(self.size, *hom)
+            self._homogeneous._nb_extra_ghost_dofs = getattr(self, "_nb_extra_ghost_dofs", None)  # same local size
         return self._homogeneous
 
     # -- distributed layouts (lifter/base.py:333-425) ------------------------------------------------------

@@ -504,6 +504,13 @@ def lifter_fixtures(out):
     out["lift_A"] = A
     out["lifted_dual"] = np.asarray(lifted(lambda uf: jnp.asarray(A @ uf), argnums=0, output="dual")(lifter, jnp.asarray(u_red)))
     out["lifted_primal"] = np.asarray(lifted(lambda uf: uf * 2.0, argnums=0, output="primal")(lifter, jnp.asarray(u_red)))
+    # chains: a master that is itself a slave of the same Periodic, and a master fixed by a LATER constraint
+    chain = Lifter(8, Periodic(dofs=jnp.asarray([1, 2]), master_dofs=jnp.asarray([0, 1])), Periodic(dofs=jnp.asarray([5]), master_dofs=jnp.asarray([6])), Fixed(jnp.asarray([6]), 3.0))
+    cu, cb, cr = np.array([10.0, 11.0, 12.0, 13.0]), np.arange(100.0, 108.0), np.arange(1.0, 9.0)
+    out["lift_chain_free_dofs"] = np.asarray(chain.free_dofs)
+    out["lift_chain_on_base"] = np.asarray(chain.lift(jnp.asarray(cu), jnp.asarray(cb)))
+    out["lift_chain_from_zeros"] = np.asarray(chain.lift_from_zeros(jnp.asarray(cu)))
+    out["lift_chain_reduce_adjoint"] = np.asarray(chain.reduce_adjoint(jnp.asarray(cr)))
     # sparsity adaptation (lifter/base.py:281-331, constraints.py:195-212): augmented by the periodic coupling, then
     # reduced to the free DOFs
     pat = sparse.pattern_from_mesh(Mesh(coords=jnp.asarray(c), elements=jnp.asarray(el)), 2)

@@ -206,3 +206,41 @@ def test_lifter_matches_the_reference_on_a_constraint_chain(golden):
     hom = lifter.homogeneous().lift_from_zeros(u_red)
     np.testing.assert_array_equal(hom, np.where(m >= 0, u_red[np.maximum(m, 0)], 0.0))
     np.testing.assert_allclose(np.bincount(m[m >= 0], weights=r_full[m >= 0], minlength=lifter.size_reduced), g("reduce_adjoint"), rtol=1e-15, atol=1e-15)
+
+
+def test_periodic_chains_follow_the_sequential_semantics_of_the_reference():
+    """Masters that still read the base vector (reference lifter/base.py:201-229 applies the constraints one after the
+    other on `u_full`): a master that is itself a slave of the SAME Periodic hands over its OLD (base) value, and a
+    master fixed by a LATER constraint hands over the base entry, not the later value."""
+    from tatva_b200.lifter import Fixed, Lifter, Periodic
+
+    n = 8
+    # dofs [1, 2] follow masters [0, 1]: 1 <- 0 and 2 <- OLD 1 (gathered before the set)
+    lifter = Lifter(n, Periodic([1, 2], [0, 1]), Periodic([5], [6]), Fixed([6], 3.0))
+    free = np.asarray(lifter.free_dofs)
+    assert list(free) == [0, 3, 4, 7]
+    ur = np.array([10.0, 11.0, 12.0, 13.0])
+    base = np.arange(100.0, 108.0)
+
+    def reference_lift(u_red, u_full):
+        u = np.array(u_full, copy=True)
+        u[free] = u_red
+        u[[1, 2]] = u[[0, 1]]
+        u[[5]] = u[[6]]
+        u[[6]] = 3.0
+        return u
+
+    np.testing.assert_array_equal(lifter.lift(ur, base), reference_lift(ur, base))
+    np.testing.assert_array_equal(lifter.lift_from_zeros(ur), reference_lift(ur, np.zeros(n)))
+    # and the outputs of the UNMODIFIED reference Lifter on the same chain (tests/golden/make_golden.py)
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+    np.testing.assert_array_equal(free, g["lift_chain_free_dofs"])
+    np.testing.assert_array_equal(lifter.lift(ur, base), g["lift_chain_on_base"])
+    np.testing.assert_array_equal(lifter.lift_from_zeros(ur), g["lift_chain_from_zeros"])
+    np.testing.assert_array_equal(lifter.reduce_adjoint(np.arange(1.0, 9.0)), g["lift_chain_reduce_adjoint"])
+    # the transpose drops what a base-reading slave collects
+    r = np.arange(1.0, 9.0)
+    np.testing.assert_array_equal(lifter.reduce_adjoint(r), np.array([r[0] + r[1], r[3], r[4], r[7]]))
+    assert list(lifter.dof_map()) == [0, 0, -1, 1, 2, -1, -1, 3]
