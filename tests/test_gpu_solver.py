@@ -288,3 +288,21 @@ def test_newton_step_converges_to_the_oracle_minimiser():
     e_gpu = float(op.energy(mat)(lifter.lift_from_zeros(u).view(-1, 3)))
     e_ref = orc.energy("hex8", omat, c, el, lifter.lift_from_zeros(ur).reshape(-1, 3))
     assert abs(e_gpu - e_ref) <= 1e-10 * abs(e_ref)
+
+
+def test_cuda_lift_handles_periodic_chains_like_the_numpy_path():
+    """`tatva_lift` with base-entry source codes: a slave whose master still reads the base vector (reference
+    lifter/base.py:201-229, `lift_chain_*` fixtures) — CUDA gather kernel == NumPy path == reference outputs."""
+    import os
+
+    from tatva_b200.lifter import Fixed, Lifter, Periodic
+
+    lifter = Lifter(8, Periodic([1, 2], [0, 1]), Periodic([5], [6]), Fixed([6], 3.0))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+    ur, base = np.array([10.0, 11.0, 12.0, 13.0]), np.arange(100.0, 108.0)
+    out = lifter.lift(torch.as_tensor(ur, device="cuda"), torch.as_tensor(base, device="cuda"))
+    np.testing.assert_array_equal(out.cpu().numpy(), g["lift_chain_on_base"])
+    out0 = lifter.lift_from_zeros(torch.as_tensor(ur, device="cuda"))
+    np.testing.assert_array_equal(out0.cpu().numpy(), g["lift_chain_from_zeros"])
+    r = lifter.reduce_adjoint(torch.as_tensor(np.arange(1.0, 9.0), device="cuda"))
+    np.testing.assert_array_equal(r.cpu().numpy(), g["lift_chain_reduce_adjoint"])
