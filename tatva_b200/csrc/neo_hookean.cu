@@ -1227,7 +1227,7 @@ TATVA_D void cp_async8(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-template <int FAT, int THIN>
+template <int FAT, int THIN, int XREG = 0>
 __global__ void __launch_bounds__(kV5Threads, 1)
     k_hex8_nh_hvp_v5(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu,
                      double lmbda, const double* __restrict__ u, const double* __restrict__ v,
@@ -1317,6 +1317,13 @@ __global__ void __launch_bounds__(kV5Threads, 1)
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+      double hx[XREG ? 3 : 1][7];  // XREG: the modal deformed coordinates stay in registers for the four iterations
+      if constexpr (XREG) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 7; ++k) hx[i][k] = col[(size_t)((3 + i) * 8 + k) * kV5Threads];
+      }
 #pragma unroll 1
       for (int pq = 0; pq < 4; ++pq) {
         const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
@@ -1339,9 +1346,13 @@ __global__ void __launch_bounds__(kV5Threads, 1)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           double t[7];
+          if constexpr (XREG) {
+            ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+          } else {
 #pragma unroll
-          for (int k = 0; k < 7; ++k) t[k] = cc[(size_t)((3 + i) * 8 + k) * kV5Threads];
-          ref_grad8_pair(t, sy, sz, Frm[i], Frp[i]);
+            for (int k = 0; k < 7; ++k) t[k] = cc[(size_t)((3 + i) * 8 + k) * kV5Threads];
+            ref_grad8_pair(t, sy, sz, Frm[i], Frp[i]);
+          }
 #pragma unroll
           for (int k = 0; k < 7; ++k) t[k] = cc[(size_t)((6 + i) * 8 + k) * kV5Threads];
           ref_grad8_pair(t, sy, sz, Gvm[i], Gvp[i]);
@@ -1959,19 +1970,19 @@ static int launch_v4(const tatva_plan* p, double mu, double lmbda, const double*
   return TATVA_OK;
 }
 
-template <int FAT, int THIN>
+template <int FAT, int THIN, int XREG = 0>
 static int launch_v5(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st) {
   constexpr size_t smem = (size_t)kV5Slots * kV5Threads * sizeof(double);  // 216 KB: one CTA per SM
   static SmemOptIn configured;
-  int rc = opt_in_smem(k_hex8_nh_hvp_v5<FAT, THIN>, smem, configured);
+  int rc = opt_in_smem(k_hex8_nh_hvp_v5<FAT, THIN, XREG>, smem, configured);
   if (rc != TATVA_OK) return rc;
   int dev = 0, sms = 0;
   TATVA_CUDA_TRY(cudaGetDevice(&dev));
   TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t tiles = (p->n_elems + 127) / 128;
   const int grid = (int)((tiles + 2) / 3 < sms ? (tiles + 2) / 3 : sms);
-  k_hex8_nh_hvp_v5<FAT, THIN><<<grid, kV5Threads, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  k_hex8_nh_hvp_v5<FAT, THIN, XREG><<<grid, kV5Threads, smem, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
   return TATVA_OK;
 }
 
@@ -2009,6 +2020,9 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
     case 40: rc = launch_v5<216, 72>(p, mu, lmbda, u, v, y, st); break;  // rotating warpgroups (setmaxnreg)
     case 41: rc = launch_v5<208, 88>(p, mu, lmbda, u, v, y, st); break;
     case 42: rc = launch_v5<200, 104>(p, mu, lmbda, u, v, y, st); break;
+    case 47: rc = launch_v5<232, 40, 1>(p, mu, lmbda, u, v, y, st); break;  // fat phase keeps modal x in registers
+    case 48: rc = launch_v5<224, 56, 1>(p, mu, lmbda, u, v, y, st); break;
+    case 49: rc = launch_v5<216, 72, 1>(p, mu, lmbda, u, v, y, st); break;
     case 16: k_hex8_nh_hvp_v2<2, 0><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     case 20: k_hex8_nh_hvp_v2<3, 1><<<grid_for(p->n_elems), kBlock, 42 * kBlock * sizeof(double), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;
     // r02 default: pair kernel, all three modal fields staged, 168 registers -> 3 CTAs (12 warps) per SM: 0.397 ms at 128^3

@@ -172,7 +172,7 @@ class Operator:
 
     # Hex8 x neo-Hookean HVP kernels kept for measurement; 0 = default.  8 / 9 are timing experiments
     # (no scatter / no gather) and do not compute the HVP.
-    HEX8_NH_HVP_VARIANTS = (0, 1, 2, 3, 15, 16, 17, 20, 22, 23, 25, 26, 27, 28, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46)
+    HEX8_NH_HVP_VARIANTS = (0, 1, 2, 3, 15, 16, 17, 20, 22, 23, 25, 26, 27, 28, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49)
 
     def hvp_variants(self) -> tuple:
         return self.HEX8_NH_HVP_VARIANTS
