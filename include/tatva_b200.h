@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 5  /* bumped on every signature change; the Python loader refuses a mismatch */
+#define TATVA_B200_ABI_VERSION 6  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */
@@ -76,7 +76,8 @@ int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, 
  * values select alternative implementations kept for A/B timing, per kernel family (DESIGN.md sections 3.1-3.3):
  *   Hex8 x neo-Hookean HVP   2, 3, 8, 9, 15, 16, 17, 20, 22, 23, 25, 26, 27 (sector-grouped scatter), 28 (16-byte gathers)
  *   Hex8 residual / energy   2 = first modal kernel, 3 / 4 = pair kernel at other register / occupancy points
- *   Tet4 x neo-Hookean       30 = persistent kernel with connectivity prefetch
+ *   Tet4 x neo-Hookean       30 = persistent kernel with connectivity prefetch, 31 = element-per-thread kernel even
+ *                            when the plan carries a node schedule (tatva_plan_set_node_schedule)
  *   building blocks          2 = element-per-thread staged kernels (same as 0), 3 = one thread per quadrature point
  *   CSR assembly             2 = full assembly also where the symmetric entry point was called
  * Every variant computes the same result to rounding; unknown values fall back to the default.                  */
@@ -116,6 +117,17 @@ int tatva_law_compile_log(char* buf, int len);
  * gathers the unique nodes once, coalesced, into shared memory.  Device views, caller-owned; NULL disables.   */
 int tatva_plan_set_tiles(tatva_plan_t* plan, const int32_t* d_tile_ptr, const int32_t* d_tile_nodes,
                          const uint16_t* d_tile_conn, int max_unique);
+
+/* Node schedule of the warp-cooperative fused kernels (r02; Tri3 / Tet4 residual and HVP — the transpose of the gather
+ * `v[self.mesh.elements]`, tatva/operator.py:221, done node-wise): every warp loads the nodal rows of its (up to) 32
+ * distinct nodes ONCE, one node per lane, and the elements fetch them with warp shuffles; the nodal contributions of a
+ * 128-element tile are summed per distinct node in shared memory and leave the SM as ONE atomic add per (node, DOF).
+ * Arrays from tatva_host_node_schedule on the plan's element list; d_tile_hdr holds four int32 per tile, 16-byte aligned:
+ * {ch_ptr[t], ch_ptr[t+1] - ch_ptr[t], ell_ptr[ch_ptr[t]], ell_ptr[ch_ptr[t+1]] - ell_ptr[ch_ptr[t]]}.  Device views,
+ * caller-owned; NULL disables.                                                                                        */
+int tatva_plan_set_node_schedule(tatva_plan_t* plan, const int32_t* d_warp_nodes, const uint8_t* d_warp_local,
+                                 const int32_t* d_tile_hdr, const int32_t* d_tn_node, const int32_t* d_ell_ptr,
+                                 const uint16_t* d_ell);
 
 /* Optional uniform background grid for tatva_op_interpolate (plane meshes): bin (ix, iy), row-major iy * nx + ix, with
  * ix = clamp((int)((x - lo[0]) * inv[0]), 0, nx - 1); d_bin_elems[d_bin_ptr[b] .. d_bin_ptr[b+1]) lists, ascending,
@@ -363,6 +375,13 @@ int tatva_host_node_to_elements(const int32_t* conn, int64_t n_elems, int npe, i
                                 int32_t* ptr, int32_t* list);
 int tatva_host_build_tiles(const int32_t* conn, int64_t n_elems, int npe, int tile_elems, int32_t* tile_ptr,
                            int32_t* tile_nodes, uint16_t* local_conn, int32_t* max_unique);
+/* Host side of tatva_plan_set_node_schedule (layout in csrc/host.cpp).  Two calls: with tn_node == NULL it fills
+ * warp_nodes (128 per tile of 128 elements), warp_local (n_elems * npe), ch_ptr (n_tiles + 1), *n_chunks and *n_ell;
+ * the second call fills tn_node (32 * n_chunks), ell_ptr (n_chunks + 1) and ell (n_ell).  cap > 0: a node's
+ * contributors are cut into entries of at most `cap` (balances the warps of a tile), 0 = one entry per node.         */
+int tatva_host_node_schedule(const int32_t* conn, int64_t n_elems, int npe, int cap, int32_t* warp_nodes, uint8_t* warp_local,
+                             int32_t* ch_ptr, int64_t* n_chunks, int64_t* n_ell, int32_t* tn_node, int32_t* ell_ptr,
+                             uint16_t* ell);
 int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int npe,
                                      int dofs_per_node, const int32_t* indptr,
                                      const int32_t* indices, int32_t* elem_pos);

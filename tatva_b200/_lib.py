@@ -15,7 +15,7 @@ TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
 USER_LAW_BASE = 1000
 PLAN_CACHE_WEIGHTS = 1
-ABI_VERSION = 5  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
+ABI_VERSION = 6  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
@@ -37,6 +37,7 @@ SIGNATURES = {
     "tatva_law_compile_log": (C.c_int, [C.c_char_p, C.c_int]),
     "tatva_plan_set_quadrature": (C.c_int, [vp, C.c_int, c_f64p, c_f64p, vp]),
     "tatva_plan_set_tiles": (C.c_int, [vp, vp, vp, vp, C.c_int]),
+    "tatva_plan_set_node_schedule": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "tatva_plan_set_point_grid": (C.c_int, [vp, C.c_int, C.c_int, c_f64p, c_f64p, vp, vp]),
     "tatva_op_grad": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "tatva_op_grad_adjoint": (C.c_int, [vp, vp, C.c_int, vp, vp]),
@@ -77,6 +78,7 @@ SIGNATURES = {
     "tatva_host_pattern_from_element_dofs": (C.c_int, [c_i32p, C.c_int64, C.c_int, c_i32p, C.c_int64, C.c_int64, c_i32p, c_i32p, C.POINTER(C.c_int64)]),
     "tatva_host_node_to_elements": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int64, c_i32p, c_i32p]),
     "tatva_host_build_tiles": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, C.POINTER(C.c_uint16), c_i32p]),
+    "tatva_host_node_schedule": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, C.POINTER(C.c_uint8), c_i32p, c_i64p, c_i64p, c_i32p, c_i32p, C.POINTER(C.c_uint16)]),
     "tatva_host_csr_element_positions": (C.c_int, [c_i32p, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p]),
     "tatva_host_build_point_grid": (C.c_int, [c_f64p, C.c_int64, c_i32p, C.c_int64, C.c_int, C.c_int, C.c_int, c_f64p, c_f64p, c_i32p, c_i32p]),
     "tatva_probe_element": (C.c_int, [C.c_int, C.c_int, c_f64p, C.c_int, C.c_int, c_f64p, c_f64p, c_f64p, c_f64p]),
@@ -140,6 +142,14 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def host_tables_only(what: str) -> None:
+    """Gate of the few places that can run their INDEX algebra on host arrays (Lifter tables on NumPy vectors, exchange
+    plans on CPU tensors over gloo): that mode exists for the world_size-2 `gloo` tests of the host logic, which opt in
+    with TATVA_B200_HOST_TABLES=1 (tests/conftest.py).  Anywhere else a non-CUDA operand is an error, not a fallback."""
+    if os.environ.get("TATVA_B200_HOST_TABLES") != "1":
+        raise TatvaError(f"{what}: operands must be CUDA tensors (there is no CPU fallback; TATVA_B200_HOST_TABLES=1 enables the host index paths for the gloo tests)")
 
 
 def check(code: int, what: str = "") -> None:

@@ -697,6 +697,13 @@ struct tatva_plan {
   const int32_t* tile_nodes;
   const uint16_t* tile_conn;
   int tile_max_unique;
+  // optional node schedule of the warp-cooperative fused kernels (tatva_plan_set_node_schedule)
+  const int32_t* ws_warp_nodes;
+  const uint8_t* ws_warp_local;
+  const int32_t* ws_tile_hdr;
+  const int32_t* ws_tn_node;
+  const int32_t* ws_ell_ptr;
+  const uint16_t* ws_ell;
   // optional uniform background grid for point location (see tatva_plan_set_point_grid)
   int grid_nx, grid_ny;
   double grid_lo[2], grid_inv[2];  // bin = clamp(floor((x - lo) * inv), 0, n - 1)
@@ -761,6 +768,7 @@ int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, 
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
 int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
 int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
+int tet4_nh_wc(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);
 
 }  // namespace tatva
 #endif  // !__CUDACC_RTC__

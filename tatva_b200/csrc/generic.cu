@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "fused.cuh"
+#include "wc.cuh"
 
 namespace tatva {
 
@@ -998,6 +999,59 @@ __global__ void __launch_bounds__(kTile) k_csr_tiled(const double* __restrict__ 
   }
 }
 
+// Hessian diagonal through the laws' rank structure: K_aa(i, i) = w1 |dN_a|^2 + (w2 + w3) g_a[i]^2 per point — the
+// geometry, F^-1 and one logarithm per point, then 3 + 3*dim fused operations per (node, point) instead of one full
+// second-variation evaluation per (node, component) as in k_hessian_diag (Hex8 x neo-Hooke: 24 tangent evaluations per
+// point).  Same element-per-thread gather and sector-grouped scatter.
+template <class T>
+struct has_rank_law : std::false_type {};
+template <int DIM>
+struct has_rank_law<LinearElastic<DIM>> : std::true_type {};
+template <>
+struct has_rank_law<NeoHookean> : std::true_type {};
+
+template <class El, class Mat>
+__global__ void __launch_bounds__(kBlock) k_hessian_diag_rank(const double* __restrict__ coords,
+                                                              const int32_t* __restrict__ conn, int64_t E, Mat mat,
+                                                              const double* __restrict__ u, double* __restrict__ diag) {
+  static_assert(Mat::dpn == El::dim, "one DOF per direction");
+  constexpr int D = El::dim, NPE = El::npe;
+  extern __shared__ double sm_diag[];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int nd[NPE];
+  double Y[NPE][D];
+#pragma unroll
+  for (int n = 0; n < NPE; ++n) {
+    nd[n] = 0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) Y[n][c] = 0.0;
+  }
+  if (e < E) {
+    load_conn<El>(conn, e, nd);
+    double X[NPE][D], U[NPE][D];
+    gather_rows(coords, nd, X);
+    gather_rows(u, nd, U);
+#pragma unroll 1
+    for (int q = 0; q < El::num_q(); ++q) {
+      double dN[D][NPE], g[D][NPE], w[3];
+      const double W = geometry<El>(q, X, dN) * El::weight(q);
+      RankLaw<Mat>::template eval<NPE>(mat, W, dN, U, g, w);
+      const double w23 = w[1] + w[2];
+#pragma unroll
+      for (int a = 0; a < NPE; ++a) {
+        double nn = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) nn = fma(dN[j][a], dN[j][a], nn);
+        const double a1 = w[0] * nn;
+#pragma unroll
+        for (int i = 0; i < D; ++i) Y[a][i] += fma(w23 * g[i][a], g[i][a], a1);
+      }
+    }
+  }
+  double* wsm = sm_diag + (size_t)(threadIdx.x >> 5) * grouped_scatter_words<NPE, D>();
+  grouped_scatter<NPE, D>(diag, nd, Y, e < E, wsm);
+}
+
 // Lower triangle from the upper one (the energy Hessian is symmetric): one warp per node row a, one lane per
 // block (a, b) with b < a:  K[(a,i),(b,k)] = K[(b,k),(a,i)].  The position of a in row b is found by binary search.
 __global__ void __launch_bounds__(128) k_csr_mirror(int64_t n_nodes, int dpn, const int32_t* __restrict__ indptr,
@@ -1472,6 +1526,7 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->tile_nodes = nullptr;
   p->tile_conn = nullptr;
   p->tile_max_unique = 0;
+  p->ws_warp_nodes = nullptr;
   p->custom = 0;
   p->scratch_len = (int64_t)grid_for(n_elems) * (kBlock / 32) > 1024 * 64 ? (int64_t)grid_for(n_elems) * (kBlock / 32) : 1024 * 64;
   cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
@@ -1516,6 +1571,20 @@ int tatva_plan_set_tiles(tatva_plan_t* p, const int32_t* d_tile_ptr, const int32
   p->tile_nodes = d_tile_nodes;
   p->tile_conn = d_tile_conn;
   p->tile_max_unique = d_tile_ptr ? max_unique : 0;
+  return TATVA_OK;
+}
+
+int tatva_plan_set_node_schedule(tatva_plan_t* p, const int32_t* d_warp_nodes, const uint8_t* d_warp_local,
+                                 const int32_t* d_tile_hdr, const int32_t* d_tn_node, const int32_t* d_ell_ptr,
+                                 const uint16_t* d_ell) {
+  if (!p || (d_warp_nodes && (!d_warp_local || !d_tile_hdr || !d_tn_node || !d_ell_ptr || !d_ell))) return TATVA_E_INVALID;
+  if (d_warp_nodes && p->npe > 8) return TATVA_E_UNSUPPORTED;
+  p->ws_warp_nodes = d_warp_nodes;
+  p->ws_warp_local = d_warp_local;
+  p->ws_tile_hdr = d_tile_hdr;
+  p->ws_tn_node = d_tn_node;
+  p->ws_ell_ptr = d_ell_ptr;
+  p->ws_ell = d_ell;
   return TATVA_OK;
 }
 
@@ -1857,6 +1926,17 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
     }
     return TATVA_E_UNSUPPORTED;
   }
+  if constexpr (MODE != MODE_ENERGY) {
+    // warp-cooperative kernels for the one-point simplices when the plan carries a node schedule
+    if (p->ws_warp_nodes && p->variant != TATVA_VARIANT_GENERIC && p->variant != 30 && p->variant != 31) {
+      if (material == TATVA_LINEAR_ELASTIC && n_params == 2) {
+        if (el == TATVA_TRI3) return launch_fused_wc<Tri3, LinearElastic<2>, MODE, GenericBody<Tri3, LinearElastic<2>>>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
+        if (el == TATVA_TET4) return launch_fused_wc<Tet4, LinearElastic<3>, MODE, GenericBody<Tet4, LinearElastic<3>>>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
+      } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
+        if (el == TATVA_TET4) return tet4_nh_wc(p, MODE == MODE_HVP, prm[0], prm[1], u, v, out, st);
+      }  // the two-field law keeps the element-per-thread kernel: its 32-byte nodal rows are sector-exact and the tile sums do not pay (measured)
+    }
+  }
   if (material == TATVA_LINEAR_ELASTIC) {
     if (n_params != 2) return TATVA_E_INVALID;
     if (el == TATVA_TRI3) return launch_fused<Tri3, LinearElastic<2>, MODE>(p, LinearElastic<2>{prm[0], prm[1]}, u, v, out, st);
@@ -1960,6 +2040,13 @@ int tatva_hessian_diag(tatva_plan_t* p, int material, const double* params, int 
     using Mat = decltype(mat);
     if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
     constexpr size_t smem = grouped_scatter_smem<El::npe, Mat::dpn>(kBlock / 32);
+    if constexpr (has_rank_law<Mat>::value) {
+      if (p->variant != TATVA_VARIANT_GENERIC) {
+        k_hessian_diag_rank<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, d_u, d_diag);
+        TATVA_LAUNCH_CHECK();
+        return TATVA_OK;
+      }
+    }
     k_hessian_diag<El, Mat><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, d_u, d_diag);
     TATVA_LAUNCH_CHECK();
     return TATVA_OK;
@@ -1999,7 +2086,7 @@ int tatva_hvp_lifted_dot(tatva_plan_t* p, int material, const double* params, in
   cudaStream_t st = (cudaStream_t)stream;
   if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y_red, 0, sizeof(double) * n_red, st));
   if (!p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
-    const int grid = grid_for(p->n_elems) * (kBlock / 32);  // one partial per warp
+    const int grid = grid_for(p->n_elems);  // one partial per CTA
     if (grid > p->scratch_len) return TATVA_E_INVALID;
     const int rc = hex8_nh_hvp_modal_lifted(p, params[0], params[1], d_u_full, d_v_red, d_dof_map, d_y_red, st, p->scratch);
     if (rc != TATVA_OK) return rc;
@@ -2030,7 +2117,7 @@ int tatva_hvp_dot(tatva_plan_t* p, int material, const double* params, int n_par
   const int64_t n = p->n_nodes * dpn;
   if (zero_y) TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * n, st));
   if (fuse_dot && !p->custom && p->element == TATVA_HEX8 && material == TATVA_NEO_HOOKEAN && n_params == 2 && p->variant != TATVA_VARIANT_GENERIC) {
-    const int grid = grid_for(p->n_elems) * (kBlock / 32);  // one partial per warp
+    const int grid = grid_for(p->n_elems);  // one partial per CTA
     if (grid > p->scratch_len) return TATVA_E_INVALID;
     const int rc = hex8_nh_hvp_modal_dot(p, params[0], params[1], d_u, d_v, d_y, p->scratch, st);
     if (rc != TATVA_OK) return rc;
@@ -2144,7 +2231,8 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
   sub.conn = p->conn + elem_begin * p->npe;
   sub.n_elems = elem_count;
   sub.zero_output = zero_y ? 1 : 0;
-  sub.tile_ptr = nullptr;  // tiles describe the whole element list, not a sub-range
+  sub.tile_ptr = nullptr;  // tiles and node schedules describe the whole element list, not a sub-range
+  sub.ws_warp_nodes = nullptr;
   return dispatch_fused<MODE_HVP>(&sub, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
 }
 int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,
@@ -2163,6 +2251,7 @@ int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, in
   sub.n_elems = elem_count;
   sub.zero_output = zero_r ? 1 : 0;
   sub.tile_ptr = nullptr;
+  sub.ws_warp_nodes = nullptr;
   return dispatch_fused<MODE_RESIDUAL>(&sub, material, params, n_params, d_u, nullptr, d_r, (cudaStream_t)stream);
 }
 }  // extern "C"

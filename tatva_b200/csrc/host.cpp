@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <utility>
 #include <vector>
 
@@ -301,6 +302,141 @@ int tatva_host_build_tiles(const int32_t* conn, int64_t n_elems, int npe, int ti
     }
     *max_unique = mx;
   }
+  return TATVA_OK;
+}
+
+// Node schedule of the warp-cooperative fused kernels (k_fused_wc, r02): the element list is cut into warps of 32 and
+// tiles of 128 consecutive elements (one CTA of 4 warps).
+//   gather   warp_nodes [n_tiles * 128]  per warp of 32 elements its (up to) 32 most referenced distinct nodes, ascending,
+//                                        -1 = unused lane: lane l loads the nodal rows of warp_nodes[32 w + l] ONCE
+//            warp_local [n_elems * npe]  per element node: the lane that holds it, or 255 = not among the 32 (the
+//                                        element then reads that row itself through the connectivity)
+//   scatter  the distinct nodes of a tile by DECREASING contributor count, in chunks of 32 (one warp pass each):
+//            ch_ptr  [n_tiles + 1]       first chunk of each tile
+//            tn_node [32 * n_chunks]     node of (chunk, lane), -1 = none
+//            ell_ptr [n_chunks + 1]      first contributor entry of each chunk (a multiple of 32)
+//            ell     [n_ell]             entry [ell_ptr[k] + 32 r + lane] = r-th contributor of the lane's node:
+//                                        (element slot in the tile) << 3 | local node, 0xFFFF = none; a chunk holds
+//                                        32 x (largest count in the chunk) entries, so a warp reads them coalesced and
+//                                        its lanes loop equally long
+// `cap` > 0 cuts the contributor list of a node into entries of at most `cap` (each entry ends in its own atomic add): a
+// tile's heaviest nodes otherwise keep one warp looping long after the others are done.
+// Two calls (same cap): with tn_node == NULL ch_ptr, *n_chunks and *n_ell are filled (and warp_nodes / warp_local, if given); the
+// second call fills tn_node, ell_ptr and ell.
+int tatva_host_node_schedule(const int32_t* conn, int64_t n_elems, int npe, int cap, int32_t* warp_nodes, uint8_t* warp_local,
+                             int32_t* ch_ptr, int64_t* n_chunks, int64_t* n_ell, int32_t* tn_node, int32_t* ell_ptr,
+                             uint16_t* ell) {
+  constexpr int kTileElems = 128;
+  if (!conn || !ch_ptr || !n_chunks || !n_ell || n_elems <= 0 || npe <= 0 || npe > 8 || cap < 0) return TATVA_E_INVALID;
+  if (tn_node && (!ell_ptr || !ell)) return TATVA_E_INVALID;
+  const int64_t n_tiles = (n_elems + kTileElems - 1) / kTileElems;
+  const int64_t n_warps = n_tiles * (kTileElems / 32);  // the last CTA reads the lists of all its warps
+  if (n_elems * npe > INT32_MAX / 64) return TATVA_E_INVALID;
+  if (warp_nodes && warp_local) {
+#pragma omp parallel for schedule(static)
+    for (int64_t w = 0; w < n_warps; ++w) {
+      int32_t* wn = warp_nodes + w * 32;
+      const int64_t e0 = w * 32, e1 = std::min<int64_t>(n_elems, e0 + 32);
+      if (e0 >= n_elems) {
+        for (int l = 0; l < 32; ++l) wn[l] = -1;
+        continue;
+      }
+      std::vector<std::pair<int32_t, int32_t>> cnt;  // (node, references)
+      std::vector<int32_t> nodes(conn + e0 * npe, conn + e1 * npe);
+      std::sort(nodes.begin(), nodes.end());
+      for (size_t i = 0; i < nodes.size();) {
+        size_t j = i;
+        while (j < nodes.size() && nodes[j] == nodes[i]) ++j;
+        cnt.emplace_back(nodes[i], (int32_t)(j - i));
+        i = j;
+      }
+      if (cnt.size() > 32) {  // keep the 32 most referenced (ties: smaller node id), then back to ascending ids
+        std::stable_sort(cnt.begin(), cnt.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+        cnt.resize(32);
+        std::sort(cnt.begin(), cnt.end());
+      }
+      for (int l = 0; l < 32; ++l) wn[l] = l < (int)cnt.size() ? cnt[l].first : -1;
+      for (int64_t i = e0 * npe; i < e1 * npe; ++i) {
+        const auto it = std::lower_bound(cnt.begin(), cnt.end(), std::make_pair(conn[i], (int32_t)0),
+                                         [](const auto& a, const auto& b) { return a.first < b.first; });
+        warp_local[i] = (it != cnt.end() && it->first == conn[i]) ? (uint8_t)(it - cnt.begin()) : (uint8_t)255;
+      }
+    }
+  }
+  std::vector<int32_t> chunks(n_tiles, 0);
+  std::vector<int64_t> ells(n_tiles, 0);
+  // one tile: its (node, slot << 3 | local) references sorted by node, cut into entries of at most `cap` contributors
+  // (0 = one entry per distinct node), entries by decreasing contributor count
+  auto tile_entries = [&](int64_t t, std::vector<std::pair<int32_t, uint16_t>>& refs, std::vector<std::pair<int32_t, int32_t>>& seg) {
+    const int64_t e0 = t * kTileElems, e1 = std::min<int64_t>(n_elems, e0 + kTileElems);
+    refs.clear();
+    seg.clear();
+    for (int64_t e = e0; e < e1; ++e)
+      for (int a = 0; a < npe; ++a) refs.emplace_back(conn[e * npe + a], (uint16_t)(((e - e0) << 3) | a));
+    std::sort(refs.begin(), refs.end());
+    for (size_t i = 0; i < refs.size();) {
+      size_t j = i;
+      while (j < refs.size() && refs[j].first == refs[i].first) ++j;
+      const int32_t count = (int32_t)(j - i);
+      const int32_t pieces = cap > 0 ? (count + cap - 1) / cap : 1;
+      for (int32_t k = 0; k < pieces; ++k) {  // balanced pieces: sizes differ by at most one
+        const int32_t lo = (int32_t)((int64_t)count * k / pieces), hi = (int32_t)((int64_t)count * (k + 1) / pieces);
+        seg.emplace_back((int32_t)i + lo, hi - lo);
+      }
+      i = j;
+    }
+    std::stable_sort(seg.begin(), seg.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+  };
+#pragma omp parallel
+  {
+    std::vector<std::pair<int32_t, uint16_t>> refs;
+    std::vector<std::pair<int32_t, int32_t>> seg;
+#pragma omp for schedule(static)
+    for (int64_t t = 0; t < n_tiles; ++t) {
+      tile_entries(t, refs, seg);
+      const int64_t nch = ((int64_t)seg.size() + 31) / 32;
+      chunks[t] = (int32_t)nch;
+      int64_t tot = 0;
+      for (int64_t k = 0; k < nch; ++k) tot += 32 * (int64_t)seg[32 * k].second;
+      ells[t] = tot;
+    }
+  }
+  if (tn_node) {
+    std::vector<int64_t> ell_first(n_tiles + 1, 0);
+    for (int64_t t = 0; t < n_tiles; ++t) ell_first[t + 1] = ell_first[t] + ells[t];
+#pragma omp parallel
+    {
+      std::vector<std::pair<int32_t, uint16_t>> refs;
+      std::vector<std::pair<int32_t, int32_t>> seg;
+#pragma omp for schedule(static)
+      for (int64_t t = 0; t < n_tiles; ++t) {
+        tile_entries(t, refs, seg);
+        int64_t off = ell_first[t];
+        for (int64_t k = 0; k < chunks[t]; ++k) {
+          const int64_t ch = ch_ptr[t] + k;
+          const int rows = seg[32 * k].second;
+          ell_ptr[ch] = (int32_t)off;
+          for (int l = 0; l < 32; ++l) {
+            const size_t i = (size_t)(32 * k + l);
+            tn_node[32 * ch + l] = i < seg.size() ? refs[seg[i].first].first : -1;
+            for (int r = 0; r < rows; ++r)
+              ell[off + 32 * r + l] = (i < seg.size() && r < seg[i].second) ? refs[seg[i].first + r].second : (uint16_t)0xFFFF;
+          }
+          off += 32 * (int64_t)rows;
+        }
+      }
+    }
+    ell_ptr[ch_ptr[n_tiles]] = (int32_t)ell_first[n_tiles];
+    return TATVA_OK;
+  }
+  ch_ptr[0] = 0;
+  int64_t tot = 0;
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    ch_ptr[t + 1] = ch_ptr[t] + chunks[t];
+    tot += ells[t];
+  }
+  *n_chunks = ch_ptr[n_tiles];
+  *n_ell = tot;
   return TATVA_OK;
 }
 

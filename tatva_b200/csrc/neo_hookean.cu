@@ -20,6 +20,7 @@
 //    RED.ADD.F64.  Elements of a lexicographic / locality-sorted mesh put consecutive lanes on
 //    consecutive nodes, so the 24-byte nodal rows of a warp share L1 lines.
 #include "common.cuh"
+#include "wc.cuh"
 
 namespace tatva {
 
@@ -1036,8 +1037,13 @@ __global__ void __launch_bounds__(kBlock, MINB)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       if constexpr (DOT) {
+        // the opaque offset pins the 7 loads of this row behind the REDs of the previous one: hoisted to the top of the
+        // epilogue (what ptxas does otherwise) they cost 21 live doubles next to R and 220 bytes of spill
+        int opq = 0;
+        asm volatile("" : "+r"(opq));
+        const double* svr = sv0 + opq;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) dot = fma(sv0[(i * 7 + k) * kBlock], R[i][k], dot);
+        for (int k = 0; k < 7; ++k) dot = fma(svr[(i * 7 + k) * kBlock], R[i][k], dot);
       }
       double f[8];
       from_modal_raw(R[i], f);
@@ -1056,7 +1062,16 @@ __global__ void __launch_bounds__(kBlock, MINB)
       if (!valid) dot = 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_down_sync(0xffffffffu, dot, o);
-      if ((threadIdx.x & 31) == 0) dot_partials[(size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)] = dot;
+      // one partial per CTA (fixed order: warp 0..3): the final sum then reads 16 K values, not 64 K
+      __shared__ double sdot[kBlock / 32];
+      if ((threadIdx.x & 31) == 0) sdot[threadIdx.x >> 5] = dot;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = sdot[0];
+#pragma unroll
+        for (int w = 1; w < kBlock / 32; ++w) t += sdot[w];
+        dot_partials[blockIdx.x] = t;
+      }
     }
   }
 }
@@ -2122,6 +2137,60 @@ int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const dou
   k_tet4_nh_ref<false><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, nullptr, y);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
+}
+
+// The reference-space arithmetic of k_tet4_nh_ref as the element body of the warp-cooperative kernel (wc.cuh).
+namespace {
+template <int MINB>
+struct Tet4NHRefBody {
+  static constexpr int min_ctas = MINB;
+  template <int MODE>
+  TATVA_D static void run(const NeoHookean& m, const double (&X)[4][3], const double (&U)[4][3], const double (&V)[4][3],
+                          double (&Y)[4][3]) {
+    double J[3][3], Fr[3][3], Gv[3][3], Q[3][3];  // J[d][c] = dX_c/dxi_d ; Fr[i][d] = dx_i/dxi_d
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        J[d][c] = X[d + 1][c] - X[0][c];
+        Fr[c][d] = J[d][c] + (U[d + 1][c] - U[0][c]);
+        if constexpr (MODE == MODE_HVP) Gv[c][d] = V[d + 1][c] - V[0][c];
+      }
+    if constexpr (MODE == MODE_HVP) point_flux(J, Fr, Gv, m.mu * (1.0 / 6.0), m.lmbda * (1.0 / 6.0), Q);
+    else point_flux_residual(J, Fr, m.mu * (1.0 / 6.0), m.lmbda * (1.0 / 6.0), Q);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      Y[1][i] = Q[i][0];
+      Y[2][i] = Q[i][1];
+      Y[3][i] = Q[i][2];
+      Y[0][i] = -(Q[i][0] + Q[i][1] + Q[i][2]);
+    }
+  }
+};
+}  // namespace
+
+int tet4_nh_wc(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y,
+               cudaStream_t st) {
+  const NeoHookean m{mu, lmbda};
+  if (p->variant == 32) {  // occupancy A/B: 4 CTAs per SM (no spill) instead of 5
+    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
+    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
+  }
+  if (p->variant == 33) {  // A/B: element's own gather + per-tile node sums
+    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>, false, true>(p, m, u, v, y, st);
+    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>, false, true>(p, m, u, v, y, st);
+  }
+  if (p->variant == 34) {  // A/B: shuffle gather + per-warp sector-grouped scatter
+    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>, true, false>(p, m, u, v, y, st);
+    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>, true, false>(p, m, u, v, y, st);
+  }
+  if (p->variant == 36) {  // persistent at 4 CTAs per SM: room for the prefetched index data without spills
+    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st, true);
+    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st, true);
+  }
+  const bool persistent = p->variant == 37;  // 37: resident grid walking the tiles, index data prefetched one tile ahead (5 CTAs per SM: spills)
+  if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>>(p, m, u, v, y, st, persistent);
+  return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>>(p, m, u, v, y, st, persistent);
 }
 
 int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y,

@@ -291,6 +291,7 @@ class Lifter:
             with torch.cuda.device(ur.device):
                 _lib.check(_lib.lib().tatva_lift(ur.data_ptr(), src.data_ptr(), consts.data_ptr(), base.data_ptr() if base is not None else None, self.size, out.data_ptr(), self._stream()), "tatva_lift")
             return out[: self._local_size] if self._local_size != self.size else out
+        _lib.host_tables_only("Lifter.lift")
         src, consts, _, _ = self._compose()
         ur = _np(u_reduced)
         out = np.zeros(self.size, dtype=ur.dtype) if u_full is None else np.array(_np(u_full), dtype=ur.dtype, copy=True)
@@ -315,6 +316,7 @@ class Lifter:
             with torch.cuda.device(uf.device):
                 _lib.check(_lib.lib().tatva_halo_pack(uf.data_ptr(), free.data_ptr(), self.size_reduced, out.data_ptr(), self._stream()), "tatva_halo_pack")
             return out
+        _lib.host_tables_only("Lifter.reduce")
         return _np(u_full)[self.free_dofs]
 
     def reduce_adjoint(self, r_full, out=None):
@@ -328,6 +330,7 @@ class Lifter:
             with torch.cuda.device(rf.device):
                 _lib.check(_lib.lib().tatva_reduce_adjoint(rf.data_ptr(), ptr.data_ptr(), lst.data_ptr(), self.size_reduced, out.data_ptr(), self._stream()), "tatva_reduce_adjoint")
             return out
+        _lib.host_tables_only("Lifter.reduce_adjoint")
         src, _, _, _ = self._compose()
         rf = _np(r_full)
         readers = src >= 0

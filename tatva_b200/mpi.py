@@ -13,8 +13,9 @@ surface as the reference: `ExchangePlan(layout, local_sparsity_pattern=None, com
 `AllreducePlan(global_size, global_sparsity_pattern=None, comm=...)` with `make_allgather`,
 `make_allreduce_owned`; `_create_dof_layout`, `_dof_range`.
 
-With CPU tensors (the world_size-2 `gloo` tests of the host logic) packing is plain tensor
-indexing; that mode exists for those tests only — GPU runs always go through the kernels.
+With CPU tensors packing is plain tensor indexing: that mode exists for the world_size-2 `gloo`
+tests of the host logic only and must be switched on with TATVA_B200_HOST_TABLES=1 (tests/conftest.py
+does); otherwise a CPU operand raises — GPU runs always go through the kernels.
 """
 from __future__ import annotations
 
@@ -223,6 +224,7 @@ def _pack(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         out = torch.empty(idx.numel(), dtype=src.dtype, device=src.device)
         _lib.check(_lib.lib().tatva_halo_pack(src.data_ptr(), idx.data_ptr(), idx.numel(), out.data_ptr(), _stream()), "tatva_halo_pack")
         return out
+    _lib.host_tables_only("ExchangePlan pack")
     return src[idx]
 
 
@@ -232,10 +234,12 @@ def _unpack(dst: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor, add: bool)
     if dst.is_cuda:
         fn = _lib.lib().tatva_halo_unpack_add if add else _lib.lib().tatva_halo_unpack_set
         _lib.check(fn(vals.data_ptr(), idx.data_ptr(), idx.numel(), dst.data_ptr(), _stream()), "tatva_halo_unpack")
-    elif add:
-        dst.index_add_(0, idx, vals)
     else:
-        dst[idx] = vals
+        _lib.host_tables_only("ExchangePlan unpack")
+        if add:
+            dst.index_add_(0, idx, vals)
+        else:
+            dst[idx] = vals
 
 
 class _Router:

@@ -5,6 +5,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the host-side index paths (Lifter tables on NumPy vectors, exchange plans on CPU tensors over gloo) are test-only:
+# they raise unless switched on; spawned gloo ranks inherit the variable
+os.environ.setdefault("TATVA_B200_HOST_TABLES", "1")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
