@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` (configs 1, 2, 5) and `strong_scaling` blocks")
-    ap.add_argument("--halo", default=os.environ.get("TATVA_HALO", "peer"), choices=["nccl", "peer"], help="multi-GPU halo transport")
+    ap.add_argument("--halo", default=os.environ.get("TATVA_HALO", "peer"), choices=["nccl", "nccl_torch", "peer"], help="multi-GPU halo transport")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 6  /* bumped on every signature change; the Python loader refuses a mismatch */
+#define TATVA_B200_ABI_VERSION 7  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */
@@ -280,6 +280,23 @@ int tatva_halo_unpack_set(const double* d_src, const int64_t* d_idx, int64_t n, 
                           tatva_stream_t stream);
 int tatva_halo_unpack_add(const double* d_src, const int64_t* d_idx, int64_t n, double* d_dst,
                           tatva_stream_t stream);
+
+/* The exchange itself over an ncclComm_t (tatva/mpi.py:372-409 forward fill, :479-516 reverse add — there
+ * one blocking mpi4jax.sendrecv per neighbour, :403-405 / :509-511): pack kernel -> ONE grouped ncclSend / ncclRecv with
+ * every neighbour -> unpack kernel, all on `stream`, no allocation, no synchronisation.  `nccl_comm` is an ncclComm_t;
+ * send_counts / recv_counts are HOST arrays with one entry per rank of the communicator (own rank: 0), the index arrays
+ * list the neighbours' entries in rank order, d_send_buf / d_recv_buf hold sum(send_counts) / sum(recv_counts) doubles.
+ * add = 0: d_dst[d_recv_idx[k]] = received (ghost refresh); add = 1: += (reverse add).  d_src may equal d_dst.
+ * NCCL is opened with dlopen at first use (TATVA_E_UNSUPPORTED if the machine has none).                           */
+int tatva_halo_exchange(void* nccl_comm, const double* d_src, const int64_t* d_send_idx, const int64_t* send_counts,
+                        double* d_send_buf, double* d_recv_buf, const int64_t* recv_counts, const int64_t* d_recv_idx,
+                        double* d_dst, int add, tatva_stream_t stream);
+/* For a host without a communicator of its own: rank 0 draws the 128-byte id (tatva_halo_comm_unique_id), the host
+ * ships it to the other ranks, every rank calls tatva_halo_comm_create (collective) with its device current.       */
+int tatva_nccl_version(int* version);
+int tatva_halo_comm_unique_id(void* id128);
+int tatva_halo_comm_create(void** nccl_comm, const void* id128, int n_ranks, int rank);
+int tatva_halo_comm_destroy(void* nccl_comm);
 
 /* Peer-memory variant of the exchange (one box, NVLink / NVSwitch): local vectors live in peer-mapped memory,
  * `d_peer_ptrs[r]` is rank r's base address of the same vector, and each ghost entry g knows its owner rank and

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtatva_b200.so")
-SOURCES = ["generic.cu", "neo_hookean.cu", "user_law.cu", "host.cpp", "xla_ffi_shim.cc"]  # the shim is empty without jaxlib headers
+SOURCES = ["generic.cu", "neo_hookean.cu", "user_law.cu", "halo_nccl.cu", "host.cpp", "xla_ffi_shim.cc"]  # the shim is empty without jaxlib headers
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "tatva_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

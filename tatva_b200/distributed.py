@@ -18,6 +18,8 @@ GPU) crosses NVLink; there is no other data-path collective.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -88,6 +90,27 @@ def _hash_uniform(gid, seed):
     return (x >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
 
 
+_ABI_COMMS = {}
+
+
+def _abi_nccl_comm(comm, device):
+    """An ncclComm_t of our own over the ranks of `comm` (torch does not hand out its communicators): rank 0 draws the
+    id through the C ABI, torch.distributed ships it, every rank joins.  One per (group, device), kept for the process."""
+    key = (id(comm.group), str(device))
+    if key not in _ABI_COMMS:
+        L = _lib.lib()
+        buf = (C.c_char * 128)()
+        if comm.rank == 0:
+            _lib.check(L.tatva_halo_comm_unique_id(buf), "tatva_halo_comm_unique_id")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(comm.group, 0) if comm.group is not None else 0, group=comm.group)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(L.tatva_halo_comm_create(C.byref(handle), box[0], comm.size, comm.rank), "tatva_halo_comm_create")
+        _ABI_COMMS[key] = handle
+    return _ABI_COMMS[key]
+
+
 class PartitionedOperator:
     """Operator over one partition + its ExchangePlan + the overlapped distributed HVP / residual."""
 
@@ -122,8 +145,14 @@ class PartitionedOperator:
         self._prm = _lib.params_array(material.params())
         self._L = _lib.lib()
         # halo = "peer": vectors in symmetric (peer-mapped) memory, ghosts pulled / pushed by our own kernels over
-        # NVLink with a device-side barrier on each side; halo = "nccl": pack -> all_to_all_single -> unpack.
-        self.halo = halo if self.comm.size > 1 else "nccl"
+        # NVLink with a device-side barrier on each side;
+        # halo = "nccl": the same exchange entirely behind the C ABI (tatva_halo_exchange: pack kernel -> grouped
+        # ncclSend / ncclRecv on an ncclComm_t of our own -> unpack kernel); "nccl_torch": torch's all_to_all_single.
+        if halo not in ("nccl", "nccl_torch", "peer"):
+            raise ValueError(f"unknown halo transport {halo!r}")
+        self.halo = halo if self.comm.size > 1 else "nccl_torch"
+        self._nccl = _abi_nccl_comm(self.comm, self.device) if self.halo == "nccl" else None
+        self._xbuf = {}
         self._sym = {}
         if self.halo == "peer":
             self._setup_peer_tables()
@@ -256,6 +285,17 @@ class PartitionedOperator:
         from .mpi import _pack, _unpack
 
         send_idx, recv_idx, _, _ = router.tables(src.device)
+        if self._nccl is not None:
+            key = id(router)
+            if key not in self._xbuf:  # staging buffers and the HOST count arrays of this direction, once
+                mk = lambda n: torch.empty(max(int(n), 1), dtype=torch.float64, device=src.device)  # noqa: E731
+                cnt = lambda v: (C.c_int64 * len(v))(*[int(x) for x in v])  # noqa: E731
+                self._xbuf[key] = (mk(sum(router.send_splits)), mk(sum(router.recv_splits)), cnt(router.send_splits), cnt(router.recv_splits))
+            sbuf, rbuf, sc, rc = self._xbuf[key]
+            with torch.cuda.device(src.device):
+                _lib.check(self._L.tatva_halo_exchange(self._nccl, src.data_ptr(), send_idx.data_ptr(), sc, sbuf.data_ptr(), rbuf.data_ptr(), rc, recv_idx.data_ptr(), dst.data_ptr(), int(bool(add)),
+                                                      torch.cuda.current_stream(src.device).cuda_stream), "tatva_halo_exchange")
+            return
         send_buf = _pack(src, send_idx)
         recv_buf = torch.empty(int(sum(router.recv_splits)), dtype=src.dtype, device=src.device)
         dist.all_to_all_single(recv_buf, send_buf, router.recv_splits, router.send_splits, group=self.comm.group)

@@ -24,7 +24,7 @@ torch.cuda.set_device(lr)
 dev = torch.device(f"cuda:{{lr}}")
 dist.init_process_group("nccl", device_id=dev)
 out = {{}}
-for halo in ("nccl", "peer"):
+for halo in ("nccl", "nccl_torch", "peer"):
     out[halo] = distributed_parity(10, rank, world, dev, materials.NeoHookean(500.0, 1000.0), halo=halo)
 if rank == 0:
     print("PARITY " + json.dumps(out))
