@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 7  /* bumped on every signature change; the Python loader refuses a mismatch */
+#define TATVA_B200_ABI_VERSION 8  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */
@@ -74,7 +74,8 @@ int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, 
 /* Measurement switch, not part of the drop-in surface: 0 (default) = the tuned kernels; 1 = the generic element /
  * law templates everywhere (TATVA_VARIANT_GENERIC, the parity cross-check of every specialised kernel); other
  * values select alternative implementations kept for A/B timing, per kernel family (DESIGN.md sections 3.1-3.3):
- *   Hex8 x neo-Hookean HVP   2, 3, 8, 9, 15, 16, 17, 20, 22, 23, 25, 26, 27 (sector-grouped scatter), 28 (16-byte gathers)
+ *   Hex8 x neo-Hookean HVP   2, 3, 8, 9, 15, 16, 17, 20, 22, 23, 25, 26, 27 (sector-grouped scatter), 28 (16-byte gathers),
+ *                            50-56 = occupancy / staging points of the cached-geometry kernel (with a geometry cache)
  *   Hex8 residual / energy   2 = first modal kernel, 3 / 4 = pair kernel at other register / occupancy points
  *   Tet4 x neo-Hookean       30 = persistent kernel with connectivity prefetch, 31 = element-per-thread kernel even
  *                            when the plan carries a node schedule (tatva_plan_set_node_schedule)
@@ -87,6 +88,14 @@ int tatva_plan_info(const tatva_plan_t* plan, int* element, int* dim, int* npe, 
 int tatva_plan_rebind(tatva_plan_t* plan, const double* d_coords, const int32_t* d_conn);
 
 int tatva_plan_set_variant(tatva_plan_t* plan, int variant);
+
+/* Geometry cache for the Hex8 x neo-Hookean HVP (r02): everything the Gauss-point loop derives from the MESH alone —
+ * (1 / det J) adj(J)^T adj(J), det J and 1 / det J at the 8 Gauss points, J = dX/dxi (tatva/element/base.py:90-93,
+ * :99-115) — computed once and kept by the plan, 512 bytes per element, as Operator(cache_weights=True) keeps det J
+ * (tatva/operator.py:119-130).  The HVP then reads it back (one coalesced 512-byte row per warp and load) instead of
+ * re-deriving it: 64 of 305 FP64 instructions per Gauss point less, paid with HBM bandwidth the FP64-bound kernel leaves
+ * idle.  enable = 0 frees the cache.  Hex8 with the default rule only (TATVA_E_UNSUPPORTED otherwise).  Allocates.   */
+int tatva_plan_cache_geometry(tatva_plan_t* plan, int enable, tatva_stream_t stream);
 
 /* User-supplied quadrature rule — Element(quad_points, quad_weights), tatva/element/base.py:37-51.  `points` is
  * (nq, reference dimension) row-major HOST memory, `weights` (nq) HOST memory, nq <= 64; nq = 0 restores the element's

@@ -697,6 +697,9 @@ struct tatva_plan {
   const int32_t* tile_nodes;
   const uint16_t* tile_conn;
   int tile_max_unique;
+  // optional geometry cache of the Hex8 pair kernels (tatva_plan_cache_geometry): plan-owned, 64 doubles per element
+  double* geo;
+  int64_t geo_stride;  // elements per row of the cache (the full element list, also for a sub-range view)
   // optional node schedule of the warp-cooperative fused kernels (tatva_plan_set_node_schedule)
   const int32_t* ws_warp_nodes;
   const uint8_t* ws_warp_local;
@@ -763,6 +766,7 @@ int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const
 
 int hex8_nh_hvp_modal_dot(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                           double* dot_partials, cudaStream_t st);
+int hex8_geometry_cache(const tatva_plan* p, double* geo, int64_t stride, cudaStream_t st);
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st);
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);

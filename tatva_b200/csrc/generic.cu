@@ -1527,6 +1527,8 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->tile_conn = nullptr;
   p->tile_max_unique = 0;
   p->ws_warp_nodes = nullptr;
+  p->geo = nullptr;
+  p->geo_stride = 0;
   p->custom = 0;
   p->scratch_len = (int64_t)grid_for(n_elems) * (kBlock / 32) > 1024 * 64 ? (int64_t)grid_for(n_elems) * (kBlock / 32) : 1024 * 64;
   cudaError_t e = cudaMalloc(&p->scratch, sizeof(double) * p->scratch_len);
@@ -1548,6 +1550,7 @@ int tatva_plan_destroy(tatva_plan_t* p) {
   if (!p) return TATVA_OK;
   if (p->scratch) cudaFree(p->scratch);
   if (p->weights) cudaFree(p->weights);
+  if (p->geo) cudaFree(p->geo);
   delete p;
   return TATVA_OK;
 }
@@ -1610,10 +1613,28 @@ int tatva_plan_set_point_grid(tatva_plan_t* p, int nx, int ny, const double* lo,
 
 int tatva_plan_rebind(tatva_plan_t* p, const double* d_coords, const int32_t* d_conn) {
   if (!p || !d_coords || !d_conn) return TATVA_E_INVALID;
-  if (p->weights && d_coords != p->coords) return TATVA_E_UNSUPPORTED;  // cached weights belong to the old coordinates
+  if ((p->weights || p->geo) && (d_coords != p->coords || (p->geo && d_conn != p->conn))) return TATVA_E_UNSUPPORTED;  // cached weights / geometry belong to the old mesh buffers
   p->coords = d_coords;
   p->conn = d_conn;
   return TATVA_OK;
+}
+
+// Mesh-only part of the Hex8 x neo-Hookean Gauss-point arithmetic, computed once and kept by the plan (64 doubles per
+// element; see k_hex8_geometry).  enable = 0 frees it.  Allocates: call it at set-up time, not inside a captured region.
+int tatva_plan_cache_geometry(tatva_plan_t* p, int enable, tatva_stream_t stream) {
+  if (!p) return TATVA_E_INVALID;
+  if (!enable) {
+    if (p->geo) TATVA_CUDA_TRY(cudaFree(p->geo));
+    p->geo = nullptr;
+    p->geo_stride = 0;
+    return TATVA_OK;
+  }
+  if (p->element != TATVA_HEX8 || p->custom) return TATVA_E_UNSUPPORTED;
+  if (!p->geo) {
+    TATVA_CUDA_TRY(cudaMalloc(&p->geo, sizeof(double) * 64 * (size_t)p->n_elems));
+    p->geo_stride = p->n_elems;
+  }
+  return hex8_geometry_cache(p, p->geo, p->geo_stride, (cudaStream_t)stream);
 }
 
 int tatva_plan_set_variant(tatva_plan_t* p, int variant) {
@@ -2233,6 +2254,7 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
   sub.zero_output = zero_y ? 1 : 0;
   sub.tile_ptr = nullptr;  // tiles and node schedules describe the whole element list, not a sub-range
   sub.ws_warp_nodes = nullptr;
+  if (sub.geo) sub.geo += 2 * elem_begin;  // the cache is element-fastest: a sub-range is an offset view (same stride)
   return dispatch_fused<MODE_HVP>(&sub, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
 }
 int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,

@@ -1077,6 +1077,204 @@ __global__ void __launch_bounds__(kBlock, MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Geometry cache (r02): the HVP is bound by FP64 issue while HBM sits at 9 % of its peak, and a fifth of the loop's FP64
+// instructions only re-derive what depends on the MESH alone — J = dX/dxi at the Gauss point, its adjugate and
+// determinant, M = K^T K.  tatva_plan_cache_geometry computes them once per plan (as Operator(cache_weights=True) keeps
+// det J, tatva/operator.py:119-130): per Gauss point 8 doubles
+//     Mg = (1 / det J) adj(J)^T adj(J)  (6, symmetric: 00 01 02 11 12 22),  det J,  1 / det J
+// in the scaled units of the pair kernels (J = 8 dX/dxi), stored element-fastest as double2 so that a warp reads 512
+// contiguous bytes per load:  geo[((pq * 2 + s) * 4 + k) * stride + e],  pq = pair iteration, s = xi sign (-, +).
+// 512 bytes per element per application (1.07 GB at 128^3) bought for 64 of 305 FP64 instructions per Gauss point.
+// ---------------------------------------------------------------------------------------------
+TATVA_HD void point_geometry(const double (&J)[3][3], double (&g)[8]) {
+  double Kc[3][3], detJ;
+  adjugate(J, Kc, detJ);
+  const double rJ = fast_rcp(detJ);
+  int t = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) g[t++] = (Kc[0][a] * Kc[0][b] + Kc[1][a] * Kc[1][b] + Kc[2][a] * Kc[2][b]) * rJ;
+  g[6] = detJ;
+  g[7] = rJ;
+}
+
+__global__ void __launch_bounds__(kBlock) k_hex8_geometry(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                          int64_t E, double2* __restrict__ geo, int64_t stride) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  double hX[3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double f[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) f[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+    to_modal_raw(f, hX[c]);
+  }
+#pragma unroll 1
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1];
+    double Jm[3][3], Jp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double gm[3], gp[3];
+      ref_grad8_pair(hX[c], sy, sz, gm, gp);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Jm[d][c] = gm[d];
+        Jp[d][c] = gp[d];
+      }
+    }
+    double g[8];
+    point_geometry(Jm, g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) geo[((pq * 2 + 0) * 4 + k) * stride + e] = make_double2(g[2 * k], g[2 * k + 1]);
+    point_geometry(Jp, g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) geo[((pq * 2 + 1) * 4 + k) * stride + e] = make_double2(g[2 * k], g[2 * k + 1]);
+  }
+}
+
+// point_flux with the mesh-only part read from the cache: g = {Mg00, Mg01, Mg02, Mg11, Mg12, Mg22, det J, 1 / det J}
+TATVA_HD void point_flux_geo(const double (&g)[8], const double (&Fr)[3][3], const double (&Gv)[3][3], double mu_s,
+                            double lm_s, double (&Q)[3][3]) {
+  double Ac[3][3], detF;
+  adjugate(Fr, Ac, detF);
+  const double rF = fast_rcp(detF);
+  const double lnJ = log_pos(detF * g[7]);
+  double B[3][3];
+  mat3(Ac, Gv, B);
+  const double wF = g[6] * rF * rF;
+  const double w2 = (mu_s - lm_s * lnJ) * wF, w3 = lm_s * wF * (B[0][0] + B[1][1] + B[2][2]);
+  double M[3][3];
+  M[0][0] = mu_s * g[0];
+  M[0][1] = M[1][0] = mu_s * g[1];
+  M[0][2] = M[2][0] = mu_s * g[2];
+  M[1][1] = mu_s * g[3];
+  M[1][2] = M[2][1] = mu_s * g[4];
+  M[2][2] = mu_s * g[5];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int f = 0; f < 3; ++f) B[d][f] = (d == f) ? fma(w2, B[d][f], w3) : w2 * B[d][f];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Q[i][d] = Gv[i][0] * M[0][d];
+#pragma unroll
+  for (int k = 1; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Q[i][d] = fma(Gv[i][k], M[k][d], Q[i][d]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Q[i][d] = fma(B[d][k], Ac[k][i], Q[i][d]);
+}
+
+// The pair kernel on the cached geometry.  STAGE: 0 = modal x and v in registers, 1 = v staged in shared memory,
+// 2 = x and v staged (42 doubles per thread).
+template <int MINB, int STAGE>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_hex8_nh_hvp_geo(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu, double lmbda,
+                      const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ y,
+                      const double2* __restrict__ geo, int64_t stride) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  extern __shared__ double sm[];
+  double* sv0 = sm + threadIdx.x;
+  double* sx0 = sm + 21 * kBlock + threadIdx.x;
+  double hx[STAGE >= 2 ? 1 : 3][7], hv[STAGE ? 1 : 3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double fx[8], fv[8], tx_[7], tv[7];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      fx[n] = __ldg(coords + (int64_t)nd[n] * 3 + c) + __ldg(u + (int64_t)nd[n] * 3 + c);  // deformed coordinates: ONE transform
+      fv[n] = __ldg(v + (int64_t)nd[n] * 3 + c);
+    }
+    to_modal_raw(fx, tx_);
+    to_modal_raw(fv, tv);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      if constexpr (STAGE >= 2) sx0[(c * 7 + k) * kBlock] = tx_[k];
+      else hx[c][k] = tx_[k];
+      if constexpr (STAGE) sv0[(c * 7 + k) * kBlock] = tv[k];
+      else hv[c][k] = tv[k];
+    }
+  }
+  double R[3][7];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
+  const double2* ge = geo + e;
+#pragma unroll 1
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
+    int opaque = 0;
+    asm volatile("" : "+r"(opaque));
+    const double* sv = sv0 + opaque;
+    const double* sx = sx0 + opaque;
+    double gm[8], gp[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double2 a = __ldg(ge + ((pq * 2 + 0) * 4 + k) * stride), b = __ldg(ge + ((pq * 2 + 1) * 4 + k) * stride);
+      gm[2 * k] = a.x; gm[2 * k + 1] = a.y;
+      gp[2 * k] = b.x; gp[2 * k + 1] = b.y;
+    }
+    double Frm[3][3], Frp[3][3], Gvm[3][3], Gvp[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if constexpr (STAGE >= 2) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sx[(i * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, Frm[i], Frp[i]);
+      } else {
+        ref_grad8_pair(hx[i], sy, sz, Frm[i], Frp[i]);
+      }
+      if constexpr (STAGE) {
+        double t[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = sv[(i * 7 + k) * kBlock];
+        ref_grad8_pair(t, sy, sz, Gvm[i], Gvp[i]);
+      } else {
+        ref_grad8_pair(hv[i], sy, sz, Gvm[i], Gvp[i]);
+      }
+    }
+    double Qm[3][3], Qp[3][3];
+    point_flux_geo(gm, Frm, Gvm, mu, lmbda, Qm);
+    point_flux_geo(gp, Frp, Gvp, mu, lmbda, Qp);
+    accumulate_pair(Qm, Qp, sy, sz, syz, R);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double f[8];
+    from_modal_raw(R[i], f);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) atomicAdd(y + (int64_t)nd[n] * 3 + i, f[n]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // v4: the v3 arithmetic in a PERSISTENT kernel that hides the gather and scatter phases.
 // ncu (profiles/r02_hvp_ncu_stalls.md): a v3 warp spends 29 % of its life in the gather / modal-transform prologue (41 %
 // of that waiting on the dependent connectivity -> nodal-row round trips to L2 / HBM) and 9 % in the scatter epilogue
@@ -2001,10 +2199,40 @@ static int launch_v5(const tatva_plan* p, double mu, double lmbda, const double*
   return TATVA_OK;
 }
 
+template <int MINB, int STAGE>
+static int launch_geo(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st) {
+  constexpr size_t smem = (size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 21 : 42)) * kBlock * sizeof(double);
+  static_assert(smem <= 48 * 1024, "fits the default shared-memory window");
+  k_hex8_nh_hvp_geo<MINB, STAGE><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y,
+                                                                             reinterpret_cast<const double2*>(p->geo), p->geo_stride);
+  return TATVA_OK;
+}
+
+int hex8_geometry_cache(const tatva_plan* p, double* geo, int64_t stride, cudaStream_t st) {
+  k_hex8_geometry<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, reinterpret_cast<double2*>(geo), stride);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   int rc = TATVA_OK;
+  if (p->geo && (p->variant == 0 || (p->variant >= 50 && p->variant <= 56))) {
+    switch (p->variant) {  // occupancy / staging points of the cached-geometry kernel
+      case 50: rc = launch_geo<2, 0>(p, mu, lmbda, u, v, y, st); break;
+      case 51: rc = launch_geo<2, 1>(p, mu, lmbda, u, v, y, st); break;
+      case 52: rc = launch_geo<3, 1>(p, mu, lmbda, u, v, y, st); break;
+      case 53: rc = launch_geo<3, 2>(p, mu, lmbda, u, v, y, st); break;
+      case 54: rc = launch_geo<4, 2>(p, mu, lmbda, u, v, y, st); break;
+      case 55: rc = launch_geo<3, 0>(p, mu, lmbda, u, v, y, st); break;
+      case 56: rc = launch_geo<4, 1>(p, mu, lmbda, u, v, y, st); break;
+      default: rc = launch_geo<3, 2>(p, mu, lmbda, u, v, y, st); break;
+    }
+    if (rc != TATVA_OK) return rc;
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   // measurement variants documented in DESIGN.md §3.1 (tatva_plan_set_variant); default = v3 pair kernel
   switch (p->variant) {
     case 2: k_hex8_nh_hvp<2><<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y); break;

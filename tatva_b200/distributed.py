@@ -143,6 +143,7 @@ class PartitionedOperator:
         # high priority: the small exchange / boundary kernels must not queue behind the interior grid
         self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap else None
         self._prm = _lib.params_array(material.params())
+        self.op._ensure_geometry(material.material_id)  # set-up work (allocates): not inside a captured application
         self._L = _lib.lib()
         # halo = "peer": vectors in symmetric (peer-mapped) memory, ghosts pulled / pushed by our own kernels over
         # NVLink with a device-side barrier on each side;

@@ -26,6 +26,7 @@ from .element import Element
 from .mesh import Mesh
 
 
+_HVP_CALLS = {"tatva_hvp", "tatva_hvp_elems", "tatva_hvp_dot"}
 _FUSED_CALLS = {"tatva_energy", "tatva_residual", "tatva_hvp", "tatva_hvp_lifted", "tatva_hvp_lifted_dot", "tatva_hvp_dot", "tatva_hessian_diag", "tatva_csr_assemble", "tatva_csr_assemble_tiled", "tatva_csr_assemble_sym", "tatva_csr_assemble_rows"}
 
 
@@ -34,7 +35,7 @@ def _stream() -> int:
 
 
 class Operator:
-    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None, sort_elements: bool = False, stage_tiles: bool = False, node_schedule: bool | int | str = "auto"):
+    def __init__(self, mesh: Mesh, element: Element, batch_size: int | None = None, cache_weights: bool = False, *, device=None, sort_elements: bool = False, stage_tiles: bool = False, node_schedule: bool | int | str = "auto", cache_geometry: bool = False):
         self.mesh = mesh
         self.element = element
         self.cache_weights = bool(cache_weights)
@@ -58,6 +59,11 @@ class Operator:
         self.n_elements, self.npe = self.elements.shape
         self.nq = len(element.quad_weights)
         self._batch_size_arg, self._sort_elements, self._node_schedule_arg = batch_size, bool(sort_elements), node_schedule
+        # Hex8 x neo-Hookean HVP, opt-in: the mesh-only part of the Gauss-point arithmetic computed once and kept by the plan
+        # (tatva_plan_cache_geometry, 512 bytes per element, built at the first such HVP).  Measured SLOWER on B200 at
+        # config 3 (0.514 vs 0.396 ms: 21 % fewer FP64 instructions, but streaming 1.07 GB per application at 12 warps per
+        # SM leaves too few bytes in flight to hide HBM latency), so the default re-derives the geometry every time.
+        self._cache_geometry, self._geometry_cached = bool(cache_geometry), False
         self.batch_size = self.n_elements if batch_size is None else int(batch_size)  # operator.py:116-117
         self.quad_points = torch.as_tensor(element.quad_points, dtype=torch.float64, device=self.device)
         self._L = _lib.lib()
@@ -124,7 +130,7 @@ class Operator:
     def _replace(self, **changes) -> "Operator":
         """A new Operator with the given constructor arguments changed (operator.py:497-504, `dataclasses.replace`);
         a new plan is created, nothing is shared with `self`."""
-        kw = dict(mesh=self.mesh, element=self.element, batch_size=self._batch_size_arg, cache_weights=self.cache_weights, device=self.device, sort_elements=self._sort_elements, stage_tiles=self._tiles is not None, node_schedule=self._node_schedule_arg)
+        kw = dict(mesh=self.mesh, element=self.element, batch_size=self._batch_size_arg, cache_weights=self.cache_weights, device=self.device, sort_elements=self._sort_elements, stage_tiles=self._tiles is not None, node_schedule=self._node_schedule_arg, cache_geometry=self._cache_geometry)
         unknown = set(changes) - set(kw)
         if unknown:
             raise TypeError(f"Operator._replace() got unexpected field(s): {sorted(unknown)}")
@@ -229,8 +235,17 @@ class Operator:
 
     def _call(self, name, *args):
         plan = self._plan_fused if name in _FUSED_CALLS else self._plan
+        if name in _HVP_CALLS and args:
+            self._ensure_geometry(args[0])
         with torch.cuda.device(self.device):
             _lib.check(getattr(self._L, name)(plan, *args, _stream()), name)
+
+    def _ensure_geometry(self, material_id) -> None:
+        """Build the plan's geometry cache before the first Hex8 x neo-Hookean HVP (set-up work: it allocates)."""
+        if self._cache_geometry and not self._geometry_cached and self.element.kind == _lib.HEX8 and not self._custom_rule and material_id == _lib.NEO_HOOKEAN:
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.tatva_plan_cache_geometry(self._plan_fused, 1, _stream()), "tatva_plan_cache_geometry")
+            self._geometry_cached = True
 
     # raw (non-differentiable) kernel wrappers; nodal arrays are (N, nv) contiguous
     def _k_grad(self, u2):

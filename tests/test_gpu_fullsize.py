@@ -111,3 +111,36 @@ def test_config5_compound_phase_field_tet4_55_vs_c_oracle():
     assert abs(float(op.energy(mat)(arr)) - e_ref) <= RTOL * abs(e_ref)
     _assert_close(op.residual(mat)(arr).reshape(-1, 4), c_oracle.residual_pf("tet4", prm, c, el, s), RTOL)
     _assert_close(op.hvp(mat)(arr, tt).reshape(-1, 4), c_oracle.hvp_pf("tet4", prm, c, el, s, t), RTOL)
+
+
+@pytest.mark.parametrize("n", [5, 32])
+def test_hex8_geometry_cache_variants_vs_c_oracle(n):
+    """The Hex8 x neo-Hookean HVP on the plan's geometry cache (tatva_plan_cache_geometry, opt-in) and every
+    occupancy / staging point of that kernel (variants 50-56), against the C oracle; the default operator runs the kernel
+    that re-derives the geometry; an element sub-range reads the cache through an offset view."""
+    import ctypes as C
+
+    from tatva_b200 import _lib
+
+    c, el, u, v, (mname, omat) = _case("hex8", n)
+    ref = c_oracle.hvp("hex8", (omat.mu, omat.lmbda), c, el, u, v)
+    mat = _material(mname, omat)
+    op = _make_op("hex8", c, el, cache_geometry=True)
+    _assert_close(op.hvp(mat)(u, v), ref, RTOL)
+    assert op._geometry_cached
+    for variant in (50, 51, 52, 53, 54, 55, 56):
+        op.set_variant(variant)
+        _assert_close(op.hvp(mat)(u, v), ref, RTOL)
+    op.set_variant(0)
+    op0 = _make_op("hex8", c, el)  # the default re-derives the geometry
+    _assert_close(op0.hvp(mat)(u, v), ref, RTOL)
+    assert not op0._geometry_cached
+    # two element sub-ranges accumulate to the full result (what the partitioned operator launches)
+    ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
+    y = torch.empty_like(ut)
+    prm, npar = _lib.params_array(mat.params())
+    E, cut = el.shape[0], el.shape[0] // 3 + 1
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), 0, cut, 1, st), "tatva_hvp_elems")
+    _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), cut, E - cut, 0, st), "tatva_hvp_elems")
+    _assert_close(y, ref, RTOL)
