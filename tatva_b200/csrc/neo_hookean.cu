@@ -1184,7 +1184,9 @@ TATVA_HD void point_flux_geo(const double (&g)[8], const double (&Fr)[3][3], con
 
 // The pair kernel on the cached geometry.  STAGE: 0 = modal x and v in registers, 1 = v staged in shared memory,
 // 2 = x and v staged (42 doubles per thread).
-template <int MINB, int STAGE>
+// PF: 1 = streaming (evict-first) loads of the cache, 2 = + the thread's 32 cache rows prefetched into L2 at kernel start
+// (one prefetch per 128-byte line: 12 warps x 16 KB in flight per SM instead of 12 x 4 KB)
+template <int MINB, int STAGE, int PF = 0>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_hex8_nh_hvp_geo(const double* __restrict__ coords, const int32_t* __restrict__ conn, int64_t E, double mu, double lmbda,
                       const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ y,
@@ -1197,6 +1199,13 @@ __global__ void __launch_bounds__(kBlock, MINB)
     const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
     nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
     nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  const double2* ge = geo + e;
+  if constexpr (PF >= 2) {
+    if ((threadIdx.x & 7) == 0) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(ge + r * stride));
+    }
   }
   extern __shared__ double sm[];
   double* sv0 = sm + threadIdx.x;
@@ -1225,7 +1234,6 @@ __global__ void __launch_bounds__(kBlock, MINB)
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int k = 0; k < 7; ++k) R[i][k] = 0.0;
-  const double2* ge = geo + e;
 #pragma unroll 1
   for (int pq = 0; pq < 4; ++pq) {
     const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
@@ -1236,7 +1244,8 @@ __global__ void __launch_bounds__(kBlock, MINB)
     double gm[8], gp[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double2 a = __ldg(ge + ((pq * 2 + 0) * 4 + k) * stride), b = __ldg(ge + ((pq * 2 + 1) * 4 + k) * stride);
+      const double2 a = PF ? __ldcs(ge + ((pq * 2 + 0) * 4 + k) * stride) : __ldg(ge + ((pq * 2 + 0) * 4 + k) * stride);
+      const double2 b = PF ? __ldcs(ge + ((pq * 2 + 1) * 4 + k) * stride) : __ldg(ge + ((pq * 2 + 1) * 4 + k) * stride);
       gm[2 * k] = a.x; gm[2 * k + 1] = a.y;
       gp[2 * k] = b.x; gp[2 * k + 1] = b.y;
     }
@@ -2199,11 +2208,11 @@ static int launch_v5(const tatva_plan* p, double mu, double lmbda, const double*
   return TATVA_OK;
 }
 
-template <int MINB, int STAGE>
+template <int MINB, int STAGE, int PF = 0>
 static int launch_geo(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st) {
   constexpr size_t smem = (size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 21 : 42)) * kBlock * sizeof(double);
   static_assert(smem <= 48 * 1024, "fits the default shared-memory window");
-  k_hex8_nh_hvp_geo<MINB, STAGE><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y,
+  k_hex8_nh_hvp_geo<MINB, STAGE, PF><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y,
                                                                              reinterpret_cast<const double2*>(p->geo), p->geo_stride);
   return TATVA_OK;
 }
@@ -2218,7 +2227,7 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
                       cudaStream_t st) {
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   int rc = TATVA_OK;
-  if (p->geo && (p->variant == 0 || (p->variant >= 50 && p->variant <= 56))) {
+  if (p->geo && (p->variant == 0 || (p->variant >= 50 && p->variant <= 58))) {
     switch (p->variant) {  // occupancy / staging points of the cached-geometry kernel
       case 50: rc = launch_geo<2, 0>(p, mu, lmbda, u, v, y, st); break;
       case 51: rc = launch_geo<2, 1>(p, mu, lmbda, u, v, y, st); break;
@@ -2227,6 +2236,8 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
       case 54: rc = launch_geo<4, 2>(p, mu, lmbda, u, v, y, st); break;
       case 55: rc = launch_geo<3, 0>(p, mu, lmbda, u, v, y, st); break;
       case 56: rc = launch_geo<4, 1>(p, mu, lmbda, u, v, y, st); break;
+      case 57: rc = launch_geo<3, 2, 1>(p, mu, lmbda, u, v, y, st); break;  // streaming loads
+      case 58: rc = launch_geo<3, 2, 2>(p, mu, lmbda, u, v, y, st); break;  // + L2 prefetch of the thread's rows
       default: rc = launch_geo<3, 2>(p, mu, lmbda, u, v, y, st); break;
     }
     if (rc != TATVA_OK) return rc;

@@ -12,7 +12,7 @@ if len(sys.argv) > 1 and sys.argv[1] in ("hvp", "residual", "energy"):
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 3, 15, 16, 17, 20, 22, 23, 25, 26, 27]
 c, el, u, v = synthetic_inputs(n)
-op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8(), cache_geometry=any(50 <= x <= 56 for x in variants))
+op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8(), cache_geometry=any(50 <= x <= 58 for x in variants))
 mat = materials.NeoHookean(500.0, 1000.0)
 ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
 y = torch.empty_like(ut)
