@@ -319,8 +319,12 @@ def secondary_single_gpu(device, hbm_peak_gbs):
         u = torch.as_tensor(smooth_u(c), device=device)
         v = torch.as_tensor(np.random.default_rng(1).normal(size=c.shape), device=device)
         y = torch.empty_like(u)
-        rec("c2_tet4_nh_residual", _timeit(lambda: op._raw_residual(mat, u)), 8 * (6 * N + 3 * N) + 16 * E, 3 * N, "DOF", fp64_floor_us=17.0)
-        rec("c2_tet4_nh_hvp", _timeit(lambda: op._raw_hvp(mat, u, v, out=y)), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", fp64_floor_us=17.0)
+        how = "node-schedule kernel (k_fused_wc): per-warp distinct-node gather, per-tile node sums before the atomic adds" if op._node_schedule is not None else "element-per-thread kernel"
+        op.set_variant(31)  # the element-per-thread kernel on the same plan
+        ept_r, ept_h = _timeit(lambda: op._raw_residual(mat, u), reps=100, warm=10), _timeit(lambda: op._raw_hvp(mat, u, v, out=y), reps=100, warm=10)
+        op.set_variant(0)
+        rec("c2_tet4_nh_residual", _timeit(lambda: op._raw_residual(mat, u), reps=100, warm=10), 8 * (6 * N + 3 * N) + 16 * E, 3 * N, "DOF", fp64_floor_us=17.0, how=how, ms_element_per_thread=round(ept_r, 5))
+        rec("c2_tet4_nh_hvp", _timeit(lambda: op._raw_hvp(mat, u, v, out=y), reps=100, warm=10), 8 * (9 * N + 3 * N) + 16 * E, 3 * N, "DOF", fp64_floor_us=17.0, how=how, ms_element_per_thread=round(ept_h, 5))
         pat = sparse.pattern_from_mesh(m, 3)
         cm = sparse.ColoredMatrix.from_csr(pat)
         asm = sparse.assembler(op, mat, cm)
@@ -358,7 +362,10 @@ def secondary_single_gpu(device, hbm_peak_gbs):
         ms_r, x_r = cg_ms(ConjugateGradient(red.matvec, n, device, use_graph=True), b)
         out["c3_cg_iteration_hex8_128"] = dict(ms=round(ms_m, 5), value=n / (ms_m * 1e-3), unit="DOF/s", how="CUDA graph; full-size vectors around the unconstrained HVP kernel, Dirichlet rows masked in the update pass (MaskedOperator)",
                                                ms_reduced_space_lifted_kernel=round(ms_r, 5), iterate_rel_diff_after_100=float((mo.restrict(x_m) - x_r).norm() / x_r.norm()))
-        del mo, red
+        diag = torch.empty(n, dtype=torch.float64, device=device)
+        rec("c3_hessian_diagonal_hex8_128", _timeit(lambda: red.diagonal(out=diag), reps=5, warm=2), 8 * 9 * c.shape[0] + 32 * el.shape[0], n, "DOF",
+            how="rank-structured diagonal (k_hessian_diag_rank): K_aa(i,i) = w1 |dN_a|^2 + (w2 + w3) g_a[i]^2; r01: 24 tangent evaluations per point, 1.72 ms")
+        del mo, red, diag
         # user-supplied densities at config 3 (README.md:93: the density is user code): written once on symbols, compiled
         # at run time into the fused kernel template; beside them the built-in law through the same generic template and
         # the r01 route for a density without a kernel (autograd through the Operator building blocks)

@@ -2411,8 +2411,8 @@ struct Tet4NHRefBody {
 int tet4_nh_wc(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y,
                cudaStream_t st) {
   const NeoHookean m{mu, lmbda};
-  if (p->variant == 32) {  // occupancy A/B: 4 CTAs per SM (no spill) instead of 5
-    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
+  if (p->variant == 32) {  // occupancy A/B: the other register point (HVP at 5 CTAs per SM with spills, residual at 4)
+    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>>(p, m, u, v, y, st, false);
     return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
   }
   if (p->variant == 33) {  // A/B: element's own gather + per-tile node sums
@@ -2428,6 +2428,9 @@ int tet4_nh_wc(const tatva_plan* p, bool hvp, double mu, double lmbda, const dou
     return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st, true);
   }
   const bool persistent = p->variant == 37;  // 37: resident grid walking the tiles, index data prefetched one tile ahead (5 CTAs per SM: spills)
+  // measured (profiles/r02_tet4_node_schedule.jsonl): the HVP is faster at 4 CTAs per SM without spills (0.0454 vs 0.0473 ms),
+  // the residual at 5 (0.0391 vs 0.0411)
+  if (hvp && !persistent) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
   if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>>(p, m, u, v, y, st, persistent);
   return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>>(p, m, u, v, y, st, persistent);
 }

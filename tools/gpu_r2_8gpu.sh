@@ -4,7 +4,7 @@
 # wrapped in its own timeout.
 mkdir -p gpurun_out
 N=${1:-8}
-TATVA_CHECK_HALOS=peer timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tools/dist_check.py 10 > gpurun_out/r02_dist_check_${N}gpu.log 2>&1; echo "dist_check rc=$?"
+TATVA_CHECK_HALOS=nccl,peer timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tools/dist_check.py 10 > gpurun_out/r02_dist_check_${N}gpu.log 2>&1; echo "dist_check rc=$?"
 tail -2 gpurun_out/r02_dist_check_${N}gpu.log | cut -c1-700
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 100 --warmup 10 > gpurun_out/r02_bench_${N}gpu.json 2> gpurun_out/r02_bench_${N}gpu.err; echo "bench rc=$?"
 python - <<PY
