@@ -2411,28 +2411,23 @@ struct Tet4NHRefBody {
 int tet4_nh_wc(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y,
                cudaStream_t st) {
   const NeoHookean m{mu, lmbda};
-  if (p->variant == 32) {  // occupancy A/B: the other register point (HVP at 5 CTAs per SM with spills, residual at 4)
-    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>>(p, m, u, v, y, st, false);
-    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
+  // A/B variants (profiles/r02_tet4_node_schedule.jsonl): 32 = the other occupancy point, 33 = the element's own gather +
+  // per-tile node sums, 34 = shuffle gather + per-warp sector-grouped scatter
+  if (p->variant == 32) {
+    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>>(p, m, u, v, y, st);
+    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st);
   }
-  if (p->variant == 33) {  // A/B: element's own gather + per-tile node sums
+  if (p->variant == 33) {
     if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>, false, true>(p, m, u, v, y, st);
     return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>, false, true>(p, m, u, v, y, st);
   }
-  if (p->variant == 34) {  // A/B: shuffle gather + per-warp sector-grouped scatter
+  if (p->variant == 34) {
     if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>, true, false>(p, m, u, v, y, st);
     return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>, true, false>(p, m, u, v, y, st);
   }
-  if (p->variant == 36) {  // persistent at 4 CTAs per SM: room for the prefetched index data without spills
-    if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st, true);
-    return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<4>>(p, m, u, v, y, st, true);
-  }
-  const bool persistent = p->variant == 37;  // 37: resident grid walking the tiles, index data prefetched one tile ahead (5 CTAs per SM: spills)
-  // measured (profiles/r02_tet4_node_schedule.jsonl): the HVP is faster at 4 CTAs per SM without spills (0.0454 vs 0.0473 ms),
-  // the residual at 5 (0.0391 vs 0.0411)
-  if (hvp && !persistent) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st, false);
-  if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<5>>(p, m, u, v, y, st, persistent);
-  return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>>(p, m, u, v, y, st, persistent);
+  // measured: the HVP is faster at 4 CTAs per SM without spills, the residual at 5
+  if (hvp) return launch_fused_wc<Tet4, NeoHookean, MODE_HVP, Tet4NHRefBody<4>>(p, m, u, v, y, st);
+  return launch_fused_wc<Tet4, NeoHookean, MODE_RESIDUAL, Tet4NHRefBody<5>>(p, m, u, v, y, st);
 }
 
 int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const double* u, const double* v, double* y,

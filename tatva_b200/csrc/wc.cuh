@@ -54,31 +54,20 @@ __global__ void __launch_bounds__(kBlock, Body::min_ctas) k_fused_wc(const doubl
   if constexpr (SW) {
     if (threadIdx.x < SP) sY[kBlock * SP + threadIdx.x] = 0.0;  // the row the empty table entries point at
   }
-  const int64_t n_tiles = (E + kBlock - 1) / kBlock;
-  // The CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: with a resident grid the INDEX data of the next tile (the
-  // warp's node list, the elements' lane indices, the tile header) is loaded one tile ahead, so only the nodal rows
-  // themselves are an exposed trip to memory.
-  int64_t tile = blockIdx.x;
-  int my_next = -1;
-  unsigned locw_next = 0;
-  int4 hdr_next = make_int4(0, 0, 0, 0);
-  if (tile < n_tiles) {
-    if constexpr (GW) {
-      my_next = __ldg(warp_nodes + (tile * (kBlock / 32) + warp) * 32 + lane);
-      if constexpr (NPE == 4) {
-        const int64_t e = tile * kBlock + threadIdx.x;
-        locw_next = e < E ? __ldg(reinterpret_cast<const unsigned*>(warp_local) + e) : 0u;
-      }
-    }
-    if constexpr (SW) hdr_next = __ldg(tile_hdr + tile);
-  }
-#pragma unroll 1
-  for (; tile < n_tiles; tile += gridDim.x) {
+  // One CTA per tile.  (A resident grid walking the tiles with the next tile's index data prefetched was measured slower,
+  // 0.049-0.050 vs 0.045-0.047 ms at config 2: the prefetched registers spill and a spill store waits for its load.)
+  {
+    const int64_t tile = blockIdx.x;
     const int64_t e = tile * kBlock + threadIdx.x;
     const bool valid = e < E;
-    const int my = my_next;
-    const unsigned locw = locw_next;
-    const int4 hdr = hdr_next;  // {first chunk, chunks, first table entry, table entries}
+    int4 hdr = make_int4(0, 0, 0, 0);  // {first chunk, chunks, first table entry, table entries}
+    if constexpr (SW) hdr = __ldg(tile_hdr + tile);
+    int my = -1;
+    unsigned locw = 0;
+    if constexpr (GW) {
+      my = __ldg(warp_nodes + (tile * (kBlock / 32) + warp) * 32 + lane);
+      if constexpr (NPE == 4) locw = valid ? __ldg(reinterpret_cast<const unsigned*>(warp_local) + e) : 0u;
+    }
     // -- scatter table of the tile: on its way into shared memory while the elements compute
     const int ch0 = hdr.x, ch1 = hdr.x + hdr.y, ebase = hdr.z, ecount = hdr.w;
     int node_first = -1, o0_first = 0, o1_first = 0;
@@ -113,17 +102,6 @@ __global__ void __launch_bounds__(kBlock, Body::min_ctas) k_fused_wc(const doubl
       } else {
 #pragma unroll
         for (int n = 0; n < NPE; ++n) loc[n] = valid ? (int)__ldg(warp_local + e * NPE + n) : 0;
-      }
-      {  // index data of the next tile
-        const int64_t nt = tile + gridDim.x;
-        if (nt < n_tiles) {
-          my_next = __ldg(warp_nodes + (nt * (kBlock / 32) + warp) * 32 + lane);
-          if constexpr (NPE == 4) {
-            const int64_t en = nt * kBlock + threadIdx.x;
-            locw_next = en < E ? __ldg(reinterpret_cast<const unsigned*>(warp_local) + en) : 0u;
-          }
-          if constexpr (SW) hdr_next = __ldg(tile_hdr + nt);
-        }
       }
       bool direct = false;
 #pragma unroll
@@ -160,10 +138,6 @@ __global__ void __launch_bounds__(kBlock, Body::min_ctas) k_fused_wc(const doubl
         gather_rows(coords, nd, X);
         gather_rows(u, nd, U);
         if constexpr (MODE == MODE_HVP) gather_rows(v, nd, V);
-      }
-      if constexpr (SW) {
-        const int64_t nt = tile + gridDim.x;
-        if (nt < n_tiles) hdr_next = __ldg(tile_hdr + nt);
       }
     }
     // -- element arithmetic
@@ -222,7 +196,6 @@ __global__ void __launch_bounds__(kBlock, Body::min_ctas) k_fused_wc(const doubl
         }
         __syncwarp();
       }
-      if (tile + gridDim.x < n_tiles) __syncthreads();  // the next tile overwrites the staging rows and the table
     }
   }
 }
@@ -230,7 +203,7 @@ __global__ void __launch_bounds__(kBlock, Body::min_ctas) k_fused_wc(const doubl
 // The arithmetic of k_fused for one element (any element / law pair): Y += sum_q W (first | second variation) . dN
 template <class El, class Mat>
 struct GenericBody {
-  static constexpr int min_ctas = Mat::dpn > El::dim ? 3 : 4;  // register cap: 168 for the two-field law, 128 otherwise (without it ptxas spends 238 on hoisted loads)
+  static constexpr int min_ctas = Mat::dpn > El::dim ? 3 : 4;  // register caps: 168 for a two-field law, 128 otherwise
   template <int MODE>
   TATVA_D static void run(const Mat& mat, const double (&X)[El::npe][El::dim], const double (&U)[El::npe][Mat::dpn],
                           const double (&V)[El::npe][Mat::dpn], double (&Y)[El::npe][Mat::dpn]) {
@@ -266,29 +239,12 @@ struct GenericBody {
 
 #ifndef __CUDACC_RTC__
 template <class El, class Mat, int MODE, class Body, bool GW = true, bool SW = true>
-static int launch_fused_wc(const tatva_plan* p, const Mat& mat, const double* u, const double* v, double* out, cudaStream_t st,
-                           bool persistent = false) {
+static int launch_fused_wc(const tatva_plan* p, const Mat& mat, const double* u, const double* v, double* out, cudaStream_t st) {
   constexpr size_t smem = wc_smem_bytes<El::npe, Mat::dpn, SW>();
   static_assert(smem <= 48 * 1024, "tile staging exceeds the default shared-memory window");
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
-  int grid = grid_for(p->n_elems);
-  if (persistent) {  // resident grid: as many CTAs as the device holds at once (queried once per device)
-    static int cache[64];
-    int dev = 0;
-    TATVA_CUDA_TRY(cudaGetDevice(&dev));
-    const bool tracked = dev >= 0 && dev < 64;
-    int g = tracked ? cache[dev] : 0;
-    if (g == 0) {
-      int sms = 0, per_sm = 0;
-      TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      TATVA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_wc<El, Mat, MODE, Body, GW, SW>, kBlock, smem));
-      g = sms * (per_sm > 0 ? per_sm : 1);
-      if (tracked) cache[dev] = g;
-    }
-    if (g < grid) grid = g;
-  }
-  k_fused_wc<El, Mat, MODE, Body, GW, SW><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, p->ws_warp_nodes, p->ws_warp_local,
-                                                                     reinterpret_cast<const int4*>(p->ws_tile_hdr), p->ws_tn_node, p->ws_ell_ptr, p->ws_ell);
+  k_fused_wc<El, Mat, MODE, Body, GW, SW><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, p->ws_warp_nodes, p->ws_warp_local,
+                                                                                     reinterpret_cast<const int4*>(p->ws_tile_hdr), p->ws_tn_node, p->ws_ell_ptr, p->ws_ell);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

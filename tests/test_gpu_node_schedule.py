@@ -33,7 +33,7 @@ def test_node_schedule_kernels_match_the_oracle(kind, n, shuffle):
     ref = op.hvp(mat)(u, v).clone()
     op.set_variant(31)
     _assert_close(op.hvp(mat)(u, v), ref.cpu().numpy(), RTOL)
-    for variant in (32, 33, 34, 36, 37):  # A/B variants of the Tet4 kernel: occupancy, element's own gather, per-warp scatter, resident grids
+    for variant in (32, 33, 34):  # A/B variants of the Tet4 kernel: occupancy, element's own gather, per-warp scatter
         op.set_variant(variant)
         _assert_close(op.hvp(mat)(u, v), ref.cpu().numpy(), RTOL)
         _assert_close(op.residual(mat)(u), c_oracle.residual(kind, prm, c, el, u, law), RTOL)
