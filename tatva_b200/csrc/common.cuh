@@ -767,6 +767,8 @@ int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const
 int hex8_nh_hvp_modal_dot(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                           double* dot_partials, cudaStream_t st);
 int hex8_geometry_cache(const tatva_plan* p, double* geo, int64_t stride, cudaStream_t st);
+int hex8_grad_modal(const tatva_plan* p, bool adjoint, const double* in, int nv, double* out, cudaStream_t st);
+int hex8_weights_modal(const tatva_plan* p, double* out, cudaStream_t st);
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st);
 int hex8_nh_energy_modal_partials(const tatva_plan* p, double mu, double lmbda, const double* u, cudaStream_t st);
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st);

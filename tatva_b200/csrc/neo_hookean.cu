@@ -1284,6 +1284,207 @@ __global__ void __launch_bounds__(kBlock, MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Operator.grad and its adjoint on Hex8 in modal form (r02; tatva/operator.py:379-397 -> element/base.py:99-115).
+// The generic building block forms dN/dX = inv(J) dN/dxi (72 fused operations per point), J = dN/dxi X (72) and the
+// gradient sum over the 8 nodes (24 per component) — 2 300 FP64 instructions per element for 3 components, which keeps
+// a 1.27 GB streaming kernel at a third of the HBM roof.  Here, as in the pair kernels above: one Walsh-Hadamard transform
+// per nodal field, reference gradients of a tx pair from the 7 modal coefficients (10 fused operations per field and
+// pair), K = adj(J) / det J once per point, and grad u = (du/dxi) K: ~95 instructions per point.  The raw transforms carry
+// 8 x the reference gradients on both J and du/dxi, which cancels in the product.  Gauss points of pair iteration pq, in
+// the element's point order (kSigns): (-xi, +xi) = (0,1), (3,2), (4,5), (7,6).
+// ---------------------------------------------------------------------------------------------
+TATVA_D void warp_rows_store(double* __restrict__ dst, const double* st, int S, int CH, int count) {
+  const int lane = threadIdx.x & 31;
+  for (int t = lane; t < count * CH; t += 32) {
+    const int j = t / CH;
+    dst[t] = st[j * S + (t - j * CH)];
+  }
+}
+// Full warps take the unrolled path: 8 independent 256-byte loads in flight per warp (the rolled loop has one load in
+// flight at a time, its store waiting on it: a streaming read then runs at the latency, not the bandwidth, of HBM).
+template <int CH>
+TATVA_D void warp_rows_load(const double* __restrict__ src, double* st, int S, int count) {
+  const int lane = threadIdx.x & 31;
+  if (count == 32) {
+#pragma unroll 8
+    for (int i = 0; i < CH; ++i) {
+      const int t = lane + 32 * i, j = t / CH;
+      st[j * S + (t - j * CH)] = __ldcs(src + t);
+    }
+    return;
+  }
+  for (int t = lane; t < count * CH; t += 32) {
+    const int j = t / CH;
+    st[j * S + (t - j * CH)] = __ldg(src + t);
+  }
+}
+
+// K = J^-1 (J[d][c] = dX_c / dxi_d, raw scaling) : K[j][d]
+TATVA_D void inverse_of(const double (&J)[3][3], double (&K)[3][3]) {
+  double det;
+  adjugate(J, K, det);
+  const double r = fast_rcp(det);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) K[a][b] *= r;
+}
+
+// Operator.get_integration_weights on Hex8 (tatva/operator.py:172-192): W[e][q] = det J(xi_q) (all weights are 1), from
+// the modal coordinates; the raw transform carries 8 J, so det(8 J) / 512.
+__global__ void __launch_bounds__(kBlock) k_hex8_weights_modal(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                               int64_t E, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * e + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  double hX[3][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double f[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) f[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+    to_modal_raw(f, hX[c]);
+  }
+  double w[8];
+#pragma unroll
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1];
+    const int qm = (pq == 0) ? 0 : (pq == 1) ? 3 : (pq == 2) ? 4 : 7, qp = (pq == 0) ? 1 : (pq == 1) ? 2 : (pq == 2) ? 5 : 6;
+    double Jm[3][3], Jp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double gm[3], gp[3];
+      ref_grad8_pair(hX[c], sy, sz, gm, gp);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Jm[d][c] = gm[d];
+        Jp[d][c] = gp[d];
+      }
+    }
+    w[qm] = (1.0 / 512.0) * (Jm[0][0] * (Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1]) + Jm[0][1] * (Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2]) + Jm[0][2] * (Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0]));
+    w[qp] = (1.0 / 512.0) * (Jp[0][0] * (Jp[1][1] * Jp[2][2] - Jp[1][2] * Jp[2][1]) + Jp[0][1] * (Jp[1][2] * Jp[2][0] - Jp[1][0] * Jp[2][2]) + Jp[0][2] * (Jp[1][0] * Jp[2][1] - Jp[1][1] * Jp[2][0]));
+  }
+  double2* o = reinterpret_cast<double2*>(out + e * 8);  // 64-byte rows of a 256-byte aligned array
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = make_double2(w[2 * k], w[2 * k + 1]);
+}
+
+template <int NV, bool ADJOINT>
+__global__ void __launch_bounds__(kBlock) k_hex8_grad_modal(const double* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                            int64_t E, const double* __restrict__ in, double* __restrict__ out) {
+  // forward: in = u (N, NV), out = grad (E, 8, NV, 3);  adjoint: in = g (E, 8, NV, 3), out = y (N, NV), accumulated
+  extern __shared__ double sm[];
+  constexpr int CH = 8 * NV * 3, S = CH | 1;
+  const int lane = threadIdx.x & 31;
+  double* st = sm + (size_t)(threadIdx.x >> 5) * 32 * S;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = e - lane;
+  if constexpr (ADJOINT) {
+    if (e0 < E) warp_rows_load<CH>(in + e0 * CH, st, S, (int)min((int64_t)32, E - e0));
+    __syncwarp();
+  }
+  const bool valid = e < E;
+  const int64_t ee = valid ? e : E - 1;
+  int nd[8];
+  {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * ee);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(conn) + 2 * ee + 1);
+    nd[0] = t0.x; nd[1] = t0.y; nd[2] = t0.z; nd[3] = t0.w;
+    nd[4] = t1.x; nd[5] = t1.y; nd[6] = t1.z; nd[7] = t1.w;
+  }
+  double hX[3][7], hu[NV][7];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double f[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) f[n] = __ldg(coords + (int64_t)nd[n] * 3 + c);
+    to_modal_raw(f, hX[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    if constexpr (ADJOINT) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) hu[c][k] = 0.0;  // modal residuals
+    } else {
+      double f[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) f[n] = __ldg(in + (int64_t)nd[n] * NV + c);
+      to_modal_raw(f, hu[c]);
+    }
+  }
+  double* row = st + lane * S;
+#pragma unroll 1
+  for (int pq = 0; pq < 4; ++pq) {
+    const double sy = kPairSigns[pq][0], sz = kPairSigns[pq][1], syz = kPairSigns[pq][2];
+    const int qm = (pq == 0) ? 0 : (pq == 1) ? 3 : (pq == 2) ? 4 : 7, qp = (pq == 0) ? 1 : (pq == 1) ? 2 : (pq == 2) ? 5 : 6;
+    double Jm[3][3], Jp[3][3], Km[3][3], Kp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double gm[3], gp[3];
+      ref_grad8_pair(hX[c], sy, sz, gm, gp);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Jm[d][c] = gm[d];
+        Jp[d][c] = gp[d];
+      }
+    }
+    inverse_of(Jm, Km);
+    inverse_of(Jp, Kp);
+    const double asz = kA * sz, asy = kA * sy;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      if constexpr (!ADJOINT) {
+        double gm[3], gp[3];
+        ref_grad8_pair(hu[c], sy, sz, gm, gp);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {  // du/dX_j = sum_d K[j][d] du/dxi_d
+          row[(qm * NV + c) * 3 + j] = fma(Km[j][2], gm[2], fma(Km[j][1], gm[1], Km[j][0] * gm[0]));
+          row[(qp * NV + c) * 3 + j] = fma(Kp[j][2], gp[2], fma(Kp[j][1], gp[1], Kp[j][0] * gp[0]));
+        }
+      } else {
+        double Qm[3], Qp[3];  // reference-space fluxes: Q[d] = sum_j g[j] K[j][d]
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          Qm[d] = fma(row[(qm * NV + c) * 3 + 2], Km[2][d], fma(row[(qm * NV + c) * 3 + 1], Km[1][d], row[(qm * NV + c) * 3] * Km[0][d]));
+          Qp[d] = fma(row[(qp * NV + c) * 3 + 2], Kp[2][d], fma(row[(qp * NV + c) * 3 + 1], Kp[1][d], row[(qp * NV + c) * 3] * Kp[0][d]));
+        }
+        // transpose of ref_grad8_pair (accumulate_pair, one component)
+        const double S0 = Qp[0] + Qm[0], S1 = Qp[1] + Qm[1], S2 = Qp[2] + Qm[2];
+        const double D1 = Qp[1] - Qm[1], D2 = Qp[2] - Qm[2];
+        hu[c][0] += S0;
+        hu[c][1] += S1;
+        hu[c][2] += S2;
+        hu[c][3] = fma(sy, S0, fma(kA, D1, hu[c][3]));
+        hu[c][4] = fma(sz, S1, fma(sy, S2, hu[c][4]));
+        hu[c][5] = fma(sz, S0, fma(kA, D2, hu[c][5]));
+        hu[c][6] = fma(syz, S0, fma(asz, D1, fma(asy, D2, hu[c][6])));
+      }
+    }
+  }
+  if constexpr (!ADJOINT) {
+    __syncwarp();
+    if (e0 < E) warp_rows_store(out + e0 * CH, st, S, CH, (int)min((int64_t)32, E - e0));
+  } else {
+    __syncwarp();  // every lane is done with its staged g: the buffer becomes the scatter staging
+    double Y[8][NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      double f[8];
+      from_modal_raw(hu[c], f);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) Y[n][c] = f[n];
+    }
+    grouped_scatter<8, NV>(out, nd, Y, valid, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // v4: the v3 arithmetic in a PERSISTENT kernel that hides the gather and scatter phases.
 // ncu (profiles/r02_hvp_ncu_stalls.md): a v3 warp spends 29 % of its life in the gather / modal-transform prologue (41 %
 // of that waiting on the dependent connectivity -> nodal-row round trips to L2 / HBM) and 9 % in the scatter epilogue
@@ -2215,6 +2416,39 @@ static int launch_geo(const tatva_plan* p, double mu, double lmbda, const double
   k_hex8_nh_hvp_geo<MINB, STAGE, PF><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y,
                                                                              reinterpret_cast<const double2*>(p->geo), p->geo_stride);
   return TATVA_OK;
+}
+
+template <int NV, bool ADJOINT>
+static int launch_grad_modal(const tatva_plan* p, const double* in, double* out, cudaStream_t st) {
+  constexpr int CH = 8 * NV * 3, S = CH | 1;
+  constexpr size_t stage = (size_t)32 * S, scat = (size_t)grouped_scatter_words<8, NV>();
+  constexpr size_t smem = (size_t)(kBlock / 32) * (ADJOINT && scat > stage ? scat : stage) * sizeof(double);
+  static SmemOptIn configured;
+  if (smem > 48 * 1024) {
+    const int rc = opt_in_smem(k_hex8_grad_modal<NV, ADJOINT>, smem, configured);
+    if (rc != TATVA_OK) return rc;
+  }
+  k_hex8_grad_modal<NV, ADJOINT><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, in, out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+int hex8_weights_modal(const tatva_plan* p, double* out, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(out) & 15) return TATVA_E_UNSUPPORTED;  // the caller falls back to the generic kernel
+  k_hex8_weights_modal<<<grid_for(p->n_elems), kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, out);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
+// Operator.grad (adjoint = false: u (N, nv) -> (E, 8, nv, 3)) and its adjoint (g -> y (N, nv), accumulated into y) for
+// nv <= 3; TATVA_E_UNSUPPORTED otherwise (the caller falls back to the generic building block).
+int hex8_grad_modal(const tatva_plan* p, bool adjoint, const double* in, int nv, double* out, cudaStream_t st) {
+  switch (nv) {
+    case 1: return adjoint ? launch_grad_modal<1, true>(p, in, out, st) : launch_grad_modal<1, false>(p, in, out, st);
+    case 2: return adjoint ? launch_grad_modal<2, true>(p, in, out, st) : launch_grad_modal<2, false>(p, in, out, st);
+    case 3: return adjoint ? launch_grad_modal<3, true>(p, in, out, st) : launch_grad_modal<3, false>(p, in, out, st);
+    default: return TATVA_E_UNSUPPORTED;
+  }
 }
 
 int hex8_geometry_cache(const tatva_plan* p, double* geo, int64_t stride, cudaStream_t st) {
