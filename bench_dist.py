@@ -82,7 +82,7 @@ class DistributedHex8Problem:
             self.n_dofs_global = 3 * c.shape[0]
             self.partition_desc = "1 GPU, whole mesh"
             n_owned = u.size
-            self.launches_per_step = 1
+            self.launches_per_step = 2  # k_zero_release (clears y, releases its dependent at once) + the element kernel
         elif world == 1:
             c, el, u, v = synthetic_inputs(n, rank)
             self.op = tatva_b200.Operator(tatva_b200.Mesh(coords=c, elements=el), element.Hexahedron8(), device=device)
@@ -90,7 +90,7 @@ class DistributedHex8Problem:
             self.n_dofs_global = 3 * c.shape[0]
             self.partition_desc = "1 GPU, whole mesh"
             n_owned = u.size
-            self.launches_per_step = 1
+            self.launches_per_step = 2  # k_zero_release (clears y, releases its dependent at once) + the element kernel
         else:
             grid = grid or GRID[world]
             mesh, info = structured_hex_block(n, grid, rank)

@@ -436,6 +436,33 @@ __global__ void __launch_bounds__(256) k_gather(const int32_t* __restrict__ conn
   out[i] = __ldg(u + (int64_t)__ldg(conn + en) * nv + c);
 }
 
+// Four outputs per thread (stride 256: every store instruction still writes 2 KB contiguous per CTA), index arithmetic in
+// 32 bits with a compile-time divisor for nv <= 4: the connectivity loads of the four go out together, then the four row
+// loads — the one-output-per-thread kernel above holds one dependent load chain per thread and a 64-bit division.
+template <int NVT>
+__global__ void __launch_bounds__(256) k_gather4(const int32_t* __restrict__ conn, uint32_t total, int nv_rt,
+                                                 const double* __restrict__ u, double* __restrict__ out) {
+  const uint32_t nv = NVT ? (uint32_t)NVT : (uint32_t)nv_rt;
+  const uint32_t base = blockIdx.x * 1024u + threadIdx.x;
+  uint32_t en[4], c[4];
+  int node[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = base + 256u * k;
+    en[k] = i / nv;
+    c[k] = i - en[k] * nv;
+    node[k] = i < total ? __ldg(conn + en[k]) : 0;
+  }
+  double val[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) val[k] = __ldg(u + (int64_t)node[k] * nv + c[k]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = base + 256u * k;
+    if (i < total) __stcs(out + i, val[k]);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_gather_adjoint(const int32_t* __restrict__ conn, int64_t total, int nv,
                                                         const double* __restrict__ g, double* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,6 +470,25 @@ __global__ void __launch_bounds__(256) k_gather_adjoint(const int32_t* __restric
   const int64_t en = i / nv;
   const int c = (int)(i - en * nv);
   atomicAdd(y + (int64_t)__ldg(conn + en) * nv + c, __ldg(g + i));
+}
+template <int NVT>
+__global__ void __launch_bounds__(256) k_gather_adjoint4(const int32_t* __restrict__ conn, uint32_t total, int nv_rt,
+                                                         const double* __restrict__ g, double* __restrict__ y) {
+  const uint32_t nv = NVT ? (uint32_t)NVT : (uint32_t)nv_rt;
+  const uint32_t base = blockIdx.x * 1024u + threadIdx.x;
+  uint32_t c[4];
+  int node[4];
+  double val[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = base + 256u * k, en = i / nv;
+    c[k] = i - en * nv;
+    node[k] = i < total ? __ldg(conn + en) : -1;
+    val[k] = i < total ? __ldcs(g + i) : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (node[k] >= 0) atomicAdd(y + (int64_t)node[k] * nv + c[k], val[k]);
 }
 
 // partial[b*nv + c] = sum over rows of chunk b; rows strided by blockDim
@@ -1899,6 +1945,19 @@ int tatva_op_interpolate(const tatva_plan_t* p, const double* d_u, int nv, const
 int tatva_op_gather(const tatva_plan_t* p, const double* d_u, int nv, double* d_out, tatva_stream_t stream) {
   if (!p || !d_u || !d_out || nv <= 0) return TATVA_E_INVALID;
   const int64_t total = p->n_elems * p->npe * nv;
+  if (total < (int64_t)0xfffff000 && p->variant == TATVA_VARIANT_DEFAULT) {
+    const int grid = (int)((total + 1023) / 1024);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nv) {
+      case 1: k_gather4<1><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_u, d_out); break;
+      case 2: k_gather4<2><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_u, d_out); break;
+      case 3: k_gather4<3><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_u, d_out); break;
+      case 4: k_gather4<4><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_u, d_out); break;
+      default: k_gather4<0><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_u, d_out); break;
+    }
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   k_gather<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p->conn, total, nv, d_u, d_out);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
@@ -1909,6 +1968,18 @@ int tatva_op_gather_adjoint(const tatva_plan_t* p, const double* d_g, int nv, do
   cudaStream_t st = (cudaStream_t)stream;
   TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * nv, st));
   const int64_t total = p->n_elems * p->npe * nv;
+  if (total < (int64_t)0xfffff000 && p->variant == TATVA_VARIANT_DEFAULT) {
+    const int grid = (int)((total + 1023) / 1024);
+    switch (nv) {
+      case 1: k_gather_adjoint4<1><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_g, d_y); break;
+      case 2: k_gather_adjoint4<2><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_g, d_y); break;
+      case 3: k_gather_adjoint4<3><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_g, d_y); break;
+      case 4: k_gather_adjoint4<4><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_g, d_y); break;
+      default: k_gather_adjoint4<0><<<grid, 256, 0, st>>>(p->conn, (uint32_t)total, nv, d_g, d_y); break;
+    }
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   k_gather_adjoint<<<grid_for(total, 256), 256, 0, st>>>(p->conn, total, nv, d_g, d_y);
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;

@@ -1008,6 +1008,9 @@ __global__ void __launch_bounds__(kBlock, MINB)
     nd[0] = a.x; nd[1] = a.y; nd[2] = a.z; nd[3] = a.w;
     nd[4] = b.x; nd[5] = b.y; nd[6] = b.z; nd[7] = b.w;
   }
+  // Programmatic dependent launch: when the launcher overlaps this grid with the kernel that zeroes y (launch_v3 with
+  // pdl = true), everything above ran while y was still being cleared; the scatter must wait for it.  A no-op otherwise.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if constexpr (GROUPED) {
     // sector-grouped scatter: consecutive lanes add the 3 consecutive doubles of one node
     constexpr int NS = STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63);
@@ -2346,15 +2349,51 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_tiled(const double* __restri
 
 }  // namespace
 
+// y = 0 as a KERNEL that releases its dependent grid at once (griddepcontrol.launch_dependents): the element kernel
+// launched behind it with programmatic stream serialization starts its gather / modal transforms / Gauss-point loop while
+// the 51.5 MB are still being cleared, and waits (griddepcontrol.wait) only before its first RED.
+__global__ void __launch_bounds__(256) k_zero_release(double* __restrict__ y, int64_t n) {
+  asm volatile("griddepcontrol.launch_dependents;" ::);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n2 = n >> 1;
+  double2* y2 = reinterpret_cast<double2*>(y);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) y2[i] = make_double2(0.0, 0.0);
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) y[n - 1] = 0.0;
+}
+
 template <int MINB, int STAGE, int GROUPED = 0, int WIDE = 0, int UNR = 1, int CPF = 0, int NDS = 0>
 static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool pdl = false) {
   static_assert(!(NDS && GROUPED), "the grouped scatter has its own staging area");
   constexpr size_t smem = ((size_t)(STAGE == 0 ? 0 : (STAGE == 1 ? 42 : 63)) * kBlock + (GROUPED ? (kBlock / 32) * grouped_scatter_words<8, 3>() : 0)) * sizeof(double) + (NDS ? 2 * kBlock * sizeof(int4) : 0);
   static SmemOptIn configured;
   if (smem > 48 * 1024) {
     const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, smem, configured);
     if (rc != TATVA_OK) return rc;
+  }
+  if (pdl) {
+    // zero y with our own kernel and let the element kernel start behind it without waiting for it to finish
+    const int64_t n = p->n_nodes * 3;
+    if (reinterpret_cast<uintptr_t>(y) & 15) return TATVA_E_INVALID;
+    int dev = 0, sms = 148;
+    TATVA_CUDA_TRY(cudaGetDevice(&dev));
+    TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    k_zero_release<<<sms * 2, 256, 0, st>>>(y, n);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid_for(p->n_elems));
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
+    const int32_t* no_map = nullptr;
+    double* no_dot = nullptr;
+    TATVA_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, p->coords, p->conn, p->n_elems, mu_s, lm_s, u, v, y, no_map, no_dot));
+    return TATVA_OK;
   }
   k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y);
   return TATVA_OK;
@@ -2459,6 +2498,14 @@ int hex8_geometry_cache(const tatva_plan* p, double* geo, int64_t stride, cudaSt
 
 int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                       cudaStream_t st) {
+  // default (variant 0) with a zeroed output: the clearing of y overlaps the element kernel's gather and Gauss-point loop
+  // (programmatic dependent launch); variant 26 is the same kernel behind a plain cudaMemsetAsync
+  if (p->zero_output && p->variant == 0 && !p->geo && !(reinterpret_cast<uintptr_t>(y) & 15)) {
+    const int rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st, true);
+    if (rc != TATVA_OK) return rc;
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   int rc = TATVA_OK;
   if (p->geo && (p->variant == 0 || (p->variant >= 50 && p->variant <= 58))) {
