@@ -661,6 +661,9 @@ TATVA_D void grouped_scatter(double* __restrict__ y, const int (&nd)[NPE], const
     for (int c = 0; c < DPN; ++c) warp_smem[lane * SP + n * DPN + c] = Y[n][c];
   }
   __syncwarp();
+  // the launcher may have put this grid behind the kernel that clears y (launch_behind_zero): everything up to here ran
+  // while y was being cleared; the adds must wait for it.  A no-op for a normally launched grid.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int t = lane; t < 32 * S; t += 32) {
     const int j = t / S, r = t - j * S;
     const int node = snode[j * NP + r / DPN];
@@ -750,6 +753,52 @@ inline int grid_for(int64_t n, int block = kBlock) { return (int)((n + block - 1
     cudaError_t _e = cudaPeekAtLastError(); \
     if (_e != cudaSuccess) return (int)_e;  \
   } while (0)
+
+// y = 0 as a KERNEL that releases its dependent grid at once (griddepcontrol.launch_dependents): the element kernel
+// launched behind it with programmatic stream serialization runs its gather and arithmetic while y is still being cleared
+// and waits (griddepcontrol.wait) only before its first atomic add.  XLA does not zero results, so every scatter-add entry
+// point clears its output; as a memset in front of the kernel that was 1-3 % of a Hex8 step and up to 15 % of a
+// launch-sized one (Tri3 config 1).
+static __global__ void __launch_bounds__(256) k_zero_release(double* __restrict__ y, int64_t n) {
+#ifdef __CUDA_ARCH__
+  asm volatile("griddepcontrol.launch_dependents;" ::);
+#endif
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n2 = n >> 1;
+  double2* y2 = reinterpret_cast<double2*>(y);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) y2[i] = make_double2(0.0, 0.0);
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) y[n - 1] = 0.0;
+}
+
+// Clear y[0..n) (when `zero`) and launch `kernel` behind it; the kernel must execute griddepcontrol.wait before it touches y.
+template <class... KArgs, class... Args>
+inline int launch_behind_zero(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool zero, double* y,
+                              int64_t n, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (zero && n > 0) {
+    if (reinterpret_cast<uintptr_t>(y) & 15) {  // not 16-byte aligned (a view into a larger array): plain memset, plain launch
+      TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * n, st));
+    } else {
+      int64_t blocks = (n / 2 + 256 * 8 - 1) / (256 * 8);  // <= 8 double2 stores per thread, at most two CTAs per SM
+      if (blocks > 296) blocks = 296;
+      if (blocks < 1) blocks = 1;
+      k_zero_release<<<(int)blocks, 256, 0, st>>>(y, n);
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.numAttrs = 1;
+    }
+  }
+  TATVA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+  return TATVA_OK;
+}
+
 
 // user-supplied laws compiled at run time (user_law.cu); material ids >= TATVA_USER_LAW_BASE
 bool is_user_law(int material);

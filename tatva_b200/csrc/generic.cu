@@ -2015,10 +2015,12 @@ static int launch_fused(tatva_plan* p, const Mat& mat, const double* u, const do
     k_fused<El, Mat, MODE><<<grid, kBlock, 0, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, nullptr, p->scratch);
     k_sum_rows_final<<<1, 256, 0, st>>>(p->scratch, grid, 1, out);
   } else {
-    if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
     constexpr size_t smem = grouped_scatter_smem<El::npe, Mat::dpn>(kBlock / 32);
     static_assert(smem <= 48 * 1024, "grouped scatter staging exceeds the default shared-memory window");
-    k_fused<El, Mat, MODE><<<grid, kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, nullptr);
+    // y is cleared under the kernel: grouped_scatter waits (griddepcontrol.wait) before its first atomic add
+    const int rc = launch_behind_zero(k_fused<El, Mat, MODE>, grid, kBlock, smem, st, p->zero_output != 0, out, p->n_nodes * Mat::dpn,
+                                      p->coords, p->conn, p->n_elems, mat, u, v, out, nullptr);
+    if (rc != TATVA_OK) return rc;
   }
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;

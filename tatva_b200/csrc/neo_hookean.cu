@@ -2163,6 +2163,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
     point_flux_residual(Jp, Frp, mu_s, lm_s, Qp);
     accumulate_pair(Qm, Qp, sy, sz, syz, R);
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // y may still be being cleared (launch_behind_zero)
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     double f[8];
@@ -2349,18 +2350,6 @@ __global__ void __launch_bounds__(kBlock) k_tet4_nh_tiled(const double* __restri
 
 }  // namespace
 
-// y = 0 as a KERNEL that releases its dependent grid at once (griddepcontrol.launch_dependents): the element kernel
-// launched behind it with programmatic stream serialization starts its gather / modal transforms / Gauss-point loop while
-// the 51.5 MB are still being cleared, and waits (griddepcontrol.wait) only before its first RED.
-__global__ void __launch_bounds__(256) k_zero_release(double* __restrict__ y, int64_t n) {
-  asm volatile("griddepcontrol.launch_dependents;" ::);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n2 = n >> 1;
-  double2* y2 = reinterpret_cast<double2*>(y);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) y2[i] = make_double2(0.0, 0.0);
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) y[n - 1] = 0.0;
-}
-
 template <int MINB, int STAGE, int GROUPED = 0, int WIDE = 0, int UNR = 1, int CPF = 0, int NDS = 0>
 static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y,
                      cudaStream_t st, bool pdl = false) {
@@ -2371,30 +2360,9 @@ static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double*
     const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, smem, configured);
     if (rc != TATVA_OK) return rc;
   }
-  if (pdl) {
-    // zero y with our own kernel and let the element kernel start behind it without waiting for it to finish
-    const int64_t n = p->n_nodes * 3;
-    if (reinterpret_cast<uintptr_t>(y) & 15) return TATVA_E_INVALID;
-    int dev = 0, sms = 148;
-    TATVA_CUDA_TRY(cudaGetDevice(&dev));
-    TATVA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    k_zero_release<<<sms * 2, 256, 0, st>>>(y, n);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid_for(p->n_elems));
-    cfg.blockDim = dim3(kBlock);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const double mu_s = mu * (1.0 / 512.0), lm_s = lmbda * (1.0 / 512.0);
-    const int32_t* no_map = nullptr;
-    double* no_dot = nullptr;
-    TATVA_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, p->coords, p->conn, p->n_elems, mu_s, lm_s, u, v, y, no_map, no_dot));
-    return TATVA_OK;
-  }
+  if (pdl)  // clear y with our own kernel and let the element kernel start behind it without waiting for it to finish
+    return launch_behind_zero(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, grid_for(p->n_elems), kBlock, smem, st, true, y, p->n_nodes * 3,
+                              p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y, nullptr, nullptr);
   k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y);
   return TATVA_OK;
 }
@@ -2500,7 +2468,7 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
                       cudaStream_t st) {
   // default (variant 0) with a zeroed output: the clearing of y overlaps the element kernel's gather and Gauss-point loop
   // (programmatic dependent launch); variant 26 is the same kernel behind a plain cudaMemsetAsync
-  if (p->zero_output && p->variant == 0 && !p->geo && !(reinterpret_cast<uintptr_t>(y) & 15)) {
+  if (p->zero_output && p->variant == 0 && !p->geo) {
     const int rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st, true);
     if (rc != TATVA_OK) return rc;
     TATVA_LAUNCH_CHECK();
@@ -2602,6 +2570,13 @@ int hex8_nh_hvp_modal_lifted(const tatva_plan* p, double mu, double lmbda, const
 }
 
 int hex8_nh_residual_modal(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
+  if (p->variant == 0) {  // default: y cleared under the kernel (launch_behind_zero)
+    const int rc = launch_behind_zero(k_hex8_nh_residual_v3<2, 0>, grid_for(p->n_elems), kBlock, 0, st, p->zero_output != 0, y, p->n_nodes * 3,
+                                      p->coords, p->conn, p->n_elems, mu, lmbda, u, y);
+    if (rc != TATVA_OK) return rc;
+    TATVA_LAUNCH_CHECK();
+    return TATVA_OK;
+  }
   if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
   // variants (tatva_plan_set_variant), r01 at 128^3: 2 = first modal kernel, 8 rolled points (0.422 ms); 3 = pair
   // kernel, all in registers (0.382); 4 = pair kernel, modal coordinates staged, 2 CTAs / SM (0.394);
@@ -2645,16 +2620,24 @@ static int tet4_nh_pipe(const tatva_plan* p, bool hvp, double mu, double lmbda, 
 }
 
 int tet4_nh_hvp_ref(const tatva_plan* p, double mu, double lmbda, const double* u, const double* v, double* y, cudaStream_t st) {
-  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
-  if (p->variant == 30) return tet4_nh_pipe(p, true, mu, lmbda, u, v, y, st);
-  k_tet4_nh_ref<true><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  if (p->variant == 30) {
+    if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+    return tet4_nh_pipe(p, true, mu, lmbda, u, v, y, st);
+  }
+  const int rc = launch_behind_zero(k_tet4_nh_ref<true>, grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st, p->zero_output != 0, y, p->n_nodes * 3,
+                                    p->coords, p->conn, p->n_elems, mu, lmbda, u, v, y);
+  if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
 int tet4_nh_residual_ref(const tatva_plan* p, double mu, double lmbda, const double* u, double* y, cudaStream_t st) {
-  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
-  if (p->variant == 30) return tet4_nh_pipe(p, false, mu, lmbda, u, nullptr, y, st);
-  k_tet4_nh_ref<false><<<grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st>>>(p->coords, p->conn, p->n_elems, mu, lmbda, u, nullptr, y);
+  if (p->variant == 30) {
+    if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * p->n_nodes * 3, st));
+    return tet4_nh_pipe(p, false, mu, lmbda, u, nullptr, y, st);
+  }
+  const int rc = launch_behind_zero(k_tet4_nh_ref<false>, grid_for(p->n_elems), kBlock, grouped_scatter_smem<4, 3>(kBlock / 32), st, p->zero_output != 0, y, p->n_nodes * 3,
+                                    p->coords, p->conn, p->n_elems, mu, lmbda, u, nullptr, y);
+  if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }

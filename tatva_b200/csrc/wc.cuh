@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(kBlock, Body::min_ctas) k_fused_wc(const doubl
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncthreads();
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // y may still be being cleared (launch_behind_zero)
       const bool staged = ecount <= kWcEllStage;
       for (int ch = ch0 + warp; ch < ch1; ch += kBlock / 32) {
         int node = node_first, o0 = o0_first, o1 = o1_first;
@@ -242,9 +243,10 @@ template <class El, class Mat, int MODE, class Body, bool GW = true, bool SW = t
 static int launch_fused_wc(const tatva_plan* p, const Mat& mat, const double* u, const double* v, double* out, cudaStream_t st) {
   constexpr size_t smem = wc_smem_bytes<El::npe, Mat::dpn, SW>();
   static_assert(smem <= 48 * 1024, "tile staging exceeds the default shared-memory window");
-  if (p->zero_output) TATVA_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * p->n_nodes * Mat::dpn, st));
-  k_fused_wc<El, Mat, MODE, Body, GW, SW><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mat, u, v, out, p->ws_warp_nodes, p->ws_warp_local,
-                                                                                     reinterpret_cast<const int4*>(p->ws_tile_hdr), p->ws_tn_node, p->ws_ell_ptr, p->ws_ell);
+  const int rc = launch_behind_zero(k_fused_wc<El, Mat, MODE, Body, GW, SW>, grid_for(p->n_elems), kBlock, smem, st, p->zero_output != 0, out, p->n_nodes * Mat::dpn,
+                                    p->coords, p->conn, p->n_elems, mat, u, v, out, p->ws_warp_nodes, p->ws_warp_local, reinterpret_cast<const int4*>(p->ws_tile_hdr),
+                                    p->ws_tn_node, p->ws_ell_ptr, p->ws_ell);
+  if (rc != TATVA_OK) return rc;
   TATVA_LAUNCH_CHECK();
   return TATVA_OK;
 }
