@@ -144,3 +144,24 @@ def test_hex8_geometry_cache_variants_vs_c_oracle(n):
     _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), 0, cut, 1, st), "tatva_hvp_elems")
     _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), cut, E - cut, 0, st), "tatva_hvp_elems")
     _assert_close(y, ref, RTOL)
+
+
+@pytest.mark.parametrize("kind,n", [("hex8", 7), ("tet4", 9), ("tri3", 33)])
+def test_output_views_at_an_8_byte_offset_take_the_plain_memset(kind, n):
+    """The fused launches clear y with a kernel that stores 16 bytes at a time and start the element kernel behind it
+    (launch_behind_zero); an output that is only 8-byte aligned (a view into a larger array) must fall back to the plain
+    memset and give the same result, as must an output that already holds garbage."""
+    c, el, u, v, (mname, omat) = _case(kind, n)
+    op = _make_op(kind, c, el)
+    mat = _material(mname, omat)
+    ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
+    ref = op._raw_hvp(mat, ut, vt).clone()
+    buf = torch.full((ut.numel() + 1,), 7.0, dtype=torch.float64, device="cuda")
+    y = buf[1:].view_as(ut)
+    assert y.data_ptr() % 16 == 8
+    op._raw_hvp(mat, ut, vt, out=y)
+    assert torch.equal(buf[:1].cpu(), torch.full((1,), 7.0, dtype=torch.float64))
+    _assert_close(y, ref.cpu().numpy(), 1e-14)
+    y2 = torch.full_like(ut, float("nan"))
+    op._raw_hvp(mat, ut, vt, out=y2)
+    _assert_close(y2, ref.cpu().numpy(), 1e-14)
