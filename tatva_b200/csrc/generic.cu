@@ -2060,7 +2060,13 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
         if (el == TATVA_TET4) return launch_fused_wc<Tet4, LinearElastic<3>, MODE, GenericBody<Tet4, LinearElastic<3>>>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
       } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
         if (el == TATVA_TET4) return tet4_nh_wc(p, MODE == MODE_HVP, prm[0], prm[1], u, v, out, st);
-      }  // the two-field law keeps the element-per-thread kernel: its 32-byte nodal rows are sector-exact and the tile sums do not pay (measured)
+      } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5 && el == TATVA_TET4 && (p->variant == 38 || p->variant == 39)) {
+        // A/B for the two-field law (32-byte nodal rows: the element's own gather is sector-exact): 38 = own gather + tile sums,
+        // 39 = shuffle gather + tile sums
+        const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
+        if (p->variant == 38) return launch_fused_wc<Tet4, NeoHookeanPhaseField, MODE, GenericBody<Tet4, NeoHookeanPhaseField>, false, true>(p, m, u, v, out, st);
+        return launch_fused_wc<Tet4, NeoHookeanPhaseField, MODE, GenericBody<Tet4, NeoHookeanPhaseField>, true, true>(p, m, u, v, out, st);
+      }
     }
   }
   if (material == TATVA_LINEAR_ELASTIC) {
