@@ -2060,9 +2060,9 @@ static int dispatch_fused(tatva_plan* p, int material, const double* prm, int n_
         if (el == TATVA_TET4) return launch_fused_wc<Tet4, LinearElastic<3>, MODE, GenericBody<Tet4, LinearElastic<3>>>(p, LinearElastic<3>{prm[0], prm[1]}, u, v, out, st);
       } else if (material == TATVA_NEO_HOOKEAN && n_params == 2) {
         if (el == TATVA_TET4) return tet4_nh_wc(p, MODE == MODE_HVP, prm[0], prm[1], u, v, out, st);
-      } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5 && el == TATVA_TET4 && (p->variant == 38 || p->variant == 39)) {
-        // A/B for the two-field law (32-byte nodal rows: the element's own gather is sector-exact): 38 = own gather + tile sums,
-        // 39 = shuffle gather + tile sums
+      } else if (material == TATVA_NEO_HOOKEAN_PHASE_FIELD && n_params == 5 && el == TATVA_TET4) {
+        // two-field law (32-byte nodal rows): shuffle gather + tile sums 0.0678 -> 0.0630 ms (HVP), 0.0475 -> 0.0453 (residual)
+        // at config 5; variant 38 = the element's own gather + tile sums (no gain: 0.0678 / 0.0514)
         const NeoHookeanPhaseField m{prm[0], prm[1], prm[2], prm[3], prm[4]};
         if (p->variant == 38) return launch_fused_wc<Tet4, NeoHookeanPhaseField, MODE, GenericBody<Tet4, NeoHookeanPhaseField>, false, true>(p, m, u, v, out, st);
         return launch_fused_wc<Tet4, NeoHookeanPhaseField, MODE, GenericBody<Tet4, NeoHookeanPhaseField>, true, true>(p, m, u, v, out, st);
@@ -2344,6 +2344,21 @@ extern "C" int tatva_probe_element(int element, int material, const double* para
   });
 }
 
+// A sub-range that starts on a tile boundary (a multiple of 128 elements) sees the node schedule through offset views —
+// the per-warp lists and per-tile headers are indexed by tile, the chunk and table arrays through the headers' absolute
+// positions; a ragged END is fine (elements past it contribute zero rows).  Any other start drops the schedule.
+static void sub_range_node_schedule(tatva_plan& sub, int64_t elem_begin) {
+  if (!sub.ws_warp_nodes) return;
+  if (elem_begin % 128 != 0) {
+    sub.ws_warp_nodes = nullptr;
+    return;
+  }
+  const int64_t tile0 = elem_begin / 128;
+  sub.ws_warp_nodes += tile0 * 128;
+  sub.ws_warp_local += elem_begin * sub.npe;
+  sub.ws_tile_hdr += tile0 * 4;
+}
+
 extern "C" {
 // Element sub-range variants (overlap of halo exchange with interior elements): elements
 // [elem_begin, elem_begin + elem_count) only; y is zeroed first iff zero_y != 0.
@@ -2363,8 +2378,8 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
   sub.conn = p->conn + elem_begin * p->npe;
   sub.n_elems = elem_count;
   sub.zero_output = zero_y ? 1 : 0;
-  sub.tile_ptr = nullptr;  // tiles and node schedules describe the whole element list, not a sub-range
-  sub.ws_warp_nodes = nullptr;
+  sub.tile_ptr = nullptr;  // staging tiles describe the whole element list, not a sub-range
+  sub_range_node_schedule(sub, elem_begin);
   if (sub.geo) sub.geo += 2 * elem_begin;  // the cache is element-fastest: a sub-range is an offset view (same stride)
   return dispatch_fused<MODE_HVP>(&sub, material, params, n_params, d_u, d_v, d_y, (cudaStream_t)stream);
 }
@@ -2384,7 +2399,7 @@ int tatva_residual_elems(tatva_plan_t* p, int material, const double* params, in
   sub.n_elems = elem_count;
   sub.zero_output = zero_r ? 1 : 0;
   sub.tile_ptr = nullptr;
-  sub.ws_warp_nodes = nullptr;
+  sub_range_node_schedule(sub, elem_begin);
   return dispatch_fused<MODE_RESIDUAL>(&sub, material, params, n_params, d_u, nullptr, d_r, (cudaStream_t)stream);
 }
 }  // extern "C"

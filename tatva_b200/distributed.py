@@ -243,7 +243,10 @@ class PartitionedOperator:
         return g
 
     def _apply_eager(self, name, u_local, v_local, y_local):
-        E, nb = self.op.n_elements, self.n_boundary
+        E = self.op.n_elements
+        # the boundary launch is rounded up to whole 128-element tiles (a few interior elements ride along): both element
+        # ranges then start on a tile boundary and keep the plan's node schedule (tatva_hvp_elems)
+        nb = min(E, -(-self.n_boundary // 128) * 128)
         if self.comm.size == 1:
             self._elems(name, u_local, v_local, y_local, 0, E, 1)
             return y_local

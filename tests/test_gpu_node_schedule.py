@@ -51,6 +51,28 @@ def test_node_schedule_tet4_linear_elastic_and_contributor_caps(cap):
     _assert_close(op.residual(mat)(u), op0.residual(mat)(u).cpu().numpy(), RTOL)
 
 
+def test_node_schedule_compound_phase_field_config5():
+    """Config 5 at its parity size (n = 55): node-interleaved [ux, uy, uz, phi]; the default two-field kernel is the
+    node-schedule one (shuffle gather + tile sums), variant 38 keeps the element's own gather, 31 is element-per-thread."""
+    from tatva_b200 import materials
+
+    rng = np.random.default_rng(1)
+    c, el, u, _, _ = _case("tet4", 55)
+    prm = (500.0, 1000.0, 2.7, 0.1, 1e-6)
+    mat = materials.NeoHookeanPhaseField(*prm)
+    op = _make_op("tet4", c, el)
+    assert op._node_schedule is not None
+    phi = 0.4 + 0.4 * np.sin(2 * np.pi * c[:, 0]) * np.cos(2 * np.pi * c[:, 1])
+    s = np.concatenate([u, phi[:, None]], axis=1)
+    t = rng.normal(size=s.shape)
+    arr, tt = torch.as_tensor(s.ravel(), device="cuda"), torch.as_tensor(t.ravel(), device="cuda")
+    ref_r, ref_h = c_oracle.residual_pf("tet4", prm, c, el, s), c_oracle.hvp_pf("tet4", prm, c, el, s, t)
+    for variant in (0, 38, 31):
+        op.set_variant(variant)
+        _assert_close(op.residual(mat)(arr).reshape(-1, 4), ref_r, RTOL)
+        _assert_close(op.hvp(mat)(arr, tt).reshape(-1, 4), ref_h, RTOL)
+
+
 def test_node_schedule_config2_and_config1_sizes():
     for kind, n, law in (("tet4", 55, "neo_hookean"), ("tri3", 256, "linear_elastic")):
         c, el, u, v, (mname, omat) = _case(kind, n)
@@ -73,3 +95,34 @@ def test_node_schedule_auto_keeps_it_only_with_locality():
     _assert_close(op.hvp(mat)(u, v), c_oracle.hvp("tet4", (omat.mu, omat.lmbda), c, el2, u, v, "neo_hookean"), RTOL)
     ch, eh, *_ = _case("hex8", 4)
     assert _make_op("hex8", ch, eh)._node_schedule is None
+
+
+@pytest.mark.parametrize("law", ["nh", "pf"])
+def test_element_sub_ranges_keep_the_schedule_on_tile_boundaries(law):
+    """tatva_hvp_elems / tatva_residual_elems (what the partitioned operator launches): a range that starts on a multiple
+    of 128 elements runs the node-schedule kernel through offset views (ragged end included), any other start falls back
+    to the element-per-thread kernel; the pieces accumulate to the full result either way."""
+    from tatva_b200 import _lib, materials
+
+    c, el, u, v, (mname, omat) = _case("tet4", 6)  # 1296 elements: 10 full tiles + 16
+    op = _make_op("tet4", c, el, node_schedule=True)
+    if law == "pf":
+        mat = materials.NeoHookeanPhaseField(500.0, 1000.0, 2.7, 0.1, 1e-6)
+        rng = np.random.default_rng(2)
+        u = np.concatenate([u, 0.4 + 0.3 * rng.uniform(size=(len(c), 1))], axis=1)
+        v = rng.normal(size=u.shape)
+    else:
+        mat = _material(mname, omat)
+    ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
+    ref_h, ref_r = op._raw_hvp(mat, ut, vt).clone(), op._raw_residual(mat, ut).clone()
+    prm, npar = _lib.params_array(mat.params())
+    E = el.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    for cuts in ([0, 384, E], [0, 200, 512, 1100, E], [0, 128, 256, E]):
+        y, r = torch.full_like(ut, 3.0), torch.full_like(ut, 3.0)
+        for k in range(len(cuts) - 1):
+            b, n = cuts[k], cuts[k + 1] - cuts[k]
+            _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), b, n, int(k == 0), st), "tatva_hvp_elems")
+            _lib.check(op._L.tatva_residual_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), r.data_ptr(), b, n, int(k == 0), st), "tatva_residual_elems")
+        _assert_close(y, ref_h.cpu().numpy(), RTOL)
+        _assert_close(r, ref_r.cpu().numpy(), RTOL)
