@@ -104,3 +104,38 @@ def test_interpolate_second_order_elements_match_reference(golden, kind):
     elem = torch.empty(allp.shape[0], dtype=torch.int32, device="cuda")
     op._call("tatva_op_interpolate", torch.as_tensor(g("s"), device="cuda").data_ptr(), 1, allp.data_ptr(), allp.shape[0], out.data_ptr(), elem.data_ptr())
     np.testing.assert_array_equal(elem.cpu().numpy(), g("containing"))
+
+
+@pytest.mark.parametrize("kind,n", [("hex8", 5), ("tet4", 4), ("tri3", 9)])
+@pytest.mark.parametrize("nv", [1, 2, 3, 4, 5])
+def test_building_blocks_for_every_component_count(kind, n, nv):
+    """gather (`v[self.mesh.elements]`, tatva/operator.py:221), grad (element/base.py:99-115) and their adjoints for
+    1..5 value components: the compile-time (nv <= 4, Hex8 modal nv <= 3) and the run-time-nv kernels, the plan's generic
+    variants, against NumPy and against each other by the adjoint identity <A x, g> = <x, A^T g>."""
+    from test_gpu_parity import _case, _make_op
+
+    c, el, _, _, _ = _case(kind, n)
+    rng = np.random.default_rng(nv)
+    op = _make_op(kind, c, el)
+    u = rng.normal(size=(c.shape[0], nv))
+    ut = torch.as_tensor(u, device="cuda")
+    G = op._k_gather(ut)
+    assert np.array_equal(G.cpu().numpy(), u[el])
+    g = rng.normal(size=G.shape)
+    ref = np.zeros_like(u)
+    np.add.at(ref, el, g)
+    assert np.allclose(op._k_gather_adj(torch.as_tensor(g, device="cuda")).cpu().numpy(), ref, rtol=1e-13, atol=1e-13)
+    D = op._k_grad(ut)
+    op.set_variant(1)  # generic kernels
+    D1 = op._k_grad(ut)
+    assert np.array_equal(op._k_gather(ut).cpu().numpy(), u[el])
+    op.set_variant(0)
+    assert float((D - D1).abs().max()) <= 1e-12 * float(D1.abs().max())
+    gd = torch.as_tensor(rng.normal(size=tuple(D.shape)), device="cuda")
+    lhs = float((D * gd).sum())
+    rhs = float((ut * op._k_grad_adj(gd)).sum())
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), 1.0)
+    op.set_variant(1)
+    rhs1 = float((ut * op._k_grad_adj(gd)).sum())
+    op.set_variant(0)
+    assert abs(lhs - rhs1) <= 1e-11 * max(abs(lhs), 1.0)
