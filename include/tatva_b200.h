@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TATVA_B200_ABI_VERSION 8  /* bumped on every signature change; the Python loader refuses a mismatch */
+#define TATVA_B200_ABI_VERSION 9  /* bumped on every signature change; the Python loader refuses a mismatch */
 
 typedef struct tatva_plan tatva_plan_t; /* opaque: mesh views + scratch for one Operator */
 typedef void* tatva_stream_t;           /* a cudaStream_t */
@@ -221,10 +221,15 @@ int tatva_hvp_lifted_dot(tatva_plan_t* plan, int material, const double* params,
                          double* d_y_red, int zero_y, double* d_partials, double* d_scalars, int slot, int roll,
                          tatva_stream_t stream);
 
+/* y[0..n) = 0 by a kernel that releases its dependent grid at once; with zero_y = 2 on the sub-range launch issued right
+ * behind it on the same stream, that launch starts while y is still being cleared and waits only before its first add.  */
+int tatva_zero_release(double* d_y, int64_t n, tatva_stream_t stream);
 /* Element sub-range variants: only elements [elem_begin, elem_begin + elem_count) contribute, and the
  * output is zeroed first only if zero_out != 0.  They let the caller run the elements that touch ghost
  * nodes and the interior elements on different streams, so the halo exchange of tatva/mpi.py:372-409,
- * :479-516 overlaps the interior quadrature loop.                                                    */
+ * :479-516 overlaps the interior quadrature loop.  tatva_hvp_elems: zero_out = 2 says the output is being
+ * cleared by the tatva_zero_release issued just before on the same stream (nothing is zeroed here; the Hex8 x
+ * neo-Hookean kernel is launched behind it with programmatic stream serialization, other kernels in stream order). */
 int tatva_hvp_elems(tatva_plan_t* plan, int material, const double* params, int n_params,
                     const double* d_u, const double* d_v, double* d_y, int64_t elem_begin,
                     int64_t elem_count, int zero_out, tatva_stream_t stream);

@@ -15,7 +15,7 @@ TRI3, TET4, HEX8, QUAD4, TRI6, QUAD8, LINE2, LINE3 = 0, 1, 2, 3, 4, 5, 6, 7
 LINEAR_ELASTIC, NEO_HOOKEAN, NEO_HOOKEAN_PHASE_FIELD = 0, 1, 2
 USER_LAW_BASE = 1000
 PLAN_CACHE_WEIGHTS = 1
-ABI_VERSION = 8  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
+ABI_VERSION = 9  # == TATVA_B200_ABI_VERSION in include/tatva_b200.h
 VARIANT_DEFAULT, VARIANT_GENERIC, VARIANT_MODAL = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
@@ -42,6 +42,7 @@ SIGNATURES = {
     "tatva_halo_comm_unique_id": (C.c_int, [vp]),
     "tatva_halo_comm_create": (C.c_int, [C.POINTER(vp), vp, C.c_int, C.c_int]),
     "tatva_halo_comm_destroy": (C.c_int, [vp]),
+    "tatva_zero_release": (C.c_int, [vp, C.c_int64, vp]),
     "tatva_plan_cache_geometry": (C.c_int, [vp, C.c_int, vp]),
     "tatva_plan_set_node_schedule": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "tatva_plan_set_point_grid": (C.c_int, [vp, C.c_int, C.c_int, c_f64p, c_f64p, vp, vp]),

@@ -692,6 +692,7 @@ struct tatva_plan {
   int flags;
   int variant;
   int zero_output;  // scatter-add entry points zero their output first (1) or accumulate (0)
+  int pss;          // 1: the output is being cleared by the tatva_zero_release launched just before on the same stream — kernels that wait before their first add may be launched with programmatic stream serialization (sub-range calls, zero_y = 2)
   double* scratch;  // plan-owned: energy partials / row-sum partials
   int64_t scratch_len;
   double* weights;  // plan-owned (n_elems, nq) when TATVA_PLAN_CACHE_WEIGHTS
@@ -772,8 +773,8 @@ static __global__ void __launch_bounds__(256) k_zero_release(double* __restrict_
 
 // Clear y[0..n) (when `zero`) and launch `kernel` behind it; the kernel must execute griddepcontrol.wait before it touches y.
 template <class... KArgs, class... Args>
-inline int launch_behind_zero(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool zero, double* y,
-                              int64_t n, Args... args) {
+inline int launch_behind_zero(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int zero, double* y,
+                              int64_t n, Args... args) {  // zero: 0 plain launch, 1 clear y and launch behind it, 2 launch behind a tatva_zero_release the caller issued
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
@@ -782,7 +783,11 @@ inline int launch_behind_zero(void (*kernel)(KArgs...), int grid, int block, siz
   cudaLaunchAttribute attr[1];
   cfg.attrs = attr;
   cfg.numAttrs = 0;
-  if (zero && n > 0) {
+  if (zero == 2) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  } else if (zero && n > 0) {
     if (reinterpret_cast<uintptr_t>(y) & 15) {  // not 16-byte aligned (a view into a larger array): plain memset, plain launch
       TATVA_CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * n, st));
     } else {

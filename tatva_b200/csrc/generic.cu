@@ -1593,6 +1593,7 @@ int tatva_plan_create(tatva_plan_t** out, int element, int64_t n_nodes, int64_t 
   p->flags = flags;
   p->variant = TATVA_VARIANT_DEFAULT;
   p->zero_output = 1;
+  p->pss = 0;
   p->weights = nullptr;
   p->tile_ptr = nullptr;
   p->tile_nodes = nullptr;
@@ -2360,6 +2361,25 @@ static void sub_range_node_schedule(tatva_plan& sub, int64_t elem_begin) {
 }
 
 extern "C" {
+// y[0..n) = 0 by the kernel that releases its dependent grid at once (see launch_behind_zero): a caller that splits one
+// application into several launches (the partitioned operator: interior and boundary elements on two streams) clears the
+// output with this and passes zero_y = 2 to the FIRST sub-range launch it issues right behind it on the same stream.
+int tatva_zero_release(double* d_y, int64_t n, tatva_stream_t stream) {
+  if (!d_y || n < 0) return TATVA_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return TATVA_OK;
+  if (reinterpret_cast<uintptr_t>(d_y) & 15) {
+    TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * n, st));
+    return TATVA_OK;
+  }
+  int64_t blocks = (n / 2 + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  k_zero_release<<<(int)blocks, 256, 0, st>>>(d_y, n);
+  TATVA_LAUNCH_CHECK();
+  return TATVA_OK;
+}
+
 // Element sub-range variants (overlap of halo exchange with interior elements): elements
 // [elem_begin, elem_begin + elem_count) only; y is zeroed first iff zero_y != 0.
 int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_params, const double* d_u,
@@ -2367,7 +2387,7 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
                     tatva_stream_t stream) {
   if (!p || elem_begin < 0 || elem_count < 0 || elem_begin + elem_count > p->n_elems) return TATVA_E_INVALID;
   if (elem_count == 0) {
-    if (zero_y) {
+    if (zero_y == 1) {
       int dpn = material == TATVA_NEO_HOOKEAN_PHASE_FIELD ? 4 : p->dim;
       if (is_user_law(material)) user_law_info(material, &dpn);
       TATVA_CUDA_TRY(cudaMemsetAsync(d_y, 0, sizeof(double) * p->n_nodes * dpn, (cudaStream_t)stream));
@@ -2377,7 +2397,8 @@ int tatva_hvp_elems(tatva_plan_t* p, int material, const double* params, int n_p
   tatva_plan sub = *p;
   sub.conn = p->conn + elem_begin * p->npe;
   sub.n_elems = elem_count;
-  sub.zero_output = zero_y ? 1 : 0;
+  sub.zero_output = zero_y == 1 ? 1 : 0;
+  sub.pss = zero_y == 2 ? 1 : 0;
   sub.tile_ptr = nullptr;  // staging tiles describe the whole element list, not a sub-range
   sub_range_node_schedule(sub, elem_begin);
   if (sub.geo) sub.geo += 2 * elem_begin;  // the cache is element-fastest: a sub-range is an offset view (same stride)

@@ -2360,8 +2360,8 @@ static int launch_v3(const tatva_plan* p, double mu, double lmbda, const double*
     const int rc = opt_in_smem(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, smem, configured);
     if (rc != TATVA_OK) return rc;
   }
-  if (pdl)  // clear y with our own kernel and let the element kernel start behind it without waiting for it to finish
-    return launch_behind_zero(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, grid_for(p->n_elems), kBlock, smem, st, true, y, p->n_nodes * 3,
+  if (pdl)  // clear y with our own kernel (or rely on the caller's, p->pss) and let the element kernel start behind it without waiting for it to finish
+    return launch_behind_zero(k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS>, grid_for(p->n_elems), kBlock, smem, st, p->zero_output ? 1 : 2, y, p->n_nodes * 3,
                               p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y, nullptr, nullptr);
   k_hex8_nh_hvp_v3<MINB, STAGE, GROUPED, false, WIDE, UNR, CPF, NDS><<<grid_for(p->n_elems), kBlock, smem, st>>>(p->coords, p->conn, p->n_elems, mu * (1.0 / 512.0), lmbda * (1.0 / 512.0), u, v, y);
   return TATVA_OK;
@@ -2468,7 +2468,7 @@ int hex8_nh_hvp_modal(const tatva_plan* p, double mu, double lmbda, const double
                       cudaStream_t st) {
   // default (variant 0) with a zeroed output: the clearing of y overlaps the element kernel's gather and Gauss-point loop
   // (programmatic dependent launch); variant 26 is the same kernel behind a plain cudaMemsetAsync
-  if (p->zero_output && p->variant == 0 && !p->geo) {
+  if ((p->zero_output || p->pss) && p->variant == 0 && !p->geo) {
     const int rc = launch_v3<3, 2>(p, mu, lmbda, u, v, y, st, true);
     if (rc != TATVA_OK) return rc;
     TATVA_LAUNCH_CHECK();

@@ -264,11 +264,15 @@ class PartitionedOperator:
                 self._exchange(self.plan._rev, y_local, y_local, add=True)
             return y_local
         main, side = torch.cuda.current_stream(self.device), self._comm_stream
-        y_local.zero_()
+        # y is cleared by the releasing kernel of the C ABI and the interior launch goes out right behind it (zero_y = 2):
+        # the Hex8 kernel then runs its gather and Gauss-point loop while y is still being cleared (programmatic dependent
+        # launch), every other kernel simply follows in stream order
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tatva_zero_release(y_local.data_ptr(), y_local.numel(), main.cuda_stream), "tatva_zero_release")
         zeroed = torch.cuda.Event()
         zeroed.record(main)
         side.wait_stream(main)  # inputs are ready
-        self._elems(name, u_local, v_local, y_local, nb, E - nb, 0)  # interior, compute stream
+        self._elems(name, u_local, v_local, y_local, nb, E - nb, 2 if name == "tatva_hvp_elems" else 0)  # interior, compute stream
         with torch.cuda.stream(side):
             if peer:
                 side.wait_event(zeroed)  # the pull's barrier then orders every rank's zeroing before any push

@@ -139,3 +139,28 @@ def test_building_blocks_for_every_component_count(kind, n, nv):
     rhs1 = float((ut * op._k_grad_adj(gd)).sum())
     op.set_variant(0)
     assert abs(lhs - rhs1) <= 1e-11 * max(abs(lhs), 1.0)
+
+
+@pytest.mark.parametrize("kind,n", [("hex8", 9), ("tet4", 6)])
+def test_zero_release_then_sub_range_launches(kind, n):
+    """What the partitioned operator issues per application: tatva_zero_release clears y, the first sub-range launch goes
+    out right behind it with zero_y = 2 (the Hex8 kernel under programmatic stream serialization, any other in stream
+    order), the second accumulates; y held garbage before."""
+    from test_gpu_parity import _case, _make_op, _material
+    from tatva_b200 import _lib
+
+    c, el, u, v, (mname, omat) = _case(kind, n)
+    op = _make_op(kind, c, el)
+    mat = _material(mname, omat)
+    ut, vt = torch.as_tensor(u, device="cuda"), torch.as_tensor(v, device="cuda")
+    ref = op._raw_hvp(mat, ut, vt).clone()
+    prm, npar = _lib.params_array(mat.params())
+    E = el.shape[0]
+    cut = (E // 3) // 128 * 128 + 128
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        y = torch.full_like(ut, float("nan"))
+        _lib.check(op._L.tatva_zero_release(y.data_ptr(), y.numel(), st), "tatva_zero_release")
+        _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), cut, E - cut, 2, st), "tatva_hvp_elems")
+        _lib.check(op._L.tatva_hvp_elems(op._plan_fused, mat.material_id, prm, npar, ut.data_ptr(), vt.data_ptr(), y.data_ptr(), 0, cut, 0, st), "tatva_hvp_elems")
+        _assert_close(y, ref.cpu().numpy(), 1e-13)
