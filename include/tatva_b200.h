@@ -422,9 +422,13 @@ int tatva_host_csr_element_positions(const int32_t* conn, int64_t n_elems, int n
  * host and device from the same source; these two entry points run one element through them on the CPU so that the
  * kernels' formulas can be verified against the oracle where no GPU is available.  All pointers are HOST pointers.
  *   tatva_probe_element:        generic element body (k_fused / k_hessian_diag): X (npe, dim), u, v (npe, dpn);
- *                               mode 0 energy -> out[0]; 1 residual, 2 HVP, 3 Hessian diagonal -> out (npe, dpn)
+ *                               mode 0 energy -> out[0]; 1 residual, 2 HVP, 3 Hessian diagonal -> out (npe, dpn);
+ *                               4 = the rank-structured diagonal (k_hessian_diag_rank; laws with a RankLaw only)
  *   tatva_probe_hex8_nh_modal:  the pair kernels of the Hex8 x neo-Hookean path (HVP v3, residual v3, energy v3):
  *                               X, u, v (8, 3); mode 0 energy, 1 residual, 2 HVP -> out[0] or out (8, 3)
+ *                               mode 3: the HVP through the geometry-cache arithmetic (point_geometry + point_flux_geo);
+ *                               mode 4: Operator.grad of u as k_hex8_grad_modal forms it -> out (8 points, 3, 3);
+ *                               mode 5: integration weights as k_hex8_weights_modal -> out (8)
  *   tatva_probe_tet4_nh_ref:    the reference-space Tet4 x neo-Hookean kernels: X, u, v (4, 3); mode 1 residual,
  *                               2 HVP -> out (4, 3)                                                               */
 int tatva_probe_element(int element, int material, const double* params, int n_params, int mode,

@@ -922,7 +922,7 @@ struct RankLaw;
 template <int DIM>
 struct RankLaw<LinearElastic<DIM>> {
   template <int NPE>
-  TATVA_D static void eval(const LinearElastic<DIM>& m, double W, const double (&dN)[DIM][NPE], const double (&)[NPE][DIM],
+  TATVA_HD static void eval(const LinearElastic<DIM>& m, double W, const double (&dN)[DIM][NPE], const double (&)[NPE][DIM],
                            double (&g)[DIM][NPE], double (&w)[3]) {
 #pragma unroll
     for (int j = 0; j < DIM; ++j)
@@ -936,7 +936,7 @@ struct RankLaw<LinearElastic<DIM>> {
 template <>
 struct RankLaw<NeoHookean> {
   template <int NPE>
-  TATVA_D static void eval(const NeoHookean& m, double W, const double (&dN)[3][NPE], const double (&U)[NPE][3], double (&g)[3][NPE],
+  TATVA_HD static void eval(const NeoHookean& m, double W, const double (&dN)[3][NPE], const double (&U)[NPE][3], double (&g)[3][NPE],
                            double (&w)[3]) {
     double F[3][3], Fi[3][3];
 #pragma unroll
@@ -2299,6 +2299,20 @@ static int probe_element(const Mat& mat, int mode, const double* Xp, const doubl
       energy += W * mat.psi(s, cache);
       continue;
     }
+    if (mode == 4) {  // the rank-structured diagonal of k_hessian_diag_rank (laws with a RankLaw)
+      if constexpr (has_rank_law<Mat>::value && Mat::dpn == El::dim) {
+        double g[El::dim][El::npe], w[3];
+        RankLaw<Mat>::template eval<El::npe>(mat, W, dNdX, U, g, w);
+        for (int a = 0; a < El::npe; ++a) {
+          double nn = 0.0;
+          for (int j = 0; j < El::dim; ++j) nn = fma(dNdX[j][a], dNdX[j][a], nn);
+          for (int i = 0; i < El::dim; ++i) Y[a][i] += fma((w[1] + w[2]) * g[i][a], g[i][a], w[0] * nn);
+        }
+        continue;
+      } else {
+        return TATVA_E_UNSUPPORTED;
+      }
+    }
     if (mode == 3) {
       for (int b = 0; b < El::npe; ++b)
         for (int k = 0; k < dpn; ++k) {
@@ -2339,7 +2353,7 @@ static int probe_element(const Mat& mat, int mode, const double* Xp, const doubl
 
 extern "C" int tatva_probe_element(int element, int material, const double* params, int n_params, int mode, const double* X,
                                    const double* u, const double* v, double* out) {
-  if (!params || !X || !u || !out || mode < 0 || mode > 3 || (mode == 2 && !v)) return TATVA_E_INVALID;
+  if (!params || !X || !u || !out || mode < 0 || mode > 4 || (mode == 2 && !v)) return TATVA_E_INVALID;
   return for_element_law(element, material, params, n_params, [&](auto el, auto mat) -> int {
     return probe_element<decltype(el), decltype(mat)>(mat, mode, X, u, v, out);
   });

@@ -1323,7 +1323,7 @@ TATVA_D void warp_rows_load(const double* __restrict__ src, double* st, int S, i
 }
 
 // K = J^-1 (J[d][c] = dX_c / dxi_d, raw scaling) : K[j][d]
-TATVA_D void inverse_of(const double (&J)[3][3], double (&K)[3][3]) {
+TATVA_HD void inverse_of(const double (&J)[3][3], double (&K)[3][3]) {
   double det;
   adjugate(J, K, det);
   const double r = fast_rcp(det);
@@ -2722,7 +2722,7 @@ int tet4_nh_tiled(const tatva_plan* p, bool hvp, double mu, double lmbda, const 
 // ---------------------------------------------------------------------------------------------
 namespace {
 void probe_hex8_pairs(int mode, const double* X, const double* u, const double* v, double mu, double lmbda, double* out) {
-  double hX[3][7], hx[3][7], hv[3][7];
+  double hX[3][7], hx[3][7], hv[3][7], hu[3][7];
   for (int c = 0; c < 3; ++c) {
     double fX[8], fu[8], fv[8];
     for (int n = 0; n < 8; ++n) {
@@ -2733,7 +2733,10 @@ void probe_hex8_pairs(int mode, const double* X, const double* u, const double* 
     to_modal_raw(fX, hX[c]);
     to_modal_raw(fu, hx[c]);
     to_modal_raw(fv, hv[c]);
-    for (int k = 0; k < 7; ++k) hx[c][k] += hX[c][k];
+    for (int k = 0; k < 7; ++k) {
+      hu[c][k] = hx[c][k];
+      hx[c][k] += hX[c][k];
+    }
   }
   double R[3][7] = {};
   double energy = 0.0;
@@ -2758,7 +2761,36 @@ void probe_hex8_pairs(int mode, const double* X, const double* u, const double* 
       continue;
     }
     double Qm[3][3], Qp[3][3];
-    if (mode == 2) {
+    if (mode == 4 || mode == 5) {  // Operator.grad of the field u / integration weights, as k_hex8_grad_modal / k_hex8_weights_modal
+      const int qm = (pq == 0) ? 0 : (pq == 1) ? 3 : (pq == 2) ? 4 : 7, qp = (pq == 0) ? 1 : (pq == 1) ? 2 : (pq == 2) ? 5 : 6;
+      if (mode == 5) {
+        double Kc[3][3], dm, dp;
+        adjugate(Jm, Kc, dm);
+        adjugate(Jp, Kc, dp);
+        out[qm] = dm * (1.0 / 512.0);
+        out[qp] = dp * (1.0 / 512.0);
+        continue;
+      }
+      double Km[3][3], Kp[3][3];
+      inverse_of(Jm, Km);
+      inverse_of(Jp, Kp);
+      for (int c = 0; c < 3; ++c) {
+        double gm[3], gp[3];
+        ref_grad8_pair(hu[c], sy, sz, gm, gp);
+        for (int j = 0; j < 3; ++j) {
+          out[(qm * 3 + c) * 3 + j] = fma(Km[j][2], gm[2], fma(Km[j][1], gm[1], Km[j][0] * gm[0]));
+          out[(qp * 3 + c) * 3 + j] = fma(Kp[j][2], gp[2], fma(Kp[j][1], gp[1], Kp[j][0] * gp[0]));
+        }
+      }
+      continue;
+    }
+    if (mode == 3) {  // the HVP through the geometry cache (point_geometry at plan time, point_flux_geo in the kernel)
+      double gm8[8], gp8[8];
+      point_geometry(Jm, gm8);
+      point_geometry(Jp, gp8);
+      point_flux_geo(gm8, Frm, Gvm, mu_s, lm_s, Qm);
+      point_flux_geo(gp8, Frp, Gvp, mu_s, lm_s, Qp);
+    } else if (mode == 2) {
       point_flux(Jm, Frm, Gvm, mu_s, lm_s, Qm);
       point_flux(Jp, Frp, Gvp, mu_s, lm_s, Qp);
     } else {
@@ -2771,6 +2803,7 @@ void probe_hex8_pairs(int mode, const double* X, const double* u, const double* 
     out[0] = energy * (1.0 / 512.0);
     return;
   }
+  if (mode == 4 || mode == 5) return;
   for (int i = 0; i < 3; ++i) {
     double f[8];
     from_modal_raw(R[i], f);
@@ -2808,7 +2841,7 @@ extern "C" int tatva_probe_tet4_nh_ref(int mode, const double* X, const double* 
 
 extern "C" int tatva_probe_hex8_nh_modal(int mode, const double* X, const double* u, const double* v, double mu, double lmbda,
                                          double* out) {
-  if (!X || !u || !out || mode < 0 || mode > 2 || (mode == 2 && !v)) return TATVA_E_INVALID;
+  if (!X || !u || !out || mode < 0 || mode > 5 || ((mode == 2 || mode == 3) && !v)) return TATVA_E_INVALID;
   tatva::probe_hex8_pairs(mode, X, u, v, mu, lmbda, out);
   return TATVA_OK;
 }

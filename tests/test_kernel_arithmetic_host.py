@@ -69,6 +69,8 @@ def test_generic_element_body_matches_the_oracle(kind, law):
     ip, ix = orc.pattern_from_mesh(el, len(c), dim)
     diag = sps.csr_matrix((orc.assemble_csr_data(kind, omat, c, el, u, ip, ix), ix, ip)).diagonal().reshape(-1, dim)
     np.testing.assert_allclose(_assemble(kind, mid, prm, 3, c, el, u, None, dim), diag, rtol=1e-11)
+    # r02: the rank-structured diagonal of k_hessian_diag_rank (both laws here have a RankLaw)
+    np.testing.assert_allclose(_assemble(kind, mid, prm, 4, c, el, u, None, dim), diag, rtol=1e-11)
 
 
 @pytest.mark.parametrize("kind", ["tet4", "hex8"])
@@ -111,6 +113,22 @@ def test_hex8_pair_kernels_arithmetic_matches_the_oracle():
     r_ref, h_ref = orc.residual("hex8", omat, c, el, u), orc.hvp("hex8", omat, c, el, u, v)
     np.testing.assert_allclose(res, r_ref, rtol=1e-10, atol=1e-13 * np.abs(r_ref).max())
     np.testing.assert_allclose(hv, h_ref, rtol=1e-10, atol=1e-13 * np.abs(h_ref).max())
+    # r02: the HVP through the geometry-cache arithmetic, Operator.grad and the weights in modal form (k_hex8_nh_hvp_geo,
+    # k_hex8_grad_modal, k_hex8_weights_modal)
+    hv3, g, w = np.zeros_like(c), np.zeros((len(el), 8, 3, 3)), np.zeros((len(el), 8))
+    gbuf, wbuf = np.zeros(72), np.zeros(8)
+    for k, e in enumerate(el):
+        X, ue, ve = (np.ascontiguousarray(a[e]) for a in (c, u, v))
+        assert L.tatva_probe_hex8_nh_modal(3, f64(X), f64(ue), f64(ve), 500.0, 1000.0, f64(buf)) == 0
+        np.add.at(hv3, e, buf.reshape(8, 3))
+        assert L.tatva_probe_hex8_nh_modal(4, f64(X), f64(ue), None, 500.0, 1000.0, f64(gbuf)) == 0
+        g[k] = gbuf.reshape(8, 3, 3)
+        assert L.tatva_probe_hex8_nh_modal(5, f64(X), f64(ue), None, 500.0, 1000.0, f64(wbuf)) == 0
+        w[k] = wbuf
+    np.testing.assert_allclose(hv3, h_ref, rtol=1e-10, atol=1e-13 * np.abs(h_ref).max())
+    g_ref = orc.op_grad("hex8", c, el, u)
+    np.testing.assert_allclose(g, g_ref, rtol=1e-11, atol=1e-13 * np.abs(g_ref).max())
+    np.testing.assert_allclose(w, orc.op_integration_weights("hex8", c, el), rtol=1e-13)
 
 
 def test_tet4_reference_space_kernels_arithmetic_matches_the_oracle():
