@@ -165,6 +165,16 @@ def check(code: int, what: str = "") -> None:
         raise TatvaError(f"{what or 'tatva_b200 call'} failed: {msg} (code {code})")
 
 
+_PARAMS = {}
+
+
 def params_array(values) -> tuple[C.Array, int]:
-    arr = (C.c_double * len(values))(*[float(v) for v in values])
-    return arr, len(values)
+    """ctypes view of a law's parameters; cached per value tuple (the hot calls pass it on every launch, and for the
+    launch-sized configurations building it was a visible part of the call)."""
+    key = tuple(float(v) for v in values)
+    hit = _PARAMS.get(key)
+    if hit is None:
+        if len(_PARAMS) > 4096:
+            _PARAMS.clear()
+        hit = _PARAMS[key] = ((C.c_double * len(key))(*key), len(key))
+    return hit

@@ -48,6 +48,7 @@ class Operator:
         if not torch.cuda.is_available():
             raise _lib.TatvaError("tatva_b200.Operator needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.coords = torch.as_tensor(_to_np_or_tensor(mesh.coords), dtype=torch.float64, device=self.device).contiguous()
         self.elements = torch.as_tensor(_to_np_or_tensor(mesh.elements), device=self.device).to(torch.int32).contiguous()
         self.n_nodes, self.dim = self.coords.shape
@@ -237,6 +238,9 @@ class Operator:
         plan = self._plan_fused if name in _FUSED_CALLS else self._plan
         if name in _HVP_CALLS and args:
             self._ensure_geometry(args[0])
+        if torch.cuda.current_device() == self._dev_index:  # the usual case (one process per GPU): no device switch needed
+            _lib.check(getattr(self._L, name)(plan, *args, _stream()), name)
+            return
         with torch.cuda.device(self.device):
             _lib.check(getattr(self._L, name)(plan, *args, _stream()), name)
 
