@@ -388,7 +388,7 @@ def main():
                 if local_elems == 128**3:
                     traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
                     traffic_src = f"profiles/{name} (ncu --set full of the same kernel and size; not re-measured in this run)"
-                    ncu_pipe = {k: tr[k] for k in ("fp64_pipe_active_pct_at_2_cycles_per_instruction", "fp64_instructions_per_element_sass", "issue_active_pct", "registers_per_thread") if k in tr} or None
+                    ncu_pipe = {k: tr[k] for k in ("fp64_pipe_active_pct_at_2_cycles_per_instruction", "fp64_instructions_per_element_sass", "instructions_per_thread", "issue_active_pct", "registers_per_thread", "kernel_us_under_ncu") if k in tr} or None
                 break
             except (OSError, KeyError, ValueError):
                 continue

@@ -23,5 +23,14 @@ if len(sys.argv) > 3:
     def to_bytes(k):
         u, v = get(k)
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-    json.dump({"kernel": get("Kernel Name")[1], "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"), "traffic": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"), "source": rep}, open(sys.argv[3], "w"))
+    num = lambda k: float(get(k)[1]) if get(k)[1] not in ("n/a", "") else None  # noqa: E731
+    grid, block = num("launch__grid_size"), num("launch__block_size")
+    json.dump({"kernel": get("Kernel Name")[1], "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"), "traffic": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+               # pipe occupancy of the same capture (bench.py copies these into roofline.ncu_same_kernel)
+               "fp64_pipe_active_pct_at_2_cycles_per_instruction": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+               "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "registers_per_thread": num("launch__registers_per_thread"),
+               "instructions_per_thread": num("smsp__inst_executed.sum") / (grid * block / 32) if grid and block else None,  # element-per-thread kernels: per element
+               "kernel_us_under_ncu": num("gpu__time_duration.sum"),
+               "source": rep}, open(sys.argv[3], "w"))
 print(open(out_md).read())
