@@ -1,5 +1,6 @@
 """Host-side (C++) pattern, colouring and CSR position map: bit-exact against reference fixtures."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -220,3 +221,33 @@ def test_csr_tile_schedule_lists_every_upper_contribution_once():
                 else:
                     assert base_t[d] == ip[rowt] + pos[e, b, a] and rl_t[d] == ip[rowt + 1] - ip[rowt]
     assert np.array_equal(seen, upper.astype(int))
+
+
+def test_halo_exchange_abi_rejects_bad_arguments_without_a_gpu():
+    """tatva_halo_exchange / the communicator helpers (tatva/mpi.py:400-407, :505-513 as one C call over an ncclComm_t):
+    argument checks that need neither a GPU nor a communicator; NCCL itself is opened lazily with dlopen."""
+    import ctypes as C
+
+    L = _lib.lib()
+    ver = C.c_int(0)
+    rc = L.tatva_nccl_version(C.byref(ver))
+    assert rc in (0, _lib_unsupported()) and (rc != 0 or ver.value >= 20700)
+    assert L.tatva_nccl_version(None) != 0
+    cnt = (C.c_int64 * 2)(0, 0)
+    assert L.tatva_halo_exchange(None, None, None, cnt, None, None, cnt, None, None, 0, None) != 0  # no communicator
+    assert L.tatva_halo_comm_unique_id(None) != 0
+    h = C.c_void_p()
+    buf = (C.c_char * 128)()
+    assert L.tatva_halo_comm_create(C.byref(h), buf, 0, 0) != 0  # n_ranks must be positive
+    assert L.tatva_halo_comm_create(C.byref(h), buf, 2, 5) != 0  # rank out of range
+    assert L.tatva_halo_comm_destroy(None) == 0
+    assert L.tatva_zero_release(None, 8, None) != 0
+    assert L.tatva_plan_cache_geometry(None, 1, None) != 0
+    assert L.tatva_plan_set_node_schedule(None, None, None, None, None, None, None) != 0
+
+
+def _lib_unsupported():
+    import re
+
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "tatva_b200.h")).read()
+    return int(re.search(r"TATVA_E_UNSUPPORTED\s*=\s*(-?\d+)", src).group(1))
