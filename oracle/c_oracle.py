@@ -25,6 +25,8 @@ def _load():
         _lib.oracle_num_threads.restype = C.c_int
         _lib.oracle_fused_pf.restype = C.c_int
         _lib.oracle_fused_pf.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 5
+        _lib.oracle_blocks.restype = C.c_int
+        _lib.oracle_blocks.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 4
         _lib.oracle_set_num_threads.restype = None
         _lib.oracle_set_num_threads.argtypes = [C.c_int]
     return _lib
@@ -93,3 +95,39 @@ def residual(kind, params, coords, conn, u, material="neo_hookean"):
 
 def hvp(kind, params, coords, conn, u, v, material="neo_hookean"):
     return _run(kind, material, 2, params, coords, conn, u, v)
+
+
+def _blocks(kind, what, coords, conn, arr, nv, out_shape):
+    L = _load()
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    a = np.ascontiguousarray(arr, dtype=np.float64) if arr is not None else None
+    out = np.empty(out_shape, dtype=np.float64)
+    rc = L.oracle_blocks(_KIND[kind], what, nv, coords.shape[0], conn.shape[0], coords.ctypes.data, conn.ctypes.data, a.ctypes.data if a is not None else None, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("oracle_blocks: unsupported arguments")
+    return out
+
+
+_NQ = {"tri3": 1, "tet4": 1, "hex8": 8}
+
+
+def op_grad(kind, coords, conn, u):
+    """Operator.grad at the config sizes: (E, Q, nv, dim) (tatva/operator.py:379-397)."""
+    u = np.asarray(u).reshape(len(coords), -1)
+    return _blocks(kind, 0, coords, conn, u, u.shape[1], (len(conn), _NQ[kind], u.shape[1], np.shape(coords)[1]))
+
+
+def op_grad_adjoint(kind, coords, conn, g):
+    """Transpose of op_grad: (E, Q, nv, dim) -> (N, nv)."""
+    g = np.asarray(g)
+    return _blocks(kind, 1, coords, conn, g, g.shape[2], (len(coords), g.shape[2]))
+
+
+def op_integration_weights(kind, coords, conn):
+    return _blocks(kind, 2, coords, conn, None, 1, (len(conn), _NQ[kind]))
+
+
+def op_gather(kind, coords, conn, u):
+    u = np.asarray(u).reshape(len(coords), -1)
+    return _blocks(kind, 3, coords, conn, u, u.shape[1], (len(conn), np.shape(conn)[1], u.shape[1]))

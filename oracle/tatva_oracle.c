@@ -216,6 +216,55 @@ int oracle_fused(int kind, int material, int mode, double mu, double lm, int64_t
   return 0;
 }
 
+/* ---- Operator building blocks at the config sizes (test infrastructure for the full-size GPU parity tests) ------------
+ * what 0: out (E, Q, nv, dim) = Operator.grad(u)            (tatva/operator.py:379-397 -> element/base.py:99-115)
+ * what 1: out (N, nv)        += adjoint of grad applied to in (E, Q, nv, dim)   (the transposed gather / gradient)
+ * what 2: out (E, Q)          = Operator.get_integration_weights()              (tatva/operator.py:172-192)
+ * what 3: out (E, npe, nv)    = in[mesh.elements]                                (tatva/operator.py:221)
+ * `in` is the nodal field (N, nv) for what 0 / 3 and the quadrature-shaped array for what 1.  returns 0 on success.      */
+int oracle_blocks(int kind, int what, int nv, int64_t n_nodes, int64_t n_elems, const double* coords, const int32_t* conn,
+                  const double* in, double* out) {
+  int dim, npe, nq;
+  elem_info(kind, &dim, &npe, &nq);
+  if (what < 0 || what > 3 || nv < 1 || nv > 8) return -1;
+  const double wq = quad_weight(kind);
+  if (what == 1) memset(out, 0, sizeof(double) * n_nodes * nv);
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < n_elems; ++e) {
+    double X[24], dNdX[24];
+    const int32_t* nd = conn + e * npe;
+    if (what == 3) {
+      for (int n = 0; n < npe; ++n)
+        for (int c = 0; c < nv; ++c) out[(e * npe + n) * nv + c] = in[(int64_t)nd[n] * nv + c];
+      continue;
+    }
+    for (int n = 0; n < npe; ++n)
+      for (int c = 0; c < dim; ++c) X[n * dim + c] = coords[(int64_t)nd[n] * dim + c];
+    for (int q = 0; q < nq; ++q) {
+      const double det = geometry(kind, dim, npe, q, X, dNdX);
+      if (what == 2) {
+        out[e * nq + q] = det * wq;
+      } else if (what == 0) {
+        for (int c = 0; c < nv; ++c)
+          for (int j = 0; j < dim; ++j) {
+            double t = 0;
+            for (int n = 0; n < npe; ++n) t += dNdX[j * npe + n] * in[(int64_t)nd[n] * nv + c];
+            out[((e * nq + q) * nv + c) * dim + j] = t;
+          }
+      } else {
+        for (int c = 0; c < nv; ++c)
+          for (int n = 0; n < npe; ++n) {
+            double t = 0;
+            for (int j = 0; j < dim; ++j) t += in[((e * nq + q) * nv + c) * dim + j] * dNdX[j * npe + n];
+#pragma omp atomic
+            out[(int64_t)nd[n] * nv + c] += t;
+          }
+      }
+    }
+  }
+  return 0;
+}
+
 /* ---- Compound (u, phi) two-field law of config 5 (builder-defined AT2 density; no counterpart in the reference, see
  * oracle/tatva_oracle.py NeoHookeanPhaseField).  Nodal state s (N,4) = [ux,uy,uz,phi] (compound/__init__.py:334-389);
  * the fields enter through Operator.grad (u, phi) and Operator.eval (phi): operator.py:358-397, element/base.py:95-115. */

@@ -165,3 +165,31 @@ def test_output_views_at_an_8_byte_offset_take_the_plain_memset(kind, n):
     y2 = torch.full_like(ut, float("nan"))
     op._raw_hvp(mat, ut, vt, out=y2)
     _assert_close(y2, ref.cpu().numpy(), 1e-14)
+
+
+def test_config3_building_blocks_at_128_vs_c_oracle():
+    """Operator.grad / its adjoint / integration weights / gather on Hex8 128^3 (the modal kernels and k_gather4 at the
+    BASELINE size) against the C oracle's generic formulas (J = dN/dxi X, dN/dX = inv(J) dN/dxi, element/base.py:90-115)."""
+    c, el, u, v, _ = _case("hex8", 128)
+    op = _make_op("hex8", c, el)
+    ut = torch.as_tensor(u, device="cuda")
+    g = op._k_grad(ut)
+    _assert_close(g, c_oracle.op_grad("hex8", c, el, u), RTOL)
+    _assert_close(op.get_integration_weights(), c_oracle.op_integration_weights("hex8", c, el), RTOL)
+    gd = np.random.default_rng(5).normal(size=tuple(g.shape))
+    del g
+    _assert_close(op._k_grad_adj(torch.as_tensor(gd, device="cuda")), c_oracle.op_grad_adjoint("hex8", c, el, gd), RTOL)
+    del gd
+    assert np.array_equal(op._k_gather(ut).cpu().numpy(), c_oracle.op_gather("hex8", c, el, u))
+
+
+def test_config2_building_blocks_vs_c_oracle():
+    """The same for Tet4 n = 55 (generic staged kernels, batched staged loads in the adjoint)."""
+    c, el, u, v, _ = _case("tet4", 55)
+    op = _make_op("tet4", c, el)
+    ut = torch.as_tensor(u, device="cuda")
+    g = op._k_grad(ut)
+    _assert_close(g, c_oracle.op_grad("tet4", c, el, u), RTOL)
+    gd = np.random.default_rng(5).normal(size=tuple(g.shape))
+    _assert_close(op._k_grad_adj(torch.as_tensor(gd, device="cuda")), c_oracle.op_grad_adjoint("tet4", c, el, gd), RTOL)
+    _assert_close(op.get_integration_weights(), c_oracle.op_integration_weights("tet4", c, el), RTOL)

@@ -45,3 +45,28 @@ def test_c_oracle_phase_field_matches_numpy_oracle(kind, n):
     assert abs(c_oracle.energy_pf(kind, prm, c, el, s) - e_ref) <= 1e-13 * abs(e_ref)
     assert _rel(c_oracle.residual_pf(kind, prm, c, el, s), orc.residual_pf(kind, mat, c, el, s)) < 1e-13
     assert _rel(c_oracle.hvp_pf(kind, prm, c, el, s, t), orc.hvp_pf(kind, mat, c, el, s, t)) < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["tri3", "tet4", "hex8"])
+def test_c_building_blocks_match_the_numpy_oracle_and_the_reference_fixtures(kind, golden):
+    """oracle_blocks (grad, its adjoint, integration weights, gather: the checker of the full-size GPU building-block
+    tests) against the NumPy oracle, and against the reference's own Operator outputs (op_* fixtures)."""
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(4)
+    c, el = {"tri3": lambda: orc.mesh_unit_square_tri(6, 5), "tet4": lambda: orc.mesh_box_tet((1, 1, 1), (3, 2, 3)), "hex8": lambda: orc.mesh_box_hex(3)}[kind]()
+    c = c + 0.03 * rng.uniform(-1, 1, c.shape)
+    for nv in (1, 3):
+        u = rng.normal(size=(len(c), nv))
+        g = c_oracle.op_grad(kind, c, el, u)
+        np.testing.assert_allclose(g, orc.op_grad(kind, c, el, u), rtol=1e-12, atol=1e-13)
+        gd = rng.normal(size=g.shape)
+        ref = np.zeros_like(u)
+        # adjoint by the defining identity, column by column of the NumPy gradient operator
+        lhs = (g * gd).sum()
+        np.testing.assert_allclose((u * c_oracle.op_grad_adjoint(kind, c, el, gd)).sum(), lhs, rtol=1e-12)
+        assert np.array_equal(c_oracle.op_gather(kind, c, el, u), u[el])
+    np.testing.assert_allclose(c_oracle.op_integration_weights(kind, c, el), orc.op_integration_weights(kind, c, el), rtol=1e-13)
+    gk = lambda k: golden[f"op_{kind}_{k}"]  # noqa: E731
+    np.testing.assert_allclose(c_oracle.op_grad(kind, gk("coords"), gk("conn"), gk("u")), gk("grad_u"), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(c_oracle.op_integration_weights(kind, gk("coords"), gk("conn")), gk("weights"), rtol=1e-13)
