@@ -89,3 +89,40 @@ def test_invalid_arguments():
     n = C.c_int64()
     cp = np.zeros(2, np.int32)
     assert L.tatva_host_node_schedule(conn.ctypes.data_as(_lib.c_i32p), 4, 9, 0, None, None, cp.ctypes.data_as(_lib.c_i32p), C.byref(n), C.byref(n), None, None, None) != 0
+
+
+def test_random_meshes_property():
+    """Property test (hypothesis): for any connectivity — repeated nodes inside an element included — the schedule lists
+    every (element, local node) reference exactly once under its node, the warp lists are consistent, and a cap bounds
+    every table row count."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 400), st.integers(1, 8), st.integers(1, 60), st.integers(0, 5), st.integers(0, 2**31 - 1))
+    def run(E, npe, n_nodes, cap, seed):
+        rng = np.random.default_rng(seed)
+        conn = rng.integers(0, n_nodes, size=(E, npe)).astype(np.int32)
+        wn, wl, cp, tn, ep, ell = _schedule(conn, cap)
+        for w in range((E + 31) // 32):
+            lst = wn[32 * w : 32 * w + 32]
+            sl = slice(32 * w, min(E, 32 * w + 32))
+            loc, nodes = wl[sl].astype(int), conn[sl]
+            picked = loc != 255
+            assert np.array_equal(lst[loc[picked]], nodes[picked])
+        seen = np.zeros((E, npe), dtype=int)
+        for t in range(len(cp) - 1):
+            for ch in range(cp[t], cp[t + 1]):
+                rows = (ep[ch + 1] - ep[ch]) // 32
+                assert cap == 0 or rows <= cap
+                tab = ell[ep[ch] : ep[ch + 1]].reshape(rows, 32).astype(int)
+                for lane in range(32):
+                    for s_ in tab[:, lane]:
+                        if s_ == 0xFFFF:
+                            continue
+                        e, a = 128 * t + (s_ >> 3), s_ & 7
+                        assert conn[e, a] == tn[32 * ch + lane]
+                        seen[e, a] += 1
+        assert np.all(seen == 1)
+
+    run()
